@@ -1,0 +1,404 @@
+// xo_celerite.cu -- celerite2 SHOTerm GP log-likelihood as a parallel scan (BASELINE
+// config 4).  celerite2 (>=0.3.1, /root/reference/setup.py:36) has NO call site in the
+// reference; the contract here is celerite2's documented SHOTerm/GaussianProcess
+// log_likelihood, pinned against a dense Cholesky oracle.
+//
+// The celerite recurrence is a Riccati (linear-fractional) recursion, so it is run in
+// its equivalent 2-state Kalman-filter form, which has an associative combine
+// (Sarkka & Garcia-Fernandez 2021).  Three phases, every thread owns a run of kRun
+// consecutive cadences:
+//   1. gp_aggregate: walk the run once from a *known* start (P = 0), tracking the affine
+//      dependence of the filtered mean on the unknown start state and the information
+//      (eta, J) the run's data carry about it -> one scan element per run, no 2x2 inverses;
+//      then an in-CTA inclusive scan of the run elements (shuffle scan + 4 warp totals).
+//   2. gp_cta_scan: one CTA scans the per-CTA totals and applies each exclusive prefix to
+//      the stationary prior -> the state (m, Z = Sigma_inf - P) entering every CTA.
+//   3. gp_loglike: each thread applies its in-CTA prefix to that state and re-walks its run
+//      with plain Kalman steps, accumulating -1/2 (v^2/D + log D); fixed-order reduction.
+// SHO in (a, c, h) form so celerite2's eps-regularised coefficients are matched exactly:
+//   underdamped k(tau) = a e^{-c tau}(cos h tau + (c/h) sin h tau), overdamped with cosh/sinh.
+#include <cuda_runtime.h>
+
+#include "xo_common.cuh"
+
+namespace {
+
+constexpr int kRun = 16;
+constexpr int kThreadsGp = 128;
+constexpr int kWarpsGp = kThreadsGp / 32;
+constexpr unsigned kFullGp = 0xffffffffu;
+constexpr int kAggDoubles = 14;
+
+struct Sho {
+  double a, c, h, w2;  // variance, damping, (pseudo)frequency, c^2 +- h^2
+  bool under;
+};
+
+__device__ __forceinline__ Sho make_sho(double S0, double w0, double Q, double eps) {
+  Sho k;
+  k.a = S0 * w0 * Q;
+  k.c = 0.5 * w0 / Q;
+  k.under = Q >= 0.5;
+  double f = sqrt(fmax(k.under ? 4.0 * Q * Q - 1.0 : 1.0 - 4.0 * Q * Q, eps));
+  k.h = k.c * f;
+  k.w2 = k.under ? k.c * k.c + k.h * k.h : k.c * k.c - k.h * k.h;
+  return k;
+}
+
+// transition matrix over dt
+__device__ __forceinline__ void sho_phi(const Sho &k, double dt, double &f00, double &f01, double &f10, double &f11) {
+  double Cf, Sf;
+  if (k.under) {
+    double sn, cs;
+    sincos(k.h * dt, &sn, &cs);
+    double ex = exp(-k.c * dt);
+    Cf = ex * cs;
+    Sf = ex * sn / k.h;
+  } else {
+    double ep = exp(-(k.c - k.h) * dt), en = exp(-(k.c + k.h) * dt);
+    Cf = 0.5 * (ep + en);
+    Sf = 0.5 * (ep - en) / k.h;
+  }
+  f00 = fma(k.c, Sf, Cf);
+  f01 = Sf;
+  f10 = -k.w2 * Sf;
+  f11 = fma(-k.c, Sf, Cf);
+}
+
+struct Agg {
+  double A00, A01, A10, A11, b0, b1, C00, C01, C11, e0, e1, J00, J01, J11;
+};
+
+__device__ __forceinline__ Agg agg_identity() { return Agg{1, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; }
+
+// combine(earlier i, later j)
+__device__ __forceinline__ Agg agg_combine(const Agg &i, const Agg &j) {
+  // M = I + C_i J_j ; X = M^-1
+  double m00 = 1.0 + i.C00 * j.J00 + i.C01 * j.J01, m01 = i.C00 * j.J01 + i.C01 * j.J11;
+  double m10 = i.C01 * j.J00 + i.C11 * j.J01, m11 = 1.0 + i.C01 * j.J01 + i.C11 * j.J11;
+  double rdet = 1.0 / (m00 * m11 - m01 * m10);
+  double x00 = m11 * rdet, x01 = -m01 * rdet, x10 = -m10 * rdet, x11 = m00 * rdet;
+  // G = A_j X
+  double g00 = j.A00 * x00 + j.A01 * x10, g01 = j.A00 * x01 + j.A01 * x11;
+  double g10 = j.A10 * x00 + j.A11 * x10, g11 = j.A10 * x01 + j.A11 * x11;
+  Agg o;
+  o.A00 = g00 * i.A00 + g01 * i.A10;
+  o.A01 = g00 * i.A01 + g01 * i.A11;
+  o.A10 = g10 * i.A00 + g11 * i.A10;
+  o.A11 = g10 * i.A01 + g11 * i.A11;
+  double u0 = i.b0 + i.C00 * j.e0 + i.C01 * j.e1, u1 = i.b1 + i.C01 * j.e0 + i.C11 * j.e1;
+  o.b0 = g00 * u0 + g01 * u1 + j.b0;
+  o.b1 = g10 * u0 + g11 * u1 + j.b1;
+  // T = G C_i ; C = T A_j^T + C_j
+  double t00 = g00 * i.C00 + g01 * i.C01, t01 = g00 * i.C01 + g01 * i.C11;
+  double t10 = g10 * i.C00 + g11 * i.C01, t11 = g10 * i.C01 + g11 * i.C11;
+  o.C00 = t00 * j.A00 + t01 * j.A01 + j.C00;
+  o.C01 = 0.5 * ((t00 * j.A10 + t01 * j.A11) + (t10 * j.A00 + t11 * j.A01)) + j.C01;
+  o.C11 = t10 * j.A10 + t11 * j.A11 + j.C11;
+  // H = A_i^T X^T
+  double h00 = i.A00 * x00 + i.A10 * x01, h01 = i.A00 * x10 + i.A10 * x11;
+  double h10 = i.A01 * x00 + i.A11 * x01, h11 = i.A01 * x10 + i.A11 * x11;
+  double v0 = j.e0 - (j.J00 * i.b0 + j.J01 * i.b1), v1 = j.e1 - (j.J01 * i.b0 + j.J11 * i.b1);
+  o.e0 = h00 * v0 + h01 * v1 + i.e0;
+  o.e1 = h10 * v0 + h11 * v1 + i.e1;
+  // S = H J_j ; J = S A_i + J_i
+  double s00 = h00 * j.J00 + h01 * j.J01, s01 = h00 * j.J01 + h01 * j.J11;
+  double s10 = h10 * j.J00 + h11 * j.J01, s11 = h10 * j.J01 + h11 * j.J11;
+  o.J00 = s00 * i.A00 + s01 * i.A10 + i.J00;
+  o.J01 = 0.5 * ((s00 * i.A01 + s01 * i.A11) + (s10 * i.A00 + s11 * i.A10)) + i.J01;
+  o.J11 = s10 * i.A01 + s11 * i.A11 + i.J11;
+  return o;
+}
+
+// apply an aggregate to a Gaussian state (m, P)
+__device__ __forceinline__ void agg_apply(const Agg &g, double &m0, double &m1, double &P00, double &P01, double &P11) {
+  double q00 = 1.0 + P00 * g.J00 + P01 * g.J01, q01 = P00 * g.J01 + P01 * g.J11;
+  double q10 = P01 * g.J00 + P11 * g.J01, q11 = 1.0 + P01 * g.J01 + P11 * g.J11;
+  double rdet = 1.0 / (q00 * q11 - q01 * q10);
+  double x00 = q11 * rdet, x01 = -q01 * rdet, x10 = -q10 * rdet, x11 = q00 * rdet;
+  double g00 = g.A00 * x00 + g.A01 * x10, g01 = g.A00 * x01 + g.A01 * x11;
+  double g10 = g.A10 * x00 + g.A11 * x10, g11 = g.A10 * x01 + g.A11 * x11;
+  double u0 = m0 + P00 * g.e0 + P01 * g.e1, u1 = m1 + P01 * g.e0 + P11 * g.e1;
+  double n0 = g00 * u0 + g01 * u1 + g.b0, n1 = g10 * u0 + g11 * u1 + g.b1;
+  double t00 = g00 * P00 + g01 * P01, t01 = g00 * P01 + g01 * P11;
+  double t10 = g10 * P00 + g11 * P01, t11 = g10 * P01 + g11 * P11;
+  double c00 = t00 * g.A00 + t01 * g.A01 + g.C00;
+  double c01 = 0.5 * ((t00 * g.A10 + t01 * g.A11) + (t10 * g.A00 + t11 * g.A01)) + g.C01;
+  double c11 = t10 * g.A10 + t11 * g.A11 + g.C11;
+  m0 = n0;
+  m1 = n1;
+  P00 = c00;
+  P01 = c01;
+  P11 = c11;
+}
+
+__device__ __forceinline__ Agg agg_shfl_up(const Agg &a, int delta) {
+  Agg o;
+  const double *src = &a.A00;
+  double *dst = &o.A00;
+#pragma unroll
+  for (int k = 0; k < kAggDoubles; ++k) dst[k] = __shfl_up_sync(kFullGp, src[k], delta);
+  return o;
+}
+
+__device__ __forceinline__ void agg_store(double *p, const Agg &a) {
+  const double *src = &a.A00;
+#pragma unroll
+  for (int k = 0; k < kAggDoubles; ++k) p[k] = src[k];
+}
+__device__ __forceinline__ Agg agg_load(const double *p) {
+  Agg a;
+  double *dst = &a.A00;
+#pragma unroll
+  for (int k = 0; k < kAggDoubles; ++k) dst[k] = p[k];
+  return a;
+}
+
+// inclusive scan of one Agg per thread across the CTA (thread order); returns inclusive value
+__device__ Agg cta_inclusive_scan(Agg v, Agg *warp_tot /* smem [kWarps] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    Agg o = agg_shfl_up(v, d);
+    if (lane >= d) v = agg_combine(o, v);
+  }
+  if (lane == 31) warp_tot[warp] = v;
+  __syncthreads();
+  if (warp > 0) {
+    Agg pre = warp_tot[0];
+    for (int w = 1; w < warp; ++w) pre = agg_combine(pre, warp_tot[w]);
+    v = agg_combine(pre, v);
+  }
+  return v;
+}
+
+// ---- phase 1 ---------------------------------------------------------------
+__global__ void __launch_bounds__(kThreadsGp) gp_aggregate_kernel(const double *__restrict__ t,
+                                                                  const double *__restrict__ y,
+                                                                  const double *__restrict__ diag, int64_t N,
+                                                                  const double *__restrict__ S0,
+                                                                  const double *__restrict__ w0,
+                                                                  const double *__restrict__ Qf, double eps,
+                                                                  int64_t T, double *__restrict__ pref,
+                                                                  double *__restrict__ cta_tot) {
+  __shared__ Agg warp_tot[kWarpsGp];
+  const int64_t bch = blockIdx.y;
+  const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
+  const int64_t g = (int64_t)blockIdx.x * kThreadsGp + threadIdx.x;
+  const int64_t s = g * kRun, e = min(s + kRun, N);
+  const double *yb = y + bch * N;
+  Agg v = agg_identity();
+  if (s < e) {
+    double A00 = 1, A01 = 0, A10 = 0, A11 = 1, b0 = 0, b1 = 0, e0 = 0, e1 = 0, J00 = 0, J01 = 0, J11 = 0;
+    double Z00 = k.a, Z01 = 0.0, Z11 = k.a * k.w2;  // P = 0  <=>  Z = Sigma_inf
+    double tprev = s > 0 ? __ldg(t + s - 1) : __ldg(t);
+    for (int64_t i = s; i < e; ++i) {
+      const double ti = __ldg(t + i);
+      double f00, f01, f10, f11;
+      sho_phi(k, ti - tprev, f00, f01, f10, f11);
+      tprev = ti;
+      // A <- Phi A, b <- Phi b, Z <- Phi Z Phi^T
+      double a00 = f00 * A00 + f01 * A10, a01 = f00 * A01 + f01 * A11;
+      double a10 = f10 * A00 + f11 * A10, a11 = f10 * A01 + f11 * A11;
+      double c0 = f00 * b0 + f01 * b1, c1 = f10 * b0 + f11 * b1;
+      double z00 = f00 * Z00 + f01 * Z01, z01 = f00 * Z01 + f01 * Z11;
+      double z10 = f10 * Z00 + f11 * Z01, z11 = f10 * Z01 + f11 * Z11;
+      double p00 = z00 * f00 + z01 * f01, p01 = z00 * f10 + z01 * f11, p11 = z10 * f10 + z11 * f11;
+      const double pm = k.a - p00;
+      const double D = pm + __ldg(diag + i);
+      const double rD = 1.0 / D;
+      const double K0 = pm * rD, K1 = -p01 * rD;
+      const double vb = __ldg(yb + i) - c0;
+      J00 = fma(a00 * a00, rD, J00);
+      J01 = fma(a00 * a01, rD, J01);
+      J11 = fma(a01 * a01, rD, J11);
+      e0 = fma(a00 * vb, rD, e0);
+      e1 = fma(a01 * vb, rD, e1);
+      A00 = a00 - K0 * a00;
+      A01 = a01 - K0 * a01;
+      A10 = a10 - K1 * a00;
+      A11 = a11 - K1 * a01;
+      b0 = fma(K0, vb, c0);
+      b1 = fma(K1, vb, c1);
+      Z00 = fma(D * K0, K0, p00);
+      Z01 = fma(D * K0, K1, p01);
+      Z11 = fma(D * K1, K1, p11);
+    }
+    v = Agg{A00, A01, A10, A11, b0, b1, k.a - Z00, -Z01, k.a * k.w2 - Z11, e0, e1, J00, J01, J11};
+  }
+  v = cta_inclusive_scan(v, warp_tot);
+  if (g < T) agg_store(pref + (bch * T + g) * kAggDoubles, v);
+  if (threadIdx.x == kThreadsGp - 1) agg_store(cta_tot + (bch * gridDim.x + blockIdx.x) * kAggDoubles, v);
+}
+
+// ---- phase 2: scan the CTA totals, emit the state entering each CTA ---------
+__global__ void __launch_bounds__(kThreadsGp) gp_cta_scan_kernel(const double *__restrict__ cta_tot, int nctas,
+                                                                 const double *__restrict__ S0,
+                                                                 const double *__restrict__ w0,
+                                                                 const double *__restrict__ Qf, double eps,
+                                                                 double *__restrict__ cta_state) {
+  __shared__ Agg warp_tot[kWarpsGp];
+  __shared__ Agg carry_s;
+  const int64_t bch = blockIdx.x;
+  const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
+  Agg carry = agg_identity();
+  for (int base = 0; base < nctas; base += kThreadsGp) {
+    const int idx = base + threadIdx.x;
+    Agg v = idx < nctas ? agg_load(cta_tot + (bch * nctas + idx) * kAggDoubles) : agg_identity();
+    v = cta_inclusive_scan(v, warp_tot);
+    Agg incl = agg_combine(carry, v);
+    // exclusive prefix of idx = inclusive of idx-1
+    Agg prev = agg_shfl_up(incl, 1);
+    __shared__ Agg lastlane[kWarpsGp];
+    if ((threadIdx.x & 31) == 31) lastlane[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    Agg excl;
+    if ((threadIdx.x & 31) == 0)
+      excl = (threadIdx.x == 0) ? carry : lastlane[(threadIdx.x >> 5) - 1];
+    else
+      excl = prev;
+    if (idx < nctas) {
+      double m0 = 0.0, m1 = 0.0, P00 = k.a, P01 = 0.0, P11 = k.a * k.w2;
+      agg_apply(excl, m0, m1, P00, P01, P11);
+      double *o = cta_state + (bch * nctas + idx) * 5;
+      o[0] = m0;
+      o[1] = m1;
+      o[2] = k.a - P00;  // Z = Sigma_inf - P
+      o[3] = -P01;
+      o[4] = k.a * k.w2 - P11;
+    }
+    if (threadIdx.x == kThreadsGp - 1) carry_s = incl;
+    __syncthreads();
+    carry = carry_s;
+    __syncthreads();
+  }
+}
+
+// ---- phase 3 ---------------------------------------------------------------
+__global__ void __launch_bounds__(kThreadsGp) gp_loglike_kernel(const double *__restrict__ t,
+                                                                const double *__restrict__ y,
+                                                                const double *__restrict__ diag, int64_t N,
+                                                                const double *__restrict__ S0,
+                                                                const double *__restrict__ w0,
+                                                                const double *__restrict__ Qf, double eps, int64_t T,
+                                                                const double *__restrict__ pref,
+                                                                const double *__restrict__ cta_state,
+                                                                double *__restrict__ cta_ll) {
+  __shared__ double red[kWarpsGp];
+  const int64_t bch = blockIdx.y;
+  const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
+  const int64_t g = (int64_t)blockIdx.x * kThreadsGp + threadIdx.x;
+  const int64_t s = g * kRun, e = min(s + kRun, N);
+  const double *yb = y + bch * N;
+  double acc = 0.0;
+  if (s < e) {
+    const double *st = cta_state + (bch * gridDim.x + blockIdx.x) * 5;
+    double m0 = st[0], m1 = st[1], Z00 = st[2], Z01 = st[3], Z11 = st[4];
+    if (threadIdx.x > 0) {
+      double P00 = k.a - Z00, P01 = -Z01, P11 = k.a * k.w2 - Z11;
+      Agg pre = agg_load(pref + (bch * T + g - 1) * kAggDoubles);
+      agg_apply(pre, m0, m1, P00, P01, P11);
+      Z00 = k.a - P00;
+      Z01 = -P01;
+      Z11 = k.a * k.w2 - P11;
+    }
+    double tprev = s > 0 ? __ldg(t + s - 1) : __ldg(t);
+    for (int64_t i = s; i < e; ++i) {
+      const double ti = __ldg(t + i);
+      double f00, f01, f10, f11;
+      sho_phi(k, ti - tprev, f00, f01, f10, f11);
+      tprev = ti;
+      double c0 = f00 * m0 + f01 * m1, c1 = f10 * m0 + f11 * m1;
+      double z00 = f00 * Z00 + f01 * Z01, z01 = f00 * Z01 + f01 * Z11;
+      double z10 = f10 * Z00 + f11 * Z01, z11 = f10 * Z01 + f11 * Z11;
+      double p00 = z00 * f00 + z01 * f01, p01 = z00 * f10 + z01 * f11, p11 = z10 * f10 + z11 * f11;
+      const double pm = k.a - p00;
+      const double D = pm + __ldg(diag + i);
+      const double rD = 1.0 / D;
+      const double K0 = pm * rD, K1 = -p01 * rD;
+      const double v = __ldg(yb + i) - c0;
+      acc += fma(v * v, rD, log(D));
+      m0 = fma(K0, v, c0);
+      m1 = fma(K1, v, c1);
+      Z00 = fma(D * K0, K0, p00);
+      Z01 = fma(D * K0, K1, p01);
+      Z11 = fma(D * K1, K1, p11);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFullGp, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s4 = 0.0;
+    for (int w = 0; w < kWarpsGp; ++w) s4 += red[w];
+    cta_ll[bch * gridDim.x + blockIdx.x] = s4;
+  }
+}
+
+__global__ void gp_fold_kernel(const double *__restrict__ cta_ll, int nctas, int64_t N, int64_t B,
+                               double *__restrict__ loglike) {
+  const int64_t bch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (bch >= B) return;
+  double acc = 0.0;
+  for (int i = 0; i < nctas; ++i) acc += cta_ll[bch * nctas + i];
+  loglike[bch] = -0.5 * acc - 0.5 * (double)N * 1.8378770664093454835606594728112;  // log(2 pi)
+}
+
+struct GpLayout {
+  int64_t T;      // runs (threads) per chain
+  int nctas;      // CTAs per chain
+  size_t off_pref, off_tot, off_state, off_ll, bytes;
+};
+inline GpLayout gp_layout(int64_t N, int64_t B) {
+  GpLayout L;
+  L.T = (N + kRun - 1) / kRun;
+  L.nctas = (int)((L.T + kThreadsGp - 1) / kThreadsGp);
+  size_t o = 0;
+  auto take = [&](size_t n) {
+    size_t at = o;
+    o += (n * sizeof(double) + 255) & ~(size_t)255;
+    return at;
+  };
+  L.off_pref = take((size_t)B * L.T * kAggDoubles);
+  L.off_tot = take((size_t)B * L.nctas * kAggDoubles);
+  L.off_state = take((size_t)B * L.nctas * 5);
+  L.off_ll = take((size_t)B * L.nctas);
+  L.bytes = o;
+  return L;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t xo_celerite_sho_workspace(int64_t N, int64_t B) {
+  if (N <= 0 || B <= 0) return 0;
+  return gp_layout(N, B).bytes;
+}
+
+int xo_celerite_sho_loglike(const double *t, const double *y, const double *diag, int64_t N, const double *S0,
+                            const double *w0, const double *Q, int64_t B, double eps, double *loglike, void *workspace,
+                            size_t workspace_bytes, void *stream) {
+  if (N < 0 || B < 0) return XO_EINVAL;
+  if (B == 0) return 0;
+  if (N == 0) return XO_EINVAL;
+  if (B > 65535) return XO_ERANGE;
+  if (!t || !y || !diag || !S0 || !w0 || !Q || !loglike || !workspace) return XO_EINVAL;
+  GpLayout L = gp_layout(N, B);
+  if (workspace_bytes < L.bytes) return XO_EWORKSPACE;
+  char *ws = static_cast<char *>(workspace);
+  double *pref = reinterpret_cast<double *>(ws + L.off_pref);
+  double *tot = reinterpret_cast<double *>(ws + L.off_tot);
+  double *state = reinterpret_cast<double *>(ws + L.off_state);
+  double *ll = reinterpret_cast<double *>(ws + L.off_ll);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid(L.nctas, (unsigned)B);
+  gp_aggregate_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, pref, tot);
+  gp_cta_scan_kernel<<<(unsigned)B, kThreadsGp, 0, st>>>(tot, L.nctas, S0, w0, Q, eps, state);
+  gp_loglike_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, pref, state, ll);
+  gp_fold_kernel<<<(unsigned)((B + 63) / 64), 64, 0, st>>>(ll, L.nctas, N, B, loglike);
+  return xo::launch_status();
+}
+
+}  // extern "C"

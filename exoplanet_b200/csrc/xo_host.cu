@@ -1,0 +1,221 @@
+// xo_host.cu -- host-buffer entry points and library metadata.
+//
+// These have the shape of exoplanet-core's pybind11 `driver` (flat contiguous fp64 host
+// arrays filled in place), i.e. what PyTensor's Op.perform would hand over at
+//   /root/reference/src/exoplanet/orbits/keplerian.py:333, :744-753
+//   /root/reference/src/exoplanet/light_curves/limb_dark.py:24
+// Each call: stream-ordered scratch (cudaMallocAsync) -> H2D -> kernel -> D2H -> sync -> free.
+// Nothing persists between calls; no CPU arithmetic path exists in this library.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "xo_common.cuh"
+
+namespace {
+
+struct DeviceScope {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  cudaStream_t st = nullptr;
+  explicit DeviceScope(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess) err = cudaSetDevice(device);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  }
+  ~DeviceScope() {
+    if (st) cudaStreamDestroy(st);
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// a bump allocator over ONE stream-ordered allocation
+struct Arena {
+  char *base = nullptr;
+  size_t off = 0, cap = 0;
+  cudaStream_t st;
+  cudaError_t err = cudaSuccess;
+  Arena(size_t bytes, cudaStream_t s) : cap(bytes), st(s) { err = cudaMallocAsync((void **)&base, bytes ? bytes : 256, s); }
+  ~Arena() {
+    if (base) cudaFreeAsync(base, st);
+  }
+  template <typename T>
+  T *take(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
+    T *p = reinterpret_cast<T *>(base + off);
+    off += bytes;
+    return p;
+  }
+};
+inline size_t pad(size_t n, size_t sz = 8) { return (n * sz + 255) & ~(size_t)255; }
+
+#define XO_TRY(expr)                         \
+  do {                                       \
+    cudaError_t _e = (expr);                 \
+    if (_e != cudaSuccess) return -(int)_e;  \
+  } while (0)
+#define XO_RC(expr)        \
+  do {                     \
+    int _rc = (expr);      \
+    if (_rc != 0) return _rc; \
+  } while (0)
+
+inline cudaError_t h2d(void *d, const void *h, size_t bytes, cudaStream_t st) {
+  return cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st);
+}
+inline cudaError_t d2h(void *h, const void *d, size_t bytes, cudaStream_t st) {
+  return cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *xo_version(void) { return "xo_b200 0.1.0 (sm_100a)"; }
+int xo_abi_version(void) { return XO_ABI_VERSION; }
+
+int xo_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+const char *xo_strerror(int status) {
+  if (status == 0) return "ok";
+  if (status == XO_EINVAL) return "xo_b200: invalid argument (null pointer or negative size)";
+  if (status == XO_ERANGE) return "xo_b200: size above a compiled limit (planets, stencil, chains or cadences)";
+  if (status == XO_EWORKSPACE) return "xo_b200: workspace too small";
+  if (status < 0) return cudaGetErrorString((cudaError_t)(-status));
+  return "xo_b200: unknown status";
+}
+
+int xo_kepler_host(const double *M, const double *e, double *sinf, double *cosf, int64_t n, int device) {
+  if (n < 0) return XO_EINVAL;
+  if (n == 0) return 0;
+  if (!M || !e || !sinf || !cosf) return XO_EINVAL;
+  DeviceScope ds(device);
+  XO_TRY(ds.err);
+  const size_t b = (size_t)n * 8;
+  Arena ar(4 * pad(n), ds.st);
+  XO_TRY(ar.err);
+  double *dM = ar.take<double>(n), *de = ar.take<double>(n), *ds_ = ar.take<double>(n), *dc = ar.take<double>(n);
+  XO_TRY(h2d(dM, M, b, ds.st));
+  XO_TRY(h2d(de, e, b, ds.st));
+  XO_RC(xo_kepler_fwd(dM, de, ds_, dc, n, ds.st));
+  XO_TRY(d2h(sinf, ds_, b, ds.st));
+  XO_TRY(d2h(cosf, dc, b, ds.st));
+  XO_TRY(cudaStreamSynchronize(ds.st));
+  return 0;
+}
+
+int xo_qsv_host(const double *b, const double *r, double *s, double *dsdb, double *dsdr, int64_t n, int device) {
+  if (n < 0) return XO_EINVAL;
+  if (n == 0) return 0;
+  if (!b || !r || !s || ((dsdb == nullptr) != (dsdr == nullptr))) return XO_EINVAL;
+  DeviceScope ds(device);
+  XO_TRY(ds.err);
+  const size_t nb = (size_t)n * 8;
+  Arena ar(2 * pad(n) + 3 * pad(3 * n), ds.st);
+  XO_TRY(ar.err);
+  double *db = ar.take<double>(n), *dr = ar.take<double>(n), *dS = ar.take<double>(3 * n);
+  double *dB = dsdb ? ar.take<double>(3 * n) : nullptr, *dR = dsdb ? ar.take<double>(3 * n) : nullptr;
+  XO_TRY(h2d(db, b, nb, ds.st));
+  XO_TRY(h2d(dr, r, nb, ds.st));
+  XO_RC(xo_qsv_fwd(db, dr, dS, dB, dR, n, ds.st));
+  XO_TRY(d2h(s, dS, 3 * nb, ds.st));
+  if (dsdb) {
+    XO_TRY(d2h(dsdb, dB, 3 * nb, ds.st));
+    XO_TRY(d2h(dsdr, dR, 3 * nb, ds.st));
+  }
+  XO_TRY(cudaStreamSynchronize(ds.st));
+  return 0;
+}
+
+int xo_contact_points_host(const double *a, const double *e, const double *cosw, const double *sinw, const double *cosi,
+                           const double *sini, const double *L, double *M_left, double *M_right, int32_t *flag,
+                           int64_t n, int device) {
+  if (n < 0) return XO_EINVAL;
+  if (n == 0) return 0;
+  if (!a || !e || !cosw || !sinw || !cosi || !sini || !L || !M_left || !M_right || !flag) return XO_EINVAL;
+  DeviceScope ds(device);
+  XO_TRY(ds.err);
+  const size_t nb = (size_t)n * 8;
+  Arena ar(9 * pad(n) + pad(n, 4), ds.st);
+  XO_TRY(ar.err);
+  const double *src[7] = {a, e, cosw, sinw, cosi, sini, L};
+  double *din[7];
+  for (int k = 0; k < 7; ++k) {
+    din[k] = ar.take<double>(n);
+    XO_TRY(h2d(din[k], src[k], nb, ds.st));
+  }
+  double *dl = ar.take<double>(n), *dr = ar.take<double>(n);
+  int32_t *df = ar.take<int32_t>(n);
+  XO_RC(xo_contact_points(din[0], din[1], din[2], din[3], din[4], din[5], din[6], dl, dr, df, n, ds.st));
+  XO_TRY(d2h(M_left, dl, nb, ds.st));
+  XO_TRY(d2h(M_right, dr, nb, ds.st));
+  XO_TRY(d2h(flag, df, (size_t)n * 4, ds.st));
+  XO_TRY(cudaStreamSynchronize(ds.st));
+  return 0;
+}
+
+int xo_transit_lc_host(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
+                       const double *dtk, const double *wk, int K, double *lc, int device) {
+  if (N < 0 || C < 0 || P < 0 || K < 1) return XO_EINVAL;
+  if (N == 0 || C == 0 || P == 0) return 0;
+  if (!t || !elem || !cl || !dtk || !wk || !lc) return XO_EINVAL;
+  DeviceScope ds(device);
+  XO_TRY(ds.err);
+  Arena ar(pad(N) + pad(C * P * XO_NEL) + pad(3 * C) + 2 * pad(K) + pad(C * N * P), ds.st);
+  XO_TRY(ar.err);
+  double *dt = ar.take<double>(N), *del = ar.take<double>(C * P * XO_NEL), *dcl = ar.take<double>(3 * C);
+  double *dd = ar.take<double>(K), *dw = ar.take<double>(K), *dlc = ar.take<double>(C * N * P);
+  XO_TRY(h2d(dt, t, (size_t)N * 8, ds.st));
+  XO_TRY(h2d(del, elem, (size_t)C * P * XO_NEL * 8, ds.st));
+  XO_TRY(h2d(dcl, cl, (size_t)C * 3 * 8, ds.st));
+  XO_TRY(h2d(dd, dtk, (size_t)K * 8, ds.st));
+  XO_TRY(h2d(dw, wk, (size_t)K * 8, ds.st));
+  XO_RC(xo_transit_lc_fwd(dt, N, del, dcl, C, P, dd, dw, K, dlc, ds.st));
+  XO_TRY(d2h(lc, dlc, (size_t)C * N * P * 8, ds.st));
+  XO_TRY(cudaStreamSynchronize(ds.st));
+  return 0;
+}
+
+int xo_transit_logp_grad_host(const double *t, const double *y, const double *ivar, int64_t N, const double *elem,
+                              const double *cl, const double *mean, int64_t C, int64_t P, const double *dtk,
+                              const double *wk, int K, double lognorm, double *logp, double *gel, double *gcl,
+                              double *gmean, int device) {
+  if (N <= 0 || C < 0 || P <= 0 || K < 1) return XO_EINVAL;
+  if (C == 0) return 0;
+  if (!t || !y || !ivar || !elem || !cl || !mean || !dtk || !wk || !logp || !gel || !gcl || !gmean) return XO_EINVAL;
+  DeviceScope ds(device);
+  XO_TRY(ds.err);
+  const size_t ws = xo_transit_logp_grad_workspace(N, C, P);
+  Arena ar(3 * pad(N) + pad(C * P * XO_NEL) + pad(3 * C) + pad(C) + 2 * pad(K) + pad(C) + pad(C * P * XO_NGRAD) +
+               pad(3 * C) + pad(C) + pad(ws, 1),
+           ds.st);
+  XO_TRY(ar.err);
+  double *dt = ar.take<double>(N), *dy = ar.take<double>(N), *dv = ar.take<double>(N);
+  double *del = ar.take<double>(C * P * XO_NEL), *dcl = ar.take<double>(3 * C), *dm = ar.take<double>(C);
+  double *dd = ar.take<double>(K), *dw = ar.take<double>(K);
+  double *dlp = ar.take<double>(C), *dge = ar.take<double>(C * P * XO_NGRAD), *dgc = ar.take<double>(3 * C),
+         *dgm = ar.take<double>(C);
+  void *dws = ar.take<char>(ws);
+  XO_TRY(h2d(dt, t, (size_t)N * 8, ds.st));
+  XO_TRY(h2d(dy, y, (size_t)N * 8, ds.st));
+  XO_TRY(h2d(dv, ivar, (size_t)N * 8, ds.st));
+  XO_TRY(h2d(del, elem, (size_t)C * P * XO_NEL * 8, ds.st));
+  XO_TRY(h2d(dcl, cl, (size_t)C * 3 * 8, ds.st));
+  XO_TRY(h2d(dm, mean, (size_t)C * 8, ds.st));
+  XO_TRY(h2d(dd, dtk, (size_t)K * 8, ds.st));
+  XO_TRY(h2d(dw, wk, (size_t)K * 8, ds.st));
+  XO_RC(xo_transit_logp_grad(dt, dy, dv, N, del, dcl, dm, C, P, dd, dw, K, lognorm, dlp, dge, dgc, dgm, dws, ws, ds.st));
+  XO_TRY(d2h(logp, dlp, (size_t)C * 8, ds.st));
+  XO_TRY(d2h(gel, dge, (size_t)C * P * XO_NGRAD * 8, ds.st));
+  XO_TRY(d2h(gcl, dgc, (size_t)C * 3 * 8, ds.st));
+  XO_TRY(d2h(gmean, dgm, (size_t)C * 8, ds.st));
+  XO_TRY(cudaStreamSynchronize(ds.st));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,445 @@
+// xo_math.cuh -- per-cadence fp64 math of the hot path, written for sm_100a.
+//
+// Everything here is a __host__ __device__ inline so the *same* arithmetic can be
+// compiled into a CPU harness by the unit tests (tests/hostcheck) -- that harness is
+// test infrastructure, not a fallback: the product library only launches kernels.
+//
+// What each routine restates (reference file:line are under /root/reference):
+//   kepler_solve   -- the op at src/exoplanet/orbits/keplerian.py:333 (exoplanet-core
+//                     `kepler`): Markley (1995) cubic starter + one 5th-order correction,
+//                     reorganised for the GPU: no data-dependent loop, one sincos, the
+//                     corrected sin/cos by angle addition, 4 reciprocals, cancellation-
+//                     free E - sin E / 1 - cos E so the e->1, M->0 corner stays accurate.
+//   qsv            -- the op at src/exoplanet/light_curves/limb_dark.py:24
+//                     (`quad_solution_vector`): Agol, Luger & Foreman-Mackey (2020)
+//                     uniform / linear / quadratic terms and their b, r derivatives, with
+//                     three Bulirsch cel integrals advanced in lock-step on one AGM ladder.
+//   lc_point       -- the PyTensor glue between them: keplerian.py:324-334 (mean anomaly),
+//                     :283-322,:400-409 (radius, rotation), limb_dark.py:216-252.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define XO_HD __host__ __device__ __forceinline__
+#else
+#define XO_HD inline
+#endif
+
+namespace xo {
+
+constexpr double kPi = 3.14159265358979323846264338327950288;
+constexpr double kTwoPiHi = 6.283185307179586232e+00;   // fp64(2 pi)
+constexpr double kTwoPiLo = 2.449293598294706414e-16;   // 2 pi - fp64(2 pi)
+constexpr double kInvTwoPi = 0.159154943091895335768883763372514362;
+constexpr double kPio2Hi = 1.570796326794896558e+00;
+constexpr double kPio2Lo = 6.123233995736766036e-17;
+constexpr double kTwoOverPi = 0.636619772367581343075535053490057448;
+
+XO_HD double rcp(double x) {
+#if defined(__CUDA_ARCH__)
+  return __drcp_rn(x);
+#else
+  return 1.0 / x;
+#endif
+}
+
+// ---------------------------------------------------------------------------
+// sin/cos on [0, pi] that also return E - sin E and 1 - cos E free of cancellation.
+// Polynomials from tools/gen_poly.py (|x| <= 1.02 pi/4; abs err 5e-18 / 1e-18).
+// ---------------------------------------------------------------------------
+XO_HD void sincos_0pi(double E, double &s, double &c, double &EmS, double &omC) {
+  double qf = rint(E * kTwoOverPi);  // 0, 1 or 2
+  double x = fma(-qf, kPio2Hi, E);
+  x = fma(-qf, kPio2Lo, x);
+  double u = x * x;
+  double ps = -7.58426609767779964718e-13;
+  ps = fma(ps, u, 1.60584895500232502802e-10);
+  ps = fma(ps, u, -2.50521059616691626032e-8);
+  ps = fma(ps, u, 0.0000027557319218543807191);
+  ps = fma(ps, u, -0.000198412698412640218792);
+  ps = fma(ps, u, 0.00833333333333333099958);
+  ps = fma(ps, u, -0.166666666666666666651);
+  double pc = 4.74452016112717801505e-14;
+  pc = fma(pc, u, -1.1470437495511350934e-11);
+  pc = fma(pc, u, 2.08767556405153041563e-9);
+  pc = fma(pc, u, -2.75573192209605647402e-7);
+  pc = fma(pc, u, 0.0000248015873015840664244);
+  pc = fma(pc, u, -0.00138888888888888875915);
+  pc = fma(pc, u, 0.0416666666666666666658);
+  double xs = x * u * ps;               // sin x - x
+  double cm1 = fma(u * u, pc, -0.5 * u);  // cos x - 1
+  double sx = x + xs, cx = 1.0 + cm1;
+  if (qf == 0.0) {
+    s = sx;
+    c = cx;
+    EmS = -xs;
+    omC = -cm1;
+  } else if (qf == 1.0) {  // E = pi/2 + x
+    s = cx;
+    c = -sx;
+    EmS = E - cx;
+    omC = 1.0 + sx;
+  } else {  // E = pi + x
+    s = -sx;
+    c = -cx;
+    EmS = E + sx;
+    omC = 2.0 + cm1;
+  }
+}
+
+// full-range sincos for the circular branch (keplerian.py:331-332): M already reduced
+// to [-pi, pi].
+XO_HD void sincos_reduced(double Mr, double &s, double &c) {
+  double a = fabs(Mr), ss, cc, d0, d1;
+  sincos_0pi(fmin(a, kPi), ss, cc, d0, d1);
+  s = Mr < 0.0 ? -ss : ss;
+  c = cc;
+}
+
+XO_HD double reduce_2pi(double M) {
+  double k = rint(M * kInvTwoPi);
+  double r = fma(-k, kTwoPiHi, M);
+  return fma(-k, kTwoPiLo, r);
+}
+
+// ---------------------------------------------------------------------------
+// Kepler: (M, e) -> (sin f, cos f).  0 <= e < 1.
+// ---------------------------------------------------------------------------
+XO_HD void kepler_solve(double M, double e, double &sinf, double &cosf) {
+  double Mr = reduce_2pi(M);
+  double Ma = fmin(fabs(Mr), kPi);
+  double ome = 1.0 - e;
+  double ope = 1.0 + e;
+  // Markley (1995) starter: one cbrt, one sqrt, two reciprocals
+  constexpr double fac = 1.0 / (kPi - 6.0 / kPi);
+  double alpha = fma(1.6 * fac * rcp(ope), kPi - Ma, 3.0 * kPi * fac);
+  double d = fma(alpha, e, 3.0 * ome);
+  double ad = alpha * d;
+  double M2 = Ma * Ma;
+  double r = fma(3.0 * ad, d - ome, M2) * Ma;
+  double q = fma(2.0 * ad, ome, -M2);
+  double q2 = q * q;
+  double w = cbrt(fabs(r) + sqrt(fma(q2, q, r * r)));
+  w = w * w;
+  double W = fma(w, w + q, q2);
+  double E = fma(2.0 * r, w, Ma * W) * rcp(d * W);
+  // one 5th-order correction: root of the quartic Taylor polynomial in dE,
+  // f0 + f1 dE + f2 dE^2/2 + f3 dE^3/6 - f2 dE^4/24 = 0, by fixed-point on 1/f1
+  double s, c, EmS, omC;
+  sincos_0pi(E, s, c, EmS, omC);
+  double f0 = fma(e, EmS, fma(E, ome, -Ma));
+  double f1 = fma(e, omC, ome);
+  double f2 = e * s;
+  double f3 = e * c;
+  double rf1 = rcp(f1);
+  double h2 = 0.5 * f2, h3 = f3 * (1.0 / 6.0), h4 = -f2 * (1.0 / 24.0);
+  double dE = -f0 * rf1;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) dE = -fma(dE * dE, fma(dE, fma(dE, h4, h3), h2), f0) * rf1;
+  // sin/cos(E + dE) by angle addition (|dE| < ~1e-2)
+  double d2 = dE * dE;
+  double sd = dE * fma(d2, fma(d2, fma(d2, -1.0 / 5040.0, 1.0 / 120.0), -1.0 / 6.0), 1.0);
+  double cdm1 = d2 * fma(d2, fma(d2, -1.0 / 720.0, 1.0 / 24.0), -0.5);
+  double s1 = s + fma(c, sd, s * cdm1);
+  double omC1 = omC - fma(c, cdm1, -s * sd);
+  double den = fma(e, omC1, ome);  // 1 - e cos E
+  double rden = rcp(den);
+  double sq = sqrt(ome * ope);
+  sinf = (Mr < 0.0 ? -sq : sq) * s1 * rden;
+  cosf = (ome - omC1) * rden;  // (cos E - e) without cancellation
+}
+
+// VJP factors of the op
+XO_HD void kepler_jac(double sinf, double cosf, double e, double &dfdM, double &dfde) {
+  double ome2 = (1.0 - e) * (1.0 + e);
+  double opc = fma(e, cosf, 1.0);
+  double r = rcp(ome2);
+  dfdM = opc * opc * r * sqrt(r);
+  dfde = (2.0 + e * cosf) * sinf * r;
+}
+
+// ---------------------------------------------------------------------------
+// Three Bulirsch (1969) cel integrals on one AGM ladder:
+//   G  = cel(kc, p,  a, b)   (p > 0)
+//   Ek = cel(kc, 1,  1, kc^2) = E(m)
+//   Em = cel(kc, 1,  1, 0)    = (E(m) - (1-m) K(m)) / m
+// ---------------------------------------------------------------------------
+XO_HD void cel3(double kc, double kc2, double p, double a, double b, double &G, double &Ek, double &Em) {
+  constexpr double CA = 1.0e-8;  // quadratic convergence: error ~ CA^2
+  double e = kc, em = 1.0;
+  p = sqrt(p);
+  b *= rcp(p);
+  double p1 = 1.0, aE = 1.0, bE = kc2, aM = 1.0, bM = 0.0;
+#pragma unroll 1
+  for (int it = 0; it < 12; ++it) {
+    double rp = rcp(p), rp1 = rcp(p1);
+    double f = a;
+    a = fma(b, rp, a);
+    double g = e * rp;
+    b = fma(f, g, b);
+    b += b;
+    p += g;
+    double g1 = e * rp1;
+    f = aE;
+    aE = fma(bE, rp1, aE);
+    bE = fma(f, g1, bE);
+    bE += bE;
+    f = aM;
+    aM = fma(bM, rp1, aM);
+    bM = fma(f, g1, bM);
+    bM += bM;
+    p1 += g1;
+    double gp = em;
+    em += kc;
+    if (fabs(gp - kc) <= gp * CA) break;
+    kc = sqrt(e);
+    kc += kc;
+    e = kc * em;
+  }
+  double t = 0.5 * kPi * rcp(em);
+  G = t * fma(a, em, b) * rcp(em + p);
+  double r1 = rcp(em + p1);
+  Ek = t * fma(aE, em, bE) * r1;
+  Em = t * fma(aM, em, bM) * r1;
+}
+
+// K is only needed on the b == r branch
+XO_HD double celK(double kc) {
+  constexpr double CA = 1.0e-8;
+  double e = kc, em = 1.0, p = 1.0, a = 1.0, b = 1.0;
+#pragma unroll 1
+  for (int it = 0; it < 12; ++it) {
+    double rp = rcp(p);
+    double f = a;
+    a = fma(b, rp, a);
+    double g = e * rp;
+    b = fma(f, g, b);
+    b += b;
+    p += g;
+    double gp = em;
+    em += kc;
+    if (fabs(gp - kc) <= gp * CA) break;
+    kc = sqrt(e);
+    kc += kc;
+    e = kc * em;
+  }
+  return 0.5 * kPi * fma(a, em, b) / (em * (em + p));
+}
+
+// ---------------------------------------------------------------------------
+// quad_solution_vector(b, r): s[3] and (optionally) ds/db, ds/dr.
+// b may be negative: |b| is used and d/db carries sign(b).
+// ---------------------------------------------------------------------------
+template <bool kJac>
+XO_HD void qsv(double b_in, double r, double *s, double *dsdb, double *dsdr) {
+  double b = fabs(b_in);
+  if (kJac) {
+    dsdb[0] = dsdb[1] = dsdb[2] = 0.0;
+    dsdr[0] = dsdr[1] = dsdr[2] = 0.0;
+  }
+  // the four kite factors; the one subtraction in each that can cancel is exact
+  double t1 = 1.0 + b + r;
+  double t2 = (r <= 2.0) ? (1.0 - r) + b : 1.0 + (b - r);  // 1 + b - r
+  double t3 = (b <= 2.0) ? (1.0 - b) + r : 1.0 + (r - b);  // 1 - b + r
+  double t4 = (b >= 0.5) ? (b - 1.0) + r : (r - 1.0) + b;  // b + r - 1
+  if (!(r > 0.0) || !(t3 > 0.0)) {                         // unocculted (r <= 0, b >= 1 + r, NaN)
+    bool bad = (b != b) || (r != r);
+    s[0] = bad ? NAN : kPi;
+    s[1] = bad ? NAN : 2.0 * kPi / 3.0;
+    s[2] = bad ? NAN : 0.0;
+    return;
+  }
+  if (t2 <= 0.0) {  // fully occulted
+    s[0] = s[1] = s[2] = 0.0;
+    return;
+  }
+  double r2 = r * r, b2 = b * b;
+  double bmr = b - r, bpr = b + r;
+  double onembmr2 = t2 * t3;   // 1 - (b-r)^2
+  double onembpr2 = -t4 * t1;  // 1 - (b+r)^2
+  double fourbr = 4.0 * b * r;
+  double kap0, sk0, ck0, s0, eta;
+  if (t4 <= 0.0) {  // occultor entirely inside the disk
+    kap0 = kPi;
+    sk0 = 0.0;
+    ck0 = -1.0;
+    s0 = kPi * (1.0 - r2);
+    eta = 0.5 * r2 * fma(2.0, b2, r2);
+  } else {
+    double D = sqrt(t1 * t2 * t3 * t4);  // twice the kite area
+    double c0 = fma(r - 1.0, r + 1.0, b2);
+    double c1 = fma(1.0 - r, 1.0 + r, b2);
+    kap0 = atan2(D, c0);
+    double kap1 = atan2(D, c1);
+    double rtwobr = rcp(2.0 * b * r);
+    sk0 = D * rtwobr;
+    ck0 = c0 * rtwobr;
+    s0 = kPi - (kap1 + r2 * kap0 - 0.5 * D);
+    eta = (kap1 + r2 * fma(2.0, b2, r2) * kap0 - 0.25 * (1.0 + 5.0 * r2 + b2) * D) * (0.5 / kPi);
+  }
+  s[0] = s0;
+  s[2] = 2.0 * s0 + 4.0 * kPi * eta - 2.0 * kPi;
+  if (kJac) {
+    double gg = 2.0 - 4.0 * b2 - 4.0 * r2;
+    dsdb[0] = 2.0 * r * sk0;
+    dsdr[0] = -2.0 * r * kap0;
+    dsdr[2] = -r * (2.0 * gg * kap0 + 16.0 * b * r * sk0);
+    dsdb[2] = r * (2.0 * gg * sk0 + 8.0 * b * r * (kap0 + sk0 * ck0));
+  }
+  // linear term  s1 = 2pi/3 (1 - Theta(r - b)) - pi Lambda
+  double Lam, d1b, d1r;
+  if (b == 0.0) {
+    double x = sqrt(fmax(0.0, 1.0 - r2));
+    Lam = -2.0 / 3.0 * x * x * x;
+    d1b = 0.0;
+    d1r = -2.0 * kPi * r * x;
+  } else if (b == r) {
+    if (r == 0.5) {
+      Lam = 1.0 / 3.0 - 4.0 / (9.0 * kPi);
+      d1r = -4.0 * r;
+      d1b = 4.0 * r / 3.0;
+    } else if (r < 0.5) {
+      double m = 4.0 * r2, kc2 = 1.0 - m, kc = sqrt(kc2);
+      double G, E, Em;
+      cel3(kc, kc2, 1.0, 1.0, 1.0, G, E, Em);  // G = K(m)
+      Lam = 1.0 / 3.0 + 2.0 / (9.0 * kPi) * (4.0 * (2.0 * r2 - 1.0) * E + (1.0 - 4.0 * r2) * G);
+      d1r = -4.0 * r * E;
+      d1b = 4.0 * r / 3.0 * (2.0 * Em - E);
+    } else {
+      double m = 0.25 / r2, kc2 = 1.0 - m, kc = sqrt(kc2);
+      double G, E, Em;
+      cel3(kc, kc2, 1.0, 1.0, 1.0, G, E, Em);
+      Lam = 1.0 / 3.0 + 16.0 * r / (9.0 * kPi) * (2.0 * r2 - 1.0) * E -
+            (1.0 - 4.0 * r2) * (3.0 - 8.0 * r2) / (9.0 * kPi * r) * G;
+      d1r = -8.0 * r2 * m * Em;
+      d1b = 8.0 * r2 / 3.0 * m * (2.0 * E - Em);
+    }
+  } else if (t4 == 0.0) {  // b = 1 - r
+    double sqA = sqrt(onembmr2);
+    Lam = 2.0 / (3.0 * kPi) * acos(1.0 - 2.0 * r) - 4.0 / (9.0 * kPi) * (3.0 + 2.0 * r - 8.0 * r2) * sqrt(r * (1.0 - r)) -
+          (r > 0.5 ? 2.0 / 3.0 : 0.0);
+    d1r = -4.0 * r * sqA;
+    d1b = 4.0 * r * sqA / 3.0;
+  } else if (t4 > 0.0) {  // k^2 < 1: the limb crosses the occultor
+    double rfourbr = rcp(fourbr);
+    double kc2 = -onembpr2 * rfourbr;
+    double kc = sqrt(kc2);
+    double rsqbr = rcp(sqrt(b * r));
+    double G, E, Em;
+    cel3(kc, kc2, bmr * bmr * kc2, 0.0, 3.0 * kc2 * bmr * bpr, G, E, Em);
+    Lam = onembmr2 * (G + fma(-3.0 + 6.0 * r2 + 2.0 * b * r, Em, -fourbr * E)) * rsqbr * (1.0 / (9.0 * kPi));
+    d1r = -2.0 * r * onembmr2 * Em * rsqbr;
+    d1b = 2.0 * r * onembmr2 * (2.0 * E - Em) * rsqbr * (1.0 / 3.0);
+  } else {  // k^2 > 1
+    double rA = rcp(onembmr2);
+    double kc2 = onembpr2 * rA;
+    double kc = sqrt(kc2);
+    double sqA = sqrt(onembmr2);
+    double qq = bmr * rcp(bpr);
+    double mu = 3.0 * qq * rA;
+    double p = qq * qq * kc2;
+    double G, E, Em;
+    cel3(kc, kc2, p, 1.0 + mu, p + mu, G, E, Em);
+    Lam = 2.0 * sqA * fma(onembpr2, G, -(4.0 - 7.0 * r2 - b2) * E) * (1.0 / (9.0 * kPi));
+    d1r = -4.0 * r * sqA * E;
+    d1b = 4.0 * r * sqA * (1.0 / 3.0) * (2.0 * Em - E);
+  }
+  s[1] = (r > b ? 0.0 : 2.0 * kPi / 3.0) - kPi * Lam;
+  if (kJac) {
+    dsdb[1] = d1b;
+    dsdr[1] = d1r;
+    if (b_in < 0.0) {
+      dsdb[0] = -dsdb[0];
+      dsdb[1] = -dsdb[1];
+      dsdb[2] = -dsdb[2];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Element block (include/xo_b200.h; XO_EL_* indices) and the per-sample evaluation.
+// `el` usually points into shared memory (one block per chain and planet).
+// ---------------------------------------------------------------------------
+// dt = mod(t - t0 + P/2, P) - P/2 in [tstart, tend]   (keplerian.py:731,769)
+XO_HD bool in_window(const double *el, double rperiod, double t) {
+  double period = el[10];
+  double hp = 0.5 * period;
+  double x = (t - el[0]) + hp;
+  double dt = fma(-period, floor(x * rperiod), x) - hp;
+  return (dt >= el[11]) & (dt <= el[12]);
+}
+
+// true anomaly at time tt (keplerian.py:324-334); M = ((t - t0) - tref) n, in that order
+XO_HD void true_anomaly(const double *el, double tt, double &sf, double &cf, double &tm) {
+  tm = (tt - el[0]) - el[1];
+  double M = tm * el[2];
+  double e = el[3];
+  if (e == 0.0) {
+    sincos_reduced(reduce_2pi(M), sf, cf);
+  } else {
+    kepler_solve(M, e, sf, cf);
+  }
+}
+
+// One light-curve sample: returns lc = s(b, ror) . cl - 1 for z > 0, else exactly 0
+// (limb_dark.py:216-252).  With kGrad, ACCUMULATES w * d lc/d(t0,tref,n,e,cosw,sinw,cosi,
+// sini,aor,ror) into g[10] and w * s into gs[3] (= w * d lc / d cl).
+template <bool kGrad>
+XO_HD double lc_point(const double *el, const double *cl, double tt, double w, double *g, double *gs) {
+  double sf, cf, tm;
+  true_anomaly(el, tt, sf, cf, tm);
+  const double e = el[3], cw = el[4], sw = el[5], ci = el[6], si = el[7], aor = el[8], ror = el[9];
+  double ome2 = (1.0 - e) * (1.0 + e);
+  double opc = fma(e, cf, 1.0);
+  double ropc = rcp(opc);
+  double rr = aor * ome2 * ropc;  // |r| / R_star   (keplerian.py:403 with a -> -a)
+  double cwf = cw * cf - sw * sf;
+  double swf = sw * cf + cw * sf;
+  double z = rr * si * swf;  // Z / R_star > 0 <=> in front of the star (limb_dark.py:252)
+  if (!(z > 0.0)) return 0.0;
+  double ci2 = ci * ci;
+  double h = fma(cwf, cwf, ci2 * swf * swf);
+  double sh = sqrt(h);
+  double b = rr * sh;
+  if (b >= 1.0 + ror) return 0.0;
+  double S[3], B[3], R[3];
+  qsv<kGrad>(b, ror, S, B, R);
+  double lc = fma(S[0], cl[0], fma(S[1], cl[1], S[2] * cl[2])) - 1.0;
+  if (!kGrad) return lc;
+  gs[0] = fma(w, S[0], gs[0]);
+  gs[1] = fma(w, S[1], gs[1]);
+  gs[2] = fma(w, S[2], gs[2]);
+  double dldb = w * fma(B[0], cl[0], fma(B[1], cl[1], B[2] * cl[2]));
+  double dldr = w * fma(R[0], cl[0], fma(R[1], cl[1], R[2] * cl[2]));
+  double db_drr = sh;
+  double db_dcwf = 0.0, db_dswf = 0.0, db_dci = 0.0;
+  if (sh > 0.0) {
+    double rsh = rr * rcp(sh);
+    db_dcwf = rsh * cwf;
+    db_dswf = rsh * ci2 * swf;
+    db_dci = rsh * ci * swf * swf;
+  }
+  double rome2 = rcp(ome2);
+  double dfdM = opc * opc * rome2 * sqrt(rome2);
+  double dfde = (2.0 + e * cf) * sf * rome2;
+  double drr_dcf = -rr * e * ropc;
+  double drr_de = aor * (-2.0 * e * opc - ome2 * cf) * ropc * ropc;
+  double db_dcf = db_drr * drr_dcf + db_dcwf * cw + db_dswf * sw;
+  double db_dsf = db_dswf * cw - db_dcwf * sw;
+  double db_df = db_dsf * cf - db_dcf * sf;
+  double dl_dM = dldb * db_df * dfdM;
+  double gt = -dl_dM * el[2];
+  g[0] += gt;
+  g[1] += gt;
+  g[2] = fma(dl_dM, tm, g[2]);
+  g[3] = fma(dldb, db_df * dfde + db_drr * drr_de, g[3]);
+  g[4] = fma(dldb, db_dcwf * cf + db_dswf * sf, g[4]);
+  g[5] = fma(dldb, db_dswf * cf - db_dcwf * sf, g[5]);
+  g[6] = fma(dldb, db_dci, g[6]);
+  g[8] = fma(dldb, db_drr * rr * rcp(aor), g[8]);
+  g[9] += dldr;
+  return lc;
+}
+
+}  // namespace xo

@@ -1,0 +1,290 @@
+// xo_ops.cu -- the three reference ops as standalone sm_100a kernels + their C ABI.
+//   kepler                (replaces /root/reference/src/exoplanet/orbits/keplerian.py:333)
+//   quad_solution_vector  (replaces /root/reference/src/exoplanet/light_curves/limb_dark.py:24)
+//   contact_points        (replaces /root/reference/src/exoplanet/orbits/keplerian.py:744-753)
+// All are elementwise fp64: no tensor cores, no shared memory needed; the levers are
+// coalesced 16-byte loads/stores, two independent elements per thread for ILP, streaming
+// cache hints (no reuse), and a grid sized as a multiple of the SM count.
+#include <cuda_runtime.h>
+
+#include "xo_common.cuh"
+#include "xo_math.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ double2 ld2(const double *p) { return __ldcs(reinterpret_cast<const double2 *>(p)); }
+__device__ __forceinline__ void st2(double *p, double a, double b) { __stcs(reinterpret_cast<double2 *>(p), make_double2(a, b)); }
+
+// ---- kepler ---------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) kepler_fwd_kernel(const double *__restrict__ M, const double *__restrict__ e,
+                                                              double *__restrict__ sinf, double *__restrict__ cosf,
+                                                              int64_t n, int64_t e_inner) {
+  const int64_t npair = n >> 1;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npair; i += stride) {
+    double2 m = ld2(M + 2 * i);
+    double e0, e1;
+    if (e_inner == 1) {
+      double2 ee = ld2(e + 2 * i);
+      e0 = ee.x;
+      e1 = ee.y;
+    } else {
+      e0 = __ldg(e + (2 * i) / e_inner);
+      e1 = __ldg(e + (2 * i + 1) / e_inner);
+    }
+    double s0, c0, s1, c1;
+    xo::kepler_solve(m.x, e0, s0, c0);
+    xo::kepler_solve(m.y, e1, s1, c1);
+    st2(sinf + 2 * i, s0, s1);
+    st2(cosf + 2 * i, c0, c1);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    int64_t i = n - 1;
+    double s, c;
+    xo::kepler_solve(M[i], e[i / e_inner], s, c);
+    sinf[i] = s;
+    cosf[i] = c;
+  }
+}
+
+// unaligned fallback (pointer not 16-byte aligned): one element per thread
+__global__ void __launch_bounds__(kThreads) kepler_fwd_kernel_scalar(const double *__restrict__ M,
+                                                                     const double *__restrict__ e,
+                                                                     double *__restrict__ sinf,
+                                                                     double *__restrict__ cosf, int64_t n,
+                                                                     int64_t e_inner) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double s, c;
+    xo::kepler_solve(M[i], e[i / e_inner], s, c);
+    sinf[i] = s;
+    cosf[i] = c;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) kepler_vjp_kernel(const double *__restrict__ sinf,
+                                                              const double *__restrict__ cosf,
+                                                              const double *__restrict__ e,
+                                                              const double *__restrict__ bs,
+                                                              const double *__restrict__ bc, double *__restrict__ bM,
+                                                              double *__restrict__ be, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double sf = __ldcs(sinf + i), cf = __ldcs(cosf + i), ee = __ldcs(e + i);
+    double dfdM, dfde;
+    xo::kepler_jac(sf, cf, ee, dfdM, dfde);
+    double bf = __ldcs(bs + i) * cf - __ldcs(bc + i) * sf;
+    __stcs(bM + i, bf * dfdM);
+    __stcs(be + i, bf * dfde);
+  }
+}
+
+// ---- quad_solution_vector --------------------------------------------------
+// One point per thread; the [n][3] outputs are staged through shared memory so each
+// warp writes 768 contiguous bytes with fully coalesced 8-byte stores.
+template <bool kJac>
+__global__ void __launch_bounds__(kThreads) qsv_fwd_kernel(const double *__restrict__ b, const double *__restrict__ r,
+                                                           double *__restrict__ s, double *__restrict__ dsdb,
+                                                           double *__restrict__ dsdr, int64_t n) {
+  __shared__ double stage[(kJac ? 3 : 1) * 3 * kThreads];
+  const int64_t tiles = (n + kThreads - 1) / kThreads;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t base = tile * kThreads;
+    const int64_t i = base + threadIdx.x;
+    double S[3] = {0, 0, 0}, B[3] = {0, 0, 0}, R[3] = {0, 0, 0};
+    if (i < n) xo::qsv<kJac>(__ldcs(b + i), __ldcs(r + i), S, B, R);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      stage[3 * threadIdx.x + k] = S[k];
+      if (kJac) {
+        stage[3 * kThreads + 3 * threadIdx.x + k] = B[k];
+        stage[6 * kThreads + 3 * threadIdx.x + k] = R[k];
+      }
+    }
+    __syncthreads();
+    const int64_t cnt = min((int64_t)kThreads, n - base) * 3;
+    for (int64_t j = threadIdx.x; j < cnt; j += kThreads) {
+      __stcs(s + 3 * base + j, stage[j]);
+      if (kJac) {
+        __stcs(dsdb + 3 * base + j, stage[3 * kThreads + j]);
+        __stcs(dsdr + 3 * base + j, stage[6 * kThreads + j]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) qsv_vjp_kernel(const double *__restrict__ bs, const double *__restrict__ dsdb,
+                                                           const double *__restrict__ dsdr, double *__restrict__ bb,
+                                                           double *__restrict__ br, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double g0 = bs[3 * i], g1 = bs[3 * i + 1], g2 = bs[3 * i + 2];
+    bb[i] = g0 * dsdb[3 * i] + g1 * dsdb[3 * i + 1] + g2 * dsdb[3 * i + 2];
+    br[i] = g0 * dsdr[3 * i] + g1 * dsdr[3 * i + 1] + g2 * dsdr[3 * i + 2];
+  }
+}
+
+// ---- contact_points --------------------------------------------------------
+// g(u) = p^2 (sin^2 u + cos^2 i cos^2 u) - L^2 (1 + e cos f)^2,  f = pi/2 - w + u.
+// One thread per planet; bracketed Newton (never leaves [lo, hi]), bounded iterations.
+__device__ __forceinline__ void cp_eval(double u, double p2, double L2, double e, double cw, double sw, double ci2,
+                                        double &g, double &dg) {
+  double su, cu;
+  sincos(u, &su, &cu);
+  double cf = sw * cu - cw * su;
+  double dcf = -sw * su - cw * cu;
+  double opc = 1.0 + e * cf;
+  g = p2 * (su * su + ci2 * cu * cu) - L2 * opc * opc;
+  dg = 2.0 * p2 * su * cu * (1.0 - ci2) - 2.0 * L2 * opc * e * dcf;
+}
+
+__device__ int cp_solve(double a, double e, double cw, double sw, double ci, double L, double &Ml, double &Mr) {
+  const double p = a * (1.0 - e) * (1.0 + e), p2 = p * p, L2 = L * L, ci2 = ci * ci;
+  Ml = Mr = 0.0;
+  double g0, dg0;
+  cp_eval(0.0, p2, L2, e, cw, sw, ci2, g0, dg0);
+  if (!(g0 < 0.0)) return 1;
+  // circular-like estimate of the half-angle, used to size the first bracket
+  double opc0 = 1.0 + e * sw;
+  double arg = (L2 * opc0 * opc0 / p2 - ci2) / fmax(1.0 - ci2, 1e-300);
+  double u0 = (arg > 0.0 && arg < 1.0) ? asin(sqrt(arg)) : 0.25 * xo::kPi;
+  double root[2];
+#pragma unroll 1
+  for (int side = 0; side < 2; ++side) {
+    const double dir = side ? 1.0 : -1.0;
+    double lo = 0.0, hi = fmin(1.5 * u0 + 1e-6, 0.5 * xo::kPi);
+    double g, dg;
+    bool found = false;
+#pragma unroll 1
+    for (int it = 0; it < 64; ++it) {
+      cp_eval(dir * hi, p2, L2, e, cw, sw, ci2, g, dg);
+      if (g > 0.0) {
+        found = true;
+        break;
+      }
+      if (hi >= 0.5 * xo::kPi) break;
+      lo = hi;
+      hi = fmin(1.5 * hi + 1e-6, 0.5 * xo::kPi);
+    }
+    if (!found) return 2;
+    double x = 0.5 * (lo + hi);
+#pragma unroll 1
+    for (int it = 0; it < 100; ++it) {
+      cp_eval(dir * x, p2, L2, e, cw, sw, ci2, g, dg);
+      if (g > 0.0) hi = x; else lo = x;
+      double dx = -g / (dir * dg);
+      double xn = x + dx;
+      if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
+      if (fabs(xn - x) <= 4e-16 * fabs(x) || hi - lo <= 4e-16 * hi) {
+        x = xn;
+        break;
+      }
+      x = xn;
+    }
+    root[side] = dir * x;
+  }
+#pragma unroll 1
+  for (int side = 0; side < 2; ++side) {
+    double su, cu;
+    sincos(root[side], &su, &cu);
+    double cf = sw * cu - cw * su;  // cos(f0 + u), cos f0 = sin w, sin f0 = cos w
+    double sf = cw * cu + sw * su;
+    double den = 1.0 + e * cf;
+    double sE = sqrt((1.0 - e) * (1.0 + e)) * sf / den, cE = (e + cf) / den;
+    double M = atan2(sE, cE) - e * sE;
+    if (side) Mr = M; else Ml = M;
+  }
+  return 0;
+}
+
+__global__ void contact_points_kernel(const double *a, const double *e, const double *cw, const double *sw,
+                                      const double *ci, const double *si, const double *L, double *Ml, double *Mr,
+                                      int32_t *flag, int64_t n) {
+  (void)si;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double l, r;
+  flag[i] = cp_solve(a[i], e[i], cw[i], sw[i], ci[i], L[i], l, r);
+  Ml[i] = l;
+  Mr[i] = r;
+}
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int xo_kepler_fwd_bcast(const double *M, const double *e, int64_t e_inner, double *sinf, double *cosf, int64_t n,
+                        void *stream) {
+  if (n < 0 || e_inner < 1) return XO_EINVAL;
+  if (n == 0) return 0;
+  if (!M || !e || !sinf || !cosf) return XO_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int sms = xo::sm_count();
+  bool vec = aligned16(M) && aligned16(sinf) && aligned16(cosf) && (e_inner != 1 || aligned16(e));
+  if (vec) {
+    int64_t work = (n / 2 + kThreads - 1) / kThreads;
+    int grid = (int)xo::clamp_grid(work, sms, 8);
+    kepler_fwd_kernel<<<grid, kThreads, 0, st>>>(M, e, sinf, cosf, n, e_inner);
+  } else {
+    int64_t work = (n + kThreads - 1) / kThreads;
+    int grid = (int)xo::clamp_grid(work, sms, 8);
+    kepler_fwd_kernel_scalar<<<grid, kThreads, 0, st>>>(M, e, sinf, cosf, n, e_inner);
+  }
+  return xo::launch_status();
+}
+
+int xo_kepler_fwd(const double *M, const double *e, double *sinf, double *cosf, int64_t n, void *stream) {
+  return xo_kepler_fwd_bcast(M, e, 1, sinf, cosf, n, stream);
+}
+
+int xo_kepler_vjp(const double *sinf, const double *cosf, const double *e, const double *bsinf, const double *bcosf,
+                  double *bM, double *be, int64_t n, void *stream) {
+  if (n < 0) return XO_EINVAL;
+  if (n == 0) return 0;
+  if (!sinf || !cosf || !e || !bsinf || !bcosf || !bM || !be) return XO_EINVAL;
+  int grid = (int)xo::clamp_grid((n + kThreads - 1) / kThreads, xo::sm_count(), 8);
+  kepler_vjp_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(sinf, cosf, e, bsinf, bcosf, bM, be, n);
+  return xo::launch_status();
+}
+
+int xo_qsv_fwd(const double *b, const double *r, double *s, double *dsdb, double *dsdr, int64_t n, void *stream) {
+  if (n < 0) return XO_EINVAL;
+  if (n == 0) return 0;
+  if (!b || !r || !s || ((dsdb == nullptr) != (dsdr == nullptr))) return XO_EINVAL;
+  int grid = (int)xo::clamp_grid((n + kThreads - 1) / kThreads, xo::sm_count(), 4);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dsdb)
+    qsv_fwd_kernel<true><<<grid, kThreads, 0, st>>>(b, r, s, dsdb, dsdr, n);
+  else
+    qsv_fwd_kernel<false><<<grid, kThreads, 0, st>>>(b, r, s, nullptr, nullptr, n);
+  return xo::launch_status();
+}
+
+int xo_qsv_vjp(const double *bs, const double *dsdb, const double *dsdr, double *bb, double *br, int64_t n, void *stream) {
+  if (n < 0) return XO_EINVAL;
+  if (n == 0) return 0;
+  if (!bs || !dsdb || !dsdr || !bb || !br) return XO_EINVAL;
+  int grid = (int)xo::clamp_grid((n + kThreads - 1) / kThreads, xo::sm_count(), 8);
+  qsv_vjp_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(bs, dsdb, dsdr, bb, br, n);
+  return xo::launch_status();
+}
+
+int xo_contact_points(const double *a, const double *e, const double *cosw, const double *sinw, const double *cosi,
+                      const double *sini, const double *L, double *M_left, double *M_right, int32_t *flag, int64_t n,
+                      void *stream) {
+  if (n < 0) return XO_EINVAL;
+  if (n == 0) return 0;
+  if (!a || !e || !cosw || !sinw || !cosi || !sini || !L || !M_left || !M_right || !flag) return XO_EINVAL;
+  int threads = 64;
+  int grid = (int)((n + threads - 1) / threads);
+  contact_points_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(a, e, cosw, sinw, cosi, sini, L, M_left,
+                                                                                M_right, flag, n);
+  return xo::launch_status();
+}
+
+}  // extern "C"

@@ -1,0 +1,494 @@
+// xo_transit.cu -- the fused L3 path over a (chains x planets x cadences) batch.
+//
+// Replaces, in one launch each, the graph PyTensor builds from
+//   /root/reference/src/exoplanet/light_curves/limb_dark.py:163-232 (get_light_curve)
+//   /root/reference/src/exoplanet/orbits/keplerian.py:324-334, 380-409 (anomaly, position)
+//   /root/reference/src/exoplanet/orbits/keplerian.py:729-775 (in_transit window)
+// plus the Gaussian likelihood and the whole reverse pass.
+//
+// Data layout in HBM: t, y, ivar are [N] and shared by all chains (L2-resident after
+// the first chain touches them); per-chain state is the element block [C][P][16],
+// cl [C][3], mean [C]; outputs are O(#params) per chain.
+//
+// Design of the logp+grad kernel (the dominant kernel):
+//  * one CTA = 4 independent warps of one chain; the chain's element block, limb-darkening
+//    vector and exposure stencil are staged once in shared memory;
+//  * each warp sweeps a contiguous range of cadences 32 at a time with coalesced loads,
+//    accumulates the out-of-transit part of the likelihood, and tests the in_transit
+//    window per planet (two FMAs and a floor - no Kepler solve);
+//  * in-window (cadence, planet) pairs are appended (ballot + prefix popcount, i.e. in
+//    a fixed order) to a per-warp, per-planet queue in shared memory; whenever a queue
+//    holds >= 32 entries the warp drains 32 of them with all lanes busy on the expensive
+//    part (Kepler solve -> projection -> limb-darkening integral -> analytic VJP);
+//  * gradient sums use fixed-order shuffle trees and fixed-order accumulation, so results
+//    are bit-reproducible run to run; a second tiny kernel folds the per-warp partials.
+#include <cuda_runtime.h>
+
+#include "xo_common.cuh"
+#include "xo_math.cuh"
+
+namespace {
+
+constexpr int kWarps = 4;
+constexpr int kThreads = kWarps * 32;
+constexpr int kQueue = 64;
+constexpr int kNBase = 5;  // lp, gmean, gcl[3]
+constexpr unsigned kFull = 0xffffffffu;
+
+struct ChainSmem {
+  double elem[XO_MAX_PLANETS][XO_NEL];
+  double rperiod[XO_MAX_PLANETS];
+  double cl[3];
+  double mean;
+  double dtk[XO_MAX_STENCIL];
+  double wk[XO_MAX_STENCIL];
+};
+
+__device__ __forceinline__ void stage_chain(ChainSmem &sm, const double *elem, const double *cl, const double *mean,
+                                            const double *dtk, const double *wk, int64_t c, int P, int K) {
+  for (int i = threadIdx.x; i < P * XO_NEL; i += blockDim.x) sm.elem[i / XO_NEL][i % XO_NEL] = elem[c * P * XO_NEL + i];
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    sm.dtk[i] = dtk[i];
+    sm.wk[i] = wk[i];
+  }
+  if (threadIdx.x < 3) sm.cl[threadIdx.x] = cl[3 * c + threadIdx.x];
+  if (threadIdx.x == 3) sm.mean = mean ? mean[c] : 0.0;
+  __syncthreads();
+  if (threadIdx.x < P) sm.rperiod[threadIdx.x] = 1.0 / sm.elem[threadIdx.x][XO_EL_PERIOD];
+  __syncthreads();
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// light curve forward: lc[C][N][P]
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transit_lc_fwd_kernel(const double *__restrict__ t, int64_t N,
+                                                             const double *__restrict__ elem,
+                                                             const double *__restrict__ cl, int P,
+                                                             const double *__restrict__ dtk,
+                                                             const double *__restrict__ wk, int K,
+                                                             double *__restrict__ lc) {
+  __shared__ ChainSmem sm;
+  const int64_t c = blockIdx.y;
+  stage_chain(sm, elem, cl, nullptr, dtk, wk, c, P, K);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+    const double tt = __ldg(t + i);
+    for (int p = 0; p < P; ++p) {
+      double acc = 0.0;
+      if (xo::in_window(sm.elem[p], sm.rperiod[p], tt)) {
+        for (int k = 0; k < K; ++k)
+          acc = fma(sm.wk[k], xo::lc_point<false>(sm.elem[p], sm.cl, tt + sm.dtk[k], 0.0, nullptr, nullptr), acc);
+      }
+      __stcs(lc + (c * N + i) * P + p, acc);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// logp + grad (see header comment)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) transit_logp_grad_kernel(
+    const double *__restrict__ t, const double *__restrict__ y, const double *__restrict__ ivar, int64_t N,
+    const double *__restrict__ elem, const double *__restrict__ cl, const double *__restrict__ mean, int P,
+    const double *__restrict__ dtk, const double *__restrict__ wk, int K, int64_t L, int slots,
+    double *__restrict__ partial) {
+  __shared__ ChainSmem sm;
+  __shared__ uint32_t queue[kWarps][XO_MAX_PLANETS][kQueue];
+  __shared__ double gacc[kWarps][XO_MAX_PLANETS][XO_NGRAD];
+  const int64_t c = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = blockIdx.x * kWarps + warp;
+  stage_chain(sm, elem, cl, mean, dtk, wk, c, P, K);
+  for (int i = lane; i < XO_MAX_PLANETS * XO_NGRAD; i += 32) (&gacc[warp][0][0])[i] = 0.0;
+  __syncwarp();
+
+  const int nacc = kNBase + P * XO_NGRAD;
+  double lp = 0.0, gm = 0.0, gc0 = 0.0, gc1 = 0.0, gc2 = 0.0;
+  int cnt = 0;  // lane p holds the fill level of queue p
+  const double mean_c = sm.mean;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
+  // drain m (<= 32) entries from the front of queue p
+  auto drain = [&](int p, int m) {
+    double g[XO_NGRAD];
+#pragma unroll
+    for (int j = 0; j < XO_NGRAD; ++j) g[j] = 0.0;
+    if (lane < m) {
+      const uint32_t idx = queue[warp][p][lane];
+      const double tt = __ldg(t + idx), yy = __ldg(y + idx), iv = __ldg(ivar + idx);
+      double gs[3] = {0.0, 0.0, 0.0};
+      double ltot = 0.0;
+      bool owner = true;  // the lowest in-window planet owns the per-cadence terms
+      for (int k = 0; k < K; ++k) {
+        const double w = sm.wk[k];
+        ltot = fma(w, xo::lc_point<true>(sm.elem[p], sm.cl, tt + sm.dtk[k], w, g, gs), ltot);
+      }
+      for (int q = 0; q < P; ++q) {
+        if (q == p || !xo::in_window(sm.elem[q], sm.rperiod[q], tt)) continue;
+        if (q < p) owner = false;
+        for (int k = 0; k < K; ++k)
+          ltot = fma(sm.wk[k], xo::lc_point<false>(sm.elem[q], sm.cl, tt + sm.dtk[k], 0.0, nullptr, nullptr), ltot);
+      }
+      const double r0 = yy - mean_c;
+      const double wres = iv * (r0 - ltot);
+#pragma unroll
+      for (int j = 0; j < XO_NGRAD; ++j) g[j] *= wres;
+      gc0 = fma(wres, gs[0], gc0);
+      gc1 = fma(wres, gs[1], gc1);
+      gc2 = fma(wres, gs[2], gc2);
+      if (owner) {  // -1/2 iv (res^2 - r0^2) and iv (res - r0), without cancellation
+        lp = fma(0.5 * iv * ltot, 2.0 * r0 - ltot, lp);
+        gm = fma(-iv, ltot, gm);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < XO_NGRAD; ++j) {
+      double v = warp_sum(g[j]);
+      if (lane == 0) gacc[warp][p][j] += v;
+    }
+    // move the tail to the front
+    __syncwarp();
+    uint32_t a = (lane + m < kQueue) ? queue[warp][p][lane + m] : 0u;
+    uint32_t b = (lane + 32 + m < kQueue) ? queue[warp][p][lane + 32 + m] : 0u;
+    __syncwarp();
+    queue[warp][p][lane] = a;
+    queue[warp][p][lane + 32] = b;
+    __syncwarp();
+  };
+
+  const int64_t start = (int64_t)slot * L;
+  const int64_t end = min(start + L, N);
+  for (int64_t base = start; base < end; base += 32) {
+    const int64_t i = base + lane;
+    const bool valid = i < end;
+    double tt = 0.0, yy = 0.0, iv = 0.0;
+    if (valid) {
+      tt = __ldg(t + i);
+      yy = __ldg(y + i);
+      iv = __ldg(ivar + i);
+    }
+    const double r0 = yy - mean_c;
+    const double wr = iv * r0;
+    lp = fma(-0.5 * wr, r0, lp);
+    gm += wr;
+    for (int p = 0; p < P; ++p) {
+      const bool inw = valid && xo::in_window(sm.elem[p], sm.rperiod[p], tt);
+      const uint32_t mask = __ballot_sync(kFull, inw);
+      if (mask == 0u) continue;
+      int fill = __shfl_sync(kFull, cnt, p);
+      if (inw) queue[warp][p][fill + __popc(mask & lt_mask)] = (uint32_t)i;
+      fill += __popc(mask);
+      __syncwarp();
+      if (fill >= 32) {
+        drain(p, 32);
+        fill -= 32;
+      }
+      if (lane == p) cnt = fill;
+    }
+  }
+  for (int p = 0; p < P; ++p) {
+    int fill = __shfl_sync(kFull, cnt, p);
+    if (fill > 0) drain(p, fill);
+  }
+  lp = warp_sum(lp);
+  gm = warp_sum(gm);
+  gc0 = warp_sum(gc0);
+  gc1 = warp_sum(gc1);
+  gc2 = warp_sum(gc2);
+  __syncwarp();
+  double *out = partial + ((int64_t)c * slots + slot) * nacc;
+  if (lane == 0) {
+    out[0] = lp;
+    out[1] = gm;
+    out[2] = gc0;
+    out[3] = gc1;
+    out[4] = gc2;
+  }
+  for (int i = lane; i < P * XO_NGRAD; i += 32) out[kNBase + i] = gacc[warp][i / XO_NGRAD][i % XO_NGRAD];
+}
+
+// fold per-warp partials in slot order: out[c][j] = sum_s partial[c][s][j]
+__global__ void fold_partials_kernel(const double *__restrict__ partial, int slots, int nacc, int64_t C, int P,
+                                     double lognorm, double *__restrict__ logp, double *__restrict__ gel,
+                                     double *__restrict__ gcl, double *__restrict__ gmean) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * nacc) return;
+  const int64_t c = idx / nacc;
+  const int j = (int)(idx % nacc);
+  const double *src = partial + c * slots * nacc + j;
+  double acc = 0.0;
+  for (int s = 0; s < slots; ++s) acc += src[(int64_t)s * nacc];
+  if (j == 0)
+    logp[c] = acc + lognorm;
+  else if (j == 1)
+    gmean[c] = acc;
+  else if (j < kNBase)
+    gcl[3 * c + (j - 2)] = acc;
+  else
+    gel[c * P * XO_NGRAD + (j - kNBase)] = acc;
+}
+
+// ---------------------------------------------------------------------------
+// orbit_eval: relative position / R_star and RV shape, thread per (c, n, p)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) orbit_eval_kernel(const double *__restrict__ t, int64_t N,
+                                                         const double *__restrict__ elem, int P,
+                                                         double *__restrict__ X, double *__restrict__ Y,
+                                                         double *__restrict__ Z, double *__restrict__ rv) {
+  __shared__ double el[XO_MAX_PLANETS][XO_NEL];
+  const int64_t c = blockIdx.y;
+  for (int i = threadIdx.x; i < P * XO_NEL; i += blockDim.x) el[i / XO_NEL][i % XO_NEL] = elem[c * P * XO_NEL + i];
+  __syncthreads();
+  const int64_t total = N * P;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += stride) {
+    const int64_t i = j / P;
+    const int p = (int)(j % P);
+    const double *e = el[p];
+    double sf, cf, tm;
+    xo::true_anomaly(e, __ldg(t + i), sf, cf, tm);
+    const double ecc = e[XO_EL_ECC], cw = e[XO_EL_COSW], sw = e[XO_EL_SINW];
+    const double rr = e[XO_EL_AOR] * (1.0 - ecc) * (1.0 + ecc) / fma(ecc, cf, 1.0);
+    const double cwf = cw * cf - sw * sf, swf = sw * cf + cw * sf;
+    const int64_t o = c * total + j;
+    if (X) __stcs(X + o, -rr * cwf);
+    if (Y) __stcs(Y + o, -rr * e[XO_EL_COSI] * swf);
+    if (Z) __stcs(Z + o, rr * e[XO_EL_SINI] * swf);
+    if (rv) __stcs(rv + o, e[XO_EL_KRV] * fma(ecc, cw, cwf));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// RV logp + grad.  blockDim = (64, P): thread (x, p) owns planet p of cadence x of each
+// 64-cadence tile, so the Kepler solution stays in registers between the forward sum
+// over planets (through shared memory) and the gradient accumulation.
+// ---------------------------------------------------------------------------
+constexpr int kRvTile = 64;
+__global__ void rv_logp_grad_kernel(const double *__restrict__ t, const double *__restrict__ y,
+                                    const double *__restrict__ ivar, int64_t N, const double *__restrict__ elem,
+                                    const double *__restrict__ gamma, int P, int64_t L, int slots,
+                                    double *__restrict__ partial) {
+  __shared__ double el[XO_MAX_PLANETS][XO_NEL];
+  __shared__ double contrib[2][XO_MAX_PLANETS][kRvTile];
+  __shared__ double red[XO_MAX_PLANETS][kRvTile / 32][XO_NGRAD_RV + 2];
+  const int64_t c = blockIdx.y;
+  const int x = threadIdx.x, p = threadIdx.y;
+  const int tid = p * kRvTile + x;
+  for (int i = tid; i < P * XO_NEL; i += kRvTile * P) el[i / XO_NEL][i % XO_NEL] = elem[c * P * XO_NEL + i];
+  __syncthreads();
+  const double *e = el[p];
+  const double nn = e[XO_EL_N], ecc = e[XO_EL_ECC], cw = e[XO_EL_COSW], sw = e[XO_EL_SINW], Kp = e[XO_EL_KRV];
+  const double gam = gamma[c];
+  double acc[XO_NGRAD_RV];
+#pragma unroll
+  for (int j = 0; j < XO_NGRAD_RV; ++j) acc[j] = 0.0;
+  double lp = 0.0, gg = 0.0;
+  const int64_t start = (int64_t)blockIdx.x * L, end = min(start + L, N);
+  int buf = 0;
+  for (int64_t base = start; base < end; base += kRvTile, buf ^= 1) {
+    const int64_t i = base + x;
+    const bool valid = i < end;
+    double sf = 0.0, cf = 1.0, tm = 0.0, shape = 0.0, cwf = 0.0, swf = 0.0;
+    if (valid) {
+      xo::true_anomaly(e, __ldg(t + i), sf, cf, tm);
+      cwf = cw * cf - sw * sf;
+      swf = sw * cf + cw * sf;
+      shape = fma(ecc, cw, cwf);
+    }
+    contrib[buf][p][x] = Kp * shape;
+    __syncthreads();
+    if (valid) {
+      double model = gam;
+      for (int q = 0; q < P; ++q) model += contrib[buf][q][x];
+      const double res = __ldg(y + i) - model;
+      const double wres = __ldg(ivar + i) * res;
+      if (p == 0) {
+        lp = fma(-0.5 * res, wres, lp);
+        gg += wres;
+      }
+      double dfdM, dfde;
+      xo::kepler_jac(sf, cf, ecc, dfdM, dfde);
+      const double gM = -Kp * swf * dfdM * wres;
+      acc[0] = fma(gM, -nn, acc[0]);
+      acc[2] = fma(gM, tm, acc[2]);
+      acc[3] = fma(wres * Kp, fma(-swf, dfde, cw), acc[3]);
+      acc[4] = fma(wres * Kp, cf + ecc, acc[4]);
+      acc[5] = fma(wres * Kp, -sf, acc[5]);
+      acc[6] = fma(wres, shape, acc[6]);
+    }
+  }
+  acc[1] = acc[0];
+  // block reduce per planet row (2 warps per row), fixed order
+  const int wrow = x >> 5, lane = x & 31;
+#pragma unroll
+  for (int j = 0; j < XO_NGRAD_RV; ++j) {
+    double v = warp_sum(acc[j]);
+    if (lane == 0) red[p][wrow][j] = v;
+  }
+  lp = warp_sum(lp);
+  gg = warp_sum(gg);
+  if (lane == 0) {
+    red[p][wrow][XO_NGRAD_RV] = lp;
+    red[p][wrow][XO_NGRAD_RV + 1] = gg;
+  }
+  __syncthreads();
+  const int nacc = 2 + P * XO_NGRAD_RV;
+  double *out = partial + ((int64_t)c * slots + blockIdx.x) * nacc;
+  if (x < XO_NGRAD_RV) out[2 + p * XO_NGRAD_RV + x] = red[p][0][x] + red[p][1][x];
+  if (p == 0 && x == 0) {
+    out[0] = red[0][0][XO_NGRAD_RV] + red[0][1][XO_NGRAD_RV];
+    out[1] = red[0][0][XO_NGRAD_RV + 1] + red[0][1][XO_NGRAD_RV + 1];
+  }
+}
+
+__global__ void fold_rv_kernel(const double *__restrict__ partial, int slots, int nacc, int64_t C, int P, double lognorm,
+                               double *__restrict__ logp, double *__restrict__ grv, double *__restrict__ ggamma) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * nacc) return;
+  const int64_t c = idx / nacc;
+  const int j = (int)(idx % nacc);
+  const double *src = partial + c * slots * nacc + j;
+  double acc = 0.0;
+  for (int s = 0; s < slots; ++s) acc += src[(int64_t)s * nacc];
+  if (j == 0)
+    logp[c] = acc + lognorm;
+  else if (j == 1)
+    ggamma[c] = acc;
+  else
+    grv[c * P * XO_NGRAD_RV + (j - 2)] = acc;
+}
+
+// work split for the logp kernels: slots (warps or CTAs) per chain and cadences per slot
+struct Split {
+  int slots;
+  int64_t L;
+};
+inline Split split_transit(int64_t N, int64_t C) {
+  const int sms = xo::sm_count();
+  // aim at ~24 resident warps per SM over the whole launch, at least 256 cadences per warp
+  int64_t target = ((int64_t)sms * 24 + C - 1) / C;
+  int64_t maxw = (N + 255) / 256;
+  int64_t w = target < 1 ? 1 : (target > maxw ? maxw : target);
+  if (w < 1) w = 1;
+  w = ((w + kWarps - 1) / kWarps) * kWarps;  // whole CTAs
+  int64_t L = (N + w - 1) / w;
+  L = ((L + 31) / 32) * 32;
+  return Split{(int)w, L};
+}
+inline Split split_rv(int64_t N, int64_t C) {
+  const int sms = xo::sm_count();
+  int64_t target = ((int64_t)sms * 6 + C - 1) / C;
+  int64_t maxc = (N + 4 * kRvTile - 1) / (4 * kRvTile);
+  int64_t s = target < 1 ? 1 : (target > maxc ? maxc : target);
+  if (s < 1) s = 1;
+  int64_t L = (N + s - 1) / s;
+  L = ((L + kRvTile - 1) / kRvTile) * kRvTile;
+  return Split{(int)s, L};
+}
+
+inline int check_batch(int64_t N, int64_t C, int64_t P) {
+  if (N < 0 || C < 0 || P < 0) return XO_EINVAL;
+  if (P > XO_MAX_PLANETS) return XO_ERANGE;
+  if (C > 65535) return XO_ERANGE;  // gridDim.y
+  if (N >= ((int64_t)1 << 32)) return XO_ERANGE;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int xo_transit_lc_fwd(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
+                      const double *dtk, const double *wk, int K, double *lc, void *stream) {
+  if (int rc = check_batch(N, C, P)) return rc;
+  if (K < 1 || K > XO_MAX_STENCIL) return XO_ERANGE;
+  if (N == 0 || C == 0 || P == 0) return 0;
+  if (!t || !elem || !cl || !dtk || !wk || !lc) return XO_EINVAL;
+  const int sms = xo::sm_count();
+  int64_t per_chain = (N + 255) / 256;
+  int64_t want = ((int64_t)sms * 8 + C - 1) / C;
+  int gx = (int)(per_chain < want ? per_chain : want);
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, (unsigned)C);
+  transit_lc_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(t, N, elem, cl, (int)P, dtk, wk, K, lc);
+  return xo::launch_status();
+}
+
+size_t xo_transit_logp_grad_workspace(int64_t N, int64_t C, int64_t P) {
+  if (N <= 0 || C <= 0 || P <= 0) return 0;
+  Split sp = split_transit(N, C);
+  return sizeof(double) * (size_t)C * (size_t)sp.slots * (size_t)(kNBase + P * XO_NGRAD);
+}
+
+int xo_transit_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *elem,
+                         const double *cl, const double *mean, int64_t C, int64_t P, const double *dtk, const double *wk,
+                         int K, double lognorm, double *logp, double *gel, double *gcl, double *gmean, void *workspace,
+                         size_t workspace_bytes, void *stream) {
+  if (int rc = check_batch(N, C, P)) return rc;
+  if (K < 1 || K > XO_MAX_STENCIL) return XO_ERANGE;
+  if (C == 0) return 0;
+  if (N == 0 || P == 0) return XO_EINVAL;
+  if (!t || !y || !ivar || !elem || !cl || !mean || !dtk || !wk || !logp || !gel || !gcl || !gmean || !workspace)
+    return XO_EINVAL;
+  if (workspace_bytes < xo_transit_logp_grad_workspace(N, C, P)) return XO_EWORKSPACE;
+  Split sp = split_transit(N, C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double *partial = static_cast<double *>(workspace);
+  dim3 grid(sp.slots / kWarps, (unsigned)C);
+  transit_logp_grad_kernel<<<grid, kThreads, 0, st>>>(t, y, ivar, N, elem, cl, mean, (int)P, dtk, wk, K, sp.L, sp.slots,
+                                                     partial);
+  const int nacc = kNBase + (int)P * XO_NGRAD;
+  const int64_t tot = C * nacc;
+  fold_partials_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(partial, sp.slots, nacc, C, (int)P, lognorm, logp,
+                                                                      gel, gcl, gmean);
+  return xo::launch_status();
+}
+
+int xo_orbit_eval(const double *t, int64_t N, const double *elem, int64_t C, int64_t P, double *X, double *Y, double *Z,
+                  double *rv, void *stream) {
+  if (int rc = check_batch(N, C, P)) return rc;
+  if (N == 0 || C == 0 || P == 0) return 0;
+  if (!t || !elem) return XO_EINVAL;
+  const int sms = xo::sm_count();
+  int64_t per_chain = (N * P + 255) / 256;
+  int64_t want = ((int64_t)sms * 8 + C - 1) / C;
+  int gx = (int)(per_chain < want ? per_chain : want);
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, (unsigned)C);
+  orbit_eval_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(t, N, elem, (int)P, X, Y, Z, rv);
+  return xo::launch_status();
+}
+
+size_t xo_rv_logp_grad_workspace(int64_t N, int64_t C, int64_t P) {
+  if (N <= 0 || C <= 0 || P <= 0) return 0;
+  Split sp = split_rv(N, C);
+  return sizeof(double) * (size_t)C * (size_t)sp.slots * (size_t)(2 + P * XO_NGRAD_RV);
+}
+
+int xo_rv_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *elem,
+                    const double *gamma, int64_t C, int64_t P, double lognorm, double *logp, double *grv, double *ggamma,
+                    void *workspace, size_t workspace_bytes, void *stream) {
+  if (int rc = check_batch(N, C, P)) return rc;
+  if (C == 0) return 0;
+  if (N == 0 || P == 0) return XO_EINVAL;
+  if (!t || !y || !ivar || !elem || !gamma || !logp || !grv || !ggamma || !workspace) return XO_EINVAL;
+  if (workspace_bytes < xo_rv_logp_grad_workspace(N, C, P)) return XO_EWORKSPACE;
+  Split sp = split_rv(N, C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double *partial = static_cast<double *>(workspace);
+  dim3 grid(sp.slots, (unsigned)C), block(kRvTile, (unsigned)P);
+  rv_logp_grad_kernel<<<grid, block, 0, st>>>(t, y, ivar, N, elem, gamma, (int)P, sp.L, sp.slots, partial);
+  const int nacc = 2 + (int)P * XO_NGRAD_RV;
+  const int64_t tot = C * nacc;
+  fold_rv_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(partial, sp.slots, nacc, C, (int)P, lognorm, logp, grv,
+                                                                ggamma);
+  return xo::launch_status();
+}
+
+}  // extern "C"

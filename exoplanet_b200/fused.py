@@ -1,0 +1,205 @@
+"""Fused (chains x planets x cadences) kernels over PyTorch CUDA tensors.
+
+These swallow the PyTensor graph the reference builds between its three ops:
+``LimbDarkLightCurve.get_light_curve`` (/root/reference/src/exoplanet/light_curves/
+limb_dark.py:99-232) over ``KeplerianOrbit.get_relative_position``
+(orbits/keplerian.py:517-542), the in-transit selection (:708-777), the Gaussian
+likelihood and its whole reverse pass.  Inputs are the per-planet *element block*
+(include/xo_b200.h, ``XO_EL_*``) so the O(P) prologue stays in ordinary autograd.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import NEL, NGRAD, NGRAD_RV
+
+__all__ = ["exposure_stencil", "limb_dark_coeffs", "TransitData", "light_curve", "transit_logp_grad", "TransitLogp",
+           "orbit_eval", "rv_logp_grad", "RvLogp"]
+
+LOG_2PI = 1.8378770664093454835606594728112
+
+
+def _ptr(x):
+    return C.c_void_p(x.data_ptr()) if x is not None else None
+
+
+def exposure_stencil(texp=None, oversample=7, order=0):
+    """(dt_k, w_k) of limb_dark.py:173-198: centred Riemann (0), trapezoid (1), Simpson (2).
+    Returns float64 numpy arrays; dt_k already multiplied by ``texp``."""
+    if texp is None:
+        return np.zeros(1), np.ones(1)
+    n = int(oversample)
+    n += 1 - n % 2
+    w = np.ones(n)
+    if order == 0:
+        x = (np.arange(n) + 0.5) / n - 0.5
+    elif order == 1:
+        x = np.linspace(-0.5, 0.5, n)
+        w[1:-1] = 2.0
+    elif order == 2:
+        x = np.linspace(-0.5, 0.5, n)
+        w[1:-1:2] = 4.0
+        w[2:-1:2] = 2.0
+    else:
+        raise ValueError("order must be <= 2")
+    if n > _lib.MAX_STENCIL:
+        raise ValueError("oversample above the compiled maximum (%d)" % _lib.MAX_STENCIL)
+    return float(texp) * x, w / w.sum()
+
+
+def limb_dark_coeffs(u1, u2):
+    """Normalised Green's-basis vector c (limb_dark.py:11-18); differentiable torch."""
+    c0 = 1.0 - u1 - 1.5 * u2
+    c1 = u1 + 2.0 * u2
+    c2 = -0.25 * u2
+    norm = np.pi * (c0 + c1 / 1.5)
+    return torch.stack([c0, c1, c2], dim=-1) / norm.unsqueeze(-1)
+
+
+class TransitData:
+    """t, y, 1/sigma^2 resident in HBM (shared by every chain) + the data-only constant
+    of the Gaussian log-density: -sum(log sigma) - N/2 log(2 pi)."""
+
+    def __init__(self, t, y=None, yerr=None, device=None):
+        dev = torch.device("cuda" if device is None else device)
+        self.t = torch.as_tensor(np.asarray(t, dtype=np.float64)).to(dev).contiguous()
+        n = self.t.numel()
+        self.y = None if y is None else torch.as_tensor(np.asarray(y, dtype=np.float64)).to(dev).contiguous()
+        if yerr is None:
+            self.ivar = None
+            self.lognorm = 0.0
+        else:
+            sig = np.broadcast_to(np.asarray(yerr, dtype=np.float64), (n,))
+            self.ivar = torch.as_tensor(np.ascontiguousarray(1.0 / sig ** 2)).to(dev)
+            self.lognorm = float(-np.sum(np.log(sig)) - 0.5 * n * LOG_2PI)
+        self.n = n
+        self.device = dev
+
+
+def _stencil_dev(stencil, dev):
+    dtk, wk = stencil
+    return (torch.as_tensor(np.ascontiguousarray(dtk, dtype=np.float64)).to(dev),
+            torch.as_tensor(np.ascontiguousarray(wk, dtype=np.float64)).to(dev))
+
+
+def light_curve(t, elem, cl, stencil=None):
+    """lc[C, N, P] for element blocks elem[C, P, 16] and limb-darkening vectors cl[C, 3]."""
+    lib = _lib.require_cuda()
+    elem = elem.detach().contiguous()
+    cl = cl.detach().contiguous()
+    Cc, P = elem.shape[0], elem.shape[1]
+    dtk, wk = _stencil_dev(stencil or exposure_stencil(), t.device)
+    lc = torch.empty((Cc, t.numel(), P), dtype=torch.float64, device=t.device)
+    with torch.cuda.device(t.device):
+        _lib.check(lib.xo_transit_lc_fwd(_ptr(t), t.numel(), _ptr(elem), _ptr(cl), Cc, P, _ptr(dtk), _ptr(wk), dtk.numel(),
+                                         _ptr(lc), _lib.stream_ptr()), "transit_lc_fwd")
+    return lc
+
+
+def transit_logp_grad(data, elem, cl, mean, stencil=None, workspace=None):
+    """One launch: (logp[C], gel[C,P,10], gcl[C,3], gmean[C])."""
+    lib = _lib.require_cuda()
+    elem = elem.detach().contiguous()
+    cl = cl.detach().contiguous()
+    mean = mean.detach().contiguous()
+    Cc, P = elem.shape[0], elem.shape[1]
+    dev = data.t.device
+    dtk, wk = _stencil_dev(stencil or exposure_stencil(), dev)
+    need = lib.xo_transit_logp_grad_workspace(data.n, Cc, P)
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty(max(need, 8) // 8 + 1, dtype=torch.float64, device=dev)
+    logp = torch.empty(Cc, dtype=torch.float64, device=dev)
+    gel = torch.empty((Cc, P, NGRAD), dtype=torch.float64, device=dev)
+    gcl = torch.empty((Cc, 3), dtype=torch.float64, device=dev)
+    gmean = torch.empty(Cc, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.xo_transit_logp_grad(_ptr(data.t), _ptr(data.y), _ptr(data.ivar), data.n, _ptr(elem), _ptr(cl),
+                                            _ptr(mean), Cc, P, _ptr(dtk), _ptr(wk), dtk.numel(), data.lognorm, _ptr(logp),
+                                            _ptr(gel), _ptr(gcl), _ptr(gmean), _ptr(workspace),
+                                            workspace.numel() * workspace.element_size(), _lib.stream_ptr()),
+                   "transit_logp_grad")
+    return logp, gel, gcl, gmean
+
+
+class _TransitLogp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, elem, cl, mean, data, stencil):
+        logp, gel, gcl, gmean = transit_logp_grad(data, elem, cl, mean, stencil)
+        full = torch.zeros_like(elem)
+        full[..., :NGRAD] = gel
+        ctx.save_for_backward(full, gcl, gmean)
+        return logp
+
+    @staticmethod
+    def backward(ctx, g):
+        full, gcl, gmean = ctx.saved_tensors
+        return g[:, None, None] * full, g[:, None] * gcl, g * gmean, None, None
+
+
+class TransitLogp:
+    """Fused ``logp`` Op: parameters in (O(#params) per chain), data resident on the device."""
+
+    def __init__(self, data, texp=None, oversample=7, order=0):
+        self.data = data
+        self.stencil = exposure_stencil(texp, oversample, order)
+
+    def __call__(self, elem, cl, mean):
+        return _TransitLogp.apply(elem, cl, mean, self.data, self.stencil)
+
+
+def orbit_eval(t, elem, want=("X", "Y", "Z", "rv")):
+    """Relative position / R_star and RV shape for every (chain, cadence, planet)."""
+    lib = _lib.require_cuda()
+    elem = elem.detach().contiguous()
+    Cc, P = elem.shape[0], elem.shape[1]
+    out = {k: torch.empty((Cc, t.numel(), P), dtype=torch.float64, device=t.device) for k in want}
+    with torch.cuda.device(t.device):
+        _lib.check(lib.xo_orbit_eval(_ptr(t), t.numel(), _ptr(elem), Cc, P, _ptr(out.get("X")), _ptr(out.get("Y")),
+                                     _ptr(out.get("Z")), _ptr(out.get("rv")), _lib.stream_ptr()), "orbit_eval")
+    return out
+
+
+def rv_logp_grad(data, elem, gamma, workspace=None):
+    """RV Gaussian log-likelihood + gradient: (logp[C], grv[C,P,7], ggamma[C])."""
+    lib = _lib.require_cuda()
+    elem = elem.detach().contiguous()
+    gamma = gamma.detach().contiguous()
+    Cc, P = elem.shape[0], elem.shape[1]
+    dev = data.t.device
+    need = lib.xo_rv_logp_grad_workspace(data.n, Cc, P)
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty(max(need, 8) // 8 + 1, dtype=torch.float64, device=dev)
+    logp = torch.empty(Cc, dtype=torch.float64, device=dev)
+    grv = torch.empty((Cc, P, NGRAD_RV), dtype=torch.float64, device=dev)
+    gg = torch.empty(Cc, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.xo_rv_logp_grad(_ptr(data.t), _ptr(data.y), _ptr(data.ivar), data.n, _ptr(elem), _ptr(gamma), Cc, P,
+                                       data.lognorm, _ptr(logp), _ptr(grv), _ptr(gg), _ptr(workspace),
+                                       workspace.numel() * workspace.element_size(), _lib.stream_ptr()), "rv_logp_grad")
+    return logp, grv, gg
+
+
+class _RvLogp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, elem, gamma, data):
+        logp, grv, gg = rv_logp_grad(data, elem, gamma)
+        full = torch.zeros_like(elem)
+        full[..., :6] = grv[..., :6]
+        full[..., _lib.EL_KRV] = grv[..., 6]
+        ctx.save_for_backward(full, gg)
+        return logp
+
+    @staticmethod
+    def backward(ctx, g):
+        full, gg = ctx.saved_tensors
+        return g[:, None, None] * full, g * gg, None
+
+
+class RvLogp:
+    def __init__(self, data):
+        self.data = data
+
+    def __call__(self, elem, gamma):
+        return _RvLogp.apply(elem, gamma, self.data)

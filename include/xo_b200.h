@@ -1,0 +1,148 @@
+/* xo_b200.h -- C ABI of libxo_b200.so, the B200 (sm_100a) engine behind the
+ * operator boundary of exoplanet-dev/exoplanet.
+ *
+ * The boundary being replaced is the module object `ops` that the reference binds at
+ *   /root/reference/src/exoplanet/compat.py:56   (from exoplanet_core.pymc import ops)
+ * and touches at exactly four call sites:
+ *   ops.kepler                /root/reference/src/exoplanet/orbits/keplerian.py:333, :818
+ *   ops.quad_solution_vector  /root/reference/src/exoplanet/light_curves/limb_dark.py:24
+ *   ops.contact_points        /root/reference/src/exoplanet/orbits/keplerian.py:744-753
+ * exoplanet-core's own FFI for those ops is a pybind11 `driver` that fills flat,
+ * contiguous fp64 host arrays in place; the `*_host` entry points below have that
+ * shape (plain pointers + element count) and are what a maintainer would bind.
+ * The device-pointer entry points are the same kernels for callers that keep
+ * their arrays in HBM (torch CUDA tensors): no torch types cross this ABI.
+ *
+ * Conventions
+ *  - every array is contiguous fp64 unless stated; sizes are int64_t element counts;
+ *  - device entry points take device pointers and a `stream` (cudaStream_t passed as
+ *    void*; NULL = the legacy default stream), enqueue asynchronously, never allocate,
+ *    never free caller memory; scratch is passed in explicitly (workspace);
+ *  - `*_host` entry points take HOST pointers, run on CUDA device `device`,
+ *    copy in, launch, copy out and synchronise before returning; their scratch is
+ *    stream-ordered (cudaMallocAsync/cudaFreeAsync), nothing persists;
+ *  - return value: 0 = ok; negative = -(cudaError_t); positive = XO_E* argument error.
+ *    No C++ exception crosses the ABI.  NaN in -> NaN out; every iteration is bounded.
+ *  - the library is stateless and re-entrant.
+ */
+#ifndef XO_B200_H
+#define XO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XO_ABI_VERSION 1
+
+/* argument errors */
+#define XO_EINVAL 1   /* bad size / null pointer */
+#define XO_ERANGE 2   /* K (stencil) or P (planets) above the compiled maximum */
+#define XO_EWORKSPACE 3 /* workspace too small */
+
+/* Element block: one per (chain, planet), XO_NEL doubles, array-of-structs
+ * [C][P][XO_NEL].  It is what KeplerianOrbit.__init__ derives per planet
+ * (keplerian.py:133-281) plus the in_transit() window (keplerian.py:729-767). */
+#define XO_NEL 16
+#define XO_EL_T0 0      /* reference transit time t0                    */
+#define XO_EL_TREF 1    /* tref = t_periastron - t0   (keplerian.py:279) */
+#define XO_EL_N 2       /* mean motion n = 2 pi / period (:146)          */
+#define XO_EL_ECC 3     /* e (0 => circular branch, :331-332)            */
+#define XO_EL_COSW 4
+#define XO_EL_SINW 5
+#define XO_EL_COSI 6
+#define XO_EL_SINI 7
+#define XO_EL_AOR 8     /* a / R_star                                    */
+#define XO_EL_ROR 9     /* r_planet / R_star                             */
+#define XO_EL_PERIOD 10
+#define XO_EL_TSTART 11 /* in-transit window on dt = mod(t-t0+P/2,P)-P/2; */
+#define XO_EL_TEND 12   /* (-inf,+inf) = evaluate every cadence          */
+#define XO_EL_KRV 13    /* RV semi-amplitude (keplerian.py:658-670)      */
+#define XO_NGRAD 10     /* d/d(t0,tref,n,e,cosw,sinw,cosi,sini,aor,ror)  */
+#define XO_NGRAD_RV 7   /* d/d(t0,tref,n,e,cosw,sinw,Krv)                */
+#define XO_MAX_STENCIL 33 /* exposure-time sub-samples per cadence        */
+#define XO_MAX_PLANETS 8
+
+const char *xo_version(void);
+int xo_abi_version(void);
+int xo_device_count(void);
+/* human-readable text for a return value of any entry point */
+const char *xo_strerror(int status);
+
+/* ---- kepler(M, e) -> (sin f, cos f)          replaces keplerian.py:333 ---- */
+int xo_kepler_fwd(const double *M, const double *e, double *sinf, double *cosf, int64_t n, void *stream);
+/* e given once per element block of `inner` consecutive M values (the reference
+ * broadcasts a per-planet scalar, keplerian.py:333); n = total elements        */
+int xo_kepler_fwd_bcast(const double *M, const double *e, int64_t e_stride_inner, double *sinf, double *cosf, int64_t n,
+                        void *stream);
+/* VJP of the op: (bsinf, bcosf) -> (bM, be) */
+int xo_kepler_vjp(const double *sinf, const double *cosf, const double *e, const double *bsinf, const double *bcosf,
+                  double *bM, double *be, int64_t n, void *stream);
+
+/* ---- quad_solution_vector(b, r) -> s[n][3]  replaces limb_dark.py:24 ----
+ * dsdb / dsdr ([n][3], may both be NULL) are the Jacobians the VJP consumes. */
+int xo_qsv_fwd(const double *b, const double *r, double *s, double *dsdb, double *dsdr, int64_t n, void *stream);
+int xo_qsv_vjp(const double *bs, const double *dsdb, const double *dsdr, double *bb, double *br, int64_t n, void *stream);
+
+/* ---- contact_points(a,e,cosw,sinw,cosi,sini,L) -> (M_left,M_right,flag)
+ *      replaces keplerian.py:744-753; flag != 0 => caller evaluates all cadences */
+int xo_contact_points(const double *a, const double *e, const double *cosw, const double *sinw, const double *cosi,
+                      const double *sini, const double *L, double *M_left, double *M_right, int32_t *flag, int64_t n,
+                      void *stream);
+
+/* ---- fused L3 path (keplerian.py:324-409 + limb_dark.py:163-252) ----
+ * t[N]; elem[C][P][XO_NEL]; cl[C][3] (get_cl, limb_dark.py:11-18);
+ * stencil dtk[K] (already multiplied by texp) and wk[K] (limb_dark.py:181-198), K=1,dtk=0,wk=1 for texp=None.
+ * lc[C][N][P]: exact 0.0 outside the window / for z<=0 / for b>=1+r. */
+int xo_transit_lc_fwd(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
+                      const double *dtk, const double *wk, int K, double *lc, void *stream);
+
+/* Gaussian log-likelihood and its gradient in one launch:
+ *   logp[c] = lognorm - 1/2 sum_n ivar[n] (y[n] - mean[c] - sum_p lc[c][n][p])^2
+ *   gel[C][P][XO_NGRAD], gcl[C][3], gmean[C].
+ * workspace: xo_transit_logp_grad_workspace(N, C, P) bytes of device memory. */
+size_t xo_transit_logp_grad_workspace(int64_t N, int64_t C, int64_t P);
+int xo_transit_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *elem,
+                         const double *cl, const double *mean, int64_t C, int64_t P, const double *dtk, const double *wk,
+                         int K, double lognorm, double *logp, double *gel, double *gcl, double *gmean, void *workspace,
+                         size_t workspace_bytes, void *stream);
+
+/* relative position / R_star and RV shape for every (chain, cadence, planet):
+ * X,Y,Z,rv each [C][N][P], any may be NULL (keplerian.py:380-409, 658-670) */
+int xo_orbit_eval(const double *t, int64_t N, const double *elem, int64_t C, int64_t P, double *X, double *Y, double *Z,
+                  double *rv, void *stream);
+
+/* RV Gaussian log-likelihood + gradient:
+ *   model[c][n] = gamma[c] + sum_p Krv_p (cos(w+f) + e cos w);  grv[C][P][XO_NGRAD_RV], ggamma[C] */
+size_t xo_rv_logp_grad_workspace(int64_t N, int64_t C, int64_t P);
+int xo_rv_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *elem,
+                    const double *gamma, int64_t C, int64_t P, double lognorm, double *logp, double *grv, double *ggamma,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- celerite SHO GP log-likelihood (celerite2 SHOTerm; no reference call site) ----
+ * B chains share (t, diag); y[B][N] (residuals), params S0[B], w0[B], Q[B]; out loglike[B].
+ * eps as celerite2's SHOTerm(eps=1e-5). */
+size_t xo_celerite_sho_workspace(int64_t N, int64_t B);
+int xo_celerite_sho_loglike(const double *t, const double *y, const double *diag, int64_t N, const double *S0,
+                            const double *w0, const double *Q, int64_t B, double eps, double *loglike, void *workspace,
+                            size_t workspace_bytes, void *stream);
+
+/* ---- host-buffer entry points (the shape of exoplanet-core's driver) ---- */
+int xo_kepler_host(const double *M, const double *e, double *sinf, double *cosf, int64_t n, int device);
+int xo_qsv_host(const double *b, const double *r, double *s, double *dsdb, double *dsdr, int64_t n, int device);
+int xo_contact_points_host(const double *a, const double *e, const double *cosw, const double *sinw, const double *cosi,
+                           const double *sini, const double *L, double *M_left, double *M_right, int32_t *flag,
+                           int64_t n, int device);
+int xo_transit_lc_host(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
+                       const double *dtk, const double *wk, int K, double *lc, int device);
+int xo_transit_logp_grad_host(const double *t, const double *y, const double *ivar, int64_t N, const double *elem,
+                              const double *cl, const double *mean, int64_t C, int64_t P, const double *dtk,
+                              const double *wk, int K, double lognorm, double *logp, double *gel, double *gcl,
+                              double *gmean, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XO_B200_H */

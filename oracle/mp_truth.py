@@ -225,7 +225,10 @@ def quad_solution_vector_jac_closed(b, r):
     if b == 0:
         ds1db = mp.mpf(0)
         ds1dr = -2 * mp.pi * r * mp.sqrt(1 - r * r)
-    elif A >= B:  # interior, m = B/A <= 1
+    elif A == B:  # b = 1 - r exactly: E(1) = 1, (1 - m) K(m) -> 0
+        ds1dr = -4 * r * mp.sqrt(A)
+        ds1db = 4 * r * mp.sqrt(A) / 3
+    elif A > B:  # interior, m = B/A < 1
         m = B / A
         K = mp.ellipk(m)
         E = mp.ellipe(m)
