@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- model+grad evaluations/s of an N=1e5-cadence eccentric (e=0.5) transit
+(BASELINE.json configs[1]) on 1..8 B200, next to the CPU restatement of the reference
+path timed on the same box (`cpu_baseline`, and `--impl reference`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One *step* = one model+grad evaluation of every chain of the batch (default 128 chains
+per GPU -- BASELINE configs[4]'s per-GPU share -- all seeing the same N=1e5 light curve):
+params -> element blocks -> fused Kepler/projection/limb-darkening logp + full gradient.
+`value` = evaluations/s with inputs resident in HBM, device-timed (CUDA events per step,
+L2 flushed between steps, max over ranks).  `e2e` = the same evaluations through the
+host-buffer C-ABI call (host arrays in, host arrays out, H2D/D2H inside the timed region).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_CADENCES = 100000
+CHAINS_PER_GPU = 128
+SIGMA = 5e-4
+ALG_BYTES_PER_CHAIN_CADENCE = 24  # t, y, sigma (SURVEY 8d / BASELINE.md section 5)
+KEPLER_BYTES_PER_ELEMENT = 32  # M, e in; sin f, cos f out
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons = [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    out["sm_max_mhz"] = float(f[2])
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def build_problem(C, seed_offset=0):
+    """numpy description of the workload (shared by both arms)."""
+    from exoplanet_b200 import synthetic
+
+    t = synthetic.cadence_times(N_CADENCES)
+    p = synthetic.transit_params(C, 1, seed=synthetic.SEED + 17 * seed_offset, ecc=0.5)
+    truth = synthetic.transit_params(1, 1, seed=synthetic.SEED - 1, ecc=0.5)
+    return t, p, truth
+
+
+def cpu_port_setup(t, p, truth):
+    """Element blocks / data through the CPU oracle (used ONLY by the baseline legs)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import xo_oracle as O
+
+    el_truth = O.elements_from_params(truth["period"], truth["t0"], truth["ecc"], truth["omega"], truth["b"], truth["ror"])
+    cl_truth = O.get_cl(truth["u1"], truth["u2"])
+    dtk, wk = O.stencil(None)
+    from exoplanet_b200 import synthetic
+
+    y = O.transit_lc(t, el_truth, cl_truth, dtk, wk)[0, :, 0] + synthetic.noise(N_CADENCES, SIGMA)
+    return O, y, dtk, wk
+
+
+def time_cpu_port(O, t, y, p, dtk, wk, budget_s, threads):
+    """evaluations/s of the CPU restatement on `threads` host threads, bounded sample."""
+    O.set_threads(threads)
+    ivar = np.full(t.size, 1.0 / SIGMA ** 2)
+    Call = p["period"].shape[0]
+
+    def run(nc):
+        el = O.elements_from_params(p["period"][:nc], p["t0"][:nc], p["ecc"][:nc], p["omega"][:nc], p["b"][:nc], p["ror"][:nc])
+        cl = O.get_cl(p["u1"][:nc], p["u2"][:nc])
+        t0 = time.perf_counter()
+        O.transit_logp_grad(t, y, ivar, el, cl, p["mean"][:nc], dtk, wk)
+        return time.perf_counter() - t0
+
+    nc = min(Call, max(threads, 1))
+    run(nc)  # warm-up
+    dt = run(nc)
+    per = dt / nc
+    reps = int(max(1, min(200, budget_s / max(dt, 1e-6))))
+    best = dt
+    tot, cnt = 0.0, 0
+    for _ in range(reps):
+        d = run(nc)
+        best = min(best, d)
+        tot += d
+        cnt += nc
+    return cnt / tot, nc, reps, per
+
+
+def arm_reference(args):
+    """The reference's own CPU implementation of the path is exoplanet-core (not in this
+    image) -> the CPU restatement (oracle port) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t, p, truth = build_problem(CHAINS_PER_GPU)
+    O, y, dtk, wk = cpu_port_setup(t, p, truth)
+    threads = O.max_threads()
+    O.set_threads(threads)
+    ivar = np.full(t.size, 1.0 / SIGMA ** 2)
+    nc = min(CHAINS_PER_GPU, max(threads, 1) * 2)  # bounded sample: 2 chains per thread per step
+    el = O.elements_from_params(p["period"][:nc], p["t0"][:nc], p["ecc"][:nc], p["omega"][:nc], p["b"][:nc], p["ror"][:nc])
+    cl = O.get_cl(p["u1"][:nc], p["u2"][:nc])
+
+    def step():
+        # prologue (contact points, elements) + logp + grad, as one reference evaluation would
+        e2 = O.elements_from_params(p["period"][:nc], p["t0"][:nc], p["ecc"][:nc], p["omega"][:nc], p["b"][:nc], p["ror"][:nc])
+        return O.transit_logp_grad(t, y, ivar, e2, cl, p["mean"][:nc], dtk, wk)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = nc * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "model+grad evals/sec, N=1e5-cadence e=0.5 transit", "value": val, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: eccentric (e=0.5) single-planet Kepler solve + LimbDarkLightCurve, N=1e5 cadences, fp64",
+                   "chains_per_step": nc, "cadences": N_CADENCES, "use_in_transit": True},
+        "cpu_baseline": {"value": val, "unit": "evals/s", "cores": threads, "kind": "port",
+                         "sample": "%d chains x N=1e5 per step (OpenMP over chains), %d steps" % (nc, args.steps)},
+        "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU restatement of the reference mathematics (oracle/xo_oracle.c); exoplanet-core/PyTensor are not installable here",
+    }
+    print(json.dumps(line))
+
+
+def arm_ours(args):
+    import torch
+
+    from exoplanet_b200 import _lib, elements, fused, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.require_cuda()
+
+    C_loc = args.chains
+    t_np, p, truth = build_problem(C_loc, seed_offset=rank)
+
+    def d(x):
+        return torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float64, device=dev)
+
+    # data: truth light curve (GPU kernels) + seeded noise, resident in HBM
+    el_truth = elements.elements_from_params(d(truth["period"]), d(truth["t0"]), d(truth["ecc"]), d(truth["omega"]), d(truth["b"]),
+                                             d(truth["ror"]))
+    cl_truth = fused.limb_dark_coeffs(d(truth["u1"]), d(truth["u2"]))
+    t_dev = d(t_np)
+    y_np = fused.light_curve(t_dev, el_truth, cl_truth)[0, :, 0].cpu().numpy() + synthetic.noise(N_CADENCES, SIGMA)
+    data = fused.TransitData(t_np, y_np, np.full(N_CADENCES, SIGMA), device=dev)
+    elem = elements.elements_from_params(d(p["period"]), d(p["t0"]), d(p["ecc"]), d(p["omega"]), d(p["b"]), d(p["ror"]))
+    elem = elem.contiguous()
+    cl = fused.limb_dark_coeffs(d(p["u1"]), d(p["u2"])).contiguous()
+    mean = d(p["mean"])
+    stencil = fused.exposure_stencil(None)
+    dtk, wk = d(stencil[0]), d(stencil[1])
+    P = 1
+    ws_bytes = lib.xo_transit_logp_grad_workspace(N_CADENCES, C_loc, P)
+    ws = torch.empty(ws_bytes // 8 + 1, dtype=torch.float64, device=dev)
+    logp = torch.empty(C_loc, dtype=torch.float64, device=dev)
+    gel = torch.empty((C_loc, P, 10), dtype=torch.float64, device=dev)
+    gcl = torch.empty((C_loc, 3), dtype=torch.float64, device=dev)
+    gmean = torch.empty(C_loc, dtype=torch.float64, device=dev)
+    ptr = lambda x: C.c_void_p(x.data_ptr())
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        rc = lib.xo_transit_logp_grad(ptr(data.t), ptr(data.y), ptr(data.ivar), N_CADENCES, ptr(elem), ptr(cl), ptr(mean), C_loc, P,
+                                      ptr(dtk), ptr(wk), 1, data.lognorm, ptr(logp), ptr(gel), ptr(gcl), ptr(gmean), ptr(ws),
+                                      ws.numel() * 8, C.c_void_p(stream.cuda_stream))
+        if rc != 0:
+            raise RuntimeError(lib.xo_strerror(rc).decode())
+
+    flush = torch.empty(192 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    wall0 = time.perf_counter()
+    for a, b in ev:
+        flush.zero_()  # L2 flush between timed iterations (outside the events)
+        a.record()
+        step_device()
+        b.record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    ms_dev = sum(a.elapsed_time(b) for a, b in ev)
+    # ---- e2e: host buffers through the C ABI -------------------------------------------
+    h = {k: np.ascontiguousarray(v) for k, v in dict(t=t_np, y=y_np, ivar=np.full(N_CADENCES, 1 / SIGMA ** 2), elem=elem.cpu().numpy(),
+                                                     cl=cl.cpu().numpy(), mean=p["mean"], dtk=stencil[0], wk=stencil[1]).items()}
+    o = dict(logp=np.empty(C_loc), gel=np.empty((C_loc, P, 10)), gcl=np.empty((C_loc, 3)), gmean=np.empty(C_loc))
+    np_ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    def step_host():
+        rc = lib.xo_transit_logp_grad_host(np_ptr(h["t"]), np_ptr(h["y"]), np_ptr(h["ivar"]), N_CADENCES, np_ptr(h["elem"]),
+                                           np_ptr(h["cl"]), np_ptr(h["mean"]), C_loc, P, np_ptr(h["dtk"]), np_ptr(h["wk"]), 1,
+                                           data.lognorm, np_ptr(o["logp"]), np_ptr(o["gel"]), np_ptr(o["gcl"]), np_ptr(o["gmean"]), local)
+        if rc != 0:
+            raise RuntimeError(lib.xo_strerror(rc).decode())
+
+    for _ in range(3):
+        step_host()
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - e0
+    clocks = sampler.stop() if rank == 0 else None
+    h2d = sum(h[k].nbytes for k in h)
+    d2h = sum(o[k].nbytes for k in o)
+
+    # ---- Kepler micro-benchmark (rank 0 numbers reported; > L2 working set) ---------------
+    kep = None
+    if not args.no_kepler:
+        n = 1 << 26
+        g = torch.Generator(device=dev).manual_seed(1234)
+        M = (torch.rand(n, dtype=torch.float64, device=dev, generator=g) * 2 - 1) * (2000 * np.pi)
+        kep = {}
+        for name, e in (("e=0.5", torch.full((n,), 0.5, dtype=torch.float64, device=dev)),
+                        ("e~U(0,0.95)", torch.rand(n, dtype=torch.float64, device=dev, generator=g) * 0.95)):
+            sf = torch.empty_like(M)
+            cf = torch.empty_like(M)
+            for _ in range(3):
+                lib.xo_kepler_fwd(ptr(M), ptr(e), ptr(sf), ptr(cf), n, C.c_void_p(stream.cuda_stream))
+            torch.cuda.synchronize()
+            evs = []
+            for _ in range(5):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                lib.xo_kepler_fwd(ptr(M), ptr(e), ptr(sf), ptr(cf), n, C.c_void_p(stream.cuda_stream))
+                b.record()
+                evs.append((a, b))
+            torch.cuda.synchronize()
+            ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+            kep[name] = {"cadences_per_s": n / (ms * 1e-3), "gb_per_s": n * KEPLER_BYTES_PER_ELEMENT / (ms * 1e-3) / 1e9,
+                         "ms": ms, "n": n}
+            del sf, cf, e
+        del M
+
+    tm = torch.tensor([ms_dev, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_dev, e2e_ms = tm[0].item(), tm[1].item()
+    total_evals = C_loc * world * args.steps
+    value = total_evals / (ms_dev * 1e-3)
+    e2e = total_evals / (e2e_ms * 1e-3)
+    peak, peak_src = _peaks()
+    ach = ALG_BYTES_PER_CHAIN_CADENCE * C_loc * N_CADENCES / (ms_dev / args.steps * 1e-3) / 1e9  # per GPU, per launch
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        O, y_o, dtk_o, wk_o = cpu_port_setup(t_np, p, truth)
+        thr = O.max_threads()
+        v_all, nc, reps, _ = time_cpu_port(O, t_np, y_np, p, dtk_o, wk_o, budget_s=12.0, threads=thr)
+        v_one, _, _, _ = time_cpu_port(O, t_np, y_np, p, dtk_o, wk_o, budget_s=4.0, threads=1)
+        cpu = {"value": v_all, "unit": "evals/s", "cores": thr, "kind": "port",
+               "sample": "%d chains x N=1e5 per call, %d calls (~12 s); single-thread: %.1f evals/s" % (nc, reps, v_one),
+               "single_thread_value": v_one}
+        # cross-check the timed GPU result against the oracle on a few chains (parity gate before reporting)
+        sel = [0, C_loc // 2, C_loc - 1]
+        lo, geo, _, _ = O.transit_logp_grad(t_np, y_np, np.full(N_CADENCES, 1 / SIGMA ** 2), elem.cpu().numpy()[sel], cl.cpu().numpy()[sel],
+                                            p["mean"][sel], dtk_o, wk_o, lognorm=data.lognorm)
+        rel = float(np.max(np.abs(logp.cpu().numpy()[sel] - lo) / np.abs(lo)))
+        if rel > 1e-10:
+            raise SystemExit("parity gate failed: logp rel err %g" % rel)
+        cpu["parity_logp_rel_err"] = rel
+
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": "model+grad evals/sec, N=1e5-cadence e=0.5 transit", "value": value, "unit": "evals/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: eccentric (e=0.5) single-planet Kepler solve + LimbDarkLightCurve, N=1e5 cadences, fp64",
+                   "chains_per_gpu": C_loc, "chains_total": C_loc * world, "cadences": N_CADENCES, "use_in_transit": True,
+                   "parallelism": "chain-sharded, no collective", "l2": "flushed between timed steps (192 MiB memset)",
+                   "step_inputs": "element blocks resident in HBM (prologue outside the step)"},
+        "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "xo_transit_logp_grad_host: t,y,ivar,elements from host memory every call"},
+        "gpu_launches": 2 * args.steps,
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                     "kernel": "transit_logp_grad_kernel", "peak_source": peak_src,
+                     "note": "algorithmic 24 B per (chain,cadence); chains share t,y,sigma through L2, and the kernel is fp64-pipe bound"},
+        "clocks": clocks, "wall_s": wall,
+    }
+    if kep is not None:
+        line["kepler"] = kep
+        k = kep["e~U(0,0.95)"]
+        line["kepler_roofline"] = {"bound": "hbm", "achieved": k["gb_per_s"], "peak": peak, "unit": "GB/s", "frac": k["gb_per_s"] / peak,
+                                   "kernel": "kepler_fwd_kernel", "bytes_per_element": KEPLER_BYTES_PER_ELEMENT}
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-kepler", action="store_true", help="skip the Kepler micro-benchmark")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        arm_reference(args)
+    else:
+        arm_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,187 @@
+"""GPU parity tests of the fused L3 kernels against the CPU oracle on identical seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+import xo_oracle as O
+from exoplanet_b200 import elements, fused, synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def dev(x):
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float64, device=DEV)
+
+
+def problem(N, C, P, ecc=None, texp=None, seed=11, use_in_transit=True):
+    p = synthetic.transit_params(C, P, seed=seed, ecc=ecc)
+    t = synthetic.cadence_times(N)
+    el_o = O.elements_from_params(p["period"], p["t0"], p["ecc"], p["omega"], p["b"], p["ror"], texp=texp, K=p["K"],
+                                  use_in_transit=use_in_transit)
+    el_g = elements.elements_from_params(dev(p["period"]), dev(p["t0"]), dev(p["ecc"]), dev(p["omega"]), dev(p["b"]),
+                                         dev(p["ror"]), K=dev(p["K"]), texp=texp, use_in_transit=use_in_transit)
+    cl = O.get_cl(p["u1"], p["u2"])
+    return p, t, el_o, el_g, cl
+
+
+def test_prologue_elements_match_oracle():
+    p, t, el_o, el_g, cl = problem(100, 16, 3)
+    eg = el_g.cpu().numpy()
+    assert np.allclose(eg[..., :11], el_o[..., :11], rtol=1e-13, atol=1e-13)
+    assert np.allclose(eg[..., 11:13], el_o[..., 11:13], rtol=0, atol=1e-10)  # contact times
+    clg = fused.limb_dark_coeffs(dev(p["u1"]), dev(p["u2"])).cpu().numpy()
+    assert np.allclose(clg, cl, rtol=1e-14, atol=1e-15)
+
+
+@pytest.mark.parametrize("P,texp,order", [(1, None, 0), (2, 0.02, 0), (3, 0.0204, 2), (1, 0.02, 1)])
+def test_light_curve_matches_oracle(P, texp, order):
+    N, C = 20000, 4
+    p, t, el_o, el_g, cl = problem(N, C, P, texp=texp)
+    st = O.stencil(texp, 7, order)
+    lc_o = O.transit_lc(t, el_o, cl, *st)
+    lc = fused.light_curve(dev(t), dev(el_o), dev(cl), fused.exposure_stencil(texp, 7, order)).cpu().numpy()
+    assert np.count_nonzero(lc_o) > 50
+    # the oracle evaluates every planet where ANY planet is in window (reference semantics);
+    # outside a planet's own window its column is exactly 0 in both unless b < 1 + r there
+    assert np.max(np.abs(lc - lc_o)) < 1e-14
+    assert np.array_equal(lc == 0.0, lc_o == 0.0)
+
+
+def test_light_curve_exact_zeros_and_use_in_transit_equivalence():
+    # tests/light_curves_test.py:75-102: use_in_transit True == False
+    N = 30000
+    p, t, el_o, el_g, cl = problem(N, 3, 2, ecc=0.5)
+    p2, _, el_all, _, _ = problem(N, 3, 2, ecc=0.5, use_in_transit=False)
+    a = fused.light_curve(dev(t), dev(el_o), dev(cl)).cpu().numpy()
+    b = fused.light_curve(dev(t), dev(el_all), dev(cl)).cpu().numpy()
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("P,texp,C", [(1, None, 5), (1, 0.02, 3), (3, None, 4), (2, 0.0204, 2)])
+def test_logp_grad_matches_oracle(P, texp, C):
+    N = 50000
+    p, t, el_o, el_g, cl = problem(N, C, P, texp=texp, seed=5 + P)
+    if P > 1:  # force overlapping transits of two planets in chain 0
+        p["period"][0, 1] = p["period"][0, 0]
+        p["t0"][0, 1] = p["t0"][0, 0] + 0.01
+        el_o = O.elements_from_params(p["period"], p["t0"], p["ecc"], p["omega"], p["b"], p["ror"], texp=texp, K=p["K"])
+    st = O.stencil(texp, 7, 0)
+    truth = O.transit_lc(t, el_o, cl, *st).sum(-1)
+    y = truth + p["mean"][:, None] * 0  # each chain sees the same data: chain 0's truth + noise
+    y = truth[0] + synthetic.noise(N)
+    sigma = 5e-4
+    data = fused.TransitData(t, y, np.full(N, sigma), device=DEV)
+    logp, gel, gcl, gmean = fused.transit_logp_grad(data, dev(el_o), dev(cl), dev(p["mean"]), fused.exposure_stencil(texp))
+    lo, geo, gco, gmo = O.transit_logp_grad(t, y, np.full(N, 1 / sigma ** 2), el_o, cl, p["mean"], *st, lognorm=data.lognorm)
+    # logp rel err <= 1e-10, gradient <= 1e-8
+    assert np.max(np.abs(logp.cpu().numpy() - lo) / np.abs(lo)) < 1e-12
+    scale = np.abs(geo).max(axis=(0, 1), keepdims=True) + 1e-300
+    assert np.max(np.abs(gel.cpu().numpy() - geo) / scale) < 1e-10
+    assert np.max(np.abs(gcl.cpu().numpy() - gco) / (np.abs(gco).max() + 1e-300)) < 1e-10
+    assert np.max(np.abs(gmean.cpu().numpy() - gmo) / np.abs(gmo).max()) < 1e-10
+
+
+def test_logp_is_deterministic_and_chain_independent():
+    N, C = 100000, 64
+    p, t, el_o, el_g, cl = problem(N, C, 1, ecc=0.5)
+    y = synthetic.noise(N)
+    data = fused.TransitData(t, y, np.full(N, 5e-4), device=DEV)
+    a = fused.transit_logp_grad(data, dev(el_o), dev(cl), dev(p["mean"]))
+    b = fused.transit_logp_grad(data, dev(el_o), dev(cl), dev(p["mean"]))
+    for x, z in zip(a, b):
+        assert torch.equal(x, z)  # bit-reproducible
+    # a chain's result does not depend on its batch: rows of a sub-batch agree bitwise
+    # only if the work split is equal, so compare to tolerance instead
+    c = fused.transit_logp_grad(data, dev(el_o[:7]), dev(cl[:7]), dev(p["mean"][:7]))
+    assert torch.allclose(a[0][:7], c[0], rtol=1e-13, atol=0)
+    assert torch.allclose(a[1][:7], c[1], rtol=1e-9, atol=1e-9)
+    # spot-check 3 chains of the full-size batch against the oracle
+    sel = [0, 31, 63]
+    lo, geo, _, _ = O.transit_logp_grad(t, y, np.full(N, 1 / 5e-4 ** 2), el_o[sel], cl[sel], p["mean"][sel], np.zeros(1),
+                                        np.ones(1), lognorm=data.lognorm)
+    assert np.max(np.abs(a[0].cpu().numpy()[sel] - lo) / np.abs(lo)) < 1e-12
+    assert np.allclose(a[1].cpu().numpy()[sel], geo, rtol=1e-8, atol=1e-6)
+
+
+def test_logp_autograd_through_prologue():
+    N = 20000
+    p = synthetic.transit_params(3, 1, seed=9, ecc=0.3)
+    t = synthetic.cadence_times(N)
+    data = fused.TransitData(t, synthetic.noise(N), np.full(N, 5e-4), device=DEV)
+    names = ["period", "t0", "ecc", "omega", "b", "ror"]
+    ts = {k: dev(p[k]).requires_grad_(True) for k in names}
+    u1 = dev(p["u1"]).requires_grad_(True)
+    u2 = dev(p["u2"]).requires_grad_(True)
+    mean = dev(p["mean"]).requires_grad_(True)
+    op = fused.TransitLogp(data)
+
+    def f():
+        el = elements.elements_from_params(ts["period"], ts["t0"], ts["ecc"], ts["omega"], ts["b"], ts["ror"])
+        return op(el, fused.limb_dark_coeffs(u1, u2), mean).sum()
+
+    val = f()
+    grads = torch.autograd.grad(val, [ts[k] for k in names] + [u1, u2, mean])
+    # central differences on a few parameters (float64, so FD is meaningful)
+    for k, h in [("b", 1e-7), ("ror", 1e-8), ("ecc", 1e-8), ("omega", 1e-8)]:
+        base = ts[k].detach().clone()
+        with torch.no_grad():
+            ts[k].copy_(base + h)
+            fp = f().item()
+            ts[k].copy_(base - h)
+            fm = f().item()
+            ts[k].copy_(base)
+        fd = (fp - fm) / (2 * h)
+        g = grads[names.index(k)].sum().item()
+        assert abs(fd - g) <= 1e-4 * abs(fd) + 1e-2, (k, fd, g)
+
+
+def test_orbit_eval_and_rv_match_oracle():
+    N, C, P = 4000, 3, 5
+    p, t, el_o, el_g, cl = problem(N, C, P, use_in_transit=False)
+    out = fused.orbit_eval(dev(t), dev(el_o))
+    Xo, Yo, Zo, rvo = O.orbit_eval(t, el_o)
+    for k, ref in zip(("X", "Y", "Z", "rv"), (Xo, Yo, Zo, rvo)):
+        assert np.max(np.abs(out[k].cpu().numpy() - ref) / (1 + np.abs(ref))) < 1e-13
+    rv_obs = rvo[0].sum(-1) + np.random.default_rng(0).normal(size=N)
+    data = fused.TransitData(t, rv_obs, np.full(N, 1.0), device=DEV)
+    logp, grv, gg = fused.rv_logp_grad(data, dev(el_o), dev(p["gamma"]))
+    lo, go, ggo = O.rv_logp_grad(t, rv_obs, np.ones(N), el_o, p["gamma"], lognorm=data.lognorm)
+    assert np.max(np.abs(logp.cpu().numpy() - lo) / np.abs(lo)) < 1e-12
+    scale = np.abs(go).max(axis=(0, 1), keepdims=True)
+    assert np.max(np.abs(grv.cpu().numpy() - go) / scale) < 1e-10
+    assert np.allclose(gg.cpu().numpy(), ggo, rtol=1e-10)
+
+
+def test_known_answer_B6(golden):
+    b6 = golden("end_to_end")["B6"]
+    el = elements.elements_from_params(dev(b6["period"]), dev(0.0), dev(b6["ecc"]), dev(b6["omega"]), dev(0.0), dev(b6["r"]))
+    assert abs(el[8].item() - b6["a"]) < 1e-12
+    assert abs(el[11].item() - b6["t_start"]) < 1e-10 and abs(el[12].item() - b6["t_end"]) < 1e-10
+    cl = fused.limb_dark_coeffs(dev(b6["u"][0]), dev(b6["u"][1]))
+    lc = fused.light_curve(dev(b6["t"]), el[None, None, :], cl[None, :])[0, :, 0].cpu().numpy()
+    assert np.max(np.abs(lc - np.array(b6["lc"]))) < 5e-15
+
+
+def test_host_buffer_logp_entry_point():
+    import ctypes as C
+
+    from exoplanet_b200 import _lib
+
+    N, Cn, P = 10000, 3, 2
+    p, t, el_o, el_g, cl = problem(N, Cn, P)
+    y = synthetic.noise(N)
+    ivar = np.full(N, 4e6)
+    dtk, wk = fused.exposure_stencil()
+    logp, gel, gcl, gm = np.empty(Cn), np.empty((Cn, P, 10)), np.empty((Cn, 3)), np.empty(Cn)
+    f = lambda a: a.ctypes.data_as(C.c_void_p)
+    el_c = np.ascontiguousarray(el_o)
+    cl_c = np.ascontiguousarray(cl)
+    rc = _lib.require_cuda().xo_transit_logp_grad_host(f(t), f(y), f(ivar), N, f(el_c), f(cl_c), f(p["mean"]), Cn, P, f(dtk),
+                                                       f(wk), 1, 0.0, f(logp), f(gel), f(gcl), f(gm), 0)
+    assert rc == 0
+    lo, geo, gco, gmo = O.transit_logp_grad(t, y, ivar, el_o, cl, p["mean"], dtk, wk)
+    assert np.allclose(logp, lo, rtol=1e-12) and np.allclose(gel, geo, rtol=1e-8, atol=1e-6)
+    lc = np.empty((Cn, N, P))
+    rc = _lib.load().xo_transit_lc_host(f(t), N, f(el_c), f(cl_c), Cn, P, f(dtk), f(wk), 1, f(lc), 0)
+    assert rc == 0 and np.max(np.abs(lc - O.transit_lc(t, el_o, cl, dtk, wk))) < 1e-14
