@@ -120,34 +120,6 @@ def cpu_port_setup(t, p, truth):
     return O, y, dtk, wk
 
 
-def time_cpu_port(O, t, y, p, dtk, wk, budget_s, threads):
-    """evaluations/s of the CPU restatement on `threads` host threads, bounded sample."""
-    O.set_threads(threads)
-    ivar = np.full(t.size, 1.0 / SIGMA ** 2)
-    Call = p["period"].shape[0]
-
-    def run(nc):
-        el = O.elements_from_params(p["period"][:nc], p["t0"][:nc], p["ecc"][:nc], p["omega"][:nc], p["b"][:nc], p["ror"][:nc])
-        cl = O.get_cl(p["u1"][:nc], p["u2"][:nc])
-        t0 = time.perf_counter()
-        O.transit_logp_grad(t, y, ivar, el, cl, p["mean"][:nc], dtk, wk)
-        return time.perf_counter() - t0
-
-    nc = min(Call, max(threads, 1))
-    run(nc)  # warm-up
-    dt = run(nc)
-    per = dt / nc
-    reps = int(max(1, min(200, budget_s / max(dt, 1e-6))))
-    best = dt
-    tot, cnt = 0.0, 0
-    for _ in range(reps):
-        d = run(nc)
-        best = min(best, d)
-        tot += d
-        cnt += nc
-    return cnt / tot, nc, reps, per
-
-
 def arm_reference(args):
     """The reference's own CPU implementation of the path is exoplanet-core (not in this
     image) -> the CPU restatement (oracle port) on all host cores."""
@@ -222,26 +194,28 @@ def arm_ours(args):
     t_dev = d(t_np)
     y_np = fused.light_curve(t_dev, el_truth, cl_truth)[0, :, 0].cpu().numpy() + synthetic.noise(N_CADENCES, SIGMA)
     data = fused.TransitData(t_np, y_np, np.full(N_CADENCES, SIGMA), device=dev)
-    elem = elements.elements_from_params(d(p["period"]), d(p["t0"]), d(p["ecc"]), d(p["omega"]), d(p["b"]), d(p["ror"]))
-    elem = elem.contiguous()
-    cl = fused.limb_dark_coeffs(d(p["u1"]), d(p["u2"])).contiguous()
+    # sampler-side parameters resident in HBM: par[C][1][8], star[C][4], mean[C]
+    par = fused.pack_params(d(p["period"]), d(p["t0"]), d(p["ecc"]), d(p["omega"]), d(p["b"]), d(p["ror"]), d(p["m_planet"]), d(p["K"]))
+    star = fused.pack_star(torch.ones(C_loc, dtype=torch.float64, device=dev), torch.ones(C_loc, dtype=torch.float64, device=dev),
+                           d(p["u1"]), d(p["u2"]))
     mean = d(p["mean"])
     stencil = fused.exposure_stencil(None)
     dtk, wk = d(stencil[0]), d(stencil[1])
     P = 1
-    ws_bytes = lib.xo_transit_logp_grad_workspace(N_CADENCES, C_loc, P)
+    ws_bytes = lib.xo_transit_model_workspace(N_CADENCES, C_loc, P)
     ws = torch.empty(ws_bytes // 8 + 1, dtype=torch.float64, device=dev)
     logp = torch.empty(C_loc, dtype=torch.float64, device=dev)
-    gel = torch.empty((C_loc, P, 10), dtype=torch.float64, device=dev)
-    gcl = torch.empty((C_loc, 3), dtype=torch.float64, device=dev)
+    gpar = torch.empty_like(par)
+    gstar = torch.empty_like(star)
     gmean = torch.empty(C_loc, dtype=torch.float64, device=dev)
     ptr = lambda x: C.c_void_p(x.data_ptr())
     stream = torch.cuda.current_stream()
 
     def step_device():
-        rc = lib.xo_transit_logp_grad(ptr(data.t), ptr(data.y), ptr(data.ivar), N_CADENCES, ptr(elem), ptr(cl), ptr(mean), C_loc, P,
-                                      ptr(dtk), ptr(wk), 1, data.lognorm, ptr(logp), ptr(gel), ptr(gcl), ptr(gmean), ptr(ws),
-                                      ws.numel() * 8, C.c_void_p(stream.cuda_stream))
+        # prologue (elements, contact points, limb-darkening vector) -> fused logp+grad -> reverse prologue
+        rc = lib.xo_transit_model_logp_grad(ptr(data.t), ptr(data.y), ptr(data.ivar), N_CADENCES, ptr(par), ptr(star), ptr(mean), C_loc, P,
+                                            ptr(dtk), ptr(wk), 1, 0.0, 1, data.lognorm, ptr(logp), ptr(gpar), ptr(gstar), ptr(gmean),
+                                            ptr(ws), ws.numel() * 8, C.c_void_p(stream.cuda_stream))
         if rc != 0:
             raise RuntimeError(lib.xo_strerror(rc).decode())
 
@@ -269,16 +243,20 @@ def arm_ours(args):
     barrier()
     wall = time.perf_counter() - wall0
     ms_dev = sum(a.elapsed_time(b) for a, b in ev)
-    # ---- e2e: host buffers through the C ABI -------------------------------------------
-    h = {k: np.ascontiguousarray(v) for k, v in dict(t=t_np, y=y_np, ivar=np.full(N_CADENCES, 1 / SIGMA ** 2), elem=elem.cpu().numpy(),
-                                                     cl=cl.cpu().numpy(), mean=p["mean"], dtk=stencil[0], wk=stencil[1]).items()}
-    o = dict(logp=np.empty(C_loc), gel=np.empty((C_loc, P, 10)), gcl=np.empty((C_loc, 3)), gmean=np.empty(C_loc))
-    np_ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    # ---- e2e: PINNED host buffers through the C ABI; everything (t, y, ivar, params) goes
+    # host->device and (logp, grads) device->host inside the timed region, every step -----------
+    def pinned(a):
+        return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).pin_memory()
+
+    h = dict(t=pinned(t_np), y=pinned(y_np), ivar=pinned(np.full(N_CADENCES, 1 / SIGMA ** 2)), par=pinned(par.cpu().numpy()),
+             star=pinned(star.cpu().numpy()), mean=pinned(p["mean"]), dtk=pinned(stencil[0]), wk=pinned(stencil[1]))
+    o = dict(logp=pinned(np.empty(C_loc)), gpar=pinned(np.empty((C_loc, P, 8))), gstar=pinned(np.empty((C_loc, 4))),
+             gmean=pinned(np.empty(C_loc)))
 
     def step_host():
-        rc = lib.xo_transit_logp_grad_host(np_ptr(h["t"]), np_ptr(h["y"]), np_ptr(h["ivar"]), N_CADENCES, np_ptr(h["elem"]),
-                                           np_ptr(h["cl"]), np_ptr(h["mean"]), C_loc, P, np_ptr(h["dtk"]), np_ptr(h["wk"]), 1,
-                                           data.lognorm, np_ptr(o["logp"]), np_ptr(o["gel"]), np_ptr(o["gcl"]), np_ptr(o["gmean"]), local)
+        rc = lib.xo_transit_model_logp_grad_host(ptr(h["t"]), ptr(h["y"]), ptr(h["ivar"]), N_CADENCES, ptr(h["par"]), ptr(h["star"]),
+                                                 ptr(h["mean"]), C_loc, P, ptr(h["dtk"]), ptr(h["wk"]), 1, 0.0, 1, data.lognorm,
+                                                 ptr(o["logp"]), ptr(o["gpar"]), ptr(o["gstar"]), ptr(o["gmean"]), local)
         if rc != 0:
             raise RuntimeError(lib.xo_strerror(rc).decode())
 
@@ -291,8 +269,8 @@ def arm_ours(args):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - e0
     clocks = sampler.stop() if rank == 0 else None
-    h2d = sum(h[k].nbytes for k in h)
-    d2h = sum(o[k].nbytes for k in o)
+    h2d = sum(h[k].numel() * 8 for k in h)
+    d2h = sum(o[k].numel() * 8 for k in o)
 
     # ---- Kepler micro-benchmark (rank 0 numbers reported; > L2 working set) ---------------
     kep = None
@@ -334,21 +312,25 @@ def arm_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        # parity gate before reporting: the timed GPU result against the oracle on a few chains
         O, y_o, dtk_o, wk_o = cpu_port_setup(t_np, p, truth)
-        thr = O.max_threads()
-        v_all, nc, reps, _ = time_cpu_port(O, t_np, y_np, p, dtk_o, wk_o, budget_s=12.0, threads=thr)
-        v_one, _, _, _ = time_cpu_port(O, t_np, y_np, p, dtk_o, wk_o, budget_s=4.0, threads=1)
-        cpu = {"value": v_all, "unit": "evals/s", "cores": thr, "kind": "port",
-               "sample": "%d chains x N=1e5 per call, %d calls (~12 s); single-thread: %.1f evals/s" % (nc, reps, v_one),
-               "single_thread_value": v_one}
-        # cross-check the timed GPU result against the oracle on a few chains (parity gate before reporting)
         sel = [0, C_loc // 2, C_loc - 1]
-        lo, geo, _, _ = O.transit_logp_grad(t_np, y_np, np.full(N_CADENCES, 1 / SIGMA ** 2), elem.cpu().numpy()[sel], cl.cpu().numpy()[sel],
-                                            p["mean"][sel], dtk_o, wk_o, lognorm=data.lognorm)
+        el_o = O.elements_from_params(p["period"][sel], p["t0"][sel], p["ecc"][sel], p["omega"][sel], p["b"][sel], p["ror"][sel],
+                                      m_planet=p["m_planet"][sel])
+        lo = O.transit_logp_grad(t_np, y_np, np.full(N_CADENCES, 1 / SIGMA ** 2), el_o, O.get_cl(p["u1"][sel], p["u2"][sel]),
+                                 p["mean"][sel], dtk_o, wk_o, lognorm=data.lognorm)[0]
         rel = float(np.max(np.abs(logp.cpu().numpy()[sel] - lo) / np.abs(lo)))
         if rel > 1e-10:
             raise SystemExit("parity gate failed: logp rel err %g" % rel)
-        cpu["parity_logp_rel_err"] = rel
+        # the CPU restatement, timed in a clean process on all host cores (~10-20 s)
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "40", "--warmup", "2"],
+                             capture_output=True, text=True, timeout=600)
+        try:
+            ref = json.loads(out.stdout.strip().splitlines()[-1])
+            cpu = ref["cpu_baseline"]
+            cpu["parity_logp_rel_err"] = rel
+        except Exception:
+            cpu = {"value": None, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: " + out.stderr[-200:]}
 
     if dist is not None:
         dist.barrier()
@@ -362,10 +344,10 @@ def arm_ours(args):
         "config": {"workload": "configs[1]: eccentric (e=0.5) single-planet Kepler solve + LimbDarkLightCurve, N=1e5 cadences, fp64",
                    "chains_per_gpu": C_loc, "chains_total": C_loc * world, "cadences": N_CADENCES, "use_in_transit": True,
                    "parallelism": "chain-sharded, no collective", "l2": "flushed between timed steps (192 MiB memset)",
-                   "step_inputs": "element blocks resident in HBM (prologue outside the step)"},
+                   "step": "params -> elements+contact points -> fused logp+grad -> reverse prologue (3 launches), params resident in HBM"},
         "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "xo_transit_logp_grad_host: t,y,ivar,elements from host memory every call"},
-        "gpu_launches": 2 * args.steps,
+                "api": "xo_transit_model_logp_grad_host: t,y,ivar,params from pinned host memory every call; logp+grads back to host"},
+        "gpu_launches": 3 * args.steps,
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                      "kernel": "transit_logp_grad_kernel", "peak_source": peak_src,
                      "note": "algorithmic 24 B per (chain,cadence); chains share t,y,sigma through L2, and the kernel is fp64-pipe bound"},

@@ -13,6 +13,8 @@ LIB_PATH = os.path.join(_HERE, "libxo_b200.so")
 NEL = 16
 NGRAD = 10
 NGRAD_RV = 7
+NPAR = 8
+NSTAR = 4
 MAX_STENCIL = 33
 MAX_PLANETS = 8
 
@@ -43,6 +45,10 @@ _SIGNATURES = {
     "xo_transit_logp_grad_workspace": (_sz, [_i64, _i64, _i64]),
     "xo_transit_logp_grad": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _dbl, _vp, _vp, _vp, _vp,
                                     _vp, _sz, _vp]),
+    "xo_transit_model_workspace": (_sz, [_i64, _i64, _i64]),
+    "xo_transit_model_logp_grad": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _dbl, _i32, _dbl, _vp,
+                                          _vp, _vp, _vp, _vp, _sz, _vp]),
+    "xo_elements_from_params": (_i32, [_vp, _vp, _i64, _i64, _dbl, _i32, _vp, _vp, _vp]),
     "xo_orbit_eval": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "xo_rv_logp_grad_workspace": (_sz, [_i64, _i64, _i64]),
     "xo_rv_logp_grad": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _dbl, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -54,6 +60,8 @@ _SIGNATURES = {
     "xo_transit_lc_host": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _i32]),
     "xo_transit_logp_grad_host": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _dbl, _vp, _vp, _vp,
                                          _vp, _i32]),
+    "xo_transit_model_logp_grad_host": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _dbl, _i32, _dbl,
+                                               _vp, _vp, _vp, _vp, _i32]),
 }
 
 EXPORTS = tuple(sorted(_SIGNATURES))

@@ -15,17 +15,33 @@
 
 namespace {
 
+// Per host thread and device: one non-blocking stream, created on first use, and the
+// device's default memory pool told to keep freed blocks (release threshold = max) so that
+// cudaMallocAsync/cudaFreeAsync in a sampling loop do not go back to the OS every call.
+// This is the only state the library keeps; it never affects results.
 struct DeviceScope {
   int prev = -1;
   cudaError_t err = cudaSuccess;
   cudaStream_t st = nullptr;
   explicit DeviceScope(int device) {
+    static thread_local cudaStream_t cache[64] = {nullptr};
     err = cudaGetDevice(&prev);
     if (err == cudaSuccess) err = cudaSetDevice(device);
-    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (err != cudaSuccess) return;
+    if (device >= 0 && device < 64 && cache[device]) {
+      st = cache[device];
+      return;
+    }
+    err = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (err != cudaSuccess) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    if (device >= 0 && device < 64) cache[device] = st;
   }
   ~DeviceScope() {
-    if (st) cudaStreamDestroy(st);
     if (prev >= 0) cudaSetDevice(prev);
   }
 };
@@ -213,6 +229,44 @@ int xo_transit_logp_grad_host(const double *t, const double *y, const double *iv
   XO_TRY(d2h(logp, dlp, (size_t)C * 8, ds.st));
   XO_TRY(d2h(gel, dge, (size_t)C * P * XO_NGRAD * 8, ds.st));
   XO_TRY(d2h(gcl, dgc, (size_t)C * 3 * 8, ds.st));
+  XO_TRY(d2h(gmean, dgm, (size_t)C * 8, ds.st));
+  XO_TRY(cudaStreamSynchronize(ds.st));
+  return 0;
+}
+
+int xo_transit_model_logp_grad_host(const double *t, const double *y, const double *ivar, int64_t N, const double *par,
+                                    const double *star, const double *mean, int64_t C, int64_t P, const double *dtk,
+                                    const double *wk, int K, double texp, int use_in_transit, double lognorm,
+                                    double *logp, double *gpar, double *gstar, double *gmean, int device) {
+  if (N <= 0 || C < 0 || P <= 0 || K < 1) return XO_EINVAL;
+  if (C == 0) return 0;
+  if (!t || !y || !ivar || !par || !star || !mean || !dtk || !wk || !logp || !gpar || !gstar || !gmean) return XO_EINVAL;
+  DeviceScope ds(device);
+  XO_TRY(ds.err);
+  const size_t ws = xo_transit_model_workspace(N, C, P);
+  Arena ar(3 * pad(N) + pad(C * P * XO_NPAR) + pad(C * XO_NSTAR) + pad(C) + 2 * pad(K) + pad(C) + pad(C * P * XO_NPAR) +
+               pad(C * XO_NSTAR) + pad(C) + pad(ws, 1),
+           ds.st);
+  XO_TRY(ar.err);
+  double *dt = ar.take<double>(N), *dy = ar.take<double>(N), *dv = ar.take<double>(N);
+  double *dp = ar.take<double>(C * P * XO_NPAR), *dst = ar.take<double>(C * XO_NSTAR), *dm = ar.take<double>(C);
+  double *dd = ar.take<double>(K), *dw = ar.take<double>(K);
+  double *dlp = ar.take<double>(C), *dgp = ar.take<double>(C * P * XO_NPAR), *dgs = ar.take<double>(C * XO_NSTAR),
+         *dgm = ar.take<double>(C);
+  void *dws = ar.take<char>(ws);
+  XO_TRY(h2d(dt, t, (size_t)N * 8, ds.st));
+  XO_TRY(h2d(dy, y, (size_t)N * 8, ds.st));
+  XO_TRY(h2d(dv, ivar, (size_t)N * 8, ds.st));
+  XO_TRY(h2d(dp, par, (size_t)C * P * XO_NPAR * 8, ds.st));
+  XO_TRY(h2d(dst, star, (size_t)C * XO_NSTAR * 8, ds.st));
+  XO_TRY(h2d(dm, mean, (size_t)C * 8, ds.st));
+  XO_TRY(h2d(dd, dtk, (size_t)K * 8, ds.st));
+  XO_TRY(h2d(dw, wk, (size_t)K * 8, ds.st));
+  XO_RC(xo_transit_model_logp_grad(dt, dy, dv, N, dp, dst, dm, C, P, dd, dw, K, texp, use_in_transit, lognorm, dlp, dgp,
+                                   dgs, dgm, dws, ws, ds.st));
+  XO_TRY(d2h(logp, dlp, (size_t)C * 8, ds.st));
+  XO_TRY(d2h(gpar, dgp, (size_t)C * P * XO_NPAR * 8, ds.st));
+  XO_TRY(d2h(gstar, dgs, (size_t)C * XO_NSTAR * 8, ds.st));
   XO_TRY(d2h(gmean, dgm, (size_t)C * 8, ds.st));
   XO_TRY(cudaStreamSynchronize(ds.st));
   return 0;

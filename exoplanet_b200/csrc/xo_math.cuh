@@ -44,6 +44,53 @@ XO_HD double rcp(double x) {
 #endif
 }
 
+// ~1 ulp reciprocal without the IEEE fix-up paths of __drcp_rn: MUFU.RCP64H seed
+// (rcp.approx.ftz.f64, ~20 bits) + two Newton steps.  x must be a normal, finite, non-zero
+// double (all call sites divide by quantities bounded away from 0 and inf).
+XO_HD double rcp_fast(double x) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+#else
+  return 1.0 / x;
+#endif
+}
+
+// reciprocal to ~1e-12 relative (seed + one Newton step): enough where the quotient is a
+// small correction term
+XO_HD double rcp_mid(double x) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  return fma(r, fma(e, e, e), r);
+#else
+  return 1.0 / x;
+#endif
+}
+
+// ~1 ulp square root of a normal positive double: MUFU.RSQ64H seed + two coupled
+// Newton (Goldschmidt) steps.  sqrt_fast(0) = 0.
+XO_HD double sqrt_fast(double x) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double g = x * r, h = 0.5 * r;
+  double e = fma(-h, g, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  e = fma(-h, g, 0.5);
+  g = fma(g, e, g);
+  return x > 0.0 ? g : 0.0;
+#else
+  return sqrt(x);
+#endif
+}
+
 // ---------------------------------------------------------------------------
 // sin/cos on [0, pi] that also return E - sin E and 1 - cos E free of cancellation.
 // Polynomials from tools/gen_poly.py (|x| <= 1.02 pi/4; abs err 5e-18 / 1e-18).
@@ -105,25 +152,54 @@ XO_HD double reduce_2pi(double M) {
 
 // ---------------------------------------------------------------------------
 // Kepler: (M, e) -> (sin f, cos f).  0 <= e < 1.
+//
+// The Markley (1995) starter only has to land within ~3e-4 (relative) of the root -- the
+// 5th-order correction that follows squares-and-more that away -- so it is evaluated in
+// fp32 on the FMA/MUFU pipes, which run beside the fp64 pipe that bounds this kernel.
+// 1 - e is formed in fp64 first so the e -> 1 corner keeps its relative accuracy.
 // ---------------------------------------------------------------------------
+XO_HD double markley_start_f32(double Ma, double e, double ome) {
+  const float M = (float)Ma, ef = (float)e, om = (float)ome;
+  constexpr float fac = (float)(1.0 / (kPi - 6.0 / kPi));
+  constexpr float pif = (float)kPi;
+#if defined(__CUDA_ARCH__)
+  const float rope = __frcp_rn(1.0f + ef);
+#else
+  const float rope = 1.0f / (1.0f + ef);
+#endif
+  const float alpha = fmaf(1.6f * fac * rope, pif - M, 3.0f * pif * fac);
+  const float d = fmaf(alpha, ef, 3.0f * om);
+  const float ad = alpha * d;
+  const float M2 = M * M;
+  const float r = fmaf(3.0f * ad, d - om, M2) * M;
+  const float q = fmaf(2.0f * ad, om, -M2);
+  const float q2 = q * q;
+  const float disc = fmaxf(fmaf(q2, q, r * r), 1e-37f);
+#if defined(__CUDA_ARCH__)
+  const float y = fabsf(r) + disc * __frsqrt_rn(disc);
+  float w = exp2f((2.0f / 3.0f) * __log2f(y));  // cbrt(y)^2
+#else
+  const float y = fabsf(r) + sqrtf(disc);
+  float w = cbrtf(y);
+  w = w * w;
+#endif
+  const float W = fmaf(w, w + q, q2);
+  const float num = fmaf(2.0f * r, w, M * W), den = d * W;
+#if defined(__CUDA_ARCH__)
+  float E = __fdividef(num, den);
+#else
+  float E = num / den;
+#endif
+  if (!(den > 0.0f) || !(E >= 0.0f)) E = M;  // underflow guard (M absurdly small): Newton recovers
+  return (double)E;
+}
+
 XO_HD void kepler_solve(double M, double e, double &sinf, double &cosf) {
   double Mr = reduce_2pi(M);
   double Ma = fmin(fabs(Mr), kPi);
   double ome = 1.0 - e;
   double ope = 1.0 + e;
-  // Markley (1995) starter: one cbrt, one sqrt, two reciprocals
-  constexpr double fac = 1.0 / (kPi - 6.0 / kPi);
-  double alpha = fma(1.6 * fac * rcp(ope), kPi - Ma, 3.0 * kPi * fac);
-  double d = fma(alpha, e, 3.0 * ome);
-  double ad = alpha * d;
-  double M2 = Ma * Ma;
-  double r = fma(3.0 * ad, d - ome, M2) * Ma;
-  double q = fma(2.0 * ad, ome, -M2);
-  double q2 = q * q;
-  double w = cbrt(fabs(r) + sqrt(fma(q2, q, r * r)));
-  w = w * w;
-  double W = fma(w, w + q, q2);
-  double E = fma(2.0 * r, w, Ma * W) * rcp(d * W);
+  double E = markley_start_f32(Ma, e, ome);
   // one 5th-order correction: root of the quartic Taylor polynomial in dE,
   // f0 + f1 dE + f2 dE^2/2 + f3 dE^3/6 - f2 dE^4/24 = 0, by fixed-point on 1/f1
   double s, c, EmS, omC;
@@ -132,11 +208,11 @@ XO_HD void kepler_solve(double M, double e, double &sinf, double &cosf) {
   double f1 = fma(e, omC, ome);
   double f2 = e * s;
   double f3 = e * c;
-  double rf1 = rcp(f1);
+  double rf1 = rcp_mid(f1);
   double h2 = 0.5 * f2, h3 = f3 * (1.0 / 6.0), h4 = -f2 * (1.0 / 24.0);
   double dE = -f0 * rf1;
 #pragma unroll
-  for (int it = 0; it < 4; ++it) dE = -fma(dE * dE, fma(dE, fma(dE, h4, h3), h2), f0) * rf1;
+  for (int it = 0; it < 3; ++it) dE = -fma(dE * dE, fma(dE, fma(dE, h4, h3), h2), f0) * rf1;
   // sin/cos(E + dE) by angle addition (|dE| < ~1e-2)
   double d2 = dE * dE;
   double sd = dE * fma(d2, fma(d2, fma(d2, -1.0 / 5040.0, 1.0 / 120.0), -1.0 / 6.0), 1.0);
@@ -144,8 +220,8 @@ XO_HD void kepler_solve(double M, double e, double &sinf, double &cosf) {
   double s1 = s + fma(c, sd, s * cdm1);
   double omC1 = omC - fma(c, cdm1, -s * sd);
   double den = fma(e, omC1, ome);  // 1 - e cos E
-  double rden = rcp(den);
-  double sq = sqrt(ome * ope);
+  double rden = rcp_fast(den);
+  double sq = sqrt_fast(ome * ope);
   sinf = (Mr < 0.0 ? -sq : sq) * s1 * rden;
   cosf = (ome - omC1) * rden;  // (cos E - e) without cancellation
 }

@@ -24,15 +24,18 @@
 //    are bit-reproducible run to run; a second tiny kernel folds the per-warp partials.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "xo_common.cuh"
 #include "xo_math.cuh"
+#include "xo_transit.cuh"
 
 namespace {
 
 constexpr int kWarps = 4;
 constexpr int kThreads = kWarps * 32;
-constexpr int kQueue = 64;
-constexpr int kNBase = 5;  // lp, gmean, gcl[3]
+using xo::kNBase;
+using xo::Split;
 constexpr unsigned kFull = 0xffffffffu;
 
 struct ChainSmem {
@@ -91,9 +94,13 @@ __global__ void __launch_bounds__(256) transit_lc_fwd_kernel(const double *__res
 }
 
 // ---------------------------------------------------------------------------
-// logp + grad (see header comment)
+// logp + grad (see header comment).  kMinBlocks trades registers for resident warps.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) transit_logp_grad_kernel(
+constexpr int kUnroll = 4;                      // 32-cadence groups loaded per sweep step
+constexpr int kQueue = 32 * (kUnroll + 1);      // 31 left over + kUnroll * 32 new entries
+
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel(
     const double *__restrict__ t, const double *__restrict__ y, const double *__restrict__ ivar, int64_t N,
     const double *__restrict__ elem, const double *__restrict__ cl, const double *__restrict__ mean, int P,
     const double *__restrict__ dtk, const double *__restrict__ wk, int K, int64_t L, int slots,
@@ -114,13 +121,13 @@ __global__ void __launch_bounds__(kThreads) transit_logp_grad_kernel(
   const double mean_c = sm.mean;
   const uint32_t lt_mask = (1u << lane) - 1u;
 
-  // drain m (<= 32) entries from the front of queue p
-  auto drain = [&](int p, int m) {
+  // evaluate m (<= 32) queued entries of planet p starting at queue offset off
+  auto drain = [&](int p, int off, int m) {
     double g[XO_NGRAD];
 #pragma unroll
     for (int j = 0; j < XO_NGRAD; ++j) g[j] = 0.0;
     if (lane < m) {
-      const uint32_t idx = queue[warp][p][lane];
+      const uint32_t idx = queue[warp][p][off + lane];
       const double tt = __ldg(t + idx), yy = __ldg(y + idx), iv = __ldg(ivar + idx);
       double gs[3] = {0.0, 0.0, 0.0};
       double ltot = 0.0;
@@ -152,49 +159,58 @@ __global__ void __launch_bounds__(kThreads) transit_logp_grad_kernel(
       double v = warp_sum(g[j]);
       if (lane == 0) gacc[warp][p][j] += v;
     }
-    // move the tail to the front
-    __syncwarp();
-    uint32_t a = (lane + m < kQueue) ? queue[warp][p][lane + m] : 0u;
-    uint32_t b = (lane + 32 + m < kQueue) ? queue[warp][p][lane + 32 + m] : 0u;
-    __syncwarp();
-    queue[warp][p][lane] = a;
-    queue[warp][p][lane + 32] = b;
-    __syncwarp();
   };
 
   const int64_t start = (int64_t)slot * L;
   const int64_t end = min(start + L, N);
-  for (int64_t base = start; base < end; base += 32) {
-    const int64_t i = base + lane;
-    const bool valid = i < end;
-    double tt = 0.0, yy = 0.0, iv = 0.0;
-    if (valid) {
-      tt = __ldg(t + i);
-      yy = __ldg(y + i);
-      iv = __ldg(ivar + i);
+#pragma unroll 1
+  for (int64_t base = start; base < end; base += 32 * kUnroll) {
+    double tt[kUnroll], yy[kUnroll], iv[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {  // all loads of the step in flight together
+      const int64_t i = base + 32 * u + lane;
+      const bool valid = i < end;
+      tt[u] = valid ? __ldg(t + i) : 0.0;
+      yy[u] = valid ? __ldg(y + i) : 0.0;
+      iv[u] = valid ? __ldg(ivar + i) : 0.0;
     }
-    const double r0 = yy - mean_c;
-    const double wr = iv * r0;
-    lp = fma(-0.5 * wr, r0, lp);
-    gm += wr;
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const double r0 = yy[u] - mean_c;
+      const double wr = iv[u] * r0;
+      lp = fma(-0.5 * wr, r0, lp);
+      gm += wr;
+    }
     for (int p = 0; p < P; ++p) {
-      const bool inw = valid && xo::in_window(sm.elem[p], sm.rperiod[p], tt);
-      const uint32_t mask = __ballot_sync(kFull, inw);
-      if (mask == 0u) continue;
       int fill = __shfl_sync(kFull, cnt, p);
-      if (inw) queue[warp][p][fill + __popc(mask & lt_mask)] = (uint32_t)i;
-      fill += __popc(mask);
+      const int fill0 = fill;
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int64_t i = base + 32 * u + lane;
+        const bool inw = (i < end) && xo::in_window(sm.elem[p], sm.rperiod[p], tt[u]);
+        const uint32_t mask = __ballot_sync(kFull, inw);
+        if (inw) queue[warp][p][fill + __popc(mask & lt_mask)] = (uint32_t)i;
+        fill += __popc(mask);
+      }
+      if (fill == fill0) continue;
       __syncwarp();
-      if (fill >= 32) {
-        drain(p, 32);
-        fill -= 32;
+      int off = 0;
+#pragma unroll 1
+      for (; fill - off >= 32; off += 32) drain(p, off, 32);
+      if (off > 0) {  // move the < 32 left-over entries to the front
+        const int rem = fill - off;
+        const uint32_t v = lane < rem ? queue[warp][p][off + lane] : 0u;
+        __syncwarp();
+        if (lane < rem) queue[warp][p][lane] = v;
+        __syncwarp();
+        fill = rem;
       }
       if (lane == p) cnt = fill;
     }
   }
   for (int p = 0; p < P; ++p) {
     int fill = __shfl_sync(kFull, cnt, p);
-    if (fill > 0) drain(p, fill);
+    if (fill > 0) drain(p, 0, fill);
   }
   lp = warp_sum(lp);
   gm = warp_sum(gm);
@@ -364,23 +380,6 @@ __global__ void fold_rv_kernel(const double *__restrict__ partial, int slots, in
     grv[c * P * XO_NGRAD_RV + (j - 2)] = acc;
 }
 
-// work split for the logp kernels: slots (warps or CTAs) per chain and cadences per slot
-struct Split {
-  int slots;
-  int64_t L;
-};
-inline Split split_transit(int64_t N, int64_t C) {
-  const int sms = xo::sm_count();
-  // aim at ~24 resident warps per SM over the whole launch, at least 256 cadences per warp
-  int64_t target = ((int64_t)sms * 24 + C - 1) / C;
-  int64_t maxw = (N + 255) / 256;
-  int64_t w = target < 1 ? 1 : (target > maxw ? maxw : target);
-  if (w < 1) w = 1;
-  w = ((w + kWarps - 1) / kWarps) * kWarps;  // whole CTAs
-  int64_t L = (N + w - 1) / w;
-  L = ((L + 31) / 32) * 32;
-  return Split{(int)w, L};
-}
 inline Split split_rv(int64_t N, int64_t C) {
   const int sms = xo::sm_count();
   int64_t target = ((int64_t)sms * 6 + C - 1) / C;
@@ -392,7 +391,39 @@ inline Split split_rv(int64_t N, int64_t C) {
   return Split{(int)s, L};
 }
 
-inline int check_batch(int64_t N, int64_t C, int64_t P) {
+}  // namespace
+
+namespace xo {
+
+// tuning knobs (read once): XO_TRANSIT_MINBLOCKS in {2,3,4} picks the register cap of the
+// logp kernel (254 / 168 / 128 registers), XO_TRANSIT_WARPS_PER_SM the launch width.
+static int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+int transit_min_blocks() {
+  static int v = env_int("XO_TRANSIT_MINBLOCKS", 3);
+  return v;
+}
+static int transit_warps_per_sm() {
+  static int v = env_int("XO_TRANSIT_WARPS_PER_SM", 24);
+  return v;
+}
+
+Split split_transit(int64_t N, int64_t C) {
+  const int sms = sm_count();
+  // aim at ~24 warps per SM over the whole launch, at least 256 cadences per warp
+  int64_t target = ((int64_t)sms * transit_warps_per_sm() + C - 1) / C;
+  int64_t maxw = (N + 255) / 256;
+  int64_t w = target < 1 ? 1 : (target > maxw ? maxw : target);
+  if (w < 1) w = 1;
+  w = ((w + kWarps - 1) / kWarps) * kWarps;  // whole CTAs
+  int64_t L = (N + w - 1) / w;
+  L = ((L + 31) / 32) * 32;
+  return Split{(int)w, L};
+}
+
+int check_batch(int64_t N, int64_t C, int64_t P) {
   if (N < 0 || C < 0 || P < 0) return XO_EINVAL;
   if (P > XO_MAX_PLANETS) return XO_ERANGE;
   if (C > 65535) return XO_ERANGE;  // gridDim.y
@@ -400,7 +431,26 @@ inline int check_batch(int64_t N, int64_t C, int64_t P) {
   return 0;
 }
 
-}  // namespace
+void launch_transit_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *elem,
+                              const double *cl, const double *mean, int64_t C, int P, const double *dtk,
+                              const double *wk, int K, Split sp, double *partial, cudaStream_t st) {
+  dim3 grid(sp.slots / kWarps, (unsigned)C);
+  switch (transit_min_blocks()) {
+    case 2:
+      transit_logp_grad_kernel<2><<<grid, kThreads, 0, st>>>(t, y, ivar, N, elem, cl, mean, P, dtk, wk, K, sp.L, sp.slots, partial);
+      break;
+    case 4:
+      transit_logp_grad_kernel<4><<<grid, kThreads, 0, st>>>(t, y, ivar, N, elem, cl, mean, P, dtk, wk, K, sp.L, sp.slots, partial);
+      break;
+    default:
+      transit_logp_grad_kernel<3><<<grid, kThreads, 0, st>>>(t, y, ivar, N, elem, cl, mean, P, dtk, wk, K, sp.L, sp.slots, partial);
+  }
+}
+
+}  // namespace xo
+
+using xo::check_batch;
+using xo::split_transit;
 
 extern "C" {
 
@@ -440,9 +490,7 @@ int xo_transit_logp_grad(const double *t, const double *y, const double *ivar, i
   Split sp = split_transit(N, C);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   double *partial = static_cast<double *>(workspace);
-  dim3 grid(sp.slots / kWarps, (unsigned)C);
-  transit_logp_grad_kernel<<<grid, kThreads, 0, st>>>(t, y, ivar, N, elem, cl, mean, (int)P, dtk, wk, K, sp.L, sp.slots,
-                                                     partial);
+  xo::launch_transit_logp_grad(t, y, ivar, N, elem, cl, mean, C, (int)P, dtk, wk, K, sp, partial, st);
   const int nacc = kNBase + (int)P * XO_NGRAD;
   const int64_t tot = C * nacc;
   fold_partials_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(partial, sp.slots, nacc, C, (int)P, lognorm, logp,

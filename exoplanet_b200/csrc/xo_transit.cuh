@@ -1,0 +1,26 @@
+// xo_transit.cuh -- host-side pieces of the fused logp+grad launch shared with xo_model.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "xo_common.cuh"
+
+namespace xo {
+
+constexpr int kNBase = 5;  // per-warp partial layout: lp, gmean, gcl[3], then gel[P][XO_NGRAD]
+
+// work split of one chain: slots (warps) and cadences per slot
+struct Split {
+  int slots;
+  int64_t L;
+};
+Split split_transit(int64_t N, int64_t C);
+int check_batch(int64_t N, int64_t C, int64_t P);
+int transit_min_blocks();
+
+// enqueue transit_logp_grad_kernel; partial[C][slots][kNBase + P*XO_NGRAD]
+void launch_transit_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *elem,
+                              const double *cl, const double *mean, int64_t C, int P, const double *dtk,
+                              const double *wk, int K, Split sp, double *partial, cudaStream_t st);
+
+}  // namespace xo

@@ -203,3 +203,72 @@ class RvLogp:
 
     def __call__(self, elem, gamma):
         return _RvLogp.apply(elem, gamma, self.data)
+
+
+# ---------------------------------------------------------------------------
+# parameter-level model: prologue + logp + reverse pass in three launches
+# ---------------------------------------------------------------------------
+def pack_params(period, t0, ecc, omega, b, ror, m_planet=0.0, K=0.0):
+    """[..., P] tensors -> par[..., P, 8] in the order the C ABI expects (XO_NPAR)."""
+    period = torch.as_tensor(period, dtype=torch.float64)
+    cols = [torch.as_tensor(x, dtype=torch.float64, device=period.device) for x in (period, t0, ecc, omega, b, ror, m_planet, K)]
+    return torch.stack(torch.broadcast_tensors(*cols), dim=-1).contiguous()
+
+
+def pack_star(r_star, m_star, u1, u2):
+    """[C] tensors -> star[C, 4] (XO_NSTAR)."""
+    u1 = torch.as_tensor(u1, dtype=torch.float64)
+    cols = [torch.as_tensor(x, dtype=torch.float64, device=u1.device) for x in (r_star, m_star, u1, u2)]
+    return torch.stack(torch.broadcast_tensors(*cols), dim=-1).contiguous()
+
+
+class TransitModel:
+    """``logp, d logp/d params`` of a transit light-curve model with Gaussian noise, from
+    sampler-side parameters, entirely on the device (the fused counterpart of the PyMC model
+    in /root/reference/docs/tutorials/data-and-models.md:458-509)."""
+
+    def __init__(self, data, texp=None, oversample=7, order=0, use_in_transit=True):
+        self.data = data
+        self.texp = 0.0 if texp is None else float(texp)
+        self.use_in_transit = bool(use_in_transit)
+        st = exposure_stencil(texp, oversample, order)
+        self.dtk, self.wk = _stencil_dev(st, data.device)
+        self._ws = None
+
+    def logp_grad(self, par, star, mean):
+        lib = _lib.require_cuda()
+        par = par.detach().contiguous()
+        star = star.detach().contiguous()
+        mean = mean.detach().contiguous()
+        Cc, P = par.shape[0], par.shape[1]
+        d = self.data
+        need = lib.xo_transit_model_workspace(d.n, Cc, P)
+        if self._ws is None or self._ws.numel() * 8 < need:
+            self._ws = torch.empty(need // 8 + 1, dtype=torch.float64, device=d.device)
+        logp = torch.empty(Cc, dtype=torch.float64, device=d.device)
+        gpar = torch.empty_like(par)
+        gstar = torch.empty_like(star)
+        gmean = torch.empty_like(mean)
+        with torch.cuda.device(d.device):
+            _lib.check(lib.xo_transit_model_logp_grad(_ptr(d.t), _ptr(d.y), _ptr(d.ivar), d.n, _ptr(par), _ptr(star), _ptr(mean), Cc, P,
+                                                      _ptr(self.dtk), _ptr(self.wk), self.dtk.numel(), self.texp,
+                                                      int(self.use_in_transit), d.lognorm, _ptr(logp), _ptr(gpar), _ptr(gstar),
+                                                      _ptr(gmean), _ptr(self._ws), self._ws.numel() * 8, _lib.stream_ptr()),
+                       "transit_model_logp_grad")
+        return logp, gpar, gstar, gmean
+
+    def __call__(self, par, star, mean):
+        return _TransitModelLogp.apply(par, star, mean, self)
+
+
+class _TransitModelLogp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, par, star, mean, model):
+        logp, gpar, gstar, gmean = model.logp_grad(par, star, mean)
+        ctx.save_for_backward(gpar, gstar, gmean)
+        return logp
+
+    @staticmethod
+    def backward(ctx, g):
+        gpar, gstar, gmean = ctx.saved_tensors
+        return g[:, None, None] * gpar, g[:, None] * gstar, g * gmean, None

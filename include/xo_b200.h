@@ -62,6 +62,8 @@ extern "C" {
 #define XO_EL_KRV 13    /* RV semi-amplitude (keplerian.py:658-670)      */
 #define XO_NGRAD 10     /* d/d(t0,tref,n,e,cosw,sinw,cosi,sini,aor,ror)  */
 #define XO_NGRAD_RV 7   /* d/d(t0,tref,n,e,cosw,sinw,Krv)                */
+#define XO_NPAR 8       /* per (chain, planet): period, t0, ecc, omega, b, r/R*, m_planet, K_rv */
+#define XO_NSTAR 4      /* per chain: R_star, M_star, u1, u2                              */
 #define XO_MAX_STENCIL 33 /* exposure-time sub-samples per cadence        */
 #define XO_MAX_PLANETS 8
 
@@ -109,6 +111,21 @@ int xo_transit_logp_grad(const double *t, const double *y, const double *ivar, i
                          int K, double lognorm, double *logp, double *gel, double *gcl, double *gmean, void *workspace,
                          size_t workspace_bytes, void *stream);
 
+/* The same evaluation from sampler-side parameters: prologue (KeplerianOrbit.__init__,
+ * keplerian.py:133-281; in_transit window :729-767; get_cl limb_dark.py:11-18) + logp +
+ * the prologue's reverse pass.  par[C][P][XO_NPAR], star[C][XO_NSTAR], mean[C] ->
+ * logp[C], gpar[C][P][XO_NPAR], gstar[C][XO_NSTAR], gmean[C].  texp = exposure time used to
+ * widen the window (0 if none; the stencil dtk/wk carries the integration itself). */
+size_t xo_transit_model_workspace(int64_t N, int64_t C, int64_t P);
+int xo_transit_model_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *par,
+                               const double *star, const double *mean, int64_t C, int64_t P, const double *dtk,
+                               const double *wk, int K, double texp, int use_in_transit, double lognorm, double *logp,
+                               double *gpar, double *gstar, double *gmean, void *workspace, size_t workspace_bytes,
+                               void *stream);
+/* prologue only: elem[C][P][XO_NEL], cl[C][3] */
+int xo_elements_from_params(const double *par, const double *star, int64_t C, int64_t P, double texp, int use_in_transit,
+                            double *elem, double *cl, void *stream);
+
 /* relative position / R_star and RV shape for every (chain, cadence, planet):
  * X,Y,Z,rv each [C][N][P], any may be NULL (keplerian.py:380-409, 658-670) */
 int xo_orbit_eval(const double *t, int64_t N, const double *elem, int64_t C, int64_t P, double *X, double *Y, double *Z,
@@ -141,6 +158,10 @@ int xo_transit_logp_grad_host(const double *t, const double *y, const double *iv
                               const double *cl, const double *mean, int64_t C, int64_t P, const double *dtk,
                               const double *wk, int K, double lognorm, double *logp, double *gel, double *gcl,
                               double *gmean, int device);
+int xo_transit_model_logp_grad_host(const double *t, const double *y, const double *ivar, int64_t N, const double *par,
+                                    const double *star, const double *mean, int64_t C, int64_t P, const double *dtk,
+                                    const double *wk, int K, double texp, int use_in_transit, double lognorm,
+                                    double *logp, double *gpar, double *gstar, double *gmean, int device);
 
 #ifdef __cplusplus
 }

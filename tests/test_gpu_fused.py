@@ -68,8 +68,7 @@ def test_logp_grad_matches_oracle(P, texp, C):
         el_o = O.elements_from_params(p["period"], p["t0"], p["ecc"], p["omega"], p["b"], p["ror"], texp=texp, K=p["K"])
     st = O.stencil(texp, 7, 0)
     truth = O.transit_lc(t, el_o, cl, *st).sum(-1)
-    y = truth + p["mean"][:, None] * 0  # each chain sees the same data: chain 0's truth + noise
-    y = truth[0] + synthetic.noise(N)
+    y = truth[0] + synthetic.noise(N)  # every chain sees the same data: chain 0's truth + noise
     sigma = 5e-4
     data = fused.TransitData(t, y, np.full(N, sigma), device=DEV)
     logp, gel, gcl, gmean = fused.transit_logp_grad(data, dev(el_o), dev(cl), dev(p["mean"]), fused.exposure_stencil(texp))
@@ -156,9 +155,10 @@ def test_orbit_eval_and_rv_match_oracle():
 def test_known_answer_B6(golden):
     b6 = golden("end_to_end")["B6"]
     el = elements.elements_from_params(dev(b6["period"]), dev(0.0), dev(b6["ecc"]), dev(b6["omega"]), dev(0.0), dev(b6["r"]))
+    el = el.reshape(16)
     assert abs(el[8].item() - b6["a"]) < 1e-12
     assert abs(el[11].item() - b6["t_start"]) < 1e-10 and abs(el[12].item() - b6["t_end"]) < 1e-10
-    cl = fused.limb_dark_coeffs(dev(b6["u"][0]), dev(b6["u"][1]))
+    cl = fused.limb_dark_coeffs(dev(b6["u"][0]), dev(b6["u"][1])).reshape(3)
     lc = fused.light_curve(dev(b6["t"]), el[None, None, :], cl[None, :])[0, :, 0].cpu().numpy()
     assert np.max(np.abs(lc - np.array(b6["lc"]))) < 5e-15
 
@@ -185,3 +185,51 @@ def test_host_buffer_logp_entry_point():
     lc = np.empty((Cn, N, P))
     rc = _lib.load().xo_transit_lc_host(f(t), N, f(el_c), f(cl_c), Cn, P, f(dtk), f(wk), 1, f(lc), 0)
     assert rc == 0 and np.max(np.abs(lc - O.transit_lc(t, el_o, cl, dtk, wk))) < 1e-14
+
+
+@pytest.mark.parametrize("P,texp", [(1, None), (3, 0.02)])
+def test_parameter_level_model_matches_autograd_prologue_and_oracle(P, texp):
+    N, C = 30000, 6
+    p = synthetic.transit_params(C, P, seed=21)
+    t = synthetic.cadence_times(N)
+    y = synthetic.noise(N)
+    data = fused.TransitData(t, y, np.full(N, 5e-4), device=DEV)
+    rs = np.linspace(0.9, 1.2, C)
+    ms = np.linspace(0.8, 1.3, C)
+    par = fused.pack_params(dev(p["period"]), dev(p["t0"]), dev(p["ecc"]), dev(p["omega"]), dev(p["b"]), dev(p["ror"]),
+                            dev(p["m_planet"]), dev(p["K"]))
+    star = fused.pack_star(dev(rs), dev(ms), dev(p["u1"]), dev(p["u2"]))
+    mean = dev(p["mean"])
+    model = fused.TransitModel(data, texp=texp)
+    logp, gpar, gstar, gmean = model.logp_grad(par, star, mean)
+    # (a) same thing through the differentiable torch prologue + element-level kernel
+    par_t = par.clone().requires_grad_(True)
+    star_t = star.clone().requires_grad_(True)
+    mean_t = mean.clone().requires_grad_(True)
+    el = elements.elements_from_params(par_t[..., 0], par_t[..., 1], par_t[..., 2], par_t[..., 3], par_t[..., 4], par_t[..., 5],
+                                       r_star=star_t[:, None, 0], m_star=star_t[:, None, 1], m_planet=par_t[..., 6], texp=texp)
+    op = fused.TransitLogp(data, texp=texp)
+    lp2 = op(el, fused.limb_dark_coeffs(star_t[:, 2], star_t[:, 3]), mean_t)
+    lp2.sum().backward()
+    assert torch.allclose(logp, lp2.detach(), rtol=1e-12, atol=0)
+    sc = par_t.grad.abs().amax(dim=(0, 1), keepdim=True) + 1e-300
+    assert ((gpar - par_t.grad).abs() / sc).max().item() < 1e-9
+    assert torch.allclose(gstar, star_t.grad, rtol=1e-8, atol=1e-6 * star_t.grad.abs().max().item())
+    assert torch.allclose(gmean, mean_t.grad, rtol=1e-10)
+    # (b) oracle logp on the same parameters
+    el_o = O.elements_from_params(p["period"], p["t0"], p["ecc"], p["omega"], p["b"], p["ror"], r_star=rs[:, None], m_star=ms[:, None],
+                                  m_planet=p["m_planet"], texp=texp)
+    lo = O.transit_logp_grad(t, y, np.full(N, 1 / 5e-4 ** 2), el_o, O.get_cl(p["u1"], p["u2"]), p["mean"], *O.stencil(texp),
+                             lognorm=data.lognorm)[0]
+    assert np.max(np.abs(logp.cpu().numpy() - lo) / np.abs(lo)) < 1e-11
+    # elements produced by the prologue kernel
+    import ctypes as Ct
+    from exoplanet_b200 import _lib
+    elem = torch.empty((C, P, 16), dtype=torch.float64, device=DEV)
+    clk = torch.empty((C, 3), dtype=torch.float64, device=DEV)
+    rc = _lib.load().xo_elements_from_params(Ct.c_void_p(par.data_ptr()), Ct.c_void_p(star.data_ptr()), C, P, 0.0 if texp is None else texp,
+                                             1, Ct.c_void_p(elem.data_ptr()), Ct.c_void_p(clk.data_ptr()), None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert np.allclose(elem.cpu().numpy()[..., :11], el_o[..., :11], rtol=1e-13, atol=1e-13)
+    assert np.allclose(elem.cpu().numpy()[..., 11:13], el_o[..., 11:13], rtol=0, atol=1e-10)

@@ -1,19 +1,26 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, smoke, bench, ncu launch list + full captures.
-# usage (under gpurun): bash tools/gpu_round.sh [tag]
+# One GPU-box visit: parity tests, smoke, bench, tuning sweep, ncu launch list + full captures.
+# usage (under gpurun): bash tools/gpu_round.sh [tag] [quick]
 TAG=${1:-r01}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_gpu.txt 2>&1
-lscpu | head -20 >> $OUT/${TAG}_gpu.txt; nproc >> $OUT/${TAG}_gpu.txt
-timeout 1200 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1; echo "pytest exit $?" >> $OUT/${TAG}_pytest.log
+lscpu | grep -E "Model name|^CPU\(s\)|Thread|Core|Socket" >> $OUT/${TAG}_gpu.txt; nproc >> $OUT/${TAG}_gpu.txt
+timeout 1500 python -m pytest tests -m gpu -q > $OUT/${TAG}_pytest.log 2>&1; echo "pytest exit $?" >> $OUT/${TAG}_pytest.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke exit $?" >> $OUT/${TAG}_smoke.log
-timeout 600 python bench.py --steps 20 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench exit $?" >> $OUT/${TAG}_bench.err
-timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/${TAG}_bench_ref.json 2>> $OUT/${TAG}_bench.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $OUT/${TAG}_launches.csv \
-    python bench.py --steps 3 --warmup 3 --no-cpu > $OUT/${TAG}_ncu_bench.log 2>&1
+timeout 900 python bench.py --steps 20 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench exit $?" >> $OUT/${TAG}_bench.err
+timeout 300 python bench.py --impl reference --steps 20 --warmup 2 > $OUT/${TAG}_bench_ref.json 2>> $OUT/${TAG}_bench.err
+# tuning sweep of the logp kernel (register cap x launch width)
+: > $OUT/${TAG}_sweep.txt
+for mb in 2 3 4; do for w in 16 24 32 48; do
+  echo -n "minblocks=$mb warps_per_sm=$w " >> $OUT/${TAG}_sweep.txt
+  XO_TRANSIT_MINBLOCKS=$mb XO_TRANSIT_WARPS_PER_SM=$w timeout 120 python bench.py --steps 20 --warmup 3 --no-cpu --no-kepler 2>/dev/null \
+    | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'])" >> $OUT/${TAG}_sweep.txt
+done; done
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"transit_|model_|kepler_fwd|fold_" -c 60 --csv --log-file $OUT/${TAG}_launches.csv \
+    python bench.py --steps 5 --warmup 3 --no-cpu > $OUT/${TAG}_ncu_bench.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:transit_logp_grad_kernel -s 3 -c 1 -f -o $OUT/${TAG}_prof_transit \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-kepler > $OUT/${TAG}_ncu_transit.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:kepler_fwd_kernel -s 4 -c 1 -f -o $OUT/${TAG}_prof_kepler \
     python bench.py --steps 1 --warmup 3 --no-cpu > $OUT/${TAG}_ncu_kepler.log 2>&1
-tail -5 $OUT/${TAG}_pytest.log; cat $OUT/${TAG}_smoke.log | tail -3; cat $OUT/${TAG}_bench.json; tail -3 $OUT/${TAG}_bench.err
+tail -8 $OUT/${TAG}_pytest.log; tail -3 $OUT/${TAG}_smoke.log; cat $OUT/${TAG}_bench.json; tail -3 $OUT/${TAG}_bench.err; cat $OUT/${TAG}_sweep.txt
