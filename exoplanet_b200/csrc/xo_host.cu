@@ -225,7 +225,7 @@ int xo_transit_logp_grad_host(const double *t, const double *y, const double *iv
   XO_TRY(h2d(dm, mean, (size_t)C * 8, ds.st));
   XO_TRY(h2d(dd, dtk, (size_t)K * 8, ds.st));
   XO_TRY(h2d(dw, wk, (size_t)K * 8, ds.st));
-  XO_RC(xo_transit_logp_grad(dt, dy, dv, N, del, dcl, dm, C, P, dd, dw, K, lognorm, dlp, dge, dgc, dgm, dws, ws, ds.st));
+  XO_RC(xo_transit_logp_grad(dt, dy, dv, N, del, dcl, dm, C, P, dd, dw, K, lognorm, nullptr, dlp, dge, dgc, dgm, dws, ws, ds.st));
   XO_TRY(d2h(logp, dlp, (size_t)C * 8, ds.st));
   XO_TRY(d2h(gel, dge, (size_t)C * P * XO_NGRAD * 8, ds.st));
   XO_TRY(d2h(gcl, dgc, (size_t)C * 3 * 8, ds.st));
@@ -262,8 +262,8 @@ int xo_transit_model_logp_grad_host(const double *t, const double *y, const doub
   XO_TRY(h2d(dm, mean, (size_t)C * 8, ds.st));
   XO_TRY(h2d(dd, dtk, (size_t)K * 8, ds.st));
   XO_TRY(h2d(dw, wk, (size_t)K * 8, ds.st));
-  XO_RC(xo_transit_model_logp_grad(dt, dy, dv, N, dp, dst, dm, C, P, dd, dw, K, texp, use_in_transit, lognorm, dlp, dgp,
-                                   dgs, dgm, dws, ws, ds.st));
+  XO_RC(xo_transit_model_logp_grad(dt, dy, dv, N, dp, dst, dm, C, P, dd, dw, K, texp, use_in_transit, lognorm, nullptr, dlp,
+                                   dgp, dgs, dgm, dws, ws, ds.st));
   XO_TRY(d2h(logp, dlp, (size_t)C * 8, ds.st));
   XO_TRY(d2h(gpar, dgp, (size_t)C * P * XO_NPAR * 8, ds.st));
   XO_TRY(d2h(gstar, dgs, (size_t)C * XO_NSTAR * 8, ds.st));

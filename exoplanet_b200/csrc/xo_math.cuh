@@ -222,8 +222,9 @@ XO_HD void kepler_solve(double M, double e, double &sinf, double &cosf) {
   double den = fma(e, omC1, ome);  // 1 - e cos E
   double rden = rcp_fast(den);
   double sq = sqrt_fast(ome * ope);
-  sinf = (Mr < 0.0 ? -sq : sq) * s1 * rden;
-  cosf = (ome - omC1) * rden;  // (cos E - e) without cancellation
+  const double nanprop = (M - M) + (e - e);  // NaN / inf in -> NaN out (fmin/fmax above drop NaNs)
+  sinf = fma((Mr < 0.0 ? -sq : sq) * s1, rden, nanprop);
+  cosf = fma(ome - omC1, rden, nanprop);  // (cos E - e) without cancellation
 }
 
 // VJP factors of the op
@@ -244,12 +245,12 @@ XO_HD void kepler_jac(double sinf, double cosf, double e, double &dfdM, double &
 XO_HD void cel3(double kc, double kc2, double p, double a, double b, double &G, double &Ek, double &Em) {
   constexpr double CA = 1.0e-8;  // quadratic convergence: error ~ CA^2
   double e = kc, em = 1.0;
-  p = sqrt(p);
-  b *= rcp(p);
+  p = sqrt_fast(p);
+  b *= rcp_fast(p);
   double p1 = 1.0, aE = 1.0, bE = kc2, aM = 1.0, bM = 0.0;
 #pragma unroll 1
   for (int it = 0; it < 12; ++it) {
-    double rp = rcp(p), rp1 = rcp(p1);
+    double rp = rcp_fast(p), rp1 = rcp_fast(p1);
     double f = a;
     a = fma(b, rp, a);
     double g = e * rp;
@@ -269,38 +270,15 @@ XO_HD void cel3(double kc, double kc2, double p, double a, double b, double &G, 
     double gp = em;
     em += kc;
     if (fabs(gp - kc) <= gp * CA) break;
-    kc = sqrt(e);
+    kc = sqrt_fast(e);
     kc += kc;
     e = kc * em;
   }
-  double t = 0.5 * kPi * rcp(em);
-  G = t * fma(a, em, b) * rcp(em + p);
-  double r1 = rcp(em + p1);
+  double t = 0.5 * kPi * rcp_fast(em);
+  G = t * fma(a, em, b) * rcp_fast(em + p);
+  double r1 = rcp_fast(em + p1);
   Ek = t * fma(aE, em, bE) * r1;
   Em = t * fma(aM, em, bM) * r1;
-}
-
-// K is only needed on the b == r branch
-XO_HD double celK(double kc) {
-  constexpr double CA = 1.0e-8;
-  double e = kc, em = 1.0, p = 1.0, a = 1.0, b = 1.0;
-#pragma unroll 1
-  for (int it = 0; it < 12; ++it) {
-    double rp = rcp(p);
-    double f = a;
-    a = fma(b, rp, a);
-    double g = e * rp;
-    b = fma(f, g, b);
-    b += b;
-    p += g;
-    double gp = em;
-    em += kc;
-    if (fabs(gp - kc) <= gp * CA) break;
-    kc = sqrt(e);
-    kc += kc;
-    e = kc * em;
-  }
-  return 0.5 * kPi * fma(a, em, b) / (em * (em + p));
 }
 
 // ---------------------------------------------------------------------------
@@ -363,63 +341,80 @@ XO_HD void qsv(double b_in, double r, double *s, double *dsdb, double *dsdr) {
     dsdr[2] = -r * (2.0 * gg * kap0 + 16.0 * b * r * sk0);
     dsdb[2] = r * (2.0 * gg * sk0 + 8.0 * b * r * (kap0 + sk0 * ck0));
   }
-  // linear term  s1 = 2pi/3 (1 - Theta(r - b)) - pi Lambda
-  double Lam, d1b, d1r;
+  // linear term  s1 = 2pi/3 (1 - Theta(r - b)) - pi Lambda.  Every regime that needs elliptic
+  // integrals first reduces to ONE cel3 call (so a warp whose lanes sit in different regimes
+  // walks the AGM ladder once, together), then finishes with its own closed form.
+  enum { kB0, kHalf, kEqSmall, kEqLarge, kTangent, kLimb, kInside };
+  int kind;
+  double kc2 = 1.0, cp = 1.0, ca = 1.0, cb = 1.0;  // cel(kc, p, a, b) arguments
+  double aux = 0.0, qq = 0.0;
   if (b == 0.0) {
-    double x = sqrt(fmax(0.0, 1.0 - r2));
+    kind = kB0;
+  } else if (b == r) {
+    if (r == 0.5) {
+      kind = kHalf;
+    } else if (r < 0.5) {
+      kind = kEqSmall;
+      kc2 = 1.0 - 4.0 * r2;  // m = 4 r^2; G = K(m)
+    } else {
+      kind = kEqLarge;
+      aux = 0.25 / r2;  // m = 1/(4 r^2)
+      kc2 = 1.0 - aux;
+    }
+  } else if (t4 == 0.0) {
+    kind = kTangent;  // b = 1 - r
+  } else if (t4 > 0.0) {
+    kind = kLimb;  // k^2 < 1: the limb crosses the occultor
+    kc2 = -onembpr2 * rcp_fast(fourbr);
+    cp = bmr * bmr * kc2;
+    ca = 0.0;
+    cb = 3.0 * kc2 * bmr * bpr;
+  } else {
+    kind = kInside;  // k^2 > 1
+    const double rA = rcp_fast(onembmr2);
+    kc2 = onembpr2 * rA;
+    qq = bmr * rcp_fast(bpr);
+    const double mu = 3.0 * qq * rA;
+    cp = qq * qq * kc2;
+    ca = 1.0 + mu;
+    cb = cp + mu;
+  }
+  double G = 0.0, E = 0.0, Em = 0.0;
+  if (kind == kEqSmall || kind == kEqLarge || kind >= kLimb) cel3(sqrt_fast(kc2), kc2, cp, ca, cb, G, E, Em);
+  double Lam, d1b, d1r;
+  if (kind == kLimb) {
+    const double rsqbr = rcp_fast(sqrt_fast(b * r));
+    Lam = onembmr2 * (G + fma(-3.0 + 6.0 * r2 + 2.0 * b * r, Em, -fourbr * E)) * rsqbr * (1.0 / (9.0 * kPi));
+    d1r = -2.0 * r * onembmr2 * Em * rsqbr;
+    d1b = 2.0 * r * onembmr2 * (2.0 * E - Em) * rsqbr * (1.0 / 3.0);
+  } else if (kind == kInside) {
+    const double sqA = sqrt_fast(onembmr2);
+    Lam = 2.0 * sqA * fma(onembpr2, G, -(4.0 - 7.0 * r2 - b2) * E) * (1.0 / (9.0 * kPi));
+    d1r = -4.0 * r * sqA * E;
+    d1b = 4.0 * r * sqA * (1.0 / 3.0) * (2.0 * Em - E);
+  } else if (kind == kB0) {
+    const double x = sqrt(fmax(0.0, 1.0 - r2));
     Lam = -2.0 / 3.0 * x * x * x;
     d1b = 0.0;
     d1r = -2.0 * kPi * r * x;
-  } else if (b == r) {
-    if (r == 0.5) {
-      Lam = 1.0 / 3.0 - 4.0 / (9.0 * kPi);
-      d1r = -4.0 * r;
-      d1b = 4.0 * r / 3.0;
-    } else if (r < 0.5) {
-      double m = 4.0 * r2, kc2 = 1.0 - m, kc = sqrt(kc2);
-      double G, E, Em;
-      cel3(kc, kc2, 1.0, 1.0, 1.0, G, E, Em);  // G = K(m)
-      Lam = 1.0 / 3.0 + 2.0 / (9.0 * kPi) * (4.0 * (2.0 * r2 - 1.0) * E + (1.0 - 4.0 * r2) * G);
-      d1r = -4.0 * r * E;
-      d1b = 4.0 * r / 3.0 * (2.0 * Em - E);
-    } else {
-      double m = 0.25 / r2, kc2 = 1.0 - m, kc = sqrt(kc2);
-      double G, E, Em;
-      cel3(kc, kc2, 1.0, 1.0, 1.0, G, E, Em);
-      Lam = 1.0 / 3.0 + 16.0 * r / (9.0 * kPi) * (2.0 * r2 - 1.0) * E -
-            (1.0 - 4.0 * r2) * (3.0 - 8.0 * r2) / (9.0 * kPi * r) * G;
-      d1r = -8.0 * r2 * m * Em;
-      d1b = 8.0 * r2 / 3.0 * m * (2.0 * E - Em);
-    }
-  } else if (t4 == 0.0) {  // b = 1 - r
-    double sqA = sqrt(onembmr2);
+  } else if (kind == kTangent) {
+    const double sqA = sqrt(onembmr2);
     Lam = 2.0 / (3.0 * kPi) * acos(1.0 - 2.0 * r) - 4.0 / (9.0 * kPi) * (3.0 + 2.0 * r - 8.0 * r2) * sqrt(r * (1.0 - r)) -
           (r > 0.5 ? 2.0 / 3.0 : 0.0);
     d1r = -4.0 * r * sqA;
     d1b = 4.0 * r * sqA / 3.0;
-  } else if (t4 > 0.0) {  // k^2 < 1: the limb crosses the occultor
-    double rfourbr = rcp(fourbr);
-    double kc2 = -onembpr2 * rfourbr;
-    double kc = sqrt(kc2);
-    double rsqbr = rcp(sqrt(b * r));
-    double G, E, Em;
-    cel3(kc, kc2, bmr * bmr * kc2, 0.0, 3.0 * kc2 * bmr * bpr, G, E, Em);
-    Lam = onembmr2 * (G + fma(-3.0 + 6.0 * r2 + 2.0 * b * r, Em, -fourbr * E)) * rsqbr * (1.0 / (9.0 * kPi));
-    d1r = -2.0 * r * onembmr2 * Em * rsqbr;
-    d1b = 2.0 * r * onembmr2 * (2.0 * E - Em) * rsqbr * (1.0 / 3.0);
-  } else {  // k^2 > 1
-    double rA = rcp(onembmr2);
-    double kc2 = onembpr2 * rA;
-    double kc = sqrt(kc2);
-    double sqA = sqrt(onembmr2);
-    double qq = bmr * rcp(bpr);
-    double mu = 3.0 * qq * rA;
-    double p = qq * qq * kc2;
-    double G, E, Em;
-    cel3(kc, kc2, p, 1.0 + mu, p + mu, G, E, Em);
-    Lam = 2.0 * sqA * fma(onembpr2, G, -(4.0 - 7.0 * r2 - b2) * E) * (1.0 / (9.0 * kPi));
-    d1r = -4.0 * r * sqA * E;
-    d1b = 4.0 * r * sqA * (1.0 / 3.0) * (2.0 * Em - E);
+  } else if (kind == kHalf) {
+    Lam = 1.0 / 3.0 - 4.0 / (9.0 * kPi);
+    d1r = -4.0 * r;
+    d1b = 4.0 * r / 3.0;
+  } else if (kind == kEqSmall) {
+    Lam = 1.0 / 3.0 + 2.0 / (9.0 * kPi) * (4.0 * (2.0 * r2 - 1.0) * E + (1.0 - 4.0 * r2) * G);
+    d1r = -4.0 * r * E;
+    d1b = 4.0 * r / 3.0 * (2.0 * Em - E);
+  } else {  // kEqLarge
+    Lam = 1.0 / 3.0 + 16.0 * r / (9.0 * kPi) * (2.0 * r2 - 1.0) * E - (1.0 - 4.0 * r2) * (3.0 - 8.0 * r2) / (9.0 * kPi * r) * G;
+    d1r = -8.0 * r2 * aux * Em;
+    d1b = 8.0 * r2 / 3.0 * aux * (2.0 * E - Em);
   }
   s[1] = (r > b ? 0.0 : 2.0 * kPi / 3.0) - kPi * Lam;
   if (kJac) {

@@ -216,9 +216,9 @@ size_t xo_transit_model_workspace(int64_t N, int64_t C, int64_t P) {
 
 int xo_transit_model_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *par,
                                const double *star, const double *mean, int64_t C, int64_t P, const double *dtk,
-                               const double *wk, int K, double texp, int use_in_transit, double lognorm, double *logp,
-                               double *gpar, double *gstar, double *gmean, void *workspace, size_t workspace_bytes,
-                               void *stream) {
+                               const double *wk, int K, double texp, int use_in_transit, double lognorm,
+                               const double *moments, double *logp, double *gpar, double *gstar, double *gmean,
+                               void *workspace, size_t workspace_bytes, void *stream) {
   if (int rc = xo::check_batch(N, C, P)) return rc;
   if (K < 1 || K > XO_MAX_STENCIL) return XO_ERANGE;
   if (C == 0) return 0;
@@ -234,7 +234,7 @@ int xo_transit_model_logp_grad(const double *t, const double *y, const double *i
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t cp = C * P;
   model_prologue_kernel<<<(unsigned)((cp + 63) / 64), 64, 0, st>>>(par, star, C, (int)P, texp, use_in_transit, elem, cl);
-  xo::launch_transit_logp_grad(t, y, ivar, N, elem, cl, mean, C, (int)P, dtk, wk, K, L.sp, partial, st);
+  xo::launch_transit_logp_grad(t, y, ivar, N, elem, cl, mean, C, (int)P, dtk, wk, K, L.sp, moments, partial, st);
   model_epilogue_kernel<<<(unsigned)((C + 3) / 4), 128, 0, st>>>(par, star, partial, L.sp.slots, C, (int)P, lognorm, logp,
                                                                  gpar, gstar, gmean);
   return xo::launch_status();

@@ -41,6 +41,7 @@ constexpr unsigned kFull = 0xffffffffu;
 struct ChainSmem {
   double elem[XO_MAX_PLANETS][XO_NEL];
   double rperiod[XO_MAX_PLANETS];
+  double wlo[XO_MAX_PLANETS], whi[XO_MAX_PLANETS];  // window in units of the period (phase)
   double cl[3];
   double mean;
   double dtk[XO_MAX_STENCIL];
@@ -57,8 +58,21 @@ __device__ __forceinline__ void stage_chain(ChainSmem &sm, const double *elem, c
   if (threadIdx.x < 3) sm.cl[threadIdx.x] = cl[3 * c + threadIdx.x];
   if (threadIdx.x == 3) sm.mean = mean ? mean[c] : 0.0;
   __syncthreads();
-  if (threadIdx.x < P) sm.rperiod[threadIdx.x] = 1.0 / sm.elem[threadIdx.x][XO_EL_PERIOD];
+  if (threadIdx.x < P) {
+    const double rp = 1.0 / sm.elem[threadIdx.x][XO_EL_PERIOD];
+    sm.rperiod[threadIdx.x] = rp;
+    sm.wlo[threadIdx.x] = sm.elem[threadIdx.x][XO_EL_TSTART] * rp;
+    sm.whi[threadIdx.x] = sm.elem[threadIdx.x][XO_EL_TEND] * rp;
+  }
   __syncthreads();
+}
+
+// window test of the sweep: phase = frac((t - t0)/P) in [-1/2, 1/2] against [tstart, tend]/P.
+// Same set as keplerian.py:731,769 up to rounding at the window edges (where lc = 0 anyway).
+__device__ __forceinline__ bool in_window_phase(const ChainSmem &sm, int p, double t) {
+  const double u = (t - sm.elem[p][XO_EL_T0]) * sm.rperiod[p];
+  const double ph = u - rint(u);
+  return (ph >= sm.wlo[p]) & (ph <= sm.whi[p]);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -99,12 +113,19 @@ __global__ void __launch_bounds__(256) transit_lc_fwd_kernel(const double *__res
 constexpr int kUnroll = 4;                      // 32-cadence groups loaded per sweep step
 constexpr int kQueue = 32 * (kUnroll + 1);      // 31 left over + kUnroll * 32 new entries
 
-template <int kMinBlocks>
+// kVjp = false: Gaussian log-likelihood (y, ivar, mean) and its gradient.
+// kVjp = true : reverse pass of the light curve alone: `y` is the cotangent bar_lc[C][N][P]
+//               (ivar, mean unused), outputs are gel/gcl only.
+// kMoments   : the out-of-transit part of the Gaussian sums comes from data-only moments
+//              (moments[4] = y_ref, S1 = sum ivar, Sy = sum ivar (y - y_ref), Syy = sum ivar (y - y_ref)^2,
+//              computed once per data set by transit_moments_kernel); the sweep then reads t only.
+template <int kMinBlocks, bool kVjp, bool kMoments>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel(
     const double *__restrict__ t, const double *__restrict__ y, const double *__restrict__ ivar, int64_t N,
     const double *__restrict__ elem, const double *__restrict__ cl, const double *__restrict__ mean, int P,
     const double *__restrict__ dtk, const double *__restrict__ wk, int K, int64_t L, int slots,
-    double *__restrict__ partial) {
+    const double *__restrict__ moments, double *__restrict__ partial) {
+  constexpr bool kBase = !kVjp && !kMoments;  // accumulate the per-cadence Gaussian terms in the sweep
   __shared__ ChainSmem sm;
   __shared__ uint32_t queue[kWarps][XO_MAX_PLANETS][kQueue];
   __shared__ double gacc[kWarps][XO_MAX_PLANETS][XO_NGRAD];
@@ -128,20 +149,30 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
     for (int j = 0; j < XO_NGRAD; ++j) g[j] = 0.0;
     if (lane < m) {
       const uint32_t idx = queue[warp][p][off + lane];
-      const double tt = __ldg(t + idx), yy = __ldg(y + idx), iv = __ldg(ivar + idx);
+      const double tt = __ldg(t + idx);
       double gs[3] = {0.0, 0.0, 0.0};
       double ltot = 0.0;
       bool owner = true;  // the lowest in-window planet owns the per-cadence terms
-      for (int k = 0; k < K; ++k) {
-        const double w = sm.wk[k];
-        ltot = fma(w, xo::lc_point<true>(sm.elem[p], sm.cl, tt + sm.dtk[k], w, g, gs), ltot);
-      }
+      // one call site for the sample evaluation: planet p with its gradient weights, any other
+      // planet that is also in transit at this cadence with weight 0 (value only)
       for (int q = 0; q < P; ++q) {
-        if (q == p || !xo::in_window(sm.elem[q], sm.rperiod[q], tt)) continue;
+        const bool self = (q == p);
+        if (!self && (kVjp || !in_window_phase(sm, q, tt))) continue;
         if (q < p) owner = false;
-        for (int k = 0; k < K; ++k)
-          ltot = fma(sm.wk[k], xo::lc_point<false>(sm.elem[q], sm.cl, tt + sm.dtk[k], 0.0, nullptr, nullptr), ltot);
+        for (int k = 0; k < K; ++k) {
+          const double w = sm.wk[k];
+          ltot = fma(w, xo::lc_point<true>(sm.elem[q], sm.cl, tt + sm.dtk[k], self ? w : 0.0, g, gs), ltot);
+        }
       }
+      if (kVjp) {
+        const double bar = __ldg(y + ((int64_t)c * N + idx) * P + p);
+#pragma unroll
+        for (int j = 0; j < XO_NGRAD; ++j) g[j] *= bar;
+        gc0 = fma(bar, gs[0], gc0);
+        gc1 = fma(bar, gs[1], gc1);
+        gc2 = fma(bar, gs[2], gc2);
+      } else {
+      const double yy = __ldg(y + idx), iv = __ldg(ivar + idx);
       const double r0 = yy - mean_c;
       const double wres = iv * (r0 - ltot);
 #pragma unroll
@@ -153,6 +184,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
         lp = fma(0.5 * iv * ltot, 2.0 * r0 - ltot, lp);
         gm = fma(-iv, ltot, gm);
       }
+      }
     }
 #pragma unroll
     for (int j = 0; j < XO_NGRAD; ++j) {
@@ -161,42 +193,59 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
     }
   };
 
-  const int64_t start = (int64_t)slot * L;
-  const int64_t end = min(start + L, N);
+  const uint32_t start = (uint32_t)min((int64_t)slot * L, N);
+  const uint32_t end = (uint32_t)min((int64_t)slot * L + L, N);
+  // sweep steps, then one final pass (last = true) that only flushes what is left in the
+  // queues -- written as ONE loop so the expensive drain body exists once in the binary
 #pragma unroll 1
-  for (int64_t base = start; base < end; base += 32 * kUnroll) {
+  for (uint32_t base = start;; base += 32 * kUnroll) {
+    const bool last = base >= end;
+    const bool full = base + 32 * kUnroll <= end;  // no bounds checks needed in this step
     double tt[kUnroll], yy[kUnroll], iv[kUnroll];
+    if (!last) {
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {  // all loads of the step in flight together
-      const int64_t i = base + 32 * u + lane;
-      const bool valid = i < end;
-      tt[u] = valid ? __ldg(t + i) : 0.0;
-      yy[u] = valid ? __ldg(y + i) : 0.0;
-      iv[u] = valid ? __ldg(ivar + i) : 0.0;
-    }
+      for (int u = 0; u < kUnroll; ++u) {  // all loads of the step in flight together
+        const uint32_t i = base + 32 * u + lane;
+        const bool valid = full || i < end;
+        tt[u] = valid ? __ldg(t + i) : 0.0;
+        if (kBase) {
+          yy[u] = valid ? __ldg(y + i) : 0.0;
+          iv[u] = valid ? __ldg(ivar + i) : 0.0;
+        }
+      }
+      if (kBase) {
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const double r0 = yy[u] - mean_c;
-      const double wr = iv[u] * r0;
-      lp = fma(-0.5 * wr, r0, lp);
-      gm += wr;
+        for (int u = 0; u < kUnroll; ++u) {
+          const double r0 = yy[u] - mean_c;
+          const double wr = iv[u] * r0;
+          lp = fma(-0.5 * wr, r0, lp);
+          gm += wr;
+        }
+      }
     }
     for (int p = 0; p < P; ++p) {
       int fill = __shfl_sync(kFull, cnt, p);
-      const int fill0 = fill;
+      if (!last) {
+        const int fill0 = fill;
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const int64_t i = base + 32 * u + lane;
-        const bool inw = (i < end) && xo::in_window(sm.elem[p], sm.rperiod[p], tt[u]);
-        const uint32_t mask = __ballot_sync(kFull, inw);
-        if (inw) queue[warp][p][fill + __popc(mask & lt_mask)] = (uint32_t)i;
-        fill += __popc(mask);
+        for (int u = 0; u < kUnroll; ++u) {
+          const uint32_t i = base + 32 * u + lane;
+          const bool inw = (full || i < end) && in_window_phase(sm, p, tt[u]);
+          const uint32_t mask = __ballot_sync(kFull, inw);
+          if (inw) queue[warp][p][fill + __popc(mask & lt_mask)] = i;
+          fill += __popc(mask);
+        }
+        if (fill == fill0) continue;
+        __syncwarp();
       }
-      if (fill == fill0) continue;
-      __syncwarp();
+      const int thr = last ? 1 : 32;
       int off = 0;
 #pragma unroll 1
-      for (; fill - off >= 32; off += 32) drain(p, off, 32);
+      while (fill - off >= thr) {
+        const int m = min(32, fill - off);
+        drain(p, off, m);
+        off += m;
+      }
       if (off > 0) {  // move the < 32 left-over entries to the front
         const int rem = fill - off;
         const uint32_t v = lane < rem ? queue[warp][p][off + lane] : 0u;
@@ -207,10 +256,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
       }
       if (lane == p) cnt = fill;
     }
+    if (last) break;
   }
-  for (int p = 0; p < P; ++p) {
-    int fill = __shfl_sync(kFull, cnt, p);
-    if (fill > 0) drain(p, 0, fill);
+  if (kMoments && slot == 0 && lane == 0) {  // out-of-transit Gaussian terms from the data moments
+    const double m = mean_c - moments[0];
+    lp += -0.5 * (moments[3] - 2.0 * m * moments[2] + m * m * moments[1]);
+    gm += moments[2] - m * moments[1];
   }
   lp = warp_sum(lp);
   gm = warp_sum(gm);
@@ -227,6 +278,57 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
     out[4] = gc2;
   }
   for (int i = lane; i < P * XO_NGRAD; i += 32) out[kNBase + i] = gacc[warp][i / XO_NGRAD][i % XO_NGRAD];
+}
+
+// data-only moments of the Gaussian likelihood, one CTA, fixed-order tree (deterministic):
+// out = (y_ref, S1, Sy, Syy) with y_ref the ivar-weighted mean of y
+__global__ void __launch_bounds__(1024) transit_moments_kernel(const double *__restrict__ y, const double *__restrict__ ivar,
+                                                               int64_t N, double *__restrict__ out) {
+  __shared__ double red[3][32];
+  __shared__ double yref_s;
+  auto block_sum3 = [&](double a, double b, double c, double &A, double &B, double &Cc) {
+    a = warp_sum(a);
+    b = warp_sum(b);
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0) {
+      red[0][threadIdx.x >> 5] = a;
+      red[1][threadIdx.x >> 5] = b;
+      red[2][threadIdx.x >> 5] = c;
+    }
+    __syncthreads();
+    A = B = Cc = 0.0;
+    for (int w = 0; w < 32; ++w) {
+      A += red[0][w];
+      B += red[1][w];
+      Cc += red[2][w];
+    }
+    __syncthreads();
+  };
+  double s1 = 0.0, sy = 0.0;
+  for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+    const double w = ivar[i];
+    s1 += w;
+    sy = fma(w, y[i], sy);
+  }
+  double S1, Sy0, dummy;
+  block_sum3(s1, sy, 0.0, S1, Sy0, dummy);
+  if (threadIdx.x == 0) yref_s = Sy0 / S1;
+  __syncthreads();
+  const double yref = yref_s;
+  double a = 0.0, b = 0.0;
+  for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+    const double w = ivar[i], d = y[i] - yref;
+    a = fma(w, d, a);
+    b = fma(w * d, d, b);
+  }
+  double Sy, Syy;
+  block_sum3(a, b, 0.0, Sy, Syy, dummy);
+  if (threadIdx.x == 0) {
+    out[0] = yref;
+    out[1] = S1;
+    out[2] = Sy;
+    out[3] = Syy;
+  }
 }
 
 // fold per-warp partials in slot order: out[c][j] = sum_s partial[c][s][j]
@@ -433,18 +535,27 @@ int check_batch(int64_t N, int64_t C, int64_t P) {
 
 void launch_transit_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *elem,
                               const double *cl, const double *mean, int64_t C, int P, const double *dtk,
-                              const double *wk, int K, Split sp, double *partial, cudaStream_t st) {
+                              const double *wk, int K, Split sp, const double *moments, double *partial,
+                              cudaStream_t st) {
   dim3 grid(sp.slots / kWarps, (unsigned)C);
-  switch (transit_min_blocks()) {
-    case 2:
-      transit_logp_grad_kernel<2><<<grid, kThreads, 0, st>>>(t, y, ivar, N, elem, cl, mean, P, dtk, wk, K, sp.L, sp.slots, partial);
-      break;
-    case 4:
-      transit_logp_grad_kernel<4><<<grid, kThreads, 0, st>>>(t, y, ivar, N, elem, cl, mean, P, dtk, wk, K, sp.L, sp.slots, partial);
-      break;
-    default:
-      transit_logp_grad_kernel<3><<<grid, kThreads, 0, st>>>(t, y, ivar, N, elem, cl, mean, P, dtk, wk, K, sp.L, sp.slots, partial);
+#define XO_LAUNCH(MB, VJP, MOM)                                                                                      \
+  transit_logp_grad_kernel<MB, VJP, MOM><<<grid, kThreads, 0, st>>>(t, y, ivar, N, elem, cl, mean, P, dtk, wk, K, sp.L, \
+                                                                    sp.slots, moments, partial)
+  if (ivar == nullptr) {  // light-curve VJP mode: y = bar_lc[C][N][P]
+    XO_LAUNCH(3, true, false);
+    return;
   }
+  const int mb = transit_min_blocks();
+  if (moments) {
+    if (mb == 2) XO_LAUNCH(2, false, true);
+    else if (mb == 4) XO_LAUNCH(4, false, true);
+    else XO_LAUNCH(3, false, true);
+  } else {
+    if (mb == 2) XO_LAUNCH(2, false, false);
+    else if (mb == 4) XO_LAUNCH(4, false, false);
+    else XO_LAUNCH(3, false, false);
+  }
+#undef XO_LAUNCH
 }
 
 }  // namespace xo
@@ -476,10 +587,16 @@ size_t xo_transit_logp_grad_workspace(int64_t N, int64_t C, int64_t P) {
   return sizeof(double) * (size_t)C * (size_t)sp.slots * (size_t)(kNBase + P * XO_NGRAD);
 }
 
+int xo_transit_data_moments(const double *y, const double *ivar, int64_t N, double *moments, void *stream) {
+  if (N <= 0 || !y || !ivar || !moments) return XO_EINVAL;
+  transit_moments_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(y, ivar, N, moments);
+  return xo::launch_status();
+}
+
 int xo_transit_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *elem,
                          const double *cl, const double *mean, int64_t C, int64_t P, const double *dtk, const double *wk,
-                         int K, double lognorm, double *logp, double *gel, double *gcl, double *gmean, void *workspace,
-                         size_t workspace_bytes, void *stream) {
+                         int K, double lognorm, const double *moments, double *logp, double *gel, double *gcl,
+                         double *gmean, void *workspace, size_t workspace_bytes, void *stream) {
   if (int rc = check_batch(N, C, P)) return rc;
   if (K < 1 || K > XO_MAX_STENCIL) return XO_ERANGE;
   if (C == 0) return 0;
@@ -490,11 +607,32 @@ int xo_transit_logp_grad(const double *t, const double *y, const double *ivar, i
   Split sp = split_transit(N, C);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   double *partial = static_cast<double *>(workspace);
-  xo::launch_transit_logp_grad(t, y, ivar, N, elem, cl, mean, C, (int)P, dtk, wk, K, sp, partial, st);
+  xo::launch_transit_logp_grad(t, y, ivar, N, elem, cl, mean, C, (int)P, dtk, wk, K, sp, moments, partial, st);
   const int nacc = kNBase + (int)P * XO_NGRAD;
   const int64_t tot = C * nacc;
   fold_partials_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(partial, sp.slots, nacc, C, (int)P, lognorm, logp,
                                                                       gel, gcl, gmean);
+  return xo::launch_status();
+}
+
+int xo_transit_lc_vjp(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
+                      const double *dtk, const double *wk, int K, const double *bar_lc, double *gel, double *gcl,
+                      void *workspace, size_t workspace_bytes, void *stream) {
+  if (int rc = check_batch(N, C, P)) return rc;
+  if (K < 1 || K > XO_MAX_STENCIL) return XO_ERANGE;
+  if (C == 0) return 0;
+  if (N == 0 || P == 0) return XO_EINVAL;
+  if (!t || !elem || !cl || !dtk || !wk || !bar_lc || !gel || !gcl || !workspace) return XO_EINVAL;
+  if (workspace_bytes < xo_transit_logp_grad_workspace(N, C, P) + sizeof(double) * 2 * (size_t)C) return XO_EWORKSPACE;
+  Split sp = split_transit(N, C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double *partial = static_cast<double *>(workspace);
+  double *scratch = partial + (size_t)C * sp.slots * (kNBase + P * XO_NGRAD);  // logp / gmean of the fold (unused)
+  xo::launch_transit_logp_grad(t, bar_lc, nullptr, N, elem, cl, nullptr, C, (int)P, dtk, wk, K, sp, nullptr, partial, st);
+  const int nacc = kNBase + (int)P * XO_NGRAD;
+  const int64_t tot = C * nacc;
+  fold_partials_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(partial, sp.slots, nacc, C, (int)P, 0.0, scratch, gel,
+                                                                      gcl, scratch + C);
   return xo::launch_status();
 }
 

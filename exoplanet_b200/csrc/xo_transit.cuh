@@ -21,6 +21,6 @@ int transit_min_blocks();
 // enqueue transit_logp_grad_kernel; partial[C][slots][kNBase + P*XO_NGRAD]
 void launch_transit_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *elem,
                               const double *cl, const double *mean, int64_t C, int P, const double *dtk,
-                              const double *wk, int K, Split sp, double *partial, cudaStream_t st);
+                              const double *wk, int K, Split sp, const double *moments, double *partial, cudaStream_t st);
 
 }  // namespace xo

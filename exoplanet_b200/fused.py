@@ -76,6 +76,18 @@ class TransitData:
             self.lognorm = float(-np.sum(np.log(sig)) - 0.5 * n * LOG_2PI)
         self.n = n
         self.device = dev
+        self._moments = None
+
+    def moments(self):
+        """Device tensor (y_ref, sum ivar, sum ivar (y - y_ref), sum ivar (y - y_ref)^2): the
+        data-only part of the Gaussian sums, computed once (xo_transit_data_moments)."""
+        if self._moments is None and self.y is not None and self.ivar is not None:
+            lib = _lib.require_cuda()
+            m = torch.empty(4, dtype=torch.float64, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.check(lib.xo_transit_data_moments(_ptr(self.y), _ptr(self.ivar), self.n, _ptr(m), _lib.stream_ptr()), "moments")
+            self._moments = m
+        return self._moments
 
 
 def _stencil_dev(stencil, dev):
@@ -98,8 +110,9 @@ def light_curve(t, elem, cl, stencil=None):
     return lc
 
 
-def transit_logp_grad(data, elem, cl, mean, stencil=None, workspace=None):
-    """One launch: (logp[C], gel[C,P,10], gcl[C,3], gmean[C])."""
+def transit_logp_grad(data, elem, cl, mean, stencil=None, workspace=None, use_moments=True):
+    """One launch: (logp[C], gel[C,P,10], gcl[C,3], gmean[C]).  ``use_moments``: take the
+    out-of-transit part of the sums from the data moments (the sweep then reads t only)."""
     lib = _lib.require_cuda()
     elem = elem.detach().contiguous()
     cl = cl.detach().contiguous()
@@ -116,7 +129,8 @@ def transit_logp_grad(data, elem, cl, mean, stencil=None, workspace=None):
     gmean = torch.empty(Cc, dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.xo_transit_logp_grad(_ptr(data.t), _ptr(data.y), _ptr(data.ivar), data.n, _ptr(elem), _ptr(cl),
-                                            _ptr(mean), Cc, P, _ptr(dtk), _ptr(wk), dtk.numel(), data.lognorm, _ptr(logp),
+                                            _ptr(mean), Cc, P, _ptr(dtk), _ptr(wk), dtk.numel(), data.lognorm,
+                                            _ptr(data.moments() if use_moments else None), _ptr(logp),
                                             _ptr(gel), _ptr(gcl), _ptr(gmean), _ptr(workspace),
                                             workspace.numel() * workspace.element_size(), _lib.stream_ptr()),
                    "transit_logp_grad")
@@ -227,10 +241,11 @@ class TransitModel:
     sampler-side parameters, entirely on the device (the fused counterpart of the PyMC model
     in /root/reference/docs/tutorials/data-and-models.md:458-509)."""
 
-    def __init__(self, data, texp=None, oversample=7, order=0, use_in_transit=True):
+    def __init__(self, data, texp=None, oversample=7, order=0, use_in_transit=True, use_moments=True):
         self.data = data
         self.texp = 0.0 if texp is None else float(texp)
         self.use_in_transit = bool(use_in_transit)
+        self.use_moments = bool(use_moments)
         st = exposure_stencil(texp, oversample, order)
         self.dtk, self.wk = _stencil_dev(st, data.device)
         self._ws = None
@@ -252,7 +267,8 @@ class TransitModel:
         with torch.cuda.device(d.device):
             _lib.check(lib.xo_transit_model_logp_grad(_ptr(d.t), _ptr(d.y), _ptr(d.ivar), d.n, _ptr(par), _ptr(star), _ptr(mean), Cc, P,
                                                       _ptr(self.dtk), _ptr(self.wk), self.dtk.numel(), self.texp,
-                                                      int(self.use_in_transit), d.lognorm, _ptr(logp), _ptr(gpar), _ptr(gstar),
+                                                      int(self.use_in_transit), d.lognorm,
+                                                      _ptr(d.moments() if self.use_moments else None), _ptr(logp), _ptr(gpar), _ptr(gstar),
                                                       _ptr(gmean), _ptr(self._ws), self._ws.numel() * 8, _lib.stream_ptr()),
                        "transit_model_logp_grad")
         return logp, gpar, gstar, gmean

@@ -1,0 +1,57 @@
+"""Chain-parallel sharding over the GPUs of one box: rank g owns a contiguous
+block of chains, every rank holds the (small) data set, and NO collective sits on the hot
+path -- the only traffic is the optional gather of O(#params) results per chain and the
+max-over-ranks of the device timings.  One process per GPU via ``torch.distributed``."""
+import os
+
+import torch
+
+__all__ = ["world", "shard_bounds", "shard", "gather_chains", "max_over_ranks"]
+
+
+def world():
+    """(rank, world_size, local_rank) from the torchrun environment (1 process if absent)."""
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def shard_bounds(n_chains, world_size, rank):
+    """Contiguous, balanced block [lo, hi) of ``n_chains`` for ``rank`` (sizes differ by <= 1)."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    base, extra = divmod(int(n_chains), int(world_size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard(x, world_size, rank, dim=0):
+    """This rank's block of a per-chain array."""
+    lo, hi = shard_bounds(x.shape[dim], world_size, rank)
+    return x.narrow(dim, lo, hi - lo) if isinstance(x, torch.Tensor) else x[(slice(None),) * dim + (slice(lo, hi),)]
+
+
+def gather_chains(local, n_chains, group=None):
+    """All ranks' per-chain results back in chain order (uneven blocks allowed).  Off the hot
+    path: ~(1 + n_params) doubles per chain."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return local
+    ws, rk = dist.get_world_size(group), dist.get_rank(group)
+    sizes = [shard_bounds(n_chains, ws, r)[1] - shard_bounds(n_chains, ws, r)[0] for r in range(ws)]
+    cap = max(sizes)
+    pad = torch.zeros((cap,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(ws)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0)
+
+
+def max_over_ranks(value, device=None, group=None):
+    """max over ranks of a python float (device timings are reported as the slowest rank's)."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device or "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return t.item()

@@ -101,15 +101,25 @@ int xo_contact_points(const double *a, const double *e, const double *cosw, cons
 int xo_transit_lc_fwd(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
                       const double *dtk, const double *wk, int K, double *lc, void *stream);
 
+/* reverse pass of xo_transit_lc_fwd: bar_lc[C][N][P] -> gel[C][P][XO_NGRAD], gcl[C][3];
+ * workspace >= xo_transit_logp_grad_workspace(N, C, P) + 16 * C bytes */
+int xo_transit_lc_vjp(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
+                      const double *dtk, const double *wk, int K, const double *bar_lc, double *gel, double *gcl,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
 /* Gaussian log-likelihood and its gradient in one launch:
  *   logp[c] = lognorm - 1/2 sum_n ivar[n] (y[n] - mean[c] - sum_p lc[c][n][p])^2
  *   gel[C][P][XO_NGRAD], gcl[C][3], gmean[C].
- * workspace: xo_transit_logp_grad_workspace(N, C, P) bytes of device memory. */
+ * workspace: xo_transit_logp_grad_workspace(N, C, P) bytes of device memory.
+ * moments: NULL, or the 4 data-only moments written by xo_transit_data_moments(y, ivar) --
+ *   (y_ref, sum ivar, sum ivar (y-y_ref), sum ivar (y-y_ref)^2); with them the out-of-transit
+ *   part of the sums is closed-form and the sweep reads t only (same result to rounding). */
 size_t xo_transit_logp_grad_workspace(int64_t N, int64_t C, int64_t P);
+int xo_transit_data_moments(const double *y, const double *ivar, int64_t N, double *moments, void *stream);
 int xo_transit_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *elem,
                          const double *cl, const double *mean, int64_t C, int64_t P, const double *dtk, const double *wk,
-                         int K, double lognorm, double *logp, double *gel, double *gcl, double *gmean, void *workspace,
-                         size_t workspace_bytes, void *stream);
+                         int K, double lognorm, const double *moments, double *logp, double *gel, double *gcl,
+                         double *gmean, void *workspace, size_t workspace_bytes, void *stream);
 
 /* The same evaluation from sampler-side parameters: prologue (KeplerianOrbit.__init__,
  * keplerian.py:133-281; in_transit window :729-767; get_cl limb_dark.py:11-18) + logp +
@@ -119,9 +129,9 @@ int xo_transit_logp_grad(const double *t, const double *y, const double *ivar, i
 size_t xo_transit_model_workspace(int64_t N, int64_t C, int64_t P);
 int xo_transit_model_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *par,
                                const double *star, const double *mean, int64_t C, int64_t P, const double *dtk,
-                               const double *wk, int K, double texp, int use_in_transit, double lognorm, double *logp,
-                               double *gpar, double *gstar, double *gmean, void *workspace, size_t workspace_bytes,
-                               void *stream);
+                               const double *wk, int K, double texp, int use_in_transit, double lognorm,
+                               const double *moments, double *logp, double *gpar, double *gstar, double *gmean,
+                               void *workspace, size_t workspace_bytes, void *stream);
 /* prologue only: elem[C][P][XO_NEL], cl[C][3] */
 int xo_elements_from_params(const double *par, const double *star, int64_t C, int64_t P, double texp, int use_in_transit,
                             double *elem, double *cl, void *stream);

@@ -81,6 +81,25 @@ def test_logp_grad_matches_oracle(P, texp, C):
     assert np.max(np.abs(gmean.cpu().numpy() - gmo) / np.abs(gmo).max()) < 1e-10
 
 
+def test_moments_path_equals_full_sweep():
+    """closed-form out-of-transit sums (data moments) vs summing every cadence in the sweep"""
+    N, C = 100000, 9
+    p, t, el_o, el_g, cl = problem(N, C, 2, seed=31)
+    y = 1.0 + synthetic.noise(N)  # a large offset: the moments are taken about y_ref, so no cancellation
+    data = fused.TransitData(t, y, np.full(N, 5e-4), device=DEV)
+    mean = dev(1.0 + p["mean"])
+    a = fused.transit_logp_grad(data, dev(el_o), dev(cl), mean, use_moments=True)
+    b = fused.transit_logp_grad(data, dev(el_o), dev(cl), mean, use_moments=False)
+    assert torch.allclose(a[0], b[0], rtol=1e-12, atol=0)
+    assert torch.allclose(a[3], b[3], rtol=1e-9, atol=1e-9 * b[3].abs().max().item())
+    assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    m = data.moments().cpu().numpy()
+    iv = 1 / 5e-4 ** 2
+    yref = np.sum(iv * y) / (iv * N)
+    assert abs(m[0] - yref) < 1e-13 and abs(m[1] - iv * N) < 1e-6 * iv
+    assert abs(m[3] - np.sum(iv * (y - yref) ** 2)) < 1e-9 * m[3]
+
+
 def test_logp_is_deterministic_and_chain_independent():
     N, C = 100000, 64
     p, t, el_o, el_g, cl = problem(N, C, 1, ecc=0.5)

@@ -1,0 +1,92 @@
+"""CPU: host-side logic (constructor algebra, stencils, sharding) -- no GPU arithmetic."""
+import numpy as np
+import pytest
+import torch
+
+import xo_oracle as O
+from exoplanet_b200 import fused, synthetic
+from exoplanet_b200.orbits import KeplerianOrbit, SimpleTransitOrbit, get_aor_from_transit_duration
+
+
+def test_constructor_known_answers(golden):
+    g = golden("end_to_end")
+    b6 = g["B6"]
+    o = KeplerianOrbit(period=b6["period"], ecc=b6["ecc"], omega=b6["omega"], device="cpu")
+    assert abs(o.a.item() - b6["a"]) < 1e-12 and abs(o.M0.item() - b6["M0"]) < 1e-13
+    assert abs(o.t_periastron.item() - b6["t_periastron"]) < 1e-13 and abs(o.n.item() - b6["n"]) < 1e-13
+    b7 = g["B7"]
+    o = KeplerianOrbit(m_star=b7["m_star"], r_star=b7["r_star"], t0=b7["t0"], period=b7["period"], ecc=b7["ecc"], omega=b7["omega"],
+                       Omega=b7["Omega"], incl=b7["incl"], m_planet=b7["m_planet"], device="cpu")
+    assert abs(o.a.item() - b7["a"]) < 1e-10 and abs(o.K0.item() - b7["K0"]) < 1e-12
+
+
+def test_consistent_inputs_roundtrip():  # orbits/keplerian_test.py:377-501 (without astropy units)
+    o1 = KeplerianOrbit(period=10.0, m_star=1.1, r_star=0.9, device="cpu")
+    o2 = KeplerianOrbit(a=o1.a, m_star=1.1, r_star=0.9, device="cpu")
+    assert abs(o2.period.item() - 10.0) < 1e-12
+    o3 = KeplerianOrbit(a=o1.a, period=10.0, r_star=0.9, device="cpu")
+    assert abs(o3.m_star.item() - 1.1) < 1e-12 and abs(o3.rho_star.item() - o1.rho_star.item()) < 1e-12
+    o4 = KeplerianOrbit(period=10.0, rho_star=o1.rho_star, r_star=0.9, device="cpu")
+    assert abs(o4.m_star.item() - 1.1) < 1e-12
+    o5 = KeplerianOrbit(period=10.0, rho_star=o1.rho_star, m_star=1.1, device="cpu")
+    assert abs(o5.r_star.item() - 0.9) < 1e-12
+    for bad in (dict(), dict(period=1.0, a=2.0, m_star=1.0), dict(period=1.0, m_star=1.0, r_star=1.0, rho_star=1.0)):
+        with pytest.raises(ValueError):
+            KeplerianOrbit(device="cpu", **bad)
+    with pytest.raises(ValueError):
+        KeplerianOrbit(period=1.0, ecc=0.1, device="cpu")  # omega missing
+    with pytest.raises(ValueError):
+        KeplerianOrbit(period=1.0, b=0.1, incl=1.0, device="cpu")
+    with pytest.raises(ValueError):
+        KeplerianOrbit(period=1.0, t0=0.0, t_periastron=0.0, device="cpu")
+
+
+def test_incl_b_duality_and_duration():
+    o = KeplerianOrbit(period=5.0, b=0.4, ecc=0.3, omega=0.7, device="cpu")
+    o2 = KeplerianOrbit(period=5.0, incl=o.incl, ecc=0.3, omega=0.7, device="cpu")
+    assert abs(o2.b.item() - 0.4) < 1e-12
+    aor, jac = get_aor_from_transit_duration(torch.tensor(0.12, dtype=torch.float64), torch.tensor(3.4, dtype=torch.float64),
+                                             torch.tensor(0.3, dtype=torch.float64), ror=0.05)
+    d = torch.tensor(0.12, dtype=torch.float64, requires_grad=True)
+    a2, _ = get_aor_from_transit_duration(d, torch.tensor(3.4, dtype=torch.float64), torch.tensor(0.3, dtype=torch.float64), ror=0.05)
+    (g,) = torch.autograd.grad(a2, d)
+    assert abs(g.item() - jac.item()) < 1e-10 * abs(jac.item())
+    with pytest.warns(UserWarning):
+        KeplerianOrbit(period=3.4, b=0.3, duration=0.12, device="cpu")
+
+
+def test_exposure_stencils_match_reference_construction():
+    for order in (0, 1, 2):
+        for n in (1, 3, 7, 8):
+            dt, w = fused.exposure_stencil(0.02, n, order)
+            dto, wo = O.stencil(0.02, n, order)  # literal limb_dark.py:181-198 construction
+            assert np.allclose(dt, dto, rtol=0, atol=1e-17) and np.allclose(w, wo, rtol=0, atol=1e-16)
+    with pytest.raises(ValueError):
+        fused.exposure_stencil(0.02, 7, 3)
+    dt, w = fused.exposure_stencil(None)
+    assert dt.tolist() == [0.0] and w.tolist() == [1.0]
+
+
+def test_limb_dark_coeffs_match_oracle():
+    u1, u2 = np.array([0.3, 0.1]), np.array([0.2, 0.5])
+    c = fused.limb_dark_coeffs(torch.tensor(u1), torch.tensor(u2)).numpy()
+    assert np.allclose(c, O.get_cl(u1, u2), rtol=1e-15)
+
+
+def test_simple_orbit_geometry():
+    o = SimpleTransitOrbit(period=3.0, duration=0.2, t0=1.0, b=0.3, r_star=1.1, ror=0.1, device="cpu")
+    x, y, z = o.get_relative_position(np.array([1.0, 1.05, 2.5, 4.0]))
+    assert abs(x[0].item()) < 1e-12 and abs(x[3].item()) < 1e-12
+    assert np.allclose(y.numpy(), 0.33)
+    assert z[0].item() > 0 and z[2].item() < 0
+    inds = o.in_transit(np.linspace(0, 6, 601))
+    assert set(inds.tolist()) <= set(np.nonzero(np.abs((np.linspace(0, 6, 601) - 1.0 + 1.5) % 3.0 - 1.5) < 0.1 + 1e-9)[0].tolist())
+    with pytest.raises(NotImplementedError):
+        o.get_planet_velocity(0.0)
+
+
+def test_synthetic_is_seeded():
+    a = synthetic.transit_params(4, 2, seed=5)
+    b = synthetic.transit_params(4, 2, seed=5)
+    assert all(np.array_equal(a[k], b[k]) for k in a)
+    assert np.array_equal(synthetic.cadence_times(5), np.arange(5) * 0.0204 + 0.0137)

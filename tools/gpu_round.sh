@@ -12,11 +12,11 @@ timeout 900 python bench.py --steps 20 --warmup 3 > $OUT/${TAG}_bench.json 2> $O
 timeout 300 python bench.py --impl reference --steps 20 --warmup 2 > $OUT/${TAG}_bench_ref.json 2>> $OUT/${TAG}_bench.err
 # tuning sweep of the logp kernel (register cap x launch width)
 : > $OUT/${TAG}_sweep.txt
-for mb in 2 3 4; do for w in 16 24 32 48; do
-  echo -n "minblocks=$mb warps_per_sm=$w " >> $OUT/${TAG}_sweep.txt
-  XO_TRANSIT_MINBLOCKS=$mb XO_TRANSIT_WARPS_PER_SM=$w timeout 120 python bench.py --steps 20 --warmup 3 --no-cpu --no-kepler 2>/dev/null \
+for SWEEPFLAG in "" "--full-sweep"; do for mb in 2 3 4; do for w in 24 48 96; do
+  echo -n "flag=$SWEEPFLAG minblocks=$mb warps_per_sm=$w " >> $OUT/${TAG}_sweep.txt
+  XO_TRANSIT_MINBLOCKS=$mb XO_TRANSIT_WARPS_PER_SM=$w timeout 120 python bench.py --steps 20 --warmup 3 --no-cpu --no-kepler $SWEEPFLAG 2>/dev/null \
     | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'])" >> $OUT/${TAG}_sweep.txt
-done; done
+done; done; done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"transit_|model_|kepler_fwd|fold_" -c 60 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 5 --warmup 3 --no-cpu > $OUT/${TAG}_ncu_bench.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:transit_logp_grad_kernel -s 3 -c 1 -f -o $OUT/${TAG}_prof_transit \
