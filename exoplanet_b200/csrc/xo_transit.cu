@@ -195,25 +195,35 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
 
   const uint32_t start = (uint32_t)min((int64_t)slot * L, N);
   const uint32_t end = (uint32_t)min((int64_t)slot * L + L, N);
-  // sweep steps, then one final pass (last = true) that only flushes what is left in the
-  // queues -- written as ONE loop so the expensive drain body exists once in the binary
+  // Sweep steps of 32*kUnroll cadences, then one final pass (last = true) that only flushes what
+  // is left in the queues -- written as ONE loop so the expensive drain body exists once in the
+  // binary.  The common step (no lane of the warp in any window) is: kUnroll coalesced loads that
+  // were issued one step ahead, 4 flops + 2 compares per cadence and planet, one vote.
+  const double *tp = t + start + lane;
+  double tnext[kUnroll];
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) tnext[u] = (start + 32 * u + lane < end) ? __ldg(tp + 32 * u) : 0.0;
 #pragma unroll 1
   for (uint32_t base = start;; base += 32 * kUnroll) {
     const bool last = base >= end;
-    const bool full = base + 32 * kUnroll <= end;  // no bounds checks needed in this step
     double tt[kUnroll], yy[kUnroll], iv[kUnroll];
+    uint32_t valid = 0u;  // bit u: cadence base + 32 u + lane exists
     if (!last) {
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {  // all loads of the step in flight together
-        const uint32_t i = base + 32 * u + lane;
-        const bool valid = full || i < end;
-        tt[u] = valid ? __ldg(t + i) : 0.0;
-        if (kBase) {
-          yy[u] = valid ? __ldg(y + i) : 0.0;
-          iv[u] = valid ? __ldg(ivar + i) : 0.0;
-        }
+      for (int u = 0; u < kUnroll; ++u) {
+        tt[u] = tnext[u];
+        valid |= (base + 32 * u + lane < end) ? (1u << u) : 0u;
       }
+      const uint32_t nb = base + 32 * kUnroll;  // prefetch the next step while this one is processed
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) tnext[u] = (nb + 32 * u + lane < end) ? __ldg(tp + (nb - start) + 32 * u) : 0.0;
       if (kBase) {
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const uint32_t i = base + 32 * u + lane;
+          yy[u] = (valid >> u) & 1u ? __ldg(y + i) : 0.0;
+          iv[u] = (valid >> u) & 1u ? __ldg(ivar + i) : 0.0;
+        }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
           const double r0 = yy[u] - mean_c;
@@ -224,19 +234,30 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
       }
     }
     for (int p = 0; p < P; ++p) {
-      int fill = __shfl_sync(kFull, cnt, p);
+      int fill;
       if (!last) {
-        const int fill0 = fill;
+        // window constants of planet p in registers for the whole step
+        const double t0p = sm.elem[p][XO_EL_T0], rpp = sm.rperiod[p], lo = sm.wlo[p], hi = sm.whi[p];
+        uint32_t inw = 0u;
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
-          const uint32_t i = base + 32 * u + lane;
-          const bool inw = (full || i < end) && in_window_phase(sm, p, tt[u]);
-          const uint32_t mask = __ballot_sync(kFull, inw);
-          if (inw) queue[warp][p][fill + __popc(mask & lt_mask)] = i;
+          const double ph0 = (tt[u] - t0p) * rpp;
+          const double ph = ph0 - rint(ph0);
+          inw |= ((ph >= lo) & (ph <= hi)) ? (1u << u) : 0u;
+        }
+        inw &= valid;
+        if (!__any_sync(kFull, inw != 0u)) continue;  // nothing of this planet in this step
+        fill = __shfl_sync(kFull, cnt, p);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const bool in = (inw >> u) & 1u;
+          const uint32_t mask = __ballot_sync(kFull, in);
+          if (in) queue[warp][p][fill + __popc(mask & lt_mask)] = base + 32 * u + lane;
           fill += __popc(mask);
         }
-        if (fill == fill0) continue;
         __syncwarp();
+      } else {
+        fill = __shfl_sync(kFull, cnt, p);
       }
       const int thr = last ? 1 : 32;
       int off = 0;

@@ -200,11 +200,14 @@ class KeplerianOrbit:
     def elements(self, r=None, texp=None, use_in_transit=True, K=None):
         """[P, 16] element blocks for the fused kernels (include/xo_b200.h).  ``r`` is the planet
         radius in R_sun (same convention as ``get_light_curve``)."""
-        z = torch.zeros_like(self.a + self.period + self.t0)
+        ror_in = None if r is None else _tensor(r, self.device).reshape(-1) / self.r_star
+        z = torch.zeros_like(self.a + self.period + self.t0).reshape(-1)
+        if ror_in is not None:
+            z = z + torch.zeros_like(ror_in)
         ecc = z if self.ecc is None else self.ecc + z
         cw = z + 1.0 if self.ecc is None else self.cos_omega + z
         sw = z if self.ecc is None else self.sin_omega + z
-        ror = z if r is None else _tensor(r, self.device).reshape(-1) / self.r_star + z
+        ror = z if ror_in is None else ror_in + z
         cosi, sini = self.cos_incl + z, self.sin_incl + z
         period, n, a = self.period + z, self.n + z, self.a + z
         if use_in_transit:
@@ -344,6 +347,8 @@ class KeplerianOrbit:
         """(t_start, t_end, flag) per planet on dt = mod(t - t0 + P/2, P) - P/2 (keplerian.py:729-767)."""
         z = torch.zeros_like(self.a + self.period)
         ror = _tensor(r, self.device) / self.r_star + z
+        if texp is not None and isinstance(texp, torch.Tensor) and texp.dim() > 0:
+            texp = texp.max()  # per-cadence exposure times: widen by the longest one (a superset)
         if self.ecc is None:
             ts, te = _el.circular_window(self.a + z, self.period + z, self.b + z, ror, self.r_star, self.sin_incl + z, texp)
         else:

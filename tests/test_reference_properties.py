@@ -169,10 +169,13 @@ def test_variable_texp():  # light_curves_test.py:105-145
     orbit, r = _lc_orbit(), dev([0.1, 0.03])
     lc = LimbDarkLightCurve(0.3, 0.2, device=DEV)
     texp0 = 0.1
-    scalar = lc.get_light_curve(orbit=orbit, r=r, t=t, texp=texp0, use_in_transit=False)
+    vec = lc.get_light_curve(orbit=orbit, r=r, t=t, texp=texp0 + torch.zeros_like(t), use_in_transit=False)
     for uit in (False, True):
-        vec = lc.get_light_curve(orbit=orbit, r=r, t=t, texp=texp0 + torch.zeros_like(t), use_in_transit=uit)
+        scalar = lc.get_light_curve(orbit=orbit, r=r, t=t, texp=texp0, use_in_transit=uit)
         assert np.allclose(scalar.cpu().numpy(), vec.cpu().numpy())
+    # extension: per-cadence texp together with the in-transit selection (window widened by max texp)
+    vec2 = lc.get_light_curve(orbit=orbit, r=r, t=t, texp=texp0 + torch.zeros_like(t), use_in_transit=True)
+    assert np.allclose(vec.cpu().numpy(), vec2.cpu().numpy())
 
 
 def test_contact_bug_regression():  # light_curves_test.py:148-164

@@ -2,6 +2,7 @@
 # One GPU-box visit: parity tests, smoke, bench, tuning sweep, ncu launch list + full captures.
 # usage (under gpurun): bash tools/gpu_round.sh [tag] [quick]
 TAG=${1:-r01}
+MODE=${2:-full}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_gpu.txt 2>&1
@@ -10,9 +11,10 @@ timeout 1500 python -m pytest tests -m gpu -q > $OUT/${TAG}_pytest.log 2>&1; ech
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke exit $?" >> $OUT/${TAG}_smoke.log
 timeout 900 python bench.py --steps 20 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench exit $?" >> $OUT/${TAG}_bench.err
 timeout 300 python bench.py --impl reference --steps 20 --warmup 2 > $OUT/${TAG}_bench_ref.json 2>> $OUT/${TAG}_bench.err
+if [ "$MODE" = "full" ]; then
 # tuning sweep of the logp kernel (register cap x launch width)
 : > $OUT/${TAG}_sweep.txt
-for SWEEPFLAG in "" "--full-sweep"; do for mb in 2 3 4; do for w in 24 48 96; do
+for SWEEPFLAG in "" "--full-sweep"; do for mb in 2 3 4; do for w in 16 24 40; do
   echo -n "flag=$SWEEPFLAG minblocks=$mb warps_per_sm=$w " >> $OUT/${TAG}_sweep.txt
   XO_TRANSIT_MINBLOCKS=$mb XO_TRANSIT_WARPS_PER_SM=$w timeout 120 python bench.py --steps 20 --warmup 3 --no-cpu --no-kepler $SWEEPFLAG 2>/dev/null \
     | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'])" >> $OUT/${TAG}_sweep.txt
@@ -23,4 +25,5 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:tran
     python bench.py --steps 2 --warmup 3 --no-cpu --no-kepler > $OUT/${TAG}_ncu_transit.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:kepler_fwd_kernel -s 4 -c 1 -f -o $OUT/${TAG}_prof_kepler \
     python bench.py --steps 1 --warmup 3 --no-cpu > $OUT/${TAG}_ncu_kepler.log 2>&1
+fi
 tail -8 $OUT/${TAG}_pytest.log; tail -3 $OUT/${TAG}_smoke.log; cat $OUT/${TAG}_bench.json; tail -3 $OUT/${TAG}_bench.err; cat $OUT/${TAG}_sweep.txt
