@@ -64,6 +64,10 @@ _SIGNATURES = {
                                          _vp, _i32]),
     "xo_transit_model_logp_grad_host": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _dbl, _i32, _dbl,
                                                _vp, _vp, _vp, _vp, _i32]),
+    "xo_transit_data_create": (_i32, [_vp, _vp, _vp, _i64, _i32, C.POINTER(_vp)]),
+    "xo_transit_data_destroy": (_i32, [_vp]),
+    "xo_transit_model_logp_grad_resident": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _dbl, _i32, _dbl, _i32, _vp, _vp,
+                                                   _vp, _vp]),
 }
 
 EXPORTS = tuple(sorted(_SIGNATURES))

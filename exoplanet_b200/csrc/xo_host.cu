@@ -10,6 +10,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <new>
 
 #include "xo_common.cuh"
 
@@ -270,6 +271,117 @@ int xo_transit_model_logp_grad_host(const double *t, const double *y, const doub
   XO_TRY(d2h(gmean, dgm, (size_t)C * 8, ds.st));
   XO_TRY(cudaStreamSynchronize(ds.st));
   return 0;
+}
+
+// ---- resident data set: t, y, ivar (+ their moments) uploaded once, owned by the caller ----
+struct xo_transit_data {
+  int device = 0;
+  int64_t N = 0;
+  double *t = nullptr, *y = nullptr, *ivar = nullptr, *moments = nullptr;
+  char *scratch = nullptr;  // parameter staging + workspace, grown on demand
+  size_t scratch_bytes = 0;
+  cudaStream_t st = nullptr;
+};
+
+int xo_transit_data_create(const double *t, const double *y, const double *ivar, int64_t N, int device,
+                           xo_transit_data **out) {
+  if (!t || !y || !ivar || N <= 0 || !out) return XO_EINVAL;
+  int prev = 0;
+  XO_TRY(cudaGetDevice(&prev));
+  XO_TRY(cudaSetDevice(device));
+  xo_transit_data *d = new (std::nothrow) xo_transit_data();
+  if (!d) return XO_EINVAL;
+  d->device = device;
+  d->N = N;
+  cudaError_t e = cudaStreamCreateWithFlags(&d->st, cudaStreamNonBlocking);
+  const size_t nb = (size_t)N * 8;
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d->t, 3 * nb + 64);
+  if (e == cudaSuccess) {
+    d->y = d->t + N;
+    d->ivar = d->y + N;
+    d->moments = d->ivar + N;
+    e = cudaMemcpyAsync(d->t, t, nb, cudaMemcpyHostToDevice, d->st);
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d->y, y, nb, cudaMemcpyHostToDevice, d->st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d->ivar, ivar, nb, cudaMemcpyHostToDevice, d->st);
+  int rc = e == cudaSuccess ? xo_transit_data_moments(d->y, d->ivar, N, d->moments, d->st) : -(int)e;
+  if (rc == 0) rc = xo::cuda_status(cudaStreamSynchronize(d->st));
+  cudaSetDevice(prev);
+  if (rc != 0) {
+    xo_transit_data_destroy(d);
+    return rc;
+  }
+  *out = d;
+  return 0;
+}
+
+int xo_transit_data_destroy(xo_transit_data *d) {
+  if (!d) return 0;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(d->device);
+  if (d->t) cudaFree(d->t);
+  if (d->scratch) cudaFree(d->scratch);
+  if (d->st) cudaStreamDestroy(d->st);
+  cudaSetDevice(prev);
+  delete d;
+  return 0;
+}
+
+// parameters and results are HOST buffers; the light curve stays on the device
+int xo_transit_model_logp_grad_resident(xo_transit_data *d, const double *par, const double *star, const double *mean,
+                                        int64_t C, int64_t P, const double *dtk, const double *wk, int K, double texp,
+                                        int use_in_transit, double lognorm, int use_moments, double *logp, double *gpar,
+                                        double *gstar, double *gmean) {
+  if (!d || C < 0 || P <= 0 || K < 1) return XO_EINVAL;
+  if (C == 0) return 0;
+  if (!par || !star || !mean || !dtk || !wk || !logp || !gpar || !gstar || !gmean) return XO_EINVAL;
+  int prev = 0;
+  XO_TRY(cudaGetDevice(&prev));
+  XO_TRY(cudaSetDevice(d->device));
+  const size_t ws = xo_transit_model_workspace(d->N, C, P);
+  const size_t nin = (size_t)C * P * XO_NPAR + (size_t)C * XO_NSTAR + (size_t)C + 2 * (size_t)K;
+  const size_t nout = (size_t)C + (size_t)C * P * XO_NPAR + (size_t)C * XO_NSTAR + (size_t)C;
+  const size_t need = pad(nin) + pad(nout) + pad(ws, 1);
+  if (need > d->scratch_bytes) {
+    if (d->scratch) cudaFree(d->scratch);
+    d->scratch = nullptr;
+    d->scratch_bytes = 0;
+    cudaError_t e = cudaMalloc((void **)&d->scratch, need);
+    if (e != cudaSuccess) {
+      cudaSetDevice(prev);
+      return -(int)e;
+    }
+    d->scratch_bytes = need;
+  }
+  double *din = reinterpret_cast<double *>(d->scratch);
+  double *dout = reinterpret_cast<double *>(d->scratch + pad(nin));
+  void *dws = d->scratch + pad(nin) + pad(nout);
+  double *dp = din, *dst = dp + C * P * XO_NPAR, *dm = dst + C * XO_NSTAR, *dd = dm + C, *dw = dd + K;
+  double *dlp = dout, *dgp = dlp + C, *dgs = dgp + C * P * XO_NPAR, *dgm = dgs + C * XO_NSTAR;
+  cudaStream_t st = d->st;
+  int rc = 0;
+  auto copy_in = [&](double *dst_, const double *src, size_t n) {
+    if (rc == 0) rc = xo::cuda_status(cudaMemcpyAsync(dst_, src, n * 8, cudaMemcpyHostToDevice, st));
+  };
+  copy_in(dp, par, (size_t)C * P * XO_NPAR);
+  copy_in(dst, star, (size_t)C * XO_NSTAR);
+  copy_in(dm, mean, (size_t)C);
+  copy_in(dd, dtk, (size_t)K);
+  copy_in(dw, wk, (size_t)K);
+  if (rc == 0)
+    rc = xo_transit_model_logp_grad(d->t, d->y, d->ivar, d->N, dp, dst, dm, C, P, dd, dw, K, texp, use_in_transit, lognorm,
+                                    use_moments ? d->moments : nullptr, dlp, dgp, dgs, dgm, dws, ws, st);
+  auto copy_out = [&](double *dst_, const double *src, size_t n) {
+    if (rc == 0) rc = xo::cuda_status(cudaMemcpyAsync(dst_, src, n * 8, cudaMemcpyDeviceToHost, st));
+  };
+  copy_out(logp, dlp, (size_t)C);
+  copy_out(gpar, dgp, (size_t)C * P * XO_NPAR);
+  copy_out(gstar, dgs, (size_t)C * XO_NSTAR);
+  copy_out(gmean, dgm, (size_t)C);
+  if (rc == 0) rc = xo::cuda_status(cudaStreamSynchronize(st));
+  cudaSetDevice(prev);
+  return rc;
 }
 
 }  // extern "C"

@@ -158,8 +158,33 @@ XO_HD double reduce_2pi(double M) {
 // fp32 on the FMA/MUFU pipes, which run beside the fp64 pipe that bounds this kernel.
 // 1 - e is formed in fp64 first so the e -> 1 corner keeps its relative accuracy.
 // ---------------------------------------------------------------------------
+// fp64 <-> fp32 by integer bit surgery (truncating; |x| < 2^-126 flushes to 0).  The F2F
+// conversion instructions run on the slow XU pipe on sm_100 -- four of them per solve cost
+// ~35% of the Kepler kernel's time in the ncu source view -- while these are 4-5 ALU ops.
+XO_HD float f64_to_f32_trunc(double x) {
+#if defined(__CUDA_ARCH__)
+  const int hi = __double2hiint(x);
+  const unsigned lo = (unsigned)__double2loint(x);
+  const unsigned mag = (unsigned)hi & 0x7fffffffu;
+  const unsigned bits = mag >= 0x38100000u ? (((mag - 0x38000000u) << 3) | (lo >> 29)) : 0u;  // exp >= 897
+  return __uint_as_float(((unsigned)hi & 0x80000000u) | bits);
+#else
+  return (float)x;
+#endif
+}
+XO_HD double f32_to_f64_exact(float f) {
+#if defined(__CUDA_ARCH__)
+  const unsigned b = __float_as_uint(f);
+  const unsigned mag = b & 0x7fffffffu;
+  const unsigned hi = mag >= 0x00800000u ? ((mag >> 3) + 0x38000000u) : 0u;  // normal floats only
+  return __hiloint2double((int)((b & 0x80000000u) | hi), (int)(mag >= 0x00800000u ? (b << 29) : 0u));
+#else
+  return (double)f;
+#endif
+}
+
 XO_HD double markley_start_f32(double Ma, double e, double ome) {
-  const float M = (float)Ma, ef = (float)e, om = (float)ome;
+  const float M = f64_to_f32_trunc(Ma), ef = f64_to_f32_trunc(e), om = f64_to_f32_trunc(ome);
   constexpr float fac = (float)(1.0 / (kPi - 6.0 / kPi));
   constexpr float pif = (float)kPi;
 #if defined(__CUDA_ARCH__)
@@ -191,7 +216,7 @@ XO_HD double markley_start_f32(double Ma, double e, double ome) {
   float E = num / den;
 #endif
   if (!(den > 0.0f) || !(E >= 0.0f)) E = M;  // underflow guard (M absurdly small): Newton recovers
-  return (double)E;
+  return f32_to_f64_exact(E);
 }
 
 XO_HD void kepler_solve(double M, double e, double &sinf, double &cosf) {

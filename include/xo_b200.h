@@ -173,6 +173,19 @@ int xo_transit_model_logp_grad_host(const double *t, const double *y, const doub
                                     const double *wk, int K, double texp, int use_in_transit, double lognorm,
                                     double *logp, double *gpar, double *gstar, double *gmean, int device);
 
+
+/* ---- resident data set (what a compiled PyTensor function holds as constants) ----
+ * The light curve (t, y, ivar) is uploaded once and owned by the handle; each evaluation moves
+ * only O(#params) bytes: par/star/mean in, logp/gradients out (all HOST buffers). */
+typedef struct xo_transit_data xo_transit_data;
+int xo_transit_data_create(const double *t, const double *y, const double *ivar, int64_t N, int device,
+                           xo_transit_data **out);
+int xo_transit_data_destroy(xo_transit_data *data);
+int xo_transit_model_logp_grad_resident(xo_transit_data *data, const double *par, const double *star, const double *mean,
+                                        int64_t C, int64_t P, const double *dtk, const double *wk, int K, double texp,
+                                        int use_in_transit, double lognorm, int use_moments, double *logp, double *gpar,
+                                        double *gstar, double *gmean);
+
 #ifdef __cplusplus
 }
 #endif

@@ -252,3 +252,38 @@ def test_parameter_level_model_matches_autograd_prologue_and_oracle(P, texp):
     torch.cuda.synchronize()
     assert np.allclose(elem.cpu().numpy()[..., :11], el_o[..., :11], rtol=1e-13, atol=1e-13)
     assert np.allclose(elem.cpu().numpy()[..., 11:13], el_o[..., 11:13], rtol=0, atol=1e-10)
+
+
+def test_resident_data_handle_matches_device_path():
+    import ctypes as C
+
+    from exoplanet_b200 import _lib
+
+    lib = _lib.require_cuda()
+    N, Cn, P = 30000, 5, 2
+    p = synthetic.transit_params(Cn, P, seed=77)
+    t = synthetic.cadence_times(N)
+    y = 1.0 + synthetic.noise(N)
+    sig = np.full(N, 5e-4)
+    data = fused.TransitData(t, y, sig, device=DEV)
+    par = fused.pack_params(dev(p["period"]), dev(p["t0"]), dev(p["ecc"]), dev(p["omega"]), dev(p["b"]), dev(p["ror"]), dev(p["m_planet"]),
+                            dev(p["K"]))
+    star = fused.pack_star(torch.ones(Cn, dtype=torch.float64, device=DEV), torch.ones(Cn, dtype=torch.float64, device=DEV), dev(p["u1"]),
+                           dev(p["u2"]))
+    mean = dev(1.0 + p["mean"])
+    ref = fused.TransitModel(data, texp=0.02).logp_grad(par, star, mean)
+    f = lambda a: a.ctypes.data_as(C.c_void_p)
+    ivar = np.ascontiguousarray(1 / sig ** 2)
+    h = C.c_void_p()
+    assert lib.xo_transit_data_create(f(t), f(y), f(ivar), N, 0, C.byref(h)) == 0
+    dtk, wk = fused.exposure_stencil(0.02)
+    parh, starh, meanh = par.cpu().numpy(), star.cpu().numpy(), mean.cpu().numpy()
+    out = [np.empty(Cn), np.empty((Cn, P, 8)), np.empty((Cn, 4)), np.empty(Cn)]
+    for use_moments in (1, 0):
+        rc = lib.xo_transit_model_logp_grad_resident(h, f(parh), f(starh), f(meanh), Cn, P, f(dtk), f(wk), dtk.size, 0.02, 1, data.lognorm,
+                                                     use_moments, *[f(x) for x in out])
+        assert rc == 0
+        assert np.allclose(out[0], ref[0].cpu().numpy(), rtol=1e-12)
+        assert np.allclose(out[1], ref[1].cpu().numpy(), rtol=1e-9, atol=1e-9 * np.abs(out[1]).max())
+        assert np.allclose(out[2], ref[2].cpu().numpy(), rtol=1e-9, atol=1e-9 * np.abs(out[2]).max())
+    assert lib.xo_transit_data_destroy(h) == 0
