@@ -36,6 +36,35 @@ constexpr double kPio2Hi = 1.570796326794896558e+00;
 constexpr double kPio2Lo = 6.123233995736766036e-17;
 constexpr double kTwoOverPi = 0.636619772367581343075535053490057448;
 
+// fp64 constants that are not encodable as instruction immediates live in ONE table in
+// __constant__ memory so that DFMA/DMUL read them as c[bank][offset] operands; otherwise ptxas
+// rebuilds every 64-bit literal with two MOVs per use (~80 extra instructions per Kepler solve).
+#define XO_CONST_TABLE                                                                                         \
+  {                                                                                                            \
+    /* 0..6  sin kernel S(u), highest degree first */                                                          \
+    -7.58426609767779964718e-13, 1.60584895500232502802e-10, -2.50521059616691626032e-8,                       \
+        0.0000027557319218543807191, -0.000198412698412640218792, 0.00833333333333333099958,                  \
+        -0.166666666666666666651, /* 7..13 cos kernel C(u) */                                                  \
+        4.74452016112717801505e-14, -1.1470437495511350934e-11, 2.08767556405153041563e-9,                     \
+        -2.75573192209605647402e-7, 0.0000248015873015840664244, -0.00138888888888888875915,                  \
+        0.0416666666666666666658, /* 14..19 range reduction */                                                 \
+        0.159154943091895335768883763372514362, 6.283185307179586232e+00, 2.449293598294706414e-16,            \
+        0.636619772367581343075535053490057448, 1.570796326794896558e+00, 6.123233995736766036e-17,            \
+        /* 20..25 small-angle sin/cos series: -1/5040, 1/120, -1/6, -1/720, 1/24, pi */                        \
+        -1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0, -1.0 / 720.0, 1.0 / 24.0, 3.14159265358979323846264338327950288 \
+  }
+namespace detail {
+#if defined(__CUDACC__)
+static __constant__ double c_tab[26] = XO_CONST_TABLE;
+#endif
+static const double h_tab[26] = XO_CONST_TABLE;
+}  // namespace detail
+#if defined(__CUDA_ARCH__)
+#define XO_K(i) (::xo::detail::c_tab[i])
+#else
+#define XO_K(i) (::xo::detail::h_tab[i])
+#endif
+
 XO_HD double rcp(double x) {
 #if defined(__CUDA_ARCH__)
   return __drcp_rn(x);
@@ -96,24 +125,24 @@ XO_HD double sqrt_fast(double x) {
 // Polynomials from tools/gen_poly.py (|x| <= 1.02 pi/4; abs err 5e-18 / 1e-18).
 // ---------------------------------------------------------------------------
 XO_HD void sincos_0pi(double E, double &s, double &c, double &EmS, double &omC) {
-  double qf = rint(E * kTwoOverPi);  // 0, 1 or 2
-  double x = fma(-qf, kPio2Hi, E);
-  x = fma(-qf, kPio2Lo, x);
+  double qf = rint(E * XO_K(17));  // 0, 1 or 2
+  double x = fma(-qf, XO_K(18), E);
+  x = fma(-qf, XO_K(19), x);
   double u = x * x;
-  double ps = -7.58426609767779964718e-13;
-  ps = fma(ps, u, 1.60584895500232502802e-10);
-  ps = fma(ps, u, -2.50521059616691626032e-8);
-  ps = fma(ps, u, 0.0000027557319218543807191);
-  ps = fma(ps, u, -0.000198412698412640218792);
-  ps = fma(ps, u, 0.00833333333333333099958);
-  ps = fma(ps, u, -0.166666666666666666651);
-  double pc = 4.74452016112717801505e-14;
-  pc = fma(pc, u, -1.1470437495511350934e-11);
-  pc = fma(pc, u, 2.08767556405153041563e-9);
-  pc = fma(pc, u, -2.75573192209605647402e-7);
-  pc = fma(pc, u, 0.0000248015873015840664244);
-  pc = fma(pc, u, -0.00138888888888888875915);
-  pc = fma(pc, u, 0.0416666666666666666658);
+  double ps = XO_K(0);
+  ps = fma(ps, u, XO_K(1));
+  ps = fma(ps, u, XO_K(2));
+  ps = fma(ps, u, XO_K(3));
+  ps = fma(ps, u, XO_K(4));
+  ps = fma(ps, u, XO_K(5));
+  ps = fma(ps, u, XO_K(6));
+  double pc = XO_K(7);
+  pc = fma(pc, u, XO_K(8));
+  pc = fma(pc, u, XO_K(9));
+  pc = fma(pc, u, XO_K(10));
+  pc = fma(pc, u, XO_K(11));
+  pc = fma(pc, u, XO_K(12));
+  pc = fma(pc, u, XO_K(13));
   double xs = x * u * ps;               // sin x - x
   double cm1 = fma(u * u, pc, -0.5 * u);  // cos x - 1
   double sx = x + xs, cx = 1.0 + cm1;
@@ -145,9 +174,9 @@ XO_HD void sincos_reduced(double Mr, double &s, double &c) {
 }
 
 XO_HD double reduce_2pi(double M) {
-  double k = rint(M * kInvTwoPi);
-  double r = fma(-k, kTwoPiHi, M);
-  return fma(-k, kTwoPiLo, r);
+  double k = rint(M * XO_K(14));
+  double r = fma(-k, XO_K(15), M);
+  return fma(-k, XO_K(16), r);
 }
 
 // ---------------------------------------------------------------------------
@@ -158,37 +187,36 @@ XO_HD double reduce_2pi(double M) {
 // fp32 on the FMA/MUFU pipes, which run beside the fp64 pipe that bounds this kernel.
 // 1 - e is formed in fp64 first so the e -> 1 corner keeps its relative accuracy.
 // ---------------------------------------------------------------------------
-// fp64 <-> fp32 by integer bit surgery (truncating; |x| < 2^-126 flushes to 0).  The F2F
-// conversion instructions run on the slow XU pipe on sm_100 -- four of them per solve cost
-// ~35% of the Kepler kernel's time in the ncu source view -- while these are 4-5 ALU ops.
-XO_HD float f64_to_f32_trunc(double x) {
+// single-instruction fp32 approximations (flush-to-zero, no denormal fix-up code)
 #if defined(__CUDA_ARCH__)
-  const int hi = __double2hiint(x);
-  const unsigned lo = (unsigned)__double2loint(x);
-  const unsigned mag = (unsigned)hi & 0x7fffffffu;
-  const unsigned bits = mag >= 0x38100000u ? (((mag - 0x38000000u) << 3) | (lo >> 29)) : 0u;  // exp >= 897
-  return __uint_as_float(((unsigned)hi & 0x80000000u) | bits);
-#else
-  return (float)x;
-#endif
+__device__ __forceinline__ float rcp_f32(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
-XO_HD double f32_to_f64_exact(float f) {
-#if defined(__CUDA_ARCH__)
-  const unsigned b = __float_as_uint(f);
-  const unsigned mag = b & 0x7fffffffu;
-  const unsigned hi = mag >= 0x00800000u ? ((mag >> 3) + 0x38000000u) : 0u;  // normal floats only
-  return __hiloint2double((int)((b & 0x80000000u) | hi), (int)(mag >= 0x00800000u ? (b << 29) : 0u));
-#else
-  return (double)f;
-#endif
+__device__ __forceinline__ float rsqrt_f32(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
+__device__ __forceinline__ float lg2_f32(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_f32(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+#endif
 
 XO_HD double markley_start_f32(double Ma, double e, double ome) {
-  const float M = f64_to_f32_trunc(Ma), ef = f64_to_f32_trunc(e), om = f64_to_f32_trunc(ome);
+  const float M = (float)Ma, ef = (float)e, om = (float)ome;  // F2F: 4 issue slots; bit surgery costs ~24 (measured slower)
   constexpr float fac = (float)(1.0 / (kPi - 6.0 / kPi));
   constexpr float pif = (float)kPi;
 #if defined(__CUDA_ARCH__)
-  const float rope = __frcp_rn(1.0f + ef);
+  const float rope = rcp_f32(1.0f + ef);
 #else
   const float rope = 1.0f / (1.0f + ef);
 #endif
@@ -201,8 +229,8 @@ XO_HD double markley_start_f32(double Ma, double e, double ome) {
   const float q2 = q * q;
   const float disc = fmaxf(fmaf(q2, q, r * r), 1e-37f);
 #if defined(__CUDA_ARCH__)
-  const float y = fabsf(r) + disc * __frsqrt_rn(disc);
-  float w = exp2f((2.0f / 3.0f) * __log2f(y));  // cbrt(y)^2
+  const float y = fabsf(r) + disc * rsqrt_f32(disc);
+  float w = ex2_f32((2.0f / 3.0f) * lg2_f32(y));  // cbrt(y)^2
 #else
   const float y = fabsf(r) + sqrtf(disc);
   float w = cbrtf(y);
@@ -211,17 +239,17 @@ XO_HD double markley_start_f32(double Ma, double e, double ome) {
   const float W = fmaf(w, w + q, q2);
   const float num = fmaf(2.0f * r, w, M * W), den = d * W;
 #if defined(__CUDA_ARCH__)
-  float E = __fdividef(num, den);
+  float E = num * rcp_f32(den);
 #else
   float E = num / den;
 #endif
   if (!(den > 0.0f) || !(E >= 0.0f)) E = M;  // underflow guard (M absurdly small): Newton recovers
-  return f32_to_f64_exact(E);
+  return (double)E;
 }
 
 XO_HD void kepler_solve(double M, double e, double &sinf, double &cosf) {
   double Mr = reduce_2pi(M);
-  double Ma = fmin(fabs(Mr), kPi);
+  double Ma = fmin(fabs(Mr), XO_K(25));
   double ome = 1.0 - e;
   double ope = 1.0 + e;
   double E = markley_start_f32(Ma, e, ome);
@@ -234,14 +262,14 @@ XO_HD void kepler_solve(double M, double e, double &sinf, double &cosf) {
   double f2 = e * s;
   double f3 = e * c;
   double rf1 = rcp_mid(f1);
-  double h2 = 0.5 * f2, h3 = f3 * (1.0 / 6.0), h4 = -f2 * (1.0 / 24.0);
+  double h2 = 0.5 * f2, h3 = -f3 * XO_K(22), h4 = -f2 * XO_K(24);
   double dE = -f0 * rf1;
 #pragma unroll
   for (int it = 0; it < 3; ++it) dE = -fma(dE * dE, fma(dE, fma(dE, h4, h3), h2), f0) * rf1;
   // sin/cos(E + dE) by angle addition (|dE| < ~1e-2)
   double d2 = dE * dE;
-  double sd = dE * fma(d2, fma(d2, fma(d2, -1.0 / 5040.0, 1.0 / 120.0), -1.0 / 6.0), 1.0);
-  double cdm1 = d2 * fma(d2, fma(d2, -1.0 / 720.0, 1.0 / 24.0), -0.5);
+  double sd = dE * fma(d2, fma(d2, fma(d2, XO_K(20), XO_K(21)), XO_K(22)), 1.0);
+  double cdm1 = d2 * fma(d2, fma(d2, XO_K(23), XO_K(24)), -0.5);
   double s1 = s + fma(c, sd, s * cdm1);
   double omC1 = omC - fma(c, cdm1, -s * sd);
   double den = fma(e, omC1, ome);  // 1 - e cos E

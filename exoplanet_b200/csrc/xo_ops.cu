@@ -7,6 +7,8 @@
 // cache hints (no reuse), and a grid sized as a multiple of the SM count.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "xo_common.cuh"
 #include "xo_contact.cuh"
 #include "xo_math.cuh"
@@ -19,25 +21,31 @@ __device__ __forceinline__ double2 ld2(const double *p) { return __ldcs(reinterp
 __device__ __forceinline__ void st2(double *p, double a, double b) { __stcs(reinterpret_cast<double2 *>(p), make_double2(a, b)); }
 
 // ---- kepler ---------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) kepler_fwd_kernel(const double *__restrict__ M, const double *__restrict__ e,
-                                                              double *__restrict__ sinf, double *__restrict__ cosf,
-                                                              int64_t n, int64_t e_inner) {
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) kepler_fwd_kernel(const double *__restrict__ M,
+                                                                          const double *__restrict__ e,
+                                                                          double *__restrict__ sinf,
+                                                                          double *__restrict__ cosf, int64_t n,
+                                                                          int64_t e_inner) {
   const int64_t npair = n >> 1;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npair; i += stride) {
-    double2 m = ld2(M + 2 * i);
-    double e0, e1;
-    if (e_inner == 1) {
-      double2 ee = ld2(e + 2 * i);
-      e0 = ee.x;
-      e1 = ee.y;
-    } else {
-      e0 = __ldg(e + (2 * i) / e_inner);
-      e1 = __ldg(e + (2 * i + 1) / e_inner);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // software pipeline: the loads of iteration k+1 are in flight while iteration k computes
+  double2 m = make_double2(0.0, 0.0), ee = make_double2(0.0, 0.0);
+  if (i < npair) {
+    m = ld2(M + 2 * i);
+    ee = (e_inner == 1) ? ld2(e + 2 * i) : make_double2(__ldg(e + (2 * i) / e_inner), __ldg(e + (2 * i + 1) / e_inner));
+  }
+  for (; i < npair; i += stride) {
+    const double2 mc = m, ec = ee;
+    const int64_t nx = i + stride;
+    if (nx < npair) {
+      m = ld2(M + 2 * nx);
+      ee = (e_inner == 1) ? ld2(e + 2 * nx) : make_double2(__ldg(e + (2 * nx) / e_inner), __ldg(e + (2 * nx + 1) / e_inner));
     }
     double s0, c0, s1, c1;
-    xo::kepler_solve(m.x, e0, s0, c0);
-    xo::kepler_solve(m.y, e1, s1, c1);
+    xo::kepler_solve(mc.x, ec.x, s0, c0);
+    xo::kepler_solve(mc.y, ec.y, s1, c1);
     st2(sinf + 2 * i, s0, s1);
     st2(cosf + 2 * i, c0, c1);
   }
@@ -156,9 +164,18 @@ int xo_kepler_fwd_bcast(const double *M, const double *e, int64_t e_inner, doubl
   const int sms = xo::sm_count();
   bool vec = aligned16(M) && aligned16(sinf) && aligned16(cosf) && (e_inner != 1 || aligned16(e));
   if (vec) {
+    static const int mb = [] {
+      const char *v = getenv("XO_KEPLER_MINBLOCKS");
+      return v && *v ? atoi(v) : 4;
+    }();
     int64_t work = (n / 2 + kThreads - 1) / kThreads;
-    int grid = (int)xo::clamp_grid(work, sms, 8);
-    kepler_fwd_kernel<<<grid, kThreads, 0, st>>>(M, e, sinf, cosf, n, e_inner);
+    int grid = (int)xo::clamp_grid(work, sms, mb);
+    if (mb == 2)
+      kepler_fwd_kernel<2><<<grid, kThreads, 0, st>>>(M, e, sinf, cosf, n, e_inner);
+    else if (mb == 3)
+      kepler_fwd_kernel<3><<<grid, kThreads, 0, st>>>(M, e, sinf, cosf, n, e_inner);
+    else
+      kepler_fwd_kernel<4><<<grid, kThreads, 0, st>>>(M, e, sinf, cosf, n, e_inner);
   } else {
     int64_t work = (n + kThreads - 1) / kThreads;
     int grid = (int)xo::clamp_grid(work, sms, 8);

@@ -19,6 +19,7 @@ for SWEEPFLAG in "" "--full-sweep"; do for mb in 2 3 4; do for w in 16 24 40; do
   XO_TRANSIT_MINBLOCKS=$mb XO_TRANSIT_WARPS_PER_SM=$w timeout 120 python bench.py --steps 20 --warmup 3 --no-cpu --no-kepler $SWEEPFLAG 2>/dev/null \
     | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'])" >> $OUT/${TAG}_sweep.txt
 done; done; done
+for mb in 2 3 4; do echo -n "kepler minblocks=$mb " >> $OUT/${TAG}_sweep.txt; XO_KEPLER_MINBLOCKS=$mb timeout 120 python bench.py --steps 3 --warmup 3 --no-cpu 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['kepler'])" >> $OUT/${TAG}_sweep.txt; done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"transit_|model_|kepler_fwd|fold_" -c 60 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 5 --warmup 3 --no-cpu > $OUT/${TAG}_ncu_bench.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:transit_logp_grad_kernel -s 3 -c 1 -f -o $OUT/${TAG}_prof_transit \
