@@ -161,6 +161,89 @@ def arm_reference(args):
     print(json.dumps(line))
 
 
+def _time_steps(fn, steps, flush):
+    import torch
+
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ev = []
+    for _ in range(steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        ev.append((a, b))
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in ev) / steps
+
+
+def extra_configs(lib, dev, args):
+    """configs[2]: 5-planet joint transit + RV model, N=1e5, batched VJP through all ops;
+    configs[3]: celerite SHOTerm GP log-likelihood, N=1e6."""
+    import torch
+
+    from exoplanet_b200 import fused, gp, synthetic
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import xo_oracle as O
+
+    def d(x):
+        return torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float64, device=dev)
+
+    flush = torch.empty(192 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
+    out = {}
+    # ---- configs[2] -----------------------------------------------------------------------------
+    Cn, P, N = 128, 5, N_CADENCES
+    p = synthetic.transit_params(Cn, P, seed=synthetic.SEED + 5)
+    t = synthetic.cadence_times(N)
+    y = synthetic.noise(N, SIGMA)
+    data = fused.TransitData(t, y, np.full(N, SIGMA), device=dev)
+    rv_obs = 3.0 * np.random.default_rng(7).normal(size=N)
+    rvdata = fused.TransitData(t, rv_obs, np.full(N, 3.0), device=dev)
+    par = fused.pack_params(d(p["period"]), d(p["t0"]), d(p["ecc"]), d(p["omega"]), d(p["b"]), d(p["ror"]), d(p["m_planet"]), d(p["K"]))
+    star = fused.pack_star(torch.ones(Cn, dtype=torch.float64, device=dev), torch.ones(Cn, dtype=torch.float64, device=dev), d(p["u1"]),
+                           d(p["u2"]))
+    mean, gamma = d(p["mean"]), d(p["gamma"])
+    model = fused.TransitModel(data)
+    el_o = O.elements_from_params(p["period"], p["t0"], p["ecc"], p["omega"], p["b"], p["ror"], m_planet=p["m_planet"], K=p["K"])
+    elem = d(el_o)
+    res = {}
+
+    def step():
+        res["lc"] = model.logp_grad(par, star, mean)
+        res["rv"] = fused.rv_logp_grad(rvdata, elem, gamma)
+
+    ms = _time_steps(step, 10, flush)
+    sel = [0, Cn - 1]
+    lo = O.transit_logp_grad(t, y, np.full(N, 1 / SIGMA ** 2), el_o[sel], O.get_cl(p["u1"][sel], p["u2"][sel]), p["mean"][sel], np.zeros(1),
+                             np.ones(1), lognorm=data.lognorm)[0]
+    lr = O.rv_logp_grad(t, rv_obs, np.full(N, 1 / 9.0), el_o[sel], p["gamma"][sel], lognorm=rvdata.lognorm)[0]
+    err = max(float(np.max(np.abs(res["lc"][0].cpu().numpy()[sel] - lo) / np.abs(lo))),
+              float(np.max(np.abs(res["rv"][0].cpu().numpy()[sel] - lr) / np.abs(lr))))
+    out["configs[2] 5-planet transit+RV, N=1e5"] = {"value": Cn / (ms * 1e-3), "unit": "model+grad evals/s", "ms_per_step": ms, "chains": Cn,
+                                                    "parity_logp_rel_err": err}
+    # ---- configs[3] -----------------------------------------------------------------------------
+    Ng = 1000000
+    pr = synthetic.gp_problem(Ng)
+    tg, yg, dg = d(pr["t"]), d(pr["y"]), d(pr["diag"])
+    lo = O.celerite_sho_loglike(pr["t"], pr["y"], pr["diag"], pr["S0"], pr["w0"], pr["Q"])
+    for B in (1, 16):
+        yb = yg[None, :].repeat(B, 1).contiguous()
+        ws = torch.empty(lib.xo_celerite_sho_workspace(Ng, B) // 8 + 1, dtype=torch.float64, device=dev)
+        r = {}
+
+        def gstep():
+            r["ll"] = gp.sho_loglike(tg, yb, dg, pr["S0"], pr["w0"], pr["Q"], workspace=ws)
+
+        ms = _time_steps(gstep, 10, flush)
+        out["configs[3] celerite SHO loglike, N=1e6, %d chain(s)" % B] = {
+            "value": B * Ng / (ms * 1e-3), "unit": "cadences/s", "ms_per_step": ms, "gb_per_s": 24.0 * B * Ng / (ms * 1e-3) / 1e9,
+            "parity_rel_err": float(abs(r["ll"][0].item() - lo) / abs(lo))}
+    return out
+
+
 def arm_ours(args):
     import torch
 
@@ -325,6 +408,11 @@ def arm_ours(args):
             del sf, cf, e
         del M
 
+    # ---- the other BASELINE configs, measured briefly on one GPU (parity-checked against the oracle) ----
+    other = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        other = extra_configs(lib, dev, args)
+
     tm = torch.tensor([ms_dev, e2e_s * 1e3, res_s * 1e3], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -389,6 +477,8 @@ def arm_ours(args):
                                    "kernel": "kepler_fwd_kernel", "bytes_per_element": KEPLER_BYTES_PER_ELEMENT}
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if other is not None:
+        line["other_configs"] = other
     print(json.dumps(line))
 
 
@@ -401,6 +491,7 @@ def main():
     ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-kepler", action="store_true", help="skip the Kepler micro-benchmark")
+    ap.add_argument("--no-extra", action="store_true", help="skip the brief configs[2] / configs[3] measurements")
     ap.add_argument("--full-sweep", action="store_true",
                     help="sum the Gaussian terms of every cadence in the sweep instead of using the data moments")
     args = ap.parse_args()

@@ -304,7 +304,7 @@ int xo_transit_data_create(const double *t, const double *y, const double *ivar,
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(d->y, y, nb, cudaMemcpyHostToDevice, d->st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d->ivar, ivar, nb, cudaMemcpyHostToDevice, d->st);
-  int rc = e == cudaSuccess ? xo_transit_data_moments(d->y, d->ivar, N, d->moments, d->st) : -(int)e;
+  int rc = e == cudaSuccess ? xo_transit_data_moments(d->t, d->y, d->ivar, N, d->moments, d->st) : -(int)e;
   if (rc == 0) rc = xo::cuda_status(cudaStreamSynchronize(d->st));
   cudaSetDevice(prev);
   if (rc != 0) {

@@ -19,13 +19,18 @@ namespace {
 constexpr double kGGrav = 2942.2062175044193;  // R_sun^3 / M_sun / day^2 (orbits/constants.py:32)
 constexpr unsigned kFullM = 0xffffffffu;
 
+// two adjacent lanes per (chain, planet): lane parity = contact side, so the two bracketed
+// Newton solves of the in-transit window run concurrently; even lane writes the element block
 __global__ void model_prologue_kernel(const double *__restrict__ par, const double *__restrict__ star, int64_t C, int P,
                                       double texp, int use_in_transit, double *__restrict__ elem,
                                       double *__restrict__ cl) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= C * P) return;
-  const int64_t c = idx / P;
-  const double *q = par + idx * XO_NPAR;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t idx = tid >> 1;
+  const int side = (int)(tid & 1);
+  const bool active = idx < C * P;
+  const int64_t ii = active ? idx : 0;
+  const int64_t c = ii / P;
+  const double *q = par + ii * XO_NPAR;
   const double period = q[0], t0 = q[1], e = q[2], omega = q[3], b = q[4], ror = q[5], mpl = q[6], K = q[7];
   const double R = star[c * XO_NSTAR + 0], Ms = star[c * XO_NSTAR + 1];
   const double a = cbrt(kGGrav * (Ms + mpl) * period * period / (4.0 * xo::kPi * xo::kPi));
@@ -39,21 +44,31 @@ __global__ void model_prologue_kernel(const double *__restrict__ par, const doub
   const double F = (1.0 + e * sw) / ome2;
   const double cosi = F * R / a * b;
   const double sini = sqrt((1.0 - cosi) * (1.0 + cosi));
-  double ts = -INFINITY, te = INFINITY;
+  double tc = side ? INFINITY : -INFINITY;  // this lane's contact time relative to t0
+  int flag = 0;
   if (use_in_transit) {
-    double Ml, Mr;
-    int flag = xo::cp_solve(a, e, cw, sw, cosi, R * (1.0 + ror), Ml, Mr);
+    double Mc;
+    flag = xo::cp_solve_side(a, e, cw, sw, cosi, R * (1.0 + ror), side ? 1.0 : -1.0, Mc);
     if (flag == 0) {
       const double hp = 0.5 * period;
-      ts = (Ml - M0) / n + hp;
-      ts = ts - period * floor(ts / period) - hp;
-      te = (Mr - M0) / n + hp;
-      te = te - period * floor(te / period) - hp;
-      if (ts > 0.0) ts -= period;
-      if (te < 0.0) te += period;
-      ts -= 0.5 * texp;
-      te += 0.5 * texp;
+      tc = (Mc - M0) / n + hp;
+      tc = tc - period * floor(tc / period) - hp;
+      if (side == 0) {
+        if (tc > 0.0) tc -= period;
+        tc -= 0.5 * texp;
+      } else {
+        if (tc < 0.0) tc += period;
+        tc += 0.5 * texp;
+      }
     }
+  }
+  const double tc_other = __shfl_xor_sync(0xffffffffu, tc, 1);
+  const int flag_other = __shfl_xor_sync(0xffffffffu, flag, 1);
+  if (!active || side != 0) return;
+  double ts = tc, te = tc_other;
+  if (flag | flag_other) {
+    ts = -INFINITY;
+    te = INFINITY;
   }
   double *el = elem + idx * XO_NEL;
   el[XO_EL_T0] = t0;
@@ -93,18 +108,27 @@ __global__ void model_epilogue_kernel(const double *__restrict__ par, const doub
   if (c >= C) return;
   const int nacc = xo::kNBase + P * XO_NGRAD;
   const double *src = partial + c * slots * nacc;
+  // fold: lane l sums slots l, l+32, ... of every accumulator (ascending), then a fixed-order
+  // butterfly combines the 32 lane sums -> deterministic, and 32x less serial latency
   double g[XO_NGRAD];
 #pragma unroll
   for (int j = 0; j < XO_NGRAD; ++j) g[j] = 0.0;
   double base = 0.0;
-  if (lane < P) {
-    for (int s = 0; s < slots; ++s) {
-      const double *row = src + (int64_t)s * nacc + xo::kNBase + lane * XO_NGRAD;
+  for (int j = 0; j < nacc; ++j) {
+    double acc = 0.0;
+    for (int s = lane; s < slots; s += 32) acc += src[(int64_t)s * nacc + j];
 #pragma unroll
-      for (int j = 0; j < XO_NGRAD; ++j) g[j] += row[j];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFullM, acc, o);
+    if (j < xo::kNBase) {
+      if (lane == 8 + j) base = acc;
+    } else {
+      const int pj = (j - xo::kNBase) / XO_NGRAD, k = (j - xo::kNBase) % XO_NGRAD;
+      if (lane == pj) {
+#pragma unroll
+        for (int kk = 0; kk < XO_NGRAD; ++kk)
+          if (kk == k) g[kk] = acc;
+      }
     }
-  } else if (lane >= 8 && lane < 8 + xo::kNBase) {
-    for (int s = 0; s < slots; ++s) base += src[(int64_t)s * nacc + (lane - 8)];
   }
   const double R = star[c * XO_NSTAR + 0], Ms = star[c * XO_NSTAR + 1];
   double gR = 0.0, gMs = 0.0;
@@ -233,7 +257,7 @@ int xo_transit_model_logp_grad(const double *t, const double *y, const double *i
   double *partial = reinterpret_cast<double *>(ws + L.off_partial);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t cp = C * P;
-  model_prologue_kernel<<<(unsigned)((cp + 63) / 64), 64, 0, st>>>(par, star, C, (int)P, texp, use_in_transit, elem, cl);
+  model_prologue_kernel<<<(unsigned)((2 * cp + 63) / 64), 64, 0, st>>>(par, star, C, (int)P, texp, use_in_transit, elem, cl);
   xo::launch_transit_logp_grad(t, y, ivar, N, elem, cl, mean, C, (int)P, dtk, wk, K, L.sp, moments, partial, st);
   model_epilogue_kernel<<<(unsigned)((C + 3) / 4), 128, 0, st>>>(par, star, partial, L.sp.slots, C, (int)P, lognorm, logp,
                                                                  gpar, gstar, gmean);
@@ -248,7 +272,7 @@ int xo_elements_from_params(const double *par, const double *star, int64_t C, in
   if (C == 0 || P == 0) return 0;
   if (!par || !star || !elem || !cl) return XO_EINVAL;
   const int64_t cp = C * P;
-  model_prologue_kernel<<<(unsigned)((cp + 63) / 64), 64, 0, static_cast<cudaStream_t>(stream)>>>(
+  model_prologue_kernel<<<(unsigned)((2 * cp + 63) / 64), 64, 0, static_cast<cudaStream_t>(stream)>>>(
       par, star, C, (int)P, texp, use_in_transit, elem, cl);
   return xo::launch_status();
 }

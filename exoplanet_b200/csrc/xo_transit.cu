@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
   // is left in the queues -- written as ONE loop so the expensive drain body exists once in the
   // binary.  The common step (no lane of the warp in any window) is: kUnroll coalesced loads that
   // were issued one step ahead, 4 flops + 2 compares per cadence and planet, one vote.
+  const bool sorted = kMoments && moments[4] != 0.0;  // t non-decreasing: steps can be skipped wholesale
   const double *tp = t + start + lane;
   double tnext[kUnroll];
 #pragma unroll
@@ -208,7 +209,26 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
     const bool last = base >= end;
     double tt[kUnroll], yy[kUnroll], iv[kUnroll];
     uint32_t valid = 0u;  // bit u: cadence base + 32 u + lane exists
-    if (!last) {
+    if (!last && sorted) {
+      // t is sorted: the step spans [tA, tB]; if that interval misses every planet's window (in
+      // phase, with wrap) no lane can be in transit -> skip the step after two broadcast loads
+      const double tA = __ldg(t + base), tB = __ldg(t + min(base + 32 * kUnroll, end) - 1);
+      bool hit = false;
+      for (int p = 0; p < P; ++p) {
+        const double rpp = sm.rperiod[p];
+        const double uA = (tA - sm.elem[p][XO_EL_T0]) * rpp;
+        const double a = uA - rint(uA), b = a + (tB - tA) * rpp;  // phase interval, a in [-1/2, 1/2]
+        const double lo = sm.wlo[p] - 1e-9, hi = sm.whi[p] + 1e-9;
+        hit |= (b - a >= 1.0) | ((a <= hi) & (b >= lo)) | ((a <= hi + 1.0) & (b >= lo + 1.0)) | ((a <= hi - 1.0) & (b >= lo - 1.0));
+      }
+      if (!hit) continue;
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const bool v = base + 32 * u + lane < end;
+        valid |= v ? (1u << u) : 0u;
+        tt[u] = v ? __ldg(tp + (base - start) + 32 * u) : 0.0;
+      }
+    } else if (!last) {
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
         tt[u] = tnext[u];
@@ -217,6 +237,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
       const uint32_t nb = base + 32 * kUnroll;  // prefetch the next step while this one is processed
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) tnext[u] = (nb + 32 * u + lane < end) ? __ldg(tp + (nb - start) + 32 * u) : 0.0;
+    }
+    if (!last) {
       if (kBase) {
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
@@ -302,9 +324,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
 }
 
 // data-only moments of the Gaussian likelihood, one CTA, fixed-order tree (deterministic):
-// out = (y_ref, S1, Sy, Syy) with y_ref the ivar-weighted mean of y
-__global__ void __launch_bounds__(1024) transit_moments_kernel(const double *__restrict__ y, const double *__restrict__ ivar,
-                                                               int64_t N, double *__restrict__ out) {
+// out = (y_ref, S1, Sy, Syy, sorted) with y_ref the ivar-weighted mean of y and sorted = 1 when
+// t is non-decreasing (lets the sweep skip whole 128-cadence steps with one interval test)
+__global__ void __launch_bounds__(1024) transit_moments_kernel(const double *__restrict__ t, const double *__restrict__ y,
+                                                               const double *__restrict__ ivar, int64_t N,
+                                                               double *__restrict__ out) {
   __shared__ double red[3][32];
   __shared__ double yref_s;
   auto block_sum3 = [&](double a, double b, double c, double &A, double &B, double &Cc) {
@@ -325,14 +349,16 @@ __global__ void __launch_bounds__(1024) transit_moments_kernel(const double *__r
     }
     __syncthreads();
   };
-  double s1 = 0.0, sy = 0.0;
+  double s1 = 0.0, sy = 0.0, bad = 0.0;
   for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
     const double w = ivar[i];
     s1 += w;
     sy = fma(w, y[i], sy);
+    if (i + 1 < N && !(t[i + 1] >= t[i])) bad += 1.0;
   }
-  double S1, Sy0, dummy;
-  block_sum3(s1, sy, 0.0, S1, Sy0, dummy);
+  double S1, Sy0, Bad;
+  block_sum3(s1, sy, bad, S1, Sy0, Bad);
+  double dummy;
   if (threadIdx.x == 0) yref_s = Sy0 / S1;
   __syncthreads();
   const double yref = yref_s;
@@ -349,6 +375,7 @@ __global__ void __launch_bounds__(1024) transit_moments_kernel(const double *__r
     out[1] = S1;
     out[2] = Sy;
     out[3] = Syy;
+    out[4] = Bad == 0.0 ? 1.0 : 0.0;
   }
 }
 
@@ -608,9 +635,10 @@ size_t xo_transit_logp_grad_workspace(int64_t N, int64_t C, int64_t P) {
   return sizeof(double) * (size_t)C * (size_t)sp.slots * (size_t)(kNBase + P * XO_NGRAD);
 }
 
-int xo_transit_data_moments(const double *y, const double *ivar, int64_t N, double *moments, void *stream) {
-  if (N <= 0 || !y || !ivar || !moments) return XO_EINVAL;
-  transit_moments_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(y, ivar, N, moments);
+int xo_transit_data_moments(const double *t, const double *y, const double *ivar, int64_t N, double *moments,
+                            void *stream) {
+  if (N <= 0 || !t || !y || !ivar || !moments) return XO_EINVAL;
+  transit_moments_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(t, y, ivar, N, moments);
   return xo::launch_status();
 }
 

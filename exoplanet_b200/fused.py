@@ -79,13 +79,14 @@ class TransitData:
         self._moments = None
 
     def moments(self):
-        """Device tensor (y_ref, sum ivar, sum ivar (y - y_ref), sum ivar (y - y_ref)^2): the
+        """Device tensor (y_ref, sum ivar, sum ivar (y - y_ref), sum ivar (y - y_ref)^2, t_is_sorted, ...): the
         data-only part of the Gaussian sums, computed once (xo_transit_data_moments)."""
         if self._moments is None and self.y is not None and self.ivar is not None:
             lib = _lib.require_cuda()
-            m = torch.empty(4, dtype=torch.float64, device=self.device)
+            m = torch.zeros(8, dtype=torch.float64, device=self.device)
             with torch.cuda.device(self.device):
-                _lib.check(lib.xo_transit_data_moments(_ptr(self.y), _ptr(self.ivar), self.n, _ptr(m), _lib.stream_ptr()), "moments")
+                _lib.check(lib.xo_transit_data_moments(_ptr(self.t), _ptr(self.y), _ptr(self.ivar), self.n, _ptr(m), _lib.stream_ptr()),
+                           "moments")
             self._moments = m
         return self._moments
 

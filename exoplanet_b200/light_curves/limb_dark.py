@@ -100,7 +100,7 @@ class LimbDarkLightCurve:
         r = _tensor(r, dev).reshape(-1)
         t = _tensor(t, dev)
         scalar_texp = texp is None or np.ndim(texp) == 0 or (isinstance(texp, torch.Tensor) and texp.dim() == 0)
-        if isinstance(orbit, KeplerianOrbit) and not light_delay and scalar_texp and t.dim() == 1 and t.is_cuda:
+        if type(orbit) is KeplerianOrbit and not light_delay and scalar_texp and t.dim() == 1 and t.is_cuda:
             tex = None if texp is None else float(texp)
             elem = orbit.elements(r=r, texp=tex, use_in_transit=use_in_transit)
             dtk, wk = fused._stencil_dev(fused.exposure_stencil(tex, oversample, order), dev)

@@ -111,11 +111,13 @@ int xo_transit_lc_vjp(const double *t, int64_t N, const double *elem, const doub
  *   logp[c] = lognorm - 1/2 sum_n ivar[n] (y[n] - mean[c] - sum_p lc[c][n][p])^2
  *   gel[C][P][XO_NGRAD], gcl[C][3], gmean[C].
  * workspace: xo_transit_logp_grad_workspace(N, C, P) bytes of device memory.
- * moments: NULL, or the 4 data-only moments written by xo_transit_data_moments(y, ivar) --
- *   (y_ref, sum ivar, sum ivar (y-y_ref), sum ivar (y-y_ref)^2); with them the out-of-transit
- *   part of the sums is closed-form and the sweep reads t only (same result to rounding). */
+ * moments: NULL, or the 8-double block written by xo_transit_data_moments(t, y, ivar) --
+ *   (y_ref, sum ivar, sum ivar (y-y_ref), sum ivar (y-y_ref)^2, t_is_sorted, 0, 0, 0); with it the
+ *   out-of-transit part of the sums is closed-form, the sweep reads t only, and for sorted t whole
+ *   128-cadence steps are skipped by one interval test (same result to rounding). */
 size_t xo_transit_logp_grad_workspace(int64_t N, int64_t C, int64_t P);
-int xo_transit_data_moments(const double *y, const double *ivar, int64_t N, double *moments, void *stream);
+int xo_transit_data_moments(const double *t, const double *y, const double *ivar, int64_t N, double *moments /*[8]*/,
+                            void *stream);
 int xo_transit_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *elem,
                          const double *cl, const double *mean, int64_t C, int64_t P, const double *dtk, const double *wk,
                          int K, double lognorm, const double *moments, double *logp, double *gel, double *gcl,

@@ -247,3 +247,37 @@ def test_simple_orbit_matches_keplerian():  # orbits/simple_test.py:51-81
     b = lc.get_light_curve(orbit=simple, r=0.04 * kep.r_star, t=t).cpu().numpy()
     assert a.min() < -1e-3
     assert np.allclose(a, b, rtol=0, atol=2e-5)
+
+
+def test_ttv_orbit_without_ttvs_equals_keplerian():  # orbits/ttv_test.py:49-83
+    from exoplanet_b200.orbits import TTVOrbit, compute_expected_transit_times
+
+    periods, t0s, lo, hi = [10.5, 56.34], [45.3, 48.1], 456.023, 595.23
+    time = dev(np.linspace(lo, hi, 5000))
+    expected = compute_expected_transit_times(lo, hi, periods, t0s)
+    for p_, t0_, tt in zip(periods, t0s, expected):  # orbits/ttv_test.py:8-20
+        assert np.all(tt >= lo) and np.all(tt <= hi) and tt[0] - p_ < lo and tt[-1] + p_ > hi
+    orbit0 = KeplerianOrbit(period=dev(periods), t0=dev(t0s))
+    orbit1 = TTVOrbit(period=dev(periods), t0=dev([t[0] for t in expected]), ttvs=[np.zeros_like(t) for t in expected])
+    orbit2 = TTVOrbit(transit_times=expected, device=DEV)
+    for name in ("get_relative_position", "get_star_position", "get_planet_position", "get_relative_velocity", "get_star_velocity",
+                 "get_planet_velocity"):
+        ref = npy(getattr(orbit0, name)(time))
+        assert np.allclose(ref, npy(getattr(orbit1, name)(time))), name
+        assert np.allclose(ref, npy(getattr(orbit2, name)(time))), name
+    rv0 = orbit0.get_radial_velocity(time).cpu().numpy()
+    assert np.allclose(rv0, orbit1.get_radial_velocity(time).cpu().numpy())
+    # consistency of the two constructors (orbits/ttv_test.py:23-46)
+    rng = np.random.default_rng(6934104)
+    ttvs = [0.01 * rng.normal(size=len(t)) for t in expected]
+    a = TTVOrbit(period=dev(periods), t0=dev([t[0] for t in expected]), ttvs=ttvs)
+    for i in range(2):
+        assert np.allclose(a.transit_times[i].cpu().numpy(), expected[i] + ttvs[i])
+    b = TTVOrbit(transit_times=[x for x in a.transit_times])
+    c = TTVOrbit(period=b.period, t0=b.t0, ttvs=b.ttvs)
+    for i in range(2):
+        assert np.allclose(b.transit_times[i].cpu().numpy(), c.transit_times[i].cpu().numpy())
+    # a light curve through the generic path moves with the TTVs
+    lc = LimbDarkLightCurve(0.3, 0.2, device=DEV)
+    shifted = lc.get_light_curve(orbit=a, r=dev([0.05, 0.08]), t=time)
+    assert shifted.shape == (5000, 2) and shifted.min().item() < -1e-3
