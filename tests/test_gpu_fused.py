@@ -94,6 +94,13 @@ def test_moments_path_equals_full_sweep():
     assert torch.allclose(a[3], b[3], rtol=1e-9, atol=1e-9 * b[3].abs().max().item())
     assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
     m = data.moments().cpu().numpy()
+    assert m[4] == 1.0  # t is sorted -> step skipping is on; an unsorted copy must give the same answer
+    perm = np.random.default_rng(3).permutation(N)
+    data_u = fused.TransitData(t[perm], y[perm], np.full(N, 5e-4), device=DEV)
+    assert data_u.moments().cpu().numpy()[4] == 0.0
+    c = fused.transit_logp_grad(data_u, dev(el_o), dev(cl), mean, use_moments=True)
+    assert torch.allclose(a[0], c[0], rtol=1e-12, atol=0)
+    assert torch.allclose(a[1], c[1], rtol=1e-9, atol=1e-9 * a[1].abs().max().item())
     iv = 1 / 5e-4 ** 2
     yref = np.sum(iv * y) / (iv * N)
     assert abs(m[0] - yref) < 1e-13 and abs(m[1] - iv * N) < 1e-6 * iv
