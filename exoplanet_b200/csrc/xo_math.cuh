@@ -509,7 +509,9 @@ XO_HD void true_anomaly(const double *el, double tt, double &sf, double &cf, dou
 // One light-curve sample: returns lc = s(b, ror) . cl - 1 for z > 0, else exactly 0
 // (limb_dark.py:216-252).  With kGrad, ACCUMULATES w * d lc/d(t0,tref,n,e,cosw,sinw,cosi,
 // sini,aor,ror) into g[10] and w * s into gs[3] (= w * d lc / d cl).
-template <bool kGrad>
+// kStride: element stride of g / gs (1 for plain arrays; blockDim for per-thread columns of a
+// shared-memory matrix, which keeps the 13 accumulators out of registers during the heavy math).
+template <bool kGrad, int kStride = 1>
 XO_HD double lc_point(const double *el, const double *cl, double tt, double w, double *g, double *gs) {
   double sf, cf, tm;
   true_anomaly(el, tt, sf, cf, tm);
@@ -532,8 +534,8 @@ XO_HD double lc_point(const double *el, const double *cl, double tt, double w, d
   double lc = fma(S[0], cl[0], fma(S[1], cl[1], S[2] * cl[2])) - 1.0;
   if (!kGrad) return lc;
   gs[0] = fma(w, S[0], gs[0]);
-  gs[1] = fma(w, S[1], gs[1]);
-  gs[2] = fma(w, S[2], gs[2]);
+  gs[kStride] = fma(w, S[1], gs[kStride]);
+  gs[2 * kStride] = fma(w, S[2], gs[2 * kStride]);
   double dldb = w * fma(B[0], cl[0], fma(B[1], cl[1], B[2] * cl[2]));
   double dldr = w * fma(R[0], cl[0], fma(R[1], cl[1], R[2] * cl[2]));
   double db_drr = sh;
@@ -555,14 +557,14 @@ XO_HD double lc_point(const double *el, const double *cl, double tt, double w, d
   double dl_dM = dldb * db_df * dfdM;
   double gt = -dl_dM * el[2];
   g[0] += gt;
-  g[1] += gt;
-  g[2] = fma(dl_dM, tm, g[2]);
-  g[3] = fma(dldb, db_df * dfde + db_drr * drr_de, g[3]);
-  g[4] = fma(dldb, db_dcwf * cf + db_dswf * sf, g[4]);
-  g[5] = fma(dldb, db_dswf * cf - db_dcwf * sf, g[5]);
-  g[6] = fma(dldb, db_dci, g[6]);
-  g[8] = fma(dldb, db_drr * rr * rcp(aor), g[8]);
-  g[9] += dldr;
+  g[kStride] += gt;
+  g[2 * kStride] = fma(dl_dM, tm, g[2 * kStride]);
+  g[3 * kStride] = fma(dldb, db_df * dfde + db_drr * drr_de, g[3 * kStride]);
+  g[4 * kStride] = fma(dldb, db_dcwf * cf + db_dswf * sf, g[4 * kStride]);
+  g[5 * kStride] = fma(dldb, db_dswf * cf - db_dcwf * sf, g[5 * kStride]);
+  g[6 * kStride] = fma(dldb, db_dci, g[6 * kStride]);
+  g[8 * kStride] = fma(dldb, db_drr * rr * rcp(aor), g[8 * kStride]);
+  g[9 * kStride] += dldr;
   return lc;
 }
 

@@ -129,12 +129,17 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
   __shared__ ChainSmem sm;
   __shared__ uint32_t queue[kWarps][XO_MAX_PLANETS][kQueue];
   __shared__ double gacc[kWarps][XO_MAX_PLANETS][XO_NGRAD];
+  __shared__ double lacc[XO_NGRAD + 3][kThreads];  // per-thread gradient accumulators of one drain
   const int64_t c = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = blockIdx.x * kWarps + warp;
   stage_chain(sm, elem, cl, mean, dtk, wk, c, P, K);
   for (int i = lane; i < XO_MAX_PLANETS * XO_NGRAD; i += 32) (&gacc[warp][0][0])[i] = 0.0;
+#pragma unroll
+  for (int j = 0; j < XO_NGRAD + 3; ++j) lacc[j][threadIdx.x] = 0.0;
   __syncwarp();
+  double *const gl = &lacc[0][threadIdx.x];          // g[j]  at gl[j * kThreads]
+  double *const gsl = &lacc[XO_NGRAD][threadIdx.x];  // gs[j] at gsl[j * kThreads]
 
   const int nacc = kNBase + P * XO_NGRAD;
   double lp = 0.0, gm = 0.0, gc0 = 0.0, gc1 = 0.0, gc2 = 0.0;
@@ -144,13 +149,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
 
   // evaluate m (<= 32) queued entries of planet p starting at queue offset off
   auto drain = [&](int p, int off, int m) {
-    double g[XO_NGRAD];
-#pragma unroll
-    for (int j = 0; j < XO_NGRAD; ++j) g[j] = 0.0;
+    double scale = 0.0;  // cotangent multiplying this lane's accumulated d lc / d elements
     if (lane < m) {
       const uint32_t idx = queue[warp][p][off + lane];
       const double tt = __ldg(t + idx);
-      double gs[3] = {0.0, 0.0, 0.0};
       double ltot = 0.0;
       bool owner = true;  // the lowest in-window planet owns the per-cadence terms
       // one call site for the sample evaluation: planet p with its gradient weights, any other
@@ -161,82 +163,72 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
         if (q < p) owner = false;
         for (int k = 0; k < K; ++k) {
           const double w = sm.wk[k];
-          ltot = fma(w, xo::lc_point<true>(sm.elem[q], sm.cl, tt + sm.dtk[k], self ? w : 0.0, g, gs), ltot);
+          ltot = fma(w, xo::lc_point<true, kThreads>(sm.elem[q], sm.cl, tt + sm.dtk[k], self ? w : 0.0, gl, gsl), ltot);
         }
       }
       if (kVjp) {
-        const double bar = __ldg(y + ((int64_t)c * N + idx) * P + p);
-#pragma unroll
-        for (int j = 0; j < XO_NGRAD; ++j) g[j] *= bar;
-        gc0 = fma(bar, gs[0], gc0);
-        gc1 = fma(bar, gs[1], gc1);
-        gc2 = fma(bar, gs[2], gc2);
+        scale = __ldg(y + ((int64_t)c * N + idx) * P + p);
       } else {
-      const double yy = __ldg(y + idx), iv = __ldg(ivar + idx);
-      const double r0 = yy - mean_c;
-      const double wres = iv * (r0 - ltot);
-#pragma unroll
-      for (int j = 0; j < XO_NGRAD; ++j) g[j] *= wres;
-      gc0 = fma(wres, gs[0], gc0);
-      gc1 = fma(wres, gs[1], gc1);
-      gc2 = fma(wres, gs[2], gc2);
-      if (owner) {  // -1/2 iv (res^2 - r0^2) and iv (res - r0), without cancellation
-        lp = fma(0.5 * iv * ltot, 2.0 * r0 - ltot, lp);
-        gm = fma(-iv, ltot, gm);
+        const double yy = __ldg(y + idx), iv = __ldg(ivar + idx);
+        const double r0 = yy - mean_c;
+        scale = iv * (r0 - ltot);
+        if (owner) {  // -1/2 iv (res^2 - r0^2) and iv (res - r0), without cancellation
+          lp = fma(0.5 * iv * ltot, 2.0 * r0 - ltot, lp);
+          gm = fma(-iv, ltot, gm);
+        }
       }
-      }
+      gc0 = fma(scale, gsl[0], gc0);
+      gc1 = fma(scale, gsl[kThreads], gc1);
+      gc2 = fma(scale, gsl[2 * kThreads], gc2);
+      gsl[0] = gsl[kThreads] = gsl[2 * kThreads] = 0.0;
     }
 #pragma unroll
     for (int j = 0; j < XO_NGRAD; ++j) {
-      double v = warp_sum(g[j]);
-      if (lane == 0) gacc[warp][p][j] += v;
+      if (j == 1 || j == 7) continue;  // d/dtref == d/dt0; sin i carries no gradient
+      double v = warp_sum(scale * gl[j * kThreads]);
+      gl[j * kThreads] = 0.0;
+      if (lane == 0) {
+        gacc[warp][p][j] += v;
+        if (j == 0) gacc[warp][p][1] += v;
+      }
     }
+    gl[kThreads] = 0.0;
   };
 
   const uint32_t start = (uint32_t)min((int64_t)slot * L, N);
   const uint32_t end = (uint32_t)min((int64_t)slot * L + L, N);
   // Sweep steps of 32*kUnroll cadences, then one final pass (last = true) that only flushes what
   // is left in the queues -- written as ONE loop so the expensive drain body exists once in the
-  // binary.  The common step (no lane of the warp in any window) is: kUnroll coalesced loads that
-  // were issued one step ahead, 4 flops + 2 compares per cadence and planet, one vote.
+  // binary.  The common step: for sorted t one interval test on two broadcast loads; otherwise
+  // kUnroll coalesced loads, 4 flops + 2 compares per cadence and planet, one vote.
   const bool sorted = kMoments && moments[4] != 0.0;  // t non-decreasing: steps can be skipped wholesale
-  const double *tp = t + start + lane;
-  double tnext[kUnroll];
-#pragma unroll
-  for (int u = 0; u < kUnroll; ++u) tnext[u] = (start + 32 * u + lane < end) ? __ldg(tp + 32 * u) : 0.0;
+  const double *tp = t + lane;
 #pragma unroll 1
   for (uint32_t base = start;; base += 32 * kUnroll) {
     const bool last = base >= end;
     double tt[kUnroll], yy[kUnroll], iv[kUnroll];
     uint32_t valid = 0u;  // bit u: cadence base + 32 u + lane exists
-    if (!last && sorted) {
-      // t is sorted: the step spans [tA, tB]; if that interval misses every planet's window (in
-      // phase, with wrap) no lane can be in transit -> skip the step after two broadcast loads
-      const double tA = __ldg(t + base), tB = __ldg(t + min(base + 32 * kUnroll, end) - 1);
-      bool hit = false;
-      for (int p = 0; p < P; ++p) {
-        const double rpp = sm.rperiod[p];
-        const double uA = (tA - sm.elem[p][XO_EL_T0]) * rpp;
-        const double a = uA - rint(uA), b = a + (tB - tA) * rpp;  // phase interval, a in [-1/2, 1/2]
-        const double lo = sm.wlo[p] - 1e-9, hi = sm.whi[p] + 1e-9;
-        hit |= (b - a >= 1.0) | ((a <= hi) & (b >= lo)) | ((a <= hi + 1.0) & (b >= lo + 1.0)) | ((a <= hi - 1.0) & (b >= lo - 1.0));
+    if (!last) {
+      if (sorted) {
+        // the step spans [tA, tB]; if that interval misses every planet's window (in phase, with
+        // wrap) no lane can be in transit -> skip the step after two broadcast loads
+        const double tA = __ldg(t + base), tB = __ldg(t + min(base + 32 * kUnroll, end) - 1);
+        bool hit = false;
+        for (int p = 0; p < P; ++p) {
+          const double rpp = sm.rperiod[p];
+          const double uA = (tA - sm.elem[p][XO_EL_T0]) * rpp;
+          const double a = uA - rint(uA), b = a + (tB - tA) * rpp;  // phase interval, a in [-1/2, 1/2]
+          const double lo = sm.wlo[p] - 1e-9, hi = sm.whi[p] + 1e-9;
+          hit |= (b - a >= 1.0) | ((a <= hi) & (b >= lo)) | ((a <= hi + 1.0) & (b >= lo + 1.0)) | ((a <= hi - 1.0) & (b >= lo - 1.0));
+        }
+        if (!hit) continue;
       }
-      if (!hit) continue;
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
+      for (int u = 0; u < kUnroll; ++u) {  // kUnroll coalesced loads in flight together
         const bool v = base + 32 * u + lane < end;
         valid |= v ? (1u << u) : 0u;
-        tt[u] = v ? __ldg(tp + (base - start) + 32 * u) : 0.0;
+        tt[u] = v ? __ldg(tp + base + 32 * u) : 0.0;
       }
-    } else if (!last) {
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        tt[u] = tnext[u];
-        valid |= (base + 32 * u + lane < end) ? (1u << u) : 0u;
-      }
-      const uint32_t nb = base + 32 * kUnroll;  // prefetch the next step while this one is processed
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) tnext[u] = (nb + 32 * u + lane < end) ? __ldg(tp + (nb - start) + 32 * u) : 0.0;
     }
     if (!last) {
       if (kBase) {
@@ -597,6 +589,7 @@ void launch_transit_logp_grad(const double *t, const double *y, const double *iv
   if (moments) {
     if (mb == 2) XO_LAUNCH(2, false, true);
     else if (mb == 4) XO_LAUNCH(4, false, true);
+    else if (mb == 5) XO_LAUNCH(5, false, true);
     else XO_LAUNCH(3, false, true);
   } else {
     if (mb == 2) XO_LAUNCH(2, false, false);

@@ -14,7 +14,7 @@ timeout 300 python bench.py --impl reference --steps 20 --warmup 2 > $OUT/${TAG}
 if [ "$MODE" = "full" ]; then
 # tuning sweep of the logp kernel (register cap x launch width)
 : > $OUT/${TAG}_sweep.txt
-for SWEEPFLAG in "" "--full-sweep"; do for mb in 2 3 4; do for w in 16 24 40; do
+for SWEEPFLAG in "" "--full-sweep"; do for mb in 2 3 4 5; do for w in 16 24 32; do
   echo -n "flag=$SWEEPFLAG minblocks=$mb warps_per_sm=$w " >> $OUT/${TAG}_sweep.txt
   XO_TRANSIT_MINBLOCKS=$mb XO_TRANSIT_WARPS_PER_SM=$w timeout 120 python bench.py --steps 20 --warmup 3 --no-cpu --no-kepler $SWEEPFLAG 2>/dev/null \
     | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'])" >> $OUT/${TAG}_sweep.txt
