@@ -1,0 +1,202 @@
+// xo_prologue.cuh -- the O(P) prologue of the transit model and its reverse pass, as warp-level
+// device routines shared by the stand-alone kernels (xo_model.cu) and the single-launch model
+// kernel (xo_transit.cu).
+//   prologue: (period, t0, e, omega, b, r/R*, m_pl, K; R*, M*) -> element block, = KeplerianOrbit.__init__
+//             (/root/reference/src/exoplanet/orbits/keplerian.py:133-281) + in_transit window (:729-767)
+//   epilogue: fold of the per-warp partial sums + reverse pass of the prologue and of get_cl
+//             (/root/reference/src/exoplanet/light_curves/limb_dark.py:11-18)
+#pragma once
+#include <cuda_runtime.h>
+
+#include "xo_common.cuh"
+#include "xo_contact.cuh"
+#include "xo_math.cuh"
+#include "xo_transit.cuh"
+
+namespace xo {
+
+constexpr double kGGrav = 2942.2062175044193;  // R_sun^3 / M_sun / day^2 (orbits/constants.py:32)
+
+// Two adjacent lanes per planet (side = lane parity = contact side): the two bracketed Newton
+// solves of the in-transit window run concurrently.  EVERY lane of the warp must call this
+// (it shuffles); inactive lanes pass active = false.  The even lane of an active pair writes el[16].
+__device__ inline void prologue_pair(const double *q, const double *st, double texp, int use_in_transit, int side,
+                                     bool active, double *el) {
+  const double period = q[0], t0 = q[1], e = q[2], omega = q[3], b = q[4], ror = q[5], mpl = q[6], K = q[7];
+  const double R = st[0], Ms = st[1];
+  const double a = cbrt(kGGrav * (Ms + mpl) * period * period / (4.0 * kPi * kPi));
+  const double n = 2.0 * kPi / period;
+  double sw, cw;
+  sincos(omega, &sw, &cw);
+  const double y = sqrt(1.0 - e) * cw, x = sqrt(1.0 + e) * (1.0 + sw);
+  const double E0 = 2.0 * atan2(y, x);
+  const double M0 = E0 - e * sin(E0);
+  const double ome2 = (1.0 - e) * (1.0 + e);
+  const double F = (1.0 + e * sw) / ome2;
+  const double cosi = F * R / a * b;
+  const double sini = sqrt((1.0 - cosi) * (1.0 + cosi));
+  double tc = side ? INFINITY : -INFINITY;  // this lane's contact time relative to t0
+  int flag = 0;
+  if (use_in_transit) {
+    double Mc;
+    flag = cp_solve_side(a, e, cw, sw, cosi, R * (1.0 + ror), side ? 1.0 : -1.0, Mc);
+    if (flag == 0) {
+      const double hp = 0.5 * period;
+      tc = (Mc - M0) / n + hp;
+      tc = tc - period * floor(tc / period) - hp;
+      if (side == 0) {
+        if (tc > 0.0) tc -= period;
+        tc -= 0.5 * texp;
+      } else {
+        if (tc < 0.0) tc += period;
+        tc += 0.5 * texp;
+      }
+    }
+  }
+  const double tc_other = __shfl_xor_sync(0xffffffffu, tc, 1);
+  const int flag_other = __shfl_xor_sync(0xffffffffu, flag, 1);
+  if (!active || side != 0) return;
+  double ts = tc, te = tc_other;
+  if (flag | flag_other) {
+    ts = -INFINITY;
+    te = INFINITY;
+  }
+  el[XO_EL_T0] = t0;
+  el[XO_EL_TREF] = -M0 / n;
+  el[XO_EL_N] = n;
+  el[XO_EL_ECC] = e;
+  el[XO_EL_COSW] = cw;
+  el[XO_EL_SINW] = sw;
+  el[XO_EL_COSI] = cosi;
+  el[XO_EL_SINI] = sini;
+  el[XO_EL_AOR] = a / R;
+  el[XO_EL_ROR] = ror;
+  el[XO_EL_PERIOD] = period;
+  el[XO_EL_TSTART] = ts;
+  el[XO_EL_TEND] = te;
+  el[XO_EL_KRV] = K;
+  el[14] = 0.0;
+  el[15] = 0.0;
+}
+
+__device__ inline void limb_coeffs(double u1, double u2, double *cl3) {
+  const double c0 = 1.0 - u1 - 1.5 * u2, c1 = u1 + 2.0 * u2, c2 = -0.25 * u2;
+  const double rn = 1.0 / (kPi * (c0 + c1 / 1.5));
+  cl3[0] = c0 * rn;
+  cl3[1] = c1 * rn;
+  cl3[2] = c2 * rn;
+}
+
+// Warp-collective epilogue of ONE chain: lane l sums slots l, l+32, ... of every accumulator
+// (ascending), a fixed-order butterfly combines the 32 lane sums (deterministic), lane p < P runs
+// the reverse pass of planet p's prologue, lane 0 the reverse of get_cl.  kCoherent: read the
+// partials through L2 (they were written by other CTAs of the same launch).
+template <bool kCoherent>
+__device__ inline void epilogue_chain(const double *par_c, const double *st, const double *src, int slots, int P,
+                                      double lognorm, double *logp, double *gpar_c, double *gstar_c, double *gmean) {
+  constexpr unsigned kFullM = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int nacc = kNBase + P * XO_NGRAD;
+  double g[XO_NGRAD];
+#pragma unroll
+  for (int j = 0; j < XO_NGRAD; ++j) g[j] = 0.0;
+  double base = 0.0;
+  for (int j = 0; j < nacc; ++j) {
+    double acc = 0.0;
+    for (int s = lane; s < slots; s += 32) {
+      const double *ptr = src + (int64_t)s * nacc + j;
+      acc += kCoherent ? __ldcg(ptr) : *ptr;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFullM, acc, o);
+    if (j < kNBase) {
+      if (lane == 8 + j) base = acc;
+    } else {
+      const int pj = (j - kNBase) / XO_NGRAD, k = (j - kNBase) % XO_NGRAD;
+      if (lane == pj) {
+#pragma unroll
+        for (int kk = 0; kk < XO_NGRAD; ++kk)
+          if (kk == k) g[kk] = acc;
+      }
+    }
+  }
+  const double R = st[0], Ms = st[1];
+  double gR = 0.0, gMs = 0.0;
+  if (lane < P) {
+    const double *q = par_c + lane * XO_NPAR;
+    const double period = q[0], e = q[2], omega = q[3], b = q[4], mpl = q[6];
+    const double mt = Ms + mpl;
+    const double a = cbrt(kGGrav * mt * period * period / (4.0 * kPi * kPi));
+    const double n = 2.0 * kPi / period;
+    double sw, cw;
+    sincos(omega, &sw, &cw);
+    const double sme = sqrt(1.0 - e), spe = sqrt(1.0 + e);
+    const double y = sme * cw, x = spe * (1.0 + sw);
+    const double E0 = 2.0 * atan2(y, x);
+    double sE0, cE0;
+    sincos(E0, &sE0, &cE0);
+    const double M0 = E0 - e * sE0;
+    const double ome2 = (1.0 - e) * (1.0 + e);
+    const double F = (1.0 + e * sw) / ome2;
+    const double cosi = F * R / a * b;
+    const double sini = sqrt((1.0 - cosi) * (1.0 + cosi));
+    // cotangents of the element block: g = (t0, tref, n, e, cw, sw, cosi, sini, aor, ror)
+    double gt0 = g[0], ge = g[3], gcw = g[4], gsw = g[5];
+    double ga = g[8] / R;
+    gR += -g[8] * a / (R * R);
+    double gcosi = g[6] + (sini > 0.0 ? -g[7] * cosi / sini : 0.0);
+    double gF = gcosi * R * b / a;
+    gR += gcosi * F * b / a;
+    ga += -gcosi * F * R * b / (a * a);
+    double gb = gcosi * F * R / a;
+    ge += gF * (sw / ome2 + (1.0 + e * sw) * 2.0 * e / (ome2 * ome2));
+    gsw += gF * e / ome2;
+    double gM0 = -g[1] / n;
+    double gn = g[2] + g[1] * M0 / (n * n);
+    double gP = -gn * n / period;
+    double gE0 = gM0 * (1.0 - e * cE0);
+    ge += -gM0 * sE0;
+    const double rr = 1.0 / (x * x + y * y);
+    double gy = 2.0 * gE0 * x * rr, gx = -2.0 * gE0 * y * rr;
+    gcw += gy * sme;
+    ge += -gy * cw / (2.0 * sme);
+    gsw += gx * spe;
+    ge += gx * (1.0 + sw) / (2.0 * spe);
+    double gomega = -gcw * sw + gsw * cw;
+    gP += ga * (2.0 / 3.0) * a / period;
+    double gmt = ga * a / (3.0 * mt);
+    gMs += gmt;
+    double *o = gpar_c + lane * XO_NPAR;
+    o[0] = gP;
+    o[1] = gt0;
+    o[2] = ge;
+    o[3] = gomega;
+    o[4] = gb;
+    o[5] = g[9];
+    o[6] = gmt;
+    o[7] = 0.0;  // K does not enter the transit likelihood
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {  // planets live in lanes 0..7
+    gR += __shfl_xor_sync(kFullM, gR, o);
+    gMs += __shfl_xor_sync(kFullM, gMs, o);
+  }
+  const double lp = __shfl_sync(kFullM, base, 8), gm = __shfl_sync(kFullM, base, 9);
+  const double q0 = __shfl_sync(kFullM, base, 10), q1 = __shfl_sync(kFullM, base, 11), q2 = __shfl_sync(kFullM, base, 12);
+  if (lane == 0) {
+    *logp = lp + lognorm;
+    *gmean = gm;
+    // reverse of get_cl
+    const double u1 = st[2], u2 = st[3];
+    const double c0 = 1.0 - u1 - 1.5 * u2, c1 = u1 + 2.0 * u2, c2 = -0.25 * u2;
+    const double norm = kPi * (c0 + c1 / 1.5), rn = 1.0 / norm;
+    double gnorm = -(q0 * c0 + q1 * c1 + q2 * c2) * rn * rn;
+    double gc0 = q0 * rn + gnorm * kPi, gc1 = q1 * rn + gnorm * kPi / 1.5, gc2 = q2 * rn;
+    gstar_c[0] = gR;
+    gstar_c[1] = gMs;
+    gstar_c[2] = -gc0 + gc1;
+    gstar_c[3] = -1.5 * gc0 + 2.0 * gc1 - 0.25 * gc2;
+  }
+}
+
+}  // namespace xo

@@ -28,6 +28,7 @@
 
 #include "xo_common.cuh"
 #include "xo_math.cuh"
+#include "xo_prologue.cuh"
 #include "xo_transit.cuh"
 
 namespace {
@@ -48,6 +49,16 @@ struct ChainSmem {
   double wk[XO_MAX_STENCIL];
 };
 
+__device__ __forceinline__ void stage_derived(ChainSmem &sm, int P) {
+  if (threadIdx.x < P) {
+    const double rp = 1.0 / sm.elem[threadIdx.x][XO_EL_PERIOD];
+    sm.rperiod[threadIdx.x] = rp;
+    sm.wlo[threadIdx.x] = sm.elem[threadIdx.x][XO_EL_TSTART] * rp;
+    sm.whi[threadIdx.x] = sm.elem[threadIdx.x][XO_EL_TEND] * rp;
+  }
+  __syncthreads();
+}
+
 __device__ __forceinline__ void stage_chain(ChainSmem &sm, const double *elem, const double *cl, const double *mean,
                                             const double *dtk, const double *wk, int64_t c, int P, int K) {
   for (int i = threadIdx.x; i < P * XO_NEL; i += blockDim.x) sm.elem[i / XO_NEL][i % XO_NEL] = elem[c * P * XO_NEL + i];
@@ -58,13 +69,29 @@ __device__ __forceinline__ void stage_chain(ChainSmem &sm, const double *elem, c
   if (threadIdx.x < 3) sm.cl[threadIdx.x] = cl[3 * c + threadIdx.x];
   if (threadIdx.x == 3) sm.mean = mean ? mean[c] : 0.0;
   __syncthreads();
-  if (threadIdx.x < P) {
-    const double rp = 1.0 / sm.elem[threadIdx.x][XO_EL_PERIOD];
-    sm.rperiod[threadIdx.x] = rp;
-    sm.wlo[threadIdx.x] = sm.elem[threadIdx.x][XO_EL_TSTART] * rp;
-    sm.whi[threadIdx.x] = sm.elem[threadIdx.x][XO_EL_TEND] * rp;
+  stage_derived(sm, P);
+}
+
+// single-launch model mode: the CTA derives its chain's element block from the sampler-side
+// parameters itself (warp 0, two lanes per planet) instead of reading one a prologue kernel wrote
+__device__ __forceinline__ void stage_chain_from_params(ChainSmem &sm, const xo::ModelArgs &ma, const double *mean,
+                                                        const double *dtk, const double *wk, int64_t c, int P, int K) {
+  if (threadIdx.x < 32) {
+    const int p = threadIdx.x >> 1;
+    const bool active = p < P;
+    const int pp = active ? p : 0;
+    xo::prologue_pair(ma.par + (c * P + pp) * XO_NPAR, ma.star + c * XO_NSTAR, ma.texp, ma.use_in_transit, threadIdx.x & 1, active,
+                      sm.elem[pp]);
+    if (threadIdx.x == 0) xo::limb_coeffs(ma.star[c * XO_NSTAR + 2], ma.star[c * XO_NSTAR + 3], sm.cl);
+  } else {
+    for (int i = threadIdx.x - 32; i < K; i += blockDim.x - 32) {
+      sm.dtk[i] = dtk[i];
+      sm.wk[i] = wk[i];
+    }
+    if (threadIdx.x == 32) sm.mean = mean[c];
   }
   __syncthreads();
+  stage_derived(sm, P);
 }
 
 // window test of the sweep: phase = frac((t - t0)/P) in [-1/2, 1/2] against [tstart, tend]/P.
@@ -119,12 +146,14 @@ constexpr int kQueue = 32 * (kUnroll + 1);      // 31 left over + kUnroll * 32 n
 // kMoments   : the out-of-transit part of the Gaussian sums comes from data-only moments
 //              (moments[4] = y_ref, S1 = sum ivar, Sy = sum ivar (y - y_ref), Syy = sum ivar (y - y_ref)^2,
 //              computed once per data set by transit_moments_kernel); the sweep then reads t only.
-template <int kMinBlocks, bool kVjp, bool kMoments>
+// kModel     : single-launch model evaluation: elements from parameters at CTA start (ma.par/star),
+//              and the last CTA of each chain folds the partials and runs the reverse prologue.
+template <int kMinBlocks, bool kVjp, bool kMoments, bool kModel>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel(
     const double *__restrict__ t, const double *__restrict__ y, const double *__restrict__ ivar, int64_t N,
     const double *__restrict__ elem, const double *__restrict__ cl, const double *__restrict__ mean, int P,
     const double *__restrict__ dtk, const double *__restrict__ wk, int K, int64_t L, int slots,
-    const double *__restrict__ moments, double *__restrict__ partial) {
+    const double *__restrict__ moments, double *__restrict__ partial, const xo::ModelArgs ma) {
   constexpr bool kBase = !kVjp && !kMoments;  // accumulate the per-cadence Gaussian terms in the sweep
   __shared__ ChainSmem sm;
   __shared__ uint32_t queue[kWarps][XO_MAX_PLANETS][kQueue];
@@ -133,7 +162,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
   const int64_t c = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = blockIdx.x * kWarps + warp;
-  stage_chain(sm, elem, cl, mean, dtk, wk, c, P, K);
+  if (kModel)
+    stage_chain_from_params(sm, ma, mean, dtk, wk, c, P, K);
+  else
+    stage_chain(sm, elem, cl, mean, dtk, wk, c, P, K);
   for (int i = lane; i < XO_MAX_PLANETS * XO_NGRAD; i += 32) (&gacc[warp][0][0])[i] = 0.0;
 #pragma unroll
   for (int j = 0; j < XO_NGRAD + 3; ++j) lacc[j][threadIdx.x] = 0.0;
@@ -313,6 +345,20 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
     out[4] = gc2;
   }
   for (int i = lane; i < P * XO_NGRAD; i += 32) out[kNBase + i] = gacc[warp][i / XO_NGRAD][i % XO_NGRAD];
+  if (kModel) {
+    // last CTA of the chain to finish folds all slots and runs the reverse pass of the prologue
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ma.counter + c, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (is_last && warp == 0) {
+      __threadfence();
+      xo::epilogue_chain<true>(ma.par + c * P * XO_NPAR, ma.star + c * XO_NSTAR, partial + (int64_t)c * slots * nacc, slots, P,
+                               ma.lognorm, ma.logp + c, ma.gpar + c * P * XO_NPAR, ma.gstar + c * XO_NSTAR, ma.gmean + c);
+      if (lane == 0) ma.counter[c] = 0u;  // leave the counters zeroed for the next launch
+    }
+  }
 }
 
 // data-only moments of the Gaussian likelihood, one CTA, fixed-order tree (deterministic):
@@ -576,25 +622,31 @@ int check_batch(int64_t N, int64_t C, int64_t P) {
 void launch_transit_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *elem,
                               const double *cl, const double *mean, int64_t C, int P, const double *dtk,
                               const double *wk, int K, Split sp, const double *moments, double *partial,
-                              cudaStream_t st) {
+                              cudaStream_t st, const ModelArgs *model) {
   dim3 grid(sp.slots / kWarps, (unsigned)C);
-#define XO_LAUNCH(MB, VJP, MOM)                                                                                      \
-  transit_logp_grad_kernel<MB, VJP, MOM><<<grid, kThreads, 0, st>>>(t, y, ivar, N, elem, cl, mean, P, dtk, wk, K, sp.L, \
-                                                                    sp.slots, moments, partial)
+  const ModelArgs ma = model ? *model : ModelArgs{};
+#define XO_LAUNCH(MB, VJP, MOM, MODEL)                                                                                  \
+  transit_logp_grad_kernel<MB, VJP, MOM, MODEL><<<grid, kThreads, 0, st>>>(t, y, ivar, N, elem, cl, mean, P, dtk, wk, K, \
+                                                                           sp.L, sp.slots, moments, partial, ma)
   if (ivar == nullptr) {  // light-curve VJP mode: y = bar_lc[C][N][P]
-    XO_LAUNCH(3, true, false);
+    XO_LAUNCH(3, true, false, false);
     return;
   }
   const int mb = transit_min_blocks();
+  if (model) {
+    if (moments) XO_LAUNCH(3, false, true, true);
+    else XO_LAUNCH(3, false, false, true);
+    return;
+  }
   if (moments) {
-    if (mb == 2) XO_LAUNCH(2, false, true);
-    else if (mb == 4) XO_LAUNCH(4, false, true);
-    else if (mb == 5) XO_LAUNCH(5, false, true);
-    else XO_LAUNCH(3, false, true);
+    if (mb == 2) XO_LAUNCH(2, false, true, false);
+    else if (mb == 4) XO_LAUNCH(4, false, true, false);
+    else if (mb == 5) XO_LAUNCH(5, false, true, false);
+    else XO_LAUNCH(3, false, true, false);
   } else {
-    if (mb == 2) XO_LAUNCH(2, false, false);
-    else if (mb == 4) XO_LAUNCH(4, false, false);
-    else XO_LAUNCH(3, false, false);
+    if (mb == 2) XO_LAUNCH(2, false, false, false);
+    else if (mb == 4) XO_LAUNCH(4, false, false, false);
+    else XO_LAUNCH(3, false, false, false);
   }
 #undef XO_LAUNCH
 }
@@ -649,7 +701,7 @@ int xo_transit_logp_grad(const double *t, const double *y, const double *ivar, i
   Split sp = split_transit(N, C);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   double *partial = static_cast<double *>(workspace);
-  xo::launch_transit_logp_grad(t, y, ivar, N, elem, cl, mean, C, (int)P, dtk, wk, K, sp, moments, partial, st);
+  xo::launch_transit_logp_grad(t, y, ivar, N, elem, cl, mean, C, (int)P, dtk, wk, K, sp, moments, partial, st, nullptr);
   const int nacc = kNBase + (int)P * XO_NGRAD;
   const int64_t tot = C * nacc;
   fold_partials_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(partial, sp.slots, nacc, C, (int)P, lognorm, logp,
@@ -670,7 +722,7 @@ int xo_transit_lc_vjp(const double *t, int64_t N, const double *elem, const doub
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   double *partial = static_cast<double *>(workspace);
   double *scratch = partial + (size_t)C * sp.slots * (kNBase + P * XO_NGRAD);  // logp / gmean of the fold (unused)
-  xo::launch_transit_logp_grad(t, bar_lc, nullptr, N, elem, cl, nullptr, C, (int)P, dtk, wk, K, sp, nullptr, partial, st);
+  xo::launch_transit_logp_grad(t, bar_lc, nullptr, N, elem, cl, nullptr, C, (int)P, dtk, wk, K, sp, nullptr, partial, st, nullptr);
   const int nacc = kNBase + (int)P * XO_NGRAD;
   const int64_t tot = C * nacc;
   fold_partials_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(partial, sp.slots, nacc, C, (int)P, 0.0, scratch, gel,

@@ -18,9 +18,22 @@ Split split_transit(int64_t N, int64_t C);
 int check_batch(int64_t N, int64_t C, int64_t P);
 int transit_min_blocks();
 
-// enqueue transit_logp_grad_kernel; partial[C][slots][kNBase + P*XO_NGRAD]
+// single-launch model mode of the logp kernel (parameters in, parameter gradients out)
+struct ModelArgs {
+  const double *par = nullptr;   // [C][P][XO_NPAR]
+  const double *star = nullptr;  // [C][XO_NSTAR]
+  double texp = 0.0;
+  int use_in_transit = 1;
+  double lognorm = 0.0;
+  unsigned *counter = nullptr;  // [C], zero on entry; left zero on exit
+  double *logp = nullptr, *gpar = nullptr, *gstar = nullptr, *gmean = nullptr;
+};
+
+// enqueue transit_logp_grad_kernel; partial[C][slots][kNBase + P*XO_NGRAD]; model != nullptr
+// selects the single-launch model mode (elem / cl are then ignored)
 void launch_transit_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *elem,
                               const double *cl, const double *mean, int64_t C, int P, const double *dtk,
-                              const double *wk, int K, Split sp, const double *moments, double *partial, cudaStream_t st);
+                              const double *wk, int K, Split sp, const double *moments, double *partial, cudaStream_t st,
+                              const ModelArgs *model);
 
 }  // namespace xo
