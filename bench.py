@@ -458,13 +458,13 @@ def arm_ours(args):
                    "chains_per_gpu": C_loc, "chains_total": C_loc * world, "cadences": N_CADENCES, "use_in_transit": True,
                    "out_of_transit_sums": "full sweep over y, ivar" if args.full_sweep else "data moments (t-only sweep)",
                    "parallelism": "chain-sharded, no collective", "l2": "flushed between timed steps (192 MiB memset)",
-                   "step": "params -> elements+contact points -> fused logp+grad -> reverse prologue, ONE kernel launch (3 with XO_MODEL_SINGLE_LAUNCH=0), params resident in HBM"},
+                   "step": "params -> elements+contact points -> fused logp+grad -> reverse prologue, 3 kernel launches (XO_MODEL_LAUNCHES=1|2 fuse them; slower), params resident in HBM"},
         "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "xo_transit_model_logp_grad_host: t,y,ivar,params from pinned host memory every call; logp+grads back to host"},
         "e2e_resident_data": {"value": total_evals / (res_ms * 1e-3), "unit": "evals/s",
                               "h2d_bytes_per_step": sum(h[k].numel() * 8 for k in ("par", "star", "mean", "dtk", "wk")), "d2h_bytes_per_step": d2h,
                               "api": "xo_transit_model_logp_grad_resident: light curve uploaded once (xo_transit_data_create); params in, logp+grads out per call"},
-        "gpu_launches": (1 if os.environ.get("XO_MODEL_SINGLE_LAUNCH", "1") != "0" else 3) * args.steps,
+        "gpu_launches": int(os.environ.get("XO_MODEL_LAUNCHES", "3")) * args.steps,
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                      "kernel": "transit_logp_grad_kernel", "peak_source": peak_src,
                      "note": "algorithmic 24 B per (chain,cadence); chains share t,y,sigma through L2, and the kernel is fp64-pipe bound"},

@@ -88,12 +88,15 @@ int xo_transit_model_logp_grad(const double *t, const double *y, const double *i
   double *cl = reinterpret_cast<double *>(ws + L.off_cl);
   double *partial = reinterpret_cast<double *>(ws + L.off_partial);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static const int fused = [] {
-    const char *v = getenv("XO_MODEL_SINGLE_LAUNCH");
-    return v && *v ? atoi(v) : 1;
+  // XO_MODEL_LAUNCHES: 3 = prologue kernel, logp kernel, epilogue kernel (default: measured fastest);
+  //                    2 = prologue kernel + logp kernel whose last CTA per chain runs the epilogue;
+  //                    1 = one kernel (every CTA re-derives its chain's elements at start)
+  static const int launches = [] {
+    const char *v = getenv("XO_MODEL_LAUNCHES");
+    return v && *v ? atoi(v) : 3;
   }();
-  if (fused) {
-    // one kernel: prologue at CTA start, reverse pass by the last CTA of each chain
+  const int64_t cp = C * P;
+  if (launches == 1 || launches == 2) {
     unsigned *counter = reinterpret_cast<unsigned *>(ws + L.off_counter);
     cudaError_t e = cudaMemsetAsync(counter, 0, (size_t)C * sizeof(unsigned), st);
     if (e != cudaSuccess) return -(int)e;
@@ -102,16 +105,18 @@ int xo_transit_model_logp_grad(const double *t, const double *y, const double *i
     ma.star = star;
     ma.texp = texp;
     ma.use_in_transit = use_in_transit;
+    ma.stage_from_params = launches == 1;
     ma.lognorm = lognorm;
     ma.counter = counter;
     ma.logp = logp;
     ma.gpar = gpar;
     ma.gstar = gstar;
     ma.gmean = gmean;
-    xo::launch_transit_logp_grad(t, y, ivar, N, nullptr, nullptr, mean, C, (int)P, dtk, wk, K, L.sp, moments, partial, st, &ma);
+    if (launches == 2)
+      model_prologue_kernel<<<(unsigned)((2 * cp + 63) / 64), 64, 0, st>>>(par, star, C, (int)P, texp, use_in_transit, elem, cl);
+    xo::launch_transit_logp_grad(t, y, ivar, N, elem, cl, mean, C, (int)P, dtk, wk, K, L.sp, moments, partial, st, &ma);
     return xo::launch_status();
   }
-  const int64_t cp = C * P;
   model_prologue_kernel<<<(unsigned)((2 * cp + 63) / 64), 64, 0, st>>>(par, star, C, (int)P, texp, use_in_transit, elem, cl);
   xo::launch_transit_logp_grad(t, y, ivar, N, elem, cl, mean, C, (int)P, dtk, wk, K, L.sp, moments, partial, st, nullptr);
   model_epilogue_kernel<<<(unsigned)((C + 3) / 4), 128, 0, st>>>(par, star, partial, L.sp.slots, C, (int)P, lognorm, logp,

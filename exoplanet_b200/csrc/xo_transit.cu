@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
   const int64_t c = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = blockIdx.x * kWarps + warp;
-  if (kModel)
+  if (kModel && ma.stage_from_params)
     stage_chain_from_params(sm, ma, mean, dtk, wk, c, P, K);
   else
     stage_chain(sm, elem, cl, mean, dtk, wk, c, P, K);

@@ -24,6 +24,7 @@ struct ModelArgs {
   const double *star = nullptr;  // [C][XO_NSTAR]
   double texp = 0.0;
   int use_in_transit = 1;
+  int stage_from_params = 1;  // 0: element blocks were written by model_prologue_kernel (elem, cl valid)
   double lognorm = 0.0;
   unsigned *counter = nullptr;  // [C], zero on entry; left zero on exit
   double *logp = nullptr, *gpar = nullptr, *gstar = nullptr, *gmean = nullptr;

@@ -8,11 +8,11 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_gpu.txt 2>&1
 lscpu | grep -E "Model name|^CPU\(s\)|Thread|Core|Socket" >> $OUT/${TAG}_gpu.txt; nproc >> $OUT/${TAG}_gpu.txt
 timeout 1500 python -m pytest tests -m gpu -q > $OUT/${TAG}_pytest.log 2>&1; echo "pytest exit $?" >> $OUT/${TAG}_pytest.log
-XO_MODEL_SINGLE_LAUNCH=0 timeout 600 python -m pytest tests/test_gpu_fused.py -m gpu -q > $OUT/${TAG}_pytest_3launch.log 2>&1; echo "pytest(3-launch model) exit $?" >> $OUT/${TAG}_pytest.log
+for ML in 1 2; do XO_MODEL_LAUNCHES=$ML timeout 600 python -m pytest tests/test_gpu_fused.py -m gpu -q > $OUT/${TAG}_pytest_launches$ML.log 2>&1; echo "pytest(XO_MODEL_LAUNCHES=$ML) exit $?" >> $OUT/${TAG}_pytest.log; done
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke exit $?" >> $OUT/${TAG}_smoke.log
 timeout 900 python bench.py --steps 20 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench exit $?" >> $OUT/${TAG}_bench.err
 timeout 300 python bench.py --impl reference --steps 20 --warmup 2 > $OUT/${TAG}_bench_ref.json 2>> $OUT/${TAG}_bench.err
-echo -n "3-launch model: " > $OUT/${TAG}_sweep.txt; XO_MODEL_SINGLE_LAUNCH=0 timeout 120 python bench.py --steps 20 --warmup 3 --no-cpu --no-kepler --no-extra 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e_resident_data']['value'])" >> $OUT/${TAG}_sweep.txt
+: > $OUT/${TAG}_sweep.txt; for ML in 1 2 3; do echo -n "XO_MODEL_LAUNCHES=$ML: " >> $OUT/${TAG}_sweep.txt; XO_MODEL_LAUNCHES=$ML timeout 120 python bench.py --steps 20 --warmup 3 --no-cpu --no-kepler --no-extra 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e_resident_data']['value'])" >> $OUT/${TAG}_sweep.txt; done
 if [ "$MODE" = "full" ]; then
 # tuning sweep of the logp kernel (register cap x launch width)
 for SWEEPFLAG in "" "--full-sweep"; do for mb in 2 3 4 5; do for w in 16 24 32; do
