@@ -283,7 +283,8 @@ __global__ void __launch_bounds__(kThreadsGp) gp_loglike_kernel(const double *__
                                                                 const double *__restrict__ Qf, double eps, int64_t T,
                                                                 const double *__restrict__ pref,
                                                                 const double *__restrict__ cta_state,
-                                                                double *__restrict__ cta_ll) {
+                                                                double *__restrict__ cta_ll,
+                                                                double *__restrict__ rec /* [B][3][N] or null */) {
   __shared__ double red[kWarpsGp];
   const int64_t bch = blockIdx.y;
   const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
@@ -318,6 +319,12 @@ __global__ void __launch_bounds__(kThreadsGp) gp_loglike_kernel(const double *__
       const double K0 = pm * rD, K1 = -p01 * rD;
       const double v = __ldg(yb + i) - c0;
       acc += fma(v * v, rD, log(D));
+      if (rec) {  // what the backward (disturbance-smoother) pass needs
+        double *rb = rec + bch * 3 * N;
+        rb[i] = v * rD;
+        rb[N + i] = K0;
+        rb[2 * N + i] = K1;
+      }
       m0 = fma(K0, v, c0);
       m1 = fma(K1, v, c1);
       Z00 = fma(D * K0, K0, p00);
@@ -336,6 +343,173 @@ __global__ void __launch_bounds__(kThreadsGp) gp_loglike_kernel(const double *__
   }
 }
 
+// ---------------------------------------------------------------------------
+// alpha = K^-1 y by the disturbance smoother (Durbin & Koopman 2012, sec. 4.5), run as an
+// affine scan in reverse time: with w_k = v_k / D_k, K_k the Kalman gain and Phi_{k+1} the next
+// transition,   R_{k-1} = (I - K_k h)^T Phi_{k+1}^T R_k + h^T w_k,  R_{N-1} = 0,
+//               alpha_k = w_k - (Phi_{k+1} K_k) . R_k.
+// Same three phases as the forward pass, thread g owning run T-1-g so the scan runs right-to-left;
+// the scan element is an affine map (A 2x2, b 2), combine = composition.
+// ---------------------------------------------------------------------------
+struct Aff {
+  double a00, a01, a10, a11, b0, b1;
+};
+__device__ __forceinline__ Aff aff_identity() { return Aff{1, 0, 0, 1, 0, 0}; }
+// cur after prev:  x -> A_cur (A_prev x + b_prev) + b_cur
+__device__ __forceinline__ Aff aff_after(const Aff &prev, const Aff &cur) {
+  Aff o;
+  o.a00 = cur.a00 * prev.a00 + cur.a01 * prev.a10;
+  o.a01 = cur.a00 * prev.a01 + cur.a01 * prev.a11;
+  o.a10 = cur.a10 * prev.a00 + cur.a11 * prev.a10;
+  o.a11 = cur.a10 * prev.a01 + cur.a11 * prev.a11;
+  o.b0 = cur.a00 * prev.b0 + cur.a01 * prev.b1 + cur.b0;
+  o.b1 = cur.a10 * prev.b0 + cur.a11 * prev.b1 + cur.b1;
+  return o;
+}
+__device__ __forceinline__ Aff aff_shfl_up(const Aff &a, int d) {
+  Aff o;
+  const double *src = &a.a00;
+  double *dst = &o.a00;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) dst[k] = __shfl_up_sync(kFullGp, src[k], d);
+  return o;
+}
+__device__ Aff aff_cta_inclusive_scan(Aff v, Aff *warp_tot) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    Aff o = aff_shfl_up(v, d);
+    if (lane >= d) v = aff_after(o, v);
+  }
+  if (lane == 31) warp_tot[warp] = v;
+  __syncthreads();
+  if (warp > 0) {
+    Aff pre = warp_tot[0];
+    for (int w = 1; w < warp; ++w) pre = aff_after(pre, warp_tot[w]);
+    v = aff_after(pre, v);
+  }
+  return v;
+}
+
+// one backward step k of run walking: given R (= R_k) returns alpha_k and updates R to R_{k-1}
+__device__ __forceinline__ double gp_bwd_step(const Sho &k, const double *__restrict__ t, const double *__restrict__ rb,
+                                              int64_t N, int64_t i, double &R0, double &R1) {
+  const double w = __ldg(rb + i), K0 = __ldg(rb + N + i), K1 = __ldg(rb + 2 * N + i);
+  double f00 = 1.0, f01 = 0.0, f10 = 0.0, f11 = 1.0;
+  if (i + 1 < N) sho_phi(k, __ldg(t + i + 1) - __ldg(t + i), f00, f01, f10, f11);
+  // q = Phi_{k+1}^T R
+  const double q0 = f00 * R0 + f10 * R1, q1 = f01 * R0 + f11 * R1;
+  const double kq = K0 * q0 + K1 * q1;  // (Phi K) . R = K . (Phi^T R)
+  const double alpha = w - kq;
+  R0 = q0 - kq + w;  // (I - K h)^T q + h^T w,  h = (1, 0)
+  R1 = q1;
+  return alpha;
+}
+
+__global__ void __launch_bounds__(kThreadsGp) gp_bwd_aggregate_kernel(const double *__restrict__ t, int64_t N,
+                                                                      const double *__restrict__ S0,
+                                                                      const double *__restrict__ w0,
+                                                                      const double *__restrict__ Qf, double eps,
+                                                                      int64_t T, const double *__restrict__ rec,
+                                                                      double *__restrict__ bpref,
+                                                                      double *__restrict__ bcta) {
+  __shared__ Aff warp_tot[kWarpsGp];
+  const int64_t bch = blockIdx.y;
+  const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
+  const int64_t g = (int64_t)blockIdx.x * kThreadsGp + threadIdx.x;
+  const int64_t run = T - 1 - g;  // reversed ownership
+  Aff v = aff_identity();
+  if (run >= 0) {
+    const int64_t s = run * kRun, e = min(s + kRun, N);
+    const double *rb = rec + bch * 3 * N;
+    // the run's map R_{e-1} -> R_{s-1}: push the two basis vectors and the origin through it
+    double o0 = 0.0, o1 = 0.0, x0 = 1.0, x1 = 0.0, y0 = 0.0, y1 = 1.0;
+    for (int64_t i = e - 1; i >= s; --i) {
+      const double K0 = __ldg(rb + N + i), K1 = __ldg(rb + 2 * N + i), w = __ldg(rb + i);
+      double f00 = 1.0, f01 = 0.0, f10 = 0.0, f11 = 1.0;
+      if (i + 1 < N) sho_phi(k, __ldg(t + i + 1) - __ldg(t + i), f00, f01, f10, f11);
+      auto lin = [&](double &r0, double &r1, double add) {
+        const double q0 = f00 * r0 + f10 * r1, q1 = f01 * r0 + f11 * r1;
+        r0 = q0 - (K0 * q0 + K1 * q1) + add;
+        r1 = q1;
+      };
+      lin(o0, o1, w);
+      lin(x0, x1, w);
+      lin(y0, y1, w);
+    }
+    v = Aff{x0 - o0, y0 - o0, x1 - o1, y1 - o1, o0, o1};
+  }
+  v = aff_cta_inclusive_scan(v, warp_tot);
+  if (g < T) {
+    double *o = bpref + (bch * T + g) * 6;
+    o[0] = v.a00; o[1] = v.a01; o[2] = v.a10; o[3] = v.a11; o[4] = v.b0; o[5] = v.b1;
+  }
+  if (threadIdx.x == kThreadsGp - 1) {
+    double *o = bcta + (bch * gridDim.x + blockIdx.x) * 6;
+    o[0] = v.a00; o[1] = v.a01; o[2] = v.a10; o[3] = v.a11; o[4] = v.b0; o[5] = v.b1;
+  }
+}
+
+// R entering each CTA (from the right): exclusive scan of the CTA totals applied to R = 0
+__global__ void __launch_bounds__(kThreadsGp) gp_bwd_cta_scan_kernel(const double *__restrict__ bcta, int nctas,
+                                                                     double *__restrict__ bstate) {
+  __shared__ Aff warp_tot[kWarpsGp];
+  __shared__ Aff lastlane[kWarpsGp];
+  __shared__ Aff carry_s;
+  const int64_t bch = blockIdx.x;
+  Aff carry = aff_identity();
+  for (int base = 0; base < nctas; base += kThreadsGp) {
+    const int idx = base + threadIdx.x;
+    Aff v = aff_identity();
+    if (idx < nctas) {
+      const double *p = bcta + (bch * nctas + idx) * 6;
+      v = Aff{p[0], p[1], p[2], p[3], p[4], p[5]};
+    }
+    v = aff_cta_inclusive_scan(v, warp_tot);
+    Aff incl = aff_after(carry, v);
+    Aff prev = aff_shfl_up(incl, 1);
+    if ((threadIdx.x & 31) == 31) lastlane[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    Aff excl = ((threadIdx.x & 31) == 0) ? (threadIdx.x == 0 ? carry : lastlane[(threadIdx.x >> 5) - 1]) : prev;
+    if (idx < nctas) {
+      double *o = bstate + (bch * nctas + idx) * 2;
+      o[0] = excl.b0;  // the map applied to R = 0
+      o[1] = excl.b1;
+    }
+    if (threadIdx.x == kThreadsGp - 1) carry_s = incl;
+    __syncthreads();
+    carry = carry_s;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kThreadsGp) gp_bwd_solve_kernel(const double *__restrict__ t, int64_t N,
+                                                                  const double *__restrict__ S0,
+                                                                  const double *__restrict__ w0,
+                                                                  const double *__restrict__ Qf, double eps, int64_t T,
+                                                                  const double *__restrict__ rec,
+                                                                  const double *__restrict__ bpref,
+                                                                  const double *__restrict__ bstate,
+                                                                  double *__restrict__ alpha) {
+  const int64_t bch = blockIdx.y;
+  const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
+  const int64_t g = (int64_t)blockIdx.x * kThreadsGp + threadIdx.x;
+  const int64_t run = T - 1 - g;
+  if (run < 0) return;
+  const int64_t s = run * kRun, e = min(s + kRun, N);
+  const double *st = bstate + (bch * gridDim.x + blockIdx.x) * 2;
+  double R0 = st[0], R1 = st[1];
+  if (threadIdx.x > 0) {  // apply the in-CTA exclusive prefix (inclusive of the previous thread)
+    const double *p = bpref + (bch * T + g - 1) * 6;
+    const double n0 = p[0] * R0 + p[1] * R1 + p[4], n1 = p[2] * R0 + p[3] * R1 + p[5];
+    R0 = n0;
+    R1 = n1;
+  }
+  const double *rb = rec + bch * 3 * N;
+  double *ab = alpha + bch * N;
+  for (int64_t i = e - 1; i >= s; --i) ab[i] = gp_bwd_step(k, t, rb, N, i, R0, R1);
+}
+
 __global__ void gp_fold_kernel(const double *__restrict__ cta_ll, int nctas, int64_t N, int64_t B,
                                double *__restrict__ loglike) {
   const int64_t bch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -348,9 +522,9 @@ __global__ void gp_fold_kernel(const double *__restrict__ cta_ll, int nctas, int
 struct GpLayout {
   int64_t T;      // runs (threads) per chain
   int nctas;      // CTAs per chain
-  size_t off_pref, off_tot, off_state, off_ll, bytes;
+  size_t off_pref, off_tot, off_state, off_ll, off_rec, off_bpref, off_bcta, off_bstate, bytes;
 };
-inline GpLayout gp_layout(int64_t N, int64_t B) {
+inline GpLayout gp_layout(int64_t N, int64_t B, bool solve = false) {
   GpLayout L;
   L.T = (N + kRun - 1) / kRun;
   L.nctas = (int)((L.T + kThreadsGp - 1) / kThreadsGp);
@@ -364,6 +538,13 @@ inline GpLayout gp_layout(int64_t N, int64_t B) {
   L.off_tot = take((size_t)B * L.nctas * kAggDoubles);
   L.off_state = take((size_t)B * L.nctas * 5);
   L.off_ll = take((size_t)B * L.nctas);
+  L.off_rec = L.off_bpref = L.off_bcta = L.off_bstate = 0;
+  if (solve) {
+    L.off_rec = take((size_t)B * 3 * N);
+    L.off_bpref = take((size_t)B * L.T * 6);
+    L.off_bcta = take((size_t)B * L.nctas * 6);
+    L.off_bstate = take((size_t)B * L.nctas * 2);
+  }
   L.bytes = o;
   return L;
 }
@@ -396,8 +577,42 @@ int xo_celerite_sho_loglike(const double *t, const double *y, const double *diag
   dim3 grid(L.nctas, (unsigned)B);
   gp_aggregate_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, pref, tot);
   gp_cta_scan_kernel<<<(unsigned)B, kThreadsGp, 0, st>>>(tot, L.nctas, S0, w0, Q, eps, state);
-  gp_loglike_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, pref, state, ll);
+  gp_loglike_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, pref, state, ll, nullptr);
   gp_fold_kernel<<<(unsigned)((B + 63) / 64), 64, 0, st>>>(ll, L.nctas, N, B, loglike);
+  return xo::launch_status();
+}
+
+size_t xo_celerite_sho_solve_workspace(int64_t N, int64_t B) {
+  if (N <= 0 || B <= 0) return 0;
+  return gp_layout(N, B, true).bytes;
+}
+
+// log-likelihood AND alpha = K^-1 y (so that d loglike / d y = -alpha): forward scan, then the
+// disturbance smoother as a reverse affine scan.  alpha[B][N].
+int xo_celerite_sho_solve(const double *t, const double *y, const double *diag, int64_t N, const double *S0,
+                          const double *w0, const double *Q, int64_t B, double eps, double *loglike, double *alpha,
+                          void *workspace, size_t workspace_bytes, void *stream) {
+  if (N < 0 || B < 0) return XO_EINVAL;
+  if (B == 0) return 0;
+  if (N == 0) return XO_EINVAL;
+  if (B > 65535) return XO_ERANGE;
+  if (!t || !y || !diag || !S0 || !w0 || !Q || !loglike || !alpha || !workspace) return XO_EINVAL;
+  GpLayout L = gp_layout(N, B, true);
+  if (workspace_bytes < L.bytes) return XO_EWORKSPACE;
+  char *ws = static_cast<char *>(workspace);
+  auto at = [&](size_t off) { return reinterpret_cast<double *>(ws + off); };
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid(L.nctas, (unsigned)B);
+  gp_aggregate_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, at(L.off_pref), at(L.off_tot));
+  gp_cta_scan_kernel<<<(unsigned)B, kThreadsGp, 0, st>>>(at(L.off_tot), L.nctas, S0, w0, Q, eps, at(L.off_state));
+  gp_loglike_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, at(L.off_pref), at(L.off_state),
+                                                 at(L.off_ll), at(L.off_rec));
+  gp_fold_kernel<<<(unsigned)((B + 63) / 64), 64, 0, st>>>(at(L.off_ll), L.nctas, N, B, loglike);
+  gp_bwd_aggregate_kernel<<<grid, kThreadsGp, 0, st>>>(t, N, S0, w0, Q, eps, L.T, at(L.off_rec), at(L.off_bpref),
+                                                       at(L.off_bcta));
+  gp_bwd_cta_scan_kernel<<<(unsigned)B, kThreadsGp, 0, st>>>(at(L.off_bcta), L.nctas, at(L.off_bstate));
+  gp_bwd_solve_kernel<<<grid, kThreadsGp, 0, st>>>(t, N, S0, w0, Q, eps, L.T, at(L.off_rec), at(L.off_bpref),
+                                                   at(L.off_bstate), alpha);
   return xo::launch_status();
 }
 

@@ -158,6 +158,13 @@ int xo_celerite_sho_loglike(const double *t, const double *y, const double *diag
                             const double *w0, const double *Q, int64_t B, double eps, double *loglike, void *workspace,
                             size_t workspace_bytes, void *stream);
 
+/* log-likelihood and alpha = K^-1 y in one call (d loglike / d y = -alpha, the cotangent a mean
+ * model such as the transit light curve needs); alpha[B][N]. */
+size_t xo_celerite_sho_solve_workspace(int64_t N, int64_t B);
+int xo_celerite_sho_solve(const double *t, const double *y, const double *diag, int64_t N, const double *S0,
+                          const double *w0, const double *Q, int64_t B, double eps, double *loglike, double *alpha,
+                          void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- host-buffer entry points (the shape of exoplanet-core's driver) ---- */
 int xo_kepler_host(const double *M, const double *e, double *sinf, double *cosf, int64_t n, int device);
 int xo_qsv_host(const double *b, const double *r, double *s, double *dsdb, double *dsdr, int64_t n, int device);
