@@ -60,8 +60,8 @@ def _dense_sho(t, diag, S0, w0, Q):
         h = c * np.sqrt(4 * Q * Q - 1)
         k = a * np.exp(-c * tau) * (np.cos(h * tau) + c / h * np.sin(h * tau))
     else:
-        h = c * np.sqrt(1 - 4 * Q * Q)
-        k = a * np.exp(-c * tau) * (np.cosh(h * tau) + c / h * np.sinh(h * tau))
+        h = c * np.sqrt(1 - 4 * Q * Q)  # two decaying exponentials (cosh/sinh would overflow at large tau)
+        k = 0.5 * a * ((1 + c / h) * np.exp(-(c - h) * tau) + (1 - c / h) * np.exp(-(c + h) * tau))
     return k + np.diag(diag)
 
 
