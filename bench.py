@@ -241,6 +241,24 @@ def extra_configs(lib, dev, args):
         out["configs[3] celerite SHO loglike, N=1e6, %d chain(s)" % B] = {
             "value": B * Ng / (ms * 1e-3), "unit": "cadences/s", "ms_per_step": ms, "gb_per_s": 24.0 * B * Ng / (ms * 1e-3) / 1e9,
             "parity_rel_err": float(abs(r["ll"][0].item() - lo) / abs(lo))}
+    # joint model of configs[3]: transit mean + SHO GP noise at N=1e6, logL and its gradient w.r.t. the
+    # orbital parameters (light curve -> residual -> GP solve (logL, alpha) -> light-curve VJP with alpha)
+    from exoplanet_b200.light_curves import LimbDarkLightCurve
+    from exoplanet_b200.orbits import KeplerianOrbit
+
+    pj = [d([7.31]).requires_grad_(True), d([0.3]).requires_grad_(True), d([0.08]).requires_grad_(True)]
+    lcm = LimbDarkLightCurve(0.3, 0.2, device=dev)
+    res = {}
+
+    def jstep():
+        orbit = KeplerianOrbit(period=pj[0], t0=d([1.3]), ecc=d([0.3]), omega=d([0.4]), b=pj[1])
+        mu = lcm.get_light_curve(orbit=orbit, r=pj[2], t=tg)[:, 0]
+        ll = gp.sho_loglike_autograd(tg, yg - mu, dg, pr["S0"], pr["w0"], pr["Q"])
+        res["g"] = torch.autograd.grad(ll, pj)
+
+    ms = _time_steps(jstep, 5, flush)
+    out["configs[3] transit + SHO GP, N=1e6: logL + d/d(period, b, r) (torch-level composition)"] = {
+        "value": 1.0 / (ms * 1e-3), "unit": "model+grad evals/s", "ms_per_step": ms}
     return out
 
 
