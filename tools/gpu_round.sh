@@ -28,7 +28,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:tran
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:kepler_fwd_kernel -s 4 -c 1 -f -o $OUT/${TAG}_prof_kepler \
     python bench.py --steps 1 --warmup 3 --no-cpu > $OUT/${TAG}_ncu_kepler.log 2>&1
 # sanitizers on the small smoke problem (memory errors, shared-memory races in the queue kernels)
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_memcheck.log 2>&1; echo "memcheck exit $?" >> $OUT/${TAG}_memcheck.log
+timeout 600 compute-sanitizer --tool memcheck --report-api-errors no --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_memcheck.log 2>&1; echo "memcheck exit $?" >> $OUT/${TAG}_memcheck.log
 timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_racecheck.log 2>&1; echo "racecheck exit $?" >> $OUT/${TAG}_racecheck.log
 fi
 tail -3 $OUT/${TAG}_memcheck.log $OUT/${TAG}_racecheck.log 2>/dev/null
