@@ -118,7 +118,20 @@ int xo_transit_model_logp_grad(const double *t, const double *y, const double *i
     return xo::launch_status();
   }
   model_prologue_kernel<<<(unsigned)((2 * cp + 63) / 64), 64, 0, st>>>(par, star, C, (int)P, texp, use_in_transit, elem, cl);
-  xo::launch_transit_logp_grad(t, y, ivar, N, elem, cl, mean, C, (int)P, dtk, wk, K, L.sp, moments, partial, st, nullptr);
+  static const int lpt = [] {
+    const char *v = getenv("XO_MODEL_HEAVY_FIRST");
+    return v && *v ? atoi(v) : 1;
+  }();
+  xo::ModelArgs ord;
+  const xo::ModelArgs *pord = nullptr;
+  if (lpt && C > 1) {
+    int *order = reinterpret_cast<int *>(ws + L.off_counter);  // the counter slot is free in this mode
+    xo::launch_chain_order(elem, C, (int)P, order, st);
+    ord.order = order;
+    ord.elements_only = 1;
+    pord = &ord;
+  }
+  xo::launch_transit_logp_grad(t, y, ivar, N, elem, cl, mean, C, (int)P, dtk, wk, K, L.sp, moments, partial, st, pord);
   model_epilogue_kernel<<<(unsigned)((C + 3) / 4), 128, 0, st>>>(par, star, partial, L.sp.slots, C, (int)P, lognorm, logp,
                                                                  gpar, gstar, gmean);
   return xo::launch_status();

@@ -159,7 +159,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
   __shared__ uint32_t queue[kWarps][XO_MAX_PLANETS][kQueue];
   __shared__ double gacc[kWarps][XO_MAX_PLANETS][XO_NGRAD];
   __shared__ double lacc[XO_NGRAD + 3][kThreads];  // per-thread gradient accumulators of one drain
-  const int64_t c = blockIdx.y;
+  // heaviest chains first (ma.order, optional): CTAs are dispatched in blockIdx order, so the long
+  // ones start early and the short ones fill the tail of the launch
+  const int64_t c = ma.order ? ma.order[blockIdx.y] : blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = blockIdx.x * kWarps + warp;
   if (kModel && ma.stage_from_params)
@@ -185,6 +187,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
     if (lane < m) {
       const uint32_t idx = queue[warp][p][off + lane];
       const double tt = __ldg(t + idx);
+      // issued now so that their latency hides behind the sample evaluation
+      const double yy = kVjp ? __ldg(y + ((int64_t)c * N + idx) * P + p) : __ldg(y + idx);
+      const double iv = kVjp ? 0.0 : __ldg(ivar + idx);
       double ltot = 0.0;
       bool owner = true;  // the lowest in-window planet owns the per-cadence terms
       // one call site for the sample evaluation: planet p with its gradient weights, any other
@@ -199,9 +204,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
         }
       }
       if (kVjp) {
-        scale = __ldg(y + ((int64_t)c * N + idx) * P + p);
+        scale = yy;  // the cotangent bar_lc[c][idx][p]
       } else {
-        const double yy = __ldg(y + idx), iv = __ldg(ivar + idx);
         const double r0 = yy - mean_c;
         scale = iv * (r0 - ltot);
         if (owner) {  // -1/2 iv (res^2 - r0^2) and iv (res - r0), without cancellation
@@ -235,8 +239,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
   // kUnroll coalesced loads, 4 flops + 2 compares per cadence and planet, one vote.
   const bool sorted = kMoments && moments[4] != 0.0;  // t non-decreasing: steps can be skipped wholesale
   const double *tp = t + lane;
+  // sorted mode: lane l holds the first/last time of step l of the current group of 32 steps
+  // (two loads per lane per 4096 cadences instead of two dependent broadcast loads per step)
+  double edgeA = 0.0, edgeB = 0.0;
+  uint32_t step = 0;
 #pragma unroll 1
-  for (uint32_t base = start;; base += 32 * kUnroll) {
+  for (uint32_t base = start;; base += 32 * kUnroll, ++step) {
     const bool last = base >= end;
     double tt[kUnroll], yy[kUnroll], iv[kUnroll];
     uint32_t valid = 0u;  // bit u: cadence base + 32 u + lane exists
@@ -244,7 +252,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
       if (sorted) {
         // the step spans [tA, tB]; if that interval misses every planet's window (in phase, with
         // wrap) no lane can be in transit -> skip the step after two broadcast loads
-        const double tA = __ldg(t + base), tB = __ldg(t + min(base + 32 * kUnroll, end) - 1);
+        if ((step & 31u) == 0u) {
+          const uint32_t sb = base + lane * (32 * kUnroll);
+          edgeA = sb < end ? __ldg(t + sb) : 0.0;
+          edgeB = sb < end ? __ldg(t + min(sb + 32 * kUnroll, end) - 1) : 0.0;
+        }
+        const double tA = __shfl_sync(kFull, edgeA, step & 31u), tB = __shfl_sync(kFull, edgeB, step & 31u);
         bool hit = false;
         for (int p = 0; p < P; ++p) {
           const double rpp = sm.rperiod[p];
@@ -415,6 +428,29 @@ __global__ void __launch_bounds__(1024) transit_moments_kernel(const double *__r
     out[3] = Syy;
     out[4] = Bad == 0.0 ? 1.0 : 0.0;
   }
+}
+
+// rank chains by expected in-transit work, sum_p (window width / period), heaviest first;
+// order[rank] = chain.  O(C^2) comparisons, C <= 65535 and typically <= 1024.
+__global__ void chain_order_kernel(const double *__restrict__ elem, int64_t C, int P, int *__restrict__ order) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  auto weight = [&](int64_t k) {
+    double w = 0.0;
+    for (int p = 0; p < P; ++p) {
+      const double *e = elem + (k * P + p) * XO_NEL;
+      const double f = (e[XO_EL_TEND] - e[XO_EL_TSTART]) / e[XO_EL_PERIOD];
+      w += (f == f && f < 1.0) ? f : 1.0;  // infinite window = every cadence
+    }
+    return w;
+  };
+  const double wc = weight(c);
+  int rank = 0;
+  for (int64_t k = 0; k < C; ++k) {
+    const double wk = weight(k);
+    rank += (wk > wc) || (wk == wc && k < c);
+  }
+  order[rank] = (int)c;
 }
 
 // fold per-warp partials in slot order: out[c][j] = sum_s partial[c][s][j]
@@ -633,7 +669,7 @@ void launch_transit_logp_grad(const double *t, const double *y, const double *iv
     return;
   }
   const int mb = transit_min_blocks();
-  if (model) {
+  if (model && !model->elements_only) {
     if (moments) XO_LAUNCH(3, false, true, true);
     else XO_LAUNCH(3, false, false, true);
     return;
@@ -649,6 +685,10 @@ void launch_transit_logp_grad(const double *t, const double *y, const double *iv
     else XO_LAUNCH(3, false, false, false);
   }
 #undef XO_LAUNCH
+}
+
+void launch_chain_order(const double *elem, int64_t C, int P, int *order, cudaStream_t st) {
+  chain_order_kernel<<<(unsigned)((C + 127) / 128), 128, 0, st>>>(elem, C, P, order);
 }
 
 }  // namespace xo

@@ -24,9 +24,11 @@ struct ModelArgs {
   const double *star = nullptr;  // [C][XO_NSTAR]
   double texp = 0.0;
   int use_in_transit = 1;
+  int elements_only = 0;      // 1: plain element-level launch that only uses `order`
   int stage_from_params = 1;  // 0: element blocks were written by model_prologue_kernel (elem, cl valid)
   double lognorm = 0.0;
   unsigned *counter = nullptr;  // [C], zero on entry; left zero on exit
+  const int *order = nullptr;   // [C] chain processed by blockIdx.y (heaviest first), or null = identity
   double *logp = nullptr, *gpar = nullptr, *gstar = nullptr, *gmean = nullptr;
 };
 
@@ -36,5 +38,8 @@ void launch_transit_logp_grad(const double *t, const double *y, const double *iv
                               const double *cl, const double *mean, int64_t C, int P, const double *dtk,
                               const double *wk, int K, Split sp, const double *moments, double *partial, cudaStream_t st,
                               const ModelArgs *model);
+
+// order[rank] = chain, heaviest expected in-transit work first
+void launch_chain_order(const double *elem, int64_t C, int P, int *order, cudaStream_t st);
 
 }  // namespace xo

@@ -13,6 +13,7 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smo
 timeout 900 python bench.py --steps 20 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench exit $?" >> $OUT/${TAG}_bench.err
 timeout 300 python bench.py --impl reference --steps 20 --warmup 2 > $OUT/${TAG}_bench_ref.json 2>> $OUT/${TAG}_bench.err
 : > $OUT/${TAG}_sweep.txt; for ML in 1 2 3; do echo -n "XO_MODEL_LAUNCHES=$ML: " >> $OUT/${TAG}_sweep.txt; XO_MODEL_LAUNCHES=$ML timeout 120 python bench.py --steps 20 --warmup 3 --no-cpu --no-kepler --no-extra 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e_resident_data']['value'])" >> $OUT/${TAG}_sweep.txt; done
+for HF in 0 1; do echo -n "XO_MODEL_HEAVY_FIRST=$HF: " >> $OUT/${TAG}_sweep.txt; XO_MODEL_HEAVY_FIRST=$HF timeout 120 python bench.py --steps 20 --warmup 3 --no-cpu --no-kepler --no-extra 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e_resident_data']['value'])" >> $OUT/${TAG}_sweep.txt; done
 if [ "$MODE" = "full" ]; then
 # tuning sweep of the logp kernel (register cap x launch width)
 for SWEEPFLAG in "" "--full-sweep"; do for mb in 2 3 4 5; do for w in 16 24 32; do
