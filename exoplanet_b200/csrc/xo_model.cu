@@ -120,7 +120,7 @@ int xo_transit_model_logp_grad(const double *t, const double *y, const double *i
   model_prologue_kernel<<<(unsigned)((2 * cp + 63) / 64), 64, 0, st>>>(par, star, C, (int)P, texp, use_in_transit, elem, cl);
   static const int lpt = [] {
     const char *v = getenv("XO_MODEL_HEAVY_FIRST");
-    return v && *v ? atoi(v) : 1;
+    return v && *v ? atoi(v) : 0;  // measured slower on B200: heavy CTAs co-resident on an SM contend
   }();
   xo::ModelArgs ord;
   const xo::ModelArgs *pord = nullptr;
