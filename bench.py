@@ -424,7 +424,36 @@ def arm_ours(args):
             kep[name] = {"cadences_per_s": n / (ms * 1e-3), "gb_per_s": n * KEPLER_BYTES_PER_ELEMENT / (ms * 1e-3) / 1e9,
                          "ms": ms, "n": n}
             del sf, cf, e
-        del M
+        # the other standalone ops at > L2 working sets (algorithmic bytes per element in BASELINE.md section 5)
+        n2 = 1 << 24
+        bb = torch.rand(n2, dtype=torch.float64, device=dev, generator=g) * 1.25
+        rr = torch.rand(n2, dtype=torch.float64, device=dev, generator=g) * 0.18 + 0.02
+        s3 = torch.empty((n2, 3), dtype=torch.float64, device=dev)
+        db3, dr3 = torch.empty_like(s3), torch.empty_like(s3)
+        e1 = torch.rand(n2, dtype=torch.float64, device=dev, generator=g) * 0.9
+        a1, a2, o1, o2 = M[:n2].sin(), M[:n2].cos(), torch.empty(n2, dtype=torch.float64, device=dev), torch.empty(n2, dtype=torch.float64, device=dev)
+        sp = C.c_void_p(stream.cuda_stream)
+        micro = {
+            "qsv_fwd+jac (88 B/pt)": (lambda: lib.xo_qsv_fwd(ptr(bb), ptr(rr), ptr(s3), ptr(db3), ptr(dr3), n2, sp), 88),
+            "qsv_fwd (40 B/pt)": (lambda: lib.xo_qsv_fwd(ptr(bb), ptr(rr), ptr(s3), None, None, n2, sp), 40),
+            "qsv_vjp (88 B/pt)": (lambda: lib.xo_qsv_vjp(ptr(s3), ptr(db3), ptr(dr3), ptr(o1), ptr(o2), n2, sp), 88),
+            "kepler_vjp (56 B/elt)": (lambda: lib.xo_kepler_vjp(ptr(a1), ptr(a2), ptr(e1), ptr(bb), ptr(rr), ptr(o1), ptr(o2), n2, sp), 56),
+        }
+        for name, (fn, nbytes) in micro.items():
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            evs = []
+            for _ in range(5):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                evs.append((a, b))
+            torch.cuda.synchronize()
+            ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+            kep[name] = {"elements_per_s": n2 / (ms * 1e-3), "gb_per_s": n2 * nbytes / (ms * 1e-3) / 1e9, "ms": ms, "n": n2}
+        del M, bb, rr, s3, db3, dr3, e1, a1, a2, o1, o2
 
     # ---- the other BASELINE configs, measured briefly on one GPU (parity-checked against the oracle) ----
     other = None

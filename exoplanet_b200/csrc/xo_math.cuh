@@ -51,13 +51,17 @@ constexpr double kTwoOverPi = 0.636619772367581343075535053490057448;
         0.159154943091895335768883763372514362, 6.283185307179586232e+00, 2.449293598294706414e-16,            \
         0.636619772367581343075535053490057448, 1.570796326794896558e+00, 6.123233995736766036e-17,            \
         /* 20..25 small-angle sin/cos series: -1/5040, 1/120, -1/6, -1/720, 1/24, pi */                        \
-        -1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0, -1.0 / 720.0, 1.0 / 24.0, 3.14159265358979323846264338327950288 \
+        -1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0, -1.0 / 720.0, 1.0 / 24.0, 3.14159265358979323846264338327950288, \
+        /* 26..31 solution-vector constants: 2pi/3, 1/(2pi), 4pi, 2pi, 1/(9pi), 1/3 */                         \
+        2.09439510239319549230842892218633526, 0.159154943091895335768883763372514362,                         \
+        12.5663706143591729538505735331180115, 6.28318530717958647692528676655900577,                          \
+        0.0353677651315322968375297252050031916, 0.333333333333333333333333333333333333                        \
   }
 namespace detail {
 #if defined(__CUDACC__)
-static __constant__ double c_tab[26] = XO_CONST_TABLE;
+static __constant__ double c_tab[32] = XO_CONST_TABLE;
 #endif
-static const double h_tab[26] = XO_CONST_TABLE;
+static const double h_tab[32] = XO_CONST_TABLE;
 }  // namespace detail
 #if defined(__CUDA_ARCH__)
 #define XO_K(i) (::xo::detail::c_tab[i])
@@ -327,7 +331,7 @@ XO_HD void cel3(double kc, double kc2, double p, double a, double b, double &G, 
     kc += kc;
     e = kc * em;
   }
-  double t = 0.5 * kPi * rcp_fast(em);
+  double t = 0.5 * XO_K(25) * rcp_fast(em);
   G = t * fma(a, em, b) * rcp_fast(em + p);
   double r1 = rcp_fast(em + p1);
   Ek = t * fma(aE, em, bE) * r1;
@@ -352,8 +356,8 @@ XO_HD void qsv(double b_in, double r, double *s, double *dsdb, double *dsdr) {
   double t4 = (b >= 0.5) ? (b - 1.0) + r : (r - 1.0) + b;  // b + r - 1
   if (!(r > 0.0) || !(t3 > 0.0)) {                         // unocculted (r <= 0, b >= 1 + r, NaN)
     bool bad = (b != b) || (r != r);
-    s[0] = bad ? NAN : kPi;
-    s[1] = bad ? NAN : 2.0 * kPi / 3.0;
+    s[0] = bad ? NAN : XO_K(25);
+    s[1] = bad ? NAN : XO_K(26);
     s[2] = bad ? NAN : 0.0;
     return;
   }
@@ -368,25 +372,25 @@ XO_HD void qsv(double b_in, double r, double *s, double *dsdb, double *dsdr) {
   double fourbr = 4.0 * b * r;
   double kap0, sk0, ck0, s0, eta;
   if (t4 <= 0.0) {  // occultor entirely inside the disk
-    kap0 = kPi;
+    kap0 = XO_K(25);
     sk0 = 0.0;
     ck0 = -1.0;
-    s0 = kPi * (1.0 - r2);
+    s0 = XO_K(25) * (1.0 - r2);
     eta = 0.5 * r2 * fma(2.0, b2, r2);
   } else {
-    double D = sqrt(t1 * t2 * t3 * t4);  // twice the kite area
+    double D = sqrt_fast(t1 * t2 * t3 * t4);  // twice the kite area
     double c0 = fma(r - 1.0, r + 1.0, b2);
     double c1 = fma(1.0 - r, 1.0 + r, b2);
     kap0 = atan2(D, c0);
     double kap1 = atan2(D, c1);
-    double rtwobr = rcp(2.0 * b * r);
+    double rtwobr = rcp_fast(2.0 * b * r);
     sk0 = D * rtwobr;
     ck0 = c0 * rtwobr;
-    s0 = kPi - (kap1 + r2 * kap0 - 0.5 * D);
-    eta = (kap1 + r2 * fma(2.0, b2, r2) * kap0 - 0.25 * (1.0 + 5.0 * r2 + b2) * D) * (0.5 / kPi);
+    s0 = XO_K(25) - (kap1 + r2 * kap0 - 0.5 * D);
+    eta = (kap1 + r2 * fma(2.0, b2, r2) * kap0 - 0.25 * (1.0 + 5.0 * r2 + b2) * D) * XO_K(27);
   }
   s[0] = s0;
-  s[2] = 2.0 * s0 + 4.0 * kPi * eta - 2.0 * kPi;
+  s[2] = fma(XO_K(28), eta, 2.0 * s0) - XO_K(29);
   if (kJac) {
     double gg = 2.0 - 4.0 * b2 - 4.0 * r2;
     dsdb[0] = 2.0 * r * sk0;
@@ -437,14 +441,14 @@ XO_HD void qsv(double b_in, double r, double *s, double *dsdb, double *dsdr) {
   double Lam, d1b, d1r;
   if (kind == kLimb) {
     const double rsqbr = rcp_fast(sqrt_fast(b * r));
-    Lam = onembmr2 * (G + fma(-3.0 + 6.0 * r2 + 2.0 * b * r, Em, -fourbr * E)) * rsqbr * (1.0 / (9.0 * kPi));
+    Lam = onembmr2 * (G + fma(-3.0 + 6.0 * r2 + 2.0 * b * r, Em, -fourbr * E)) * rsqbr * XO_K(30);
     d1r = -2.0 * r * onembmr2 * Em * rsqbr;
-    d1b = 2.0 * r * onembmr2 * (2.0 * E - Em) * rsqbr * (1.0 / 3.0);
+    d1b = 2.0 * r * onembmr2 * (2.0 * E - Em) * rsqbr * XO_K(31);
   } else if (kind == kInside) {
     const double sqA = sqrt_fast(onembmr2);
-    Lam = 2.0 * sqA * fma(onembpr2, G, -(4.0 - 7.0 * r2 - b2) * E) * (1.0 / (9.0 * kPi));
+    Lam = 2.0 * sqA * fma(onembpr2, G, -(4.0 - 7.0 * r2 - b2) * E) * XO_K(30);
     d1r = -4.0 * r * sqA * E;
-    d1b = 4.0 * r * sqA * (1.0 / 3.0) * (2.0 * Em - E);
+    d1b = 4.0 * r * sqA * XO_K(31) * (2.0 * Em - E);
   } else if (kind == kB0) {
     const double x = sqrt(fmax(0.0, 1.0 - r2));
     Lam = -2.0 / 3.0 * x * x * x;
@@ -469,7 +473,7 @@ XO_HD void qsv(double b_in, double r, double *s, double *dsdb, double *dsdr) {
     d1r = -8.0 * r2 * aux * Em;
     d1b = 8.0 * r2 / 3.0 * aux * (2.0 * E - Em);
   }
-  s[1] = (r > b ? 0.0 : 2.0 * kPi / 3.0) - kPi * Lam;
+  s[1] = fma(-XO_K(25), Lam, r > b ? 0.0 : XO_K(26));
   if (kJac) {
     dsdb[1] = d1b;
     dsdr[1] = d1r;
@@ -518,7 +522,7 @@ XO_HD double lc_point(const double *el, const double *cl, double tt, double w, d
   const double e = el[3], cw = el[4], sw = el[5], ci = el[6], si = el[7], aor = el[8], ror = el[9];
   double ome2 = (1.0 - e) * (1.0 + e);
   double opc = fma(e, cf, 1.0);
-  double ropc = rcp(opc);
+  double ropc = rcp_fast(opc);
   double rr = aor * ome2 * ropc;  // |r| / R_star   (keplerian.py:403 with a -> -a)
   double cwf = cw * cf - sw * sf;
   double swf = sw * cf + cw * sf;
@@ -526,7 +530,7 @@ XO_HD double lc_point(const double *el, const double *cl, double tt, double w, d
   if (!(z > 0.0)) return 0.0;
   double ci2 = ci * ci;
   double h = fma(cwf, cwf, ci2 * swf * swf);
-  double sh = sqrt(h);
+  double sh = sqrt_fast(h);
   double b = rr * sh;
   if (b >= 1.0 + ror) return 0.0;
   double S[3], B[3], R[3];
@@ -541,13 +545,13 @@ XO_HD double lc_point(const double *el, const double *cl, double tt, double w, d
   double db_drr = sh;
   double db_dcwf = 0.0, db_dswf = 0.0, db_dci = 0.0;
   if (sh > 0.0) {
-    double rsh = rr * rcp(sh);
+    double rsh = rr * rcp_fast(sh);
     db_dcwf = rsh * cwf;
     db_dswf = rsh * ci2 * swf;
     db_dci = rsh * ci * swf * swf;
   }
-  double rome2 = rcp(ome2);
-  double dfdM = opc * opc * rome2 * sqrt(rome2);
+  double rome2 = rcp_fast(ome2);
+  double dfdM = opc * opc * rome2 * sqrt_fast(rome2);
   double dfde = (2.0 + e * cf) * sf * rome2;
   double drr_dcf = -rr * e * ropc;
   double drr_de = aor * (-2.0 * e * opc - ome2 * cf) * ropc * ropc;
@@ -563,7 +567,7 @@ XO_HD double lc_point(const double *el, const double *cl, double tt, double w, d
   g[4 * kStride] = fma(dldb, db_dcwf * cf + db_dswf * sf, g[4 * kStride]);
   g[5 * kStride] = fma(dldb, db_dswf * cf - db_dcwf * sf, g[5 * kStride]);
   g[6 * kStride] = fma(dldb, db_dci, g[6 * kStride]);
-  g[8 * kStride] = fma(dldb, db_drr * rr * rcp(aor), g[8 * kStride]);
+  g[8 * kStride] = fma(dldb, db_drr * rr * rcp_fast(aor), g[8 * kStride]);
   g[9 * kStride] += dldr;
   return lc;
 }
