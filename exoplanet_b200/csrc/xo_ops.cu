@@ -73,6 +73,8 @@ __global__ void __launch_bounds__(kThreads) kepler_fwd_kernel_scalar(const doubl
   }
 }
 
+// two elements per thread, 16-byte streaming loads/stores when every pointer allows it
+template <bool kVec>
 __global__ void __launch_bounds__(kThreads) kepler_vjp_kernel(const double *__restrict__ sinf,
                                                               const double *__restrict__ cosf,
                                                               const double *__restrict__ e,
@@ -80,13 +82,34 @@ __global__ void __launch_bounds__(kThreads) kepler_vjp_kernel(const double *__re
                                                               const double *__restrict__ bc, double *__restrict__ bM,
                                                               double *__restrict__ be, int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    double sf = __ldcs(sinf + i), cf = __ldcs(cosf + i), ee = __ldcs(e + i);
+  auto one = [](double sf, double cf, double ee, double gs, double gc, double &oM, double &oe) {
     double dfdM, dfde;
     xo::kepler_jac(sf, cf, ee, dfdM, dfde);
-    double bf = __ldcs(bs + i) * cf - __ldcs(bc + i) * sf;
-    __stcs(bM + i, bf * dfdM);
-    __stcs(be + i, bf * dfde);
+    const double bf = gs * cf - gc * sf;
+    oM = bf * dfdM;
+    oe = bf * dfde;
+  };
+  if (kVec) {
+    const int64_t npair = n >> 1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npair; i += stride) {
+      const double2 sf = ld2(sinf + 2 * i), cf = ld2(cosf + 2 * i), ee = ld2(e + 2 * i), gs = ld2(bs + 2 * i), gc = ld2(bc + 2 * i);
+      double m0, e0, m1, e1;
+      one(sf.x, cf.x, ee.x, gs.x, gc.x, m0, e0);
+      one(sf.y, cf.y, ee.y, gs.y, gc.y, m1, e1);
+      st2(bM + 2 * i, m0, m1);
+      st2(be + 2 * i, e0, e1);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+      const int64_t i = n - 1;
+      one(sinf[i], cosf[i], e[i], bs[i], bc[i], bM[i], be[i]);
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      double m0, e0;
+      one(__ldcs(sinf + i), __ldcs(cosf + i), __ldcs(e + i), __ldcs(bs + i), __ldcs(bc + i), m0, e0);
+      __stcs(bM + i, m0);
+      __stcs(be + i, e0);
+    }
   }
 }
 
@@ -193,8 +216,16 @@ int xo_kepler_vjp(const double *sinf, const double *cosf, const double *e, const
   if (n < 0) return XO_EINVAL;
   if (n == 0) return 0;
   if (!sinf || !cosf || !e || !bsinf || !bcosf || !bM || !be) return XO_EINVAL;
-  int grid = (int)xo::clamp_grid((n + kThreads - 1) / kThreads, xo::sm_count(), 8);
-  kepler_vjp_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(sinf, cosf, e, bsinf, bcosf, bM, be, n);
+  const bool vec = aligned16(sinf) && aligned16(cosf) && aligned16(e) && aligned16(bsinf) && aligned16(bcosf) && aligned16(bM) &&
+                   aligned16(be);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (vec) {
+    int grid = (int)xo::clamp_grid((n / 2 + kThreads - 1) / kThreads, xo::sm_count(), 8);
+    kepler_vjp_kernel<true><<<grid, kThreads, 0, st>>>(sinf, cosf, e, bsinf, bcosf, bM, be, n);
+  } else {
+    int grid = (int)xo::clamp_grid((n + kThreads - 1) / kThreads, xo::sm_count(), 8);
+    kepler_vjp_kernel<false><<<grid, kThreads, 0, st>>>(sinf, cosf, e, bsinf, bcosf, bM, be, n);
+  }
   return xo::launch_status();
 }
 

@@ -49,3 +49,29 @@ for name, fn, deg in [("S", S, 6), ("C", Cc, 6)]:
             err = abs(1 - u / 2 + u * u * p - mp.cos(x))
         worst = max(worst, err)
     print("  max abs err with fp64 coefficients:", mp.nstr(worst, 3))
+
+
+# ---- atan x = x + x^3 A(x^2) on |x| <= tan(pi/8) (after the usual two reductions) -------------
+def A(u):
+    x = mp.sqrt(u)
+    return (mp.atan(x) - x) / (x ** 3) if u > 0 else -mp.mpf(1) / 3
+
+
+def report_atan(deg):
+    xm = mp.tan(mp.pi / 8) * mp.mpf("1.01")
+    c = fit(A, deg, xm)
+    cf = [mp.mpf(float(v)) for v in c]
+    worst = 0
+    for k in range(2001):
+        x = xm * k / 2000
+        u = x * x
+        p = sum(cf[j] * u ** j for j in range(deg + 1))
+        worst = max(worst, abs(x + x ** 3 * p - mp.atan(x)))
+    print("atan deg", deg, "max abs err", mp.nstr(worst, 3))
+    return c
+
+
+if __name__ == "__main__":
+    for deg in (9, 10, 11, 12):
+        c = report_atan(deg)
+    print("A = {" + ", ".join(mp.nstr(v, 21) for v in c) + "}")
