@@ -53,9 +53,7 @@ constexpr double kTwoOverPi = 0.636619772367581343075535053490057448;
         /* 20..25 small-angle sin/cos series: -1/5040, 1/120, -1/6, -1/720, 1/24, pi */                        \
         -1.0 / 5040.0, 1.0 / 120.0, -1.0 / 6.0, -1.0 / 720.0, 1.0 / 24.0, 3.14159265358979323846264338327950288, \
         /* 26..31 solution-vector constants: 2pi/3, 1/(2pi), 4pi, 2pi, 1/(9pi), 1/3 */                         \
-        2.09439510239319549230842892218633526, 0.159154943091895335768883763372514362,                         \
-        12.5663706143591729538505735331180115, 6.28318530717958647692528676655900577,                          \
-        0.0353677651315322968375297252050031916, 0.333333333333333333333333333333333333,                       \
+        2.0 * kPi / 3.0, 0.5 / kPi, 4.0 * kPi, 2.0 * kPi, 1.0 / (9.0 * kPi), 1.0 / 3.0, /* fp64-folded like the oracle */ \
         /* 32..42 atan kernel A(u), LOWEST degree first (tools/gen_poly.py); 43 pi/4; 44 tan(pi/8) */            \
         -0.333333333333333295843, 0.199999999999947778464, -0.14285714284510125851, 0.111111110025998437107, -0.0909090406207583984612, 0.0769217118408174259129, -0.066643423247421068204, 0.0585668160968349331121, -0.0507778892612066834491, 0.0390110323660379116755, -0.0189077255845882088276, \
         0.785398163397448309615660845819875721, 0.414213562373095048801688724209698079                         \
