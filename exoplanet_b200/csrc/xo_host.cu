@@ -47,6 +47,25 @@ struct DeviceScope {
   }
 };
 
+// Per-thread pinned staging buffers: the small per-call arrays (parameters in, results out) are
+// packed through them so that each direction is ONE DMA instead of 4-5 tiny ones, and pageable
+// caller memory never meets cudaMemcpyAsync.  Grown on demand, kept for the thread's lifetime.
+struct HostStage {
+  char *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n < 65536 ? 65536 : n;
+    cudaError_t e = cudaHostAlloc((void **)&p, want, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+};
+static thread_local HostStage g_stage_in, g_stage_out;
+
 // a bump allocator over ONE stream-ordered allocation
 struct Arena {
   char *base = nullptr;
@@ -245,31 +264,49 @@ int xo_transit_model_logp_grad_host(const double *t, const double *y, const doub
   DeviceScope ds(device);
   XO_TRY(ds.err);
   const size_t ws = xo_transit_model_workspace(N, C, P);
-  Arena ar(3 * pad(N) + pad(C * P * XO_NPAR) + pad(C * XO_NSTAR) + pad(C) + 2 * pad(K) + pad(C) + pad(C * P * XO_NPAR) +
-               pad(C * XO_NSTAR) + pad(C) + pad(ws, 1),
-           ds.st);
+  const size_t nin = (size_t)C * P * XO_NPAR + (size_t)C * XO_NSTAR + (size_t)C + 2 * (size_t)K;
+  const size_t nout = (size_t)C + (size_t)C * P * XO_NPAR + (size_t)C * XO_NSTAR + (size_t)C;
+  Arena ar(3 * pad(N) + pad(nin) + pad(nout) + pad(ws, 1), ds.st);
   XO_TRY(ar.err);
   double *dt = ar.take<double>(N), *dy = ar.take<double>(N), *dv = ar.take<double>(N);
-  double *dp = ar.take<double>(C * P * XO_NPAR), *dst = ar.take<double>(C * XO_NSTAR), *dm = ar.take<double>(C);
-  double *dd = ar.take<double>(K), *dw = ar.take<double>(K);
-  double *dlp = ar.take<double>(C), *dgp = ar.take<double>(C * P * XO_NPAR), *dgs = ar.take<double>(C * XO_NSTAR),
-         *dgm = ar.take<double>(C);
+  double *din = ar.take<double>(nin), *dout = ar.take<double>(nout);
   void *dws = ar.take<char>(ws);
+  double *dp = din, *dst = dp + C * P * XO_NPAR, *dm = dst + C * XO_NSTAR, *dd = dm + C, *dw = dd + K;
+  double *dlp = dout, *dgp = dlp + C, *dgs = dgp + C * P * XO_NPAR, *dgm = dgs + C * XO_NSTAR;
+  XO_TRY(g_stage_in.ensure(nin * 8));
+  XO_TRY(g_stage_out.ensure(nout * 8));
+  // the light curve: three DMAs straight from the caller's (ideally pinned) memory
   XO_TRY(h2d(dt, t, (size_t)N * 8, ds.st));
   XO_TRY(h2d(dy, y, (size_t)N * 8, ds.st));
   XO_TRY(h2d(dv, ivar, (size_t)N * 8, ds.st));
-  XO_TRY(h2d(dp, par, (size_t)C * P * XO_NPAR * 8, ds.st));
-  XO_TRY(h2d(dst, star, (size_t)C * XO_NSTAR * 8, ds.st));
-  XO_TRY(h2d(dm, mean, (size_t)C * 8, ds.st));
-  XO_TRY(h2d(dd, dtk, (size_t)K * 8, ds.st));
-  XO_TRY(h2d(dw, wk, (size_t)K * 8, ds.st));
+  {  // the parameters: packed through pinned staging -> one DMA
+    double *hin = reinterpret_cast<double *>(g_stage_in.p);
+    size_t o = 0;
+    auto put = [&](const double *src, size_t n) {
+      memcpy(hin + o, src, n * 8);
+      o += n;
+    };
+    put(par, (size_t)C * P * XO_NPAR);
+    put(star, (size_t)C * XO_NSTAR);
+    put(mean, (size_t)C);
+    put(dtk, (size_t)K);
+    put(wk, (size_t)K);
+    XO_TRY(h2d(din, hin, nin * 8, ds.st));
+  }
   XO_RC(xo_transit_model_logp_grad(dt, dy, dv, N, dp, dst, dm, C, P, dd, dw, K, texp, use_in_transit, lognorm, nullptr, dlp,
                                    dgp, dgs, dgm, dws, ws, ds.st));
-  XO_TRY(d2h(logp, dlp, (size_t)C * 8, ds.st));
-  XO_TRY(d2h(gpar, dgp, (size_t)C * P * XO_NPAR * 8, ds.st));
-  XO_TRY(d2h(gstar, dgs, (size_t)C * XO_NSTAR * 8, ds.st));
-  XO_TRY(d2h(gmean, dgm, (size_t)C * 8, ds.st));
+  double *hout = reinterpret_cast<double *>(g_stage_out.p);
+  XO_TRY(d2h(hout, dout, nout * 8, ds.st));
   XO_TRY(cudaStreamSynchronize(ds.st));
+  size_t o = 0;
+  auto get = [&](double *dst_, size_t n) {
+    memcpy(dst_, hout + o, n * 8);
+    o += n;
+  };
+  get(logp, (size_t)C);
+  get(gpar, (size_t)C * P * XO_NPAR);
+  get(gstar, (size_t)C * XO_NSTAR);
+  get(gmean, (size_t)C);
   return 0;
 }
 
@@ -360,26 +397,40 @@ int xo_transit_model_logp_grad_resident(xo_transit_data *d, const double *par, c
   double *dp = din, *dst = dp + C * P * XO_NPAR, *dm = dst + C * XO_NSTAR, *dd = dm + C, *dw = dd + K;
   double *dlp = dout, *dgp = dlp + C, *dgs = dgp + C * P * XO_NPAR, *dgm = dgs + C * XO_NSTAR;
   cudaStream_t st = d->st;
-  int rc = 0;
-  auto copy_in = [&](double *dst_, const double *src, size_t n) {
-    if (rc == 0) rc = xo::cuda_status(cudaMemcpyAsync(dst_, src, n * 8, cudaMemcpyHostToDevice, st));
-  };
-  copy_in(dp, par, (size_t)C * P * XO_NPAR);
-  copy_in(dst, star, (size_t)C * XO_NSTAR);
-  copy_in(dm, mean, (size_t)C);
-  copy_in(dd, dtk, (size_t)K);
-  copy_in(dw, wk, (size_t)K);
+  int rc = xo::cuda_status(g_stage_in.ensure(nin * 8));
+  if (rc == 0) rc = xo::cuda_status(g_stage_out.ensure(nout * 8));
+  if (rc == 0) {
+    // pack [par | star | mean | dtk | wk] exactly as the device block is laid out -> one H2D
+    double *hin = reinterpret_cast<double *>(g_stage_in.p);
+    size_t o = 0;
+    auto put = [&](const double *src, size_t n) {
+      memcpy(hin + o, src, n * 8);
+      o += n;
+    };
+    put(par, (size_t)C * P * XO_NPAR);
+    put(star, (size_t)C * XO_NSTAR);
+    put(mean, (size_t)C);
+    put(dtk, (size_t)K);
+    put(wk, (size_t)K);
+    rc = xo::cuda_status(cudaMemcpyAsync(din, hin, nin * 8, cudaMemcpyHostToDevice, st));
+  }
   if (rc == 0)
     rc = xo_transit_model_logp_grad(d->t, d->y, d->ivar, d->N, dp, dst, dm, C, P, dd, dw, K, texp, use_in_transit, lognorm,
                                     use_moments ? d->moments : nullptr, dlp, dgp, dgs, dgm, dws, ws, st);
-  auto copy_out = [&](double *dst_, const double *src, size_t n) {
-    if (rc == 0) rc = xo::cuda_status(cudaMemcpyAsync(dst_, src, n * 8, cudaMemcpyDeviceToHost, st));
-  };
-  copy_out(logp, dlp, (size_t)C);
-  copy_out(gpar, dgp, (size_t)C * P * XO_NPAR);
-  copy_out(gstar, dgs, (size_t)C * XO_NSTAR);
-  copy_out(gmean, dgm, (size_t)C);
+  double *hout = reinterpret_cast<double *>(g_stage_out.p);
+  if (rc == 0) rc = xo::cuda_status(cudaMemcpyAsync(hout, dout, nout * 8, cudaMemcpyDeviceToHost, st));
   if (rc == 0) rc = xo::cuda_status(cudaStreamSynchronize(st));
+  if (rc == 0) {  // [logp | gpar | gstar | gmean]
+    size_t o = 0;
+    auto get = [&](double *dst_, size_t n) {
+      memcpy(dst_, hout + o, n * 8);
+      o += n;
+    };
+    get(logp, (size_t)C);
+    get(gpar, (size_t)C * P * XO_NPAR);
+    get(gstar, (size_t)C * XO_NSTAR);
+    get(gmean, (size_t)C);
+  }
   cudaSetDevice(prev);
   return rc;
 }

@@ -294,3 +294,10 @@ def test_resident_data_handle_matches_device_path():
         assert np.allclose(out[1], ref[1].cpu().numpy(), rtol=1e-9, atol=1e-9 * np.abs(out[1]).max())
         assert np.allclose(out[2], ref[2].cpu().numpy(), rtol=1e-9, atol=1e-9 * np.abs(out[2]).max())
     assert lib.xo_transit_data_destroy(h) == 0
+    # the fully stateless host call (light curve uploaded inside the call) gives the same numbers
+    out2 = [np.empty(Cn), np.empty((Cn, P, 8)), np.empty((Cn, 4)), np.empty(Cn)]
+    rc = lib.xo_transit_model_logp_grad_host(f(t), f(y), f(ivar), N, f(parh), f(starh), f(meanh), Cn, P, f(dtk), f(wk), dtk.size, 0.02, 1,
+                                             data.lognorm, *[f(x) for x in out2], 0)
+    assert rc == 0
+    for a_, b_ in zip(out, out2):
+        assert np.allclose(a_, b_, rtol=1e-9, atol=1e-9 * np.abs(a_).max())
