@@ -157,3 +157,37 @@ def test_host_buffer_entry_points_match_device_path(golden):
     Ml, Mr, flag = ops.contact_points(*[Cn[:, k] for k in range(7)])
     Mld, _, _ = ops.contact_points(*[dev(Cn[:, k]) for k in range(7)])
     assert np.array_equal(Ml, Mld.cpu().numpy())
+
+
+def test_kepler_broadcast_e_entry_point():
+    """xo_kepler_fwd_bcast: one e per `inner` consecutive M (per-planet scalar e, keplerian.py:333)."""
+    import ctypes as C
+
+    from exoplanet_b200 import _lib
+
+    lib = _lib.require_cuda()
+    rng = np.random.default_rng(2)
+    inner, blocks = 1001, 7
+    M = rng.uniform(-50, 50, inner * blocks)
+    e = rng.uniform(0, 0.9, blocks)
+    Md, ed = dev(M), dev(e)
+    sf, cf = torch.empty_like(Md), torch.empty_like(Md)
+    p = lambda x: C.c_void_p(x.data_ptr())
+    assert lib.xo_kepler_fwd_bcast(p(Md), p(ed), inner, p(sf), p(cf), Md.numel(), None) == 0
+    torch.cuda.synchronize()
+    so, co = O.kepler(M, np.repeat(e, inner))
+    assert np.max(np.abs(sf.cpu().numpy() - so)) < 5e-15 and np.max(np.abs(cf.cpu().numpy() - co)) < 5e-15
+
+
+def test_error_codes_on_device():
+    import ctypes as C
+
+    from exoplanet_b200 import _lib
+
+    lib = _lib.require_cuda()
+    x = dev(np.zeros(8))
+    p = C.c_void_p(x.data_ptr())
+    assert lib.xo_transit_logp_grad(p, p, p, 8, p, p, p, 1, 1, p, p, 1, 0.0, None, p, p, p, p, p, 8, None) == 3  # XO_EWORKSPACE
+    assert lib.xo_transit_lc_fwd(p, 8, p, p, 1, 1, p, p, 99, p, None) == 2  # stencil above XO_MAX_STENCIL
+    with pytest.raises(_lib.XoError):
+        _lib.check(3, "demo")
