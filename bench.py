@@ -34,6 +34,22 @@ ALG_BYTES_PER_CHAIN_CADENCE = 24  # t, y, sigma (SURVEY 8d / BASELINE.md section
 KEPLER_BYTES_PER_ELEMENT = 32  # M, e in; sin f, cos f out
 
 
+def _ncu_traffic(summary, kernel_tag):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu summary
+    (profiles/*.txt written by tools/ncu_summary.py from one `ncu --set full` capture), or None."""
+    path = os.path.join(ROOT, "profiles", summary)
+    if not os.path.exists(path):
+        return None
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, ok = 0.0, False
+    for line in open(path):
+        f = line.split()
+        if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and f[2] in mult:
+            tot += float(f[1]) * mult[f[2]]
+            ok = True
+    return tot if ok else None
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -512,15 +528,18 @@ def arm_ours(args):
                               "h2d_bytes_per_step": sum(h[k].numel() * 8 for k in ("par", "star", "mean", "dtk", "wk")), "d2h_bytes_per_step": d2h,
                               "api": "xo_transit_model_logp_grad_resident: light curve uploaded once (xo_transit_data_create); params in, logp+grads out per call"},
         "gpu_launches": int(os.environ.get("XO_MODEL_LAUNCHES", "3")) * args.steps,
-        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": _ncu_traffic("r01_transit.txt", "transit"), "traffic_unit": "bytes of DRAM per launch (ncu, profiles/r01_transit.txt)",
+                     "algorithmic_bytes_per_launch": ALG_BYTES_PER_CHAIN_CADENCE * C_loc * N_CADENCES,
                      "kernel": "transit_logp_grad_kernel", "peak_source": peak_src,
-                     "note": "algorithmic 24 B per (chain,cadence); chains share t,y,sigma through L2, and the kernel is fp64-pipe bound"},
+                     "note": "nominal 24 B per (chain,cadence); the chains share t,y,sigma through L2 (DRAM traffic = `traffic`), the kernel is latency/fp64-bound, not HBM-bound (DESIGN.md section 5)"},
         "clocks": clocks, "wall_s": wall,
     }
     if kep is not None:
         line["kepler"] = kep
         k = kep["e~U(0,0.95)"]
         line["kepler_roofline"] = {"bound": "hbm", "achieved": k["gb_per_s"], "peak": peak, "unit": "GB/s", "frac": k["gb_per_s"] / peak,
+                                   "traffic": _ncu_traffic("r01_kepler.txt", "kepler"), "algorithmic_bytes_per_launch": k["n"] * KEPLER_BYTES_PER_ELEMENT,
                                    "kernel": "kepler_fwd_kernel", "bytes_per_element": KEPLER_BYTES_PER_ELEMENT}
     if cpu is not None:
         line["cpu_baseline"] = cpu
