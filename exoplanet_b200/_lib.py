@@ -15,6 +15,7 @@ NGRAD = 10
 NGRAD_RV = 7
 NPAR = 8
 NSTAR = 4
+MOMENTS_LEN = 1024  # XO_MOMENTS_LEN: doubles in the buffer xo_transit_data_moments writes (8 results + scratch)
 MAX_STENCIL = 33
 MAX_PLANETS = 8
 
@@ -58,6 +59,8 @@ _SIGNATURES = {
     "xo_celerite_sho_loglike": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _dbl, _vp, _vp, _sz, _vp]),
     "xo_celerite_sho_solve_workspace": (_sz, [_i64, _i64]),
     "xo_celerite_sho_solve": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _dbl, _vp, _vp, _vp, _sz, _vp]),
+    "xo_celerite_sho_grad_workspace": (_sz, [_i64, _i64]),
+    "xo_celerite_sho_grad": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _dbl, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "xo_kepler_host": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32]),
     "xo_qsv_host": (_i32, [_vp] * 5 + [_i64, _i32]),
     "xo_contact_points_host": (_i32, [_vp] * 10 + [_i64, _i32]),

@@ -45,9 +45,8 @@ __device__ __forceinline__ Sho make_sho(double S0, double w0, double Q, double e
   return k;
 }
 
-// transition matrix over dt
-__device__ __forceinline__ void sho_phi(const Sho &k, double dt, double &f00, double &f01, double &f10, double &f11) {
-  double Cf, Sf;
+// Cf = e^{-c dt} cos(h dt) (cosh when overdamped), Sf = e^{-c dt} sin(h dt) / h (sinh)
+__device__ __forceinline__ void sho_cs(const Sho &k, double dt, double &Cf, double &Sf) {
   if (k.under) {
     double sn, cs;
     sincos(k.h * dt, &sn, &cs);
@@ -59,6 +58,12 @@ __device__ __forceinline__ void sho_phi(const Sho &k, double dt, double &f00, do
     Cf = 0.5 * (ep + en);
     Sf = 0.5 * (ep - en) / k.h;
   }
+}
+
+// transition matrix over dt
+__device__ __forceinline__ void sho_phi(const Sho &k, double dt, double &f00, double &f01, double &f10, double &f11) {
+  double Cf, Sf;
+  sho_cs(k, dt, Cf, Sf);
   f00 = fma(k.c, Sf, Cf);
   f01 = Sf;
   f10 = -k.w2 * Sf;
@@ -284,7 +289,8 @@ __global__ void __launch_bounds__(kThreadsGp) gp_loglike_kernel(const double *__
                                                                 const double *__restrict__ pref,
                                                                 const double *__restrict__ cta_state,
                                                                 double *__restrict__ cta_ll,
-                                                                double *__restrict__ rec /* [B][3][N] or null */) {
+                                                                double *__restrict__ rec /* [B][3][N] or null */,
+                                                                double *__restrict__ rec5 /* [B][5][N] or null */) {
   __shared__ double red[kWarpsGp];
   const int64_t bch = blockIdx.y;
   const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
@@ -309,6 +315,14 @@ __global__ void __launch_bounds__(kThreadsGp) gp_loglike_kernel(const double *__
       double f00, f01, f10, f11;
       sho_phi(k, ti - tprev, f00, f01, f10, f11);
       tprev = ti;
+      if (rec5) {  // state entering step i: what the reverse-mode pass (gp_grad_*) restarts from
+        double *rb = rec5 + bch * 5 * N + i;
+        rb[0] = m0;
+        rb[N] = m1;
+        rb[2 * N] = Z00;
+        rb[3 * N] = Z01;
+        rb[4 * N] = Z11;
+      }
       double c0 = f00 * m0 + f01 * m1, c1 = f10 * m0 + f11 * m1;
       double z00 = f00 * Z00 + f01 * Z01, z01 = f00 * Z01 + f01 * Z11;
       double z10 = f10 * Z00 + f11 * Z01, z11 = f10 * Z01 + f11 * Z11;
@@ -510,6 +524,343 @@ __global__ void __launch_bounds__(kThreadsGp) gp_bwd_solve_kernel(const double *
   for (int64_t i = e - 1; i >= s; --i) ab[i] = gp_bwd_step(k, t, rb, N, i, R0, R1);
 }
 
+// ---------------------------------------------------------------------------
+// Reverse-mode gradient of the log-likelihood w.r.t. (S0, w0, Q), diag[N] and y[N] -- what
+// celerite2's own reverse pass provides, here as a second parallel scan.
+//
+// Forward step i maps the state s = (m, Z) to
+//   cvec = Phi m,  Pz = Phi Z Phi^T,  k = (a - Pz00, -Pz01),  D = k0 + diag_i,  v = y_i - cvec0,
+//   l_i = -1/2 (v^2/D + log D),       m' = cvec + k v/D,       Z' = Pz + k k^T / D.
+// Its adjoint  lambda_{i-1} = J_i^T lambda_i + d l_i / d s_{i-1}  is AFFINE in the 5-vector
+// lambda = (mbar0, mbar1, Zbar00, Zbar01, Zbar11), with block-triangular J^T (mbar does not depend
+// on Zbar), so it runs as a reverse affine scan exactly like the disturbance smoother above:
+// thread g owns run T-1-g, composes its run's map (24 doubles), in-CTA shuffle scan, one CTA over
+// the CTA totals, then every thread re-walks its run backwards with the now known incoming lambda
+// and accumulates the parameter cotangents.  The forward quantities of a step are recomputed from
+// the recorded state entering it (rec5, written by gp_loglike_kernel).
+// ---------------------------------------------------------------------------
+constexpr int kAdjDoubles = 24;
+struct Adj {
+  double A[4];  // mbar_in = A mbar_out + om
+  double B[6];  // Zbar_in = B mbar_out + C Zbar_out + oz   (B 3x2, C 3x3, row-major)
+  double C[9];
+  double om[2], oz[3];
+};
+__device__ __forceinline__ Adj adj_identity() {
+  Adj a;
+  double *d = a.A;
+#pragma unroll
+  for (int i = 0; i < kAdjDoubles; ++i) d[i] = 0.0;
+  a.A[0] = a.A[3] = 1.0;
+  a.C[0] = a.C[4] = a.C[8] = 1.0;
+  return a;
+}
+// cur after prev:  lambda -> cur(prev(lambda))
+__device__ __forceinline__ Adj adj_after(const Adj &p, const Adj &c) {
+  Adj o;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) o.A[2 * r + q] = c.A[2 * r] * p.A[q] + c.A[2 * r + 1] * p.A[2 + q];
+    o.om[r] = c.A[2 * r] * p.om[0] + c.A[2 * r + 1] * p.om[1] + c.om[r];
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      o.B[2 * r + q] = c.B[2 * r] * p.A[q] + c.B[2 * r + 1] * p.A[2 + q] + c.C[3 * r] * p.B[q] + c.C[3 * r + 1] * p.B[2 + q] +
+                       c.C[3 * r + 2] * p.B[4 + q];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) o.C[3 * r + q] = c.C[3 * r] * p.C[q] + c.C[3 * r + 1] * p.C[3 + q] + c.C[3 * r + 2] * p.C[6 + q];
+    o.oz[r] = c.B[2 * r] * p.om[0] + c.B[2 * r + 1] * p.om[1] + c.C[3 * r] * p.oz[0] + c.C[3 * r + 1] * p.oz[1] +
+              c.C[3 * r + 2] * p.oz[2] + c.oz[r];
+  }
+  return o;
+}
+__device__ __forceinline__ void adj_apply(const Adj &a, double (&L)[5]) {
+  const double m0 = a.A[0] * L[0] + a.A[1] * L[1] + a.om[0], m1 = a.A[2] * L[0] + a.A[3] * L[1] + a.om[1];
+  double z[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+    z[r] = a.B[2 * r] * L[0] + a.B[2 * r + 1] * L[1] + a.C[3 * r] * L[2] + a.C[3 * r + 1] * L[3] + a.C[3 * r + 2] * L[4] + a.oz[r];
+  L[0] = m0;
+  L[1] = m1;
+  L[2] = z[0];
+  L[3] = z[1];
+  L[4] = z[2];
+}
+__device__ __forceinline__ Adj adj_shfl_up(const Adj &a, int d) {
+  Adj o;
+  const double *src = a.A;
+  double *dst = o.A;
+#pragma unroll
+  for (int k = 0; k < kAdjDoubles; ++k) dst[k] = __shfl_up_sync(kFullGp, src[k], d);
+  return o;
+}
+__device__ __forceinline__ void adj_store(double *p, const Adj &a) {
+  const double *src = a.A;
+#pragma unroll
+  for (int k = 0; k < kAdjDoubles; ++k) p[k] = src[k];
+}
+__device__ __forceinline__ Adj adj_load(const double *p) {
+  Adj a;
+  double *dst = a.A;
+#pragma unroll
+  for (int k = 0; k < kAdjDoubles; ++k) dst[k] = p[k];
+  return a;
+}
+__device__ Adj adj_cta_inclusive_scan(Adj v, Adj *warp_tot) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 1
+  for (int d = 1; d < 32; d <<= 1) {
+    Adj o = adj_shfl_up(v, d);
+    if (lane >= d) v = adj_after(o, v);
+  }
+  if (lane == 31) warp_tot[warp] = v;
+  __syncthreads();
+  if (warp > 0) {
+    Adj pre = warp_tot[0];
+    for (int w = 1; w < warp; ++w) pre = adj_after(pre, warp_tot[w]);
+    v = adj_after(pre, v);
+  }
+  return v;
+}
+
+// forward quantities of step i, recomputed from the recorded state entering it
+struct StepFwd {
+  double f00, f01, f10, f11, Cf, Sf, dt;
+  double m0, m1;
+  double w00, w01, w10, w11;  // W = Phi Z
+  double k0, k1, rD, w;       // k, 1/D, v/D
+};
+__device__ __forceinline__ StepFwd gp_step_fwd(const Sho &k, const double *__restrict__ t, const double *__restrict__ yb,
+                                               const double *__restrict__ diag, const double *__restrict__ r5, int64_t N,
+                                               int64_t i) {
+  StepFwd s;
+  s.dt = i > 0 ? __ldg(t + i) - __ldg(t + i - 1) : 0.0;
+  sho_cs(k, s.dt, s.Cf, s.Sf);
+  s.f00 = fma(k.c, s.Sf, s.Cf);
+  s.f01 = s.Sf;
+  s.f10 = -k.w2 * s.Sf;
+  s.f11 = fma(-k.c, s.Sf, s.Cf);
+  s.m0 = __ldg(r5 + i);
+  s.m1 = __ldg(r5 + N + i);
+  const double Z00 = __ldg(r5 + 2 * N + i), Z01 = __ldg(r5 + 3 * N + i), Z11 = __ldg(r5 + 4 * N + i);
+  s.w00 = s.f00 * Z00 + s.f01 * Z01;
+  s.w01 = s.f00 * Z01 + s.f01 * Z11;
+  s.w10 = s.f10 * Z00 + s.f11 * Z01;
+  s.w11 = s.f10 * Z01 + s.f11 * Z11;
+  const double p00 = s.w00 * s.f00 + s.w01 * s.f01, p01 = s.w00 * s.f10 + s.w01 * s.f11;
+  s.k0 = k.a - p00;
+  s.k1 = -p01;
+  s.rD = 1.0 / (s.k0 + __ldg(diag + i));
+  s.w = (__ldg(yb + i) - (s.f00 * s.m0 + s.f01 * s.m1)) * s.rD;
+  return s;
+}
+
+// lambda_i -> lambda_{i-1}.  kForce: include d l_i / d(v, D) (the affine part); kAcc: also return
+// acc = (vbar, Dbar, abar, Phibar00, Phibar01, Phibar10, Phibar11) of this step.
+template <bool kForce, bool kAcc>
+__device__ __forceinline__ void gp_step_adj(const StepFwd &s, double (&L)[5], double *acc) {
+  const double mb0 = L[0], mb1 = L[1], zb00 = L[2], zb01 = L[3], zb11 = L[4];
+  const double km = s.k0 * mb0 + s.k1 * mb1;
+  const double q = zb00 * s.k0 * s.k0 + zb01 * s.k0 * s.k1 + zb11 * s.k1 * s.k1;
+  double vbar = km * s.rD;
+  double Dbar = -(km * s.w + q * s.rD) * s.rD;
+  if (kForce) {
+    vbar -= s.w;
+    Dbar += 0.5 * (s.w * s.w - s.rD);
+  }
+  const double kb0 = mb0 * s.w + (2.0 * zb00 * s.k0 + zb01 * s.k1) * s.rD;
+  const double kb1 = mb1 * s.w + (zb01 * s.k0 + 2.0 * zb11 * s.k1) * s.rD;
+  const double cb0 = mb0 - vbar, cb1 = mb1;
+  const double pb00 = zb00 - kb0 - Dbar, hb = 0.5 * (zb01 - kb1), pb11 = zb11;
+  // Zbar = Phi^T Sbar Phi, Sbar = [[pb00, hb], [hb, pb11]]
+  const double u00 = pb00 * s.f00 + hb * s.f10, u01 = pb00 * s.f01 + hb * s.f11;
+  const double u10 = hb * s.f00 + pb11 * s.f10, u11 = hb * s.f01 + pb11 * s.f11;
+  L[2] = s.f00 * u00 + s.f10 * u10;
+  L[3] = 2.0 * (s.f00 * u01 + s.f10 * u11);
+  L[4] = s.f01 * u01 + s.f11 * u11;
+  L[0] = s.f00 * cb0 + s.f10 * cb1;
+  L[1] = s.f01 * cb0 + s.f11 * cb1;
+  if (kAcc) {
+    acc[0] = vbar;
+    acc[1] = Dbar;
+    acc[2] = kb0 + Dbar;
+    // Phibar = cbar m^T + 2 Sbar W
+    acc[3] = cb0 * s.m0 + 2.0 * (pb00 * s.w00 + hb * s.w10);
+    acc[4] = cb0 * s.m1 + 2.0 * (pb00 * s.w01 + hb * s.w11);
+    acc[5] = cb1 * s.m0 + 2.0 * (hb * s.w00 + pb11 * s.w10);
+    acc[6] = cb1 * s.m1 + 2.0 * (hb * s.w01 + pb11 * s.w11);
+  }
+}
+
+__global__ void __launch_bounds__(kThreadsGp) gp_grad_aggregate_kernel(const double *__restrict__ t,
+                                                                       const double *__restrict__ y,
+                                                                       const double *__restrict__ diag, int64_t N,
+                                                                       const double *__restrict__ S0,
+                                                                       const double *__restrict__ w0,
+                                                                       const double *__restrict__ Qf, double eps,
+                                                                       int64_t T, const double *__restrict__ rec5,
+                                                                       double *__restrict__ gpref,
+                                                                       double *__restrict__ gcta) {
+  __shared__ Adj warp_tot[kWarpsGp];
+  const int64_t bch = blockIdx.y;
+  const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
+  const int64_t g = (int64_t)blockIdx.x * kThreadsGp + threadIdx.x;
+  const int64_t run = T - 1 - g;  // reversed ownership
+  Adj v = adj_identity();
+  if (run >= 0) {
+    const int64_t s = run * kRun, e = min(s + kRun, N);
+    const double *yb = y + bch * N, *r5 = rec5 + bch * 5 * N;
+    // the run's map lambda_{e-1} -> lambda_{s-1}: push the origin (with the forcing) and the five
+    // basis vectors (linear part) through it
+    double O[5] = {0, 0, 0, 0, 0}, X0[5] = {1, 0, 0, 0, 0}, X1[5] = {0, 1, 0, 0, 0}, X2[5] = {0, 0, 1, 0, 0},
+           X3[5] = {0, 0, 0, 1, 0}, X4[5] = {0, 0, 0, 0, 1};
+    for (int64_t i = e - 1; i >= s; --i) {
+      const StepFwd f = gp_step_fwd(k, t, yb, diag, r5, N, i);
+      gp_step_adj<true, false>(f, O, nullptr);
+      gp_step_adj<false, false>(f, X0, nullptr);
+      gp_step_adj<false, false>(f, X1, nullptr);
+      gp_step_adj<false, false>(f, X2, nullptr);
+      gp_step_adj<false, false>(f, X3, nullptr);
+      gp_step_adj<false, false>(f, X4, nullptr);
+    }
+    v.A[0] = X0[0]; v.A[1] = X1[0]; v.A[2] = X0[1]; v.A[3] = X1[1];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      v.B[2 * r] = X0[2 + r];
+      v.B[2 * r + 1] = X1[2 + r];
+      v.C[3 * r] = X2[2 + r];
+      v.C[3 * r + 1] = X3[2 + r];
+      v.C[3 * r + 2] = X4[2 + r];
+      v.oz[r] = O[2 + r];
+    }
+    v.om[0] = O[0];
+    v.om[1] = O[1];
+  }
+  v = adj_cta_inclusive_scan(v, warp_tot);
+  if (g < T) adj_store(gpref + (bch * T + g) * kAdjDoubles, v);
+  if (threadIdx.x == kThreadsGp - 1) adj_store(gcta + (bch * gridDim.x + blockIdx.x) * kAdjDoubles, v);
+}
+
+// lambda entering each CTA (from the right): exclusive scan of the CTA totals applied to lambda = 0
+__global__ void __launch_bounds__(kThreadsGp) gp_grad_cta_scan_kernel(const double *__restrict__ gcta, int nctas,
+                                                                      double *__restrict__ gstate) {
+  __shared__ Adj warp_tot[kWarpsGp];
+  __shared__ Adj lastlane[kWarpsGp];
+  __shared__ Adj carry_s;
+  const int64_t bch = blockIdx.x;
+  Adj carry = adj_identity();
+  for (int base = 0; base < nctas; base += kThreadsGp) {
+    const int idx = base + threadIdx.x;
+    Adj v = idx < nctas ? adj_load(gcta + (bch * nctas + idx) * kAdjDoubles) : adj_identity();
+    v = adj_cta_inclusive_scan(v, warp_tot);
+    Adj incl = adj_after(carry, v);
+    Adj prev = adj_shfl_up(incl, 1);
+    if ((threadIdx.x & 31) == 31) lastlane[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) prev = threadIdx.x == 0 ? carry : lastlane[(threadIdx.x >> 5) - 1];
+    if (idx < nctas) {
+      double *o = gstate + (bch * nctas + idx) * 5;
+      o[0] = prev.om[0];
+      o[1] = prev.om[1];
+      o[2] = prev.oz[0];
+      o[3] = prev.oz[1];
+      o[4] = prev.oz[2];
+    }
+    if (threadIdx.x == kThreadsGp - 1) carry_s = incl;
+    __syncthreads();
+    carry = carry_s;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kThreadsGp) gp_grad_final_kernel(const double *__restrict__ t,
+                                                                   const double *__restrict__ y,
+                                                                   const double *__restrict__ diag, int64_t N,
+                                                                   const double *__restrict__ S0,
+                                                                   const double *__restrict__ w0,
+                                                                   const double *__restrict__ Qf, double eps, int64_t T,
+                                                                   const double *__restrict__ rec5,
+                                                                   const double *__restrict__ gpref,
+                                                                   const double *__restrict__ gstate,
+                                                                   double *__restrict__ gy, double *__restrict__ gdiag,
+                                                                   double *__restrict__ gpart /* [B][nctas][4] */) {
+  __shared__ double red[4][kWarpsGp];
+  const int64_t bch = blockIdx.y;
+  const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
+  const int64_t g = (int64_t)blockIdx.x * kThreadsGp + threadIdx.x;
+  const int64_t run = T - 1 - g;
+  double ga = 0.0, gc = 0.0, gh = 0.0, gw2 = 0.0;  // cotangents of a, c, h and w2 = c^2 +- h^2
+  if (run >= 0) {
+    const int64_t s = run * kRun, e = min(s + kRun, N);
+    const double *st = gstate + (bch * gridDim.x + blockIdx.x) * 5;
+    double L[5] = {st[0], st[1], st[2], st[3], st[4]};
+    if (threadIdx.x > 0) adj_apply(adj_load(gpref + (bch * T + g - 1) * kAdjDoubles), L);
+    const double *yb = y + bch * N, *r5 = rec5 + bch * 5 * N;
+    for (int64_t i = e - 1; i >= s; --i) {
+      const StepFwd f = gp_step_fwd(k, t, yb, diag, r5, N, i);
+      double acc[7];
+      gp_step_adj<true, true>(f, L, acc);
+      if (gy) gy[bch * N + i] = acc[0];
+      if (gdiag) gdiag[bch * N + i] = acc[1];
+      ga += acc[2];
+      // Phi = [[Cf + c Sf, Sf], [-w2 Sf, Cf - c Sf]]
+      const double d0011 = acc[3] - acc[6];
+      const double Cb = acc[3] + acc[6];
+      const double Sb = k.c * d0011 + acc[4] - k.w2 * acc[5];
+      gc += f.Sf * d0011 - f.dt * (f.Cf * Cb + f.Sf * Sb);
+      gw2 -= f.Sf * acc[5];
+      const double dCdh = (k.under ? -f.dt : f.dt) * k.h * f.Sf;
+      gh += dCdh * Cb + (f.dt * f.Cf - f.Sf) / k.h * Sb;
+    }
+  }
+  double vals[4] = {ga, gc, gh, gw2};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    double v = vals[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullGp, v, o);
+    if ((threadIdx.x & 31) == 0) red[j][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double s4 = 0.0;
+    for (int w = 0; w < kWarpsGp; ++w) s4 += red[threadIdx.x][w];
+    gpart[(bch * gridDim.x + blockIdx.x) * 4 + threadIdx.x] = s4;
+  }
+}
+
+// fold the per-CTA cotangents of (a, c, h, w2) in CTA order and chain them to (S0, w0, Q):
+//   a = S0 w0 Q,  c = w0 / (2Q),  h = c f,  f = sqrt(max(+-(4Q^2 - 1), eps)),  w2 = c^2 +- h^2
+__global__ void gp_grad_fold_kernel(const double *__restrict__ gpart, int nctas, const double *__restrict__ S0,
+                                    const double *__restrict__ w0, const double *__restrict__ Qf, double eps, int64_t B,
+                                    double *__restrict__ ghyper /* [B][3] */) {
+  const int64_t bch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (bch >= B) return;
+  double ga = 0.0, gc = 0.0, gh = 0.0, gw2 = 0.0;
+  for (int i = 0; i < nctas; ++i) {
+    const double *p = gpart + (bch * nctas + i) * 4;
+    ga += p[0];
+    gc += p[1];
+    gh += p[2];
+    gw2 += p[3];
+  }
+  const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
+  const double sgn = k.under ? 1.0 : -1.0;
+  gc += 2.0 * k.c * gw2;
+  gh += sgn * 2.0 * k.h * gw2;
+  const double s0 = S0[bch], w = w0[bch], Q = Qf[bch];
+  const double arg = sgn * (4.0 * Q * Q - 1.0);
+  const double f = sqrt(fmax(arg, eps));
+  const double dfdQ = arg > eps ? sgn * 4.0 * Q / f : 0.0;
+  const double dcdQ = -k.c / Q;
+  ghyper[3 * bch + 0] = ga * w * Q;
+  ghyper[3 * bch + 1] = ga * s0 * Q + gc * (0.5 / Q) + gh * (0.5 / Q) * f;
+  ghyper[3 * bch + 2] = ga * s0 * w + gc * dcdQ + gh * (dcdQ * f + k.c * dfdQ);
+}
+
 __global__ void gp_fold_kernel(const double *__restrict__ cta_ll, int nctas, int64_t N, int64_t B,
                                double *__restrict__ loglike) {
   const int64_t bch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -522,9 +873,10 @@ __global__ void gp_fold_kernel(const double *__restrict__ cta_ll, int nctas, int
 struct GpLayout {
   int64_t T;      // runs (threads) per chain
   int nctas;      // CTAs per chain
-  size_t off_pref, off_tot, off_state, off_ll, off_rec, off_bpref, off_bcta, off_bstate, bytes;
+  size_t off_pref, off_tot, off_state, off_ll, off_rec, off_bpref, off_bcta, off_bstate, off_rec5, off_gpref, off_gcta, off_gstate,
+      off_gpart, bytes;
 };
-inline GpLayout gp_layout(int64_t N, int64_t B, bool solve = false) {
+inline GpLayout gp_layout(int64_t N, int64_t B, bool solve = false, bool grad = false) {
   GpLayout L;
   L.T = (N + kRun - 1) / kRun;
   L.nctas = (int)((L.T + kThreadsGp - 1) / kThreadsGp);
@@ -544,6 +896,14 @@ inline GpLayout gp_layout(int64_t N, int64_t B, bool solve = false) {
     L.off_bpref = take((size_t)B * L.T * 6);
     L.off_bcta = take((size_t)B * L.nctas * 6);
     L.off_bstate = take((size_t)B * L.nctas * 2);
+  }
+  L.off_rec5 = L.off_gpref = L.off_gcta = L.off_gstate = L.off_gpart = 0;
+  if (grad) {
+    L.off_rec5 = take((size_t)B * 5 * N);
+    L.off_gpref = take((size_t)B * L.T * kAdjDoubles);
+    L.off_gcta = take((size_t)B * L.nctas * kAdjDoubles);
+    L.off_gstate = take((size_t)B * L.nctas * 5);
+    L.off_gpart = take((size_t)B * L.nctas * 4);
   }
   L.bytes = o;
   return L;
@@ -577,7 +937,7 @@ int xo_celerite_sho_loglike(const double *t, const double *y, const double *diag
   dim3 grid(L.nctas, (unsigned)B);
   gp_aggregate_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, pref, tot);
   gp_cta_scan_kernel<<<(unsigned)B, kThreadsGp, 0, st>>>(tot, L.nctas, S0, w0, Q, eps, state);
-  gp_loglike_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, pref, state, ll, nullptr);
+  gp_loglike_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, pref, state, ll, nullptr, nullptr);
   gp_fold_kernel<<<(unsigned)((B + 63) / 64), 64, 0, st>>>(ll, L.nctas, N, B, loglike);
   return xo::launch_status();
 }
@@ -606,13 +966,48 @@ int xo_celerite_sho_solve(const double *t, const double *y, const double *diag, 
   gp_aggregate_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, at(L.off_pref), at(L.off_tot));
   gp_cta_scan_kernel<<<(unsigned)B, kThreadsGp, 0, st>>>(at(L.off_tot), L.nctas, S0, w0, Q, eps, at(L.off_state));
   gp_loglike_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, at(L.off_pref), at(L.off_state),
-                                                 at(L.off_ll), at(L.off_rec));
+                                                 at(L.off_ll), at(L.off_rec), nullptr);
   gp_fold_kernel<<<(unsigned)((B + 63) / 64), 64, 0, st>>>(at(L.off_ll), L.nctas, N, B, loglike);
   gp_bwd_aggregate_kernel<<<grid, kThreadsGp, 0, st>>>(t, N, S0, w0, Q, eps, L.T, at(L.off_rec), at(L.off_bpref),
                                                        at(L.off_bcta));
   gp_bwd_cta_scan_kernel<<<(unsigned)B, kThreadsGp, 0, st>>>(at(L.off_bcta), L.nctas, at(L.off_bstate));
   gp_bwd_solve_kernel<<<grid, kThreadsGp, 0, st>>>(t, N, S0, w0, Q, eps, L.T, at(L.off_rec), at(L.off_bpref),
                                                    at(L.off_bstate), alpha);
+  return xo::launch_status();
+}
+
+size_t xo_celerite_sho_grad_workspace(int64_t N, int64_t B) {
+  if (N <= 0 || B <= 0) return 0;
+  return gp_layout(N, B, false, true).bytes;
+}
+
+// log-likelihood and its exact reverse-mode gradient: ghyper[B][3] = d/d(S0, w0, Q), and (each
+// optional) gy[B][N] = d/dy (= -K^-1 y), gdiag[B][N] = d/d diag.
+int xo_celerite_sho_grad(const double *t, const double *y, const double *diag, int64_t N, const double *S0,
+                         const double *w0, const double *Q, int64_t B, double eps, double *loglike, double *ghyper,
+                         double *gy, double *gdiag, void *workspace, size_t workspace_bytes, void *stream) {
+  if (N < 0 || B < 0) return XO_EINVAL;
+  if (B == 0) return 0;
+  if (N == 0) return XO_EINVAL;
+  if (B > 65535) return XO_ERANGE;
+  if (!t || !y || !diag || !S0 || !w0 || !Q || !loglike || !ghyper || !workspace) return XO_EINVAL;
+  GpLayout L = gp_layout(N, B, false, true);
+  if (workspace_bytes < L.bytes) return XO_EWORKSPACE;
+  char *ws = static_cast<char *>(workspace);
+  auto at = [&](size_t off) { return reinterpret_cast<double *>(ws + off); };
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid(L.nctas, (unsigned)B);
+  gp_aggregate_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, at(L.off_pref), at(L.off_tot));
+  gp_cta_scan_kernel<<<(unsigned)B, kThreadsGp, 0, st>>>(at(L.off_tot), L.nctas, S0, w0, Q, eps, at(L.off_state));
+  gp_loglike_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, at(L.off_pref), at(L.off_state),
+                                                 at(L.off_ll), nullptr, at(L.off_rec5));
+  gp_fold_kernel<<<(unsigned)((B + 63) / 64), 64, 0, st>>>(at(L.off_ll), L.nctas, N, B, loglike);
+  gp_grad_aggregate_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, at(L.off_rec5), at(L.off_gpref),
+                                                        at(L.off_gcta));
+  gp_grad_cta_scan_kernel<<<(unsigned)B, kThreadsGp, 0, st>>>(at(L.off_gcta), L.nctas, at(L.off_gstate));
+  gp_grad_final_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, at(L.off_rec5), at(L.off_gpref),
+                                                    at(L.off_gstate), gy, gdiag, at(L.off_gpart));
+  gp_grad_fold_kernel<<<(unsigned)((B + 63) / 64), 64, 0, st>>>(at(L.off_gpart), L.nctas, S0, w0, Q, eps, B, ghyper);
   return xo::launch_status();
 }
 

@@ -228,7 +228,7 @@ int xo_transit_logp_grad_host(const double *t, const double *y, const double *iv
   XO_TRY(ds.err);
   const size_t ws = xo_transit_logp_grad_workspace(N, C, P);
   Arena ar(3 * pad(N) + pad(C * P * XO_NEL) + pad(3 * C) + pad(C) + 2 * pad(K) + pad(C) + pad(C * P * XO_NGRAD) +
-               pad(3 * C) + pad(C) + pad(ws, 1),
+               pad(3 * C) + pad(C) + pad(XO_MOMENTS_LEN) + pad(ws, 1),
            ds.st);
   XO_TRY(ar.err);
   double *dt = ar.take<double>(N), *dy = ar.take<double>(N), *dv = ar.take<double>(N);
@@ -236,6 +236,7 @@ int xo_transit_logp_grad_host(const double *t, const double *y, const double *iv
   double *dd = ar.take<double>(K), *dw = ar.take<double>(K);
   double *dlp = ar.take<double>(C), *dge = ar.take<double>(C * P * XO_NGRAD), *dgc = ar.take<double>(3 * C),
          *dgm = ar.take<double>(C);
+  double *dmom = ar.take<double>(XO_MOMENTS_LEN);
   void *dws = ar.take<char>(ws);
   XO_TRY(h2d(dt, t, (size_t)N * 8, ds.st));
   XO_TRY(h2d(dy, y, (size_t)N * 8, ds.st));
@@ -245,7 +246,9 @@ int xo_transit_logp_grad_host(const double *t, const double *y, const double *iv
   XO_TRY(h2d(dm, mean, (size_t)C * 8, ds.st));
   XO_TRY(h2d(dd, dtk, (size_t)K * 8, ds.st));
   XO_TRY(h2d(dw, wk, (size_t)K * 8, ds.st));
-  XO_RC(xo_transit_logp_grad(dt, dy, dv, N, del, dcl, dm, C, P, dd, dw, K, lognorm, nullptr, dlp, dge, dgc, dgm, dws, ws, ds.st));
+  // data moments (one pass, a few microseconds): the sweep then reads t only and skips quiet steps
+  XO_RC(xo_transit_data_moments(dt, dy, dv, N, dmom, ds.st));
+  XO_RC(xo_transit_logp_grad(dt, dy, dv, N, del, dcl, dm, C, P, dd, dw, K, lognorm, dmom, dlp, dge, dgc, dgm, dws, ws, ds.st));
   XO_TRY(d2h(logp, dlp, (size_t)C * 8, ds.st));
   XO_TRY(d2h(gel, dge, (size_t)C * P * XO_NGRAD * 8, ds.st));
   XO_TRY(d2h(gcl, dgc, (size_t)C * 3 * 8, ds.st));
@@ -266,10 +269,11 @@ int xo_transit_model_logp_grad_host(const double *t, const double *y, const doub
   const size_t ws = xo_transit_model_workspace(N, C, P);
   const size_t nin = (size_t)C * P * XO_NPAR + (size_t)C * XO_NSTAR + (size_t)C + 2 * (size_t)K;
   const size_t nout = (size_t)C + (size_t)C * P * XO_NPAR + (size_t)C * XO_NSTAR + (size_t)C;
-  Arena ar(3 * pad(N) + pad(nin) + pad(nout) + pad(ws, 1), ds.st);
+  Arena ar(3 * pad(N) + pad(nin) + pad(nout) + pad(XO_MOMENTS_LEN) + pad(ws, 1), ds.st);
   XO_TRY(ar.err);
   double *dt = ar.take<double>(N), *dy = ar.take<double>(N), *dv = ar.take<double>(N);
   double *din = ar.take<double>(nin), *dout = ar.take<double>(nout);
+  double *dmom = ar.take<double>(XO_MOMENTS_LEN);
   void *dws = ar.take<char>(ws);
   double *dp = din, *dst = dp + C * P * XO_NPAR, *dm = dst + C * XO_NSTAR, *dd = dm + C, *dw = dd + K;
   double *dlp = dout, *dgp = dlp + C, *dgs = dgp + C * P * XO_NPAR, *dgm = dgs + C * XO_NSTAR;
@@ -293,7 +297,8 @@ int xo_transit_model_logp_grad_host(const double *t, const double *y, const doub
     put(wk, (size_t)K);
     XO_TRY(h2d(din, hin, nin * 8, ds.st));
   }
-  XO_RC(xo_transit_model_logp_grad(dt, dy, dv, N, dp, dst, dm, C, P, dd, dw, K, texp, use_in_transit, lognorm, nullptr, dlp,
+  XO_RC(xo_transit_data_moments(dt, dy, dv, N, dmom, ds.st));
+  XO_RC(xo_transit_model_logp_grad(dt, dy, dv, N, dp, dst, dm, C, P, dd, dw, K, texp, use_in_transit, lognorm, dmom, dlp,
                                    dgp, dgs, dgm, dws, ws, ds.st));
   double *hout = reinterpret_cast<double *>(g_stage_out.p);
   XO_TRY(d2h(hout, dout, nout * 8, ds.st));
@@ -332,7 +337,7 @@ int xo_transit_data_create(const double *t, const double *y, const double *ivar,
   d->N = N;
   cudaError_t e = cudaStreamCreateWithFlags(&d->st, cudaStreamNonBlocking);
   const size_t nb = (size_t)N * 8;
-  if (e == cudaSuccess) e = cudaMalloc((void **)&d->t, 3 * nb + 64);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d->t, 3 * nb + XO_MOMENTS_LEN * 8);
   if (e == cudaSuccess) {
     d->y = d->t + N;
     d->ivar = d->y + N;

@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
   __shared__ uint32_t queue[kWarps][XO_MAX_PLANETS][kQueue];
   __shared__ double gacc[kWarps][XO_MAX_PLANETS][XO_NGRAD];
   __shared__ double lacc[XO_NGRAD + 3][kThreads];  // per-thread gradient accumulators of one drain
+  __shared__ double pacc[XO_NGRAD][kThreads];      // per-thread cotangent-scaled sums of the current planet
   // heaviest chains first (ma.order, optional): CTAs are dispatched in blockIdx order, so the long
   // ones start early and the short ones fill the tail of the launch
   const int64_t c = ma.order ? ma.order[blockIdx.y] : blockIdx.y;
@@ -171,9 +172,27 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
   for (int i = lane; i < XO_MAX_PLANETS * XO_NGRAD; i += 32) (&gacc[warp][0][0])[i] = 0.0;
 #pragma unroll
   for (int j = 0; j < XO_NGRAD + 3; ++j) lacc[j][threadIdx.x] = 0.0;
+#pragma unroll
+  for (int j = 0; j < XO_NGRAD; ++j) pacc[j][threadIdx.x] = 0.0;
   __syncwarp();
   double *const gl = &lacc[0][threadIdx.x];          // g[j]  at gl[j * kThreads]
   double *const gsl = &lacc[XO_NGRAD][threadIdx.x];  // gs[j] at gsl[j * kThreads]
+  double *const pa = &pacc[0][threadIdx.x];          // sum over this lane's samples of scale * g[j]
+  int pcur = -1;                                     // planet whose sums pa[] currently holds (warp-uniform)
+  // lane sums -> gacc[warp][p] with a fixed-order shuffle tree; runs when the drained planet
+  // changes and once at the end, not once per drain
+  auto flush = [&](int p) {
+#pragma unroll 1
+    for (int j = 0; j < XO_NGRAD; ++j) {
+      if (j == 1 || j == 7) continue;  // d/dtref == d/dt0; sin i carries no gradient
+      const double v = warp_sum(pa[j * kThreads]);
+      pa[j * kThreads] = 0.0;
+      if (lane == 0) {
+        gacc[warp][p][j] += v;
+        if (j == 0) gacc[warp][p][1] += v;
+      }
+    }
+  };
 
   const int nacc = kNBase + P * XO_NGRAD;
   double lp = 0.0, gm = 0.0, gc0 = 0.0, gc1 = 0.0, gc2 = 0.0;
@@ -183,8 +202,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
 
   // evaluate m (<= 32) queued entries of planet p starting at queue offset off
   auto drain = [&](int p, int off, int m) {
-    double scale = 0.0;  // cotangent multiplying this lane's accumulated d lc / d elements
+    if (p != pcur) {
+      if (pcur >= 0) flush(pcur);
+      pcur = p;
+    }
     if (lane < m) {
+      double scale;  // cotangent multiplying this lane's accumulated d lc / d elements
       const uint32_t idx = queue[warp][p][off + lane];
       const double tt = __ldg(t + idx);
       // issued now so that their latency hides behind the sample evaluation
@@ -217,18 +240,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
       gc1 = fma(scale, gsl[kThreads], gc1);
       gc2 = fma(scale, gsl[2 * kThreads], gc2);
       gsl[0] = gsl[kThreads] = gsl[2 * kThreads] = 0.0;
-    }
 #pragma unroll
-    for (int j = 0; j < XO_NGRAD; ++j) {
-      if (j == 1 || j == 7) continue;  // d/dtref == d/dt0; sin i carries no gradient
-      double v = warp_sum(scale * gl[j * kThreads]);
-      gl[j * kThreads] = 0.0;
-      if (lane == 0) {
-        gacc[warp][p][j] += v;
-        if (j == 0) gacc[warp][p][1] += v;
+      for (int j = 0; j < XO_NGRAD; ++j) {
+        if (j == 1 || j == 7) continue;
+        pa[j * kThreads] = fma(scale, gl[j * kThreads], pa[j * kThreads]);
+        gl[j * kThreads] = 0.0;
       }
+      gl[kThreads] = 0.0;
     }
-    gl[kThreads] = 0.0;
   };
 
   const uint32_t start = (uint32_t)min((int64_t)slot * L, N);
@@ -239,35 +258,44 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
   // kUnroll coalesced loads, 4 flops + 2 compares per cadence and planet, one vote.
   const bool sorted = kMoments && moments[4] != 0.0;  // t non-decreasing: steps can be skipped wholesale
   const double *tp = t + lane;
-  // sorted mode: lane l holds the first/last time of step l of the current group of 32 steps
-  // (two loads per lane per 4096 cadences instead of two dependent broadcast loads per step)
-  double edgeA = 0.0, edgeB = 0.0;
-  uint32_t step = 0;
+  constexpr uint32_t kStep = 32 * kUnroll;
+  // Steps are taken 32 at a time: lane l decides whether step l of the group can contain an
+  // in-transit cadence (sorted t: the step spans [tA, tB]; if that interval misses every planet's
+  // window in phase, with wrap, no cadence of it is in transit), one ballot gives the group's hit
+  // mask, and only the set bits are visited.  Unsorted t: every existing step is a hit.
+  uint32_t gnext = start, gcur = start, hitmask = 0u;
 #pragma unroll 1
-  for (uint32_t base = start;; base += 32 * kUnroll, ++step) {
-    const bool last = base >= end;
+  for (;;) {
+    bool last = false;
+    uint32_t base = 0u;
+    if (hitmask == 0u) {
+      if (gnext >= end) {
+        last = true;
+      } else {
+        const uint32_t sb = gnext + lane * kStep;
+        bool hit = sb < end;
+        if (sorted && hit) {
+          const double tA = __ldg(t + sb), tB = __ldg(t + min(sb + kStep, end) - 1);
+          hit = false;
+          for (int p = 0; p < P; ++p) {
+            const double rpp = sm.rperiod[p];
+            const double uA = (tA - sm.elem[p][XO_EL_T0]) * rpp;
+            const double a = uA - rint(uA), b = a + (tB - tA) * rpp;  // phase interval, a in [-1/2, 1/2]
+            const double lo = sm.wlo[p] - 1e-9, hi = sm.whi[p] + 1e-9;
+            hit |= (b - a >= 1.0) | ((a <= hi) & (b >= lo)) | ((a <= hi + 1.0) & (b >= lo + 1.0)) | ((a <= hi - 1.0) & (b >= lo - 1.0));
+          }
+        }
+        hitmask = __ballot_sync(kFull, hit);
+        gcur = gnext;
+        gnext = (end - gnext > 32u * kStep) ? gnext + 32u * kStep : end;
+        if (hitmask == 0u) continue;
+      }
+    }
     double tt[kUnroll], yy[kUnroll], iv[kUnroll];
     uint32_t valid = 0u;  // bit u: cadence base + 32 u + lane exists
     if (!last) {
-      if (sorted) {
-        // the step spans [tA, tB]; if that interval misses every planet's window (in phase, with
-        // wrap) no lane can be in transit -> skip the step after two broadcast loads
-        if ((step & 31u) == 0u) {
-          const uint32_t sb = base + lane * (32 * kUnroll);
-          edgeA = sb < end ? __ldg(t + sb) : 0.0;
-          edgeB = sb < end ? __ldg(t + min(sb + 32 * kUnroll, end) - 1) : 0.0;
-        }
-        const double tA = __shfl_sync(kFull, edgeA, step & 31u), tB = __shfl_sync(kFull, edgeB, step & 31u);
-        bool hit = false;
-        for (int p = 0; p < P; ++p) {
-          const double rpp = sm.rperiod[p];
-          const double uA = (tA - sm.elem[p][XO_EL_T0]) * rpp;
-          const double a = uA - rint(uA), b = a + (tB - tA) * rpp;  // phase interval, a in [-1/2, 1/2]
-          const double lo = sm.wlo[p] - 1e-9, hi = sm.whi[p] + 1e-9;
-          hit |= (b - a >= 1.0) | ((a <= hi) & (b >= lo)) | ((a <= hi + 1.0) & (b >= lo + 1.0)) | ((a <= hi - 1.0) & (b >= lo - 1.0));
-        }
-        if (!hit) continue;
-      }
+      base = gcur + (uint32_t)(__ffs(hitmask) - 1) * kStep;
+      hitmask &= hitmask - 1u;
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {  // kUnroll coalesced loads in flight together
         const bool v = base + 32 * u + lane < end;
@@ -338,6 +366,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
     }
     if (last) break;
   }
+  if (pcur >= 0) flush(pcur);
   if (kMoments && slot == 0 && lane == 0) {  // out-of-transit Gaussian terms from the data moments
     const double m = mean_c - moments[0];
     lp += -0.5 * (moments[3] - 2.0 * m * moments[2] + m * m * moments[1]);
@@ -374,59 +403,72 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
   }
 }
 
-// data-only moments of the Gaussian likelihood, one CTA, fixed-order tree (deterministic):
-// out = (y_ref, S1, Sy, Syy, sorted) with y_ref the ivar-weighted mean of y and sorted = 1 when
-// t is non-decreasing (lets the sweep skip whole 128-cadence steps with one interval test)
-__global__ void __launch_bounds__(1024) transit_moments_kernel(const double *__restrict__ t, const double *__restrict__ y,
-                                                               const double *__restrict__ ivar, int64_t N,
-                                                               double *__restrict__ out) {
-  __shared__ double red[3][32];
+// data-only moments of the Gaussian likelihood in ONE pass over (t, y, ivar), many CTAs:
+// out = (y_ref, S1, Sy, Syy, sorted) with y_ref a reference value inside the data's range (the
+// mean of 32 strided samples, the same in every CTA) so that the shifted sums
+// Sy = sum ivar (y - y_ref), Syy = sum ivar (y - y_ref)^2 carry no cancellation, and sorted = 1
+// when t is non-decreasing (lets the sweep skip whole 128-cadence steps with one interval test).
+// Per-CTA partials go to out[8 + 4 b]; the last CTA to arrive (ticket in out[7]) folds them in
+// CTA order, so the result does not depend on the arrival order (deterministic).
+constexpr int kMomThreads = 256;
+constexpr int kMomMaxCtas = (XO_MOMENTS_LEN - 8) / 4;
+__global__ void __launch_bounds__(kMomThreads) transit_moments_kernel(const double *__restrict__ t, const double *__restrict__ y,
+                                                                      const double *__restrict__ ivar, int64_t N,
+                                                                      double *__restrict__ out) {
+  __shared__ double red[4][kMomThreads / 32];
   __shared__ double yref_s;
-  auto block_sum3 = [&](double a, double b, double c, double &A, double &B, double &Cc) {
-    a = warp_sum(a);
-    b = warp_sum(b);
-    c = warp_sum(c);
-    if ((threadIdx.x & 31) == 0) {
-      red[0][threadIdx.x >> 5] = a;
-      red[1][threadIdx.x >> 5] = b;
-      red[2][threadIdx.x >> 5] = c;
-    }
-    __syncthreads();
-    A = B = Cc = 0.0;
-    for (int w = 0; w < 32; ++w) {
-      A += red[0][w];
-      B += red[1][w];
-      Cc += red[2][w];
-    }
-    __syncthreads();
-  };
-  double s1 = 0.0, sy = 0.0, bad = 0.0;
-  for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
-    const double w = ivar[i];
-    s1 += w;
-    sy = fma(w, y[i], sy);
-    if (i + 1 < N && !(t[i + 1] >= t[i])) bad += 1.0;
+  __shared__ int is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    const double v = warp_sum(__ldg(y + (int64_t)lane * N / 32));
+    if (lane == 0) yref_s = v * (1.0 / 32.0);
   }
-  double S1, Sy0, Bad;
-  block_sum3(s1, sy, bad, S1, Sy0, Bad);
-  double dummy;
-  if (threadIdx.x == 0) yref_s = Sy0 / S1;
   __syncthreads();
   const double yref = yref_s;
-  double a = 0.0, b = 0.0;
-  for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
-    const double w = ivar[i], d = y[i] - yref;
-    a = fma(w, d, a);
-    b = fma(w * d, d, b);
+  double s1 = 0.0, sy = 0.0, syy = 0.0, bad = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * kMomThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kMomThreads + threadIdx.x; i < N; i += stride) {
+    const double w = __ldg(ivar + i), d = __ldg(y + i) - yref;
+    s1 += w;
+    sy = fma(w, d, sy);
+    syy = fma(w * d, d, syy);
+    if (i + 1 < N && !(__ldg(t + i + 1) >= __ldg(t + i))) bad += 1.0;
   }
-  double Sy, Syy;
-  block_sum3(a, b, 0.0, Sy, Syy, dummy);
-  if (threadIdx.x == 0) {
+  double v4[4] = {s1, sy, syy, bad};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const double v = warp_sum(v4[j]);
+    if (lane == 0) red[j][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double a = 0.0;
+    for (int w = 0; w < kMomThreads / 32; ++w) a += red[threadIdx.x][w];
+    out[8 + 4 * blockIdx.x + threadIdx.x] = a;
+  }
+  __threadfence();
+  __syncthreads();
+  unsigned *ticket = reinterpret_cast<unsigned *>(out + 7);
+  if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last || warp != 0) return;
+  __threadfence();
+  double f4[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int b = lane; b < (int)gridDim.x; b += 32) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) f4[j] += __ldcg(out + 8 + 4 * b + j);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) f4[j] = warp_sum(f4[j]);
+  if (lane == 0) {
     out[0] = yref;
-    out[1] = S1;
-    out[2] = Sy;
-    out[3] = Syy;
-    out[4] = Bad == 0.0 ? 1.0 : 0.0;
+    out[1] = f4[0];
+    out[2] = f4[1];
+    out[3] = f4[2];
+    out[4] = f4[3] == 0.0 ? 1.0 : 0.0;
+    out[5] = out[6] = 0.0;
+    *ticket = 0u;
+    reinterpret_cast<unsigned *>(out + 7)[1] = 0u;
   }
 }
 
@@ -723,7 +765,12 @@ size_t xo_transit_logp_grad_workspace(int64_t N, int64_t C, int64_t P) {
 int xo_transit_data_moments(const double *t, const double *y, const double *ivar, int64_t N, double *moments,
                             void *stream) {
   if (N <= 0 || !t || !y || !ivar || !moments) return XO_EINVAL;
-  transit_moments_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(t, y, ivar, N, moments);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(moments + 7, 0, sizeof(double), st);  // the arrival ticket
+  if (e != cudaSuccess) return -(int)e;
+  const int64_t want = (N + 4 * kMomThreads - 1) / (4 * kMomThreads);
+  const int ctas = (int)(want < 1 ? 1 : want > kMomMaxCtas ? kMomMaxCtas : want);
+  transit_moments_kernel<<<ctas, kMomThreads, 0, st>>>(t, y, ivar, N, moments);
   return xo::launch_status();
 }
 

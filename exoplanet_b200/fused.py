@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import NEL, NGRAD, NGRAD_RV
+from ._lib import MOMENTS_LEN, NEL, NGRAD, NGRAD_RV
 
 __all__ = ["exposure_stencil", "limb_dark_coeffs", "TransitData", "light_curve", "transit_logp_grad", "TransitLogp",
            "orbit_eval", "rv_logp_grad", "RvLogp"]
@@ -83,7 +83,7 @@ class TransitData:
         data-only part of the Gaussian sums, computed once (xo_transit_data_moments)."""
         if self._moments is None and self.y is not None and self.ivar is not None:
             lib = _lib.require_cuda()
-            m = torch.zeros(8, dtype=torch.float64, device=self.device)
+            m = torch.zeros(MOMENTS_LEN, dtype=torch.float64, device=self.device)
             with torch.cuda.device(self.device):
                 _lib.check(lib.xo_transit_data_moments(_ptr(self.t), _ptr(self.y), _ptr(self.ivar), self.n, _ptr(m), _lib.stream_ptr()),
                            "moments")

@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["sho_loglike", "sho_solve", "sho_loglike_autograd", "sho_params_from_sigma_rho"]
+__all__ = ["sho_loglike", "sho_solve", "sho_grad", "sho_loglike_autograd", "sho_params_from_sigma_rho"]
 
 
 def _ptr(x):
@@ -79,45 +79,65 @@ def sho_solve(t, y, diag, S0, w0, Q, eps=1e-5, workspace=None):
     return (ll, alpha) if y.dim() == 2 else (ll[0], alpha[0])
 
 
-class _SHOLogLike(torch.autograd.Function):
-    """log-likelihood[B] with gradients: exact w.r.t. y (= -K^-1 y, one reverse scan); w.r.t.
-    (S0, w0, Q) by central differences of the forward scan, the 6 perturbed evaluations batched
-    into one launch (relative step 1e-6 -- NOT an analytic VJP)."""
+def sho_grad(t, y, diag, S0, w0, Q, eps=1e-5, want_y=True, want_diag=True, workspace=None):
+    """(loglike[B], ghyper[B, 3], gy[B, N] | None, gdiag[B, N] | None): the log-likelihood and its
+    exact reverse-mode gradient w.r.t. (S0, w0, Q), y and diag (xo_celerite_sho_grad): the forward
+    scan, then the adjoint of the Kalman recursion as a reverse affine scan."""
+    lib = _lib.require_cuda()
+    dev = t.device
+    y2 = (y if y.dim() == 2 else y[None, :]).contiguous()
+    B, N = y2.shape
 
-    REL_STEP = 1e-6
+    def vec(x):
+        x = torch.as_tensor(x, dtype=torch.float64, device=dev).detach()
+        return x.expand(B).contiguous() if x.dim() == 0 else x.contiguous()
+
+    S0, w0, Q = vec(S0), vec(w0), vec(Q)
+    t = t.contiguous()
+    diag = diag.contiguous()
+    need = lib.xo_celerite_sho_grad_workspace(N, B)
+    if workspace is None or workspace.numel() * 8 < need:
+        workspace = torch.empty(need // 8 + 1, dtype=torch.float64, device=dev)
+    ll = torch.empty(B, dtype=torch.float64, device=dev)
+    gh = torch.empty((B, 3), dtype=torch.float64, device=dev)
+    gy = torch.empty((B, N), dtype=torch.float64, device=dev) if want_y else None
+    gd = torch.empty((B, N), dtype=torch.float64, device=dev) if want_diag else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.xo_celerite_sho_grad(_ptr(t), _ptr(y2), _ptr(diag), N, _ptr(S0), _ptr(w0), _ptr(Q), B, float(eps), _ptr(ll),
+                                            _ptr(gh), _ptr(gy), _ptr(gd), _ptr(workspace), workspace.numel() * 8,
+                                            _lib.stream_ptr()), "celerite_sho_grad")
+    if y.dim() == 2:
+        return ll, gh, gy, gd
+    return ll[0], gh[0], (gy[0] if want_y else None), (gd[0] if want_diag else None)
+
+
+class _SHOLogLike(torch.autograd.Function):
+    """log-likelihood[B] with its exact gradient w.r.t. y, (S0, w0, Q) and diag: one forward scan and
+    one reverse (adjoint) scan, both in forward() -- the reverse scan restarts from the states the
+    forward one records, so the pair is cheaper than keeping them for backward()."""
 
     @staticmethod
     def forward(ctx, y, S0, w0, Q, t, diag, eps):
-        ll, alpha = sho_solve(t, y, diag, S0, w0, Q, eps)
-        ctx.save_for_backward(y, S0, w0, Q, t, diag, alpha)
-        ctx.eps = eps
+        need = ctx.needs_input_grad
+        if not any(need):
+            return sho_loglike(t, y, diag, S0, w0, Q, eps)
+        ll, gh, gy, gd = sho_grad(t, y, diag, S0, w0, Q, eps, want_y=need[0], want_diag=need[5])
+        ctx.save_for_backward(gh, gy, gd)
         return ll
 
     @staticmethod
     def backward(ctx, g):
-        y, S0, w0, Q, t, diag, alpha = ctx.saved_tensors
-        B = y.shape[0]
-        gy = -g[:, None] * alpha if ctx.needs_input_grad[0] else None
-        gth = [None, None, None]
-        if any(ctx.needs_input_grad[1:4]):
-            th = [S0, w0, Q]
-            rows = []
-            for i in range(3):
-                for sgn in (1.0, -1.0):
-                    p = [x.clone() for x in th]
-                    p[i] = p[i] * (1.0 + sgn * _SHOLogLike.REL_STEP)
-                    rows.append(p)
-            S = torch.cat([r[0] for r in rows])
-            W = torch.cat([r[1] for r in rows])
-            Qq = torch.cat([r[2] for r in rows])
-            ll = sho_loglike(t, y.repeat(6, 1), diag, S, W, Qq, ctx.eps).reshape(6, B)
-            for i in range(3):
-                gth[i] = g * (ll[2 * i] - ll[2 * i + 1]) / (2.0 * _SHOLogLike.REL_STEP * th[i])
-        return gy, gth[0], gth[1], gth[2], None, None, None
+        gh, gy, gd = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        out_y = g[:, None] * gy if need[0] else None
+        out_d = (g[:, None] * gd).sum(0) if need[5] else None
+        return (out_y, g * gh[:, 0] if need[1] else None, g * gh[:, 1] if need[2] else None, g * gh[:, 2] if need[3] else None, None,
+                out_d, None)
 
 
 def sho_loglike_autograd(t, y, diag, S0, w0, Q, eps=1e-5):
-    """Differentiable SHO GP log-likelihood: y[B, N] (residuals), S0/w0/Q [B] tensors."""
+    """Differentiable SHO GP log-likelihood: y[B, N] (residuals), S0/w0/Q [B] tensors, diag[N];
+    exact gradients w.r.t. all of them."""
     y2 = y if y.dim() == 2 else y[None, :]
     B = y2.shape[0]
     dev = t.device

@@ -111,12 +111,16 @@ int xo_transit_lc_vjp(const double *t, int64_t N, const double *elem, const doub
  *   logp[c] = lognorm - 1/2 sum_n ivar[n] (y[n] - mean[c] - sum_p lc[c][n][p])^2
  *   gel[C][P][XO_NGRAD], gcl[C][3], gmean[C].
  * workspace: xo_transit_logp_grad_workspace(N, C, P) bytes of device memory.
- * moments: NULL, or the 8-double block written by xo_transit_data_moments(t, y, ivar) --
- *   (y_ref, sum ivar, sum ivar (y-y_ref), sum ivar (y-y_ref)^2, t_is_sorted, 0, 0, 0); with it the
+ * moments: NULL, or the block written by xo_transit_data_moments(t, y, ivar) (a device buffer of
+ *   XO_MOMENTS_LEN doubles; the first 8 are the result, the rest scratch of the reduction) --
+ *   (y_ref, sum ivar, sum ivar (y-y_ref), sum ivar (y-y_ref)^2, t_is_sorted, 0, 0, 0), y_ref a value
+ *   inside the data's range so the shifted sums carry no cancellation; with it the
  *   out-of-transit part of the sums is closed-form, the sweep reads t only, and for sorted t whole
  *   128-cadence steps are skipped by one interval test (same result to rounding). */
 size_t xo_transit_logp_grad_workspace(int64_t N, int64_t C, int64_t P);
-int xo_transit_data_moments(const double *t, const double *y, const double *ivar, int64_t N, double *moments /*[8]*/,
+#define XO_MOMENTS_LEN 1024
+int xo_transit_data_moments(const double *t, const double *y, const double *ivar, int64_t N,
+                            double *moments /*[XO_MOMENTS_LEN]*/,
                             void *stream);
 int xo_transit_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *elem,
                          const double *cl, const double *mean, int64_t C, int64_t P, const double *dtk, const double *wk,
@@ -164,6 +168,15 @@ size_t xo_celerite_sho_solve_workspace(int64_t N, int64_t B);
 int xo_celerite_sho_solve(const double *t, const double *y, const double *diag, int64_t N, const double *S0,
                           const double *w0, const double *Q, int64_t B, double eps, double *loglike, double *alpha,
                           void *workspace, size_t workspace_bytes, void *stream);
+
+/* log-likelihood and its exact reverse-mode gradient (what celerite2's own backward pass gives):
+ * ghyper[B][3] = d loglike / d(S0, w0, Q); optional gy[B][N] = d/dy (= -K^-1 y) and
+ * gdiag[B][N] = d/d diag (sum over chains for a shared jitter term).  The adjoint of the Kalman
+ * recursion is affine in a 5-vector and runs as a second (reverse) parallel scan. */
+size_t xo_celerite_sho_grad_workspace(int64_t N, int64_t B);
+int xo_celerite_sho_grad(const double *t, const double *y, const double *diag, int64_t N, const double *S0,
+                         const double *w0, const double *Q, int64_t B, double eps, double *loglike, double *ghyper,
+                         double *gy, double *gdiag, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- host-buffer entry points (the shape of exoplanet-core's driver) ---- */
 int xo_kepler_host(const double *M, const double *e, double *sinf, double *cosf, int64_t n, int device);

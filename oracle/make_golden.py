@@ -119,7 +119,13 @@ def golden_celerite():
     y = np.sin(t) + sig * rng.normal(size=N)
     for (S0, w0, Q, n) in [(1.3, 2.1, 3.0, 120), (1.3, 2.1, 1 / np.sqrt(2), 120), (0.7, 1.1, 0.3, 120), (1.3, 2.1, 3.0, 300)]:
         ll = T.sho_loglike_dense(t[:n], y[:n], (sig ** 2)[:n], S0, w0, Q)
-        out.append({"S0": S0, "w0": w0, "Q": float(Q), "n": n, "loglike": f(ll)})
+        case = {"S0": S0, "w0": w0, "Q": float(Q), "n": n, "loglike": f(ll)}
+        if n <= 120:  # gradient goldens (dense identities at 40 digits) on a 60-point prefix
+            m = 60
+            llg, gth, gy, gd = T.sho_loglike_dense_grad(t[:m], y[:m], (sig ** 2)[:m], S0, w0, Q)
+            case["grad"] = {"n": m, "loglike": f(llg), "hyper": [f(v) for v in gth], "gy": [f(v) for v in gy],
+                            "gdiag": [f(v) for v in gd]}
+        out.append(case)
     return {"seed": 42, "N": N, "t": t.tolist(), "y": y.tolist(), "diag": (sig ** 2).tolist(), "cases": out,
             "appendix_B9": 2.5488694069}
 

@@ -321,3 +321,38 @@ def sho_loglike_dense(t, y, diag, S0, w0, Q):
     z = mp.lu_solve(L, yv)  # L is triangular; lu_solve is fine for small n
     logdet = 2 * sum(mp.log(L[i, i]) for i in range(n))
     return -(z.T * z)[0] / 2 - logdet / 2 - n * mp.log(2 * mp.pi) / 2
+
+
+def sho_loglike_dense_grad(t, y, diag, S0, w0, Q):
+    """Gradient of the dense log-likelihood by the textbook identities (Rasmussen & Williams eq. 5.9):
+       dL/dtheta = 1/2 alpha^T (dK/dtheta) alpha - 1/2 tr(K^-1 dK/dtheta),   alpha = K^-1 y,
+       dL/dy = -alpha,   dL/d diag_k = 1/2 alpha_k^2 - 1/2 (K^-1)_kk,
+    with dK/dtheta taken by mp.diff of the kernel definition (no hand-derived kernel derivatives).
+    Returns (loglike, [dS0, dw0, dQ], gy[n], gdiag[n])."""
+    n = len(t)
+    S0, w0, Q = mp.mpf(S0), mp.mpf(w0), mp.mpf(Q)
+    K = mp.matrix(n, n)
+    dK = [mp.matrix(n, n) for _ in range(3)]
+    for i in range(n):
+        for j in range(i, n):
+            tau = mp.mpf(t[i]) - mp.mpf(t[j])
+            K[i, j] = K[j, i] = sho_kernel(tau, S0, w0, Q)
+            d = [mp.diff(lambda x: sho_kernel(tau, x, w0, Q), S0), mp.diff(lambda x: sho_kernel(tau, S0, x, Q), w0),
+                 mp.diff(lambda x: sho_kernel(tau, S0, w0, x), Q)]
+            for k in range(3):
+                dK[k][i, j] = dK[k][j, i] = d[k]
+        K[i, i] += mp.mpf(diag[i])
+    Kinv = K ** -1
+    yv = mp.matrix([mp.mpf(v) for v in y])
+    alpha = Kinv * yv
+    L = mp.cholesky(K)
+    logdet = 2 * sum(mp.log(L[i, i]) for i in range(n))
+    ll = -(yv.T * alpha)[0] / 2 - logdet / 2 - n * mp.log(2 * mp.pi) / 2
+    grads = []
+    for k in range(3):
+        quad = (alpha.T * dK[k] * alpha)[0]
+        tr = sum(Kinv[i, j] * dK[k][j, i] for i in range(n) for j in range(n))
+        grads.append(quad / 2 - tr / 2)
+    gy = [-alpha[i] for i in range(n)]
+    gdiag = [alpha[i] ** 2 / 2 - Kinv[i, i] / 2 for i in range(n)]
+    return ll, grads, gy, gdiag

@@ -147,6 +147,81 @@ def celerite_sho_loglike(t, y, diag, S0, w0, Q, eps=1e-5):
     return out.value
 
 
+def celerite_sho_grad(t, y, diag, S0, w0, Q, eps=1e-5):
+    """(loglike, [dS0, dw0, dQ], gy[N], gdiag[N]): the SHO GP log-likelihood and its gradient by a
+    sequential 2-state Kalman filter followed by its hand-written adjoint (pure-Python loops: small N
+    only).  Same contract as celerite2's reverse pass (GaussianProcess.log_likelihood under autodiff);
+    pinned against the 40-digit dense identities of mp_truth.sho_loglike_dense_grad
+    (tests/golden/celerite.json, tests/test_oracle.py)."""
+    import math
+    t, y, diag = [_f64(x) for x in (t, y, diag)]
+    N = t.size
+    a, c = S0 * w0 * Q, 0.5 * w0 / Q
+    under = Q >= 0.5
+    sgn = 1.0 if under else -1.0
+    arg = sgn * (4.0 * Q * Q - 1.0)
+    f = math.sqrt(max(arg, eps))
+    h = c * f
+    w2 = c * c + sgn * h * h
+
+    def phi(dt):
+        if under:
+            ex = math.exp(-c * dt)
+            Cf, Sf = ex * math.cos(h * dt), ex * math.sin(h * dt) / h
+        else:
+            ep, en = math.exp(-(c - h) * dt), math.exp(-(c + h) * dt)
+            Cf, Sf = 0.5 * (ep + en), 0.5 * (ep - en) / h
+        return Cf, Sf, np.array([[Cf + c * Sf, Sf], [-w2 * Sf, Cf - c * Sf]])
+
+    # forward: state (m, Z) with Z = Sigma_inf - P, Sigma_inf = diag(a, a w2); record what the adjoint needs
+    m, Z = np.zeros(2), np.zeros((2, 2))
+    rec, acc = [], 0.0
+    for i in range(N):
+        dt = t[i] - t[i - 1] if i > 0 else 0.0
+        Cf, Sf, F = phi(dt)
+        cv, W = F @ m, F @ Z
+        Pz = W @ F.T
+        k = np.array([a - Pz[0, 0], -Pz[0, 1]])
+        D = k[0] + diag[i]
+        v = y[i] - cv[0]
+        acc += v * v / D + math.log(D)
+        rec.append((dt, Cf, Sf, F, m.copy(), W, k, D, v))
+        m = cv + k * v / D
+        Z = Pz + np.outer(k, k) / D
+    ll = -0.5 * acc - 0.5 * N * math.log(2.0 * math.pi)
+    # adjoint, last cadence first: mb = dL/dm, Zb = dL/dZ (full symmetric matrix)
+    mb, Zb = np.zeros(2), np.zeros((2, 2))
+    ga = gc = gh = gw2 = 0.0
+    gy, gd = np.zeros(N), np.zeros(N)
+    for i in range(N - 1, -1, -1):
+        dt, Cf, Sf, F, m0, W, k, D, v = rec[i]
+        w = v / D
+        vbar = (k @ mb) / D - w
+        Dbar = -(k @ mb) * w / D - (k @ Zb @ k) / (D * D) + 0.5 * (w * w - 1.0 / D)
+        kb = mb * w + 2.0 * (Zb @ k) / D
+        cb = mb.copy()
+        cb[0] -= vbar
+        Pb = Zb.copy()
+        Pb[0, 0] -= kb[0] + Dbar
+        Pb[0, 1] -= 0.5 * kb[1]
+        Pb[1, 0] -= 0.5 * kb[1]
+        ga += kb[0] + Dbar
+        gy[i], gd[i] = vbar, Dbar
+        Fb = np.outer(cb, m0) + 2.0 * Pb @ W
+        mb, Zb = F.T @ cb, F.T @ Pb @ F
+        Cb = Fb[0, 0] + Fb[1, 1]
+        Sb = c * (Fb[0, 0] - Fb[1, 1]) + Fb[0, 1] - w2 * Fb[1, 0]
+        gc += Sf * (Fb[0, 0] - Fb[1, 1]) - dt * (Cf * Cb + Sf * Sb)
+        gw2 -= Sf * Fb[1, 0]
+        gh += -sgn * dt * h * Sf * Cb + (dt * Cf - Sf) / h * Sb
+    gc += 2.0 * c * gw2
+    gh += sgn * 2.0 * h * gw2
+    dfdQ = sgn * 4.0 * Q / f if arg > eps else 0.0
+    dcdQ = -c / Q
+    g = [ga * w0 * Q, ga * S0 * Q + gc * 0.5 / Q + gh * 0.5 / Q * f, ga * S0 * w0 + gc * dcdQ + gh * (dcdQ * f + c * dfdQ)]
+    return ll, np.array(g), gy, gd
+
+
 # ---------------------------------------------------------------------------
 # host-side helpers shared by tests/bench (pure numpy restatement of the O(P)
 # prologue, /root/reference/src/exoplanet/orbits/keplerian.py:133-281)

@@ -81,6 +81,31 @@ def test_logp_grad_matches_oracle(P, texp, C):
     assert np.max(np.abs(gmean.cpu().numpy() - gmo) / np.abs(gmo).max()) < 1e-10
 
 
+@pytest.mark.parametrize("N", [1, 31, 1000, 100000, 1234567])
+def test_data_moments_kernel(N):
+    """one-pass multi-CTA moments: y_ref inside the data's range, shifted sums vs numpy (long double),
+    sortedness flag, bit-reproducible (the last-arriving CTA folds the partials in CTA order)"""
+    rng = np.random.default_rng(N)
+    t = np.cumsum(rng.uniform(0.01, 0.03, N))
+    y = 1.0 + 5e-4 * rng.normal(size=N)
+    ivar = rng.uniform(0.5, 2.0, N) / 5e-4 ** 2
+    d = fused.TransitData(t, y, 1 / np.sqrt(ivar), device=DEV)
+    m = d.moments().cpu().numpy()
+    iv = d.ivar.cpu().numpy().astype(np.longdouble)
+    assert y.min() <= m[0] <= y.max()
+    dy = y.astype(np.longdouble) - np.longdouble(m[0])
+    ref = [iv.sum(), (iv * dy).sum(), (iv * dy * dy).sum()]
+    for k in range(3):
+        assert abs(m[1 + k] - float(ref[k])) <= 1e-13 * float((iv * np.abs(dy) ** k).sum()), (k, m[1 + k], ref[k])
+    assert m[4] == 1.0 and np.all(m[5:8] == 0.0)
+    d2 = fused.TransitData(t, y, 1 / np.sqrt(ivar), device=DEV)
+    assert np.array_equal(d2.moments().cpu().numpy()[:8], m[:8])
+    if N > 2:
+        tu = t.copy()
+        tu[[N // 2, N // 2 + 1]] = tu[[N // 2 + 1, N // 2]]
+        assert fused.TransitData(tu, y, 1 / np.sqrt(ivar), device=DEV).moments().cpu().numpy()[4] == 0.0
+
+
 def test_moments_path_equals_full_sweep():
     """closed-form out-of-transit sums (data moments) vs summing every cadence in the sweep"""
     N, C = 100000, 9

@@ -111,26 +111,100 @@ def test_solve_large_batch_is_consistent():
     assert torch.allclose(ll, gp.sho_loglike(t, y, diag, S0, w0, Q), rtol=1e-14)
 
 
+def test_gradient_golden(golden):
+    """xo_celerite_sho_grad vs the dense gradient identities evaluated at 40 digits"""
+    g = golden("celerite")
+    t, y, diag = np.array(g["t"]), np.array(g["y"]), np.array(g["diag"])
+    for c in g["cases"]:
+        if "grad" not in c:
+            continue
+        gr = c["grad"]
+        n = gr["n"]
+        ll, gh, gy, gd = gp.sho_grad(dev(t[:n]), dev(y[:n]), dev(diag[:n]), c["S0"], c["w0"], c["Q"], eps=0.0)
+        assert abs(ll.item() - gr["loglike"]) < 1e-10 * max(1.0, abs(gr["loglike"]))
+        ref = np.array(gr["hyper"])
+        assert np.all(np.abs(gh.cpu().numpy() - ref) < 1e-9 * (1.0 + np.abs(ref))), (c["Q"], gh, ref)
+        assert np.max(np.abs(gy.cpu().numpy() - np.array(gr["gy"]))) < 1e-9 * (1.0 + np.max(np.abs(gr["gy"])))
+        assert np.max(np.abs(gd.cpu().numpy() - np.array(gr["gdiag"]))) < 1e-9 * (1.0 + np.max(np.abs(gr["gdiag"])))
+
+
+@pytest.mark.parametrize("Q", [3.0, 0.70710678, 0.3, 0.5])
+@pytest.mark.parametrize("N", [1, 2, 15, 16, 17, 300, 2049, 4100])
+def test_gradient_matches_oracle(N, Q):
+    """the reverse affine scan (runs of 16, CTA boundaries at 2048) vs the sequential adjoint of the oracle;
+    Q = 0.5 with eps = 1e-5 exercises the clamped (zero-derivative) branch of celerite2's SHOTerm"""
+    rng = np.random.default_rng(100 + N)
+    t = np.sort(rng.uniform(0, 0.15 * N + 1, N))
+    diag = (0.1 + 0.05 * rng.uniform(size=N)) ** 2
+    y = np.sin(t) + 0.1 * rng.normal(size=N)
+    S0, w0 = 1.3, 2.1
+    eps = 1e-5 if Q == 0.5 else 0.0
+    ll, gh, gy, gd = gp.sho_grad(dev(t), dev(y), dev(diag), S0, w0, Q, eps=eps)
+    lo, go, gyo, gdo = O.celerite_sho_grad(t, y, diag, S0, w0, Q, eps=eps)
+    assert abs(ll.item() - lo) < 1e-10 * (1 + abs(lo))
+    assert np.all(np.abs(gh.cpu().numpy() - go) < 1e-9 * (1 + np.abs(go))), (gh, go)
+    assert np.max(np.abs(gy.cpu().numpy() - gyo)) < 1e-9 * (1 + np.abs(gyo).max())
+    assert np.max(np.abs(gd.cpu().numpy() - gdo)) < 1e-9 * (1 + np.abs(gdo).max())
+
+
+def test_gradient_large_batch():
+    """N = 1e5, three chains: d/dy equals -alpha of the disturbance smoother (independent kernel), the
+    hyper-parameter and diag gradients agree with central differences of the forward scan, and the
+    result is bit-reproducible."""
+    N = 100000
+    pr = synthetic.gp_problem(N)
+    t, diag = dev(pr["t"]), dev(pr["diag"])
+    B = 3
+    y = dev(np.stack([pr["y"] * (1 + 0.1 * k) for k in range(B)]))
+    th = [dev([pr["S0"], 2 * pr["S0"], 0.5 * pr["S0"]]), dev([pr["w0"], 1.5 * pr["w0"], pr["w0"]]), dev([3.0, 0.4, 1.0])]
+    ll, gh, gy, gd = gp.sho_grad(t, y, diag, *th)
+    ll_s, alpha = gp.sho_solve(t, y, diag, *th)
+    assert torch.allclose(ll, ll_s, rtol=1e-14)
+    assert torch.allclose(gy, -alpha, rtol=1e-9, atol=1e-9 * alpha.abs().max().item())
+    for i in range(3):
+        h = 1e-6 * th[i]
+        p = [x.clone() for x in th]
+        m = [x.clone() for x in th]
+        p[i] = p[i] + h
+        m[i] = m[i] - h
+        fd = (gp.sho_loglike(t, y, diag, *p) - gp.sho_loglike(t, y, diag, *m)) / (2 * h)
+        assert torch.allclose(gh[:, i], fd, rtol=2e-5, atol=1e-6 * gh[:, i].abs().max().item()), (i, gh[:, i], fd)
+    d = dev(np.random.default_rng(3).uniform(0.5, 1.5, N)) * diag
+    hh = 1e-4
+    fd = (gp.sho_loglike(t, y, diag + hh * d, *th) - gp.sho_loglike(t, y, diag - hh * d, *th)) / (2 * hh)
+    assert torch.allclose((gd * d).sum(1), fd, rtol=1e-6)
+    ll2, gh2, gy2, gd2 = gp.sho_grad(t, y, diag, *th)
+    assert torch.equal(gh, gh2) and torch.equal(gy, gy2) and torch.equal(gd, gd2)
+
+
 def test_autograd_gradients_match_dense():
+    """torch autograd through sho_loglike_autograd: y, (S0, w0, Q) and diag (a shared jitter term)"""
     rng = np.random.default_rng(4)
     N = 200
     t = np.sort(rng.uniform(0, 30, N))
-    diag = (0.1 + 0.05 * rng.uniform(size=N)) ** 2
+    sig2 = (0.1 + 0.05 * rng.uniform(size=N)) ** 2
     ynp = np.sin(t) + 0.1 * rng.normal(size=N)
     th = np.array([1.3, 2.1, 3.0])
     y = dev(ynp).requires_grad_(True)
     S0, w0, Q = [dev(v).reshape(()).requires_grad_(True) for v in th]
-    ll = gp.sho_loglike_autograd(dev(t), y, dev(diag), S0, w0, Q, eps=0.0)
-    gy, g0, g1, g2 = torch.autograd.grad(ll, (y, S0, w0, Q))
-    ref_alpha = np.linalg.solve(_dense_sho(t, diag, *th), ynp)
+    logj = dev(np.log(0.05)).reshape(()).requires_grad_(True)
+    diag = dev(sig2) + torch.exp(2.0 * logj)
+    ll = gp.sho_loglike_autograd(dev(t), y, diag, S0, w0, Q, eps=0.0)
+    gy, g0, g1, g2, gj = torch.autograd.grad(ll, (y, S0, w0, Q, logj))
+    dnp = sig2 + 0.05 ** 2
+    lo, go, gyo, gdo = O.celerite_sho_grad(t, ynp, dnp, *th, eps=0.0)
+    assert abs(ll.item() - _dense_loglike(t, ynp, dnp, *th)) < 1e-9 * (1 + abs(lo))
+    ref_alpha = np.linalg.solve(_dense_sho(t, dnp, *th), ynp)
     assert np.max(np.abs(gy.cpu().numpy() + ref_alpha)) < 1e-9 * (1 + np.abs(ref_alpha).max())
     for i, g in enumerate((g0, g1, g2)):
+        assert abs(g.item() - go[i]) < 1e-9 * (1 + abs(go[i])), (i, g.item(), go[i])
         hh = 1e-6 * th[i]
         p, m = th.copy(), th.copy()
         p[i] += hh
         m[i] -= hh
-        fd = (_dense_loglike(t, ynp, diag, *p) - _dense_loglike(t, ynp, diag, *m)) / (2 * hh)
-        assert abs(g.item() - fd) < 1e-5 * (1 + abs(fd)), (i, g.item(), fd)
+        fd = (_dense_loglike(t, ynp, dnp, *p) - _dense_loglike(t, ynp, dnp, *m)) / (2 * hh)
+        assert abs(g.item() - fd) < 1e-6 * (1 + abs(fd)), (i, g.item(), fd)
+    assert abs(gj.item() - gdo.sum() * 2 * 0.05 ** 2) < 1e-9 * (1 + abs(gj.item()))
 
 
 def test_transit_plus_gp_joint_gradient():

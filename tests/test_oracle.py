@@ -80,6 +80,27 @@ def test_celerite_golden(golden):
     assert abs(O.celerite_sho_loglike(t, y, diag, 1.3, 2.1, 3.0) - g["appendix_B9"]) < 1e-9
 
 
+def test_celerite_gradient_golden(golden):
+    """the Kalman-filter adjoint restated in oracle/xo_oracle.py vs the dense identities at 40 digits
+    (dL/dtheta = 1/2 a^T dK a - 1/2 tr(K^-1 dK), dL/dy = -a, dL/d diag = 1/2 a^2 - 1/2 diag(K^-1))"""
+    g = golden("celerite")
+    t, y, diag = np.array(g["t"]), np.array(g["y"]), np.array(g["diag"])
+    seen = 0
+    for c in g["cases"]:
+        if "grad" not in c:
+            continue
+        seen += 1
+        gr = c["grad"]
+        n = gr["n"]
+        ll, gth, gy, gd = O.celerite_sho_grad(t[:n], y[:n], diag[:n], c["S0"], c["w0"], c["Q"], eps=0.0)
+        assert abs(ll - gr["loglike"]) < 1e-10 * max(1.0, abs(gr["loglike"]))
+        ref = np.array(gr["hyper"])
+        assert np.all(np.abs(gth - ref) < 1e-9 * (1.0 + np.abs(ref))), (c["Q"], gth, ref)
+        assert np.max(np.abs(gy - np.array(gr["gy"]))) < 1e-9 * (1.0 + np.max(np.abs(gr["gy"])))
+        assert np.max(np.abs(gd - np.array(gr["gdiag"]))) < 1e-9 * (1.0 + np.max(np.abs(gr["gdiag"])))
+    assert seen >= 3  # under-damped, critically-ish damped (Q = 1/sqrt 2), over-damped
+
+
 def test_end_to_end_known_answers(golden):
     g = golden("end_to_end")
     b5 = g["B5"]

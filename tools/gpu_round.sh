@@ -5,6 +5,20 @@ TAG=${1:-r01}
 MODE=${2:-full}
 OUT=gpurun_out
 mkdir -p $OUT
+if [ "$MODE" = "tune" ]; then
+# short visit while tuning the logp kernel: fused parity tests, launch-width sweep, one ncu capture
+timeout 900 python -m pytest tests/test_gpu_fused.py tests/test_reference_glue.py -m gpu -q > $OUT/${TAG}_pytest.log 2>&1; echo "pytest exit $?" >> $OUT/${TAG}_pytest.log
+: > $OUT/${TAG}_sweep.txt
+for mb in 3 4; do for w in 8 12 16 24 32 48; do
+  echo -n "minblocks=$mb warps_per_sm=$w " >> $OUT/${TAG}_sweep.txt
+  XO_TRANSIT_MINBLOCKS=$mb XO_TRANSIT_WARPS_PER_SM=$w timeout 120 python bench.py --steps 20 --warmup 3 --no-cpu --no-kepler --no-extra 2>/dev/null \
+    | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'])" >> $OUT/${TAG}_sweep.txt
+done; done
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:transit_logp_grad_kernel -s 3 -c 1 -f -o $OUT/${TAG}_prof_transit \
+    python bench.py --steps 2 --warmup 3 --no-cpu --no-kepler --no-extra > $OUT/${TAG}_ncu_transit.log 2>&1
+tail -5 $OUT/${TAG}_pytest.log; cat $OUT/${TAG}_sweep.txt
+exit 0
+fi
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_gpu.txt 2>&1
 lscpu | grep -E "Model name|^CPU\(s\)|Thread|Core|Socket" >> $OUT/${TAG}_gpu.txt; nproc >> $OUT/${TAG}_gpu.txt
 timeout 1500 python -m pytest tests -m gpu -q > $OUT/${TAG}_pytest.log 2>&1; echo "pytest exit $?" >> $OUT/${TAG}_pytest.log
