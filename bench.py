@@ -257,23 +257,35 @@ def extra_configs(lib, dev, args):
         out["configs[3] celerite SHO loglike, N=1e6, %d chain(s)" % B] = {
             "value": B * Ng / (ms * 1e-3), "unit": "cadences/s", "ms_per_step": ms, "gb_per_s": 24.0 * B * Ng / (ms * 1e-3) / 1e9,
             "parity_rel_err": float(abs(r["ll"][0].item() - lo) / abs(lo))}
+        del ws
+        wg = torch.empty(lib.xo_celerite_sho_grad_workspace(Ng, B) // 8 + 1, dtype=torch.float64, device=dev)
+
+        def ggrad():
+            r["g"] = gp.sho_grad(tg, yb, dg, pr["S0"], pr["w0"], pr["Q"], workspace=wg)
+
+        ms = _time_steps(ggrad, 10, flush)
+        out["configs[3] celerite SHO loglike + exact gradient (S0, w0, Q, y, diag), N=1e6, %d chain(s)" % B] = {
+            "value": B * Ng / (ms * 1e-3), "unit": "cadences/s", "ms_per_step": ms,
+            "loglike_rel_err": float(abs(r["g"][0][0].item() - lo) / abs(lo))}
+        del wg
     # joint model of configs[3]: transit mean + SHO GP noise at N=1e6, logL and its gradient w.r.t. the
     # orbital parameters (light curve -> residual -> GP solve (logL, alpha) -> light-curve VJP with alpha)
     from exoplanet_b200.light_curves import LimbDarkLightCurve
     from exoplanet_b200.orbits import KeplerianOrbit
 
     pj = [d([7.31]).requires_grad_(True), d([0.3]).requires_grad_(True), d([0.08]).requires_grad_(True)]
+    hj = [d(pr[k]).reshape(()).requires_grad_(True) for k in ("S0", "w0", "Q")]
     lcm = LimbDarkLightCurve(0.3, 0.2, device=dev)
     res = {}
 
     def jstep():
         orbit = KeplerianOrbit(period=pj[0], t0=d([1.3]), ecc=d([0.3]), omega=d([0.4]), b=pj[1])
         mu = lcm.get_light_curve(orbit=orbit, r=pj[2], t=tg)[:, 0]
-        ll = gp.sho_loglike_autograd(tg, yg - mu, dg, pr["S0"], pr["w0"], pr["Q"])
-        res["g"] = torch.autograd.grad(ll, pj)
+        ll = gp.sho_loglike_autograd(tg, yg - mu, dg, *hj)
+        res["g"] = torch.autograd.grad(ll, pj + hj)
 
     ms = _time_steps(jstep, 5, flush)
-    out["configs[3] transit + SHO GP, N=1e6: logL + d/d(period, b, r) (torch-level composition)"] = {
+    out["configs[3] transit + SHO GP, N=1e6: logL + d/d(period, b, r, S0, w0, Q) (torch-level composition)"] = {
         "value": 1.0 / (ms * 1e-3), "unit": "model+grad evals/s", "ms_per_step": ms}
     return out
 
@@ -291,6 +303,10 @@ def arm_ours(args):
             raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # one process per GPU, bound to the GPU's NUMA node before any pinned buffer is allocated
+    from exoplanet_b200 import parallel as xo_parallel
+
+    bound_cpus, prev_affinity = xo_parallel.bind_to_device_numa(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -499,8 +515,12 @@ def arm_ours(args):
         if rel > 1e-10:
             raise SystemExit("parity gate failed: logp rel err %g" % rel)
         # the CPU restatement, timed in a clean process on all host cores (~10-20 s)
+        def all_cores():  # the child must not inherit this rank's NUMA binding
+            if prev_affinity:
+                os.sched_setaffinity(0, prev_affinity)
+
         out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "40", "--warmup", "2"],
-                             capture_output=True, text=True, timeout=600)
+                             capture_output=True, text=True, timeout=600, preexec_fn=all_cores)
         try:
             ref = json.loads(out.stdout.strip().splitlines()[-1])
             cpu = ref["cpu_baseline"]
@@ -520,7 +540,9 @@ def arm_ours(args):
         "config": {"workload": "configs[1]: eccentric (e=0.5) single-planet Kepler solve + LimbDarkLightCurve, N=1e5 cadences, fp64",
                    "chains_per_gpu": C_loc, "chains_total": C_loc * world, "cadences": N_CADENCES, "use_in_transit": True,
                    "out_of_transit_sums": "full sweep over y, ivar" if args.full_sweep else "data moments (t-only sweep)",
-                   "parallelism": "chain-sharded, no collective", "l2": "flushed between timed steps (192 MiB memset)",
+                   "parallelism": "chain-sharded, no collective",
+                   "host_affinity": ("process bound to the %d CPUs of the GPU's NUMA node" % len(bound_cpus)) if bound_cpus else "unbound",
+                   "l2": "flushed between timed steps (192 MiB memset)",
                    "step": "params -> elements+contact points -> fused logp+grad -> reverse prologue, 3 kernel launches (XO_MODEL_LAUNCHES=1|2 fuse them; slower), params resident in HBM"},
         "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "xo_transit_model_logp_grad_host: t,y,ivar,params from pinned host memory every call; logp+grads back to host"},

@@ -34,4 +34,29 @@ inline int launch_status() {
 
 inline int cuda_status(cudaError_t err) { return err == cudaSuccess ? 0 : -(int)err; }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with `pdl = true` may begin while the
+// preceding kernel of the stream is still running; it must execute pdl_wait() before touching
+// anything that kernel writes.  The preceding kernel lets it start early with
+// pdl_launch_dependents().  Both are no-ops for a kernel launched the ordinary way.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 }  // namespace xo

@@ -19,6 +19,7 @@ namespace {
 __global__ void model_prologue_kernel(const double *__restrict__ par, const double *__restrict__ star, int64_t C, int P,
                                       double texp, int use_in_transit, double *__restrict__ elem,
                                       double *__restrict__ cl) {
+  xo::pdl_launch_dependents();  // the logp kernel may start its data-only preamble now
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t idx = tid >> 1;
   const bool active = idx < C * P;
@@ -36,8 +37,12 @@ __global__ void model_epilogue_kernel(const double *__restrict__ par, const doub
   const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
   const int nacc = xo::kNBase + P * XO_NGRAD;
-  xo::epilogue_chain<false>(par + c * P * XO_NPAR, star + c * XO_NSTAR, partial + c * slots * nacc, slots, P, lognorm, logp + c,
-                            gpar + c * P * XO_NPAR, gstar + c * XO_NSTAR, gmean + c);
+  const int lane = threadIdx.x & 31;
+  // parameter-only half first: as a programmatic dependent of the logp kernel this overlaps its tail
+  const xo::EpiPre pre = xo::epilogue_pre(par + (c * P + (lane < P ? lane : 0)) * XO_NPAR, star + c * XO_NSTAR);
+  xo::pdl_wait();
+  xo::epilogue_chain<true>(pre, star + c * XO_NSTAR, partial + c * slots * nacc, slots, P, lognorm, logp + c,
+                           gpar + c * P * XO_NPAR, gstar + c * XO_NSTAR, gmean + c);
 }
 
 struct ModelLayout {
@@ -117,6 +122,10 @@ int xo_transit_model_logp_grad(const double *t, const double *y, const double *i
     xo::launch_transit_logp_grad(t, y, ivar, N, elem, cl, mean, C, (int)P, dtk, wk, K, L.sp, moments, partial, st, &ma);
     return xo::launch_status();
   }
+  static const bool pdl = [] {  // XO_MODEL_PDL=0: plain stream order between the three kernels
+    const char *v = getenv("XO_MODEL_PDL");
+    return !(v && *v == '0');
+  }();
   model_prologue_kernel<<<(unsigned)((2 * cp + 63) / 64), 64, 0, st>>>(par, star, C, (int)P, texp, use_in_transit, elem, cl);
   static const int lpt = [] {
     const char *v = getenv("XO_MODEL_HEAVY_FIRST");
@@ -131,9 +140,12 @@ int xo_transit_model_logp_grad(const double *t, const double *y, const double *i
     ord.elements_only = 1;
     pord = &ord;
   }
-  xo::launch_transit_logp_grad(t, y, ivar, N, elem, cl, mean, C, (int)P, dtk, wk, K, L.sp, moments, partial, st, pord);
-  model_epilogue_kernel<<<(unsigned)((C + 3) / 4), 128, 0, st>>>(par, star, partial, L.sp.slots, C, (int)P, lognorm, logp,
-                                                                 gpar, gstar, gmean);
+  // heavy-first inserts the ordering kernel between prologue and logp kernel: no early start then
+  xo::launch_transit_logp_grad(t, y, ivar, N, elem, cl, mean, C, (int)P, dtk, wk, K, L.sp, moments, partial, st, pord,
+                               pdl && !pord);
+  cudaError_t le = xo::launch_pdl(model_epilogue_kernel, dim3((unsigned)((C + 3) / 4)), dim3(128), st, pdl, par, star,
+                                  (const double *)partial, L.sp.slots, C, (int)P, lognorm, logp, gpar, gstar, gmean);
+  if (le != cudaSuccess) return -(int)le;
   return xo::launch_status();
 }
 

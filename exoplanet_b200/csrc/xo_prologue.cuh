@@ -87,12 +87,43 @@ __device__ inline void limb_coeffs(double u1, double u2, double *cl3) {
   cl3[2] = c2 * rn;
 }
 
+// Parameter-only part of the reverse prologue of planet `lane` (everything that does not need the
+// accumulated cotangents): computed before the partial sums are waited for.
+struct EpiPre {
+  double period, e, b, mt, a, n, sw, cw, sme, spe, x, y, sE0, cE0, M0, ome2, F, cosi, sini;
+};
+__device__ inline EpiPre epilogue_pre(const double *q, const double *st) {
+  EpiPre r;
+  const double R = st[0], Ms = st[1];
+  r.period = q[0];
+  r.e = q[2];
+  r.b = q[4];
+  r.mt = Ms + q[6];
+  r.a = cbrt(kGGrav * r.mt * r.period * r.period / (4.0 * kPi * kPi));
+  r.n = 2.0 * kPi / r.period;
+  sincos(q[3], &r.sw, &r.cw);
+  r.sme = sqrt(1.0 - r.e);
+  r.spe = sqrt(1.0 + r.e);
+  r.y = r.sme * r.cw;
+  r.x = r.spe * (1.0 + r.sw);
+  const double E0 = 2.0 * atan2(r.y, r.x);
+  sincos(E0, &r.sE0, &r.cE0);
+  r.M0 = E0 - r.e * r.sE0;
+  r.ome2 = (1.0 - r.e) * (1.0 + r.e);
+  r.F = (1.0 + r.e * r.sw) / r.ome2;
+  r.cosi = r.F * R / r.a * r.b;
+  r.sini = sqrt((1.0 - r.cosi) * (1.0 + r.cosi));
+  return r;
+}
+
 // Warp-collective epilogue of ONE chain: lane l sums slots l, l+32, ... of every accumulator
 // (ascending), a fixed-order butterfly combines the 32 lane sums (deterministic), lane p < P runs
-// the reverse pass of planet p's prologue, lane 0 the reverse of get_cl.  kCoherent: read the
-// partials through L2 (they were written by other CTAs of the same launch).
+// the reverse pass of planet p's prologue (pre = epilogue_pre of that planet), lane 0 the reverse
+// of get_cl.  Accumulators are folded five at a time (nacc = 5 + 10 P) so that the loads and the
+// shuffle trees of a group overlap.  kCoherent: read the partials through L2 (they were written by
+// other CTAs of the same launch).
 template <bool kCoherent>
-__device__ inline void epilogue_chain(const double *par_c, const double *st, const double *src, int slots, int P,
+__device__ inline void epilogue_chain(const EpiPre &pre, const double *st, const double *src, int slots, int P,
                                       double lognorm, double *logp, double *gpar_c, double *gstar_c, double *gmean) {
   constexpr unsigned kFullM = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -101,45 +132,39 @@ __device__ inline void epilogue_chain(const double *par_c, const double *st, con
 #pragma unroll
   for (int j = 0; j < XO_NGRAD; ++j) g[j] = 0.0;
   double base = 0.0;
-  for (int j = 0; j < nacc; ++j) {
-    double acc = 0.0;
+  for (int j0 = 0; j0 < nacc; j0 += 5) {
+    double a5[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     for (int s = lane; s < slots; s += 32) {
-      const double *ptr = src + (int64_t)s * nacc + j;
-      acc += kCoherent ? __ldcg(ptr) : *ptr;
+      const double *ptr = src + (int64_t)s * nacc + j0;
+#pragma unroll
+      for (int u = 0; u < 5; ++u) a5[u] += kCoherent ? __ldcg(ptr + u) : ptr[u];
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFullM, acc, o);
-    if (j < kNBase) {
-      if (lane == 8 + j) base = acc;
-    } else {
-      const int pj = (j - kNBase) / XO_NGRAD, k = (j - kNBase) % XO_NGRAD;
-      if (lane == pj) {
+    for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-        for (int kk = 0; kk < XO_NGRAD; ++kk)
-          if (kk == k) g[kk] = acc;
+      for (int u = 0; u < 5; ++u) a5[u] += __shfl_xor_sync(kFullM, a5[u], o);
+    }
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+      const int j = j0 + u;
+      if (j < kNBase) {
+        if (lane == 8 + j) base = a5[u];
+      } else {
+        const int pj = (j - kNBase) / XO_NGRAD, k = (j - kNBase) % XO_NGRAD;
+        if (lane == pj) {
+#pragma unroll
+          for (int kk = 0; kk < XO_NGRAD; ++kk)
+            if (kk == k) g[kk] = a5[u];
+        }
       }
     }
   }
-  const double R = st[0], Ms = st[1];
+  const double R = st[0];
   double gR = 0.0, gMs = 0.0;
   if (lane < P) {
-    const double *q = par_c + lane * XO_NPAR;
-    const double period = q[0], e = q[2], omega = q[3], b = q[4], mpl = q[6];
-    const double mt = Ms + mpl;
-    const double a = cbrt(kGGrav * mt * period * period / (4.0 * kPi * kPi));
-    const double n = 2.0 * kPi / period;
-    double sw, cw;
-    sincos(omega, &sw, &cw);
-    const double sme = sqrt(1.0 - e), spe = sqrt(1.0 + e);
-    const double y = sme * cw, x = spe * (1.0 + sw);
-    const double E0 = 2.0 * atan2(y, x);
-    double sE0, cE0;
-    sincos(E0, &sE0, &cE0);
-    const double M0 = E0 - e * sE0;
-    const double ome2 = (1.0 - e) * (1.0 + e);
-    const double F = (1.0 + e * sw) / ome2;
-    const double cosi = F * R / a * b;
-    const double sini = sqrt((1.0 - cosi) * (1.0 + cosi));
+    const double period = pre.period, e = pre.e, b = pre.b, mt = pre.mt, a = pre.a, n = pre.n, sw = pre.sw, cw = pre.cw;
+    const double sme = pre.sme, spe = pre.spe, x = pre.x, y = pre.y, sE0 = pre.sE0, cE0 = pre.cE0, M0 = pre.M0;
+    const double ome2 = pre.ome2, F = pre.F, cosi = pre.cosi, sini = pre.sini;
     // cotangents of the element block: g = (t0, tref, n, e, cw, sw, cosi, sini, aor, ror)
     double gt0 = g[0], ge = g[3], gcw = g[4], gsw = g[5];
     double ga = g[8] / R;
@@ -197,6 +222,15 @@ __device__ inline void epilogue_chain(const double *par_c, const double *st, con
     gstar_c[2] = -gc0 + gc1;
     gstar_c[3] = -1.5 * gc0 + 2.0 * gc1 - 0.25 * gc2;
   }
+}
+
+// convenience: both halves back to back (single-launch modes of the logp kernel)
+template <bool kCoherent>
+__device__ inline void epilogue_chain(const double *par_c, const double *st, const double *src, int slots, int P,
+                                      double lognorm, double *logp, double *gpar_c, double *gstar_c, double *gmean) {
+  const int lane = threadIdx.x & 31;
+  const EpiPre pre = epilogue_pre(par_c + (lane < P ? lane : 0) * XO_NPAR, st);
+  epilogue_chain<kCoherent>(pre, st, src, slots, P, lognorm, logp, gpar_c, gstar_c, gmean);
 }
 
 }  // namespace xo

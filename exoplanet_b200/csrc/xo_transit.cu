@@ -162,19 +162,26 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
   __shared__ double pacc[XO_NGRAD][kThreads];      // per-thread cotangent-scaled sums of the current planet
   // heaviest chains first (ma.order, optional): CTAs are dispatched in blockIdx order, so the long
   // ones start early and the short ones fill the tail of the launch
-  const int64_t c = ma.order ? ma.order[blockIdx.y] : blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slot = blockIdx.x * kWarps + warp;
-  if (kModel && ma.stage_from_params)
-    stage_chain_from_params(sm, ma, mean, dtk, wk, c, P, K);
-  else
-    stage_chain(sm, elem, cl, mean, dtk, wk, c, P, K);
+  const uint32_t start = (uint32_t)min((int64_t)slot * L, N);
+  const uint32_t end = (uint32_t)min((int64_t)slot * L + L, N);
+  // Everything up to pdl_wait() is independent of the kernel that precedes this one in the stream
+  // (the model prologue writing elem / cl): when launched as its programmatic dependent this part
+  // overlaps the prologue's tail -- accumulators zeroed, this warp's time stamps pulled into L2.
+  xo::pdl_launch_dependents();
   for (int i = lane; i < XO_MAX_PLANETS * XO_NGRAD; i += 32) (&gacc[warp][0][0])[i] = 0.0;
 #pragma unroll
   for (int j = 0; j < XO_NGRAD + 3; ++j) lacc[j][threadIdx.x] = 0.0;
 #pragma unroll
   for (int j = 0; j < XO_NGRAD; ++j) pacc[j][threadIdx.x] = 0.0;
-  __syncwarp();
+  for (uint32_t i = start + 16u * lane; i < end; i += 16u * 32u) xo::prefetch_l2(t + i);
+  xo::pdl_wait();
+  const int64_t c = ma.order ? ma.order[blockIdx.y] : blockIdx.y;
+  if (kModel && ma.stage_from_params)
+    stage_chain_from_params(sm, ma, mean, dtk, wk, c, P, K);
+  else
+    stage_chain(sm, elem, cl, mean, dtk, wk, c, P, K);
   double *const gl = &lacc[0][threadIdx.x];          // g[j]  at gl[j * kThreads]
   double *const gsl = &lacc[XO_NGRAD][threadIdx.x];  // gs[j] at gsl[j * kThreads]
   double *const pa = &pacc[0][threadIdx.x];          // sum over this lane's samples of scale * g[j]
@@ -250,8 +257,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
     }
   };
 
-  const uint32_t start = (uint32_t)min((int64_t)slot * L, N);
-  const uint32_t end = (uint32_t)min((int64_t)slot * L + L, N);
   // Sweep steps of 32*kUnroll cadences, then one final pass (last = true) that only flushes what
   // is left in the queues -- written as ONE loop so the expensive drain body exists once in the
   // binary.  The common step: for sorted t one interval test on two broadcast loads; otherwise
@@ -700,12 +705,12 @@ int check_batch(int64_t N, int64_t C, int64_t P) {
 void launch_transit_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *elem,
                               const double *cl, const double *mean, int64_t C, int P, const double *dtk,
                               const double *wk, int K, Split sp, const double *moments, double *partial,
-                              cudaStream_t st, const ModelArgs *model) {
+                              cudaStream_t st, const ModelArgs *model, bool pdl) {
   dim3 grid(sp.slots / kWarps, (unsigned)C);
   const ModelArgs ma = model ? *model : ModelArgs{};
-#define XO_LAUNCH(MB, VJP, MOM, MODEL)                                                                                  \
-  transit_logp_grad_kernel<MB, VJP, MOM, MODEL><<<grid, kThreads, 0, st>>>(t, y, ivar, N, elem, cl, mean, P, dtk, wk, K, \
-                                                                           sp.L, sp.slots, moments, partial, ma)
+#define XO_LAUNCH(MB, VJP, MOM, MODEL)                                                                                    \
+  xo::launch_pdl(transit_logp_grad_kernel<MB, VJP, MOM, MODEL>, grid, dim3(kThreads), st, pdl, t, y, ivar, N, elem, cl, mean, P, \
+                 dtk, wk, K, sp.L, sp.slots, moments, partial, ma)
   if (ivar == nullptr) {  // light-curve VJP mode: y = bar_lc[C][N][P]
     XO_LAUNCH(3, true, false, false);
     return;

@@ -37,7 +37,7 @@ struct ModelArgs {
 void launch_transit_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *elem,
                               const double *cl, const double *mean, int64_t C, int P, const double *dtk,
                               const double *wk, int K, Split sp, const double *moments, double *partial, cudaStream_t st,
-                              const ModelArgs *model);
+                              const ModelArgs *model, bool pdl = false);
 
 // order[rank] = chain, heaviest expected in-transit work first
 void launch_chain_order(const double *elem, int64_t C, int P, int *order, cudaStream_t st);

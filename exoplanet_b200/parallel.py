@@ -6,7 +6,7 @@ import os
 
 import torch
 
-__all__ = ["world", "shard_bounds", "shard", "gather_chains", "max_over_ranks"]
+__all__ = ["world", "shard_bounds", "shard", "gather_chains", "max_over_ranks", "device_local_cpus", "bind_to_device_numa"]
 
 
 def world():
@@ -55,3 +55,44 @@ def max_over_ranks(value, device=None, group=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device or "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return t.item()
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def device_local_cpus(device_index):
+    """CPUs on the NUMA node the GPU's PCIe root hangs off (sysfs ``local_cpulist``), or None."""
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as fh:
+            cpus = _parse_cpulist(fh.read())
+        return cpus or None
+    except Exception:
+        return None
+
+
+def bind_to_device_numa(device_index):
+    """Pin this process (one per GPU) to the CPUs local to its GPU so that pinned staging buffers
+    allocated afterwards (first touch) and the submitting thread sit on the GPU's side of the
+    socket interconnect: on a 2-socket box a far-side process pays ~2x on every host<->device copy.
+    Returns (cpus_bound_or_None, previous_affinity)."""
+    prev = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    cpus = device_local_cpus(device_index)
+    if prev is None or not cpus:
+        return None, prev
+    use = cpus & prev
+    if not use:
+        return None, prev
+    try:
+        os.sched_setaffinity(0, use)
+    except OSError:
+        return None, prev
+    return use, prev
