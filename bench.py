@@ -71,11 +71,13 @@ class ClockSampler:
         self.path = None
 
     def start(self):
+        if os.environ.get("XO_BENCH_SAMPLER", "1") == "0":  # diagnostic: does the NVML polling perturb the host-side numbers?
+            return
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                                          "-lms", "200"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -396,14 +398,24 @@ def arm_ours(args):
         if rc != 0:
             raise RuntimeError(lib.xo_strerror(rc).decode())
 
-    for _ in range(3):
+    # warm-up: >= W calls AND >= 0.15 s of sustained host<->device traffic -- the PCIe link / copy
+    # engines reach full speed only after tens of ms of activity (tools/numa_probe.py: the same
+    # 3 x 0.8 MB copy takes 185 us cold, 65 us warm), and an MCMC run is sustained traffic
+    w0, nw = time.perf_counter(), 0
+    while nw < max(3, args.warmup) or time.perf_counter() - w0 < 0.15:
         step_host()
+        nw += 1
     barrier()
+    e2e_steps = []
     e0 = time.perf_counter()
     for _ in range(args.steps):
-        step_host()
+        s0 = time.perf_counter()
+        step_host()  # synchronous: returns when logp and the gradients are in host memory
+        e2e_steps.append(time.perf_counter() - s0)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - e0
+    if os.environ.get("XO_BENCH_VERBOSE"):
+        sys.stderr.write("e2e per-step us: " + " ".join("%.0f" % (x * 1e6) for x in e2e_steps) + "\n")
     # ---- e2e with the light curve resident (uploaded once, as a compiled model holds its
     # constants): per step only the parameters go in and logp + gradients come back ----------
     handle = C.c_void_p()
@@ -418,13 +430,20 @@ def arm_ours(args):
         if rc != 0:
             raise RuntimeError(lib.xo_strerror(rc).decode())
 
-    for _ in range(3):
+    w0, nw = time.perf_counter(), 0
+    while nw < max(3, args.warmup) or time.perf_counter() - w0 < 0.05:
         step_resident()
+        nw += 1
     barrier()
+    res_steps = []
     r0 = time.perf_counter()
     for _ in range(args.steps):
+        s0 = time.perf_counter()
         step_resident()
+        res_steps.append(time.perf_counter() - s0)
     res_s = time.perf_counter() - r0
+    if os.environ.get("XO_BENCH_VERBOSE"):
+        sys.stderr.write("resident per-step us: " + " ".join("%.0f" % (x * 1e6) for x in res_steps) + "\n")
     lib.xo_transit_data_destroy(handle)
     clocks = sampler.stop() if rank == 0 else None
     h2d = sum(h[k].numel() * 8 for k in h)

@@ -13,6 +13,7 @@
 #include <new>
 
 #include "xo_common.cuh"
+#include "xo_transit.cuh"
 
 namespace {
 
@@ -24,23 +25,40 @@ struct DeviceScope {
   int prev = -1;
   cudaError_t err = cudaSuccess;
   cudaStream_t st = nullptr;
+  cudaStream_t side = nullptr;            // second stream: parameter-only work that overlaps the data upload
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   explicit DeviceScope(int device) {
-    static thread_local cudaStream_t cache[64] = {nullptr};
+    struct Cached {
+      cudaStream_t st = nullptr, side = nullptr;
+      cudaEvent_t fork = nullptr, join = nullptr;
+    };
+    static thread_local Cached cache[64];
     err = cudaGetDevice(&prev);
     if (err == cudaSuccess) err = cudaSetDevice(device);
     if (err != cudaSuccess) return;
-    if (device >= 0 && device < 64 && cache[device]) {
-      st = cache[device];
+    if (device >= 0 && device < 64 && cache[device].st) {
+      st = cache[device].st;
+      side = cache[device].side;
+      ev_fork = cache[device].fork;
+      ev_join = cache[device].join;
       return;
     }
     err = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
     if (err != cudaSuccess) return;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
       unsigned long long keep = ~0ull;
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
-    if (device >= 0 && device < 64) cache[device] = st;
+    if (device >= 0 && device < 64) {
+      cache[device].st = st;
+      cache[device].side = side;
+      cache[device].fork = ev_fork;
+      cache[device].join = ev_join;
+    }
   }
   ~DeviceScope() {
     if (prev >= 0) cudaSetDevice(prev);
@@ -71,10 +89,14 @@ struct Arena {
   char *base = nullptr;
   size_t off = 0, cap = 0;
   cudaStream_t st;
+  cudaStream_t also = nullptr;  // a second stream that touched the arena: the free is ordered after it too
+  cudaEvent_t also_ev = nullptr;
   cudaError_t err = cudaSuccess;
   Arena(size_t bytes, cudaStream_t s) : cap(bytes), st(s) { err = cudaMallocAsync((void **)&base, bytes ? bytes : 256, s); }
   ~Arena() {
-    if (base) cudaFreeAsync(base, st);
+    if (!base) return;
+    if (also && also_ev && cudaEventRecord(also_ev, also) == cudaSuccess) cudaStreamWaitEvent(st, also_ev, 0);
+    cudaFreeAsync(base, st);
   }
   template <typename T>
   T *take(size_t n) {
@@ -279,10 +301,18 @@ int xo_transit_model_logp_grad_host(const double *t, const double *y, const doub
   double *dlp = dout, *dgp = dlp + C, *dgs = dgp + C * P * XO_NPAR, *dgm = dgs + C * XO_NSTAR;
   XO_TRY(g_stage_in.ensure(nin * 8));
   XO_TRY(g_stage_out.ensure(nout * 8));
-  // the light curve: three DMAs straight from the caller's (ideally pinned) memory
+  const bool split = xo::model_split_supported();
+  if (split) {
+    ar.also = ds.side;
+    ar.also_ev = ds.ev_join;
+    XO_TRY(cudaEventRecord(ds.ev_fork, ds.st));  // the arena exists from here on in stream order
+  }
+  // the light curve: three DMAs straight from the caller's (ideally pinned) memory, enqueued first
   XO_TRY(h2d(dt, t, (size_t)N * 8, ds.st));
   XO_TRY(h2d(dy, y, (size_t)N * 8, ds.st));
   XO_TRY(h2d(dv, ivar, (size_t)N * 8, ds.st));
+  cudaStream_t ps = split ? ds.side : ds.st;  // the parameters and the prologue overlap that upload
+  if (split) XO_TRY(cudaStreamWaitEvent(ps, ds.ev_fork, 0));
   {  // the parameters: packed through pinned staging -> one DMA
     double *hin = reinterpret_cast<double *>(g_stage_in.p);
     size_t o = 0;
@@ -295,11 +325,21 @@ int xo_transit_model_logp_grad_host(const double *t, const double *y, const doub
     put(mean, (size_t)C);
     put(dtk, (size_t)K);
     put(wk, (size_t)K);
-    XO_TRY(h2d(din, hin, nin * 8, ds.st));
+    XO_TRY(h2d(din, hin, nin * 8, ps));
   }
+  if (split) {
+    XO_RC(xo::model_logp_grad_phases(dt, dy, dv, N, dp, dst, dm, C, P, dd, dw, K, texp, use_in_transit, lognorm, dmom, dlp, dgp,
+                                     dgs, dgm, dws, ws, ps, 1));
+    XO_TRY(cudaEventRecord(ds.ev_join, ps));
+  }
+  // data moments (one pass, a few microseconds): the sweep then reads t only and skips quiet steps
   XO_RC(xo_transit_data_moments(dt, dy, dv, N, dmom, ds.st));
-  XO_RC(xo_transit_model_logp_grad(dt, dy, dv, N, dp, dst, dm, C, P, dd, dw, K, texp, use_in_transit, lognorm, dmom, dlp,
-                                   dgp, dgs, dgm, dws, ws, ds.st));
+  if (split) {
+    XO_TRY(cudaStreamWaitEvent(ds.st, ds.ev_join, 0));
+    ar.also = nullptr;  // joined: the main stream is ordered after everything the side stream did
+  }
+  XO_RC(xo::model_logp_grad_phases(dt, dy, dv, N, dp, dst, dm, C, P, dd, dw, K, texp, use_in_transit, lognorm, dmom, dlp, dgp, dgs,
+                                   dgm, dws, ws, ds.st, split ? 2 : 3));
   double *hout = reinterpret_cast<double *>(g_stage_out.p);
   XO_TRY(d2h(hout, dout, nout * 8, ds.st));
   XO_TRY(cudaStreamSynchronize(ds.st));

@@ -68,18 +68,28 @@ inline ModelLayout model_layout(int64_t N, int64_t C, int64_t P) {
 
 }  // namespace
 
-extern "C" {
+namespace xo {
 
-size_t xo_transit_model_workspace(int64_t N, int64_t C, int64_t P) {
-  if (N <= 0 || C <= 0 || P <= 0) return 0;
-  return model_layout(N, C, P).bytes;
+static int model_launches() {
+  // XO_MODEL_LAUNCHES: 3 = prologue kernel, logp kernel, epilogue kernel (default: measured fastest);
+  //                    2 = prologue kernel + logp kernel whose last CTA per chain runs the epilogue;
+  //                    1 = one kernel (every CTA re-derives its chain's elements at start)
+  static const int launches = [] {
+    const char *v = getenv("XO_MODEL_LAUNCHES");
+    return v && *v ? atoi(v) : 3;
+  }();
+  return launches;
 }
 
-int xo_transit_model_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *par,
-                               const double *star, const double *mean, int64_t C, int64_t P, const double *dtk,
-                               const double *wk, int K, double texp, int use_in_transit, double lognorm,
-                               const double *moments, double *logp, double *gpar, double *gstar, double *gmean,
-                               void *workspace, size_t workspace_bytes, void *stream) {
+bool model_split_supported() { return model_launches() == 3; }
+
+// phases: 1 = prologue only (may run on another stream than the rest), 2 = logp kernel + epilogue
+// (the caller has ordered them after the prologue), 3 = everything on `stream`
+int model_logp_grad_phases(const double *t, const double *y, const double *ivar, int64_t N, const double *par,
+                           const double *star, const double *mean, int64_t C, int64_t P, const double *dtk, const double *wk,
+                           int K, double texp, int use_in_transit, double lognorm, const double *moments, double *logp,
+                           double *gpar, double *gstar, double *gmean, void *workspace, size_t workspace_bytes, void *stream,
+                           int phases) {
   if (int rc = xo::check_batch(N, C, P)) return rc;
   if (K < 1 || K > XO_MAX_STENCIL) return XO_ERANGE;
   if (C == 0) return 0;
@@ -93,15 +103,10 @@ int xo_transit_model_logp_grad(const double *t, const double *y, const double *i
   double *cl = reinterpret_cast<double *>(ws + L.off_cl);
   double *partial = reinterpret_cast<double *>(ws + L.off_partial);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // XO_MODEL_LAUNCHES: 3 = prologue kernel, logp kernel, epilogue kernel (default: measured fastest);
-  //                    2 = prologue kernel + logp kernel whose last CTA per chain runs the epilogue;
-  //                    1 = one kernel (every CTA re-derives its chain's elements at start)
-  static const int launches = [] {
-    const char *v = getenv("XO_MODEL_LAUNCHES");
-    return v && *v ? atoi(v) : 3;
-  }();
+  const int launches = model_launches();
   const int64_t cp = C * P;
   if (launches == 1 || launches == 2) {
+    if (phases != 3) return XO_EINVAL;
     unsigned *counter = reinterpret_cast<unsigned *>(ws + L.off_counter);
     cudaError_t e = cudaMemsetAsync(counter, 0, (size_t)C * sizeof(unsigned), st);
     if (e != cudaSuccess) return -(int)e;
@@ -126,7 +131,9 @@ int xo_transit_model_logp_grad(const double *t, const double *y, const double *i
     const char *v = getenv("XO_MODEL_PDL");
     return !(v && *v == '0');
   }();
-  model_prologue_kernel<<<(unsigned)((2 * cp + 63) / 64), 64, 0, st>>>(par, star, C, (int)P, texp, use_in_transit, elem, cl);
+  if (phases & 1)
+    model_prologue_kernel<<<(unsigned)((2 * cp + 63) / 64), 64, 0, st>>>(par, star, C, (int)P, texp, use_in_transit, elem, cl);
+  if (!(phases & 2)) return xo::launch_status();
   static const int lpt = [] {
     const char *v = getenv("XO_MODEL_HEAVY_FIRST");
     return v && *v ? atoi(v) : 0;  // measured slower on B200: heavy CTAs co-resident on an SM contend
@@ -141,12 +148,31 @@ int xo_transit_model_logp_grad(const double *t, const double *y, const double *i
     pord = &ord;
   }
   // heavy-first inserts the ordering kernel between prologue and logp kernel: no early start then
+  // (nor when the prologue ran on another stream: the kernel preceding this one is then unrelated)
   xo::launch_transit_logp_grad(t, y, ivar, N, elem, cl, mean, C, (int)P, dtk, wk, K, L.sp, moments, partial, st, pord,
-                               pdl && !pord);
+                               pdl && !pord && phases == 3);
   cudaError_t le = xo::launch_pdl(model_epilogue_kernel, dim3((unsigned)((C + 3) / 4)), dim3(128), st, pdl, par, star,
                                   (const double *)partial, L.sp.slots, C, (int)P, lognorm, logp, gpar, gstar, gmean);
   if (le != cudaSuccess) return -(int)le;
   return xo::launch_status();
+}
+
+}  // namespace xo
+
+extern "C" {
+
+size_t xo_transit_model_workspace(int64_t N, int64_t C, int64_t P) {
+  if (N <= 0 || C <= 0 || P <= 0) return 0;
+  return model_layout(N, C, P).bytes;
+}
+
+int xo_transit_model_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *par,
+                               const double *star, const double *mean, int64_t C, int64_t P, const double *dtk,
+                               const double *wk, int K, double texp, int use_in_transit, double lognorm,
+                               const double *moments, double *logp, double *gpar, double *gstar, double *gmean,
+                               void *workspace, size_t workspace_bytes, void *stream) {
+  return xo::model_logp_grad_phases(t, y, ivar, N, par, star, mean, C, P, dtk, wk, K, texp, use_in_transit, lognorm, moments, logp,
+                                    gpar, gstar, gmean, workspace, workspace_bytes, stream, 3);
 }
 
 // element blocks only (prologue), for callers that want to inspect / reuse them

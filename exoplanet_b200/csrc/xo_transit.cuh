@@ -39,6 +39,15 @@ void launch_transit_logp_grad(const double *t, const double *y, const double *iv
                               const double *wk, int K, Split sp, const double *moments, double *partial, cudaStream_t st,
                               const ModelArgs *model, bool pdl = false);
 
+// the model evaluation in phases (xo_model.cu): 1 = prologue only, 2 = logp kernel + epilogue, 3 = all.
+// A host driver can run phase 1 on a side stream while the light curve is still being uploaded.
+bool model_split_supported();
+int model_logp_grad_phases(const double *t, const double *y, const double *ivar, int64_t N, const double *par,
+                           const double *star, const double *mean, int64_t C, int64_t P, const double *dtk, const double *wk,
+                           int K, double texp, int use_in_transit, double lognorm, const double *moments, double *logp,
+                           double *gpar, double *gstar, double *gmean, void *workspace, size_t workspace_bytes, void *stream,
+                           int phases);
+
 // order[rank] = chain, heaviest expected in-transit work first
 void launch_chain_order(const double *elem, int64_t C, int P, int *order, cudaStream_t st);
 
