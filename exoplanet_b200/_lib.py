@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libxo_b200.so")
+# XO_B200_LIB: an alternative build of the same library (tuning experiments); default = the in-tree build
+LIB_PATH = os.environ.get("XO_B200_LIB") or os.path.join(_HERE, "libxo_b200.so")
 
 NEL = 16
 NGRAD = 10

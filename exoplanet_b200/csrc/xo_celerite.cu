@@ -837,16 +837,25 @@ __global__ void __launch_bounds__(kThreadsGp) gp_grad_final_kernel(const double 
 __global__ void gp_grad_fold_kernel(const double *__restrict__ gpart, int nctas, const double *__restrict__ S0,
                                     const double *__restrict__ w0, const double *__restrict__ Qf, double eps, int64_t B,
                                     double *__restrict__ ghyper /* [B][3] */) {
-  const int64_t bch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t bch = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (bch >= B) return;
+  const int lane = threadIdx.x & 31;
   double ga = 0.0, gc = 0.0, gh = 0.0, gw2 = 0.0;
-  for (int i = 0; i < nctas; ++i) {
+  for (int i = lane; i < nctas; i += 32) {  // one warp per chain, fixed order (deterministic)
     const double *p = gpart + (bch * nctas + i) * 4;
     ga += p[0];
     gc += p[1];
     gh += p[2];
     gw2 += p[3];
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ga += __shfl_xor_sync(kFullGp, ga, o);
+    gc += __shfl_xor_sync(kFullGp, gc, o);
+    gh += __shfl_xor_sync(kFullGp, gh, o);
+    gw2 += __shfl_xor_sync(kFullGp, gw2, o);
+  }
+  if (lane != 0) return;
   const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
   const double sgn = k.under ? 1.0 : -1.0;
   gc += 2.0 * k.c * gw2;
@@ -861,13 +870,17 @@ __global__ void gp_grad_fold_kernel(const double *__restrict__ gpart, int nctas,
   ghyper[3 * bch + 2] = ga * s0 * w + gc * dcdQ + gh * (dcdQ * f + k.c * dfdQ);
 }
 
+// one warp per chain: lane-strided partial sums in CTA order, then a fixed butterfly (deterministic)
 __global__ void gp_fold_kernel(const double *__restrict__ cta_ll, int nctas, int64_t N, int64_t B,
                                double *__restrict__ loglike) {
-  const int64_t bch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t bch = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (bch >= B) return;
+  const int lane = threadIdx.x & 31;
   double acc = 0.0;
-  for (int i = 0; i < nctas; ++i) acc += cta_ll[bch * nctas + i];
-  loglike[bch] = -0.5 * acc - 0.5 * (double)N * 1.8378770664093454835606594728112;  // log(2 pi)
+  for (int i = lane; i < nctas; i += 32) acc += cta_ll[bch * nctas + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFullGp, acc, o);
+  if (lane == 0) loglike[bch] = -0.5 * acc - 0.5 * (double)N * 1.8378770664093454835606594728112;  // log(2 pi)
 }
 
 struct GpLayout {
@@ -938,7 +951,7 @@ int xo_celerite_sho_loglike(const double *t, const double *y, const double *diag
   gp_aggregate_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, pref, tot);
   gp_cta_scan_kernel<<<(unsigned)B, kThreadsGp, 0, st>>>(tot, L.nctas, S0, w0, Q, eps, state);
   gp_loglike_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, pref, state, ll, nullptr, nullptr);
-  gp_fold_kernel<<<(unsigned)((B + 63) / 64), 64, 0, st>>>(ll, L.nctas, N, B, loglike);
+  gp_fold_kernel<<<(unsigned)((B + 3) / 4), 128, 0, st>>>(ll, L.nctas, N, B, loglike);
   return xo::launch_status();
 }
 
@@ -967,7 +980,7 @@ int xo_celerite_sho_solve(const double *t, const double *y, const double *diag, 
   gp_cta_scan_kernel<<<(unsigned)B, kThreadsGp, 0, st>>>(at(L.off_tot), L.nctas, S0, w0, Q, eps, at(L.off_state));
   gp_loglike_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, at(L.off_pref), at(L.off_state),
                                                  at(L.off_ll), at(L.off_rec), nullptr);
-  gp_fold_kernel<<<(unsigned)((B + 63) / 64), 64, 0, st>>>(at(L.off_ll), L.nctas, N, B, loglike);
+  gp_fold_kernel<<<(unsigned)((B + 3) / 4), 128, 0, st>>>(at(L.off_ll), L.nctas, N, B, loglike);
   gp_bwd_aggregate_kernel<<<grid, kThreadsGp, 0, st>>>(t, N, S0, w0, Q, eps, L.T, at(L.off_rec), at(L.off_bpref),
                                                        at(L.off_bcta));
   gp_bwd_cta_scan_kernel<<<(unsigned)B, kThreadsGp, 0, st>>>(at(L.off_bcta), L.nctas, at(L.off_bstate));
@@ -1001,13 +1014,13 @@ int xo_celerite_sho_grad(const double *t, const double *y, const double *diag, i
   gp_cta_scan_kernel<<<(unsigned)B, kThreadsGp, 0, st>>>(at(L.off_tot), L.nctas, S0, w0, Q, eps, at(L.off_state));
   gp_loglike_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, at(L.off_pref), at(L.off_state),
                                                  at(L.off_ll), nullptr, at(L.off_rec5));
-  gp_fold_kernel<<<(unsigned)((B + 63) / 64), 64, 0, st>>>(at(L.off_ll), L.nctas, N, B, loglike);
+  gp_fold_kernel<<<(unsigned)((B + 3) / 4), 128, 0, st>>>(at(L.off_ll), L.nctas, N, B, loglike);
   gp_grad_aggregate_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, at(L.off_rec5), at(L.off_gpref),
                                                         at(L.off_gcta));
   gp_grad_cta_scan_kernel<<<(unsigned)B, kThreadsGp, 0, st>>>(at(L.off_gcta), L.nctas, at(L.off_gstate));
   gp_grad_final_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, at(L.off_rec5), at(L.off_gpref),
                                                     at(L.off_gstate), gy, gdiag, at(L.off_gpart));
-  gp_grad_fold_kernel<<<(unsigned)((B + 63) / 64), 64, 0, st>>>(at(L.off_gpart), L.nctas, S0, w0, Q, eps, B, ghyper);
+  gp_grad_fold_kernel<<<(unsigned)((B + 3) / 4), 128, 0, st>>>(at(L.off_gpart), L.nctas, S0, w0, Q, eps, B, ghyper);
   return xo::launch_status();
 }
 

@@ -33,7 +33,10 @@
 
 namespace {
 
-constexpr int kWarps = 4;
+#ifndef XO_TRANSIT_WARPS
+#define XO_TRANSIT_WARPS 4  // warps per CTA of the logp kernel (build-time knob for occupancy experiments)
+#endif
+constexpr int kWarps = XO_TRANSIT_WARPS;
 constexpr int kThreads = kWarps * 32;
 using xo::kNBase;
 using xo::Split;
@@ -137,8 +140,12 @@ __global__ void __launch_bounds__(256) transit_lc_fwd_kernel(const double *__res
 // ---------------------------------------------------------------------------
 // logp + grad (see header comment).  kMinBlocks trades registers for resident warps.
 // ---------------------------------------------------------------------------
-constexpr int kUnroll = 4;                      // 32-cadence groups loaded per sweep step
-constexpr int kQueue = 32 * (kUnroll + 1);      // 31 left over + kUnroll * 32 new entries
+// 32-cadence groups per sweep step: with the data moments the sweep is sparse (only steps that
+// can contain an in-transit cadence are visited), and a fine step wastes the least work around
+// each transit; without them every cadence is read (t, y, ivar) and 4 loads in flight per array
+// hide the latency.
+constexpr int sweep_unroll(bool moments) { return (moments || kWarps > 4) ? 1 : 4; }
+constexpr int kQueueMax = 32 * (4 + 1);  // 31 left over + kUnroll * 32 new entries
 
 // kVjp = false: Gaussian log-likelihood (y, ivar, mean) and its gradient.
 // kVjp = true : reverse pass of the light curve alone: `y` is the cotangent bar_lc[C][N][P]
@@ -156,6 +163,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
     const double *__restrict__ moments, double *__restrict__ partial, const xo::ModelArgs ma) {
   constexpr bool kBase = !kVjp && !kMoments;  // accumulate the per-cadence Gaussian terms in the sweep
   __shared__ ChainSmem sm;
+  constexpr int kUnroll = sweep_unroll(kMoments);
+  constexpr int kQueue = 32 * (kUnroll + 1);
+  static_assert(kQueue <= kQueueMax, "queue");
   __shared__ uint32_t queue[kWarps][XO_MAX_PLANETS][kQueue];
   __shared__ double gacc[kWarps][XO_MAX_PLANETS][XO_NGRAD];
   __shared__ double lacc[XO_NGRAD + 3][kThreads];  // per-thread gradient accumulators of one drain
