@@ -581,7 +581,9 @@ __global__ void __launch_bounds__(256) orbit_eval_kernel(const double *__restric
 // over planets (through shared memory) and the gradient accumulation.
 // ---------------------------------------------------------------------------
 constexpr int kRvTile = 64;
-__global__ void rv_logp_grad_kernel(const double *__restrict__ t, const double *__restrict__ y,
+// kCap: cap registers at 64 (two 512-thread CTAs, i.e. three 320-thread CTAs at P = 5, per SM)
+template <bool kCap>
+__global__ void __launch_bounds__(kRvTile *XO_MAX_PLANETS, kCap ? 2 : 1) rv_logp_grad_kernel(const double *__restrict__ t, const double *__restrict__ y,
                                     const double *__restrict__ ivar, int64_t N, const double *__restrict__ elem,
                                     const double *__restrict__ gamma, int P, int64_t L, int slots,
                                     double *__restrict__ partial) {
@@ -879,7 +881,14 @@ int xo_rv_logp_grad(const double *t, const double *y, const double *ivar, int64_
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   double *partial = static_cast<double *>(workspace);
   dim3 grid(sp.slots, (unsigned)C), block(kRvTile, (unsigned)P);
-  rv_logp_grad_kernel<<<grid, block, 0, st>>>(t, y, ivar, N, elem, gamma, (int)P, sp.L, sp.slots, partial);
+  static const bool cap = [] {  // XO_RV_REGCAP=0: uncapped build (66 registers, 2 CTAs of 320 threads per SM)
+    const char *v = getenv("XO_RV_REGCAP");
+    return !(v && *v == '0');
+  }();
+  if (cap)
+    rv_logp_grad_kernel<true><<<grid, block, 0, st>>>(t, y, ivar, N, elem, gamma, (int)P, sp.L, sp.slots, partial);
+  else
+    rv_logp_grad_kernel<false><<<grid, block, 0, st>>>(t, y, ivar, N, elem, gamma, (int)P, sp.L, sp.slots, partial);
   const int nacc = 2 + (int)P * XO_NGRAD_RV;
   const int64_t tot = C * nacc;
   fold_rv_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(partial, sp.slots, nacc, C, (int)P, lognorm, logp, grv,

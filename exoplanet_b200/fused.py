@@ -242,8 +242,12 @@ class TransitModel:
     sampler-side parameters, entirely on the device (the fused counterpart of the PyMC model
     in /root/reference/docs/tutorials/data-and-models.md:458-509)."""
 
-    def __init__(self, data, texp=None, oversample=7, order=0, use_in_transit=True, use_moments=True):
+    def __init__(self, data, texp=None, oversample=7, order=0, use_in_transit=True, use_moments=True, cadence_group=None):
+        """``cadence_group``: a torch.distributed process group (or True for the default group) when
+        ``data`` holds only this rank's block of the light curve (parallel.cadence_bounds): logp and the
+        gradients are then summed over the group with one packed all-reduce per evaluation."""
         self.data = data
+        self.cadence_group = cadence_group
         self.texp = 0.0 if texp is None else float(texp)
         self.use_in_transit = bool(use_in_transit)
         self.use_moments = bool(use_moments)
@@ -272,6 +276,10 @@ class TransitModel:
                                                       _ptr(d.moments() if self.use_moments else None), _ptr(logp), _ptr(gpar), _ptr(gstar),
                                                       _ptr(gmean), _ptr(self._ws), self._ws.numel() * 8, _lib.stream_ptr()),
                        "transit_model_logp_grad")
+        if self.cadence_group is not None:
+            from . import parallel
+
+            parallel.allreduce_sum_([logp, gpar, gstar, gmean], None if self.cadence_group is True else self.cadence_group)
         return logp, gpar, gstar, gmean
 
     def __call__(self, par, star, mean):

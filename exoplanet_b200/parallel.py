@@ -6,7 +6,8 @@ import os
 
 import torch
 
-__all__ = ["world", "shard_bounds", "shard", "gather_chains", "max_over_ranks", "device_local_cpus", "bind_to_device_numa"]
+__all__ = ["world", "shard_bounds", "shard", "gather_chains", "max_over_ranks", "cadence_bounds", "allreduce_sum_",
+           "device_local_cpus", "bind_to_device_numa"]
 
 
 def world():
@@ -55,6 +56,36 @@ def max_over_ranks(value, device=None, group=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device or "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return t.item()
+
+
+def cadence_bounds(n_cadences, world_size, rank, align=32):
+    """Cadence-parallel sharding ("few chains, huge N"): rank g owns the contiguous block
+    [lo, hi) of the time series, block edges on multiples of ``align`` cadences.  log-likelihood and
+    gradients are sums over cadences, so every rank evaluates ALL chains on its block and one
+    all-reduce of (1 + n_params) doubles per chain (``allreduce_sum_``) completes the step."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    units = -(-int(n_cadences) // align)
+    lo, hi = shard_bounds(units, world_size, rank)
+    return min(lo * align, n_cadences), min(hi * align, n_cadences)
+
+
+def allreduce_sum_(tensors, group=None):
+    """In-place SUM over ranks of a list of tensors with ONE collective: packed into a single flat
+    buffer (latency-bound exchange: bytes are irrelevant on NVLink, the launch count is not).
+    No-op outside a process group."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return tensors
+    flat = torch.cat([x.reshape(-1) for x in tensors])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    o = 0
+    for x in tensors:
+        n = x.numel()
+        x.copy_(flat[o:o + n].view_as(x))
+        o += n
+    return tensors
 
 
 def _parse_cpulist(text):
