@@ -287,6 +287,28 @@ def extra_configs(lib, dev, args):
         res["g"] = torch.autograd.grad(ll, pj + hj)
 
     ms = _time_steps(jstep, 5, flush)
+    # ---- the lock-step HMC driver on configs[1] (128 chains x N=1e5), one CUDA graph per transition
+    from exoplanet_b200.sampling import BatchedHMC, TransitPosterior
+
+    p1 = synthetic.transit_params(128, 1, seed=synthetic.SEED + 9, ecc=0.5)
+    q_init = TransitPosterior.pack(p1["period"], p1["t0"], p1["ecc"], p1["omega"], p1["b"], p1["ror"], p1["u1"], p1["u2"], p1["mean"]).to(dev)
+    sig = torch.tensor([1e-3, 0.02, 0.3, 0.3, 0.3, 0.3, 1.5, 1.5, 1e-3], dtype=torch.float64, device=dev)
+    post = TransitPosterior(fused.TransitModel(fused.TransitData(t, y, np.full(N, SIGMA), device=dev)), 1, q_init, sig)
+    for use_graph in (True, False):
+        hmc = BatchedHMC(post, q_init, step_size=1e-6, n_leapfrog=8, seed=1, use_graph=use_graph)
+        for _ in range(3):
+            hmc.transition()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            hmc.transition()
+        b.record()
+        torch.cuda.synchronize()
+        msj = a.elapsed_time(b) / 20
+        out["HMC driver, configs[1] x 128 chains, 8 leapfrog steps per transition, %s" % ("CUDA graph replay" if use_graph else "eager launches")] = {
+            "value": 128 * 8 / (msj * 1e-3), "unit": "leapfrog model+grad evals/s (incl. parameter transforms and their autograd)",
+            "ms_per_transition": msj, "chain_transitions_per_s": 128 / (msj * 1e-3)}
     out["configs[3] transit + SHO GP, N=1e6: logL + d/d(period, b, r, S0, w0, Q) (torch-level composition)"] = {
         "value": 1.0 / (ms * 1e-3), "unit": "model+grad evals/s", "ms_per_step": ms}
     return out

@@ -1,0 +1,209 @@
+"""Device-resident batched Hamiltonian Monte Carlo over many chains in lock-step: what
+turns model+gradient evaluations per second into samples per second.
+
+PyMC's NUTS (the sampler of /root/reference/docs/tutorials/data-and-models.md:458-509) advances ONE
+chain per process and crosses the Python/C boundary at every leapfrog step.  Here every chain of the
+batch takes the same number of leapfrog steps per transition, all state (positions, momenta, step
+sizes, mass matrices, accept decisions) lives on the device, nothing synchronises with the host, and one
+whole transition -- L fused logp+grad launches plus the elementwise updates around them -- is captured
+in a CUDA graph and replayed.
+
+This is plain HMC with per-chain dual-averaging step sizes and a diagonal mass matrix estimated in
+warm-up; NUTS's tree doubling (a data-dependent trajectory length per chain) is NOT implemented.
+"""
+import math
+
+import torch
+
+__all__ = ["BatchedHMC", "TransitPosterior"]
+
+
+class TransitPosterior:
+    """log posterior and its gradient for a batch of chains, in an unconstrained vector q[C, D]:
+
+        per planet   log period, t0, sqrt(e) cos w, sqrt(e) sin w, b, log(r/R*)
+        per chain    logit q1, logit q2 (Kipping 2013 limb darkening, distributions.py:98-102), mean flux
+
+    with independent Normal priors on the unconstrained coordinates (prior_mu / prior_sigma, [D] or
+    [C, D]).  The likelihood and its parameter gradients come from the fused kernels
+    (fused.TransitModel); the change of variables is a handful of elementwise torch ops whose
+    chain rule torch.autograd applies.  r_star = m_star = 1."""
+
+    NPL = 6
+
+    def __init__(self, model, n_planets, prior_mu, prior_sigma):
+        self.model = model
+        self.P = int(n_planets)
+        self.D = self.NPL * self.P + 3
+        dev = model.data.device
+        self.mu = torch.as_tensor(prior_mu, dtype=torch.float64, device=dev)
+        self.sigma = torch.as_tensor(prior_sigma, dtype=torch.float64, device=dev)
+
+    @staticmethod
+    def pack(period, t0, ecc, omega, b, ror, u1, u2, mean):
+        """numpy/torch parameters ([C, P] and [C]) -> q[C, D]"""
+        as_t = lambda x: torch.as_tensor(x, dtype=torch.float64)  # noqa: E731
+        period, t0, ecc, omega, b, ror = [as_t(x) for x in (period, t0, ecc, omega, b, ror)]
+        u1, u2, mean = [as_t(x) for x in (u1, u2, mean)]
+        se = torch.sqrt(ecc)
+        pl = torch.stack([torch.log(period), t0, se * torch.cos(omega), se * torch.sin(omega), b, torch.log(ror)], dim=-1)
+        q1 = (u1 + u2) ** 2
+        q2 = 0.5 * u1 / (u1 + u2)
+        logit = lambda x: torch.log(x) - torch.log1p(-x)  # noqa: E731
+        return torch.cat([pl.reshape(pl.shape[0], -1), torch.stack([logit(q1), logit(q2), mean], dim=-1)], dim=-1)
+
+    def unpack(self, q):
+        """q[C, D] -> (par[C, P, 8], star[C, 4], mean[C]) as differentiable torch expressions"""
+        C = q.shape[0]
+        pl = q[:, : self.NPL * self.P].reshape(C, self.P, self.NPL)
+        period = torch.exp(pl[..., 0])
+        h, k = pl[..., 2], pl[..., 3]
+        ecc = h * h + k * k
+        omega = torch.atan2(k, h)
+        zero = torch.zeros_like(period)
+        par = torch.stack([period, pl[..., 1], ecc, omega, pl[..., 4], torch.exp(pl[..., 5]), zero, zero], dim=-1)
+        q1 = torch.sigmoid(q[:, -3])
+        q2 = torch.sigmoid(q[:, -2])
+        sq = torch.sqrt(q1)
+        one = torch.ones_like(q1)
+        star = torch.stack([one, one, 2.0 * sq * q2, sq * (1.0 - 2.0 * q2)], dim=-1)
+        return par, star, q[:, -1]
+
+    def __call__(self, q):
+        """(log posterior[C], gradient[C, D]); no host synchronisation."""
+        q = q.detach().requires_grad_(True)
+        with torch.enable_grad():
+            par, star, mean = self.unpack(q)
+            z = (q - self.mu) / self.sigma
+            lp = self.model(par, star, mean) - 0.5 * (z * z).sum(dim=-1)
+            (g,) = torch.autograd.grad(lp.sum(), q)
+        return lp.detach(), g
+
+
+class BatchedHMC:
+    """HMC over C chains in lock-step.  ``logp_grad(q[C, D]) -> (logp[C], grad[C, D])`` must not
+    synchronise with the host (TransitPosterior, or any torch expression).
+
+    state (device tensors): q, logp, grad, step size eps[C], inverse diagonal mass inv_mass[C, D]."""
+
+    def __init__(self, logp_grad, q0, step_size=1e-2, n_leapfrog=16, seed=0, target_accept=0.8, use_graph=True):
+        self.f = logp_grad
+        self.q = q0.detach().clone().contiguous()
+        dev = self.q.device
+        C, D = self.q.shape
+        self.L = int(n_leapfrog)
+        self.eps = torch.full((C,), float(step_size), dtype=torch.float64, device=dev)
+        self.inv_mass = torch.ones((C, D), dtype=torch.float64, device=dev)
+        self.gen = torch.Generator(device=dev)
+        self.gen.manual_seed(int(seed))
+        self.logp, self.grad = self.f(self.q)
+        self.logp, self.grad = self.logp.clone(), self.grad.clone()
+        self.accept_prob = torch.zeros(C, dtype=torch.float64, device=dev)
+        self.energy_error = torch.zeros(C, dtype=torch.float64, device=dev)
+        self.target = float(target_accept)
+        self.n_evals = 0
+        self._graph = None
+        self._use_graph = bool(use_graph) and dev.type == "cuda"
+        # dual averaging (Hoffman & Gelman 2014, algorithm 5), one instance per chain
+        self._mu = torch.log(10.0 * self.eps)
+        self._log_eps_bar = torch.zeros_like(self.eps)
+        self._hbar = torch.zeros_like(self.eps)
+        self._m = 0
+
+    # one transition for every chain; everything in place so that it can be captured once and replayed
+    def _transition(self):
+        q, eps, im = self.q, self.eps[:, None], self.inv_mass
+        p = torch.randn(q.shape, dtype=q.dtype, device=q.device, generator=self.gen) / torch.sqrt(im)
+        h0 = -self.logp + 0.5 * (p * p * im).sum(dim=-1)
+        qn, g, lp = q, self.grad, self.logp
+        p = p + 0.5 * eps * g
+        for i in range(self.L):
+            qn = qn + eps * im * p
+            lp, g = self.f(qn)
+            p = p + (eps if i + 1 < self.L else 0.5 * eps) * g
+        h1 = -lp + 0.5 * (p * p * im).sum(dim=-1)
+        dh = h0 - h1
+        dh = torch.where(torch.isfinite(dh), dh, torch.full_like(dh, -float("inf")))
+        a = torch.exp(torch.clamp(dh, max=0.0))
+        u = torch.rand(a.shape, dtype=a.dtype, device=a.device, generator=self.gen)
+        acc = u < a
+        self.q.copy_(torch.where(acc[:, None], qn, q))
+        self.logp.copy_(torch.where(acc, lp, self.logp))
+        self.grad.copy_(torch.where(acc[:, None], g, self.grad))
+        self.accept_prob.copy_(a)
+        self.energy_error.copy_(-dh)
+
+    def transition(self):
+        if not self._use_graph:
+            self._transition()
+        else:
+            if self._graph is None:
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):  # warm-up on a side stream, as graph capture requires
+                    self._transition()
+                torch.cuda.current_stream().wait_stream(s)
+                self._graph = torch.cuda.CUDAGraph()
+                self._graph.register_generator_state(self.gen)
+                with torch.cuda.graph(self._graph):
+                    self._transition()
+                self.n_evals += self.L
+            self._graph.replay()
+        self.n_evals += self.L
+
+    def _adapt_step(self, gamma=0.05, t0=10.0, kappa=0.75):
+        self._m += 1
+        m = self._m
+        w = 1.0 / (m + t0)
+        self._hbar.mul_(1.0 - w).add_(w * (self.target - self.accept_prob))
+        log_eps = self._mu - math.sqrt(m) / gamma * self._hbar
+        eta = m ** (-kappa)
+        self._log_eps_bar.mul_(1.0 - eta).add_(eta * log_eps)
+        self.eps.copy_(torch.exp(log_eps))
+
+    def warmup(self, n, adapt_mass=True):
+        """n transitions of step-size adaptation; half way through, the diagonal mass matrix is set from
+        the variance of the positions seen since the first quarter, pooled over the chains (they all
+        target the same posterior, so C chains x k draws estimate it far better than k draws of one
+        chain), and the step-size search restarts."""
+        half = n // 2 if adapt_mass else -1
+        s1 = torch.zeros_like(self.q)
+        s2 = torch.zeros_like(self.q)
+        k = 0
+        for it in range(n):
+            self.transition()
+            self._adapt_step()
+            if adapt_mass and it >= n // 4 and it < half:
+                s1 += self.q
+                s2 += self.q * self.q
+                k += 1
+            if it + 1 == half and k > 4:
+                nk = k * self.q.shape[0]
+                m1 = s1.sum(dim=0, keepdim=True) / nk
+                var = (s2.sum(dim=0, keepdim=True) / nk - m1 * m1) * (nk / (nk - 1.0))
+                var = ((nk / (nk + 5.0)) * var + 1e-3 * (5.0 / (nk + 5.0))).expand_as(self.q)  # Stan's shrinkage
+                # rescale the step so that eps^2 * inv_mass keeps its order of magnitude
+                scale = torch.sqrt(self.inv_mass.mean(dim=-1) / var.mean(dim=-1))
+                self.inv_mass.copy_(var)
+                self.eps.mul_(scale)
+                self._mu = torch.log(10.0 * self.eps)
+                self._log_eps_bar.zero_()
+                self._hbar.zero_()
+                self._m = 0
+        if self._m > 0:
+            self.eps.copy_(torch.exp(self._log_eps_bar))
+
+    def sample(self, n):
+        """n transitions; returns dict(q[n, C, D], logp[n, C], accept_prob[n, C], energy_error[n, C]) on the device."""
+        C, D = self.q.shape
+        dev = self.q.device
+        out = dict(q=torch.empty((n, C, D), dtype=torch.float64, device=dev), logp=torch.empty((n, C), dtype=torch.float64, device=dev),
+                   accept_prob=torch.empty((n, C), dtype=torch.float64, device=dev),
+                   energy_error=torch.empty((n, C), dtype=torch.float64, device=dev))
+        for i in range(n):
+            self.transition()
+            out["q"][i].copy_(self.q)
+            out["logp"][i].copy_(self.logp)
+            out["accept_prob"][i].copy_(self.accept_prob)
+            out["energy_error"][i].copy_(self.energy_error)
+        return out
