@@ -36,12 +36,17 @@ for SWEEPFLAG in "" "--full-sweep"; do for mb in 2 3 4 5; do for w in 16 24 32; 
     | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'])" >> $OUT/${TAG}_sweep.txt
 done; done; done
 for mb in 2 3 4; do echo -n "kepler minblocks=$mb " >> $OUT/${TAG}_sweep.txt; XO_KEPLER_MINBLOCKS=$mb timeout 120 python bench.py --steps 3 --warmup 3 --no-cpu 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['kepler'])" >> $OUT/${TAG}_sweep.txt; done
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"transit_|model_|kepler_fwd|fold_" -c 60 --csv --log-file $OUT/${TAG}_launches.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"transit_|model_|kepler_fwd|fold_" -c 80 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 5 --warmup 3 --no-cpu > $OUT/${TAG}_ncu_bench.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:transit_logp_grad_kernel -s 3 -c 1 -f -o $OUT/${TAG}_prof_transit \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-kepler > $OUT/${TAG}_ncu_transit.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:kepler_fwd_kernel -s 4 -c 1 -f -o $OUT/${TAG}_prof_kepler \
     python bench.py --steps 1 --warmup 3 --no-cpu > $OUT/${TAG}_ncu_kepler.log 2>&1
+# the other kernels of the section-8 rows: RV likelihood (configs[2]) and the celerite scans (configs[3])
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:rv_logp_grad_kernel -s 4 -c 1 -f -o $OUT/${TAG}_prof_rv \
+    python bench.py --steps 1 --warmup 3 --no-cpu --no-kepler > $OUT/${TAG}_ncu_rv.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gp_loglike_kernel|gp_grad_final_kernel" -s 6 -c 1 -f -o $OUT/${TAG}_prof_gp \
+    python bench.py --steps 1 --warmup 3 --no-cpu --no-kepler > $OUT/${TAG}_ncu_gp.log 2>&1
 # sanitizers on the small smoke problem (memory errors, shared-memory races in the queue kernels)
 timeout 600 compute-sanitizer --tool memcheck --report-api-errors no --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_memcheck.log 2>&1; echo "memcheck exit $?" >> $OUT/${TAG}_memcheck.log
 timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_racecheck.log 2>&1; echo "racecheck exit $?" >> $OUT/${TAG}_racecheck.log
