@@ -287,6 +287,17 @@ def extra_configs(lib, dev, args):
         res["g"] = torch.autograd.grad(ll, pj + hj)
 
     ms = _time_steps(jstep, 5, flush)
+    # ---- configs[4]'s chain count on ONE GPU: 1024 chains per step (the fixed ~30 us of prologue,
+    # epilogue and launches is amortised over 8x the work of the headline step)
+    pb = synthetic.transit_params(1024, 1, seed=synthetic.SEED + 11, ecc=0.5)
+    parb = fused.pack_params(d(pb["period"]), d(pb["t0"]), d(pb["ecc"]), d(pb["omega"]), d(pb["b"]), d(pb["ror"]), d(pb["m_planet"]), d(pb["K"]))
+    one = torch.ones(1024, dtype=torch.float64, device=dev)
+    starb = fused.pack_star(one, one, d(pb["u1"]), d(pb["u2"]))
+    meanb = d(pb["mean"])
+    big = fused.TransitModel(fused.TransitData(t, y, np.full(N, SIGMA), device=dev))
+    msb = _time_steps(lambda: big.logp_grad(parb, starb, meanb), 10, flush)
+    out["configs[1] with 1024 chains on one GPU (N=1e5, e=0.5)"] = {"value": 1024 / (msb * 1e-3), "unit": "model+grad evals/s", "ms_per_step": msb,
+                                                                  "chains": 1024}
     # ---- the lock-step HMC driver on configs[1] (128 chains x N=1e5), one CUDA graph per transition
     from exoplanet_b200.sampling import BatchedHMC, TransitPosterior
 
@@ -335,6 +346,8 @@ def arm_ours(args):
     if world > 1:
         import torch.distributed as dist
 
+        # keep stdout to the one JSON line: NCCL's version banner goes to stdout at NCCL_DEBUG >= VERSION
+        os.environ["NCCL_DEBUG"] = os.environ.get("XO_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.require_cuda()
 
