@@ -42,6 +42,18 @@ def test_argument_errors_do_not_need_a_gpu():
     assert lib.xo_kepler_fwd(None, None, None, None, -1, None) == 1  # XO_EINVAL
     assert lib.xo_transit_lc_fwd(None, 10, None, None, 1, 9, None, None, 1, None, None) == 2  # XO_ERANGE (P > 8)
     assert b"invalid" in lib.xo_strerror(1)
+    # every family validates before it touches the device: negative sizes, null pointers, limits
+    assert lib.xo_celerite_sho_loglike(None, None, None, 10, None, None, None, 1, 1e-5, None, None, 0, None) == 1
+    assert lib.xo_celerite_sho_grad(None, None, None, -1, None, None, None, 1, 1e-5, None, None, None, None, None, 0, None) == 1
+    assert lib.xo_celerite_sho_grad(None, None, None, 10, None, None, None, 0, 1e-5, None, None, None, None, None, 0, None) == 0  # no chains
+    assert lib.xo_celerite_sho_grad(None, None, None, 10, None, None, None, 70000, 1e-5, None, None, None, None, None, 0, None) == 2
+    assert lib.xo_celerite_sho_grad_workspace(0, 1) == 0 and lib.xo_celerite_sho_grad_workspace(1000, 2) > 0
+    assert lib.xo_transit_data_moments(None, None, None, 0, None, None) == 1
+    assert lib.xo_transit_model_logp_grad(None, None, None, 10, None, None, None, 0, 1, None, None, 1, 0.0, 1, 0.0, None, None, None,
+                                          None, None, None, 0, None) == 0  # zero chains: nothing to do
+    assert lib.xo_transit_model_logp_grad(None, None, None, 10, None, None, None, 4, 1, None, None, 1, 0.0, 1, 0.0, None, None, None,
+                                          None, None, None, 0, None) == 1
+    assert lib.xo_transit_model_workspace(1000, 4, 2) > 0 and lib.xo_transit_model_workspace(0, 4, 2) == 0
 
 
 def test_product_never_imports_the_oracle():
