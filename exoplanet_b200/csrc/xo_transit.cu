@@ -10,18 +10,23 @@
 // the first chain touches them); per-chain state is the element block [C][P][16],
 // cl [C][3], mean [C]; outputs are O(#params) per chain.
 //
-// Design of the logp+grad kernel (the dominant kernel):
-//  * one CTA = 4 independent warps of one chain; the chain's element block, limb-darkening
-//    vector and exposure stencil are staged once in shared memory;
-//  * each warp sweeps a contiguous range of cadences 32 at a time with coalesced loads,
-//    accumulates the out-of-transit part of the likelihood, and tests the in_transit
-//    window per planet (two FMAs and a floor - no Kepler solve);
-//  * in-window (cadence, planet) pairs are appended (ballot + prefix popcount, i.e. in
-//    a fixed order) to a per-warp, per-planet queue in shared memory; whenever a queue
-//    holds >= 32 entries the warp drains 32 of them with all lanes busy on the expensive
-//    part (Kepler solve -> projection -> limb-darkening integral -> analytic VJP);
-//  * gradient sums use fixed-order shuffle trees and fixed-order accumulation, so results
-//    are bit-reproducible run to run; a second tiny kernel folds the per-warp partials.
+// Design of the logp+grad kernel (the dominant kernel; DESIGN.md section 5):
+//  * one CTA = 4 independent warps of one chain, each owning a contiguous cadence range; the
+//    chain's element block, limb-darkening vector and exposure stencil are staged once in
+//    shared memory;
+//  * with the data moments and sorted t the sweep is sparse: steps of 32 cadences are tested 32
+//    at a time (lane l: can step l contain an in-transit cadence of any planet?), one ballot
+//    gives the hit mask and only hit steps are loaded; otherwise every cadence is read, 128 per
+//    step, and the out-of-transit part of the likelihood is accumulated on the way;
+//  * in-window (cadence, planet) pairs are appended (ballot + prefix popcount, i.e. in a fixed
+//    order) to a per-warp, per-planet queue in shared memory; whenever a queue holds >= 32
+//    entries the warp drains 32 of them with all lanes busy on the expensive part (Kepler
+//    solve -> projection -> limb-darkening integral -> analytic VJP);
+//  * per-lane gradient sums live in shared memory and are added up over the warp in a fixed
+//    order once per warp (or when the drained planet changes), so results are bit-reproducible
+//    run to run; a second tiny kernel (or the model epilogue) folds the per-warp partials;
+//  * launched as a programmatic dependent of the model prologue: everything before pdl_wait()
+//    (accumulator zeroing, L2 prefetch of the time stamps) overlaps the prologue's tail.
 #include <cuda_runtime.h>
 
 #include <cstdlib>

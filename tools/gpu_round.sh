@@ -23,6 +23,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 lscpu | grep -E "Model name|^CPU\(s\)|Thread|Core|Socket" >> $OUT/${TAG}_gpu.txt; nproc >> $OUT/${TAG}_gpu.txt
 timeout 1500 python -m pytest tests -m gpu -q > $OUT/${TAG}_pytest.log 2>&1; echo "pytest exit $?" >> $OUT/${TAG}_pytest.log
 for ML in 1 2; do XO_MODEL_LAUNCHES=$ML timeout 600 python -m pytest tests/test_gpu_fused.py -m gpu -q > $OUT/${TAG}_pytest_launches$ML.log 2>&1; echo "pytest(XO_MODEL_LAUNCHES=$ML) exit $?" >> $OUT/${TAG}_pytest.log; done
+XO_MODEL_PDL=0 timeout 600 python -m pytest tests/test_gpu_fused.py -m gpu -q > $OUT/${TAG}_pytest_nopdl.log 2>&1; echo "pytest(XO_MODEL_PDL=0) exit $?" >> $OUT/${TAG}_pytest.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke exit $?" >> $OUT/${TAG}_smoke.log
 timeout 900 python bench.py --steps 20 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench exit $?" >> $OUT/${TAG}_bench.err
 timeout 300 python bench.py --impl reference --steps 20 --warmup 2 > $OUT/${TAG}_bench_ref.json 2>> $OUT/${TAG}_bench.err
