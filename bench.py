@@ -346,8 +346,8 @@ def arm_ours(args):
     if world > 1:
         import torch.distributed as dist
 
-        # keep stdout to the one JSON line: NCCL's version banner goes to stdout at NCCL_DEBUG >= VERSION
-        os.environ["NCCL_DEBUG"] = os.environ.get("XO_NCCL_DEBUG", "WARN")
+        # keep stdout to the one JSON line: NCCL logs (its version banner at NCCL_DEBUG >= VERSION) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.require_cuda()
 
