@@ -107,6 +107,8 @@ __device__ inline void limb_coeffs(double u1, double u2, double *cl3) {
 // accumulated cotangents): computed before the partial sums are waited for.
 struct EpiPre {
   double period, e, b, mt, a, n, sw, cw, sme, spe, x, y, sE0, cE0, M0, ome2, F, cosi, sini;
+  // reciprocals the reverse pass multiplies by (computed here, before the partial sums are waited for)
+  double rR, ra, rome2, rn, rper, rsme, rspe, rmt, rsini, rxy;
 };
 __device__ inline EpiPre epilogue_pre(const double *q, const double *st) {
   EpiPre r;
@@ -115,20 +117,42 @@ __device__ inline EpiPre epilogue_pre(const double *q, const double *st) {
   r.e = q[2];
   r.b = q[4];
   r.mt = Ms + q[6];
-  r.a = cbrt(kGGrav * r.mt * r.period * r.period / (4.0 * kPi * kPi));
-  r.n = 2.0 * kPi / r.period;
-  sincos(q[3], &r.sw, &r.cw);
-  r.sme = sqrt(1.0 - r.e);
-  r.spe = sqrt(1.0 + r.e);
+  // same instruction-lean forms as prologue_pair (this half overlaps the logp kernel's tail, but the
+  // sooner it is done the sooner the fold can start)
+  r.a = cbrt(kGGrav * r.mt * r.period * r.period * (1.0 / (4.0 * kPi * kPi)));
+  r.n = 2.0 * kPi * rcp_fast(r.period);
+  if (fabs(q[3]) <= kPi) {
+    double d0, d1;
+    sincos_0pi(fabs(q[3]), r.sw, r.cw, d0, d1);
+    r.sw = q[3] < 0.0 ? -r.sw : r.sw;
+  } else {
+    sincos(q[3], &r.sw, &r.cw);
+  }
+  r.sme = sqrt_fast(1.0 - r.e);
+  r.spe = sqrt_fast(1.0 + r.e);
   r.y = r.sme * r.cw;
   r.x = r.spe * (1.0 + r.sw);
-  const double E0 = 2.0 * atan2(r.y, r.x);
-  sincos(E0, &r.sE0, &r.cE0);
+  const double hE = atan2_pos(fabs(r.y), r.x);
+  const double E0 = 2.0 * (r.y < 0.0 ? -hE : hE);
+  const double x2y2 = fma(r.x, r.x, r.y * r.y);
+  const double rxy = x2y2 > 0.0 ? rcp_fast(x2y2) : 0.0;
+  r.sE0 = 2.0 * r.x * r.y * rxy;
+  r.cE0 = x2y2 > 0.0 ? (r.x - r.y) * (r.x + r.y) * rxy : 1.0;
   r.M0 = E0 - r.e * r.sE0;
   r.ome2 = (1.0 - r.e) * (1.0 + r.e);
-  r.F = (1.0 + r.e * r.sw) / r.ome2;
-  r.cosi = r.F * R / r.a * r.b;
-  r.sini = sqrt((1.0 - r.cosi) * (1.0 + r.cosi));
+  r.F = (1.0 + r.e * r.sw) * rcp_fast(r.ome2);
+  r.cosi = r.F * R * rcp_fast(r.a) * r.b;
+  r.sini = sqrt_fast((1.0 - r.cosi) * (1.0 + r.cosi));
+  r.rR = rcp_fast(R);
+  r.ra = rcp_fast(r.a);
+  r.rome2 = rcp_fast(r.ome2);
+  r.rper = rcp_fast(r.period);
+  r.rn = r.period * (1.0 / (2.0 * kPi));
+  r.rsme = rcp_fast(r.sme);
+  r.rspe = rcp_fast(r.spe);
+  r.rmt = rcp_fast(r.mt);
+  r.rsini = r.sini > 0.0 ? rcp_fast(r.sini) : 0.0;
+  r.rxy = rxy;
   return r;
 }
 
@@ -178,34 +202,35 @@ __device__ inline void epilogue_chain(const EpiPre &pre, const double *st, const
   const double R = st[0];
   double gR = 0.0, gMs = 0.0;
   if (lane < P) {
-    const double period = pre.period, e = pre.e, b = pre.b, mt = pre.mt, a = pre.a, n = pre.n, sw = pre.sw, cw = pre.cw;
+    const double e = pre.e, b = pre.b, a = pre.a, n = pre.n, sw = pre.sw, cw = pre.cw;
     const double sme = pre.sme, spe = pre.spe, x = pre.x, y = pre.y, sE0 = pre.sE0, cE0 = pre.cE0, M0 = pre.M0;
-    const double ome2 = pre.ome2, F = pre.F, cosi = pre.cosi, sini = pre.sini;
+    const double F = pre.F, cosi = pre.cosi;
     // cotangents of the element block: g = (t0, tref, n, e, cw, sw, cosi, sini, aor, ror)
+    const double rR = pre.rR, ra = pre.ra, rome2 = pre.rome2, rn = pre.rn;
     double gt0 = g[0], ge = g[3], gcw = g[4], gsw = g[5];
-    double ga = g[8] / R;
-    gR += -g[8] * a / (R * R);
-    double gcosi = g[6] + (sini > 0.0 ? -g[7] * cosi / sini : 0.0);
-    double gF = gcosi * R * b / a;
-    gR += gcosi * F * b / a;
-    ga += -gcosi * F * R * b / (a * a);
-    double gb = gcosi * F * R / a;
-    ge += gF * (sw / ome2 + (1.0 + e * sw) * 2.0 * e / (ome2 * ome2));
-    gsw += gF * e / ome2;
-    double gM0 = -g[1] / n;
-    double gn = g[2] + g[1] * M0 / (n * n);
-    double gP = -gn * n / period;
+    double ga = g[8] * rR;
+    gR += -g[8] * a * rR * rR;
+    double gcosi = g[6] - g[7] * cosi * pre.rsini;
+    double gF = gcosi * R * b * ra;
+    gR += gcosi * F * b * ra;
+    ga += -gcosi * F * R * b * ra * ra;
+    double gb = gcosi * F * R * ra;
+    ge += gF * (sw * rome2 + (1.0 + e * sw) * 2.0 * e * rome2 * rome2);
+    gsw += gF * e * rome2;
+    double gM0 = -g[1] * rn;
+    double gn = g[2] + g[1] * M0 * rn * rn;
+    double gP = -gn * n * pre.rper;
     double gE0 = gM0 * (1.0 - e * cE0);
     ge += -gM0 * sE0;
-    const double rr = 1.0 / (x * x + y * y);
+    const double rr = pre.rxy;
     double gy = 2.0 * gE0 * x * rr, gx = -2.0 * gE0 * y * rr;
     gcw += gy * sme;
-    ge += -gy * cw / (2.0 * sme);
+    ge += -gy * cw * 0.5 * pre.rsme;
     gsw += gx * spe;
-    ge += gx * (1.0 + sw) / (2.0 * spe);
+    ge += gx * (1.0 + sw) * 0.5 * pre.rspe;
     double gomega = -gcw * sw + gsw * cw;
-    gP += ga * (2.0 / 3.0) * a / period;
-    double gmt = ga * a / (3.0 * mt);
+    gP += ga * (2.0 / 3.0) * a * pre.rper;
+    double gmt = ga * a * (1.0 / 3.0) * pre.rmt;
     gMs += gmt;
     double *o = gpar_c + lane * XO_NPAR;
     o[0] = gP;
