@@ -329,3 +329,56 @@ def test_resident_data_handle_matches_device_path():
     assert rc == 0
     for a_, b_ in zip(out, out2):
         assert np.allclose(a_, b_, rtol=1e-9, atol=1e-9 * np.abs(a_).max())
+
+
+def test_host_entry_point_from_two_threads():
+    """the host-buffer call keeps per-thread streams, events and pinned staging: two sampler threads
+    driving it concurrently (ctypes drops the GIL) get exactly what each gets alone"""
+    import ctypes as C
+    import threading
+
+    from exoplanet_b200 import _lib
+
+    lib = _lib.require_cuda()
+    N, Cn, P = 20000, 4, 2
+    t = synthetic.cadence_times(N)
+    y = synthetic.noise(N)
+    ivar = np.full(N, 1 / 5e-4 ** 2)
+    dtk, wk = np.zeros(1), np.ones(1)
+    f = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    def problem_for(seed):
+        p = synthetic.transit_params(Cn, P, seed=seed)
+        par = np.ascontiguousarray(np.stack([p["period"], p["t0"], p["ecc"], p["omega"], p["b"], p["ror"], p["m_planet"], p["K"]], axis=-1))
+        star = np.ascontiguousarray(np.stack([np.ones(Cn), np.ones(Cn), p["u1"], p["u2"]], axis=-1))
+        return par, star, np.ascontiguousarray(p["mean"])
+
+    def call(args):
+        par, star, mean = args
+        out = [np.empty(Cn), np.empty((Cn, P, 8)), np.empty((Cn, 4)), np.empty(Cn)]
+        rc = lib.xo_transit_model_logp_grad_host(f(t), f(y), f(ivar), N, f(par), f(star), f(mean), Cn, P, f(dtk), f(wk), 1, 0.0, 1, 0.0,
+                                                 *[f(x) for x in out], 0)
+        assert rc == 0
+        return out
+
+    probs = [problem_for(101), problem_for(202)]
+    alone = [call(pr) for pr in probs]
+    results = [None, None]
+    errors = []
+
+    def worker(k):
+        try:
+            for _ in range(25):
+                results[k] = call(probs[k])
+        except Exception as exc:  # surfaced below: an assert inside a thread would otherwise be lost
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    for k in range(2):
+        for a, b in zip(alone[k], results[k]):
+            assert np.array_equal(a, b)
