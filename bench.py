@@ -346,9 +346,23 @@ def arm_ours(args):
     if world > 1:
         import torch.distributed as dist
 
-        # keep stdout to the one JSON line: NCCL logs (its version banner at NCCL_DEBUG >= VERSION) go to stderr
+        # keep stdout to the one JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION/WARN
+        # (and honours NCCL_DEBUG_FILE only above VERSION), so raise the level to WARN, point the log at
+        # stderr, and park fd 1 on stderr while the communicator is created
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     lib = _lib.require_cuda()
 
     C_loc = args.chains
