@@ -622,6 +622,10 @@ def arm_ours(args):
                      "traffic": _ncu_traffic("r01_transit.txt", "transit"), "traffic_unit": "bytes of DRAM per launch (ncu, profiles/r01_transit.txt)",
                      "algorithmic_bytes_per_launch": ALG_BYTES_PER_CHAIN_CADENCE * C_loc * N_CADENCES,
                      "kernel": "transit_logp_grad_kernel", "peak_source": peak_src,
+                     "duration_ms": ms_dev / args.steps,
+                     "duration_note": "CUDA events around the whole 3-kernel step (prologue + this kernel + epilogue, chained by programmatic "
+                                      "dependent launch, so the kernel cannot be bracketed alone without breaking the overlap): a lower bound on "
+                                      "the kernel's own rate; ncu times it at 69 us of the step (profiles/r01_launches.txt)",
                      "note": "nominal 24 B per (chain,cadence); the chains share t,y,sigma through L2 (DRAM traffic = `traffic`), the kernel is latency/fp64-bound, not HBM-bound (DESIGN.md section 5)"},
         "clocks": clocks, "wall_s": wall,
     }
