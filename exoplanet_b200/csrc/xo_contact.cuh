@@ -66,7 +66,7 @@ __device__ inline int cp_solve_side(double a, double e, double cw, double sw, do
     if (g > 0.0) hi = x; else lo = x;
     // (a zero or denormal slope gives inf / NaN here, which the bracket test below turns into a bisection)
     double xn = kFast ? fma(-g, rcp_fast(dir * dg), x) : x - g / (dir * dg);
-    if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
+    if (!(xn >= lo && xn <= hi)) xn = 0.5 * (lo + hi);  // (>=, <=: a converged iterate sits ON the bracket edge it just set)
     const double step = fabs(xn - x);
     x = xn;
     if (step <= (kFast ? 3e-8 : 1e-15) * fabs(x) + 1e-300 || hi - lo <= 4e-16 * hi) break;

@@ -156,6 +156,7 @@ __device__ inline EpiPre epilogue_pre(const double *q, const double *st) {
   return r;
 }
 
+#if defined(__CUDACC__)  // (tests/hostcheck compiles the prologue above for the CPU; what follows needs a warp)
 // Warp-collective epilogue of ONE chain: lane l sums slots l, l+32, ... of every accumulator
 // (ascending), a fixed-order butterfly combines the 32 lane sums (deterministic), lane p < P runs
 // the reverse pass of planet p's prologue (pre = epilogue_pre of that planet), lane 0 the reverse
@@ -273,5 +274,6 @@ __device__ inline void epilogue_chain(const double *par_c, const double *st, con
   const EpiPre pre = epilogue_pre(par_c + (lane < P ? lane : 0) * XO_NPAR, st);
   epilogue_chain<kCoherent>(pre, st, src, slots, P, lognorm, logp, gpar_c, gstar_c, gmean);
 }
+#endif  // __CUDACC__
 
 }  // namespace xo
