@@ -25,6 +25,15 @@ def test_shard_bounds_partition():
     assert torch.equal(torch.cat([parallel.shard(x, 3, r) for r in range(3)]), x)
 
 
+def test_cpulist_parsing_and_binding_is_harmless_without_a_gpu():
+    assert parallel._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert parallel._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    cpus, prev = parallel.bind_to_device_numa(0)  # no CUDA device here: nothing to bind to, affinity untouched
+    assert prev == before and os.sched_getaffinity(0) == before
+    assert cpus is None or cpus <= before
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
