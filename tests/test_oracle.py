@@ -92,13 +92,41 @@ def test_celerite_gradient_golden(golden):
         seen += 1
         gr = c["grad"]
         n = gr["n"]
-        ll, gth, gy, gd = O.celerite_sho_grad(t[:n], y[:n], diag[:n], c["S0"], c["w0"], c["Q"], eps=0.0)
-        assert abs(ll - gr["loglike"]) < 1e-10 * max(1.0, abs(gr["loglike"]))
-        ref = np.array(gr["hyper"])
-        assert np.all(np.abs(gth - ref) < 1e-9 * (1.0 + np.abs(ref))), (c["Q"], gth, ref)
-        assert np.max(np.abs(gy - np.array(gr["gy"]))) < 1e-9 * (1.0 + np.max(np.abs(gr["gy"])))
-        assert np.max(np.abs(gd - np.array(gr["gdiag"]))) < 1e-9 * (1.0 + np.max(np.abs(gr["gdiag"])))
+        for impl in (O.celerite_sho_grad, O.celerite_sho_grad_c):  # pure-Python and C restatements
+            ll, gth, gy, gd = impl(t[:n], y[:n], diag[:n], c["S0"], c["w0"], c["Q"], eps=0.0)
+            assert abs(ll - gr["loglike"]) < 1e-10 * max(1.0, abs(gr["loglike"]))
+            ref = np.array(gr["hyper"])
+            assert np.all(np.abs(gth - ref) < 1e-9 * (1.0 + np.abs(ref))), (c["Q"], gth, ref)
+            assert np.max(np.abs(gy - np.array(gr["gy"]))) < 1e-9 * (1.0 + np.max(np.abs(gr["gy"])))
+            assert np.max(np.abs(gd - np.array(gr["gdiag"]))) < 1e-9 * (1.0 + np.max(np.abs(gr["gdiag"])))
     assert seen >= 3  # under-damped, critically-ish damped (Q = 1/sqrt 2), over-damped
+
+
+def test_celerite_gradient_c_matches_python_and_finite_differences():
+    rng = np.random.default_rng(21)
+    N = 3000
+    t = np.sort(rng.uniform(0, 400, N))
+    diag = (0.1 + 0.05 * rng.uniform(size=N)) ** 2
+    y = np.sin(t) + 0.1 * rng.normal(size=N)
+    for Q, eps in ((3.0, 1e-5), (0.3, 1e-5), (0.5, 1e-5)):
+        a = O.celerite_sho_grad(t[:500], y[:500], diag[:500], 1.3, 2.1, Q, eps=eps)
+        b = O.celerite_sho_grad_c(t[:500], y[:500], diag[:500], 1.3, 2.1, Q, eps=eps)
+        assert abs(a[0] - b[0]) < 1e-11 * (1 + abs(a[0]))
+        for u, v in zip(a[1:], b[1:]):
+            assert np.max(np.abs(u - v)) < 1e-10 * (1 + np.max(np.abs(u)))
+        # the likelihood the C gradient belongs to is the celerite recurrence of this same file
+        ll, gh, _, _ = O.celerite_sho_grad_c(t, y, diag, 1.3, 2.1, Q, eps=eps)
+        assert abs(ll - O.celerite_sho_loglike(t, y, diag, 1.3, 2.1, Q, eps=eps)) < 1e-9 * (1 + abs(ll))
+        th = np.array([1.3, 2.1, Q])
+        for i in range(3):
+            if Q == 0.5:
+                continue  # clamped: non-smooth in Q, and the recurrence's two nearly equal exponents make its value too noisy for differences
+            hh = 1e-6 * th[i]
+            p, m = th.copy(), th.copy()
+            p[i] += hh
+            m[i] -= hh
+            fd = (O.celerite_sho_loglike(t, y, diag, *p, eps=eps) - O.celerite_sho_loglike(t, y, diag, *m, eps=eps)) / (2 * hh)
+            assert abs(gh[i] - fd) < 2e-6 * (1 + abs(fd)), (Q, i, gh[i], fd)
 
 
 def test_end_to_end_known_answers(golden):
