@@ -8,14 +8,18 @@ sizes, mass matrices, accept decisions) lives on the device, nothing synchronise
 whole transition -- L fused logp+grad launches plus the elementwise updates around them -- is captured
 in a CUDA graph and replayed.
 
-This is plain HMC with per-chain dual-averaging step sizes and a diagonal mass matrix estimated in
-warm-up; NUTS's tree doubling (a data-dependent trajectory length per chain) is NOT implemented.
+``BatchedHMC`` is plain HMC (fixed number of leapfrog steps) with per-chain dual-averaging step sizes
+and a diagonal mass matrix estimated in warm-up.  ``BatchedNUTS`` adds the No-U-Turn criterion: the
+trajectory of every chain doubles until it turns back on itself (multinomial sampling over the tree,
+generalised U-turn test on every completed subtree, as in Stan / PyMC), still in lock-step -- all chains
+take the 2^j leapfrog steps of doubling j together, chains whose tree has already ended are masked, and
+the host looks at the device once per doubling ("is any chain still growing?").
 """
 import math
 
 import torch
 
-__all__ = ["BatchedHMC", "TransitPosterior"]
+__all__ = ["BatchedHMC", "BatchedNUTS", "TransitPosterior"]
 
 
 class TransitPosterior:
@@ -207,3 +211,142 @@ class BatchedHMC:
             out["accept_prob"][i].copy_(self.accept_prob)
             out["energy_error"][i].copy_(self.energy_error)
         return out
+
+
+def _popcount(n):
+    return bin(n).count("1")
+
+
+def _trailing_ones(n):
+    k = 0
+    while n & 1:
+        n >>= 1
+        k += 1
+    return k
+
+
+class BatchedNUTS(BatchedHMC):
+    """No-U-Turn sampler over C chains in lock-step (Hoffman & Gelman 2014; multinomial variant with
+    the generalised U-turn criterion of Betancourt 2017, the scheme of Stan and of PyMC's NUTS that the
+    reference's tutorials run, docs/tutorials/data-and-models.md:458-509).
+
+    One transition: every chain draws a momentum and grows a trajectory by doubling.  Doubling j picks a
+    direction per chain and integrates 2^j leapfrog steps from that end of the tree; the new half is
+    checked for U-turns on each of its completed sub-trees with the O(log) checkpoint scheme (momentum
+    and momentum-sum remembered at even leaves), merged into the tree by biased progressive sampling, and
+    the merged tree is checked once more.  A chain stops when it turns, diverges (energy error > 1000) or
+    reaches ``max_depth``; all chains integrate together, stopped ones are masked.  Step sizes adapt on
+    the mean Metropolis acceptance over the leaves of the last tree (dual averaging), the diagonal mass
+    matrix on the pooled variance of the warm-up draws -- both inherited from BatchedHMC.
+
+    Extra state after a transition: ``depth[C]`` (doublings used), ``diverging[C]``, ``n_leapfrog``."""
+
+    def __init__(self, logp_grad, q0, step_size=1e-2, max_depth=8, seed=0, target_accept=0.8):
+        super().__init__(logp_grad, q0, step_size=step_size, n_leapfrog=1, seed=seed, target_accept=target_accept, use_graph=False)
+        self.max_depth = int(max_depth)
+        C = self.q.shape[0]
+        dev = self.q.device
+        self.depth = torch.zeros(C, dtype=torch.int64, device=dev)
+        self.diverging = torch.zeros(C, dtype=torch.bool, device=dev)
+        self.n_leapfrog = 0
+
+    @staticmethod
+    def _turning(im, p_left, p_right, p_sum):
+        adj = p_sum - 0.5 * (p_left + p_right)
+        return ((im * p_left * adj).sum(-1) <= 0.0) | ((im * p_right * adj).sum(-1) <= 0.0)
+
+    def _transition(self):
+        q0, im = self.q, self.inv_mass
+        C, D = q0.shape
+        dev, dt = q0.device, q0.dtype
+        eps = self.eps[:, None]
+        p0 = torch.randn((C, D), dtype=dt, device=dev, generator=self.gen) / torch.sqrt(im)
+        h0 = -self.logp + 0.5 * (p0 * p0 * im).sum(-1)
+        # the tree: both edges, the current proposal, sum of momenta, log of the summed weights exp(-H)
+        ql, pl, gl = q0.clone(), p0.clone(), self.grad.clone()
+        qr, pr, gr = q0.clone(), p0.clone(), self.grad.clone()
+        q_prop, lp_prop, g_prop = q0.clone(), self.logp.clone(), self.grad.clone()
+        p_sum = p0.clone()
+        log_w = -h0  # weight of the initial point
+        active = torch.ones(C, dtype=torch.bool, device=dev)
+        depth = torch.zeros(C, dtype=torch.int64, device=dev)
+        diverged = torch.zeros(C, dtype=torch.bool, device=dev)
+        acc_sum = torch.zeros(C, dtype=dt, device=dev)
+        n_leaves = torch.zeros(C, dtype=dt, device=dev)
+        ck_p = torch.zeros((self.max_depth + 1, C, D), dtype=dt, device=dev)
+        ck_s = torch.zeros((self.max_depth + 1, C, D), dtype=dt, device=dev)
+        neg_inf = torch.full((C,), -float("inf"), dtype=dt, device=dev)
+        dh_max = torch.zeros(C, dtype=dt, device=dev)
+        for j in range(self.max_depth):
+            go_right = torch.rand(C, dtype=dt, device=dev, generator=self.gen) < 0.5
+            sgn = torch.where(go_right, 1.0, -1.0).to(dt)[:, None]
+            # start from the edge the new half grows out of
+            q = torch.where(go_right[:, None], qr, ql)
+            p = torch.where(go_right[:, None], pr, pl)
+            g = torch.where(go_right[:, None], gr, gl)
+            sub_ok = active.clone()  # still building a valid (non-turning, non-diverging) half
+            s_psum = torch.zeros_like(p)
+            s_logw = neg_inf.clone()
+            s_q, s_lp, s_g = q.clone(), self.logp.clone(), g.clone()
+            first_p = None
+            for n in range(2 ** j):
+                p = p + 0.5 * sgn * eps * g
+                q = q + sgn * eps * im * p
+                lp, g = self.f(q)
+                p = p + 0.5 * sgn * eps * g
+                self.n_leapfrog += 1
+                h = -lp + 0.5 * (p * p * im).sum(-1)
+                dh = h - h0
+                dh = torch.where(torch.isfinite(dh), dh, torch.full_like(dh, float("inf")))
+                dh_max = torch.where(active & (dh.abs() > dh_max.abs()) & torch.isfinite(dh), dh, dh_max)
+                div_now = sub_ok & (dh > 1000.0)
+                diverged |= div_now
+                sub_ok = sub_ok & ~div_now
+                # acceptance statistic over every leaf that was actually visited
+                acc_sum += torch.where(active, torch.exp(torch.clamp(-dh, max=0.0)), torch.zeros_like(dh))
+                n_leaves += active.to(dt)
+                # progressive (uniform-by-weight) sampling of the proposal inside this half
+                w_new = torch.where(sub_ok, -h, neg_inf)
+                s_logw_new = torch.logaddexp(s_logw, w_new)
+                take = sub_ok & (torch.log(torch.rand(C, dtype=dt, device=dev, generator=self.gen)) < w_new - s_logw_new)
+                s_q = torch.where(take[:, None], q, s_q)
+                s_lp = torch.where(take, lp, s_lp)
+                s_g = torch.where(take[:, None], g, s_g)
+                s_logw = torch.where(sub_ok, s_logw_new, s_logw)
+                s_psum = torch.where(sub_ok[:, None], s_psum + p, s_psum)
+                if n == 0:
+                    first_p = p.clone()
+                # U-turn checks inside the half: checkpoints at even leaves, checks at odd ones
+                idx_max = _popcount(n >> 1)
+                if n % 2 == 0:
+                    ck_p[idx_max] = p
+                    ck_s[idx_max] = s_psum
+                else:
+                    idx_min = idx_max - _trailing_ones(n) + 1
+                    for i in range(idx_max, idx_min - 1, -1):
+                        sub_sum = s_psum - ck_s[i] + ck_p[i]
+                        sub_ok = sub_ok & ~self._turning(im, ck_p[i], p, sub_sum)
+            # merge the half into the tree (only where it is valid)
+            merged = active & sub_ok
+            take = merged & (torch.log(torch.rand(C, dtype=dt, device=dev, generator=self.gen)) < s_logw - log_w)
+            q_prop = torch.where(take[:, None], s_q, q_prop)
+            lp_prop = torch.where(take, s_lp, lp_prop)
+            g_prop = torch.where(take[:, None], s_g, g_prop)
+            log_w = torch.where(merged, torch.logaddexp(log_w, s_logw), log_w)
+            p_sum = torch.where(merged[:, None], p_sum + s_psum, p_sum)
+            mr, ml = (merged & go_right)[:, None], (merged & ~go_right)[:, None]
+            qr, pr, gr = torch.where(mr, q, qr), torch.where(mr, p, pr), torch.where(mr, g, gr)
+            ql, pl, gl = torch.where(ml, q, ql), torch.where(ml, p, pl), torch.where(ml, g, gl)
+            depth = depth + active.to(depth.dtype)
+            # the whole tree must not have turned either
+            turned = self._turning(im, pl, pr, p_sum)
+            active = merged & ~turned
+            if j + 1 < self.max_depth and not bool(active.any()):  # the one look at the device per doubling
+                break
+        self.q.copy_(q_prop)
+        self.logp.copy_(lp_prop)
+        self.grad.copy_(g_prop)
+        self.accept_prob.copy_(acc_sum / torch.clamp(n_leaves, min=1.0))
+        self.energy_error.copy_(dh_max)  # largest energy error met along the trajectory
+        self.depth.copy_(depth)
+        self.diverging.copy_(diverged)

@@ -119,3 +119,50 @@ def test_batched_hmc_gaussian_target_cpu():
     assert torch.all((flat.std(0) / sd - 1.0).abs() < 0.1), flat.std(0)
     # the mass matrix picked up the scales (variance per coordinate)
     assert torch.all((hmc.inv_mass.median(0).values / sd ** 2 - 1.0).abs() < 0.6)
+
+
+def test_batched_nuts_gaussian_targets_cpu():
+    """lock-step NUTS (tree doubling, multinomial sampling, generalised U-turn checks on every completed
+    sub-tree): leaves a product of Gaussians with very different scales and a strongly correlated
+    Gaussian invariant -- the second cannot be fixed by the diagonal mass matrix, so it exercises deep trees"""
+    import torch
+
+    from exoplanet_b200.sampling import BatchedNUTS
+
+    torch.manual_seed(0)
+    C = 192
+    mu = torch.tensor([1.0, -2.0, 0.5], dtype=torch.float64)
+    sd = torch.tensor([0.1, 1.0, 10.0], dtype=torch.float64)
+
+    def diag_target(q):
+        z = (q - mu) / sd
+        return -0.5 * (z * z).sum(-1), -z / sd
+
+    nuts = BatchedNUTS(diag_target, mu + sd * torch.randn(C, 3, dtype=torch.float64), step_size=0.05, max_depth=8, seed=3)
+    nuts.warmup(120)
+    out = nuts.sample(120)
+    flat = out["q"].reshape(-1, 3)
+    assert 0.7 < out["accept_prob"].mean().item() < 0.98
+    assert torch.all((flat.mean(0) - mu).abs() < 0.06 * sd), flat.mean(0)
+    assert torch.all((flat.std(0) / sd - 1.0).abs() < 0.08), flat.std(0)
+    assert not nuts.diverging.any() and 1 <= nuts.depth.float().mean().item() <= 5
+
+    cov = torch.tensor([[1.0, 1.9], [1.9, 4.0]], dtype=torch.float64)  # correlation 0.95
+    prec = torch.linalg.inv(cov)
+
+    def corr_target(q):
+        g = -(q @ prec)
+        return 0.5 * (q * g).sum(-1), g
+
+    nuts = BatchedNUTS(corr_target, torch.randn(C, 2, dtype=torch.float64), step_size=0.1, max_depth=8, seed=5)
+    nuts.warmup(120)
+    out = nuts.sample(150)
+    flat = out["q"].reshape(-1, 2)
+    est = torch.cov(flat.T)
+    assert torch.all((est - cov).abs() < 0.12 * torch.sqrt(torch.outer(torch.diag(cov), torch.diag(cov)))), est
+    assert flat.mean(0).abs().max().item() < 0.1
+    assert nuts.depth.float().mean().item() > 2.0  # the ridge needs longer trajectories than the isotropic case
+    # a chain count of one and a tree capped at depth 1 still work (edge cases of the masking)
+    one = BatchedNUTS(corr_target, torch.zeros(1, 2, dtype=torch.float64), step_size=0.3, max_depth=1, seed=1)
+    one.warmup(10, adapt_mass=False)
+    assert one.sample(5)["q"].shape == (5, 1, 2) and int(one.depth.max()) <= 1
