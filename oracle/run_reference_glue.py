@@ -68,8 +68,10 @@ def make_tensor_module():
     pt = types.ModuleType("pytensor.tensor")
     pt.as_tensor_variable = lambda x, **kw: _t(np.asarray(x, dtype=np.float64) if not isinstance(x, np.ndarray) or x.dtype != np.int64 else x)
     for name in ["sqrt", "sin", "cos", "arctan2", "arccos", "arcsin", "zeros_like", "ones_like", "square", "squeeze", "concatenate",
-                 "dot", "arange", "mod", "reshape", "any", "all", "abs", "sum"]:
+                 "dot", "arange", "mod", "reshape", "any", "all", "abs", "sum", "log", "exp"]:
         setattr(pt, name, _wrap(getattr(np, name)))
+    pt.cast = lambda x, dtype: T(np.asarray(x).astype(dtype))
+    pt.extra_ops = types.SimpleNamespace(searchsorted=_wrap(np.searchsorted))  # orbits/ttv.py:178
     pt.stack = lambda xs, axis=0: T(np.stack([np.asarray(x) for x in xs], axis=axis))
     pt.switch = _wrap(np.where)
     pt.gt, pt.lt, pt.eq, pt.ge, pt.le = _wrap(np.greater), _wrap(np.less), _wrap(np.equal), _wrap(np.greater_equal), _wrap(np.less_equal)
@@ -196,6 +198,7 @@ def main():
         warnings.simplefilter("ignore")
         kep = importlib.import_module("exoplanet.orbits.keplerian")
         simple = importlib.import_module("exoplanet.orbits.simple")
+        ttv = importlib.import_module("exoplanet.orbits.ttv")
         ld = importlib.import_module("exoplanet.light_curves.limb_dark")
         sec = importlib.import_module("exoplanet.light_curves.secondary_eclipse")
     assert kep.G_grav == 2942.2062175044193  # the fall-back constants of constants.py:32
@@ -271,6 +274,31 @@ def main():
     out["simple"] = {"t": arr(t5), "relpos": [arr(c) for c in so.get_relative_position(t5)],
                      "in_transit": np.asarray(so.in_transit(t5, r=0.048)).astype(int).tolist(),
                      "lc": arr(lc5.get_light_curve(orbit=so, r=0.048, t=t5))}
+
+    # ---- scenario 6: TTVOrbit (orbits/ttv.py:35-187; tests/orbits/ttv_test.py:23-83): both constructors, a
+    # missing transit (transit_inds), eccentric shape, light curve with and without exposure integration
+    rng = np.random.default_rng(6934104)
+    periods, t0s = [10.5, 56.34], [45.3, 48.1]
+    tmin, tmax = 30.0, 330.0
+    expected = ttv.compute_expected_transit_times(tmin, tmax, periods, t0s)
+    inds = [np.delete(np.arange(len(expected[0])), 3), np.arange(len(expected[1]))]  # planet 0 misses transit #3
+    ttvs = [0.02 * rng.normal(size=len(i)) for i in inds]
+    shape = dict(ecc=np.array([0.3, 0.05]), omega=np.array([0.7, -1.1]), b=np.array([0.3, 0.5]), r_star=1.1, m_star=0.95)
+    oa = ttv.TTVOrbit(period=np.array(periods), t0=np.array([e[0] for e in expected]), ttvs=ttvs, transit_inds=inds, **shape)
+    t6 = np.linspace(tmin, tmax, 6001)
+    r6 = np.array([0.07, 0.11])
+    lc6 = ld.LimbDarkLightCurve(0.35, 0.2)
+    s6 = {"periods": periods, "t0": arr([e[0] for e in expected]), "ttvs": [arr(v) for v in ttvs], "transit_inds": [i.tolist() for i in inds],
+          "shape": {k: (arr(v) if isinstance(v, np.ndarray) else v) for k, v in shape.items()}, "t": arr(t6), "r": arr(r6), "u": [0.35, 0.2],
+          "transit_times": [arr(v) for v in oa.transit_times], "all_transit_times": [arr(v) for v in oa.all_transit_times],
+          "bin_edges": [arr(v) for v in oa._bin_edges], "warp_times": arr(oa._warp_times(_t(t6))),
+          "relpos": [arr(c) for c in oa.get_relative_position(t6)], "rv": arr(oa.get_radial_velocity(t6, K=np.array([5.0, 2.0]))),
+          "in_transit": np.asarray(oa.in_transit(t6, r=r6)).astype(int).tolist(),
+          "lc": arr(lc6.get_light_curve(orbit=oa, r=r6, t=t6)), "lc_texp": arr(lc6.get_light_curve(orbit=oa, r=r6, t=t6, texp=0.05, oversample=5))}
+    ob = ttv.TTVOrbit(transit_times=[np.asarray(v) for v in oa.transit_times], transit_inds=inds, delta_log_period=np.array([1e-4, -2e-4]), **shape)
+    s6["fit"] = {"t0": arr(ob.t0), "ttv_period": arr(ob.ttv_period), "period": arr(ob.period), "ttvs": [arr(v) for v in ob.ttvs],
+                 "lc": arr(lc6.get_light_curve(orbit=ob, r=r6, t=t6))}
+    out["ttv"] = s6
 
     with open(OUT, "w") as fh:
         json.dump(out, fh)
