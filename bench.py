@@ -50,6 +50,57 @@ def _ncu_traffic(summary, kernel_tag):
     return tot if ok else None
 
 
+def _ncu_metric(summary, name):
+    """one metric value per launch from a committed ncu summary (profiles/*.txt), or None"""
+    path = os.path.join(ROOT, "profiles", summary)
+    if not os.path.exists(path):
+        return None
+    for line in open(path):
+        f = line.split()
+        if len(f) >= 2 and f[0] == name:
+            try:
+                return float(f[1].replace(",", ""))
+            except ValueError:
+                return None
+    return None
+
+
+def _first_profile(*names):
+    for n in names:
+        if os.path.exists(os.path.join(ROOT, "profiles", n)):
+            return n
+    return names[-1]
+
+
+def probe_reference_tier():
+    """every run starts by checking whether the reference's own CPU path is importable
+    (a driver-provided install under baseline/_ref, or site-packages).  Tier P = the reference itself (PyTensor +
+    exoplanet-core); tier R = the C restatement of the same mathematics (oracle/)."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    code = ("import sys; sys.path.insert(0, %r); import importlib; miss = []\n"
+            "for m in ('pytensor', 'pymc', 'exoplanet_core', 'exoplanet'):\n"
+            "    try: importlib.import_module(m)\n"
+            "    except Exception as e: miss.append(m)\n"
+            "print(','.join(miss))") % ref_dir
+    try:
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+        missing = [m for m in out.stdout.strip().split(",") if m]
+    except Exception:
+        missing = ["probe failed"]
+    return {"tier": "R (C restatement of the reference mathematics, oracle/xo_oracle.c -- NOT the reference binary)" if missing
+            else "P (reference PyTensor CPU path)", "not_importable": missing, "baseline_ref_dir_present": os.path.isdir(ref_dir)}
+
+
+WORKLOAD = "configs[1]: eccentric (e=0.5) single-planet Kepler solve + LimbDarkLightCurve, N=1e5 cadences, fp64"
+
+
+def bench_config(chains, gpus):
+    """the `config` object BOTH arms print (identical keys and values for the same --gpus / --chains)"""
+    return {"workload": WORKLOAD, "chains_per_gpu": chains, "chains_total": chains * gpus, "cadences": N_CADENCES,
+            "use_in_transit": True, "parallelism": "chain-sharded, no collective",
+            "l2": "flushed between timed steps (192 MiB memset) on the GPU arm"}
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -139,41 +190,83 @@ def cpu_port_setup(t, p, truth):
 
 
 def arm_reference(args):
-    """The reference's own CPU implementation of the path is exoplanet-core (not in this
-    image) -> the CPU restatement (oracle port) on all host cores."""
+    """The reference's own CPU implementation of the path is exoplanet-core (not in this image) -> the
+    CPU restatement (oracle port) on all host cores.  One step = `inner` passes over the same 128-chain batch the
+    GPU arm evaluates per step (inner is calibrated in the warm-up so that a step lasts >= ~0.1 s: 20 steps are
+    >= 2 s of timed work); every pass derives the element blocks + contact points in C and evaluates logp + the full
+    gradient, OpenMP over chains (dynamic schedule), threads pinned (OMP_PROC_BIND=close, OMP_PLACES=cores, set in
+    main() before libgomp loads).  value = evaluations / MEDIAN step time; mean and best are reported beside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    t, p, truth = build_problem(CHAINS_PER_GPU)
+    tier = probe_reference_tier()
+    nc = args.chains
+    t, p, truth = build_problem(nc)
     O, y, dtk, wk = cpu_port_setup(t, p, truth)
     threads = O.max_threads()
     O.set_threads(threads)
     ivar = np.full(t.size, 1.0 / SIGMA ** 2)
-    nc = min(CHAINS_PER_GPU, max(threads, 1) * 2)  # bounded sample: 2 chains per thread per step
-    el = O.elements_from_params(p["period"][:nc], p["t0"][:nc], p["ecc"][:nc], p["omega"][:nc], p["b"][:nc], p["ror"][:nc])
-    cl = O.get_cl(p["u1"][:nc], p["u2"][:nc])
+    cl = O.get_cl(p["u1"], p["u2"])
+
+    def one_pass(sel=slice(None), use_in_transit=True):
+        # prologue (contact points, elements) + logp + grad, as one reference evaluation would
+        e2 = O.elements_from_params_c(p["period"][sel], p["t0"][sel], p["ecc"][sel], p["omega"][sel], p["b"][sel], p["ror"][sel],
+                                      m_planet=p["m_planet"][sel], use_in_transit=use_in_transit)
+        return O.transit_logp_grad(t, y, ivar, e2, cl[sel], p["mean"][sel], dtk, wk)
+
+    one_pass()
+    c0 = time.perf_counter()
+    one_pass()
+    dt1 = time.perf_counter() - c0
+    inner = max(1, int(np.ceil(0.1 / max(dt1, 1e-6))))
 
     def step():
-        # prologue (contact points, elements) + logp + grad, as one reference evaluation would
-        e2 = O.elements_from_params(p["period"][:nc], p["t0"][:nc], p["ecc"][:nc], p["omega"][:nc], p["b"][:nc], p["ror"][:nc])
-        return O.transit_logp_grad(t, y, ivar, e2, cl, p["mean"][:nc], dtk, wk)
+        for _ in range(inner):
+            one_pass()
 
     for _ in range(args.warmup):
         step()
-    t0 = time.perf_counter()
+    per = []
     for _ in range(args.steps):
+        s0 = time.perf_counter()
         step()
-    dt = time.perf_counter() - t0
-    val = nc * args.steps / dt
+        per.append(time.perf_counter() - s0)
+    per = np.array(per)
+    med, best, mean = float(np.median(per)), float(per.min()), float(per.mean())
+    val = nc * inner / med
+    # BASELINE.md section 4 legs: one thread; and use_in_transit=False (every cadence solved) on all threads
+    O.set_threads(1)
+    k1 = min(nc, 8)
+    one_pass(slice(0, k1))
+    b1 = []
+    for _ in range(3):
+        s0 = time.perf_counter()
+        one_pass(slice(0, k1))
+        b1.append(time.perf_counter() - s0)
+    O.set_threads(threads)
+    ka = min(nc, max(threads, 1))
+    ba = []
+    for _ in range(2):
+        s0 = time.perf_counter()
+        one_pass(slice(0, ka), use_in_transit=False)
+        ba.append(time.perf_counter() - s0)
     line = {
         "impl": "reference", "metric": "model+grad evals/sec, N=1e5-cadence e=0.5 transit", "value": val, "unit": "evals/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * med,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: eccentric (e=0.5) single-planet Kepler solve + LimbDarkLightCurve, N=1e5 cadences, fp64",
-                   "chains_per_step": nc, "cadences": N_CADENCES, "use_in_transit": True},
+        "config": bench_config(nc, args.gpus),
         "cpu_baseline": {"value": val, "unit": "evals/s", "cores": threads, "kind": "port",
-                         "sample": "%d chains x N=1e5 per step (OpenMP over chains), %d steps" % (nc, args.steps)},
+                         "sample": "%d passes over %d chains x N=1e5 per step (OpenMP over chains, pinned), %d steps, %.2f s timed; "
+                                   "value from the median step" % (inner, nc, args.steps, float(per.sum())),
+                         "value_mean": nc * inner / mean, "value_best": nc * inner / best,
+                         "step_time_spread": float((per.max() - per.min()) / med),
+                         "one_thread": {"value": k1 / min(b1), "unit": "evals/s", "sample": "%d chains, best of 3" % k1},
+                         "use_in_transit_false": {"value": ka / min(ba), "unit": "evals/s", "cores": threads,
+                                                  "sample": "%d chains, every cadence solved, best of 2" % ka},
+                         "omp": {k: os.environ.get(k) for k in ("OMP_PROC_BIND", "OMP_PLACES", "OMP_NUM_THREADS")},
+                         "host_cpus": os.cpu_count()},
         "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "reference_tier": tier,
         "note": "CPU restatement of the reference mathematics (oracle/xo_oracle.c); exoplanet-core/PyTensor are not installable here",
     }
     print(json.dumps(line))
@@ -366,7 +459,7 @@ def arm_ours(args):
     lib = _lib.require_cuda()
 
     C_loc = args.chains
-    t_np, p, truth = build_problem(C_loc, seed_offset=rank)
+    t_np, p, truth = build_problem(C_loc, seed_offset=0 if args.same_seed else rank)
 
     def d(x):
         return torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float64, device=dev)
@@ -417,19 +510,41 @@ def arm_ours(args):
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
+    # measured fp64 ceiling of THIS box (register-resident DFMA loop on every SM, CUDA events on the launch stream)
+    dfma = C.c_double(0.0)
+    dfma_ms = C.c_double(0.0)
+    rc = lib.xo_diag_dfma_peak(5, C.byref(dfma), C.byref(dfma_ms), C.c_void_p(stream.cuda_stream))
+    if rc != 0:
+        raise RuntimeError(lib.xo_strerror(rc).decode())
+    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     wall0 = time.perf_counter()
+    launches0 = lib.xo_diag_launch_count()
     for a, b in ev:
         flush.zero_()  # L2 flush between timed iterations (outside the events)
         a.record()
         step_device()
         b.record()
     barrier()
+    gpu_launches = lib.xo_diag_launch_count() - launches0  # counted by the library at every launch site
     wall = time.perf_counter() - wall0
     ms_dev = sum(a.elapsed_time(b) for a, b in ev)
+    # the same step with the Gaussian terms of EVERY cadence summed in the sweep (what the CPU arm does): no data moments
+    saved_mom, mom_ptr = mom_ptr, None
+    for _ in range(3):
+        step_device()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in ev2:
+        flush.zero_()
+        a.record()
+        step_device()
+        b.record()
+    barrier()
+    ms_full = sum(a.elapsed_time(b) for a, b in ev2)
+    mom_ptr = saved_mom
     # ---- e2e: PINNED host buffers through the C ABI; everything (t, y, ivar, params) goes
     # host->device and (logp, grads) device->host inside the timed region, every step -----------
     def pinned(a):
@@ -560,10 +675,10 @@ def arm_ours(args):
     if rank == 0 and world == 1 and not args.no_extra:
         other = extra_configs(lib, dev, args)
 
-    tm = torch.tensor([ms_dev, e2e_s * 1e3, res_s * 1e3], dtype=torch.float64, device=dev)
+    tm = torch.tensor([ms_dev, e2e_s * 1e3, res_s * 1e3, ms_full], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms_dev, e2e_ms, res_ms = tm[0].item(), tm[1].item(), tm[2].item()
+    ms_dev, e2e_ms, res_ms, ms_full = tm[0].item(), tm[1].item(), tm[2].item(), tm[3].item()
     total_evals = C_loc * world * args.steps
     value = total_evals / (ms_dev * 1e-3)
     e2e = total_evals / (e2e_ms * 1e-3)
@@ -587,12 +702,13 @@ def arm_ours(args):
             if prev_affinity:
                 os.sched_setaffinity(0, prev_affinity)
 
-        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "40", "--warmup", "2"],
-                             capture_output=True, text=True, timeout=600, preexec_fn=all_cores)
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(args.steps), "--warmup",
+                              str(args.warmup), "--chains", str(C_loc)], capture_output=True, text=True, timeout=900, preexec_fn=all_cores)
         try:
             ref = json.loads(out.stdout.strip().splitlines()[-1])
             cpu = ref["cpu_baseline"]
             cpu["parity_logp_rel_err"] = rel
+            cpu["reference_tier"] = ref.get("reference_tier")
         except Exception:
             cpu = {"value": None, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: " + out.stderr[-200:]}
 
@@ -601,39 +717,58 @@ def arm_ours(args):
         dist.destroy_process_group()
     if rank != 0:
         return
+    prof = _first_profile("r02_transit.txt", "r01_transit.txt")
+    fp64_inst = _ncu_metric(prof, "smsp__inst_executed_pipe_fp64.sum")  # warp-level fp64-pipe instructions per launch
+    fp64_pct = _ncu_metric(prof, "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active")
+    step_s = ms_dev / args.steps * 1e-3
+    peak_tf = 2.0 * dfma.value / 1e12
+    if fp64_inst is not None and C_loc == CHAINS_PER_GPU:
+        ach_tf = 2.0 * 32.0 * fp64_inst / step_s / 1e12
+        how = ("fp64-pipe warp instructions per launch (ncu smsp__inst_executed_pipe_fp64.sum, profiles/%s; the workload is deterministic) "
+               "x 32 lanes x 2 flop / the live CUDA-event duration of the step" % prof)
+    else:
+        ach_tf, how = None, "no fp64 instruction count committed for this chain count"
     line = {
         "metric": "model+grad evals/sec, N=1e5-cadence e=0.5 transit", "value": value, "unit": "evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: eccentric (e=0.5) single-planet Kepler solve + LimbDarkLightCurve, N=1e5 cadences, fp64",
-                   "chains_per_gpu": C_loc, "chains_total": C_loc * world, "cadences": N_CADENCES, "use_in_transit": True,
-                   "out_of_transit_sums": "full sweep over y, ivar" if args.full_sweep else "data moments (t-only sweep)",
-                   "parallelism": "chain-sharded, no collective",
-                   "host_affinity": ("process bound to the %d CPUs of the GPU's NUMA node" % len(bound_cpus)) if bound_cpus else "unbound",
-                   "l2": "flushed between timed steps (192 MiB memset)",
-                   "step": "params -> elements+contact points -> fused logp+grad -> reverse prologue, 3 kernel launches (XO_MODEL_LAUNCHES=1|2 fuse them; slower), params resident in HBM"},
+        "config": bench_config(C_loc, world),
+        "run": {"out_of_transit_sums": "full sweep over y, ivar" if args.full_sweep else "data moments (t-only sweep)",
+                "host_affinity": ("process bound to the %d CPUs of the GPU's NUMA node" % len(bound_cpus)) if bound_cpus else "unbound",
+                "step": "params -> elements+contact points -> fused logp+grad -> reverse prologue, 3 kernel launches chained by programmatic "
+                        "dependent launch (XO_MODEL_LAUNCHES=1|2 fuse them; slower), params resident in HBM",
+                "seeds": "rank r draws its chains with seed SEED + 17 r (heterogeneous ranks); --same-seed gives every rank rank 0's chains"
+                         if not args.same_seed else "every rank evaluates rank 0's chains (identical per-rank work)"},
+        "value_full_sweep": {"value": total_evals / (ms_full * 1e-3), "unit": "evals/s", "ms_per_step": ms_full / args.steps,
+                             "note": "same step with moments = NULL: y and ivar of every cadence are read and summed in the sweep, as the CPU arm does"},
         "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "xo_transit_model_logp_grad_host: t,y,ivar,params from pinned host memory every call; logp+grads back to host"},
         "e2e_resident_data": {"value": total_evals / (res_ms * 1e-3), "unit": "evals/s",
                               "h2d_bytes_per_step": sum(h[k].numel() * 8 for k in ("par", "star", "mean", "dtk", "wk")), "d2h_bytes_per_step": d2h,
                               "api": "xo_transit_model_logp_grad_resident: light curve uploaded once (xo_transit_data_create); params in, logp+grads out per call"},
-        "gpu_launches": int(os.environ.get("XO_MODEL_LAUNCHES", "3")) * args.steps,
-        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "traffic": _ncu_traffic("r01_transit.txt", "transit"), "traffic_unit": "bytes of DRAM per launch (ncu, profiles/r01_transit.txt)",
-                     "algorithmic_bytes_per_launch": ALG_BYTES_PER_CHAIN_CADENCE * C_loc * N_CADENCES,
-                     "kernel": "transit_logp_grad_kernel", "peak_source": peak_src,
+        "gpu_launches": int(gpu_launches),
+        "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": (ach_tf / peak_tf) if ach_tf else None,
+                     "traffic": _ncu_traffic(prof, "transit"), "traffic_unit": "bytes of DRAM per launch (ncu, profiles/%s)" % prof,
+                     "kernel": "transit_logp_grad_kernel",
+                     "peak_source": "measured in this run: xo_diag_dfma_peak (register-resident DFMA loop, %d CTAs x 256 threads, 8 chains per thread, "
+                                    "best of 5, %.3f ms) = %.3e DFMA/s" % (4 * torch.cuda.get_device_properties(dev).multi_processor_count, dfma_ms.value, dfma.value),
+                     "achieved_how": how, "ncu_pipe_fp64_pct_in_capture": fp64_pct,
                      "duration_ms": ms_dev / args.steps,
                      "duration_note": "CUDA events around the whole 3-kernel step (prologue + this kernel + epilogue, chained by programmatic "
                                       "dependent launch, so the kernel cannot be bracketed alone without breaking the overlap): a lower bound on "
-                                      "the kernel's own rate; ncu times it at 69 us of the step (profiles/r01_launches.txt)",
-                     "note": "nominal 24 B per (chain,cadence); the chains share t,y,sigma through L2 (DRAM traffic = `traffic`), the kernel is latency/fp64-bound, not HBM-bound (DESIGN.md section 5)"},
+                                      "the kernel's own rate",
+                     "note": "the kernel is fp64-pipe / dependent-issue bound, not HBM bound: an N=1e5 light curve is L2-resident and shared by every "
+                             "chain (BASELINE.md section 5), so the nominal-bytes figure is kept separately in roofline_hbm_nominal"},
+        "roofline_hbm_nominal": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                 "algorithmic_bytes_per_launch": ALG_BYTES_PER_CHAIN_CADENCE * C_loc * N_CADENCES, "peak_source": peak_src,
+                                 "note": "nominal 24 B per (chain,cadence) / step duration; real DRAM traffic is `roofline.traffic`"},
         "clocks": clocks, "wall_s": wall,
     }
     if kep is not None:
         line["kepler"] = kep
         k = kep["e~U(0,0.95)"]
         line["kepler_roofline"] = {"bound": "hbm", "achieved": k["gb_per_s"], "peak": peak, "unit": "GB/s", "frac": k["gb_per_s"] / peak,
-                                   "traffic": _ncu_traffic("r01_kepler.txt", "kepler"), "algorithmic_bytes_per_launch": k["n"] * KEPLER_BYTES_PER_ELEMENT,
+                                   "traffic": _ncu_traffic(_first_profile("r02_kepler.txt", "r01_kepler.txt"), "kepler"), "algorithmic_bytes_per_launch": k["n"] * KEPLER_BYTES_PER_ELEMENT,
                                    "kernel": "kepler_fwd_kernel", "bytes_per_element": KEPLER_BYTES_PER_ELEMENT}
     if cpu is not None:
         line["cpu_baseline"] = cpu
@@ -652,10 +787,16 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-kepler", action="store_true", help="skip the Kepler micro-benchmark")
     ap.add_argument("--no-extra", action="store_true", help="skip the brief configs[2] / configs[3] measurements")
+    ap.add_argument("--same-seed", action="store_true", help="multi-GPU: every rank evaluates the same chains (identical per-rank work)")
     ap.add_argument("--full-sweep", action="store_true",
                     help="sum the Gaussian terms of every cadence in the sweep instead of using the data moments")
     args = ap.parse_args()
     if args.impl == "reference":
+        # pin the OpenMP team before libgomp is loaded (the oracle is dlopen'ed later): unpinned threads were the
+        # main source of the 2x run-to-run spread of this arm in round 1
+        os.environ.setdefault("OMP_PROC_BIND", "close")
+        os.environ.setdefault("OMP_PLACES", "cores")
+        os.environ.setdefault("OMP_WAIT_POLICY", "active")
         arm_reference(args)
     else:
         arm_ours(args)

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libxo_b200.so")
 BUILD = os.path.join(HERE, "_build")
-SOURCES = ["xo_ops.cu", "xo_transit.cu", "xo_model.cu", "xo_celerite.cu", "xo_host.cu"]
+SOURCES = ["xo_ops.cu", "xo_transit.cu", "xo_model.cu", "xo_celerite.cu", "xo_host.cu", "xo_diag.cu"]
 HEADERS = ["xo_math.cuh", "xo_common.cuh", "xo_contact.cuh", "xo_transit.cuh", "xo_prologue.cuh", os.path.join("..", "..", "include", "xo_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -59,7 +59,7 @@ def build(force=False, verbose=False):
             list(ex.map(run, jobs))
     if jobs or force or _stale(OUT, objs):
         cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++",
-                                                      "-cudart", "shared"]
+                                                      "-cudart", "shared", "-ldl"]
         run(cmd)
     return OUT
 

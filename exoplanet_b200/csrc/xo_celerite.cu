@@ -998,10 +998,10 @@ int xo_celerite_sho_loglike(const double *t, const double *y, const double *diag
   double *ll = reinterpret_cast<double *>(ws + L.off_ll);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(L.nctas, (unsigned)B);
-  gp_aggregate_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, pref, tot);
-  gp_cta_scan_kernel<<<(unsigned)B, kThreadsGp, 0, st>>>(tot, L.nctas, S0, w0, Q, eps, state);
-  gp_loglike_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, pref, state, ll, nullptr, nullptr);
-  gp_fold_kernel<<<(unsigned)((B + 3) / 4), 128, 0, st>>>(ll, L.nctas, N, B, loglike);
+  xo::launch(gp_aggregate_kernel, grid, kThreadsGp, 0, st, t, y, diag, N, S0, w0, Q, eps, L.T, pref, tot);
+  xo::launch(gp_cta_scan_kernel, (unsigned)B, kThreadsGp, 0, st, tot, L.nctas, S0, w0, Q, eps, state);
+  xo::launch(gp_loglike_kernel, grid, kThreadsGp, 0, st, t, y, diag, N, S0, w0, Q, eps, L.T, pref, state, ll, nullptr, nullptr);
+  xo::launch(gp_fold_kernel, (unsigned)((B + 3) / 4), 128, 0, st, ll, L.nctas, N, B, loglike);
   return xo::launch_status();
 }
 
@@ -1026,16 +1026,16 @@ int xo_celerite_sho_solve(const double *t, const double *y, const double *diag, 
   auto at = [&](size_t off) { return reinterpret_cast<double *>(ws + off); };
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(L.nctas, (unsigned)B);
-  gp_aggregate_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, at(L.off_pref), at(L.off_tot));
-  gp_cta_scan_kernel<<<(unsigned)B, kThreadsGp, 0, st>>>(at(L.off_tot), L.nctas, S0, w0, Q, eps, at(L.off_state));
-  gp_loglike_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, at(L.off_pref), at(L.off_state),
+  xo::launch(gp_aggregate_kernel, grid, kThreadsGp, 0, st, t, y, diag, N, S0, w0, Q, eps, L.T, at(L.off_pref), at(L.off_tot));
+  xo::launch(gp_cta_scan_kernel, (unsigned)B, kThreadsGp, 0, st, at(L.off_tot), L.nctas, S0, w0, Q, eps, at(L.off_state));
+  xo::launch(gp_loglike_kernel, grid, kThreadsGp, 0, st, t, y, diag, N, S0, w0, Q, eps, L.T, at(L.off_pref), at(L.off_state),
                                                  at(L.off_ll), at(L.off_rec), nullptr);
-  gp_fold_kernel<<<(unsigned)((B + 3) / 4), 128, 0, st>>>(at(L.off_ll), L.nctas, N, B, loglike);
+  xo::launch(gp_fold_kernel, (unsigned)((B + 3) / 4), 128, 0, st, at(L.off_ll), L.nctas, N, B, loglike);
   dim3 gridb(L.nctas_b, (unsigned)B);
-  gp_bwd_aggregate_kernel<<<gridb, kThreadsGp, 0, st>>>(t, N, S0, w0, Q, eps, L.Tb, at(L.off_rec), at(L.off_bpref),
+  xo::launch(gp_bwd_aggregate_kernel, gridb, kThreadsGp, 0, st, t, N, S0, w0, Q, eps, L.Tb, at(L.off_rec), at(L.off_bpref),
                                                        at(L.off_bcta));
-  gp_bwd_cta_scan_kernel<<<(unsigned)B, kThreadsGp, 0, st>>>(at(L.off_bcta), L.nctas_b, at(L.off_bstate));
-  gp_bwd_solve_kernel<<<gridb, kThreadsGp, 0, st>>>(t, N, S0, w0, Q, eps, L.Tb, at(L.off_rec), at(L.off_bpref),
+  xo::launch(gp_bwd_cta_scan_kernel, (unsigned)B, kThreadsGp, 0, st, at(L.off_bcta), L.nctas_b, at(L.off_bstate));
+  xo::launch(gp_bwd_solve_kernel, gridb, kThreadsGp, 0, st, t, N, S0, w0, Q, eps, L.Tb, at(L.off_rec), at(L.off_bpref),
                                                    at(L.off_bstate), alpha);
   return xo::launch_status();
 }
@@ -1061,18 +1061,18 @@ int xo_celerite_sho_grad(const double *t, const double *y, const double *diag, i
   auto at = [&](size_t off) { return reinterpret_cast<double *>(ws + off); };
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(L.nctas, (unsigned)B);
-  gp_aggregate_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, at(L.off_pref), at(L.off_tot));
-  gp_cta_scan_kernel<<<(unsigned)B, kThreadsGp, 0, st>>>(at(L.off_tot), L.nctas, S0, w0, Q, eps, at(L.off_state));
-  gp_loglike_kernel<<<grid, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.T, at(L.off_pref), at(L.off_state),
+  xo::launch(gp_aggregate_kernel, grid, kThreadsGp, 0, st, t, y, diag, N, S0, w0, Q, eps, L.T, at(L.off_pref), at(L.off_tot));
+  xo::launch(gp_cta_scan_kernel, (unsigned)B, kThreadsGp, 0, st, at(L.off_tot), L.nctas, S0, w0, Q, eps, at(L.off_state));
+  xo::launch(gp_loglike_kernel, grid, kThreadsGp, 0, st, t, y, diag, N, S0, w0, Q, eps, L.T, at(L.off_pref), at(L.off_state),
                                                  at(L.off_ll), nullptr, at(L.off_rec5));
-  gp_fold_kernel<<<(unsigned)((B + 3) / 4), 128, 0, st>>>(at(L.off_ll), L.nctas, N, B, loglike);
+  xo::launch(gp_fold_kernel, (unsigned)((B + 3) / 4), 128, 0, st, at(L.off_ll), L.nctas, N, B, loglike);
   dim3 gridb(L.nctas_b, (unsigned)B);
-  gp_grad_aggregate_kernel<<<gridb, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.Tb, at(L.off_rec5), at(L.off_gpref),
+  xo::launch(gp_grad_aggregate_kernel, gridb, kThreadsGp, 0, st, t, y, diag, N, S0, w0, Q, eps, L.Tb, at(L.off_rec5), at(L.off_gpref),
                                                         at(L.off_gcta));
-  gp_grad_cta_scan_kernel<<<(unsigned)B, kThreadsGp, 0, st>>>(at(L.off_gcta), L.nctas_b, at(L.off_gstate));
-  gp_grad_final_kernel<<<gridb, kThreadsGp, 0, st>>>(t, y, diag, N, S0, w0, Q, eps, L.Tb, at(L.off_rec5), at(L.off_gpref),
+  xo::launch(gp_grad_cta_scan_kernel, (unsigned)B, kThreadsGp, 0, st, at(L.off_gcta), L.nctas_b, at(L.off_gstate));
+  xo::launch(gp_grad_final_kernel, gridb, kThreadsGp, 0, st, t, y, diag, N, S0, w0, Q, eps, L.Tb, at(L.off_rec5), at(L.off_gpref),
                                                     at(L.off_gstate), gy, gdiag, at(L.off_gpart));
-  gp_grad_fold_kernel<<<(unsigned)((B + 3) / 4), 128, 0, st>>>(at(L.off_gpart), L.nctas_b, S0, w0, Q, eps, B, ghyper);
+  xo::launch(gp_grad_fold_kernel, (unsigned)((B + 3) / 4), 128, 0, st, at(L.off_gpart), L.nctas_b, S0, w0, Q, eps, B, ghyper);
   return xo::launch_status();
 }
 

@@ -3,6 +3,12 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
+#ifndef XO_NO_NVTX
+#include <nvtx3/nvToolsExt.h>
+#endif
+
 #include "../../include/xo_b200.h"
 
 namespace xo {
@@ -27,6 +33,22 @@ inline int64_t clamp_grid(int64_t work_ctas, int sms, int ctas_per_sm) {
   return work_ctas < 1 ? 1 : work_ctas;
 }
 
+// kernels launched by this library in this process (xo_diag_launch_count; bench.py's `gpu_launches`)
+extern std::atomic<long long> g_launch_count;
+inline void note_launch() { g_launch_count.fetch_add(1, std::memory_order_relaxed); }
+
+// NVTX range around an entry point's launches (tracing); header-only NVTX v3, a no-op
+// unless a profiler is attached.  -DXO_NO_NVTX compiles it out.
+struct NvtxScope {
+#ifndef XO_NO_NVTX
+  explicit NvtxScope(const char *name) { nvtxRangePushA(name); }
+  ~NvtxScope() { nvtxRangePop(); }
+#else
+  explicit NvtxScope(const char *) {}
+#endif
+};
+#define XO_NVTX_SCOPE(name) xo::NvtxScope _xo_nvtx_scope(name)
+
 inline int launch_status() {
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? 0 : -(int)err;
@@ -45,6 +67,15 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #endif
 
+#ifdef __CUDACC__
+// every ordinary launch of the library goes through here (counted)
+template <class... KArgs, class... Args>
+inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  note_launch();
+  kernel<<<grid, block, smem, st>>>(KArgs(args)...);
+}
+#endif
+
 template <class... KArgs, class... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, bool pdl, Args... args) {
   cudaLaunchConfig_t cfg = {};
@@ -57,6 +88,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, c
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
+  note_launch();
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 

@@ -123,7 +123,7 @@ int model_logp_grad_phases(const double *t, const double *y, const double *ivar,
     ma.gstar = gstar;
     ma.gmean = gmean;
     if (launches == 2)
-      model_prologue_kernel<<<(unsigned)((2 * cp + 63) / 64), 64, 0, st>>>(par, star, C, (int)P, texp, use_in_transit, elem, cl);
+      xo::launch(model_prologue_kernel, (unsigned)((2 * cp + 63) / 64), 64, 0, st, par, star, C, (int)P, texp, use_in_transit, elem, cl);
     xo::launch_transit_logp_grad(t, y, ivar, N, elem, cl, mean, C, (int)P, dtk, wk, K, L.sp, moments, partial, st, &ma);
     return xo::launch_status();
   }
@@ -132,7 +132,7 @@ int model_logp_grad_phases(const double *t, const double *y, const double *ivar,
     return !(v && *v == '0');
   }();
   if (phases & 1)
-    model_prologue_kernel<<<(unsigned)((2 * cp + 63) / 64), 64, 0, st>>>(par, star, C, (int)P, texp, use_in_transit, elem, cl);
+    xo::launch(model_prologue_kernel, (unsigned)((2 * cp + 63) / 64), 64, 0, st, par, star, C, (int)P, texp, use_in_transit, elem, cl);
   if (!(phases & 2)) return xo::launch_status();
   static const int lpt = [] {
     const char *v = getenv("XO_MODEL_HEAVY_FIRST");
@@ -183,7 +183,7 @@ int xo_elements_from_params(const double *par, const double *star, int64_t C, in
   if (C == 0 || P == 0) return 0;
   if (!par || !star || !elem || !cl) return XO_EINVAL;
   const int64_t cp = C * P;
-  model_prologue_kernel<<<(unsigned)((2 * cp + 63) / 64), 64, 0, static_cast<cudaStream_t>(stream)>>>(
+  xo::launch(model_prologue_kernel, (unsigned)((2 * cp + 63) / 64), 64, 0, static_cast<cudaStream_t>(stream), 
       par, star, C, (int)P, texp, use_in_transit, elem, cl);
   return xo::launch_status();
 }

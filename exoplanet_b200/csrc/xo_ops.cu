@@ -194,15 +194,15 @@ int xo_kepler_fwd_bcast(const double *M, const double *e, int64_t e_inner, doubl
     int64_t work = (n / 2 + kThreads - 1) / kThreads;
     int grid = (int)xo::clamp_grid(work, sms, mb);
     if (mb == 2)
-      kepler_fwd_kernel<2><<<grid, kThreads, 0, st>>>(M, e, sinf, cosf, n, e_inner);
+      xo::launch(kepler_fwd_kernel<2>, grid, kThreads, 0, st, M, e, sinf, cosf, n, e_inner);
     else if (mb == 3)
-      kepler_fwd_kernel<3><<<grid, kThreads, 0, st>>>(M, e, sinf, cosf, n, e_inner);
+      xo::launch(kepler_fwd_kernel<3>, grid, kThreads, 0, st, M, e, sinf, cosf, n, e_inner);
     else
-      kepler_fwd_kernel<4><<<grid, kThreads, 0, st>>>(M, e, sinf, cosf, n, e_inner);
+      xo::launch(kepler_fwd_kernel<4>, grid, kThreads, 0, st, M, e, sinf, cosf, n, e_inner);
   } else {
     int64_t work = (n + kThreads - 1) / kThreads;
     int grid = (int)xo::clamp_grid(work, sms, 8);
-    kepler_fwd_kernel_scalar<<<grid, kThreads, 0, st>>>(M, e, sinf, cosf, n, e_inner);
+    xo::launch(kepler_fwd_kernel_scalar, grid, kThreads, 0, st, M, e, sinf, cosf, n, e_inner);
   }
   return xo::launch_status();
 }
@@ -221,10 +221,10 @@ int xo_kepler_vjp(const double *sinf, const double *cosf, const double *e, const
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (vec) {
     int grid = (int)xo::clamp_grid((n / 2 + kThreads - 1) / kThreads, xo::sm_count(), 8);
-    kepler_vjp_kernel<true><<<grid, kThreads, 0, st>>>(sinf, cosf, e, bsinf, bcosf, bM, be, n);
+    xo::launch(kepler_vjp_kernel<true>, grid, kThreads, 0, st, sinf, cosf, e, bsinf, bcosf, bM, be, n);
   } else {
     int grid = (int)xo::clamp_grid((n + kThreads - 1) / kThreads, xo::sm_count(), 8);
-    kepler_vjp_kernel<false><<<grid, kThreads, 0, st>>>(sinf, cosf, e, bsinf, bcosf, bM, be, n);
+    xo::launch(kepler_vjp_kernel<false>, grid, kThreads, 0, st, sinf, cosf, e, bsinf, bcosf, bM, be, n);
   }
   return xo::launch_status();
 }
@@ -236,9 +236,9 @@ int xo_qsv_fwd(const double *b, const double *r, double *s, double *dsdb, double
   int grid = (int)xo::clamp_grid((n + kThreads - 1) / kThreads, xo::sm_count(), 4);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dsdb)
-    qsv_fwd_kernel<true><<<grid, kThreads, 0, st>>>(b, r, s, dsdb, dsdr, n);
+    xo::launch(qsv_fwd_kernel<true>, grid, kThreads, 0, st, b, r, s, dsdb, dsdr, n);
   else
-    qsv_fwd_kernel<false><<<grid, kThreads, 0, st>>>(b, r, s, nullptr, nullptr, n);
+    xo::launch(qsv_fwd_kernel<false>, grid, kThreads, 0, st, b, r, s, nullptr, nullptr, n);
   return xo::launch_status();
 }
 
@@ -247,7 +247,7 @@ int xo_qsv_vjp(const double *bs, const double *dsdb, const double *dsdr, double 
   if (n == 0) return 0;
   if (!bs || !dsdb || !dsdr || !bb || !br) return XO_EINVAL;
   int grid = (int)xo::clamp_grid((n + kThreads - 1) / kThreads, xo::sm_count(), 8);
-  qsv_vjp_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(bs, dsdb, dsdr, bb, br, n);
+  xo::launch(qsv_vjp_kernel, grid, kThreads, 0, static_cast<cudaStream_t>(stream), bs, dsdb, dsdr, bb, br, n);
   return xo::launch_status();
 }
 
@@ -259,7 +259,7 @@ int xo_contact_points(const double *a, const double *e, const double *cosw, cons
   if (!a || !e || !cosw || !sinw || !cosi || !sini || !L || !M_left || !M_right || !flag) return XO_EINVAL;
   int threads = 64;
   int grid = (int)((n + threads - 1) / threads);
-  contact_points_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(a, e, cosw, sinw, cosi, sini, L, M_left,
+  xo::launch(contact_points_kernel, grid, threads, 0, static_cast<cudaStream_t>(stream), a, e, cosw, sinw, cosi, sini, L, M_left,
                                                                                 M_right, flag, n);
   return xo::launch_status();
 }

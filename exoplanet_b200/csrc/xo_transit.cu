@@ -766,7 +766,7 @@ void launch_transit_logp_grad(const double *t, const double *y, const double *iv
 }
 
 void launch_chain_order(const double *elem, int64_t C, int P, int *order, cudaStream_t st) {
-  chain_order_kernel<<<(unsigned)((C + 127) / 128), 128, 0, st>>>(elem, C, P, order);
+  xo::launch(chain_order_kernel, (unsigned)((C + 127) / 128), 128, 0, st, elem, C, P, order);
 }
 
 }  // namespace xo
@@ -788,7 +788,7 @@ int xo_transit_lc_fwd(const double *t, int64_t N, const double *elem, const doub
   int gx = (int)(per_chain < want ? per_chain : want);
   if (gx < 1) gx = 1;
   dim3 grid(gx, (unsigned)C);
-  transit_lc_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(t, N, elem, cl, (int)P, dtk, wk, K, lc);
+  xo::launch(transit_lc_fwd_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), t, N, elem, cl, (int)P, dtk, wk, K, lc);
   return xo::launch_status();
 }
 
@@ -806,7 +806,7 @@ int xo_transit_data_moments(const double *t, const double *y, const double *ivar
   if (e != cudaSuccess) return -(int)e;
   const int64_t want = (N + 4 * kMomThreads - 1) / (4 * kMomThreads);
   const int ctas = (int)(want < 1 ? 1 : want > kMomMaxCtas ? kMomMaxCtas : want);
-  transit_moments_kernel<<<ctas, kMomThreads, 0, st>>>(t, y, ivar, N, moments);
+  xo::launch(transit_moments_kernel, ctas, kMomThreads, 0, st, t, y, ivar, N, moments);
   return xo::launch_status();
 }
 
@@ -827,7 +827,7 @@ int xo_transit_logp_grad(const double *t, const double *y, const double *ivar, i
   xo::launch_transit_logp_grad(t, y, ivar, N, elem, cl, mean, C, (int)P, dtk, wk, K, sp, moments, partial, st, nullptr);
   const int nacc = kNBase + (int)P * XO_NGRAD;
   const int64_t tot = C * nacc;
-  fold_partials_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(partial, sp.slots, nacc, C, (int)P, lognorm, logp,
+  xo::launch(fold_partials_kernel, (unsigned)((tot + 127) / 128), 128, 0, st, partial, sp.slots, nacc, C, (int)P, lognorm, logp,
                                                                       gel, gcl, gmean);
   return xo::launch_status();
 }
@@ -848,7 +848,7 @@ int xo_transit_lc_vjp(const double *t, int64_t N, const double *elem, const doub
   xo::launch_transit_logp_grad(t, bar_lc, nullptr, N, elem, cl, nullptr, C, (int)P, dtk, wk, K, sp, nullptr, partial, st, nullptr);
   const int nacc = kNBase + (int)P * XO_NGRAD;
   const int64_t tot = C * nacc;
-  fold_partials_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(partial, sp.slots, nacc, C, (int)P, 0.0, scratch, gel,
+  xo::launch(fold_partials_kernel, (unsigned)((tot + 127) / 128), 128, 0, st, partial, sp.slots, nacc, C, (int)P, 0.0, scratch, gel,
                                                                       gcl, scratch + C);
   return xo::launch_status();
 }
@@ -864,7 +864,7 @@ int xo_orbit_eval(const double *t, int64_t N, const double *elem, int64_t C, int
   int gx = (int)(per_chain < want ? per_chain : want);
   if (gx < 1) gx = 1;
   dim3 grid(gx, (unsigned)C);
-  orbit_eval_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(t, N, elem, (int)P, X, Y, Z, rv);
+  xo::launch(orbit_eval_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), t, N, elem, (int)P, X, Y, Z, rv);
   return xo::launch_status();
 }
 
@@ -891,12 +891,12 @@ int xo_rv_logp_grad(const double *t, const double *y, const double *ivar, int64_
     return !(v && *v == '0');
   }();
   if (cap)
-    rv_logp_grad_kernel<true><<<grid, block, 0, st>>>(t, y, ivar, N, elem, gamma, (int)P, sp.L, sp.slots, partial);
+    xo::launch(rv_logp_grad_kernel<true>, grid, block, 0, st, t, y, ivar, N, elem, gamma, (int)P, sp.L, sp.slots, partial);
   else
-    rv_logp_grad_kernel<false><<<grid, block, 0, st>>>(t, y, ivar, N, elem, gamma, (int)P, sp.L, sp.slots, partial);
+    xo::launch(rv_logp_grad_kernel<false>, grid, block, 0, st, t, y, ivar, N, elem, gamma, (int)P, sp.L, sp.slots, partial);
   const int nacc = 2 + (int)P * XO_NGRAD_RV;
   const int64_t tot = C * nacc;
-  fold_rv_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(partial, sp.slots, nacc, C, (int)P, lognorm, logp, grv,
+  xo::launch(fold_rv_kernel, (unsigned)((tot + 127) / 128), 128, 0, st, partial, sp.slots, nacc, C, (int)P, lognorm, logp, grv,
                                                                 ggamma);
   return xo::launch_status();
 }

@@ -208,6 +208,14 @@ int xo_transit_model_logp_grad_resident(xo_transit_data *data, const double *par
                                         int use_in_transit, double lognorm, int use_moments, double *logp, double *gpar,
                                         double *gstar, double *gmean);
 
+/* ---- measurement helpers (no reference counterpart) ----
+ * xo_diag_dfma_peak: register-resident DFMA loop on every SM of the current device, best of `reps` launches timed
+ *   with CUDA events on `stream` -> thread-level DFMA per second (x2 = flop/s): the measured fp64 ceiling the
+ *   fused kernels are quoted against (SURVEY.md 8d ceiling (B)).
+ * xo_diag_launch_count: number of kernels this library has launched in this process so far. */
+int xo_diag_dfma_peak(int reps, double *dfma_per_s, double *best_ms, void *stream);
+long long xo_diag_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

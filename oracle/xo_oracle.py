@@ -295,6 +295,23 @@ def elements_from_params(period, t0, ecc, omega, b, ror, r_star=1.0, m_star=1.0,
     return el
 
 
+def elements_from_params_c(period, t0, ecc, omega, b, ror, r_star=1.0, m_star=1.0, m_planet=0.0, texp=None, K=0.0,
+                           use_in_transit=True):
+    """the same element blocks from the C restatement (xo_oracle_elements_from_params): [C, P] inputs, r_star /
+    m_star scalars or [C]; used by the CPU-baseline legs so that their per-evaluation prologue is not Python"""
+    arrs = np.broadcast_arrays(*[np.asarray(x, dtype=np.float64) for x in (period, t0, ecc, omega, b, ror, m_planet, K)])
+    shape = arrs[0].shape
+    planets = shape[-1] if len(shape) > 1 else 1
+    par = _f64(np.stack(arrs, axis=-1).reshape(-1, 8))
+    n = par.shape[0]
+    star = _f64(np.stack(np.broadcast_arrays(np.asarray(r_star, dtype=np.float64), np.asarray(m_star, dtype=np.float64),
+                                             np.zeros(max(n // planets, 1))), axis=-1)[:, :2])
+    el = np.empty((n, NEL))
+    lib().xo_oracle_elements_from_params(_p(par), _p(star), C.c_int64(n), C.c_int64(planets), C.c_double(0.0 if texp is None else texp),
+                                         C.c_int(int(use_in_transit)), _p(el))
+    return el.reshape(shape + (NEL,))
+
+
 def stencil(texp, oversample=7, order=0):
     """limb_dark.py:173-198 -> (dt_k * texp, w_k)."""
     if texp is None:

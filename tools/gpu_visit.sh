@@ -1,0 +1,70 @@
+#!/bin/bash
+# One GPU-box visit (round 2).  usage (under gpurun): bash tools/gpu_visit.sh TAG MODE
+#   MODE = check   : full -m gpu test suite, smoke, bench (ours + reference arm twice), launch list, transit ncu capture
+#   MODE = gp      : celerite tests + bench extra configs + ncu capture of the celerite kernels
+#   MODE = transit : fused tests + bench (no extras) + ncu capture of the logp kernel
+#   MODE = final   : everything, captures of every kernel, sanitizers
+TAG=${1:-r02}
+MODE=${2:-check}
+OUT=gpurun_out
+mkdir -p $OUT
+NCU_FULL="ncu --set full --metrics smsp__inst_executed_pipe_fp64.sum --clock-control none --import-source on"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_gpu.txt 2>&1
+lscpu | grep -E "Model name|^CPU\(s\)|Thread|Core|Socket" >> $OUT/${TAG}_gpu.txt; nproc >> $OUT/${TAG}_gpu.txt
+
+run_pytest() { # name, args...
+  local name=$1; shift
+  timeout 2400 python -m pytest "$@" -m gpu -q -x > $OUT/${TAG}_pytest_$name.log 2>&1; echo "pytest($name) exit $?" | tee -a $OUT/${TAG}_pytest_$name.log
+}
+bench_line() { # name, args...
+  local name=$1; shift
+  timeout 1200 python bench.py "$@" > $OUT/${TAG}_bench_$name.json 2> $OUT/${TAG}_bench_$name.err; echo "bench($name) exit $?" >> $OUT/${TAG}_bench_$name.err
+}
+capture() { # name, kernel regex, skip, bench args...
+  local name=$1 rx=$2 skip=$3; shift 3
+  timeout 900 $NCU_FULL -k regex:"$rx" -s $skip -c 1 -f -o $OUT/${TAG}_prof_$name python bench.py "$@" > $OUT/${TAG}_ncu_$name.log 2>&1
+}
+
+case $MODE in
+check)
+  run_pytest all tests
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke exit $?" >> $OUT/${TAG}_smoke.log
+  bench_line ours --steps 20 --warmup 5
+  bench_line ref1 --impl reference --steps 20 --warmup 5
+  bench_line ref2 --impl reference --steps 20 --warmup 5
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"transit_|model_|kepler_fwd|fold_|gp_" -c 120 --csv --log-file $OUT/${TAG}_launches.csv \
+      python bench.py --steps 5 --warmup 3 --no-cpu > $OUT/${TAG}_ncu_bench.log 2>&1
+  capture transit transit_logp_grad_kernel 3 --steps 2 --warmup 3 --no-cpu --no-kepler --no-extra
+  ;;
+gp)
+  run_pytest gp tests/test_gpu_gp.py tests/test_gpu_configs.py
+  bench_line ours --steps 20 --warmup 5 --no-cpu --no-kepler
+  capture gp "gp_" 0 --steps 1 --warmup 3 --no-cpu --no-kepler
+  ;;
+transit)
+  run_pytest fused tests/test_gpu_fused.py tests/test_reference_glue.py tests/test_gpu_configs.py
+  bench_line ours --steps 20 --warmup 5 --no-cpu --no-kepler --no-extra
+  capture transit transit_logp_grad_kernel 3 --steps 2 --warmup 3 --no-cpu --no-kepler --no-extra
+  ;;
+final)
+  run_pytest all tests
+  for ML in 1 2; do XO_MODEL_LAUNCHES=$ML run_pytest launches$ML tests/test_gpu_fused.py; done
+  XO_MODEL_PDL=0 run_pytest nopdl tests/test_gpu_fused.py
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke exit $?" >> $OUT/${TAG}_smoke.log
+  bench_line ours --steps 20 --warmup 5
+  bench_line ref1 --impl reference --steps 20 --warmup 5
+  bench_line ref2 --impl reference --steps 20 --warmup 5
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"transit_|model_|kepler_fwd|fold_|gp_|rv_" -c 200 --csv --log-file $OUT/${TAG}_launches.csv \
+      python bench.py --steps 5 --warmup 3 --no-cpu > $OUT/${TAG}_ncu_bench.log 2>&1
+  capture transit transit_logp_grad_kernel 3 --steps 2 --warmup 3 --no-cpu --no-kepler --no-extra
+  capture kepler kepler_fwd_kernel 4 --steps 1 --warmup 3 --no-cpu --no-extra
+  capture rv rv_logp_grad_kernel 4 --steps 1 --warmup 3 --no-cpu --no-kepler
+  capture gp "gp_" 0 --steps 1 --warmup 3 --no-cpu --no-kepler
+  timeout 600 compute-sanitizer --tool memcheck --report-api-errors no --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_memcheck.log 2>&1; echo "memcheck exit $?" >> $OUT/${TAG}_memcheck.log
+  timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_racecheck.log 2>&1; echo "racecheck exit $?" >> $OUT/${TAG}_racecheck.log
+  ;;
+esac
+tail -4 $OUT/${TAG}_pytest_*.log 2>/dev/null; tail -2 $OUT/${TAG}_smoke.log 2>/dev/null
+for f in $OUT/${TAG}_bench_*.json; do echo "== $f"; head -c 3000 $f; echo; done
+tail -3 $OUT/${TAG}_bench_*.err 2>/dev/null
+exit 0
