@@ -305,11 +305,30 @@ def extra_configs(lib, dev, args):
 
     flush = torch.empty(192 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
     out = {}
+    only = set(args.extra.split(",")) if args.extra else None
+    want = lambda name: only is None or name in only  # noqa: E731
+    N = N_CADENCES
+    t = synthetic.cadence_times(N)
+    y = synthetic.noise(N, SIGMA)
+    if want("c2"):
+        _extra_config2(lib, dev, d, flush, out, O, t, y)
+    if want("gp"):
+        _extra_gp(lib, dev, d, flush, out, O)
+    if want("c4"):
+        _extra_1024(lib, dev, d, flush, out, O, t, y)
+    if want("hmc"):
+        _extra_hmc(lib, dev, d, flush, out, O, t, y)
+    return out
+
+
+def _extra_config2(lib, dev, d, flush, out, O, t, y):
+    import torch
+
+    from exoplanet_b200 import fused, synthetic
+
     # ---- configs[2] -----------------------------------------------------------------------------
     Cn, P, N = 128, 5, N_CADENCES
     p = synthetic.transit_params(Cn, P, seed=synthetic.SEED + 5)
-    t = synthetic.cadence_times(N)
-    y = synthetic.noise(N, SIGMA)
     data = fused.TransitData(t, y, np.full(N, SIGMA), device=dev)
     rv_obs = 3.0 * np.random.default_rng(7).normal(size=N)
     rvdata = fused.TransitData(t, rv_obs, np.full(N, 3.0), device=dev)
@@ -330,11 +349,20 @@ def extra_configs(lib, dev, args):
     sel = [0, Cn - 1]
     lo = O.transit_logp_grad(t, y, np.full(N, 1 / SIGMA ** 2), el_o[sel], O.get_cl(p["u1"][sel], p["u2"][sel]), p["mean"][sel], np.zeros(1),
                              np.ones(1), lognorm=data.lognorm)[0]
-    lr = O.rv_logp_grad(t, rv_obs, np.full(N, 1 / 9.0), el_o[sel], p["gamma"][sel], lognorm=rvdata.lognorm)[0]
+    lr, grvo, _ = O.rv_logp_grad(t, rv_obs, np.full(N, 1 / 9.0), el_o[sel], p["gamma"][sel], lognorm=rvdata.lognorm)
     err = max(float(np.max(np.abs(res["lc"][0].cpu().numpy()[sel] - lo) / np.abs(lo))),
               float(np.max(np.abs(res["rv"][0].cpu().numpy()[sel] - lr) / np.abs(lr))))
+    gerr = float(np.max(np.abs(res["rv"][1].cpu().numpy()[sel] - grvo) / (np.abs(grvo).max(axis=(0, 1), keepdims=True) + 1e-300)))
     out["configs[2] 5-planet transit+RV, N=1e5"] = {"value": Cn / (ms * 1e-3), "unit": "model+grad evals/s", "ms_per_step": ms, "chains": Cn,
-                                                    "parity_logp_rel_err": err}
+                                                    "parity_logp_rel_err": err, "parity_rv_grad_rel_err": gerr,
+                                                    "parity_note": "2 sampled chains here; all gradients of 8 chains in tests/test_gpu_configs.py"}
+
+
+def _extra_gp(lib, dev, d, flush, out, O):
+    import torch
+
+    from exoplanet_b200 import gp, synthetic
+
     # ---- configs[3] -----------------------------------------------------------------------------
     Ng = 1000000
     pr = synthetic.gp_problem(Ng)
@@ -363,6 +391,12 @@ def extra_configs(lib, dev, args):
             "value": B * Ng / (ms * 1e-3), "unit": "cadences/s", "ms_per_step": ms,
             "loglike_rel_err": float(abs(r["g"][0][0].item() - lo) / abs(lo))}
         del wg
+    # gradient parity of the 16-chain result (every chain sees the same data) against the O(N) C adjoint
+    _, gho, gyo, gdo = O.celerite_sho_grad_c(pr["t"], pr["y"], pr["diag"], pr["S0"], pr["w0"], pr["Q"])
+    gh, gy_, gd_ = r["g"][1][-1].cpu().numpy(), r["g"][2][-1].cpu().numpy(), r["g"][3][-1].cpu().numpy()
+    out["configs[3] celerite SHO loglike + exact gradient (S0, w0, Q, y, diag), N=1e6, 16 chain(s)"].update(
+        parity_hyper_rel_err=float(np.max(np.abs(gh - gho) / np.abs(gho))), parity_gy_rel_err=float(np.max(np.abs(gy_ - gyo)) / np.abs(gyo).max()),
+        parity_gdiag_rel_err=float(np.max(np.abs(gd_ - gdo)) / np.abs(gdo).max()))
     # joint model of configs[3]: transit mean + SHO GP noise at N=1e6, logL and its gradient w.r.t. the
     # orbital parameters (light curve -> residual -> GP solve (logL, alpha) -> light-curve VJP with alpha)
     from exoplanet_b200.light_curves import LimbDarkLightCurve
@@ -380,6 +414,16 @@ def extra_configs(lib, dev, args):
         res["g"] = torch.autograd.grad(ll, pj + hj)
 
     ms = _time_steps(jstep, 5, flush)
+    out["configs[3] transit + SHO GP, N=1e6: logL + d/d(period, b, r, S0, w0, Q) (torch-level composition)"] = {
+        "value": 1.0 / (ms * 1e-3), "unit": "model+grad evals/s", "ms_per_step": ms}
+
+
+def _extra_1024(lib, dev, d, flush, out, O, t, y):
+    import torch
+
+    from exoplanet_b200 import fused, synthetic
+
+    N = N_CADENCES
     # ---- configs[4]'s chain count on ONE GPU: 1024 chains per step (the fixed ~30 us of prologue,
     # epilogue and launches is amortised over 8x the work of the headline step)
     pb = synthetic.transit_params(1024, 1, seed=synthetic.SEED + 11, ecc=0.5)
@@ -388,9 +432,30 @@ def extra_configs(lib, dev, args):
     starb = fused.pack_star(one, one, d(pb["u1"]), d(pb["u2"]))
     meanb = d(pb["mean"])
     big = fused.TransitModel(fused.TransitData(t, y, np.full(N, SIGMA), device=dev))
-    msb = _time_steps(lambda: big.logp_grad(parb, starb, meanb), 10, flush)
-    out["configs[1] with 1024 chains on one GPU (N=1e5, e=0.5)"] = {"value": 1024 / (msb * 1e-3), "unit": "model+grad evals/s", "ms_per_step": msb,
-                                                                  "chains": 1024}
+    res = {}
+
+    def bstep():
+        res["o"] = big.logp_grad(parb, starb, meanb)
+
+    msb = _time_steps(bstep, 10, flush)
+    sel = np.linspace(0, 1023, 8).astype(int)
+    el_o = O.elements_from_params(pb["period"][sel], pb["t0"][sel], pb["ecc"][sel], pb["omega"][sel], pb["b"][sel], pb["ror"][sel],
+                                  m_planet=pb["m_planet"][sel])
+    lo, _, _, gmo = O.transit_logp_grad(t, y, np.full(N, 1 / SIGMA ** 2), el_o, O.get_cl(pb["u1"][sel], pb["u2"][sel]), pb["mean"][sel], np.zeros(1),
+                                        np.ones(1), lognorm=big.data.lognorm)
+    out["configs[1] with 1024 chains on one GPU (N=1e5, e=0.5)"] = {
+        "value": 1024 / (msb * 1e-3), "unit": "model+grad evals/s", "ms_per_step": msb, "chains": 1024,
+        "parity_logp_rel_err": float(np.max(np.abs(res["o"][0].cpu().numpy()[sel] - lo) / np.abs(lo))),
+        "parity_gmean_rel_err": float(np.max(np.abs(res["o"][3].cpu().numpy()[sel] - gmo) / np.abs(gmo).max())),
+        "parity_note": "8 sampled chains against the oracle; every parameter gradient of 16 chains in tests/test_gpu_configs.py"}
+
+
+def _extra_hmc(lib, dev, d, flush, out, O, t, y):
+    import torch
+
+    from exoplanet_b200 import fused, synthetic
+
+    N = N_CADENCES
     # ---- the lock-step HMC driver on configs[1] (128 chains x N=1e5), one CUDA graph per transition
     from exoplanet_b200.sampling import BatchedHMC, TransitPosterior
 
@@ -413,9 +478,6 @@ def extra_configs(lib, dev, args):
         out["HMC driver, configs[1] x 128 chains, 8 leapfrog steps per transition, %s" % ("CUDA graph replay" if use_graph else "eager launches")] = {
             "value": 128 * 8 / (msj * 1e-3), "unit": "leapfrog model+grad evals/s (incl. parameter transforms and their autograd)",
             "ms_per_transition": msj, "chain_transitions_per_s": 128 / (msj * 1e-3)}
-    out["configs[3] transit + SHO GP, N=1e6: logL + d/d(period, b, r, S0, w0, Q) (torch-level composition)"] = {
-        "value": 1.0 / (ms * 1e-3), "unit": "model+grad evals/s", "ms_per_step": ms}
-    return out
 
 
 def arm_ours(args):
@@ -787,6 +849,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-kepler", action="store_true", help="skip the Kepler micro-benchmark")
     ap.add_argument("--no-extra", action="store_true", help="skip the brief configs[2] / configs[3] measurements")
+    ap.add_argument("--extra", default="", help="comma list restricting the other-config measurements: c2,gp,c4,hmc (default: all)")
     ap.add_argument("--same-seed", action="store_true", help="multi-GPU: every rank evaluates the same chains (identical per-rank work)")
     ap.add_argument("--full-sweep", action="store_true",
                     help="sum the Gaussian terms of every cadence in the sweep instead of using the data moments")

@@ -71,6 +71,7 @@ _SIGNATURES = {
     "xo_transit_model_logp_grad_host": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _dbl, _i32, _dbl,
                                                _vp, _vp, _vp, _vp, _i32]),
     "xo_diag_dfma_peak": (_i32, [_i32, C.POINTER(_dbl), C.POINTER(_dbl), _vp]),
+    "xo_read_status": (_i32, [_vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), _vp]),
     "xo_diag_launch_count": (C.c_longlong, []),
     "xo_transit_data_create": (_i32, [_vp, _vp, _vp, _i64, _i32, C.POINTER(_vp)]),
     "xo_transit_data_destroy": (_i32, [_vp]),

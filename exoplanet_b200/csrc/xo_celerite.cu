@@ -5,16 +5,13 @@
 //
 // The celerite recurrence is a Riccati (linear-fractional) recursion, so it is run in
 // its equivalent 2-state Kalman-filter form, which has an associative combine
-// (Sarkka & Garcia-Fernandez 2021).  Three phases, every thread owns a run of kRun
-// consecutive cadences:
-//   1. gp_aggregate: walk the run once from a *known* start (P = 0), tracking the affine
-//      dependence of the filtered mean on the unknown start state and the information
-//      (eta, J) the run's data carry about it -> one scan element per run, no 2x2 inverses;
-//      then an in-CTA inclusive scan of the run elements (shuffle scan + 4 warp totals).
-//   2. gp_cta_scan: one CTA scans the per-CTA totals and applies each exclusive prefix to
-//      the stationary prior -> the state (m, Z = Sigma_inf - P) entering every CTA.
-//   3. gp_loglike: each thread applies its in-CTA prefix to that state and re-walks its run
-//      with plain Kalman steps, accumulating -1/2 (v^2/D + log D); fixed-order reduction.
+// (Sarkka & Garcia-Fernandez 2021).  One kernel, one read of the data (gp_forward_kernel): a CTA stages a
+// tile of (t, diag, y) in shared memory, every thread walks a run of kRun consecutive cadences once from a
+// *known* start (P = 0), tracking the affine dependence of the filtered mean on the unknown start state and the
+// information (eta, J) the run's data carry about it -> one scan element per run, no 2x2 inverses; in-CTA
+// scan; a fixed two-level tree over the tile totals of the chain (flags + bounded waits, tiles handed out by
+// ticket) gives the state entering the tile; every thread then re-walks its run from shared memory with plain
+// Kalman steps, accumulating -1/2 (v^2/D + log D); the last tile of a chain folds the per-tile sums in order.
 // SHO in (a, c, h) form so celerite2's eps-regularised coefficients are matched exactly:
 //   underdamped k(tau) = a e^{-c tau}(cos h tau + (c/h) sin h tau), overdamped with cosh/sinh.
 #include <cuda_runtime.h>
@@ -180,14 +177,6 @@ __device__ __forceinline__ void agg_store(double *p, const Agg &a) {
 #pragma unroll
   for (int k = 0; k < kAggDoubles; ++k) p[k] = src[k];
 }
-__device__ __forceinline__ Agg agg_load(const double *p) {
-  Agg a;
-  double *dst = &a.A00;
-#pragma unroll
-  for (int k = 0; k < kAggDoubles; ++k) dst[k] = p[k];
-  return a;
-}
-
 // inclusive scan of one Agg per thread across the CTA (thread order); returns inclusive value
 __device__ Agg cta_inclusive_scan(Agg v, Agg *warp_tot /* smem [kWarps] */) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -206,29 +195,172 @@ __device__ Agg cta_inclusive_scan(Agg v, Agg *warp_tot /* smem [kWarps] */) {
   return v;
 }
 
-// ---- phase 1 ---------------------------------------------------------------
-__global__ void __launch_bounds__(kThreadsGp) gp_aggregate_kernel(const double *__restrict__ t,
-                                                                  const double *__restrict__ y,
-                                                                  const double *__restrict__ diag, int64_t N,
-                                                                  const double *__restrict__ S0,
-                                                                  const double *__restrict__ w0,
-                                                                  const double *__restrict__ Qf, double eps,
-                                                                  int64_t T, double *__restrict__ pref,
-                                                                  double *__restrict__ cta_tot) {
-  __shared__ Agg warp_tot[kWarpsGp];
-  const int64_t bch = blockIdx.y;
+// ---------------------------------------------------------------------------
+// Inter-CTA plumbing of the one-pass scans: tickets, flags, bounded spin-waits.
+//
+// Tiles are handed out by an atomic ticket (chain-major: ticket = chain * tiles + tile), so a CTA only
+// ever waits on tiles with a LOWER ticket, i.e. on CTAs that are already running: forward progress does
+// not depend on the hardware's CTA scheduling order.  A flag is published with a release store after the
+// payload; readers poll it with acquire loads and read the payload through L2 (ld.cg).  Every wait is
+// bounded (kSpinLimit polls with back-off): on expiry the CTA records a failure in the status word and
+// carries on with an identity element, so the kernel always terminates (include/xo_b200.h: "every
+// iteration is bounded").
+// ---------------------------------------------------------------------------
+constexpr unsigned kSpinLimit = 1u << 22;  // x >= 40 ns back-off: > 0.15 s, far beyond any real wait
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// true when *flag became non-zero within the bound
+__device__ __forceinline__ bool wait_flag(const unsigned *flag) {
+  unsigned ns = 20;
+  for (unsigned it = 0; it < kSpinLimit; ++it) {
+    if (ld_acquire_u32(flag) != 0u) return true;
+    __nanosleep(ns);
+    if (ns < 160) ns += 20;
+  }
+  return false;
+}
+
+// status word at the head of every celerite workspace (see xo_read_status): [0] lanes whose result was
+// not finite, [1] expired waits (a broken scan: the result must be discarded)
+struct GpStatus {
+  unsigned long long bad_lanes, wait_failures;
+};
+
+// fixed-order combine of the elements held by lanes [0, count) of a warp (lane order = time order):
+// every lane returns e_0 o e_1 o ... o e_{count-1}; lanes >= count pass the identity.  The shuffle tree has
+// a fixed shape, so the result is bit-reproducible.
+__device__ __forceinline__ Agg agg_warp_reduce(Agg v, int count) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int d = 1; d < 32; d <<= 1) {
+    Agg o = agg_shfl_up(v, d);
+    if (lane >= d && lane < count) v = agg_combine(o, v);
+  }
+  const int last = count > 0 ? count - 1 : 0;
+  Agg r;
+  const double *src = &v.A00;
+  double *dst = &r.A00;
+#pragma unroll
+  for (int k = 0; k < kAggDoubles; ++k) dst[k] = __shfl_sync(kFullGp, src[k], last);
+  return count > 0 ? r : agg_identity();
+}
+
+__device__ __forceinline__ Agg agg_load_cg(const double *p) {
+  Agg a;
+  double *dst = &a.A00;
+#pragma unroll
+  for (int k = 0; k < kAggDoubles; ++k) dst[k] = __ldcg(p + k);
+  return a;
+}
+
+// ---- one-pass forward scan ---------------------------------------------------
+// One CTA owns a tile of kTile = kThreadsGp * kRun cadences of one chain:
+//   1. the tile of (t, diag, y) is read from HBM ONCE, coalesced, into shared memory (row pitch kRun + 1
+//      doubles: thread r then walks row r conflict-free);
+//   2. every thread walks its run from a known start (P = 0) -> one scan element per run; in-CTA scan;
+//   3. the CTA total is published (A flag); warp 0 builds the exclusive prefix over all earlier tiles of the
+//      chain from a FIXED two-level tree -- totals of whole groups of 32 tiles (published by each group's
+//      last tile, T flag) combined in windows of 32, then the tiles of the own group -- and applies it to the
+//      stationary prior: the state entering the tile;
+//   4. every thread applies its in-CTA exclusive prefix and re-walks its run from shared memory with plain
+//      Kalman steps, accumulating -1/2 (v^2/D + log D);
+//   5. per-CTA sums are folded in tile order by the last CTA of the chain to finish (bit-reproducible).
+constexpr int kTile = kThreadsGp * kRun;
+constexpr int kPitch = kRun + 1;
+constexpr int kGroup = 32;  // tiles per group of the inter-CTA tree
+
+struct GpFwdLayout {  // device scratch of one forward pass (all offsets in bytes from the workspace base)
+  int tiles, groups;
+  size_t off_status, off_flags, off_aggA, off_aggT, off_ll, flag_bytes, bytes;
+};
+
+struct GpFwdSmem {
+  double t[kThreadsGp * kPitch];
+  double d[kThreadsGp * kPitch];
+  double y[kThreadsGp * kPitch];
+  Agg warp_tot[kWarpsGp];   // in-CTA scan: inclusive total of each warp
+  Agg warp_incl[kWarpsGp];  // inclusive prefix (within the CTA) at the last lane of each warp
+  double entry[5];          // state entering the tile: m0, m1, Z00, Z01, Z11
+  double t_halo;            // time stamp before the tile's first cadence
+  double red[kWarpsGp];
+  unsigned ticket;
+  int is_last;
+};
+
+// sum of log D over a run as the log of a product of mantissas plus an integer exponent sum: one DMUL and a
+// few integer instructions per cadence instead of a log; mantissas are in [0.5, 1), so a run of <= 64 cadences
+// cannot underflow, and the exponent sum is exact for ANY finite positive D (no D^4 overflow).
+struct LogProd {
+  double mant = 1.0, slow = 0.0;
+  int expo = 0;
+  __device__ __forceinline__ void mul(double D) {
+    const int hi = __double2hiint(D);
+    const int ef = (hi >> 20) & 0x7ff;
+    if (hi > 0 && ef != 0 && ef != 0x7ff) {  // positive, normal
+      expo += ef - 1022;
+      mant *= __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(D));
+    } else {
+      slow += log(D);  // denormal, zero, negative, inf, nan: exact library semantics (NaN / -inf propagate)
+    }
+  }
+  __device__ __forceinline__ double value() const { return log(mant) + slow + (double)expo * 0.69314718055994530941723212145818; }
+};
+
+#ifndef XO_GP_MINBLOCKS
+#define XO_GP_MINBLOCKS 4  // resident CTAs per SM the forward scan is compiled for (build-time knob)
+#endif
+template <int REC /* 0: none, 1: (v/D, K0, K1) per cadence for the smoother, 2: state entering every run of kRunB cadences */>
+__global__ void __launch_bounds__(kThreadsGp, XO_GP_MINBLOCKS)
+    gp_forward_kernel(const double *__restrict__ t, const double *__restrict__ y, const double *__restrict__ diag, int64_t N,
+                      const double *__restrict__ S0, const double *__restrict__ w0, const double *__restrict__ Qf, double eps,
+                      int tiles, int groups, unsigned *__restrict__ counters /* [0] ticket, [1 + b] tiles done of chain b */,
+                      unsigned *__restrict__ flagA, unsigned *__restrict__ flagT, double *__restrict__ aggA,
+                      double *__restrict__ aggT, double *__restrict__ cta_ll, GpStatus *__restrict__ status,
+                      double *__restrict__ loglike, double *__restrict__ rec, int64_t Tb) {
+  extern __shared__ __align__(16) unsigned char gp_smem_raw[];
+  GpFwdSmem &sm = *reinterpret_cast<GpFwdSmem *>(gp_smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) sm.ticket = atomicAdd(&counters[0], 1u);
+  __syncthreads();
+  const unsigned ticket = sm.ticket;
+  const int64_t bch = ticket / (unsigned)tiles;
+  const int tile = (int)(ticket % (unsigned)tiles);
   const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
-  const int64_t g = (int64_t)blockIdx.x * kThreadsGp + threadIdx.x;
-  const int64_t s = g * kRun, e = min(s + kRun, N);
+  const int64_t base = (int64_t)tile * kTile;
+  const int64_t nvalid = min((int64_t)kTile, N - base);
   const double *yb = y + bch * N;
+  // 1. the tile, coalesced (consecutive threads read consecutive cadences), once
+  for (int idx = tid; idx < kTile; idx += kThreadsGp) {
+    const int r = idx / kRun, i = idx % kRun, at = r * kPitch + i;
+    if (idx < nvalid) {
+      sm.t[at] = __ldg(t + base + idx);
+      sm.d[at] = __ldg(diag + base + idx);
+      sm.y[at] = __ldg(yb + base + idx);
+    }
+  }
+  if (tid == 0) sm.t_halo = __ldg(t + (base > 0 ? base - 1 : 0));
+  __syncthreads();
+  const int64_t s = base + (int64_t)tid * kRun;
+  const int len = (int)max((int64_t)0, min((int64_t)kRun, N - s));
+  const double *ts = sm.t + tid * kPitch, *ds = sm.d + tid * kPitch, *ys = sm.y + tid * kPitch;
+  const double t_before = tid > 0 ? sm.t[(tid - 1) * kPitch + kRun - 1] : sm.t_halo;
+  // 2. the run's scan element, from a known start
   Agg v = agg_identity();
-  if (s < e) {
+  if (len > 0) {
     double A00 = 1, A01 = 0, A10 = 0, A11 = 1, b0 = 0, b1 = 0, e0 = 0, e1 = 0, J00 = 0, J01 = 0, J11 = 0;
     double Z00 = k.a, Z01 = 0.0, Z11 = k.a * k.w2;  // P = 0  <=>  Z = Sigma_inf
-    double tprev = s > 0 ? __ldg(t + s - 1) : __ldg(t);
+    double tprev = t_before;
     ShoCache cc;
-    for (int64_t i = s; i < e; ++i) {
-      const double ti = __ldg(t + i);
+#pragma unroll 1
+    for (int i = 0; i < len; ++i) {
+      const double ti = ts[i];
       double f00, f01, f10, f11;
       sho_phi(k, ti - tprev, cc, f00, f01, f10, f11);
       tprev = ti;
@@ -240,10 +372,10 @@ __global__ void __launch_bounds__(kThreadsGp) gp_aggregate_kernel(const double *
       double z10 = f10 * Z00 + f11 * Z01, z11 = f10 * Z01 + f11 * Z11;
       double p00 = z00 * f00 + z01 * f01, p01 = z00 * f10 + z01 * f11, p11 = z10 * f10 + z11 * f11;
       const double pm = k.a - p00;
-      const double D = pm + __ldg(diag + i);
+      const double D = pm + ds[i];
       const double rD = xo::rcp_fast(D);
       const double K0 = pm * rD, K1 = -p01 * rD;
-      const double vb = __ldg(yb + i) - c0;
+      const double vb = ys[i] - c0;
       J00 = fma(a00 * a00, rD, J00);
       J01 = fma(a00 * a01, rD, J01);
       J11 = fma(a01 * a01, rD, J11);
@@ -261,141 +393,134 @@ __global__ void __launch_bounds__(kThreadsGp) gp_aggregate_kernel(const double *
     }
     v = Agg{A00, A01, A10, A11, b0, b1, k.a - Z00, -Z01, k.a * k.w2 - Z11, e0, e1, J00, J01, J11};
   }
-  v = cta_inclusive_scan(v, warp_tot);
-  if (g < T) agg_store(pref + (bch * T + g) * kAggDoubles, v);
-  if (threadIdx.x == kThreadsGp - 1) agg_store(cta_tot + (bch * gridDim.x + blockIdx.x) * kAggDoubles, v);
-}
-
-// ---- phase 2: scan the CTA totals, emit the state entering each CTA ---------
-__global__ void __launch_bounds__(kThreadsGp) gp_cta_scan_kernel(const double *__restrict__ cta_tot, int nctas,
-                                                                 const double *__restrict__ S0,
-                                                                 const double *__restrict__ w0,
-                                                                 const double *__restrict__ Qf, double eps,
-                                                                 double *__restrict__ cta_state) {
-  __shared__ Agg warp_tot[kWarpsGp];
-  __shared__ Agg carry_s;
-  const int64_t bch = blockIdx.x;
-  const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
-  Agg carry = agg_identity();
-  for (int base = 0; base < nctas; base += kThreadsGp) {
-    const int idx = base + threadIdx.x;
-    Agg v = idx < nctas ? agg_load(cta_tot + (bch * nctas + idx) * kAggDoubles) : agg_identity();
-    v = cta_inclusive_scan(v, warp_tot);
-    Agg incl = agg_combine(carry, v);
-    // exclusive prefix of idx = inclusive of idx-1
-    Agg prev = agg_shfl_up(incl, 1);
-    __shared__ Agg lastlane[kWarpsGp];
-    if ((threadIdx.x & 31) == 31) lastlane[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    Agg excl;
-    if ((threadIdx.x & 31) == 0)
-      excl = (threadIdx.x == 0) ? carry : lastlane[(threadIdx.x >> 5) - 1];
-    else
-      excl = prev;
-    if (idx < nctas) {
+  v = cta_inclusive_scan(v, sm.warp_tot);  // inclusive over the CTA's runs (contains a __syncthreads)
+  if (lane == 31) sm.warp_incl[warp] = v;
+  // 3. publish the tile total, build the state entering the tile
+  if (tid == kThreadsGp - 1) {
+    agg_store(aggA + ((size_t)bch * tiles + tile) * kAggDoubles, v);
+    __threadfence();
+    st_release_u32(flagA + (size_t)bch * tiles + tile, 1u);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int g = tile / kGroup, in_group = tile % kGroup;
+    bool ok = true;
+    // whole groups before this one, windows of 32 totals in group order
+    Agg carry = agg_identity();
+    for (int w0g = 0; w0g < g; w0g += 32) {
+      const int cnt = min(32, g - w0g);
+      Agg mine = agg_identity();
+      if (lane < cnt) {
+        ok &= wait_flag(flagT + (size_t)bch * groups + w0g + lane);
+        mine = agg_load_cg(aggT + ((size_t)bch * groups + w0g + lane) * kAggDoubles);
+      }
+      carry = agg_combine(carry, agg_warp_reduce(mine, cnt));
+    }
+    // earlier tiles of the own group
+    Agg mine = agg_identity();
+    if (lane < in_group) {
+      ok &= wait_flag(flagA + (size_t)bch * tiles + (size_t)g * kGroup + lane);
+      mine = agg_load_cg(aggA + ((size_t)bch * tiles + (size_t)g * kGroup + lane) * kAggDoubles);
+    }
+    const Agg local = agg_warp_reduce(mine, in_group);
+    if (in_group == kGroup - 1 && g + 1 < groups) {  // last tile of a full group that has successors: publish the group total
+      const Agg total = agg_combine(local, sm.warp_incl[kWarpsGp - 1]);
+      if (lane == 0) {
+        agg_store(aggT + ((size_t)bch * groups + g) * kAggDoubles, total);
+        __threadfence();
+        st_release_u32(flagT + (size_t)bch * groups + g, 1u);
+      }
+    }
+    const Agg excl = agg_combine(carry, local);
+    if (!__all_sync(kFullGp, ok) && lane == 0) atomicAdd(&status->wait_failures, 1ull);
+    if (lane == 0) {
       double m0 = 0.0, m1 = 0.0, P00 = k.a, P01 = 0.0, P11 = k.a * k.w2;
       agg_apply(excl, m0, m1, P00, P01, P11);
-      double *o = cta_state + (bch * nctas + idx) * 5;
-      o[0] = m0;
-      o[1] = m1;
-      o[2] = k.a - P00;  // Z = Sigma_inf - P
-      o[3] = -P01;
-      o[4] = k.a * k.w2 - P11;
+      sm.entry[0] = m0;
+      sm.entry[1] = m1;
+      sm.entry[2] = k.a - P00;  // Z = Sigma_inf - P
+      sm.entry[3] = -P01;
+      sm.entry[4] = k.a * k.w2 - P11;
     }
-    if (threadIdx.x == kThreadsGp - 1) carry_s = incl;
-    __syncthreads();
-    carry = carry_s;
-    __syncthreads();
   }
-}
-
-// ---- phase 3 ---------------------------------------------------------------
-__global__ void __launch_bounds__(kThreadsGp) gp_loglike_kernel(const double *__restrict__ t,
-                                                                const double *__restrict__ y,
-                                                                const double *__restrict__ diag, int64_t N,
-                                                                const double *__restrict__ S0,
-                                                                const double *__restrict__ w0,
-                                                                const double *__restrict__ Qf, double eps, int64_t T,
-                                                                const double *__restrict__ pref,
-                                                                const double *__restrict__ cta_state,
-                                                                double *__restrict__ cta_ll,
-                                                                double *__restrict__ rec /* [B][3][N] or null */,
-                                                                double *__restrict__ rec5 /* [B][5][N] or null */) {
-  __shared__ double red[kWarpsGp];
-  const int64_t bch = blockIdx.y;
-  const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
-  const int64_t g = (int64_t)blockIdx.x * kThreadsGp + threadIdx.x;
-  const int64_t s = g * kRun, e = min(s + kRun, N);
-  const double *yb = y + bch * N;
+  // exclusive in-CTA prefix of this thread's run: the inclusive value of the previous thread
+  Agg pre = agg_shfl_up(v, 1);
+  __syncthreads();
+  if (lane == 0 && warp > 0) pre = sm.warp_incl[warp - 1];
+  // 4. re-walk with plain Kalman steps
   double acc = 0.0;
-  if (s < e) {
-    const double *st = cta_state + (bch * gridDim.x + blockIdx.x) * 5;
-    double m0 = st[0], m1 = st[1], Z00 = st[2], Z01 = st[3], Z11 = st[4];
-    if (threadIdx.x > 0) {
+  if (len > 0) {
+    double m0 = sm.entry[0], m1 = sm.entry[1], Z00 = sm.entry[2], Z01 = sm.entry[3], Z11 = sm.entry[4];
+    if (tid > 0) {
       double P00 = k.a - Z00, P01 = -Z01, P11 = k.a * k.w2 - Z11;
-      Agg pre = agg_load(pref + (bch * T + g - 1) * kAggDoubles);
       agg_apply(pre, m0, m1, P00, P01, P11);
       Z00 = k.a - P00;
       Z01 = -P01;
       Z11 = k.a * k.w2 - P11;
     }
-    double tprev = s > 0 ? __ldg(t + s - 1) : __ldg(t);
+    double tprev = t_before;
     ShoCache cc;
-    double dprod = 1.0;
-    int dexp = 0;
-    for (int64_t i = s; i < e; ++i) {
-      const double ti = __ldg(t + i);
+    LogProd lp;
+#pragma unroll 1
+    for (int i = 0; i < len; ++i) {
+      const double ti = ts[i];
       double f00, f01, f10, f11;
       sho_phi(k, ti - tprev, cc, f00, f01, f10, f11);
       tprev = ti;
-      if (rec5) {  // state entering step i: what the reverse-mode pass (gp_grad_*) restarts from
-        double *rb = rec5 + bch * 5 * N + i;
+      if (REC == 2 && (i % kRunB) == 0) {  // state entering every run of kRunB cadences: where the reverse pass restarts
+        double *rb = rec + bch * 5 * Tb + (s + i) / kRunB;
         rb[0] = m0;
-        rb[N] = m1;
-        rb[2 * N] = Z00;
-        rb[3 * N] = Z01;
-        rb[4 * N] = Z11;
+        rb[Tb] = m1;
+        rb[2 * Tb] = Z00;
+        rb[3 * Tb] = Z01;
+        rb[4 * Tb] = Z11;
       }
       double c0 = f00 * m0 + f01 * m1, c1 = f10 * m0 + f11 * m1;
       double z00 = f00 * Z00 + f01 * Z01, z01 = f00 * Z01 + f01 * Z11;
       double z10 = f10 * Z00 + f11 * Z01, z11 = f10 * Z01 + f11 * Z11;
       double p00 = z00 * f00 + z01 * f01, p01 = z00 * f10 + z01 * f11, p11 = z10 * f10 + z11 * f11;
       const double pm = k.a - p00;
-      const double D = pm + __ldg(diag + i);
+      const double D = pm + ds[i];
       const double rD = xo::rcp_fast(D);
       const double K0 = pm * rD, K1 = -p01 * rD;
-      const double v = __ldg(yb + i) - c0;
-      // sum of log D as the log of a running product, renormalised every 4 steps (one log per run
-      // instead of one per cadence); D^4 cannot leave the double range for any sane variance
-      acc = fma(v * v, rD, acc);
-      dprod *= D;
-      if (((i - s) & 3) == 3) {
-        int ex;
-        dprod = frexp(dprod, &ex);
-        dexp += ex;
+      const double vv = ys[i] - c0;
+      acc = fma(vv * vv, rD, acc);
+      lp.mul(D);
+      if (REC == 1) {  // what the backward (disturbance-smoother) pass needs
+        double *rb = rec + bch * 3 * N + s + i;
+        rb[0] = vv * rD;
+        rb[N] = K0;
+        rb[2 * N] = K1;
       }
-      if (rec) {  // what the backward (disturbance-smoother) pass needs
-        double *rb = rec + bch * 3 * N;
-        rb[i] = v * rD;
-        rb[N + i] = K0;
-        rb[2 * N + i] = K1;
-      }
-      m0 = fma(K0, v, c0);
-      m1 = fma(K1, v, c1);
+      m0 = fma(K0, vv, c0);
+      m1 = fma(K1, vv, c1);
       Z00 = fma(D * K0, K0, p00);
       Z01 = fma(D * K0, K1, p01);
       Z11 = fma(D * K1, K1, p11);
     }
-    acc += log(dprod) + (double)dexp * 0.69314718055994530941723212145818;
+    acc += lp.value();
+    if (!isfinite(acc)) atomicAdd(&status->bad_lanes, 1ull);
   }
+  // 5. CTA sum in a fixed order; the last CTA of the chain folds the per-tile sums in tile order
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFullGp, acc, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  if (lane == 0) sm.red[warp] = acc;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     double s4 = 0.0;
-    for (int w = 0; w < kWarpsGp; ++w) s4 += red[w];
-    cta_ll[bch * gridDim.x + blockIdx.x] = s4;
+    for (int w = 0; w < kWarpsGp; ++w) s4 += sm.red[w];
+    cta_ll[(size_t)bch * tiles + tile] = s4;
+    __threadfence();
+    sm.is_last = atomicAdd(&counters[1 + bch], 1u) == (unsigned)(tiles - 1);
+  }
+  __syncthreads();
+  if (sm.is_last && warp == 0) {
+    __threadfence();
+    double tot = 0.0;
+    for (int i = lane; i < tiles; i += 32) tot += __ldcg(cta_ll + (size_t)bch * tiles + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(kFullGp, tot, o);
+    if (lane == 0) loglike[bch] = -0.5 * tot - 0.5 * (double)N * 1.8378770664093454835606594728112;  // log(2 pi)
   }
 }
 
@@ -581,7 +706,7 @@ __global__ void __launch_bounds__(kThreadsGp) gp_bwd_solve_kernel(const double *
 // thread g owns run T-1-g, composes its run's map (24 doubles), in-CTA shuffle scan, one CTA over
 // the CTA totals, then every thread re-walks its run backwards with the now known incoming lambda
 // and accumulates the parameter cotangents.  The forward quantities of a step are recomputed from
-// the recorded state entering it (rec5, written by gp_loglike_kernel).
+// the state entering every run of kRunB cadences, which the forward scan leaves behind.
 // ---------------------------------------------------------------------------
 constexpr int kAdjDoubles = 24;
 struct Adj {
@@ -646,13 +771,6 @@ __device__ __forceinline__ void adj_store(double *p, const Adj &a) {
 #pragma unroll
   for (int k = 0; k < kAdjDoubles; ++k) p[k] = src[k];
 }
-__device__ __forceinline__ Adj adj_load(const double *p) {
-  Adj a;
-  double *dst = a.A;
-#pragma unroll
-  for (int k = 0; k < kAdjDoubles; ++k) dst[k] = p[k];
-  return a;
-}
 __device__ Adj adj_cta_inclusive_scan(Adj v, Adj *warp_tot) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll 1
@@ -677,19 +795,17 @@ struct StepFwd {
   double w00, w01, w10, w11;  // W = Phi Z
   double k0, k1, rD, w;       // k, 1/D, v/D
 };
-__device__ __forceinline__ StepFwd gp_step_fwd(const Sho &k, const double *__restrict__ t, const double *__restrict__ yb,
-                                               const double *__restrict__ diag, const double *__restrict__ r5, int64_t N,
-                                               int64_t i, ShoCache &cc) {
+__device__ __forceinline__ StepFwd gp_step_fwd(const Sho &k, double dt, double yi, double di, double m0, double m1, double Z00,
+                                               double Z01, double Z11, ShoCache &cc) {
   StepFwd s;
-  s.dt = i > 0 ? __ldg(t + i) - __ldg(t + i - 1) : 0.0;
+  s.dt = dt;
   sho_cs(k, s.dt, cc, s.Cf, s.Sf);
   s.f00 = fma(k.c, s.Sf, s.Cf);
   s.f01 = s.Sf;
   s.f10 = -k.w2 * s.Sf;
   s.f11 = fma(-k.c, s.Sf, s.Cf);
-  s.m0 = __ldg(r5 + i);
-  s.m1 = __ldg(r5 + N + i);
-  const double Z00 = __ldg(r5 + 2 * N + i), Z01 = __ldg(r5 + 3 * N + i), Z11 = __ldg(r5 + 4 * N + i);
+  s.m0 = m0;
+  s.m1 = m1;
   s.w00 = s.f00 * Z00 + s.f01 * Z01;
   s.w01 = s.f00 * Z01 + s.f01 * Z11;
   s.w10 = s.f10 * Z00 + s.f11 * Z01;
@@ -697,8 +813,8 @@ __device__ __forceinline__ StepFwd gp_step_fwd(const Sho &k, const double *__res
   const double p00 = s.w00 * s.f00 + s.w01 * s.f01, p01 = s.w00 * s.f10 + s.w01 * s.f11;
   s.k0 = k.a - p00;
   s.k1 = -p01;
-  s.rD = xo::rcp_fast(s.k0 + __ldg(diag + i));
-  s.w = (__ldg(yb + i) - (s.f00 * s.m0 + s.f01 * s.m1)) * s.rD;
+  s.rD = xo::rcp_fast(s.k0 + di);
+  s.w = (yi - (s.f00 * s.m0 + s.f01 * s.m1)) * s.rD;
   return s;
 }
 
@@ -739,31 +855,143 @@ __device__ __forceinline__ void gp_step_adj(const StepFwd &s, double (&L)[5], do
   }
 }
 
-__global__ void __launch_bounds__(kThreadsGp) gp_grad_aggregate_kernel(const double *__restrict__ t,
-                                                                       const double *__restrict__ y,
-                                                                       const double *__restrict__ diag, int64_t N,
-                                                                       const double *__restrict__ S0,
-                                                                       const double *__restrict__ w0,
-                                                                       const double *__restrict__ Qf, double eps,
-                                                                       int64_t T, const double *__restrict__ rec5,
-                                                                       double *__restrict__ gpref,
-                                                                       double *__restrict__ gcta) {
-  __shared__ Adj warp_tot[kWarpsGp];
-  const int64_t bch = blockIdx.y;
+__device__ __forceinline__ Adj adj_load_cg(const double *p) {
+  Adj a;
+  double *dst = a.A;
+#pragma unroll
+  for (int k = 0; k < kAdjDoubles; ++k) dst[k] = __ldcg(p + k);
+  return a;
+}
+// fixed-order composition of the maps held by lanes [0, count) (lane 0 applied first); every lane gets the result
+__device__ __forceinline__ Adj adj_warp_reduce(Adj v, int count) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int d = 1; d < 32; d <<= 1) {
+    Adj o = adj_shfl_up(v, d);
+    if (lane >= d && lane < count) v = adj_after(o, v);
+  }
+  const int last = count > 0 ? count - 1 : 0;
+  Adj r;
+  const double *src = v.A;
+  double *dst = r.A;
+#pragma unroll
+  for (int k = 0; k < kAdjDoubles; ++k) dst[k] = __shfl_sync(kFullGp, src[k], last);
+  return count > 0 ? r : adj_identity();
+}
+
+// ---- one-pass reverse (adjoint) scan -------------------------------------------
+// Same structure as the forward scan, run right-to-left: ticket -> (chain, reverse tile), thread `tid` owns
+// time-run 127 - tid of a tile of kTileB = 128 x 8 cadences, so thread order = scan order.  The forward pass
+// left only the state entering every run of 8 cadences (5 doubles per run, 5 B per cadence instead of 40);
+// each thread re-derives the states inside its run into shared memory (thread-contiguous, conflict-free) and
+// walks the run backwards twice: once pushing the origin and the five basis vectors (the run's affine map),
+// once -- after the in-CTA scan and the fixed-tree look-back over earlier tiles -- with the known incoming
+// lambda, accumulating the hyper-parameter cotangents and emitting d/dy, d/d diag through shared memory
+// (coalesced stores).  The last tile of a chain to finish folds the per-tile sums in tile order and chains
+// (a, c, h, w2) -> (S0, w0, Q).
+constexpr int kTileB = kThreadsGp * kRunB;
+constexpr int kPitchB = kRunB + 1;
+
+struct GpBwdSmem {
+  double t[kThreadsGp * kPitchB];
+  double d[kThreadsGp * kPitchB];  // diag in, d loglike / d diag out
+  double y[kThreadsGp * kPitchB];  // y in, d loglike / d y out
+  double st[5][kRunB][kThreadsGp]; // state entering every step of every run
+  Adj warp_tot[kWarpsGp];
+  Adj warp_incl[kWarpsGp];
+  double entry[5];
+  double t_halo;
+  double red[4][kWarpsGp];
+  unsigned ticket;
+  int is_last;
+};
+
+__global__ void __launch_bounds__(kThreadsGp, 3)
+    gp_backward_kernel(const double *__restrict__ t, const double *__restrict__ y, const double *__restrict__ diag, int64_t N,
+                       const double *__restrict__ S0, const double *__restrict__ w0, const double *__restrict__ Qf, double eps,
+                       int tiles, int groups, int64_t Tb, const double *__restrict__ rs /* [B][5][Tb] run-start states */,
+                       unsigned *__restrict__ counters, unsigned *__restrict__ flagA, unsigned *__restrict__ flagT,
+                       double *__restrict__ adjA, double *__restrict__ adjT, double *__restrict__ gpart /* [B][tiles][4] */,
+                       GpStatus *__restrict__ status, double *__restrict__ gy, double *__restrict__ gdiag,
+                       double *__restrict__ ghyper /* [B][3] */) {
+  extern __shared__ __align__(16) unsigned char gp_smem_raw[];
+  GpBwdSmem &sm = *reinterpret_cast<GpBwdSmem *>(gp_smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) sm.ticket = atomicAdd(&counters[0], 1u);
+  __syncthreads();
+  const unsigned ticket = sm.ticket;
+  const int64_t bch = ticket / (unsigned)tiles;
+  const int rtile = (int)(ticket % (unsigned)tiles);  // 0 = the LAST tile in time
+  const int ttile = tiles - 1 - rtile;
   const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
-  const int64_t g = (int64_t)blockIdx.x * kThreadsGp + threadIdx.x;
-  const int64_t run = T - 1 - g;  // reversed ownership
+  const int64_t base = (int64_t)ttile * kTileB;
+  const int64_t nvalid = min((int64_t)kTileB, N - base);
+  const double *yb = y + bch * N;
+  for (int idx = tid; idx < kTileB; idx += kThreadsGp) {
+    const int r = idx / kRunB, i = idx % kRunB, at = r * kPitchB + i;
+    if (idx < nvalid) {
+      sm.t[at] = __ldg(t + base + idx);
+      sm.d[at] = __ldg(diag + base + idx);
+      sm.y[at] = __ldg(yb + base + idx);
+    }
+  }
+  if (tid == 0) sm.t_halo = __ldg(t + (base > 0 ? base - 1 : 0));
+  __syncthreads();
+  const int r = kThreadsGp - 1 - tid;  // time-run inside the tile
+  const int64_t s = base + (int64_t)r * kRunB;
+  const int len = (int)max((int64_t)0, min((int64_t)kRunB, N - s));
+  double *ts = sm.t + r * kPitchB, *ds = sm.d + r * kPitchB, *ys = sm.y + r * kPitchB;
+  const double t_before = r > 0 ? sm.t[(r - 1) * kPitchB + kRunB - 1] : sm.t_halo;
+  // states entering every step of the run, re-derived from the run-start state the forward pass left
+  if (len > 0) {
+    const int64_t run = s / kRunB;
+    const double *rp = rs + (size_t)bch * 5 * Tb + run;
+    double m0 = __ldg(rp), m1 = __ldg(rp + Tb), Z00 = __ldg(rp + 2 * Tb), Z01 = __ldg(rp + 3 * Tb), Z11 = __ldg(rp + 4 * Tb);
+    double tprev = t_before;
+    ShoCache cc;
+#pragma unroll 1
+    for (int i = 0; i < len; ++i) {
+      sm.st[0][i][tid] = m0;
+      sm.st[1][i][tid] = m1;
+      sm.st[2][i][tid] = Z00;
+      sm.st[3][i][tid] = Z01;
+      sm.st[4][i][tid] = Z11;
+      if (i + 1 == len) break;
+      const double ti = ts[i];
+      double f00, f01, f10, f11;
+      sho_phi(k, (s + i) > 0 ? ti - tprev : 0.0, cc, f00, f01, f10, f11);
+      tprev = ti;
+      double c0 = f00 * m0 + f01 * m1, c1 = f10 * m0 + f11 * m1;
+      double z00 = f00 * Z00 + f01 * Z01, z01 = f00 * Z01 + f01 * Z11;
+      double z10 = f10 * Z00 + f11 * Z01, z11 = f10 * Z01 + f11 * Z11;
+      double p00 = z00 * f00 + z01 * f01, p01 = z00 * f10 + z01 * f11, p11 = z10 * f10 + z11 * f11;
+      const double pm = k.a - p00;
+      const double D = pm + ds[i];
+      const double rD = xo::rcp_fast(D);
+      const double K0 = pm * rD, K1 = -p01 * rD;
+      const double vv = ys[i] - c0;
+      m0 = fma(K0, vv, c0);
+      m1 = fma(K1, vv, c1);
+      Z00 = fma(D * K0, K0, p00);
+      Z01 = fma(D * K0, K1, p01);
+      Z11 = fma(D * K1, K1, p11);
+    }
+  }
+  auto step_fwd = [&](int i, ShoCache &cc) {
+    const double tp = i > 0 ? ts[i - 1] : t_before;
+    const double dt = (s + i) > 0 ? ts[i] - tp : 0.0;
+    return gp_step_fwd(k, dt, ys[i], ds[i], sm.st[0][i][tid], sm.st[1][i][tid], sm.st[2][i][tid], sm.st[3][i][tid],
+                       sm.st[4][i][tid], cc);
+  };
+  // the run's map lambda_{e-1} -> lambda_{s-1}: push the origin (with the forcing) and the five basis vectors through it
   Adj v = adj_identity();
-  if (run >= 0) {
-    const int64_t s = run * kRunB, e = min(s + kRunB, N);
-    const double *yb = y + bch * N, *r5 = rec5 + bch * 5 * N;
-    // the run's map lambda_{e-1} -> lambda_{s-1}: push the origin (with the forcing) and the five
-    // basis vectors (linear part) through it
+  if (len > 0) {
     double O[5] = {0, 0, 0, 0, 0}, X0[5] = {1, 0, 0, 0, 0}, X1[5] = {0, 1, 0, 0, 0}, X2[5] = {0, 0, 1, 0, 0},
            X3[5] = {0, 0, 0, 1, 0}, X4[5] = {0, 0, 0, 0, 1};
     ShoCache cc;
-    for (int64_t i = e - 1; i >= s; --i) {
-      const StepFwd f = gp_step_fwd(k, t, yb, diag, r5, N, i, cc);
+#pragma unroll 1
+    for (int i = len - 1; i >= 0; --i) {
+      const StepFwd f = step_fwd(i, cc);
       gp_step_adj<true, false>(f, O, nullptr);
       gp_step_adj<false, false>(f, X0, nullptr);
       gp_step_adj<false, false>(f, X1, nullptr);
@@ -773,84 +1001,77 @@ __global__ void __launch_bounds__(kThreadsGp) gp_grad_aggregate_kernel(const dou
     }
     v.A[0] = X0[0]; v.A[1] = X1[0]; v.A[2] = X0[1]; v.A[3] = X1[1];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      v.B[2 * r] = X0[2 + r];
-      v.B[2 * r + 1] = X1[2 + r];
-      v.C[3 * r] = X2[2 + r];
-      v.C[3 * r + 1] = X3[2 + r];
-      v.C[3 * r + 2] = X4[2 + r];
-      v.oz[r] = O[2 + r];
+    for (int q = 0; q < 3; ++q) {
+      v.B[2 * q] = X0[2 + q];
+      v.B[2 * q + 1] = X1[2 + q];
+      v.C[3 * q] = X2[2 + q];
+      v.C[3 * q + 1] = X3[2 + q];
+      v.C[3 * q + 2] = X4[2 + q];
+      v.oz[q] = O[2 + q];
     }
     v.om[0] = O[0];
     v.om[1] = O[1];
   }
-  v = adj_cta_inclusive_scan(v, warp_tot);
-  if (g < T) adj_store(gpref + (bch * T + g) * kAdjDoubles, v);
-  if (threadIdx.x == kThreadsGp - 1) adj_store(gcta + (bch * gridDim.x + blockIdx.x) * kAdjDoubles, v);
-}
-
-// lambda entering each CTA (from the right): exclusive scan of the CTA totals applied to lambda = 0
-__global__ void __launch_bounds__(kThreadsGp) gp_grad_cta_scan_kernel(const double *__restrict__ gcta, int nctas,
-                                                                      double *__restrict__ gstate) {
-  __shared__ Adj warp_tot[kWarpsGp];
-  __shared__ Adj lastlane[kWarpsGp];
-  __shared__ Adj carry_s;
-  const int64_t bch = blockIdx.x;
-  Adj carry = adj_identity();
-  for (int base = 0; base < nctas; base += kThreadsGp) {
-    const int idx = base + threadIdx.x;
-    Adj v = idx < nctas ? adj_load(gcta + (bch * nctas + idx) * kAdjDoubles) : adj_identity();
-    v = adj_cta_inclusive_scan(v, warp_tot);
-    Adj incl = adj_after(carry, v);
-    Adj prev = adj_shfl_up(incl, 1);
-    if ((threadIdx.x & 31) == 31) lastlane[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) prev = threadIdx.x == 0 ? carry : lastlane[(threadIdx.x >> 5) - 1];
-    if (idx < nctas) {
-      double *o = gstate + (bch * nctas + idx) * 5;
-      o[0] = prev.om[0];
-      o[1] = prev.om[1];
-      o[2] = prev.oz[0];
-      o[3] = prev.oz[1];
-      o[4] = prev.oz[2];
-    }
-    if (threadIdx.x == kThreadsGp - 1) carry_s = incl;
-    __syncthreads();
-    carry = carry_s;
-    __syncthreads();
+  v = adj_cta_inclusive_scan(v, sm.warp_tot);
+  if (lane == 31) sm.warp_incl[warp] = v;
+  if (tid == kThreadsGp - 1) {
+    adj_store(adjA + ((size_t)bch * tiles + rtile) * kAdjDoubles, v);
+    __threadfence();
+    st_release_u32(flagA + (size_t)bch * tiles + rtile, 1u);
   }
-}
-
-__global__ void __launch_bounds__(kThreadsGp) gp_grad_final_kernel(const double *__restrict__ t,
-                                                                   const double *__restrict__ y,
-                                                                   const double *__restrict__ diag, int64_t N,
-                                                                   const double *__restrict__ S0,
-                                                                   const double *__restrict__ w0,
-                                                                   const double *__restrict__ Qf, double eps, int64_t T,
-                                                                   const double *__restrict__ rec5,
-                                                                   const double *__restrict__ gpref,
-                                                                   const double *__restrict__ gstate,
-                                                                   double *__restrict__ gy, double *__restrict__ gdiag,
-                                                                   double *__restrict__ gpart /* [B][nctas][4] */) {
-  __shared__ double red[4][kWarpsGp];
-  const int64_t bch = blockIdx.y;
-  const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
-  const int64_t g = (int64_t)blockIdx.x * kThreadsGp + threadIdx.x;
-  const int64_t run = T - 1 - g;
+  __syncthreads();
+  if (warp == 0) {
+    const int g = rtile / kGroup, in_group = rtile % kGroup;
+    bool ok = true;
+    Adj carry = adj_identity();
+    for (int w0g = 0; w0g < g; w0g += 32) {
+      const int cnt = min(32, g - w0g);
+      Adj mine = adj_identity();
+      if (lane < cnt) {
+        ok &= wait_flag(flagT + (size_t)bch * groups + w0g + lane);
+        mine = adj_load_cg(adjT + ((size_t)bch * groups + w0g + lane) * kAdjDoubles);
+      }
+      carry = adj_after(carry, adj_warp_reduce(mine, cnt));
+    }
+    Adj mine = adj_identity();
+    if (lane < in_group) {
+      ok &= wait_flag(flagA + (size_t)bch * tiles + (size_t)g * kGroup + lane);
+      mine = adj_load_cg(adjA + ((size_t)bch * tiles + (size_t)g * kGroup + lane) * kAdjDoubles);
+    }
+    const Adj local = adj_warp_reduce(mine, in_group);
+    if (in_group == kGroup - 1 && g + 1 < groups) {
+      const Adj total = adj_after(local, sm.warp_incl[kWarpsGp - 1]);
+      if (lane == 0) {
+        adj_store(adjT + ((size_t)bch * groups + g) * kAdjDoubles, total);
+        __threadfence();
+        st_release_u32(flagT + (size_t)bch * groups + g, 1u);
+      }
+    }
+    const Adj excl = adj_after(carry, local);
+    if (!__all_sync(kFullGp, ok) && lane == 0) atomicAdd(&status->wait_failures, 1ull);
+    if (lane == 0) {  // the map applied to lambda = 0 beyond the last cadence
+      sm.entry[0] = excl.om[0];
+      sm.entry[1] = excl.om[1];
+      sm.entry[2] = excl.oz[0];
+      sm.entry[3] = excl.oz[1];
+      sm.entry[4] = excl.oz[2];
+    }
+  }
+  Adj pre = adj_shfl_up(v, 1);
+  __syncthreads();
+  if (lane == 0 && warp > 0) pre = sm.warp_incl[warp - 1];
   double ga = 0.0, gc = 0.0, gh = 0.0, gw2 = 0.0;  // cotangents of a, c, h and w2 = c^2 +- h^2
-  if (run >= 0) {
-    const int64_t s = run * kRunB, e = min(s + kRunB, N);
-    const double *st = gstate + (bch * gridDim.x + blockIdx.x) * 5;
-    double L[5] = {st[0], st[1], st[2], st[3], st[4]};
-    if (threadIdx.x > 0) adj_apply(adj_load(gpref + (bch * T + g - 1) * kAdjDoubles), L);
-    const double *yb = y + bch * N, *r5 = rec5 + bch * 5 * N;
+  if (len > 0) {
+    double L[5] = {sm.entry[0], sm.entry[1], sm.entry[2], sm.entry[3], sm.entry[4]};
+    if (tid > 0) adj_apply(pre, L);
     ShoCache cc;
-    for (int64_t i = e - 1; i >= s; --i) {
-      const StepFwd f = gp_step_fwd(k, t, yb, diag, r5, N, i, cc);
+#pragma unroll 1
+    for (int i = len - 1; i >= 0; --i) {
+      const StepFwd f = step_fwd(i, cc);
       double acc[7];
       gp_step_adj<true, true>(f, L, acc);
-      if (gy) gy[bch * N + i] = acc[0];
-      if (gdiag) gdiag[bch * N + i] = acc[1];
+      ys[i] = acc[0];  // d / d y_i     (y_i, diag_i are dead from here on: every step reads its own only)
+      ds[i] = acc[1];  // d / d diag_i
       ga += acc[2];
       // Phi = [[Cf + c Sf, Sf], [-w2 Sf, Cf - c Sf]]
       const double d0011 = acc[3] - acc[6];
@@ -861,98 +1082,111 @@ __global__ void __launch_bounds__(kThreadsGp) gp_grad_final_kernel(const double 
       const double dCdh = (k.under ? -f.dt : f.dt) * k.h * f.Sf;
       gh += dCdh * Cb + (f.dt * f.Cf - f.Sf) / k.h * Sb;
     }
+    if (!isfinite(ga + gc + gh + gw2)) atomicAdd(&status->bad_lanes, 1ull);
   }
   double vals[4] = {ga, gc, gh, gw2};
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    double v = vals[j];
+    double x = vals[j];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullGp, v, o);
-    if ((threadIdx.x & 31) == 0) red[j][threadIdx.x >> 5] = v;
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFullGp, x, o);
+    if (lane == 0) sm.red[j][warp] = x;
   }
   __syncthreads();
-  if (threadIdx.x < 4) {
+  // per-cadence gradients out, coalesced
+  if (gy || gdiag) {
+    for (int idx = tid; idx < kTileB; idx += kThreadsGp) {
+      if (idx < nvalid) {
+        const int at = (idx / kRunB) * kPitchB + idx % kRunB;
+        if (gy) gy[bch * N + base + idx] = sm.y[at];
+        if (gdiag) gdiag[bch * N + base + idx] = sm.d[at];
+      }
+    }
+  }
+  if (tid < 4) {
     double s4 = 0.0;
-    for (int w = 0; w < kWarpsGp; ++w) s4 += red[threadIdx.x][w];
-    gpart[(bch * gridDim.x + blockIdx.x) * 4 + threadIdx.x] = s4;
+    for (int w = 0; w < kWarpsGp; ++w) s4 += sm.red[tid][w];
+    gpart[((size_t)bch * tiles + rtile) * 4 + tid] = s4;
   }
-}
-
-// fold the per-CTA cotangents of (a, c, h, w2) in CTA order and chain them to (S0, w0, Q):
-//   a = S0 w0 Q,  c = w0 / (2Q),  h = c f,  f = sqrt(max(+-(4Q^2 - 1), eps)),  w2 = c^2 +- h^2
-__global__ void gp_grad_fold_kernel(const double *__restrict__ gpart, int nctas, const double *__restrict__ S0,
-                                    const double *__restrict__ w0, const double *__restrict__ Qf, double eps, int64_t B,
-                                    double *__restrict__ ghyper /* [B][3] */) {
-  const int64_t bch = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (bch >= B) return;
-  const int lane = threadIdx.x & 31;
-  double ga = 0.0, gc = 0.0, gh = 0.0, gw2 = 0.0;
-  for (int i = lane; i < nctas; i += 32) {  // one warp per chain, fixed order (deterministic)
-    const double *p = gpart + (bch * nctas + i) * 4;
-    ga += p[0];
-    gc += p[1];
-    gh += p[2];
-    gw2 += p[3];
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    sm.is_last = atomicAdd(&counters[1 + bch], 1u) == (unsigned)(tiles - 1);
   }
+  __syncthreads();
+  if (sm.is_last && warp == 0) {
+    // fold the per-tile cotangents of (a, c, h, w2) in tile order and chain them to (S0, w0, Q):
+    //   a = S0 w0 Q,  c = w0 / (2Q),  h = c f,  f = sqrt(max(+-(4Q^2 - 1), eps)),  w2 = c^2 +- h^2
+    __threadfence();
+    double fa = 0.0, fc = 0.0, fh = 0.0, fw2 = 0.0;
+    for (int i = lane; i < tiles; i += 32) {
+      const double *p = gpart + ((size_t)bch * tiles + i) * 4;
+      fa += __ldcg(p);
+      fc += __ldcg(p + 1);
+      fh += __ldcg(p + 2);
+      fw2 += __ldcg(p + 3);
+    }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    ga += __shfl_xor_sync(kFullGp, ga, o);
-    gc += __shfl_xor_sync(kFullGp, gc, o);
-    gh += __shfl_xor_sync(kFullGp, gh, o);
-    gw2 += __shfl_xor_sync(kFullGp, gw2, o);
+    for (int o = 16; o > 0; o >>= 1) {
+      fa += __shfl_xor_sync(kFullGp, fa, o);
+      fc += __shfl_xor_sync(kFullGp, fc, o);
+      fh += __shfl_xor_sync(kFullGp, fh, o);
+      fw2 += __shfl_xor_sync(kFullGp, fw2, o);
+    }
+    if (lane == 0) {
+      const double sgn = k.under ? 1.0 : -1.0;
+      fc += 2.0 * k.c * fw2;
+      fh += sgn * 2.0 * k.h * fw2;
+      const double s0 = S0[bch], w = w0[bch], Q = Qf[bch];
+      const double arg = sgn * (4.0 * Q * Q - 1.0);
+      const double f = sqrt(fmax(arg, eps));
+      const double dfdQ = arg > eps ? sgn * 4.0 * Q / f : 0.0;
+      const double dcdQ = -k.c / Q;
+      ghyper[3 * bch + 0] = fa * w * Q;
+      ghyper[3 * bch + 1] = fa * s0 * Q + fc * (0.5 / Q) + fh * (0.5 / Q) * f;
+      ghyper[3 * bch + 2] = fa * s0 * w + fc * dcdQ + fh * (dcdQ * f + k.c * dfdQ);
+    }
   }
-  if (lane != 0) return;
-  const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
-  const double sgn = k.under ? 1.0 : -1.0;
-  gc += 2.0 * k.c * gw2;
-  gh += sgn * 2.0 * k.h * gw2;
-  const double s0 = S0[bch], w = w0[bch], Q = Qf[bch];
-  const double arg = sgn * (4.0 * Q * Q - 1.0);
-  const double f = sqrt(fmax(arg, eps));
-  const double dfdQ = arg > eps ? sgn * 4.0 * Q / f : 0.0;
-  const double dcdQ = -k.c / Q;
-  ghyper[3 * bch + 0] = ga * w * Q;
-  ghyper[3 * bch + 1] = ga * s0 * Q + gc * (0.5 / Q) + gh * (0.5 / Q) * f;
-  ghyper[3 * bch + 2] = ga * s0 * w + gc * dcdQ + gh * (dcdQ * f + k.c * dfdQ);
-}
-
-// one warp per chain: lane-strided partial sums in CTA order, then a fixed butterfly (deterministic)
-__global__ void gp_fold_kernel(const double *__restrict__ cta_ll, int nctas, int64_t N, int64_t B,
-                               double *__restrict__ loglike) {
-  const int64_t bch = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (bch >= B) return;
-  const int lane = threadIdx.x & 31;
-  double acc = 0.0;
-  for (int i = lane; i < nctas; i += 32) acc += cta_ll[bch * nctas + i];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFullGp, acc, o);
-  if (lane == 0) loglike[bch] = -0.5 * acc - 0.5 * (double)N * 1.8378770664093454835606594728112;  // log(2 pi)
 }
 
 struct GpLayout {
-  int64_t T;      // runs (threads) per chain
-  int nctas;      // CTAs per chain
-  int64_t Tb;     // the same for the reverse passes (runs of kRunB)
-  int nctas_b;
-  size_t off_pref, off_tot, off_state, off_ll, off_rec, off_bpref, off_bcta, off_bstate, off_rec5, off_gpref, off_gcta, off_gstate,
-      off_gpart, bytes;
+  int tiles, groups;    // forward pass: tiles of kTile cadences per chain, groups of kGroup tiles
+  int tiles_b, groups_b;  // reverse (adjoint) pass: tiles of kTileB cadences
+  int64_t Tb;           // runs of kRunB cadences per chain
+  int nctas_b;          // smoother pass (three-kernel form): CTAs per chain
+  size_t zero_bytes;    // status word + counters + flags at the head of the workspace: cleared before every call
+  size_t off_counters, off_flagA, off_flagT, off_aggA, off_aggT, off_ll;
+  size_t off_counters_b, off_flagA_b, off_flagT_b, off_adjA, off_adjT, off_rs, off_gpart;
+  size_t off_rec, off_bpref, off_bcta, off_bstate, bytes;
 };
 inline GpLayout gp_layout(int64_t N, int64_t B, bool solve = false, bool grad = false) {
   GpLayout L;
-  L.T = (N + kRun - 1) / kRun;
-  L.nctas = (int)((L.T + kThreadsGp - 1) / kThreadsGp);
+  L.tiles = (int)((N + kTile - 1) / kTile);
+  L.groups = (L.tiles + kGroup - 1) / kGroup;
+  L.tiles_b = (int)((N + kTileB - 1) / kTileB);
+  L.groups_b = (L.tiles_b + kGroup - 1) / kGroup;
   L.Tb = (N + kRunB - 1) / kRunB;
   L.nctas_b = (int)((L.Tb + kThreadsGp - 1) / kThreadsGp);
-  size_t o = 0;
-  auto take = [&](size_t n) {
+  size_t o = 256;  // GpStatus
+  auto take_bytes = [&](size_t n) {
     size_t at = o;
-    o += (n * sizeof(double) + 255) & ~(size_t)255;
+    o += (n + 255) & ~(size_t)255;
     return at;
   };
-  L.off_pref = take((size_t)B * L.T * kAggDoubles);
-  L.off_tot = take((size_t)B * L.nctas * kAggDoubles);
-  L.off_state = take((size_t)B * L.nctas * 5);
-  L.off_ll = take((size_t)B * L.nctas);
+  auto take = [&](size_t n) { return take_bytes(n * sizeof(double)); };
+  L.off_counters = take_bytes((size_t)(1 + B) * sizeof(unsigned));
+  L.off_flagA = take_bytes((size_t)B * L.tiles * sizeof(unsigned));
+  L.off_flagT = take_bytes((size_t)B * L.groups * sizeof(unsigned));
+  L.off_counters_b = L.off_flagA_b = L.off_flagT_b = 0;
+  if (grad) {
+    L.off_counters_b = take_bytes((size_t)(1 + B) * sizeof(unsigned));
+    L.off_flagA_b = take_bytes((size_t)B * L.tiles_b * sizeof(unsigned));
+    L.off_flagT_b = take_bytes((size_t)B * L.groups_b * sizeof(unsigned));
+  }
+  L.zero_bytes = o;
+  L.off_aggA = take((size_t)B * L.tiles * kAggDoubles);
+  L.off_aggT = take((size_t)B * L.groups * kAggDoubles);
+  L.off_ll = take((size_t)B * L.tiles);
   L.off_rec = L.off_bpref = L.off_bcta = L.off_bstate = 0;
   if (solve) {
     L.off_rec = take((size_t)B * 3 * N);
@@ -960,16 +1194,38 @@ inline GpLayout gp_layout(int64_t N, int64_t B, bool solve = false, bool grad = 
     L.off_bcta = take((size_t)B * L.nctas_b * 6);
     L.off_bstate = take((size_t)B * L.nctas_b * 2);
   }
-  L.off_rec5 = L.off_gpref = L.off_gcta = L.off_gstate = L.off_gpart = 0;
+  L.off_adjA = L.off_adjT = L.off_rs = L.off_gpart = 0;
   if (grad) {
-    L.off_rec5 = take((size_t)B * 5 * N);
-    L.off_gpref = take((size_t)B * L.Tb * kAdjDoubles);
-    L.off_gcta = take((size_t)B * L.nctas_b * kAdjDoubles);
-    L.off_gstate = take((size_t)B * L.nctas_b * 5);
-    L.off_gpart = take((size_t)B * L.nctas_b * 4);
+    L.off_rs = take((size_t)B * 5 * L.Tb);
+    L.off_adjA = take((size_t)B * L.tiles_b * kAdjDoubles);
+    L.off_adjT = take((size_t)B * L.groups_b * kAdjDoubles);
+    L.off_gpart = take((size_t)B * L.tiles_b * 4);
   }
   L.bytes = o;
   return L;
+}
+
+// the one-pass forward scan: clear status/counters/flags (one stream-ordered memset), one kernel
+template <int REC>
+int gp_forward(const double *t, const double *y, const double *diag, int64_t N, const double *S0, const double *w0, const double *Q,
+               int64_t B, double eps, double *loglike, double *rec, char *ws, const GpLayout &L, cudaStream_t st) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gp_forward_kernel<REC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GpFwdSmem));
+    if (e != cudaSuccess) return -(int)e;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  cudaError_t e = cudaMemsetAsync(ws, 0, L.zero_bytes, st);
+  if (e != cudaSuccess) return -(int)e;
+  const size_t total = (size_t)B * L.tiles;
+  xo::launch(gp_forward_kernel<REC>, dim3((unsigned)total), dim3(kThreadsGp), sizeof(GpFwdSmem), st, t, y, diag, N, S0, w0, Q, eps, L.tiles,
+             L.groups, reinterpret_cast<unsigned *>(ws + L.off_counters), reinterpret_cast<unsigned *>(ws + L.off_flagA),
+             reinterpret_cast<unsigned *>(ws + L.off_flagT), reinterpret_cast<double *>(ws + L.off_aggA),
+             reinterpret_cast<double *>(ws + L.off_aggT), reinterpret_cast<double *>(ws + L.off_ll), reinterpret_cast<GpStatus *>(ws),
+             loglike, rec, L.Tb);
+  return 0;
 }
 
 }  // namespace
@@ -987,22 +1243,14 @@ int xo_celerite_sho_loglike(const double *t, const double *y, const double *diag
   if (N < 0 || B < 0) return XO_EINVAL;
   if (B == 0) return 0;
   if (N == 0) return XO_EINVAL;
-  if (B > 65535) return XO_ERANGE;
+  if ((double)B * (double)((N + kTile - 1) / kTile) > 2.0e9) return XO_ERANGE;
   if (!t || !y || !diag || !S0 || !w0 || !Q || !loglike || !workspace) return XO_EINVAL;
+  XO_NVTX_SCOPE("xo_celerite_sho_loglike");
   GpLayout L = gp_layout(N, B);
   if (workspace_bytes < L.bytes) return XO_EWORKSPACE;
-  char *ws = static_cast<char *>(workspace);
-  double *pref = reinterpret_cast<double *>(ws + L.off_pref);
-  double *tot = reinterpret_cast<double *>(ws + L.off_tot);
-  double *state = reinterpret_cast<double *>(ws + L.off_state);
-  double *ll = reinterpret_cast<double *>(ws + L.off_ll);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  dim3 grid(L.nctas, (unsigned)B);
-  xo::launch(gp_aggregate_kernel, grid, kThreadsGp, 0, st, t, y, diag, N, S0, w0, Q, eps, L.T, pref, tot);
-  xo::launch(gp_cta_scan_kernel, (unsigned)B, kThreadsGp, 0, st, tot, L.nctas, S0, w0, Q, eps, state);
-  xo::launch(gp_loglike_kernel, grid, kThreadsGp, 0, st, t, y, diag, N, S0, w0, Q, eps, L.T, pref, state, ll, nullptr, nullptr);
-  xo::launch(gp_fold_kernel, (unsigned)((B + 3) / 4), 128, 0, st, ll, L.nctas, N, B, loglike);
-  return xo::launch_status();
+  int rc = gp_forward<0>(t, y, diag, N, S0, w0, Q, B, eps, loglike, nullptr, static_cast<char *>(workspace), L, st);
+  return rc ? rc : xo::launch_status();
 }
 
 size_t xo_celerite_sho_solve_workspace(int64_t N, int64_t B) {
@@ -1018,19 +1266,16 @@ int xo_celerite_sho_solve(const double *t, const double *y, const double *diag, 
   if (N < 0 || B < 0) return XO_EINVAL;
   if (B == 0) return 0;
   if (N == 0) return XO_EINVAL;
-  if (B > 65535) return XO_ERANGE;
+  if (B > 65535 || (double)B * (double)((N + kTileB - 1) / kTileB) > 2.0e9) return XO_ERANGE;
   if (!t || !y || !diag || !S0 || !w0 || !Q || !loglike || !alpha || !workspace) return XO_EINVAL;
   GpLayout L = gp_layout(N, B, true);
   if (workspace_bytes < L.bytes) return XO_EWORKSPACE;
   char *ws = static_cast<char *>(workspace);
   auto at = [&](size_t off) { return reinterpret_cast<double *>(ws + off); };
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  dim3 grid(L.nctas, (unsigned)B);
-  xo::launch(gp_aggregate_kernel, grid, kThreadsGp, 0, st, t, y, diag, N, S0, w0, Q, eps, L.T, at(L.off_pref), at(L.off_tot));
-  xo::launch(gp_cta_scan_kernel, (unsigned)B, kThreadsGp, 0, st, at(L.off_tot), L.nctas, S0, w0, Q, eps, at(L.off_state));
-  xo::launch(gp_loglike_kernel, grid, kThreadsGp, 0, st, t, y, diag, N, S0, w0, Q, eps, L.T, at(L.off_pref), at(L.off_state),
-                                                 at(L.off_ll), at(L.off_rec), nullptr);
-  xo::launch(gp_fold_kernel, (unsigned)((B + 3) / 4), 128, 0, st, at(L.off_ll), L.nctas, N, B, loglike);
+  XO_NVTX_SCOPE("xo_celerite_sho_solve");
+  int rc = gp_forward<1>(t, y, diag, N, S0, w0, Q, B, eps, loglike, at(L.off_rec), ws, L, st);
+  if (rc) return rc;
   dim3 gridb(L.nctas_b, (unsigned)B);
   xo::launch(gp_bwd_aggregate_kernel, gridb, kThreadsGp, 0, st, t, N, S0, w0, Q, eps, L.Tb, at(L.off_rec), at(L.off_bpref),
                                                        at(L.off_bcta));
@@ -1053,26 +1298,28 @@ int xo_celerite_sho_grad(const double *t, const double *y, const double *diag, i
   if (N < 0 || B < 0) return XO_EINVAL;
   if (B == 0) return 0;
   if (N == 0) return XO_EINVAL;
-  if (B > 65535) return XO_ERANGE;
+  if (B > 65535 || (double)B * (double)((N + kTileB - 1) / kTileB) > 2.0e9) return XO_ERANGE;
   if (!t || !y || !diag || !S0 || !w0 || !Q || !loglike || !ghyper || !workspace) return XO_EINVAL;
   GpLayout L = gp_layout(N, B, false, true);
   if (workspace_bytes < L.bytes) return XO_EWORKSPACE;
   char *ws = static_cast<char *>(workspace);
   auto at = [&](size_t off) { return reinterpret_cast<double *>(ws + off); };
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  dim3 grid(L.nctas, (unsigned)B);
-  xo::launch(gp_aggregate_kernel, grid, kThreadsGp, 0, st, t, y, diag, N, S0, w0, Q, eps, L.T, at(L.off_pref), at(L.off_tot));
-  xo::launch(gp_cta_scan_kernel, (unsigned)B, kThreadsGp, 0, st, at(L.off_tot), L.nctas, S0, w0, Q, eps, at(L.off_state));
-  xo::launch(gp_loglike_kernel, grid, kThreadsGp, 0, st, t, y, diag, N, S0, w0, Q, eps, L.T, at(L.off_pref), at(L.off_state),
-                                                 at(L.off_ll), nullptr, at(L.off_rec5));
-  xo::launch(gp_fold_kernel, (unsigned)((B + 3) / 4), 128, 0, st, at(L.off_ll), L.nctas, N, B, loglike);
-  dim3 gridb(L.nctas_b, (unsigned)B);
-  xo::launch(gp_grad_aggregate_kernel, gridb, kThreadsGp, 0, st, t, y, diag, N, S0, w0, Q, eps, L.Tb, at(L.off_rec5), at(L.off_gpref),
-                                                        at(L.off_gcta));
-  xo::launch(gp_grad_cta_scan_kernel, (unsigned)B, kThreadsGp, 0, st, at(L.off_gcta), L.nctas_b, at(L.off_gstate));
-  xo::launch(gp_grad_final_kernel, gridb, kThreadsGp, 0, st, t, y, diag, N, S0, w0, Q, eps, L.Tb, at(L.off_rec5), at(L.off_gpref),
-                                                    at(L.off_gstate), gy, gdiag, at(L.off_gpart));
-  xo::launch(gp_grad_fold_kernel, (unsigned)((B + 3) / 4), 128, 0, st, at(L.off_gpart), L.nctas_b, S0, w0, Q, eps, B, ghyper);
+  XO_NVTX_SCOPE("xo_celerite_sho_grad");
+  int rc = gp_forward<2>(t, y, diag, N, S0, w0, Q, B, eps, loglike, at(L.off_rs), ws, L, st);
+  if (rc) return rc;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GpBwdSmem));
+    if (e != cudaSuccess) return -(int)e;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  xo::launch(gp_backward_kernel, dim3((unsigned)((size_t)B * L.tiles_b)), dim3(kThreadsGp), sizeof(GpBwdSmem), st, t, y, diag, N, S0, w0, Q,
+             eps, L.tiles_b, L.groups_b, L.Tb, at(L.off_rs), reinterpret_cast<unsigned *>(ws + L.off_counters_b),
+             reinterpret_cast<unsigned *>(ws + L.off_flagA_b), reinterpret_cast<unsigned *>(ws + L.off_flagT_b), at(L.off_adjA),
+             at(L.off_adjT), at(L.off_gpart), reinterpret_cast<GpStatus *>(ws), gy, gdiag, ghyper);
   return xo::launch_status();
 }
 

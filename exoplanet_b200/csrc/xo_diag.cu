@@ -43,6 +43,20 @@ extern "C" {
 
 long long xo_diag_launch_count(void) { return xo::g_launch_count.load(std::memory_order_relaxed); }
 
+// status word at the head of a workspace (celerite entry points): lanes with a non-finite result, expired
+// inter-CTA waits.  Copies 16 bytes device -> host on `stream` and waits for them.
+int xo_read_status(const void *workspace, unsigned long long *bad_lanes, unsigned long long *wait_failures, void *stream) {
+  if (!workspace) return XO_EINVAL;
+  unsigned long long h[2] = {0, 0};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemcpyAsync(h, workspace, sizeof(h), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return -(int)e;
+  if (bad_lanes) *bad_lanes = h[0];
+  if (wait_failures) *wait_failures = h[1];
+  return 0;
+}
+
 int xo_diag_dfma_peak(int reps, double *dfma_per_s, double *best_ms, void *stream) {
   if (reps < 1 || !dfma_per_s) return XO_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

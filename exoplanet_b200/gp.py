@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["sho_loglike", "sho_solve", "sho_grad", "sho_loglike_autograd", "sho_params_from_sigma_rho"]
+__all__ = ["read_status", "sho_loglike", "sho_solve", "sho_grad", "sho_loglike_autograd", "sho_params_from_sigma_rho"]
 
 
 def _ptr(x):
@@ -22,6 +22,16 @@ def sho_params_from_sigma_rho(sigma, rho, Q):
     w0 = 2.0 * np.pi / rho
     S0 = sigma ** 2 / (w0 * Q)
     return S0, w0, Q
+
+
+def read_status(workspace):
+    """(bad_lanes, wait_failures) of the last celerite call that used ``workspace`` (xo_read_status); synchronises
+    the current stream."""
+    lib = _lib.require_cuda()
+    bad, wf = C.c_ulonglong(0), C.c_ulonglong(0)
+    with torch.cuda.device(workspace.device):
+        _lib.check(lib.xo_read_status(_ptr(workspace), C.byref(bad), C.byref(wf), _lib.stream_ptr()), "read_status")
+    return bad.value, wf.value
 
 
 def sho_loglike(t, y, diag, S0, w0, Q, eps=1e-5, workspace=None):

@@ -213,6 +213,14 @@ int xo_transit_model_logp_grad_resident(xo_transit_data *data, const double *par
  *   with CUDA events on `stream` -> thread-level DFMA per second (x2 = flop/s): the measured fp64 ceiling the
  *   fused kernels are quoted against (SURVEY.md 8d ceiling (B)).
  * xo_diag_launch_count: number of kernels this library has launched in this process so far. */
+/* Device status word.  The celerite entry points keep, in the first 16 bytes of their workspace, (a) the number of
+ * lanes whose result was not finite (NaN / inf input, non-positive variance) and (b) the number of inter-CTA waits of
+ * the one-pass scans that expired (never expected; the result must then be discarded).  They are written by the
+ * asynchronous launches; this call copies them to the host on `stream` and synchronises it.  This is SURVEY.md 8(b)'s
+ * "count of non-converged/NaN lanes written to a device status word" for entry points that cannot return it
+ * themselves because they do not synchronise. */
+int xo_read_status(const void *workspace, unsigned long long *bad_lanes, unsigned long long *wait_failures, void *stream);
+
 int xo_diag_dfma_peak(int reps, double *dfma_per_s, double *best_ms, void *stream);
 long long xo_diag_launch_count(void);
 

@@ -241,3 +241,50 @@ def test_transit_plus_gp_joint_gradient():
             ps[i].copy_(base)
         fd = (fp - fm) / (2 * h)
         assert abs(grads[i].item() - fd) <= 2e-4 * abs(fd) + 1e-3, (i, grads[i].item(), fd)
+
+
+def test_status_word_counts_non_finite_lanes_and_no_expired_waits():
+    """the device status word (xo_read_status): clean input -> (0, 0); a NaN in y or a non-positive variance is
+    counted, NaN in -> NaN out, and no inter-CTA wait of the one-pass scans ever expires"""
+    from exoplanet_b200 import _lib
+
+    pr = synthetic.gp_problem(300000)
+    lib = _lib.require_cuda()
+    t, y, diag = dev(pr["t"]), dev(pr["y"]), dev(pr["diag"])
+    ws = torch.empty(lib.xo_celerite_sho_grad_workspace(t.numel(), 2) // 8 + 1, dtype=torch.float64, device=DEV)
+    yb = torch.stack([y, y])
+    ll, gh, gy, gd = gp.sho_grad(t, yb, diag, pr["S0"], pr["w0"], pr["Q"], workspace=ws)
+    assert gp.read_status(ws) == (0, 0)
+    assert torch.isfinite(ll).all()
+    yb[1, 12345] = float("nan")
+    ll, gh, gy, gd = gp.sho_grad(t, yb, diag, pr["S0"], pr["w0"], pr["Q"], workspace=ws)
+    bad, waits = gp.read_status(ws)
+    assert waits == 0 and bad > 0
+    assert torch.isfinite(ll[0]) and torch.isnan(ll[1])
+    d2 = diag.clone()
+    d2[777] = -1.0  # D = a - p00 + diag < 0 at that cadence: log of a negative number
+    ws1 = torch.empty(lib.xo_celerite_sho_workspace(t.numel(), 1) // 8 + 1, dtype=torch.float64, device=DEV)
+    l1 = gp.sho_loglike(t, y, d2, pr["S0"], pr["w0"], pr["Q"], workspace=ws1)
+    bad, waits = gp.read_status(ws1)
+    assert waits == 0 and bad > 0 and not torch.isfinite(l1)
+
+
+def test_many_tiles_and_chains_exercise_the_inter_cta_tree():
+    """N = 3e6 (1465 forward tiles = 46 groups: two windows of group totals; 2930 reverse tiles) x 3 chains in all
+    damping regimes against the sequential oracle, gradient included; bit-reproducible"""
+    N = 3000000
+    pr = synthetic.gp_problem(N)
+    t, diag = dev(pr["t"]), dev(pr["diag"])
+    Qs = [3.0, 0.4, 1.0]
+    y = dev(np.stack([pr["y"] * (1 + 0.1 * k) for k in range(3)]))
+    S0 = dev([pr["S0"], 2 * pr["S0"], 0.5 * pr["S0"]])
+    w0 = dev([pr["w0"], 1.5 * pr["w0"], pr["w0"]])
+    ll, gh, gy, gd = gp.sho_grad(t, y, diag, S0, w0, dev(Qs))
+    ll2, gh2, gy2, gd2 = gp.sho_grad(t, y, diag, S0, w0, dev(Qs))
+    assert torch.equal(ll, ll2) and torch.equal(gh, gh2) and torch.equal(gy, gy2) and torch.equal(gd, gd2)
+    for k in range(3):
+        lo, gho, gyo, gdo = O.celerite_sho_grad_c(pr["t"], pr["y"] * (1 + 0.1 * k), pr["diag"], S0[k].item(), w0[k].item(), Qs[k])
+        assert abs(ll[k].item() - lo) < 1e-10 * abs(lo)
+        assert np.all(np.abs(gh[k].cpu().numpy() - gho) < 1e-8 * (np.abs(gho) + 1e-6 * np.abs(gho).max())), (k, gh[k], gho)
+        assert np.max(np.abs(gy[k].cpu().numpy() - gyo)) < 1e-9 * np.abs(gyo).max()
+        assert np.max(np.abs(gd[k].cpu().numpy() - gdo)) < 1e-9 * np.abs(gdo).max()

@@ -14,7 +14,7 @@ lscpu | grep -E "Model name|^CPU\(s\)|Thread|Core|Socket" >> $OUT/${TAG}_gpu.txt
 
 run_pytest() { # name, args...
   local name=$1; shift
-  timeout 2400 python -m pytest "$@" -m gpu -q -x > $OUT/${TAG}_pytest_$name.log 2>&1; echo "pytest($name) exit $?" | tee -a $OUT/${TAG}_pytest_$name.log
+  timeout 2400 python -m pytest "$@" -m gpu -q > $OUT/${TAG}_pytest_$name.log 2>&1; echo "pytest($name) exit $?" | tee -a $OUT/${TAG}_pytest_$name.log
 }
 bench_line() { # name, args...
   local name=$1; shift
@@ -38,8 +38,12 @@ check)
   ;;
 gp)
   run_pytest gp tests/test_gpu_gp.py tests/test_gpu_configs.py
-  bench_line ours --steps 20 --warmup 5 --no-cpu --no-kepler
-  capture gp "gp_" 0 --steps 1 --warmup 3 --no-cpu --no-kepler
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke exit $?" >> $OUT/${TAG}_smoke.log
+  bench_line ours --steps 20 --warmup 5 --no-cpu --no-kepler --extra gp
+  for V in $GP_VARIANTS; do XO_B200_LIB=exoplanet_b200/libxo_b200_$V.so bench_line $V --steps 20 --warmup 5 --no-cpu --no-kepler --extra gp; done
+  # B = 16 launches: the bench runs 13 launches at B = 1 first
+  capture gpfwd "gp_forward_kernel<0>" 14 --steps 1 --warmup 3 --no-cpu --no-kepler --extra gp
+  capture gpbwd "gp_backward_kernel" 14 --steps 1 --warmup 3 --no-cpu --no-kepler --extra gp
   ;;
 transit)
   run_pytest fused tests/test_gpu_fused.py tests/test_reference_glue.py tests/test_gpu_configs.py
