@@ -397,25 +397,33 @@ def _extra_gp(lib, dev, d, flush, out, O):
     out["configs[3] celerite SHO loglike + exact gradient (S0, w0, Q, y, diag), N=1e6, 16 chain(s)"].update(
         parity_hyper_rel_err=float(np.max(np.abs(gh - gho) / np.abs(gho))), parity_gy_rel_err=float(np.max(np.abs(gy_ - gyo)) / np.abs(gyo).max()),
         parity_gdiag_rel_err=float(np.max(np.abs(gd_ - gdo)) / np.abs(gdo).max()))
-    # joint model of configs[3]: transit mean + SHO GP noise at N=1e6, logL and its gradient w.r.t. the
-    # orbital parameters (light curve -> residual -> GP solve (logL, alpha) -> light-curve VJP with alpha)
-    from exoplanet_b200.light_curves import LimbDarkLightCurve
-    from exoplanet_b200.orbits import KeplerianOrbit
+    # joint model of configs[3]: transit mean + SHO GP noise at N=1e6: logL and its gradient w.r.t. every parameter through
+    # ONE C call (xo_transit_gp_logp_grad: prologue -> residual -> GP scan + adjoint -> light-curve VJP -> epilogue)
+    from exoplanet_b200 import fused
 
-    pj = [d([7.31]).requires_grad_(True), d([0.3]).requires_grad_(True), d([0.08]).requires_grad_(True)]
-    hj = [d(pr[k]).reshape(()).requires_grad_(True) for k in ("S0", "w0", "Q")]
-    lcm = LimbDarkLightCurve(0.3, 0.2, device=dev)
-    res = {}
+    for Cj in (1, 16):
+        pj = synthetic.transit_params(Cj, 1, seed=synthetic.SEED + 21, ecc_max=0.4)
+        par = fused.pack_params(d(pj["period"]), d(pj["t0"]), d(pj["ecc"]), d(pj["omega"]), d(pj["b"]), d(pj["ror"]))
+        one = torch.ones(Cj, dtype=torch.float64, device=dev)
+        star = fused.pack_star(one, one, d(pj["u1"]), d(pj["u2"]))
+        hyp = [d(np.full(Cj, pr[k])) for k in ("S0", "w0", "Q")]
+        jm = fused.TransitGPModel(pr["t"], pr["y"], pr["diag"], device=dev)
+        res = {}
 
-    def jstep():
-        orbit = KeplerianOrbit(period=pj[0], t0=d([1.3]), ecc=d([0.3]), omega=d([0.4]), b=pj[1])
-        mu = lcm.get_light_curve(orbit=orbit, r=pj[2], t=tg)[:, 0]
-        ll = gp.sho_loglike_autograd(tg, yg - mu, dg, *hj)
-        res["g"] = torch.autograd.grad(ll, pj + hj)
+        def jstep():
+            res["o"] = jm.logp_grad(par, star, d(pj["mean"]), *hyp)
 
-    ms = _time_steps(jstep, 5, flush)
-    out["configs[3] transit + SHO GP, N=1e6: logL + d/d(period, b, r, S0, w0, Q) (torch-level composition)"] = {
-        "value": 1.0 / (ms * 1e-3), "unit": "model+grad evals/s", "ms_per_step": ms}
+        ms = _time_steps(jstep, 10, flush)
+        # parity of chain 0: the oracle's light curve -> residual -> sequential celerite adjoint
+        el0 = O.elements_from_params(pj["period"][:1], pj["t0"][:1], pj["ecc"][:1], pj["omega"][:1], pj["b"][:1], pj["ror"][:1])
+        mu0 = O.transit_lc(pr["t"], el0, O.get_cl(pj["u1"][:1], pj["u2"][:1]), np.zeros(1), np.ones(1))[0, :, 0]
+        lo0, gh0, gy0, _ = O.celerite_sho_grad_c(pr["t"], pr["y"] - pj["mean"][0] - mu0, pr["diag"], pr["S0"], pr["w0"], pr["Q"])
+        o = res["o"]
+        out["configs[3] transit + SHO GP, N=1e6, %d chain(s): logL + d/d(all orbital, stellar, mean, S0, w0, Q) in one C call" % Cj] = {
+            "value": Cj / (ms * 1e-3), "unit": "model+grad evals/s", "ms_per_step": ms, "chains": Cj, "status_word": list(jm.status()),
+            "parity_loglike_rel_err": float(abs(o["loglike"][0].item() - lo0) / abs(lo0)),
+            "parity_hyper_rel_err": float(np.max(np.abs(o["ghyper"][0].cpu().numpy() - gh0) / np.abs(gh0))),
+            "parity_gmean_rel_err": float(abs(o["gmean"][0].item() + gy0.sum()) / np.abs(gy0).sum())}
 
 
 def _extra_1024(lib, dev, d, flush, out, O, t, y):

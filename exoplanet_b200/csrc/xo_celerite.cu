@@ -319,7 +319,8 @@ struct LogProd {
 template <int REC /* 0: none, 1: (v/D, K0, K1) per cadence for the smoother, 2: state entering every run of kRunB cadences */>
 __global__ void __launch_bounds__(kThreadsGp, XO_GP_MINBLOCKS)
     gp_forward_kernel(const double *__restrict__ t, const double *__restrict__ y, const double *__restrict__ diag, int64_t N,
-                      const double *__restrict__ S0, const double *__restrict__ w0, const double *__restrict__ Qf, double eps,
+                      const double *__restrict__ S0, const double *__restrict__ w0, const double *__restrict__ Qf,
+                      const double *__restrict__ jitter /* [B] added to diag, or null */, double eps,
                       int tiles, int groups, unsigned *__restrict__ counters /* [0] ticket, [1 + b] tiles done of chain b */,
                       unsigned *__restrict__ flagA, unsigned *__restrict__ flagT, double *__restrict__ aggA,
                       double *__restrict__ aggT, double *__restrict__ cta_ll, GpStatus *__restrict__ status,
@@ -333,6 +334,7 @@ __global__ void __launch_bounds__(kThreadsGp, XO_GP_MINBLOCKS)
   const int64_t bch = ticket / (unsigned)tiles;
   const int tile = (int)(ticket % (unsigned)tiles);
   const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
+  const double jit = jitter ? jitter[bch] : 0.0;
   const int64_t base = (int64_t)tile * kTile;
   const int64_t nvalid = min((int64_t)kTile, N - base);
   const double *yb = y + bch * N;
@@ -341,7 +343,7 @@ __global__ void __launch_bounds__(kThreadsGp, XO_GP_MINBLOCKS)
     const int r = idx / kRun, i = idx % kRun, at = r * kPitch + i;
     if (idx < nvalid) {
       sm.t[at] = __ldg(t + base + idx);
-      sm.d[at] = __ldg(diag + base + idx);
+      sm.d[at] = __ldg(diag + base + idx) + jit;
       sm.y[at] = __ldg(yb + base + idx);
     }
   }
@@ -405,18 +407,8 @@ __global__ void __launch_bounds__(kThreadsGp, XO_GP_MINBLOCKS)
   if (warp == 0) {
     const int g = tile / kGroup, in_group = tile % kGroup;
     bool ok = true;
-    // whole groups before this one, windows of 32 totals in group order
-    Agg carry = agg_identity();
-    for (int w0g = 0; w0g < g; w0g += 32) {
-      const int cnt = min(32, g - w0g);
-      Agg mine = agg_identity();
-      if (lane < cnt) {
-        ok &= wait_flag(flagT + (size_t)bch * groups + w0g + lane);
-        mine = agg_load_cg(aggT + ((size_t)bch * groups + w0g + lane) * kAggDoubles);
-      }
-      carry = agg_combine(carry, agg_warp_reduce(mine, cnt));
-    }
-    // earlier tiles of the own group
+    // earlier tiles of the own group first: the group total must not wait for anything outside the group, or the
+    // totals of successive groups would be published one after the other (a serial chain over the whole chain)
     Agg mine = agg_identity();
     if (lane < in_group) {
       ok &= wait_flag(flagA + (size_t)bch * tiles + (size_t)g * kGroup + lane);
@@ -430,6 +422,17 @@ __global__ void __launch_bounds__(kThreadsGp, XO_GP_MINBLOCKS)
         __threadfence();
         st_release_u32(flagT + (size_t)bch * groups + g, 1u);
       }
+    }
+    // whole groups before this one, windows of 32 totals in group order
+    Agg carry = agg_identity();
+    for (int w0g = 0; w0g < g; w0g += 32) {
+      const int cnt = min(32, g - w0g);
+      Agg tot = agg_identity();
+      if (lane < cnt) {
+        ok &= wait_flag(flagT + (size_t)bch * groups + w0g + lane);
+        tot = agg_load_cg(aggT + ((size_t)bch * groups + w0g + lane) * kAggDoubles);
+      }
+      carry = agg_combine(carry, agg_warp_reduce(tot, cnt));
     }
     const Agg excl = agg_combine(carry, local);
     if (!__all_sync(kFullGp, ok) && lane == 0) atomicAdd(&status->wait_failures, 1ull);
@@ -901,19 +904,20 @@ struct GpBwdSmem {
   Adj warp_incl[kWarpsGp];
   double entry[5];
   double t_halo;
-  double red[4][kWarpsGp];
+  double red[6][kWarpsGp];
   unsigned ticket;
   int is_last;
 };
 
 __global__ void __launch_bounds__(kThreadsGp, 3)
     gp_backward_kernel(const double *__restrict__ t, const double *__restrict__ y, const double *__restrict__ diag, int64_t N,
-                       const double *__restrict__ S0, const double *__restrict__ w0, const double *__restrict__ Qf, double eps,
+                       const double *__restrict__ S0, const double *__restrict__ w0, const double *__restrict__ Qf,
+                       const double *__restrict__ jitter, double eps,
                        int tiles, int groups, int64_t Tb, const double *__restrict__ rs /* [B][5][Tb] run-start states */,
                        unsigned *__restrict__ counters, unsigned *__restrict__ flagA, unsigned *__restrict__ flagT,
-                       double *__restrict__ adjA, double *__restrict__ adjT, double *__restrict__ gpart /* [B][tiles][4] */,
+                       double *__restrict__ adjA, double *__restrict__ adjT, double *__restrict__ gpart /* [B][tiles][6] */,
                        GpStatus *__restrict__ status, double *__restrict__ gy, double *__restrict__ gdiag,
-                       double *__restrict__ ghyper /* [B][3] */) {
+                       double *__restrict__ ghyper /* [B][3] */, double *__restrict__ gsum /* [B][2] or null */) {
   extern __shared__ __align__(16) unsigned char gp_smem_raw[];
   GpBwdSmem &sm = *reinterpret_cast<GpBwdSmem *>(gp_smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -924,6 +928,7 @@ __global__ void __launch_bounds__(kThreadsGp, 3)
   const int rtile = (int)(ticket % (unsigned)tiles);  // 0 = the LAST tile in time
   const int ttile = tiles - 1 - rtile;
   const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
+  const double jit = jitter ? jitter[bch] : 0.0;
   const int64_t base = (int64_t)ttile * kTileB;
   const int64_t nvalid = min((int64_t)kTileB, N - base);
   const double *yb = y + bch * N;
@@ -931,7 +936,7 @@ __global__ void __launch_bounds__(kThreadsGp, 3)
     const int r = idx / kRunB, i = idx % kRunB, at = r * kPitchB + i;
     if (idx < nvalid) {
       sm.t[at] = __ldg(t + base + idx);
-      sm.d[at] = __ldg(diag + base + idx);
+      sm.d[at] = __ldg(diag + base + idx) + jit;
       sm.y[at] = __ldg(yb + base + idx);
     }
   }
@@ -1023,16 +1028,7 @@ __global__ void __launch_bounds__(kThreadsGp, 3)
   if (warp == 0) {
     const int g = rtile / kGroup, in_group = rtile % kGroup;
     bool ok = true;
-    Adj carry = adj_identity();
-    for (int w0g = 0; w0g < g; w0g += 32) {
-      const int cnt = min(32, g - w0g);
-      Adj mine = adj_identity();
-      if (lane < cnt) {
-        ok &= wait_flag(flagT + (size_t)bch * groups + w0g + lane);
-        mine = adj_load_cg(adjT + ((size_t)bch * groups + w0g + lane) * kAdjDoubles);
-      }
-      carry = adj_after(carry, adj_warp_reduce(mine, cnt));
-    }
+    // own group first, group total published before anything outside the group is waited for (see the forward scan)
     Adj mine = adj_identity();
     if (lane < in_group) {
       ok &= wait_flag(flagA + (size_t)bch * tiles + (size_t)g * kGroup + lane);
@@ -1046,6 +1042,16 @@ __global__ void __launch_bounds__(kThreadsGp, 3)
         __threadfence();
         st_release_u32(flagT + (size_t)bch * groups + g, 1u);
       }
+    }
+    Adj carry = adj_identity();
+    for (int w0g = 0; w0g < g; w0g += 32) {
+      const int cnt = min(32, g - w0g);
+      Adj tot = adj_identity();
+      if (lane < cnt) {
+        ok &= wait_flag(flagT + (size_t)bch * groups + w0g + lane);
+        tot = adj_load_cg(adjT + ((size_t)bch * groups + w0g + lane) * kAdjDoubles);
+      }
+      carry = adj_after(carry, adj_warp_reduce(tot, cnt));
     }
     const Adj excl = adj_after(carry, local);
     if (!__all_sync(kFullGp, ok) && lane == 0) atomicAdd(&status->wait_failures, 1ull);
@@ -1061,6 +1067,7 @@ __global__ void __launch_bounds__(kThreadsGp, 3)
   __syncthreads();
   if (lane == 0 && warp > 0) pre = sm.warp_incl[warp - 1];
   double ga = 0.0, gc = 0.0, gh = 0.0, gw2 = 0.0;  // cotangents of a, c, h and w2 = c^2 +- h^2
+  double sy = 0.0, sd = 0.0;                        // sums of d/dy and d/d diag over the run
   if (len > 0) {
     double L[5] = {sm.entry[0], sm.entry[1], sm.entry[2], sm.entry[3], sm.entry[4]};
     if (tid > 0) adj_apply(pre, L);
@@ -1072,6 +1079,8 @@ __global__ void __launch_bounds__(kThreadsGp, 3)
       gp_step_adj<true, true>(f, L, acc);
       ys[i] = acc[0];  // d / d y_i     (y_i, diag_i are dead from here on: every step reads its own only)
       ds[i] = acc[1];  // d / d diag_i
+      sy += acc[0];
+      sd += acc[1];
       ga += acc[2];
       // Phi = [[Cf + c Sf, Sf], [-w2 Sf, Cf - c Sf]]
       const double d0011 = acc[3] - acc[6];
@@ -1084,9 +1093,9 @@ __global__ void __launch_bounds__(kThreadsGp, 3)
     }
     if (!isfinite(ga + gc + gh + gw2)) atomicAdd(&status->bad_lanes, 1ull);
   }
-  double vals[4] = {ga, gc, gh, gw2};
+  double vals[6] = {ga, gc, gh, gw2, sy, sd};
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < 6; ++j) {
     double x = vals[j];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFullGp, x, o);
@@ -1103,10 +1112,10 @@ __global__ void __launch_bounds__(kThreadsGp, 3)
       }
     }
   }
-  if (tid < 4) {
+  if (tid < 6) {
     double s4 = 0.0;
     for (int w = 0; w < kWarpsGp; ++w) s4 += sm.red[tid][w];
-    gpart[((size_t)bch * tiles + rtile) * 4 + tid] = s4;
+    gpart[((size_t)bch * tiles + rtile) * 6 + tid] = s4;
   }
   __syncthreads();
   if (tid == 0) {
@@ -1118,13 +1127,15 @@ __global__ void __launch_bounds__(kThreadsGp, 3)
     // fold the per-tile cotangents of (a, c, h, w2) in tile order and chain them to (S0, w0, Q):
     //   a = S0 w0 Q,  c = w0 / (2Q),  h = c f,  f = sqrt(max(+-(4Q^2 - 1), eps)),  w2 = c^2 +- h^2
     __threadfence();
-    double fa = 0.0, fc = 0.0, fh = 0.0, fw2 = 0.0;
+    double fa = 0.0, fc = 0.0, fh = 0.0, fw2 = 0.0, fy = 0.0, fd = 0.0;
     for (int i = lane; i < tiles; i += 32) {
-      const double *p = gpart + ((size_t)bch * tiles + i) * 4;
+      const double *p = gpart + ((size_t)bch * tiles + i) * 6;
       fa += __ldcg(p);
       fc += __ldcg(p + 1);
       fh += __ldcg(p + 2);
       fw2 += __ldcg(p + 3);
+      fy += __ldcg(p + 4);
+      fd += __ldcg(p + 5);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -1132,6 +1143,12 @@ __global__ void __launch_bounds__(kThreadsGp, 3)
       fc += __shfl_xor_sync(kFullGp, fc, o);
       fh += __shfl_xor_sync(kFullGp, fh, o);
       fw2 += __shfl_xor_sync(kFullGp, fw2, o);
+      fy += __shfl_xor_sync(kFullGp, fy, o);
+      fd += __shfl_xor_sync(kFullGp, fd, o);
+    }
+    if (lane == 0 && gsum) {
+      gsum[2 * bch] = fy;
+      gsum[2 * bch + 1] = fd;
     }
     if (lane == 0) {
       const double sgn = k.under ? 1.0 : -1.0;
@@ -1199,7 +1216,7 @@ inline GpLayout gp_layout(int64_t N, int64_t B, bool solve = false, bool grad = 
     L.off_rs = take((size_t)B * 5 * L.Tb);
     L.off_adjA = take((size_t)B * L.tiles_b * kAdjDoubles);
     L.off_adjT = take((size_t)B * L.groups_b * kAdjDoubles);
-    L.off_gpart = take((size_t)B * L.tiles_b * 4);
+    L.off_gpart = take((size_t)B * L.tiles_b * 6);
   }
   L.bytes = o;
   return L;
@@ -1208,7 +1225,7 @@ inline GpLayout gp_layout(int64_t N, int64_t B, bool solve = false, bool grad = 
 // the one-pass forward scan: clear status/counters/flags (one stream-ordered memset), one kernel
 template <int REC>
 int gp_forward(const double *t, const double *y, const double *diag, int64_t N, const double *S0, const double *w0, const double *Q,
-               int64_t B, double eps, double *loglike, double *rec, char *ws, const GpLayout &L, cudaStream_t st) {
+               const double *jitter, int64_t B, double eps, double *loglike, double *rec, char *ws, const GpLayout &L, cudaStream_t st) {
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1220,7 +1237,7 @@ int gp_forward(const double *t, const double *y, const double *diag, int64_t N, 
   cudaError_t e = cudaMemsetAsync(ws, 0, L.zero_bytes, st);
   if (e != cudaSuccess) return -(int)e;
   const size_t total = (size_t)B * L.tiles;
-  xo::launch(gp_forward_kernel<REC>, dim3((unsigned)total), dim3(kThreadsGp), sizeof(GpFwdSmem), st, t, y, diag, N, S0, w0, Q, eps, L.tiles,
+  xo::launch(gp_forward_kernel<REC>, dim3((unsigned)total), dim3(kThreadsGp), sizeof(GpFwdSmem), st, t, y, diag, N, S0, w0, Q, jitter, eps, L.tiles,
              L.groups, reinterpret_cast<unsigned *>(ws + L.off_counters), reinterpret_cast<unsigned *>(ws + L.off_flagA),
              reinterpret_cast<unsigned *>(ws + L.off_flagT), reinterpret_cast<double *>(ws + L.off_aggA),
              reinterpret_cast<double *>(ws + L.off_aggT), reinterpret_cast<double *>(ws + L.off_ll), reinterpret_cast<GpStatus *>(ws),
@@ -1229,6 +1246,44 @@ int gp_forward(const double *t, const double *y, const double *diag, int64_t N, 
 }
 
 }  // namespace
+
+namespace xo {
+
+// xo_celerite_sho_grad plus a per-chain jitter term added to diag and the per-chain sums gsum[B][2] =
+// (sum_n d/dy_n, sum_n d/d diag_n): what the joint transit + GP model needs (d/d mean = -gsum[0],
+// d/d jitter = gsum[1]).  Two kernels and one memset, all on `stream`.
+int celerite_sho_grad_impl(const double *t, const double *y, const double *diag, int64_t N, const double *S0, const double *w0,
+                           const double *Q, const double *jitter, int64_t B, double eps, double *loglike, double *ghyper,
+                           double *gy, double *gdiag, double *gsum, void *workspace, size_t workspace_bytes, void *stream) {
+  if (N < 0 || B < 0) return XO_EINVAL;
+  if (B == 0) return 0;
+  if (N == 0) return XO_EINVAL;
+  if (B > 65535 || (double)B * (double)((N + kTileB - 1) / kTileB) > 2.0e9) return XO_ERANGE;
+  if (!t || !y || !diag || !S0 || !w0 || !Q || !loglike || !ghyper || !workspace) return XO_EINVAL;
+  GpLayout L = gp_layout(N, B, false, true);
+  if (workspace_bytes < L.bytes) return XO_EWORKSPACE;
+  char *ws = static_cast<char *>(workspace);
+  auto at = [&](size_t off) { return reinterpret_cast<double *>(ws + off); };
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  XO_NVTX_SCOPE("xo_celerite_sho_grad");
+  int rc = gp_forward<2>(t, y, diag, N, S0, w0, Q, jitter, B, eps, loglike, at(L.off_rs), ws, L, st);
+  if (rc) return rc;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GpBwdSmem));
+    if (e != cudaSuccess) return -(int)e;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  xo::launch(gp_backward_kernel, dim3((unsigned)((size_t)B * L.tiles_b)), dim3(kThreadsGp), sizeof(GpBwdSmem), st, t, y, diag, N, S0, w0, Q,
+             jitter, eps, L.tiles_b, L.groups_b, L.Tb, at(L.off_rs), reinterpret_cast<unsigned *>(ws + L.off_counters_b),
+             reinterpret_cast<unsigned *>(ws + L.off_flagA_b), reinterpret_cast<unsigned *>(ws + L.off_flagT_b), at(L.off_adjA),
+             at(L.off_adjT), at(L.off_gpart), reinterpret_cast<GpStatus *>(ws), gy, gdiag, ghyper, gsum);
+  return xo::launch_status();
+}
+
+}  // namespace xo
 
 extern "C" {
 
@@ -1249,7 +1304,7 @@ int xo_celerite_sho_loglike(const double *t, const double *y, const double *diag
   GpLayout L = gp_layout(N, B);
   if (workspace_bytes < L.bytes) return XO_EWORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc = gp_forward<0>(t, y, diag, N, S0, w0, Q, B, eps, loglike, nullptr, static_cast<char *>(workspace), L, st);
+  int rc = gp_forward<0>(t, y, diag, N, S0, w0, Q, nullptr, B, eps, loglike, nullptr, static_cast<char *>(workspace), L, st);
   return rc ? rc : xo::launch_status();
 }
 
@@ -1274,7 +1329,7 @@ int xo_celerite_sho_solve(const double *t, const double *y, const double *diag, 
   auto at = [&](size_t off) { return reinterpret_cast<double *>(ws + off); };
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   XO_NVTX_SCOPE("xo_celerite_sho_solve");
-  int rc = gp_forward<1>(t, y, diag, N, S0, w0, Q, B, eps, loglike, at(L.off_rec), ws, L, st);
+  int rc = gp_forward<1>(t, y, diag, N, S0, w0, Q, nullptr, B, eps, loglike, at(L.off_rec), ws, L, st);
   if (rc) return rc;
   dim3 gridb(L.nctas_b, (unsigned)B);
   xo::launch(gp_bwd_aggregate_kernel, gridb, kThreadsGp, 0, st, t, N, S0, w0, Q, eps, L.Tb, at(L.off_rec), at(L.off_bpref),
@@ -1295,32 +1350,8 @@ size_t xo_celerite_sho_grad_workspace(int64_t N, int64_t B) {
 int xo_celerite_sho_grad(const double *t, const double *y, const double *diag, int64_t N, const double *S0,
                          const double *w0, const double *Q, int64_t B, double eps, double *loglike, double *ghyper,
                          double *gy, double *gdiag, void *workspace, size_t workspace_bytes, void *stream) {
-  if (N < 0 || B < 0) return XO_EINVAL;
-  if (B == 0) return 0;
-  if (N == 0) return XO_EINVAL;
-  if (B > 65535 || (double)B * (double)((N + kTileB - 1) / kTileB) > 2.0e9) return XO_ERANGE;
-  if (!t || !y || !diag || !S0 || !w0 || !Q || !loglike || !ghyper || !workspace) return XO_EINVAL;
-  GpLayout L = gp_layout(N, B, false, true);
-  if (workspace_bytes < L.bytes) return XO_EWORKSPACE;
-  char *ws = static_cast<char *>(workspace);
-  auto at = [&](size_t off) { return reinterpret_cast<double *>(ws + off); };
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  XO_NVTX_SCOPE("xo_celerite_sho_grad");
-  int rc = gp_forward<2>(t, y, diag, N, S0, w0, Q, B, eps, loglike, at(L.off_rs), ws, L, st);
-  if (rc) return rc;
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GpBwdSmem));
-    if (e != cudaSuccess) return -(int)e;
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
-  }
-  xo::launch(gp_backward_kernel, dim3((unsigned)((size_t)B * L.tiles_b)), dim3(kThreadsGp), sizeof(GpBwdSmem), st, t, y, diag, N, S0, w0, Q,
-             eps, L.tiles_b, L.groups_b, L.Tb, at(L.off_rs), reinterpret_cast<unsigned *>(ws + L.off_counters_b),
-             reinterpret_cast<unsigned *>(ws + L.off_flagA_b), reinterpret_cast<unsigned *>(ws + L.off_flagT_b), at(L.off_adjA),
-             at(L.off_adjT), at(L.off_gpart), reinterpret_cast<GpStatus *>(ws), gy, gdiag, ghyper);
-  return xo::launch_status();
+  return xo::celerite_sho_grad_impl(t, y, diag, N, S0, w0, Q, nullptr, B, eps, loglike, ghyper, gy, gdiag, nullptr, workspace,
+                                    workspace_bytes, stream);
 }
 
 }  // extern "C"

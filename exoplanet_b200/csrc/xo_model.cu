@@ -83,6 +83,13 @@ static int model_launches() {
 
 bool model_split_supported() { return model_launches() == 3; }
 
+int launch_model_epilogue(const double *par, const double *star, const double *partial, int slots, int64_t C, int P, double lognorm,
+                          double *logp, double *gpar, double *gstar, double *gmean, cudaStream_t st, bool pdl) {
+  cudaError_t le = xo::launch_pdl(model_epilogue_kernel, dim3((unsigned)((C + 3) / 4)), dim3(128), st, pdl, par, star, partial, slots, C, P,
+                                  lognorm, logp, gpar, gstar, gmean);
+  return le == cudaSuccess ? 0 : -(int)le;
+}
+
 // phases: 1 = prologue only (may run on another stream than the rest), 2 = logp kernel + epilogue
 // (the caller has ordered them after the prologue), 3 = everything on `stream`
 int model_logp_grad_phases(const double *t, const double *y, const double *ivar, int64_t N, const double *par,

@@ -142,6 +142,30 @@ __global__ void __launch_bounds__(256) transit_lc_fwd_kernel(const double *__res
   }
 }
 
+// residual of the light curve model: resid[C][N] = y - mean - sum_p lc  (the input of a noise model, e.g. the
+// celerite scan of the joint transit + GP likelihood); same evaluation as transit_lc_fwd_kernel
+__global__ void __launch_bounds__(256) transit_resid_kernel(const double *__restrict__ t, const double *__restrict__ y, int64_t N,
+                                                            const double *__restrict__ elem, const double *__restrict__ cl,
+                                                            const double *__restrict__ mean, int P,
+                                                            const double *__restrict__ dtk, const double *__restrict__ wk, int K,
+                                                            double *__restrict__ resid) {
+  __shared__ ChainSmem sm;
+  const int64_t c = blockIdx.y;
+  stage_chain(sm, elem, cl, mean, dtk, wk, c, P, K);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
+    const double tt = __ldg(t + i);
+    double model = sm.mean;
+    for (int p = 0; p < P; ++p) {
+      if (xo::in_window(sm.elem[p], sm.rperiod[p], tt)) {
+        for (int k = 0; k < K; ++k)
+          model = fma(sm.wk[k], xo::lc_point<false>(sm.elem[p], sm.cl, tt + sm.dtk[k], 0.0, nullptr, nullptr), model);
+      }
+    }
+    resid[c * N + i] = __ldg(y + i) - model;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // logp + grad (see header comment).  kMinBlocks trades registers for resident warps.
 // ---------------------------------------------------------------------------
@@ -248,7 +272,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
       const uint32_t idx = queue[warp][p][off + lane];
       const double tt = __ldg(t + idx);
       // issued now so that their latency hides behind the sample evaluation
-      const double yy = kVjp ? __ldg(y + ((int64_t)c * N + idx) * P + p) : __ldg(y + idx);
+      const double yy = kVjp ? (ma.vjp_shared ? -__ldg(y + (int64_t)c * N + idx) : __ldg(y + ((int64_t)c * N + idx) * P + p)) : __ldg(y + idx);
       const double iv = kVjp ? 0.0 : __ldg(ivar + idx);
       double ltot = 0.0;
       bool owner = true;  // the lowest in-window planet owns the per-cadence terms
@@ -411,6 +435,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
     lp += -0.5 * (moments[3] - 2.0 * m * moments[2] + m * m * moments[1]);
     gm += moments[2] - m * moments[1];
   }
+  if (kVjp && ma.vjp_gsum && slot == 0 && lane == 0) gm = -ma.vjp_gsum[2 * c];  // d / d mean of a likelihood of the residuals
   // the five per-warp scalars through the same row sums (lacc's rows are free by now)
   gl[0] = lp;
   gl[kThreads] = gm;
@@ -742,7 +767,7 @@ void launch_transit_logp_grad(const double *t, const double *y, const double *iv
 #define XO_LAUNCH(MB, VJP, MOM, MODEL)                                                                                    \
   xo::launch_pdl(transit_logp_grad_kernel<MB, VJP, MOM, MODEL>, grid, dim3(kThreads), st, pdl, t, y, ivar, N, elem, cl, mean, P, \
                  dtk, wk, K, sp.L, sp.slots, moments, partial, ma)
-  if (ivar == nullptr) {  // light-curve VJP mode: y = bar_lc[C][N][P]
+  if (ivar == nullptr) {  // light-curve VJP mode: y = bar_lc[C][N][P] (or -ybar[C][N] with model->vjp_shared)
     XO_LAUNCH(3, true, false, false);
     return;
   }
@@ -763,6 +788,16 @@ void launch_transit_logp_grad(const double *t, const double *y, const double *iv
     else XO_LAUNCH(3, false, false, false);
   }
 #undef XO_LAUNCH
+}
+
+void launch_transit_resid(const double *t, const double *y, int64_t N, const double *elem, const double *cl, const double *mean,
+                          int64_t C, int P, const double *dtk, const double *wk, int K, double *resid, cudaStream_t st) {
+  const int sms = sm_count();
+  int64_t per_chain = (N + 255) / 256;
+  int64_t want = ((int64_t)sms * 8 + C - 1) / C;
+  int gx = (int)(per_chain < want ? per_chain : want);
+  if (gx < 1) gx = 1;
+  xo::launch(transit_resid_kernel, dim3(gx, (unsigned)C), dim3(256), 0, st, t, y, N, elem, cl, mean, P, dtk, wk, K, resid);
 }
 
 void launch_chain_order(const double *elem, int64_t C, int P, int *order, cudaStream_t st) {

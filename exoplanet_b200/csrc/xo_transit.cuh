@@ -30,6 +30,10 @@ struct ModelArgs {
   unsigned *counter = nullptr;  // [C], zero on entry; left zero on exit
   const int *order = nullptr;   // [C] chain processed by blockIdx.y (heaviest first), or null = identity
   double *logp = nullptr, *gpar = nullptr, *gstar = nullptr, *gmean = nullptr;
+  // light-curve VJP mode only: the cotangent is -ybar[C][N], one value per (chain, cadence) shared by every planet
+  // (d/d lc of a likelihood of the residual y - mean - sum_p lc), and gmean is taken from -vjp_gsum[2 c]
+  int vjp_shared = 0;
+  const double *vjp_gsum = nullptr;
 };
 
 // enqueue transit_logp_grad_kernel; partial[C][slots][kNBase + P*XO_NGRAD]; model != nullptr
@@ -47,6 +51,18 @@ int model_logp_grad_phases(const double *t, const double *y, const double *ivar,
                            int K, double texp, int use_in_transit, double lognorm, const double *moments, double *logp,
                            double *gpar, double *gstar, double *gmean, void *workspace, size_t workspace_bytes, void *stream,
                            int phases);
+
+// resid[C][N] = y[n] - mean[c] - sum_p lc[c][n][p]   (what a noise model of the residuals consumes)
+void launch_transit_resid(const double *t, const double *y, int64_t N, const double *elem, const double *cl, const double *mean,
+                          int64_t C, int P, const double *dtk, const double *wk, int K, double *resid, cudaStream_t st);
+// fold of the per-warp partials + reverse pass of the prologue (xo_model.cu)
+int launch_model_epilogue(const double *par, const double *star, const double *partial, int slots, int64_t C, int P, double lognorm,
+                          double *logp, double *gpar, double *gstar, double *gmean, cudaStream_t st, bool pdl);
+
+// celerite gradient with per-chain jitter and per-chain sums of d/dy, d/d diag (xo_celerite.cu)
+int celerite_sho_grad_impl(const double *t, const double *y, const double *diag, int64_t N, const double *S0, const double *w0,
+                           const double *Q, const double *jitter, int64_t B, double eps, double *loglike, double *ghyper,
+                           double *gy, double *gdiag, double *gsum, void *workspace, size_t workspace_bytes, void *stream);
 
 // order[rank] = chain, heaviest expected in-transit work first
 void launch_chain_order(const double *elem, int64_t C, int P, int *order, cudaStream_t st);

@@ -16,13 +16,37 @@ from . import _lib
 from ._lib import MOMENTS_LEN, NEL, NGRAD, NGRAD_RV
 
 __all__ = ["exposure_stencil", "limb_dark_coeffs", "TransitData", "light_curve", "transit_logp_grad", "TransitLogp",
-           "orbit_eval", "rv_logp_grad", "RvLogp"]
+           "orbit_eval", "rv_logp_grad", "RvLogp", "TransitModel", "TransitGPModel", "pack_params", "pack_star"]
 
 LOG_2PI = 1.8378770664093454835606594728112
 
 
 def _ptr(x):
     return C.c_void_p(x.data_ptr()) if x is not None else None
+
+
+def _arg(x, shape, name, dev):
+    """Validated kernel argument: a float64 CUDA tensor on ``dev`` with exactly ``shape`` (the kernels index raw
+    pointers, so a wrong shape would read out of bounds or give silently wrong results); returned detached and
+    contiguous.  No implicit broadcasting: expand explicitly (``x.expand(C, 3)``) where a shared value is meant."""
+    if not isinstance(x, torch.Tensor):
+        raise TypeError("%s must be a torch tensor, got %s" % (name, type(x).__name__))
+    if x.dtype != torch.float64:
+        raise ValueError("%s must be float64, got %s" % (name, x.dtype))
+    want = torch.device(dev)
+    if not x.is_cuda or (want.index is not None and x.device.index != want.index):
+        raise ValueError("%s lives on %s, expected %s" % (name, x.device, want))
+    if tuple(x.shape) != tuple(shape):
+        raise ValueError("%s has shape %s, expected %s" % (name, tuple(x.shape), tuple(shape)))
+    return x.detach().contiguous()
+
+
+def _elem_dims(elem, name="elem"):
+    if not isinstance(elem, torch.Tensor) or elem.dim() != 3 or elem.shape[-1] != NEL:
+        raise ValueError("%s must have shape [C, P, %d], got %s" % (name, NEL, tuple(getattr(elem, "shape", ()))))
+    if elem.shape[1] > _lib.MAX_PLANETS:
+        raise ValueError("at most %d planets per chain" % _lib.MAX_PLANETS)
+    return elem.shape[0], elem.shape[1]
 
 
 def exposure_stencil(texp=None, oversample=7, order=0):
@@ -100,9 +124,10 @@ def _stencil_dev(stencil, dev):
 def light_curve(t, elem, cl, stencil=None):
     """lc[C, N, P] for element blocks elem[C, P, 16] and limb-darkening vectors cl[C, 3]."""
     lib = _lib.require_cuda()
-    elem = elem.detach().contiguous()
-    cl = cl.detach().contiguous()
-    Cc, P = elem.shape[0], elem.shape[1]
+    Cc, P = _elem_dims(elem)
+    t = _arg(t, (t.numel(),), "t", t.device)
+    elem = _arg(elem, (Cc, P, NEL), "elem", t.device)
+    cl = _arg(cl, (Cc, 3), "cl", t.device)
     dtk, wk = _stencil_dev(stencil or exposure_stencil(), t.device)
     lc = torch.empty((Cc, t.numel(), P), dtype=torch.float64, device=t.device)
     with torch.cuda.device(t.device):
@@ -115,11 +140,13 @@ def transit_logp_grad(data, elem, cl, mean, stencil=None, workspace=None, use_mo
     """One launch: (logp[C], gel[C,P,10], gcl[C,3], gmean[C]).  ``use_moments``: take the
     out-of-transit part of the sums from the data moments (the sweep then reads t only)."""
     lib = _lib.require_cuda()
-    elem = elem.detach().contiguous()
-    cl = cl.detach().contiguous()
-    mean = mean.detach().contiguous()
-    Cc, P = elem.shape[0], elem.shape[1]
+    Cc, P = _elem_dims(elem)
     dev = data.t.device
+    if data.y is None or data.ivar is None:
+        raise ValueError("TransitData needs y and yerr for a likelihood")
+    elem = _arg(elem, (Cc, P, NEL), "elem", dev)
+    cl = _arg(cl, (Cc, 3), "cl", dev)
+    mean = _arg(mean, (Cc,), "mean", dev)
     dtk, wk = _stencil_dev(stencil or exposure_stencil(), dev)
     need = lib.xo_transit_logp_grad_workspace(data.n, Cc, P)
     if workspace is None or workspace.numel() * workspace.element_size() < need:
@@ -167,8 +194,9 @@ class TransitLogp:
 def orbit_eval(t, elem, want=("X", "Y", "Z", "rv")):
     """Relative position / R_star and RV shape for every (chain, cadence, planet)."""
     lib = _lib.require_cuda()
-    elem = elem.detach().contiguous()
-    Cc, P = elem.shape[0], elem.shape[1]
+    Cc, P = _elem_dims(elem)
+    t = _arg(t, (t.numel(),), "t", t.device)
+    elem = _arg(elem, (Cc, P, NEL), "elem", t.device)
     out = {k: torch.empty((Cc, t.numel(), P), dtype=torch.float64, device=t.device) for k in want}
     with torch.cuda.device(t.device):
         _lib.check(lib.xo_orbit_eval(_ptr(t), t.numel(), _ptr(elem), Cc, P, _ptr(out.get("X")), _ptr(out.get("Y")),
@@ -179,10 +207,12 @@ def orbit_eval(t, elem, want=("X", "Y", "Z", "rv")):
 def rv_logp_grad(data, elem, gamma, workspace=None):
     """RV Gaussian log-likelihood + gradient: (logp[C], grv[C,P,7], ggamma[C])."""
     lib = _lib.require_cuda()
-    elem = elem.detach().contiguous()
-    gamma = gamma.detach().contiguous()
-    Cc, P = elem.shape[0], elem.shape[1]
+    Cc, P = _elem_dims(elem)
     dev = data.t.device
+    if data.y is None or data.ivar is None:
+        raise ValueError("TransitData needs y and yerr for a likelihood")
+    elem = _arg(elem, (Cc, P, NEL), "elem", dev)
+    gamma = _arg(gamma, (Cc,), "gamma", dev)
     need = lib.xo_rv_logp_grad_workspace(data.n, Cc, P)
     if workspace is None or workspace.numel() * workspace.element_size() < need:
         workspace = torch.empty(max(need, 8) // 8 + 1, dtype=torch.float64, device=dev)
@@ -237,6 +267,14 @@ def pack_star(r_star, m_star, u1, u2):
     return torch.stack(torch.broadcast_tensors(*cols), dim=-1).contiguous()
 
 
+def _par_dims(par):
+    if not isinstance(par, torch.Tensor) or par.dim() != 3 or par.shape[-1] != _lib.NPAR:
+        raise ValueError("par must have shape [C, P, %d] (pack_params), got %s" % (_lib.NPAR, tuple(getattr(par, "shape", ()))))
+    if par.shape[1] > _lib.MAX_PLANETS:
+        raise ValueError("at most %d planets per chain" % _lib.MAX_PLANETS)
+    return par.shape[0], par.shape[1]
+
+
 class TransitModel:
     """``logp, d logp/d params`` of a transit light-curve model with Gaussian noise, from
     sampler-side parameters, entirely on the device (the fused counterpart of the PyMC model
@@ -257,11 +295,11 @@ class TransitModel:
 
     def logp_grad(self, par, star, mean):
         lib = _lib.require_cuda()
-        par = par.detach().contiguous()
-        star = star.detach().contiguous()
-        mean = mean.detach().contiguous()
-        Cc, P = par.shape[0], par.shape[1]
         d = self.data
+        Cc, P = _par_dims(par)
+        par = _arg(par, (Cc, P, _lib.NPAR), "par", d.device)
+        star = _arg(star, (Cc, _lib.NSTAR), "star", d.device)
+        mean = _arg(mean, (Cc,), "mean", d.device)
         need = lib.xo_transit_model_workspace(d.n, Cc, P)
         if self._ws is None or self._ws.numel() * 8 < need:
             self._ws = torch.empty(need // 8 + 1, dtype=torch.float64, device=d.device)
@@ -297,3 +335,57 @@ class _TransitModelLogp(torch.autograd.Function):
     def backward(ctx, g):
         gpar, gstar, gmean = ctx.saved_tensors
         return g[:, None, None] * gpar, g[:, None] * gstar, g * gmean, None
+
+
+class TransitGPModel:
+    """Transit mean model + celerite SHO GP noise model (BASELINE configs[3]): ``loglike[C]`` and its gradient w.r.t.
+    the orbital / stellar parameters, the mean flux, the GP hyper-parameters (S0, w0, Q) and an optional per-chain
+    jitter term added to ``diag``, in one stream-ordered C call (``xo_transit_gp_logp_grad``): no torch op, no host
+    round trip between the light curve, the residuals, the GP scans and the light curve's reverse pass.
+
+    ``t, y, diag``: [N] (diag = sigma^2, the argument of celerite2's ``gp.compute(t, diag=...)``)."""
+
+    def __init__(self, t, y, diag, texp=None, oversample=7, order=0, use_in_transit=True, device=None, eps=1e-5):
+        dev = torch.device("cuda" if device is None else device)
+        as_dev = lambda x: torch.as_tensor(np.asarray(x, dtype=np.float64)).to(dev).contiguous()  # noqa: E731
+        self.t, self.y, self.diag = as_dev(t), as_dev(y), as_dev(diag)
+        self.n = self.t.numel()
+        if self.y.shape != (self.n,) or self.diag.shape != (self.n,):
+            raise ValueError("t, y, diag must have the same length")
+        self.device = dev
+        self.texp = 0.0 if texp is None else float(texp)
+        self.use_in_transit = bool(use_in_transit)
+        self.eps = float(eps)
+        self.dtk, self.wk = _stencil_dev(exposure_stencil(texp, oversample, order), dev)
+        self._ws = None
+
+    def logp_grad(self, par, star, mean, S0, w0, Q, jitter=None):
+        """-> dict(loglike[C], gpar[C,P,8], gstar[C,4], gmean[C], ghyper[C,3], gjitter[C] | None)"""
+        lib = _lib.require_cuda()
+        dev = self.device
+        Cc, P = _par_dims(par)
+        par = _arg(par, (Cc, P, _lib.NPAR), "par", dev)
+        star = _arg(star, (Cc, _lib.NSTAR), "star", dev)
+        mean = _arg(mean, (Cc,), "mean", dev)
+        S0, w0, Q = _arg(S0, (Cc,), "S0", dev), _arg(w0, (Cc,), "w0", dev), _arg(Q, (Cc,), "Q", dev)
+        jit = None if jitter is None else _arg(jitter, (Cc,), "jitter", dev)
+        need = lib.xo_transit_gp_workspace(self.n, Cc, P)
+        if self._ws is None or self._ws.numel() * 8 < need:
+            self._ws = torch.empty(need // 8 + 1, dtype=torch.float64, device=dev)
+        new = lambda *shape: torch.empty(shape, dtype=torch.float64, device=dev)  # noqa: E731
+        out = dict(loglike=new(Cc), gpar=new(Cc, P, _lib.NPAR), gstar=new(Cc, _lib.NSTAR), gmean=new(Cc), ghyper=new(Cc, 3),
+                   gjitter=None if jit is None else new(Cc))
+        with torch.cuda.device(dev):
+            _lib.check(lib.xo_transit_gp_logp_grad(_ptr(self.t), _ptr(self.y), _ptr(self.diag), self.n, _ptr(par), _ptr(star), _ptr(mean),
+                                                   _ptr(S0), _ptr(w0), _ptr(Q), _ptr(jit), Cc, P, _ptr(self.dtk), _ptr(self.wk),
+                                                   self.dtk.numel(), self.texp, int(self.use_in_transit), self.eps, _ptr(out["loglike"]),
+                                                   _ptr(out["gpar"]), _ptr(out["gstar"]), _ptr(out["gmean"]), _ptr(out["ghyper"]),
+                                                   _ptr(out["gjitter"]), _ptr(self._ws), self._ws.numel() * 8, _lib.stream_ptr()),
+                       "transit_gp_logp_grad")
+        return out
+
+    def status(self):
+        """(bad_lanes, wait_failures) of the last evaluation (xo_read_status); synchronises the current stream"""
+        from . import gp
+
+        return gp.read_status(self._ws)

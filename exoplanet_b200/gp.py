@@ -17,6 +17,33 @@ def _ptr(x):
     return C.c_void_p(x.data_ptr()) if x is not None else None
 
 
+def _gp_args(t, y, diag, S0, w0, Q):
+    """validated (t[N], y2[B, N], diag[N], S0[B], w0[B], Q[B]): float64 tensors on t's CUDA device; hyper-parameters
+    may be python scalars / 0-d tensors (one value for every chain) or [B] tensors"""
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.dim() == 1):
+        raise ValueError("t must be a 1-d float64 CUDA tensor")
+    dev, N = t.device, t.numel()
+    for name, x in (("y", y), ("diag", diag)):
+        if not (isinstance(x, torch.Tensor) and x.dtype == torch.float64 and x.device == dev):
+            raise ValueError("%s must be a float64 tensor on %s" % (name, dev))
+    if y.dim() not in (1, 2) or y.shape[-1] != N:
+        raise ValueError("y must have shape [N] or [B, N] with N = %d, got %s" % (N, tuple(y.shape)))
+    if tuple(diag.shape) != (N,):
+        raise ValueError("diag must have shape [%d], got %s" % (N, tuple(diag.shape)))
+    y2 = (y if y.dim() == 2 else y[None, :]).detach().contiguous()
+    B = y2.shape[0]
+
+    def vec(x, name):
+        x = torch.as_tensor(x, dtype=torch.float64, device=dev).detach()
+        if x.dim() == 0:
+            return x.expand(B).contiguous()
+        if tuple(x.shape) != (B,):
+            raise ValueError("%s must be a scalar or have shape [%d], got %s" % (name, B, tuple(x.shape)))
+        return x.contiguous()
+
+    return t.detach().contiguous(), y2, diag.detach().contiguous(), vec(S0, "S0"), vec(w0, "w0"), vec(Q, "Q")
+
+
 def sho_params_from_sigma_rho(sigma, rho, Q):
     """celerite2's alternative SHOTerm parameterisation: sigma^2 = S0 w0 Q, rho = 2 pi / w0."""
     w0 = 2.0 * np.pi / rho
@@ -39,18 +66,9 @@ def sho_loglike(t, y, diag, S0, w0, Q, eps=1e-5, workspace=None):
 
     t[N] sorted, diag[N] = sigma^2 (+ jitter), S0/w0/Q scalars or [B] tensors."""
     lib = _lib.require_cuda()
+    t, y2, diag, S0, w0, Q = _gp_args(t, y, diag, S0, w0, Q)
     dev = t.device
-    y2 = y if y.dim() == 2 else y[None, :]
-    y2 = y2.contiguous()
     B, N = y2.shape
-
-    def vec(x):
-        x = torch.as_tensor(x, dtype=torch.float64, device=dev).detach()
-        return x.expand(B).contiguous() if x.dim() == 0 else x.contiguous()
-
-    S0, w0, Q = vec(S0), vec(w0), vec(Q)
-    t = t.contiguous()
-    diag = diag.contiguous()
     need = lib.xo_celerite_sho_workspace(N, B)
     if workspace is None or workspace.numel() * 8 < need:
         workspace = torch.empty(need // 8 + 1, dtype=torch.float64, device=dev)
@@ -66,17 +84,9 @@ def sho_solve(t, y, diag, S0, w0, Q, eps=1e-5, workspace=None):
     """(loglike[B], alpha[B, N]) with alpha = K^-1 y: the forward scan followed by the disturbance
     smoother run as a reverse affine scan (xo_celerite_sho_solve).  d loglike / d y = -alpha."""
     lib = _lib.require_cuda()
+    t, y2, diag, S0, w0, Q = _gp_args(t, y, diag, S0, w0, Q)
     dev = t.device
-    y2 = (y if y.dim() == 2 else y[None, :]).contiguous()
     B, N = y2.shape
-
-    def vec(x):
-        x = torch.as_tensor(x, dtype=torch.float64, device=dev).detach()
-        return x.expand(B).contiguous() if x.dim() == 0 else x.contiguous()
-
-    S0, w0, Q = vec(S0), vec(w0), vec(Q)
-    t = t.contiguous()
-    diag = diag.contiguous()
     need = lib.xo_celerite_sho_solve_workspace(N, B)
     if workspace is None or workspace.numel() * 8 < need:
         workspace = torch.empty(need // 8 + 1, dtype=torch.float64, device=dev)
@@ -94,17 +104,9 @@ def sho_grad(t, y, diag, S0, w0, Q, eps=1e-5, want_y=True, want_diag=True, works
     exact reverse-mode gradient w.r.t. (S0, w0, Q), y and diag (xo_celerite_sho_grad): the forward
     scan, then the adjoint of the Kalman recursion as a reverse affine scan."""
     lib = _lib.require_cuda()
+    t, y2, diag, S0, w0, Q = _gp_args(t, y, diag, S0, w0, Q)
     dev = t.device
-    y2 = (y if y.dim() == 2 else y[None, :]).contiguous()
     B, N = y2.shape
-
-    def vec(x):
-        x = torch.as_tensor(x, dtype=torch.float64, device=dev).detach()
-        return x.expand(B).contiguous() if x.dim() == 0 else x.contiguous()
-
-    S0, w0, Q = vec(S0), vec(w0), vec(Q)
-    t = t.contiguous()
-    diag = diag.contiguous()
     need = lib.xo_celerite_sho_grad_workspace(N, B)
     if workspace is None or workspace.numel() * 8 < need:
         workspace = torch.empty(need // 8 + 1, dtype=torch.float64, device=dev)

@@ -178,6 +178,19 @@ int xo_celerite_sho_grad(const double *t, const double *y, const double *diag, i
                          const double *w0, const double *Q, int64_t B, double eps, double *loglike, double *ghyper,
                          double *gy, double *gdiag, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- joint transit + celerite SHO GP model (BASELINE configs[3]) ----
+ * loglike[c] = log N(y - mean[c] - sum_p lc(par[c], star[c]); 0, K_SHO(S0[c], w0[c], Q[c]) + diag + jitter[c])
+ * and its gradient w.r.t. every parameter, one stream-ordered call (6 kernels + 1 memset + 1 strided copy, no
+ * host round trip): par[C][P][XO_NPAR], star[C][XO_NSTAR], mean[C], S0/w0/Q[C], jitter[C] or NULL (added to
+ * diag[N]); outputs loglike[C], gpar, gstar, gmean[C], ghyper[C][3] = d/d(S0, w0, Q), gjitter[C] or NULL.
+ * The first 16 bytes of the workspace are the status word of xo_read_status. */
+size_t xo_transit_gp_workspace(int64_t N, int64_t C, int64_t P);
+int xo_transit_gp_logp_grad(const double *t, const double *y, const double *diag, int64_t N, const double *par,
+                            const double *star, const double *mean, const double *S0, const double *w0, const double *Q,
+                            const double *jitter, int64_t C, int64_t P, const double *dtk, const double *wk, int K, double texp,
+                            int use_in_transit, double eps, double *loglike, double *gpar, double *gstar, double *gmean,
+                            double *ghyper, double *gjitter, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- host-buffer entry points (the shape of exoplanet-core's driver) ---- */
 int xo_kepler_host(const double *M, const double *e, double *sinf, double *cosf, int64_t n, int device);
 int xo_qsv_host(const double *b, const double *r, double *s, double *dsdb, double *dsdr, int64_t n, int device);

@@ -288,3 +288,76 @@ def test_many_tiles_and_chains_exercise_the_inter_cta_tree():
         assert np.all(np.abs(gh[k].cpu().numpy() - gho) < 1e-8 * (np.abs(gho) + 1e-6 * np.abs(gho).max())), (k, gh[k], gho)
         assert np.max(np.abs(gy[k].cpu().numpy() - gyo)) < 1e-9 * np.abs(gyo).max()
         assert np.max(np.abs(gd[k].cpu().numpy() - gdo)) < 1e-9 * np.abs(gdo).max()
+
+
+def _joint_oracle(t, y, diag, p, hyper, jit, texp=None):
+    """log-likelihood of the joint transit + SHO GP model composed from the oracle's pieces"""
+    el = O.elements_from_params(p["period"], p["t0"], p["ecc"], p["omega"], p["b"], p["ror"], texp=texp)
+    lc = O.transit_lc(t, el, O.get_cl(p["u1"], p["u2"]), *O.stencil(texp)).sum(-1)
+    out = []
+    for c in range(lc.shape[0]):
+        r = y - p["mean"][c] - lc[c]
+        out.append(O.celerite_sho_grad_c(t, r, diag + jit[c], hyper[0][c], hyper[1][c], hyper[2][c]))
+    return out
+
+
+@pytest.mark.parametrize("P,texp", [(1, None), (2, 0.02)])
+def test_fused_transit_gp_entry_point(P, texp):
+    """xo_transit_gp_logp_grad: logL, d/d(S0, w0, Q), d/d mean, d/d jitter against the oracle composition; orbital and
+    limb-darkening gradients against central differences of the oracle composition and against the torch-level
+    composition (light curve -> residual -> sho_loglike_autograd) on the same engine"""
+    from exoplanet_b200 import fused
+
+    N, C = 40000, 3
+    rng = np.random.default_rng(17 + P)
+    t = np.arange(N) * 0.0204 + 0.0137
+    p = synthetic.transit_params(C, P, seed=23 + P, ecc_max=0.4)
+    el = O.elements_from_params(p["period"][:1], p["t0"][:1], p["ecc"][:1], p["omega"][:1], p["b"][:1], p["ror"][:1], texp=texp)
+    truth = O.transit_lc(t, el, O.get_cl(p["u1"][:1], p["u2"][:1]), *O.stencil(texp)).sum(-1)[0]
+    y = truth + 5e-4 * rng.normal(size=N) + 1e-3 * np.sin(2 * np.pi * t / 5.0)
+    diag = np.full(N, 5e-4 ** 2)
+    hyper = [np.array([2e-7, 3e-7, 1e-7]), np.array([1.2, 0.9, 2.0]), np.array([3.0, 0.4, 1.0])]
+    jit = np.array([1e-8, 0.0, 5e-8])
+    model = fused.TransitGPModel(t, y, diag, texp=texp, device=DEV)
+    par = fused.pack_params(dev(p["period"]), dev(p["t0"]), dev(p["ecc"]), dev(p["omega"]), dev(p["b"]), dev(p["ror"]))
+    one = torch.ones(C, dtype=torch.float64, device=DEV)
+    star = fused.pack_star(one, one, dev(p["u1"]), dev(p["u2"]))
+    out = model.logp_grad(par, star, dev(p["mean"]), dev(hyper[0]), dev(hyper[1]), dev(hyper[2]), jitter=dev(jit))
+    assert model.status() == (0, 0)
+    ref = _joint_oracle(t, y, diag, p, hyper, jit, texp)
+    for c in range(C):
+        lo, gho, gyo, gdo = ref[c]
+        assert abs(out["loglike"][c].item() - lo) < 1e-10 * abs(lo)
+        assert np.all(np.abs(out["ghyper"][c].cpu().numpy() - gho) < 1e-8 * (np.abs(gho) + 1e-6 * np.abs(gho).max()))
+        assert abs(out["gmean"][c].item() + gyo.sum()) < 1e-8 * np.abs(gyo).sum()
+        assert abs(out["gjitter"][c].item() - gdo.sum()) < 1e-8 * np.abs(gdo).sum()
+    # orbital parameters: central differences of the oracle composition (chain 0, planet 0)
+    for j, (key, h) in enumerate([("period", 1e-7), ("t0", 1e-6), ("ecc", 1e-6), ("omega", 1e-6), ("b", 1e-6), ("ror", 1e-7)]):
+        vals = []
+        for sgn in (+1, -1):
+            q = {k: np.array(v, copy=True) for k, v in p.items()}
+            q[key][0, 0] += sgn * h
+            vals.append(_joint_oracle(t, y, diag, {k: v[:1] for k, v in q.items()}, [x[:1] for x in hyper], jit[:1], texp)[0][0])
+        fd = (vals[0] - vals[1]) / (2 * h)
+        got = out["gpar"][0, 0, j].item()
+        assert abs(got - fd) < 2e-5 * max(abs(fd), 1.0) + 1e-4 * np.abs(out["gpar"][0, :, j].cpu().numpy()).max(), (key, got, fd)
+    # every gradient against the torch-level composition on the same engine
+    from exoplanet_b200 import elements
+
+    leaves = [dev(p[k]).requires_grad_(True) for k in ("period", "t0", "ecc", "omega", "b", "ror")]
+    u = [dev(p[k]).requires_grad_(True) for k in ("u1", "u2")]
+    el_t = elements.elements_from_params(*leaves, texp=texp)
+    from exoplanet_b200.light_curves.limb_dark import _FusedLightCurve
+
+    dtk, wk = fused._stencil_dev(fused.exposure_stencil(texp), torch.device(DEV))
+    tt = dev(t)
+    total = 0.0
+    for c in range(C):
+        mu = _FusedLightCurve.apply(el_t[c], fused.limb_dark_coeffs(u[0][c:c + 1], u[1][c:c + 1])[0], tt, dtk, wk).sum(-1)
+        total = total + gp.sho_loglike_autograd(tt, dev(y) - p["mean"][c] - mu, dev(diag) + jit[c], hyper[0][c], hyper[1][c], hyper[2][c])
+    g = torch.autograd.grad(total, leaves + u)
+    for j in range(6):
+        a, b = out["gpar"][..., j].cpu().numpy(), g[j].cpu().numpy()
+        assert np.max(np.abs(a - b)) < 1e-8 * np.abs(b).max() + 1e-12, (j, a, b)
+    assert np.max(np.abs(out["gstar"][:, 2].cpu().numpy() - g[6].cpu().numpy())) < 1e-8 * np.abs(g[6].cpu().numpy()).max()
+    assert np.max(np.abs(out["gstar"][:, 3].cpu().numpy() - g[7].cpu().numpy())) < 1e-8 * np.abs(g[7].cpu().numpy()).max()

@@ -42,7 +42,8 @@ gp)
   bench_line ours --steps 20 --warmup 5 --no-cpu --no-kepler --extra gp
   for V in $GP_VARIANTS; do XO_B200_LIB=exoplanet_b200/libxo_b200_$V.so bench_line $V --steps 20 --warmup 5 --no-cpu --no-kepler --extra gp; done
   # B = 16 launches: the bench runs 13 launches at B = 1 first
-  capture gpfwd "gp_forward_kernel<0>" 14 --steps 1 --warmup 3 --no-cpu --no-kepler --extra gp
+  # launch order of bench --extra gp: 13 x forward<0> (B=1), 13 x (forward<2>, backward) (B=1), then the same at B=16
+  capture gpfwd "gp_forward_kernel" 27 --steps 1 --warmup 3 --no-cpu --no-kepler --extra gp
   capture gpbwd "gp_backward_kernel" 14 --steps 1 --warmup 3 --no-cpu --no-kepler --extra gp
   ;;
 transit)
