@@ -250,7 +250,7 @@ int xo_transit_logp_grad_host(const double *t, const double *y, const double *iv
   XO_TRY(ds.err);
   const size_t ws = xo_transit_logp_grad_workspace(N, C, P);
   Arena ar(3 * pad(N) + pad(C * P * XO_NEL) + pad(3 * C) + pad(C) + 2 * pad(K) + pad(C) + pad(C * P * XO_NGRAD) +
-               pad(3 * C) + pad(C) + pad(XO_MOMENTS_LEN) + pad(ws, 1),
+               pad(3 * C) + pad(C) + pad(xo_transit_moments_len(N)) + pad(ws, 1),
            ds.st);
   XO_TRY(ar.err);
   double *dt = ar.take<double>(N), *dy = ar.take<double>(N), *dv = ar.take<double>(N);
@@ -258,7 +258,8 @@ int xo_transit_logp_grad_host(const double *t, const double *y, const double *iv
   double *dd = ar.take<double>(K), *dw = ar.take<double>(K);
   double *dlp = ar.take<double>(C), *dge = ar.take<double>(C * P * XO_NGRAD), *dgc = ar.take<double>(3 * C),
          *dgm = ar.take<double>(C);
-  double *dmom = ar.take<double>(XO_MOMENTS_LEN);
+  const size_t mom_len = xo_transit_moments_len(N);
+  double *dmom = ar.take<double>(mom_len);
   void *dws = ar.take<char>(ws);
   XO_TRY(h2d(dt, t, (size_t)N * 8, ds.st));
   XO_TRY(h2d(dy, y, (size_t)N * 8, ds.st));
@@ -268,8 +269,9 @@ int xo_transit_logp_grad_host(const double *t, const double *y, const double *iv
   XO_TRY(h2d(dm, mean, (size_t)C * 8, ds.st));
   XO_TRY(h2d(dd, dtk, (size_t)K * 8, ds.st));
   XO_TRY(h2d(dw, wk, (size_t)K * 8, ds.st));
-  // data moments (one pass, a few microseconds): the sweep then reads t only and skips quiet steps
+  // data moments + time index (two small data-only kernels): the sweep then reads no time stamp, y / ivar only in transit
   XO_RC(xo_transit_data_moments(dt, dy, dv, N, dmom, ds.st));
+  XO_RC(xo_transit_data_index(dt, N, dmom, mom_len, ds.st));
   XO_RC(xo_transit_logp_grad(dt, dy, dv, N, del, dcl, dm, C, P, dd, dw, K, lognorm, dmom, dlp, dge, dgc, dgm, dws, ws, ds.st));
   XO_TRY(d2h(logp, dlp, (size_t)C * 8, ds.st));
   XO_TRY(d2h(gel, dge, (size_t)C * P * XO_NGRAD * 8, ds.st));
@@ -291,11 +293,12 @@ int xo_transit_model_logp_grad_host(const double *t, const double *y, const doub
   const size_t ws = xo_transit_model_workspace(N, C, P);
   const size_t nin = (size_t)C * P * XO_NPAR + (size_t)C * XO_NSTAR + (size_t)C + 2 * (size_t)K;
   const size_t nout = (size_t)C + (size_t)C * P * XO_NPAR + (size_t)C * XO_NSTAR + (size_t)C;
-  Arena ar(3 * pad(N) + pad(nin) + pad(nout) + pad(XO_MOMENTS_LEN) + pad(ws, 1), ds.st);
+  Arena ar(3 * pad(N) + pad(nin) + pad(nout) + pad(xo_transit_moments_len(N)) + pad(ws, 1), ds.st);
   XO_TRY(ar.err);
   double *dt = ar.take<double>(N), *dy = ar.take<double>(N), *dv = ar.take<double>(N);
   double *din = ar.take<double>(nin), *dout = ar.take<double>(nout);
-  double *dmom = ar.take<double>(XO_MOMENTS_LEN);
+  const size_t mom_len = xo_transit_moments_len(N);
+  double *dmom = ar.take<double>(mom_len);
   void *dws = ar.take<char>(ws);
   double *dp = din, *dst = dp + C * P * XO_NPAR, *dm = dst + C * XO_NSTAR, *dd = dm + C, *dw = dd + K;
   double *dlp = dout, *dgp = dlp + C, *dgs = dgp + C * P * XO_NPAR, *dgm = dgs + C * XO_NSTAR;
@@ -332,8 +335,9 @@ int xo_transit_model_logp_grad_host(const double *t, const double *y, const doub
                                      dgs, dgm, dws, ws, ps, 1));
     XO_TRY(cudaEventRecord(ds.ev_join, ps));
   }
-  // data moments (one pass, a few microseconds): the sweep then reads t only and skips quiet steps
+  // data moments + time index (two small data-only kernels): the sweep then reads no time stamp, y / ivar only in transit
   XO_RC(xo_transit_data_moments(dt, dy, dv, N, dmom, ds.st));
+  XO_RC(xo_transit_data_index(dt, N, dmom, mom_len, ds.st));
   if (split) {
     XO_TRY(cudaStreamWaitEvent(ds.st, ds.ev_join, 0));
     ar.also = nullptr;  // joined: the main stream is ordered after everything the side stream did
@@ -377,7 +381,8 @@ int xo_transit_data_create(const double *t, const double *y, const double *ivar,
   d->N = N;
   cudaError_t e = cudaStreamCreateWithFlags(&d->st, cudaStreamNonBlocking);
   const size_t nb = (size_t)N * 8;
-  if (e == cudaSuccess) e = cudaMalloc((void **)&d->t, 3 * nb + XO_MOMENTS_LEN * 8);
+  const size_t mom_len = xo_transit_moments_len(N);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&d->t, 3 * nb + mom_len * 8);
   if (e == cudaSuccess) {
     d->y = d->t + N;
     d->ivar = d->y + N;
@@ -387,6 +392,7 @@ int xo_transit_data_create(const double *t, const double *y, const double *ivar,
   if (e == cudaSuccess) e = cudaMemcpyAsync(d->y, y, nb, cudaMemcpyHostToDevice, d->st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d->ivar, ivar, nb, cudaMemcpyHostToDevice, d->st);
   int rc = e == cudaSuccess ? xo_transit_data_moments(d->t, d->y, d->ivar, N, d->moments, d->st) : -(int)e;
+  if (rc == 0) rc = xo_transit_data_index(d->t, N, d->moments, mom_len, d->st);
   if (rc == 0) rc = xo::cuda_status(cudaStreamSynchronize(d->st));
   cudaSetDevice(prev);
   if (rc != 0) {

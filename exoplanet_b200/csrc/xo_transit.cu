@@ -167,6 +167,74 @@ __global__ void __launch_bounds__(256) transit_resid_kernel(const double *__rest
 }
 
 // ---------------------------------------------------------------------------
+// time -> cadence index (data only, built once per data set by xo_transit_data_index, stored behind the
+// moments in the same block): table[j] = number of cadences with t < t[0] + j w, j = 0..nb, w = (t[N-1] - t[0]) / nb.
+// With it the sweep of the logp kernel does not look at the time stamps at all: for every transit epoch that
+// touches a warp's cadence range it gets the index range of the in-transit window from two table look-ups and a
+// short binary search inside one bin (lanes work on 32 epochs at a time).
+// ---------------------------------------------------------------------------
+struct TimeIndex {
+  const uint32_t *table;
+  int nb;
+  double tmin, inv_w;
+};
+// first index i in [0, N] with t[i] >= x (kUpper: t[i] > x); t sorted ascending
+template <bool kUpper>
+__device__ __forceinline__ uint32_t index_bound(const double *__restrict__ t, uint32_t N, const TimeIndex &ix, double x) {
+  double u = (x - ix.tmin) * ix.inv_w;
+  u = u > 0.0 ? u : 0.0;  // also NaN -> 0
+  u = fmin(u, (double)(ix.nb - 1));
+  const int j = (int)u;
+  uint32_t lo = __ldg(ix.table + j), hi = __ldg(ix.table + j + 1);
+  auto before = [&](double v) { return kUpper ? (v <= x) : (v < x); };  // t[i] lies before the bound
+  // the bin was picked in floating point: make sure the answer is inside [lo, hi], else search the whole array
+  if (lo > 0u && !before(__ldg(t + lo - 1))) lo = 0u;
+  if (hi < N && before(__ldg(t + hi))) hi = N;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (before(__ldg(t + mid)))
+      lo = mid + 1u;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+__global__ void transit_index_kernel(const double *__restrict__ t, int64_t N, double *__restrict__ moments, int nb) {
+  uint32_t *table = reinterpret_cast<uint32_t *>(moments + XO_MOMENTS_LEN);
+  const double tmin = __ldg(t), tmax = __ldg(t + N - 1);
+  const double w = (tmax - tmin) / (double)nb;
+  const bool usable = moments[4] != 0.0 && w > 0.0 && isfinite(w);  // sorted (transit_moments_kernel ran before), non-degenerate
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0) {
+    moments[5] = usable ? (double)nb : 0.0;
+    moments[6] = usable ? 1.0 / w : 0.0;
+  }
+  if (j > nb || !usable) return;
+  uint32_t lo = 0u, hi = (uint32_t)N;
+  if (j < nb) {
+    const double x = fma((double)j, w, tmin);
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (__ldg(t + mid) < x)
+        lo = mid + 1u;
+      else
+        hi = mid;
+    }
+  } else {
+    lo = (uint32_t)N;
+  }
+  table[j] = lo;
+}
+
+inline int index_bins(int64_t N) {
+  int64_t nb = N / 2;
+  if (nb < 1) nb = 1;
+  if (nb > (1 << 22)) nb = 1 << 22;
+  return (int)nb;
+}
+
+// ---------------------------------------------------------------------------
 // logp + grad (see header comment).  kMinBlocks trades registers for resident warps.
 // ---------------------------------------------------------------------------
 // 32-cadence groups per sweep step: with the data moments the sweep is sparse (only steps that
@@ -175,6 +243,15 @@ __global__ void __launch_bounds__(256) transit_resid_kernel(const double *__rest
 // hide the latency.
 constexpr int sweep_unroll(bool moments) { return (moments || kWarps > 4) ? 1 : 4; }
 constexpr int kQueueMax = 32 * (4 + 1);  // 31 left over + kUnroll * 32 new entries
+
+// per-warp state of the indexed producer (shared memory: it must not cost registers across the drain)
+struct WarpIndexState {
+  uint32_t rlo[32], rcnt[32];  // index range of the epoch each lane looked up
+  long long kcur, klast;       // next / last epoch of the current planet
+  int p;                       // current planet
+  uint32_t rmask;              // lanes of the current batch whose range is still to be fed
+  uint32_t clo, ccnt;          // what is left of the range being fed
+};
 
 // kVjp = false: Gaussian log-likelihood (y, ivar, mean) and its gradient.
 // kVjp = true : reverse pass of the light curve alone: `y` is the cotangent bar_lc[C][N][P]
@@ -311,105 +388,206 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
     }
   };
 
-  // Sweep steps of 32*kUnroll cadences, then one final pass (last = true) that only flushes what
-  // is left in the queues -- written as ONE loop so the expensive drain body exists once in the
-  // binary.  The common step: for sorted t one interval test on two broadcast loads; otherwise
-  // kUnroll coalesced loads, 4 flops + 2 compares per cadence and planet, one vote.
+  // The sweep is a producer / consumer loop written as ONE loop, so that the expensive drain body exists once in
+  // the binary.  Each iteration the producer appends at most 32 candidate cadences per planet to the queues, the
+  // consumer drains every queue that holds >= 32 entries; a final pass (last = true) drains what is left.
+  // Two producers:
+  //  * indexed (data moments + time index, sorted t): no time stamp is read.  Per planet the transit epochs that
+  //    can touch this warp's cadence range are enumerated 32 at a time (one per lane: window bounds -> index range
+  //    by table look-up), and the ranges are fed to the queue in order.  State lives in shared memory (widx).
+  //  * stepping: steps of 32*kUnroll cadences; for sorted t with moments, steps are taken 32 at a time (lane l:
+  //    can step l contain an in-transit cadence of any planet?  one ballot gives the group's hit mask, only set
+  //    bits are visited); otherwise every cadence is read and the out-of-transit Gaussian terms accumulated.
   const bool sorted = kMoments && moments[4] != 0.0;  // t non-decreasing: steps can be skipped wholesale
+  const int nbins = kMoments ? (int)moments[5] : 0;   // > 0: the block carries the time index
   const double *tp = t + lane;
   constexpr uint32_t kStep = 32 * kUnroll;
-  // Steps are taken 32 at a time: lane l decides whether step l of the group can contain an
-  // in-transit cadence (sorted t: the step spans [tA, tB]; if that interval misses every planet's
-  // window in phase, with wrap, no cadence of it is in transit), one ballot gives the group's hit
-  // mask, and only the set bits are visited.  Unsorted t: every existing step is a hit.
   uint32_t gnext = start, gcur = start, hitmask = 0u;
+  __shared__ WarpIndexState widx[kMoments ? kWarps : 1];
+  if (kMoments && nbins > 0) {
+    if (lane == 0) {
+      WarpIndexState &W = widx[warp];
+      W.p = -1;
+      W.kcur = 1;
+      W.klast = 0;
+      W.rmask = 0u;
+      W.clo = 0u;
+      W.ccnt = 0u;
+    }
+    __syncwarp();
+  }
 #pragma unroll 1
   for (;;) {
     bool last = false;
-    uint32_t base = 0u;
-    if (hitmask == 0u) {
-      if (gnext >= end) {
-        last = true;
-      } else {
-        const uint32_t sb = gnext + lane * kStep;
-        bool hit = sb < end;
-        if (sorted && hit) {
-          const double tA = __ldg(t + sb), tB = __ldg(t + min(sb + kStep, end) - 1);
-          hit = false;
-          for (int p = 0; p < P; ++p) {
-            const double rpp = sm.rperiod[p];
-            const double uA = (tA - sm.elem[p][XO_EL_T0]) * rpp;
-            const double a = uA - rint(uA), b = a + (tB - tA) * rpp;  // phase interval, a in [-1/2, 1/2]
-            const double lo = sm.wlo[p] - 1e-9, hi = sm.whi[p] + 1e-9;
-            hit |= (b - a >= 1.0) | ((a <= hi) & (b >= lo)) | ((a <= hi + 1.0) & (b >= lo + 1.0)) | ((a <= hi - 1.0) & (b >= lo - 1.0));
+    int pb = 0, pe = P;  // planets whose queues the consumer looks at this iteration
+    if (kMoments && nbins > 0) {
+      // ---------------- indexed producer ----------------
+      WarpIndexState &W = widx[warp];
+      uint32_t ccnt = W.ccnt, clo = W.clo;
+      int p = W.p;
+      if (ccnt == 0u) {
+        uint32_t rmask = W.rmask;
+        while (rmask == 0u && !last) {  // a new batch of 32 epochs (of the next planet when this one is exhausted)
+          long long kcur = W.kcur, klast = W.klast;
+          bool dense = false;
+          while (kcur > klast) {
+            if (++p >= P) break;
+            const double per = sm.elem[p][XO_EL_PERIOD], t0p = sm.elem[p][XO_EL_T0];
+            const double tA = __ldg(t + start), tB = __ldg(t + (end > start ? end - 1 : start));
+            const double ka = floor((tA - t0p) * sm.rperiod[p] - 0.5) - 1.0, kb = ceil((tB - t0p) * sm.rperiod[p] + 0.5) + 1.0;
+            // more epochs than cadences (or a non-finite / non-positive period): every cadence is a candidate
+            dense = !(per > 0.0) || !(kb - ka <= (double)(end - start) + 4.0) || start >= end;
+            kcur = dense ? 0 : (long long)ka;
+            klast = dense ? 0 : (long long)kb;
+            if (start >= end) klast = kcur - 1;  // empty slot: nothing to enumerate
           }
+          if (p >= P) {
+            last = true;
+            break;
+          }
+          uint32_t lo = 0u, cnt = 0u;
+          const long long k = kcur + lane;
+          if (dense) {
+            if (lane == 0) {
+              lo = start;
+              cnt = end - start;
+            }
+          } else if (k <= klast) {
+            const TimeIndex ix{reinterpret_cast<const uint32_t *>(moments + XO_MOMENTS_LEN), nbins, __ldg(t), moments[6]};
+            const double per = sm.elem[p][XO_EL_PERIOD], t0p = sm.elem[p][XO_EL_T0], hp = 0.5 * per;
+            const double ts = sm.elem[p][XO_EL_TSTART], te = sm.elem[p][XO_EL_TEND];
+            const double tc = fma((double)k, per, t0p);
+            // the window clipped to the epoch's own period; the clip boundary B_k = t0 + (k + 1/2) P is computed by the
+            // same expression on both sides, so consecutive epochs neither overlap nor leave a gap
+            const uint32_t i0 = (ts > -hp) ? index_bound<false>(t, (uint32_t)N, ix, tc + ts)
+                                           : index_bound<false>(t, (uint32_t)N, ix, fma((double)k - 0.5, per, t0p));
+            const uint32_t i1 = (te < hp) ? index_bound<true>(t, (uint32_t)N, ix, tc + te)
+                                          : index_bound<false>(t, (uint32_t)N, ix, fma((double)k + 0.5, per, t0p));
+            lo = max(i0, start);
+            const uint32_t hi = min(i1, end);
+            cnt = hi > lo ? hi - lo : 0u;
+          }
+          __syncwarp();
+          W.rlo[lane] = lo;
+          W.rcnt[lane] = cnt;
+          rmask = __ballot_sync(kFull, cnt != 0u);
+          if (lane == 0) {
+            W.p = p;
+            W.kcur = kcur + 32;
+            W.klast = klast;
+          }
+          __syncwarp();
         }
-        hitmask = __ballot_sync(kFull, hit);
-        gcur = gnext;
-        gnext = (end - gnext > 32u * kStep) ? gnext + 32u * kStep : end;
-        if (hitmask == 0u) continue;
-      }
-    }
-    double tt[kUnroll], yy[kUnroll], iv[kUnroll];
-    uint32_t valid = 0u;  // bit u: cadence base + 32 u + lane exists
-    if (!last) {
-      base = gcur + (uint32_t)(__ffs(hitmask) - 1) * kStep;
-      hitmask &= hitmask - 1u;
-      if (kUnroll == 1 && hitmask != 0u && (lane & 15) == 0) {  // the next hit step's two lines on their way to L1
-        const uint32_t bn = gcur + (uint32_t)(__ffs(hitmask) - 1) * kStep + lane;
-        if (bn < end) xo::prefetch_l1(t + bn);
-      }
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {  // kUnroll coalesced loads in flight together
-        const bool v = base + 32 * u + lane < end;
-        valid |= v ? (1u << u) : 0u;
-        tt[u] = v ? __ldg(tp + base + 32 * u) : 0.0;
-      }
-    }
-    if (!last) {
-      if (kBase) {
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-          const uint32_t i = base + 32 * u + lane;
-          yy[u] = (valid >> u) & 1u ? __ldg(y + i) : 0.0;
-          iv[u] = (valid >> u) & 1u ? __ldg(ivar + i) : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-          const double r0 = yy[u] - mean_c;
-          const double wr = iv[u] * r0;
-          lp = fma(-0.5 * wr, r0, lp);
-          gm += wr;
+        if (!last) {
+          const int src = __ffs(rmask) - 1;
+          rmask &= rmask - 1u;
+          clo = W.rlo[src];
+          ccnt = W.rcnt[src];
+          if (lane == 0) W.rmask = rmask;
         }
       }
-    }
-    for (int p = 0; p < P; ++p) {
-      int fill;
       if (!last) {
-        // window constants of planet p in registers for the whole step
-        const double t0p = sm.elem[p][XO_EL_T0], rpp = sm.rperiod[p], lo = sm.wlo[p], hi = sm.whi[p];
-        uint32_t inw = 0u;
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-          const double ph0 = (tt[u] - t0p) * rpp;
-          const double ph = ph0 - rint(ph0);
-          inw |= ((ph >= lo) & (ph <= hi)) ? (1u << u) : 0u;
-        }
-        inw &= valid;
-        if (!__any_sync(kFull, inw != 0u)) continue;  // nothing of this planet in this step
-        fill = __shfl_sync(kFull, cnt, p);
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-          const bool in = (inw >> u) & 1u;
-          const uint32_t mask = __ballot_sync(kFull, in);
-          if (in) queue[warp][p][fill + __popc(mask & lt_mask)] = base + 32 * u + lane;
-          fill += __popc(mask);
+        const uint32_t m = min(ccnt, 32u);
+        const int fill = __shfl_sync(kFull, cnt, p);
+        if (lane < m) queue[warp][p][fill + lane] = clo + lane;
+        if (lane == p) cnt = fill + (int)m;
+        if (lane == 0) {
+          W.clo = clo + m;
+          W.ccnt = ccnt - m;
         }
         __syncwarp();
-      } else {
-        fill = __shfl_sync(kFull, cnt, p);
+        pb = p;
+        pe = p + 1;
       }
-      const int thr = last ? 1 : 32;
+    } else {
+      // ---------------- stepping producer ----------------
+      uint32_t base = 0u;
+      bool have = true;
+      if (hitmask == 0u) {
+        if (gnext >= end) {
+          last = true;
+        } else {
+          const uint32_t sb = gnext + lane * kStep;
+          bool hit = sb < end;
+          if (sorted && hit) {
+            const double tA = __ldg(t + sb), tB = __ldg(t + min(sb + kStep, end) - 1);
+            hit = false;
+            for (int p = 0; p < P; ++p) {
+              const double rpp = sm.rperiod[p];
+              const double uA = (tA - sm.elem[p][XO_EL_T0]) * rpp;
+              const double a = uA - rint(uA), b = a + (tB - tA) * rpp;  // phase interval, a in [-1/2, 1/2]
+              const double lo = sm.wlo[p] - 1e-9, hi = sm.whi[p] + 1e-9;
+              hit |= (b - a >= 1.0) | ((a <= hi) & (b >= lo)) | ((a <= hi + 1.0) & (b >= lo + 1.0)) | ((a <= hi - 1.0) & (b >= lo - 1.0));
+            }
+          }
+          hitmask = __ballot_sync(kFull, hit);
+          gcur = gnext;
+          gnext = (end - gnext > 32u * kStep) ? gnext + 32u * kStep : end;
+          have = hitmask != 0u;
+        }
+      }
+      if (!last && have) {
+        double tt[kUnroll], yy[kUnroll], iv[kUnroll];
+        uint32_t valid = 0u;  // bit u: cadence base + 32 u + lane exists
+        base = gcur + (uint32_t)(__ffs(hitmask) - 1) * kStep;
+        hitmask &= hitmask - 1u;
+        if (kUnroll == 1 && hitmask != 0u && (lane & 15) == 0) {  // the next hit step's two lines on their way to L1
+          const uint32_t bn = gcur + (uint32_t)(__ffs(hitmask) - 1) * kStep + lane;
+          if (bn < end) xo::prefetch_l1(t + bn);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {  // kUnroll coalesced loads in flight together
+          const bool v = base + 32 * u + lane < end;
+          valid |= v ? (1u << u) : 0u;
+          tt[u] = v ? __ldg(tp + base + 32 * u) : 0.0;
+        }
+        if (kBase) {
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            const uint32_t i = base + 32 * u + lane;
+            yy[u] = (valid >> u) & 1u ? __ldg(y + i) : 0.0;
+            iv[u] = (valid >> u) & 1u ? __ldg(ivar + i) : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            const double r0 = yy[u] - mean_c;
+            const double wr = iv[u] * r0;
+            lp = fma(-0.5 * wr, r0, lp);
+            gm += wr;
+          }
+        }
+        for (int p = 0; p < P; ++p) {
+          // window constants of planet p in registers for the whole step
+          const double t0p = sm.elem[p][XO_EL_T0], rpp = sm.rperiod[p], lo = sm.wlo[p], hi = sm.whi[p];
+          uint32_t inw = 0u;
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            const double ph0 = (tt[u] - t0p) * rpp;
+            const double ph = ph0 - rint(ph0);
+            inw |= ((ph >= lo) & (ph <= hi)) ? (1u << u) : 0u;
+          }
+          inw &= valid;
+          if (!__any_sync(kFull, inw != 0u)) continue;  // nothing of this planet in this step
+          int fill = __shfl_sync(kFull, cnt, p);
+#pragma unroll
+          for (int u = 0; u < kUnroll; ++u) {
+            const bool in = (inw >> u) & 1u;
+            const uint32_t mask = __ballot_sync(kFull, in);
+            if (in) queue[warp][p][fill + __popc(mask & lt_mask)] = base + 32 * u + lane;
+            fill += __popc(mask);
+          }
+          if (lane == p) cnt = fill;
+        }
+        __syncwarp();
+      } else if (!last) {
+        continue;  // a group of 32 steps without a hit
+      }
+    }
+    // ---------------- consumer: the one drain call site ----------------
+    const int thr = last ? 1 : 32;
+    for (int p = pb; p < pe; ++p) {
+      int fill = __shfl_sync(kFull, cnt, p);
+      if (fill < thr) continue;
       int off = 0;
 #pragma unroll 1
       while (fill - off >= thr) {
@@ -417,7 +595,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
         drain(p, off, m);
         off += m;
       }
-      if (off > 0) {  // move the < 32 left-over entries to the front
+      {  // move the < 32 left-over entries to the front
         const int rem = fill - off;
         const uint32_t v = lane < rem ? queue[warp][p][off + lane] : 0u;
         __syncwarp();
@@ -842,6 +1020,20 @@ int xo_transit_data_moments(const double *t, const double *y, const double *ivar
   const int64_t want = (N + 4 * kMomThreads - 1) / (4 * kMomThreads);
   const int ctas = (int)(want < 1 ? 1 : want > kMomMaxCtas ? kMomMaxCtas : want);
   xo::launch(transit_moments_kernel, ctas, kMomThreads, 0, st, t, y, ivar, N, moments);
+  return xo::launch_status();
+}
+
+size_t xo_transit_moments_len(int64_t N) {
+  if (N <= 0) return XO_MOMENTS_LEN;
+  return (size_t)XO_MOMENTS_LEN + ((size_t)index_bins(N) + 2) / 2;  // the table holds nb + 1 32-bit entries
+}
+
+int xo_transit_data_index(const double *t, int64_t N, double *moments, size_t moments_len, void *stream) {
+  if (N <= 0 || !t || !moments) return XO_EINVAL;
+  if (N >= ((int64_t)1 << 32)) return XO_ERANGE;
+  if (moments_len < xo_transit_moments_len(N)) return XO_EWORKSPACE;
+  const int nb = index_bins(N);
+  xo::launch(transit_index_kernel, (unsigned)((nb + 1 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream), t, N, moments, nb);
   return xo::launch_status();
 }
 

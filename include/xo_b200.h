@@ -122,6 +122,13 @@ size_t xo_transit_logp_grad_workspace(int64_t N, int64_t C, int64_t P);
 int xo_transit_data_moments(const double *t, const double *y, const double *ivar, int64_t N,
                             double *moments /*[XO_MOMENTS_LEN]*/,
                             void *stream);
+/* Optional time index behind the moments (sorted t only): allocate xo_transit_moments_len(N) doubles instead of
+ * XO_MOMENTS_LEN, call xo_transit_data_moments and then xo_transit_data_index on the same stream.  The block then
+ * also holds table[j] = #{n : t[n] < t[0] + j w} on a uniform grid of N/2 bins (moments[5] = number of bins,
+ * moments[6] = 1/w), and the logp kernels find the cadences of every transit window by table look-up instead of
+ * testing time stamps (same result, same evaluated set).  A block without the index (moments[5] = 0) keeps working. */
+size_t xo_transit_moments_len(int64_t N); /* in doubles */
+int xo_transit_data_index(const double *t, int64_t N, double *moments, size_t moments_len, void *stream);
 int xo_transit_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *elem,
                          const double *cl, const double *mean, int64_t C, int64_t P, const double *dtk, const double *wk,
                          int K, double lognorm, const double *moments, double *logp, double *gel, double *gcl,

@@ -97,13 +97,30 @@ def test_data_moments_kernel(N):
     ref = [iv.sum(), (iv * dy).sum(), (iv * dy * dy).sum()]
     for k in range(3):
         assert abs(m[1 + k] - float(ref[k])) <= 1e-13 * float((iv * np.abs(dy) ** k).sum()), (k, m[1 + k], ref[k])
-    assert m[4] == 1.0 and np.all(m[5:8] == 0.0)
+    assert m[4] == 1.0 and m[7] == 0.0
+    # the time index behind the moments: table[j] = #{t < t[0] + j w}, only for sorted, non-degenerate time stamps
+    nb = int(m[5])
+    if N > 1:
+        assert nb == max(N // 2, 1) and len(m) >= 1024 + (nb + 2) // 2
+        w = (t[-1] - t[0]) / nb
+        assert abs(m[6] * w - 1.0) < 1e-12
+        table = d.moments().cpu().numpy()[1024:].view(np.uint32)[: nb + 1]
+        grid = np.array([np.float64(j) * w + t[0] for j in range(nb)]) if nb < 2000 else t[0] + np.arange(nb) * w
+        ref_tab = np.searchsorted(t, grid, side="left")
+        # a grid point within rounding of a time stamp may fall on either side: compare where the bin edge is well separated
+        sep = np.min(np.abs(grid[:, None] - t[None, np.clip(ref_tab, 0, N - 1)]), axis=1) > 1e-9 if nb < 2000 else np.ones(nb, bool)
+        assert np.array_equal(table[:nb][sep], ref_tab[sep]) or nb >= 2000
+        assert table[nb] == N and np.all(np.diff(table.astype(np.int64)) >= 0)
+    else:
+        assert nb == 0
+    assert np.all(fused.TransitData(t, y, 1 / np.sqrt(ivar), device=DEV).moments(index=False).cpu().numpy()[5:8] == 0.0)
     d2 = fused.TransitData(t, y, 1 / np.sqrt(ivar), device=DEV)
-    assert np.array_equal(d2.moments().cpu().numpy()[:8], m[:8])
+    assert np.array_equal(d2.moments().cpu().numpy(), d.moments().cpu().numpy())
     if N > 2:
         tu = t.copy()
         tu[[N // 2, N // 2 + 1]] = tu[[N // 2 + 1, N // 2]]
-        assert fused.TransitData(tu, y, 1 / np.sqrt(ivar), device=DEV).moments().cpu().numpy()[4] == 0.0
+        mu = fused.TransitData(tu, y, 1 / np.sqrt(ivar), device=DEV).moments().cpu().numpy()
+        assert mu[4] == 0.0 and mu[5] == 0.0  # unsorted: no index, the stepping sweep reads every time stamp
 
 
 def test_moments_path_equals_full_sweep():
@@ -117,7 +134,17 @@ def test_moments_path_equals_full_sweep():
     b = fused.transit_logp_grad(data, dev(el_o), dev(cl), mean, use_moments=False)
     assert torch.allclose(a[0], b[0], rtol=1e-12, atol=0)
     assert torch.allclose(a[3], b[3], rtol=1e-9, atol=1e-9 * b[3].abs().max().item())
-    assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    # element / limb-darkening gradients: the same samples, enumerated in a different order (time index vs stepping)
+    assert torch.allclose(a[1], b[1], rtol=1e-11, atol=1e-11 * b[1].abs().max().item())
+    assert torch.allclose(a[2], b[2], rtol=1e-11, atol=1e-11 * b[2].abs().max().item())
+    # without the index the stepping sweep over the same moments visits the same samples in the same order as ... itself
+    d2 = fused.TransitData(t, y, np.full(N, 5e-4), device=DEV)
+    d2.moments(index=False)
+    c = fused.transit_logp_grad(d2, dev(el_o), dev(cl), mean, use_moments=True)
+    assert torch.allclose(a[0], c[0], rtol=1e-12, atol=0) and torch.allclose(a[1], c[1], rtol=1e-11, atol=1e-11 * b[1].abs().max().item())
+    # bit-reproducible run to run
+    a2 = fused.transit_logp_grad(data, dev(el_o), dev(cl), mean, use_moments=True)
+    assert all(torch.equal(x, z) for x, z in zip(a, a2))
     m = data.moments().cpu().numpy()
     assert m[4] == 1.0  # t is sorted -> step skipping is on; an unsorted copy must give the same answer
     perm = np.random.default_rng(3).permutation(N)
@@ -382,3 +409,67 @@ def test_host_entry_point_from_two_threads():
     for k in range(2):
         for a, b in zip(alone[k], results[k]):
             assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("case", ["gaps", "short_period", "flag_window", "wide_window", "three_planets", "tiny", "unsorted", "texp"])
+def test_indexed_sweep_edge_cases(case):
+    """the epoch-enumerating sweep (time index) against the oracle where its bookkeeping could go wrong: irregular
+    sampling with long gaps, periods shorter than the cadence (dense fallback), contact-solver flag windows
+    (-inf, +inf), windows clipped at half a period, overlapping planets, slots with a handful of cadences, unsorted
+    time stamps (stepping fallback) and exposure-widened windows"""
+    rng = np.random.default_rng(abs(hash(case)) % 1000)
+    N, C, P, texp = 30000, 6, 1, None
+    t = synthetic.cadence_times(N)
+    if case == "gaps":
+        keep = np.ones(N, bool)
+        for a in rng.integers(0, N - 3000, 6):
+            keep[a:a + int(rng.integers(200, 3000))] = False
+        t = t[keep] + 1e-4 * rng.uniform(size=keep.sum())
+        t.sort()
+        N = t.size
+    if case == "tiny":
+        N = 700
+        t = t[:N]
+    if case == "three_planets":
+        P = 3
+    if case == "texp":
+        texp, P = 0.0204, 2
+    p = synthetic.transit_params(C, P, seed=77 + len(case))
+    if case == "short_period":
+        p["period"][1, 0] = 0.31
+        p["b"][:2] = 0.2
+    if case == "three_planets":
+        p["period"][0, 1] = p["period"][0, 0]
+        p["t0"][0, 1] = p["t0"][0, 0] + 0.02
+        p["period"][1, 2] = 2.0 * p["period"][1, 0]
+        p["t0"][1, 2] = p["t0"][1, 0]
+    el = O.elements_from_params(p["period"], p["t0"], p["ecc"], p["omega"], p["b"], p["ror"], texp=texp)
+    if case == "short_period":  # a period shorter than the cadence: more epochs than cadences in a slot -> dense fallback
+        el[0, 0, 10] = 0.011
+        el[0, 0, 2] = 2 * np.pi / 0.011
+        el[0, 0, 11], el[0, 0, 12] = -0.003, 0.003
+    if case == "flag_window":
+        el[0, 0, 11], el[0, 0, 12] = -np.inf, np.inf  # what the contact solver's flag produces
+        el[1, 0, 11], el[1, 0, 12] = -np.inf, 0.3
+    if case == "wide_window":
+        el[0, 0, 11] = -0.7 * el[0, 0, 10]  # beyond half a period on both sides: clipped, every cadence evaluated once
+        el[0, 0, 12] = 0.8 * el[0, 0, 10]
+        el[1, 0, 11] = -0.5 * el[1, 0, 10]
+        el[2, 0, 12] = 0.5 * el[2, 0, 10]
+    cl = O.get_cl(p["u1"], p["u2"])
+    st = O.stencil(texp)
+    y = O.transit_lc(t, el[:1], cl[:1], *st).sum(-1)[0] + synthetic.noise(N)
+    if case == "unsorted":
+        perm = rng.permutation(N)
+        t, y = t[perm], y[perm]
+    sigma = 5e-4
+    data = fused.TransitData(t, y, np.full(N, sigma), device=DEV)
+    m = data.moments().cpu().numpy()
+    assert (m[5] > 0) == (case != "unsorted")
+    logp, gel, gcl, gmean = fused.transit_logp_grad(data, dev(el), dev(cl), dev(p["mean"]), fused.exposure_stencil(texp))
+    lo, geo, gco, gmo = O.transit_logp_grad(t, y, np.full(N, 1 / sigma ** 2), el, cl, p["mean"], *st, lognorm=data.lognorm)
+    assert np.max(np.abs(logp.cpu().numpy() - lo) / np.abs(lo)) < 1e-12
+    scale = np.abs(geo).max(axis=(0, 1), keepdims=True) + 1e-300
+    assert np.max(np.abs(gel.cpu().numpy() - geo) / scale) < 1e-10
+    assert np.max(np.abs(gcl.cpu().numpy() - gco) / (np.abs(gco).max() + 1e-300)) < 1e-10
+    assert np.max(np.abs(gmean.cpu().numpy() - gmo) / np.abs(gmo).max()) < 1e-10
