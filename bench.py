@@ -471,8 +471,9 @@ def _extra_hmc(lib, dev, d, flush, out, O, t, y):
     q_init = TransitPosterior.pack(p1["period"], p1["t0"], p1["ecc"], p1["omega"], p1["b"], p1["ror"], p1["u1"], p1["u2"], p1["mean"]).to(dev)
     sig = torch.tensor([1e-3, 0.02, 0.3, 0.3, 0.3, 0.3, 1.5, 1.5, 1e-3], dtype=torch.float64, device=dev)
     post = TransitPosterior(fused.TransitModel(fused.TransitData(t, y, np.full(N, SIGMA), device=dev)), 1, q_init, sig)
-    for use_graph in (True, False):
-        hmc = BatchedHMC(post, q_init, step_size=1e-6, n_leapfrog=8, seed=1, use_graph=use_graph)
+    for mode in ("one C call per transition (xo_hmc_transition)", "CUDA graph replay", "eager launches"):
+        use_graph = mode == "CUDA graph replay"
+        hmc = BatchedHMC(post, q_init, step_size=1e-6, n_leapfrog=8, seed=1, use_graph=use_graph, fused=None if mode.startswith("one C") else False)
         for _ in range(3):
             hmc.transition()
         torch.cuda.synchronize()
@@ -483,9 +484,9 @@ def _extra_hmc(lib, dev, d, flush, out, O, t, y):
         b.record()
         torch.cuda.synchronize()
         msj = a.elapsed_time(b) / 20
-        out["HMC driver, configs[1] x 128 chains, 8 leapfrog steps per transition, %s" % ("CUDA graph replay" if use_graph else "eager launches")] = {
-            "value": 128 * 8 / (msj * 1e-3), "unit": "leapfrog model+grad evals/s (incl. parameter transforms and their autograd)",
-            "ms_per_transition": msj, "chain_transitions_per_s": 128 / (msj * 1e-3)}
+        out["HMC driver, configs[1] x 128 chains, 8 leapfrog steps per transition, %s" % mode] = {
+            "value": 128 * 8 / (msj * 1e-3), "unit": "leapfrog model+grad evals/s (incl. parameter transforms, their chain rule and the priors)",
+            "ms_per_transition": msj, "chain_transitions_per_s": 128 / (msj * 1e-3), "accept_mean": float(hmc.accept_prob.mean().item())}
 
 
 def arm_ours(args):

@@ -73,8 +73,62 @@ class TransitPosterior:
         star = torch.stack([one, one, 2.0 * sq * q2, sq * (1.0 - 2.0 * q2)], dim=-1)
         return par, star, q[:, -1]
 
+    def _prior_vectors(self):
+        """prior_mu[D], prior_sigma[D] as contiguous device vectors, or None when the priors differ between chains"""
+        if self.mu.dim() > 1 or self.sigma.dim() > 1:
+            return None
+        D = self.D
+        return self.mu.expand(D).contiguous(), self.sigma.expand(D).contiguous()
+
+    def fused_args(self, C):
+        """what the C-ABI posterior / HMC entry points need besides the state; None when this posterior cannot take the
+        fused path (per-chain priors, cadence-parallel model)"""
+        import ctypes as C_
+
+        from . import _lib
+
+        m = self.model
+        pv = self._prior_vectors()
+        if pv is None or m.cadence_group is not None or not m.data.t.is_cuda:
+            return None
+        lib = _lib.require_cuda()
+        d = m.data
+        need = lib.xo_transit_posterior_workspace(d.n, C, self.P)
+        ws = getattr(self, "_fused_ws", None)
+        if ws is None or ws.numel() * 8 < need:
+            ws = self._fused_ws = torch.empty(need // 8 + 1, dtype=torch.float64, device=d.device)
+        ptr = lambda x: C_.c_void_p(x.data_ptr()) if x is not None else None  # noqa: E731
+        mom = d.moments() if m.use_moments else None
+        self._keep = (pv, mom)
+        return dict(lib=lib, head=(ptr(d.t), ptr(d.y), ptr(d.ivar), d.n, ptr(mom)), prior=(ptr(pv[0]), ptr(pv[1])),
+                    tail=(ptr(m.dtk), ptr(m.wk), m.dtk.numel(), m.texp, int(m.use_in_transit), d.lognorm), ws=ws)
+
     def __call__(self, q):
-        """(log posterior[C], gradient[C, D]); no host synchronisation."""
+        """(log posterior[C], gradient[C, D]); no host synchronisation.  One C call (xo_transit_posterior_logp_grad:
+        unpack kernel, fused model evaluation, chain-rule + prior kernel) when the priors are shared by the chains;
+        otherwise the same mathematics through torch autograd."""
+        import ctypes as C_
+
+        from . import _lib
+
+        q = q.detach().contiguous()
+        fa = self.fused_args(q.shape[0]) if q.is_cuda else None
+        if fa is not None:
+            C = q.shape[0]
+            if q.dtype != torch.float64 or tuple(q.shape) != (C, self.D):
+                raise ValueError("q must be float64 [C, %d]" % self.D)
+            lp = torch.empty(C, dtype=torch.float64, device=q.device)
+            g = torch.empty_like(q)
+            ptr = lambda x: C_.c_void_p(x.data_ptr())  # noqa: E731
+            with torch.cuda.device(q.device):
+                _lib.check(fa["lib"].xo_transit_posterior_logp_grad(*fa["head"], ptr(q), C, self.P, *fa["prior"], *fa["tail"], ptr(lp), ptr(g),
+                                                                    ptr(fa["ws"]), fa["ws"].numel() * 8, _lib.stream_ptr()),
+                           "transit_posterior_logp_grad")
+            return lp, g
+        return self.autograd_call(q)
+
+    def autograd_call(self, q):
+        """the same posterior through torch autograd (reference implementation of the fused path; per-chain priors)"""
         q = q.detach().requires_grad_(True)
         with torch.enable_grad():
             par, star, mean = self.unpack(q)
@@ -90,7 +144,7 @@ class BatchedHMC:
 
     state (device tensors): q, logp, grad, step size eps[C], inverse diagonal mass inv_mass[C, D]."""
 
-    def __init__(self, logp_grad, q0, step_size=1e-2, n_leapfrog=16, seed=0, target_accept=0.8, use_graph=True):
+    def __init__(self, logp_grad, q0, step_size=1e-2, n_leapfrog=16, seed=0, target_accept=0.8, use_graph=True, fused=None):
         self.f = logp_grad
         self.q = q0.detach().clone().contiguous()
         dev = self.q.device
@@ -108,6 +162,13 @@ class BatchedHMC:
         self.n_evals = 0
         self._graph = None
         self._use_graph = bool(use_graph) and dev.type == "cuda"
+        # a TransitPosterior with chain-independent priors advances through ONE C call per transition
+        # (xo_hmc_transition: momentum draw, L x (model evaluation + chain rule + kick + drift), accept / reject)
+        self._fused = None
+        self._seed = int(seed)
+        self._counter = 0
+        if fused is not False and dev.type == "cuda" and isinstance(logp_grad, TransitPosterior) and type(self) is BatchedHMC:
+            self._fused = logp_grad.fused_args(C)
         # dual averaging (Hoffman & Gelman 2014, algorithm 5), one instance per chain
         self._mu = torch.log(10.0 * self.eps)
         self._log_eps_bar = torch.zeros_like(self.eps)
@@ -137,7 +198,26 @@ class BatchedHMC:
         self.accept_prob.copy_(a)
         self.energy_error.copy_(-dh)
 
+    def _fused_transition(self):
+        import ctypes as C_
+
+        from . import _lib
+
+        fa = self._fused
+        ptr = lambda x: C_.c_void_p(x.data_ptr())  # noqa: E731
+        C = self.q.shape[0]
+        with torch.cuda.device(self.q.device):
+            _lib.check(fa["lib"].xo_hmc_transition(*fa["head"], C, self.f.P, *fa["prior"], *fa["tail"], ptr(self.q), ptr(self.logp),
+                                                   ptr(self.grad), ptr(self.eps), ptr(self.inv_mass), self.L, self._seed, self._counter,
+                                                   ptr(self.accept_prob), ptr(self.energy_error), ptr(fa["ws"]), fa["ws"].numel() * 8,
+                                                   _lib.stream_ptr()), "hmc_transition")
+        self._counter += 1
+        self.n_evals += self.L
+
     def transition(self):
+        if self._fused is not None:
+            self._fused_transition()
+            return
         if not self._use_graph:
             self._transition()
         else:
@@ -151,7 +231,10 @@ class BatchedHMC:
                 self._graph.register_generator_state(self.gen)
                 with torch.cuda.graph(self._graph):
                     self._transition()
+                # the side-stream run above was a real transition (state and generator advanced): it IS this call's
+                # transition; the captured graph is replayed from the next call on
                 self.n_evals += self.L
+                return
             self._graph.replay()
         self.n_evals += self.L
 
@@ -346,6 +429,7 @@ class BatchedNUTS(BatchedHMC):
         self.q.copy_(q_prop)
         self.logp.copy_(lp_prop)
         self.grad.copy_(g_prop)
+        self.n_evals = self.n_leapfrog - self.L  # transition() adds L (= 1): n_evals counts model evaluations
         self.accept_prob.copy_(acc_sum / torch.clamp(n_leaves, min=1.0))
         self.energy_error.copy_(dh_max)  # largest energy error met along the trajectory
         self.depth.copy_(depth)

@@ -198,6 +198,29 @@ int xo_transit_gp_logp_grad(const double *t, const double *y, const double *diag
                             int use_in_transit, double eps, double *loglike, double *gpar, double *gstar, double *gmean,
                             double *ghyper, double *gjitter, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- posterior in unconstrained coordinates + lock-step HMC ----
+ * The PyMC model of /root/reference/docs/tutorials/data-and-models.md:458-509 as one device-resident evaluation:
+ * q[C][D], D = 6 P + 3 = per planet (log period, t0, sqrt(e) cos w, sqrt(e) sin w, b, log r/R*), per chain
+ * (logit q1, logit q2, mean flux) with Kipping's (q1, q2) -> (u1, u2) (/root/reference/src/exoplanet/distributions.py:98-102),
+ * R* = M* = 1, independent Normal priors prior_mu[D], prior_sigma[D] on q.
+ *   logp[c] = Gaussian log-likelihood of the light curve + log prior (without the priors' normalisation constants)
+ *   grad[C][D] = d logp / d q      (change of variables, its chain rule and the priors are two small kernels
+ *                                   around xo_transit_model_logp_grad; moments may be NULL)
+ * xo_hmc_transition advances every chain by one HMC transition of n_leapfrog steps (momenta ~ N(0, 1/inv_mass),
+ * per-chain step sizes eps[C], Metropolis accept/reject) entirely on `stream`: 2 + 4 n_leapfrog kernel launches, no
+ * host synchronisation; q / logp / grad are the chains' current state (in and out).  Random numbers: Philox with
+ * (seed, chain, counter): pass a different `counter` for every transition. */
+size_t xo_transit_posterior_workspace(int64_t N, int64_t C, int64_t P);
+int xo_transit_posterior_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *moments,
+                                   const double *q, int64_t C, int64_t P, const double *prior_mu, const double *prior_sigma,
+                                   const double *dtk, const double *wk, int K, double texp, int use_in_transit, double lognorm,
+                                   double *logp, double *grad, void *workspace, size_t workspace_bytes, void *stream);
+int xo_hmc_transition(const double *t, const double *y, const double *ivar, int64_t N, const double *moments, int64_t C, int64_t P,
+                      const double *prior_mu, const double *prior_sigma, const double *dtk, const double *wk, int K, double texp,
+                      int use_in_transit, double lognorm, double *q, double *logp, double *grad, const double *eps,
+                      const double *inv_mass, int n_leapfrog, unsigned long long seed, unsigned long long counter,
+                      double *accept_prob, double *energy_error, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- host-buffer entry points (the shape of exoplanet-core's driver) ---- */
 int xo_kepler_host(const double *M, const double *e, double *sinf, double *cosf, int64_t n, int device);
 int xo_qsv_host(const double *b, const double *r, double *s, double *dsdb, double *dsdr, int64_t n, int device);

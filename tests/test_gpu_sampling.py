@@ -42,11 +42,31 @@ def test_posterior_gradient_matches_finite_differences():
         assert torch.allclose(g[:, j], fd, rtol=2e-5, atol=1e-6 * g[:, j].abs().max().item() + 1e-4), (j, g[:, j], fd)
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_batched_hmc_recovers_transit_parameters(use_graph):
-    """64 chains in lock-step; the whole transition replayed from a CUDA graph when use_graph"""
+def test_fused_posterior_equals_autograd_composition():
+    """xo_transit_posterior_logp_grad (unpack kernel, fused model, chain rule + prior kernel) against the same posterior
+    assembled from torch ops and torch.autograd around the fused model"""
+    post, q0, _, _ = _problem(C=16)
+    assert post.fused_args(16) is not None
+    lp, g = post(q0)
+    lp2, g2 = post.autograd_call(q0)
+    assert torch.allclose(lp, lp2, rtol=1e-13, atol=0)
+    assert torch.allclose(g, g2, rtol=1e-10, atol=1e-10 * g2.abs().max().item())
+    # per-chain priors cannot take the fused path and fall back to autograd
+    from exoplanet_b200.sampling import TransitPosterior
+
+    per_chain = TransitPosterior(post.model, 1, post.mu.expand(16, -1).clone(), post.sigma)
+    assert per_chain.fused_args(16) is None
+    lp3, g3 = per_chain(q0)
+    assert torch.allclose(lp3, lp2, rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("mode", ["fused", "graph", "eager"])
+def test_batched_hmc_recovers_transit_parameters(mode):
+    """64 chains in lock-step: one C call per transition (xo_hmc_transition), the torch transition replayed from a CUDA
+    graph, or eager torch launches"""
     post, q0, q_true, _ = _problem()
-    hmc = BatchedHMC(post, q0, step_size=2e-3, n_leapfrog=8, seed=11, use_graph=use_graph)
+    hmc = BatchedHMC(post, q0, step_size=2e-3, n_leapfrog=8, seed=11, use_graph=(mode == "graph"), fused=None if mode == "fused" else False)
+    assert (hmc._fused is not None) == (mode == "fused")
     hmc.warmup(160)
     out = hmc.sample(120)
     torch.cuda.synchronize()

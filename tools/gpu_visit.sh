@@ -47,8 +47,9 @@ gp)
   capture gpbwd "gp_backward_kernel" 14 --steps 1 --warmup 3 --no-cpu --no-kepler --extra gp
   ;;
 transit)
-  run_pytest fused tests/test_gpu_fused.py tests/test_reference_glue.py tests/test_gpu_configs.py
-  bench_line ours --steps 20 --warmup 5 --no-cpu --no-kepler --no-extra
+  run_pytest fused tests/test_gpu_fused.py tests/test_reference_glue.py tests/test_gpu_configs.py tests/test_gpu_sampling.py
+  bench_line ours --steps 20 --warmup 5 --no-cpu --no-kepler --extra c4,hmc
+  for V in $TRANSIT_VARIANTS; do XO_B200_LIB=exoplanet_b200/libxo_b200_$V.so bench_line $V --steps 20 --warmup 5 --no-cpu --no-kepler --no-extra; done
   capture transit transit_logp_grad_kernel 3 --steps 2 --warmup 3 --no-cpu --no-kepler --no-extra
   ;;
 final)
