@@ -5,13 +5,15 @@
 //
 // The celerite recurrence is a Riccati (linear-fractional) recursion, so it is run in
 // its equivalent 2-state Kalman-filter form, which has an associative combine
-// (Sarkka & Garcia-Fernandez 2021).  One kernel, one read of the data (gp_forward_kernel): a CTA stages a
-// tile of (t, diag, y) in shared memory, every thread walks a run of kRun consecutive cadences once from a
+// (Sarkka & Garcia-Fernandez 2021).  One kernel, one read of the data (gp_forward_kernel): a warp stages a tile of
+// 512 cadences of (t, diag, y) in shared memory, every lane walks a run of kRun consecutive cadences once from a
 // *known* start (P = 0), tracking the affine dependence of the filtered mean on the unknown start state and the
-// information (eta, J) the run's data carry about it -> one scan element per run, no 2x2 inverses; in-CTA
-// scan; a fixed two-level tree over the tile totals of the chain (flags + bounded waits, tiles handed out by
-// ticket) gives the state entering the tile; every thread then re-walks its run from shared memory with plain
-// Kalman steps, accumulating -1/2 (v^2/D + log D); the last tile of a chain folds the per-tile sums in order.
+// information (eta, J) the run's data carry about it -> one scan element per run, no 2x2 inverses; warp scan; a
+// fixed 32-ary tree over the tile totals of the chain (flags + bounded waits, tiles handed out by ticket) gives
+// the state entering the tile; every lane then re-walks its run from shared memory with plain Kalman steps,
+// accumulating -1/2 (v^2/D + log D); the last tile of a chain folds the per-tile sums in order.  A tile is ONE
+// warp on purpose: the tree look-back is a serial stretch of a few thousand dependent instructions, and with
+// one-warp CTAs nobody waits at a barrier for it -- the other 15 resident warps of the SM keep computing.
 // SHO in (a, c, h) form so celerite2's eps-regularised coefficients are matched exactly:
 //   underdamped k(tau) = a e^{-c tau}(cos h tau + (c/h) sin h tau), overdamped with cosh/sinh.
 #include <cuda_runtime.h>
@@ -163,48 +165,24 @@ __device__ __forceinline__ void agg_apply(const Agg &g, double &m0, double &m1, 
   P11 = c11;
 }
 
-__device__ __forceinline__ Agg agg_shfl_up(const Agg &a, int delta) {
-  Agg o;
-  const double *src = &a.A00;
-  double *dst = &o.A00;
-#pragma unroll
-  for (int k = 0; k < kAggDoubles; ++k) dst[k] = __shfl_up_sync(kFullGp, src[k], delta);
-  return o;
-}
-
-__device__ __forceinline__ void agg_store(double *p, const Agg &a) {
-  const double *src = &a.A00;
-#pragma unroll
-  for (int k = 0; k < kAggDoubles; ++k) p[k] = src[k];
-}
-// inclusive scan of one Agg per thread across the CTA (thread order); returns inclusive value
-__device__ Agg cta_inclusive_scan(Agg v, Agg *warp_tot /* smem [kWarps] */) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    Agg o = agg_shfl_up(v, d);
-    if (lane >= d) v = agg_combine(o, v);
-  }
-  if (lane == 31) warp_tot[warp] = v;
-  __syncthreads();
-  if (warp > 0) {
-    Agg pre = warp_tot[0];
-    for (int w = 1; w < warp; ++w) pre = agg_combine(pre, warp_tot[w]);
-    v = agg_combine(pre, v);
-  }
-  return v;
-}
-
 // ---------------------------------------------------------------------------
-// Inter-CTA plumbing of the one-pass scans: tickets, flags, bounded spin-waits.
+// Inter-tile plumbing of the one-pass scans: tickets, flags, bounded spin-waits, a fixed 32-ary tree.
 //
-// Tiles are handed out by an atomic ticket (chain-major: ticket = chain * tiles + tile), so a CTA only
-// ever waits on tiles with a LOWER ticket, i.e. on CTAs that are already running: forward progress does
-// not depend on the hardware's CTA scheduling order.  A flag is published with a release store after the
-// payload; readers poll it with acquire loads and read the payload through L2 (ld.cg).  Every wait is
-// bounded (kSpinLimit polls with back-off): on expiry the CTA records a failure in the status word and
-// carries on with an identity element, so the kernel always terminates (include/xo_b200.h: "every
-// iteration is bounded").
+// A tile is the work of ONE WARP (a CTA of 32 threads): while a warp waits for its predecessors no other warp
+// idles at a barrier, and the other resident warps of the SM (16 forward, 12 reverse) keep the pipes busy.
+// Tiles are handed out by an atomic ticket (chain-major: ticket = chain * tiles + tile), so a warp only ever waits
+// on tiles with a LOWER ticket, i.e. on warps that are already running: forward progress does not depend on the
+// hardware's CTA scheduling order.  A flag is published with a release store after the payload; readers poll it
+// with acquire loads and read the payload through L2 (ld.cg).  Every wait is bounded (kSpinLimit polls with
+// back-off): on expiry the warp records a failure in the status word and carries on, so the kernel always
+// terminates (include/xo_b200.h: "every iteration is bounded").
+//
+// The exclusive prefix of tile k over the earlier tiles of its chain comes from a FIXED tree, so the result is
+// bit-reproducible: level 0 = tile totals, level 1 = totals of groups of 32 tiles, level 2 = totals of groups of
+// 1024 tiles.  prefix(k) = [level-2 totals before k's level-2 group] o [level-1 totals before k's group, inside that
+// level-2 group] o [tile totals before k inside its group] -- at most 31 + 31 entries below level 2, reduced in one
+// pass by a warp holding two entries per lane.  The last tile of a group publishes the group total BEFORE it waits
+// for anything outside the group (else the group totals would be published one after the other, a serial chain).
 // ---------------------------------------------------------------------------
 constexpr unsigned kSpinLimit = 1u << 22;  // x >= 40 ns back-off: > 0.15 s, far beyond any real wait
 
@@ -233,66 +211,149 @@ struct GpStatus {
   unsigned long long bad_lanes, wait_failures;
 };
 
-// fixed-order combine of the elements held by lanes [0, count) of a warp (lane order = time order):
-// every lane returns e_0 o e_1 o ... o e_{count-1}; lanes >= count pass the identity.  The shuffle tree has
-// a fixed shape, so the result is bit-reproducible.
-__device__ __forceinline__ Agg agg_warp_reduce(Agg v, int count) {
+struct AggOps {
+  using E = Agg;
+  static constexpr int kDoubles = kAggDoubles;
+  static __device__ __forceinline__ E identity() { return agg_identity(); }
+  static __device__ __forceinline__ E combine(const E &earlier, const E &later) { return agg_combine(earlier, later); }
+  static __device__ __forceinline__ double *data(E &e) { return &e.A00; }
+  static __device__ __forceinline__ const double *data(const E &e) { return &e.A00; }
+};
+
+template <class O>
+__device__ __forceinline__ typename O::E elem_shfl_up(const typename O::E &a, int delta) {
+  typename O::E o;
+#pragma unroll
+  for (int k = 0; k < O::kDoubles; ++k) O::data(o)[k] = __shfl_up_sync(kFullGp, O::data(a)[k], delta);
+  return o;
+}
+template <class O>
+__device__ __forceinline__ typename O::E elem_shfl(const typename O::E &a, int src) {
+  typename O::E o;
+#pragma unroll
+  for (int k = 0; k < O::kDoubles; ++k) O::data(o)[k] = __shfl_sync(kFullGp, O::data(a)[k], src);
+  return o;
+}
+template <class O>
+__device__ __forceinline__ typename O::E elem_load_cg(const double *p) {
+  typename O::E a;
+#pragma unroll
+  for (int k = 0; k < O::kDoubles; ++k) O::data(a)[k] = __ldcg(p + k);
+  return a;
+}
+template <class O>
+__device__ __forceinline__ void elem_store(double *p, const typename O::E &a) {
+#pragma unroll
+  for (int k = 0; k < O::kDoubles; ++k) p[k] = O::data(a)[k];
+}
+
+// inclusive scan over the 32 lanes of a warp (lane order = scan order)
+template <class O>
+__device__ __forceinline__ typename O::E warp_inclusive_scan(typename O::E v) {
   const int lane = threadIdx.x & 31;
 #pragma unroll 1
   for (int d = 1; d < 32; d <<= 1) {
-    Agg o = agg_shfl_up(v, d);
-    if (lane >= d && lane < count) v = agg_combine(o, v);
+    typename O::E o = elem_shfl_up<O>(v, d);
+    if (lane >= d) v = O::combine(o, v);
   }
-  const int last = count > 0 ? count - 1 : 0;
-  Agg r;
-  const double *src = &v.A00;
-  double *dst = &r.A00;
-#pragma unroll
-  for (int k = 0; k < kAggDoubles; ++k) dst[k] = __shfl_sync(kFullGp, src[k], last);
-  return count > 0 ? r : agg_identity();
+  return v;
+}
+// fixed-order combination of the elements held by lanes [0, count): e_0 o e_1 o ... o e_{count-1} in every lane;
+// only ceil(log2 count) levels are executed
+template <class O>
+__device__ __forceinline__ typename O::E warp_reduce_n(typename O::E v, int count) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int d = 1; d < count; d <<= 1) {
+    typename O::E o = elem_shfl_up<O>(v, d);
+    if (lane >= d && lane < count) v = O::combine(o, v);
+  }
+  return elem_shfl<O>(v, count > 0 ? count - 1 : 0);
 }
 
-__device__ __forceinline__ Agg agg_load_cg(const double *p) {
-  Agg a;
-  double *dst = &a.A00;
-#pragma unroll
-  for (int k = 0; k < kAggDoubles; ++k) dst[k] = __ldcg(p + k);
-  return a;
+// one level of the tree for one chain
+struct TreeSeg {
+  const double *elems;
+  const unsigned *flags;
+  int start, count;  // entries [start, start + count) of the level, in order
+};
+// e = entry `pos` of the concatenation s0 | s1 | s2 (waits for its flag)
+template <class O>
+__device__ __forceinline__ typename O::E tree_fetch(const TreeSeg &s0, const TreeSeg &s1, const TreeSeg &s2, int pos, bool &ok) {
+  const TreeSeg &s = pos < s0.count ? s0 : (pos < s0.count + s1.count ? s1 : s2);
+  const int idx = s.start + (pos < s0.count ? pos : (pos < s0.count + s1.count ? pos - s0.count : pos - s0.count - s1.count));
+  ok &= wait_flag(s.flags + idx);
+  return elem_load_cg<O>(s.elems + (size_t)idx * O::kDoubles);
+}
+// the concatenation s0 | s1 | s2 combined in order, 64 entries per pass (two per lane)
+template <class O>
+__device__ __forceinline__ typename O::E tree_reduce(const TreeSeg &s0, const TreeSeg &s1, const TreeSeg &s2, bool &ok) {
+  const int lane = threadIdx.x & 31;
+  const int total = s0.count + s1.count + s2.count;
+  typename O::E carry = O::identity();
+#pragma unroll 1
+  for (int base = 0; base < total; base += 64) {
+    const int cnt = min(64, total - base);
+    typename O::E mine = O::identity();
+    if (cnt <= 32) {
+      if (lane < cnt) mine = tree_fetch<O>(s0, s1, s2, base + lane, ok);
+      mine = warp_reduce_n<O>(mine, cnt);
+    } else {
+      if (2 * lane < cnt) mine = tree_fetch<O>(s0, s1, s2, base + 2 * lane, ok);
+      if (2 * lane + 1 < cnt) mine = O::combine(mine, tree_fetch<O>(s0, s1, s2, base + 2 * lane + 1, ok));
+      mine = warp_reduce_n<O>(mine, (cnt + 1) / 2);
+    }
+    carry = base == 0 ? mine : O::combine(carry, mine);
+  }
+  return carry;
+}
+
+// scratch of one chain's tree (pointers already offset to the chain)
+struct TreeView {
+  double *e0, *e1, *e2;
+  unsigned *f0, *f1, *f2;
+  int n0;  // tiles of the chain
+};
+template <class O>
+__device__ __forceinline__ void tree_publish(double *elems, unsigned *flags, int idx, const typename O::E &v) {
+  if ((threadIdx.x & 31) == 0) {
+    elem_store<O>(elems + (size_t)idx * O::kDoubles, v);
+    __threadfence();
+    st_release_u32(flags + idx, 1u);
+  }
+}
+// exclusive prefix of tile `tile` over the earlier tiles of the chain; `own` = this tile's total (valid in every lane).
+// Publishes the tile total and, from the last tile of a group, the group totals.
+// (not inlined: called once per tile; its many live scan elements must not compete with the walks for registers)
+template <class O>
+__device__ __noinline__ typename O::E tree_exclusive(const TreeView &tv, int tile, const typename O::E &own, bool &ok) {
+  tree_publish<O>(tv.e0, tv.f0, tile, own);
+  const int d0 = tile & 31, g1 = tile >> 5, d1 = g1 & 31, g2 = g1 >> 5;
+  const TreeSeg none{nullptr, nullptr, 0, 0};
+  const TreeSeg tiles{tv.e0, tv.f0, g1 * 32, d0}, groups{tv.e1, tv.f1, g2 * 32, d1}, supers{tv.e2, tv.f2, 0, g2};
+  if (d0 != 31) return tree_reduce<O>(supers, groups, tiles, ok);
+  // last tile of a full group of 32
+  const typename O::E a = tree_reduce<O>(tiles, none, none, ok);
+  const typename O::E t1 = O::combine(a, own);
+  if ((g1 + 1) * 32 < tv.n0) tree_publish<O>(tv.e1, tv.f1, g1, t1);
+  if (d1 != 31) return O::combine(tree_reduce<O>(supers, groups, none, ok), a);
+  const typename O::E b = tree_reduce<O>(groups, none, none, ok);
+  if ((g2 + 1) * 1024 < tv.n0) tree_publish<O>(tv.e2, tv.f2, g2, O::combine(b, t1));
+  return O::combine(O::combine(tree_reduce<O>(supers, none, none, ok), b), a);
 }
 
 // ---- one-pass forward scan ---------------------------------------------------
-// One CTA owns a tile of kTile = kThreadsGp * kRun cadences of one chain:
+// One warp owns a tile of kTile = 32 * kRun cadences of one chain:
 //   1. the tile of (t, diag, y) is read from HBM ONCE, coalesced, into shared memory (row pitch kRun + 1
-//      doubles: thread r then walks row r conflict-free);
-//   2. every thread walks its run from a known start (P = 0) -> one scan element per run; in-CTA scan;
-//   3. the CTA total is published (A flag); warp 0 builds the exclusive prefix over all earlier tiles of the
-//      chain from a FIXED two-level tree -- totals of whole groups of 32 tiles (published by each group's
-//      last tile, T flag) combined in windows of 32, then the tiles of the own group -- and applies it to the
-//      stationary prior: the state entering the tile;
-//   4. every thread applies its in-CTA exclusive prefix and re-walks its run from shared memory with plain
+//      doubles: lane r then walks row r conflict-free);
+//   2. every lane walks its run from a known start (P = 0) -> one scan element per run; warp scan;
+//   3. the tile total is published and the exclusive prefix over the earlier tiles of the chain comes from the
+//      fixed tree above; applied to the stationary prior it gives the state entering the tile;
+//   4. every lane applies its in-warp exclusive prefix and re-walks its run from shared memory with plain
 //      Kalman steps, accumulating -1/2 (v^2/D + log D);
-//   5. per-CTA sums are folded in tile order by the last CTA of the chain to finish (bit-reproducible).
-constexpr int kTile = kThreadsGp * kRun;
+//   5. per-tile sums are folded in tile order by the last tile of the chain to finish (bit-reproducible).
+constexpr int kTile = 32 * kRun;
 constexpr int kPitch = kRun + 1;
-constexpr int kGroup = 32;  // tiles per group of the inter-CTA tree
-
-struct GpFwdLayout {  // device scratch of one forward pass (all offsets in bytes from the workspace base)
-  int tiles, groups;
-  size_t off_status, off_flags, off_aggA, off_aggT, off_ll, flag_bytes, bytes;
-};
-
-struct GpFwdSmem {
-  double t[kThreadsGp * kPitch];
-  double d[kThreadsGp * kPitch];
-  double y[kThreadsGp * kPitch];
-  Agg warp_tot[kWarpsGp];   // in-CTA scan: inclusive total of each warp
-  Agg warp_incl[kWarpsGp];  // inclusive prefix (within the CTA) at the last lane of each warp
-  double entry[5];          // state entering the tile: m0, m1, Z00, Z01, Z11
-  double t_halo;            // time stamp before the tile's first cadence
-  double red[kWarpsGp];
-  unsigned ticket;
-  int is_last;
-};
 
 // sum of log D over a run as the log of a product of mantissas plus an integer exponent sum: one DMUL and a
 // few integer instructions per cadence instead of a log; mantissas are in [0.5, 1), so a run of <= 64 cadences
@@ -313,46 +374,57 @@ struct LogProd {
   __device__ __forceinline__ double value() const { return log(mant) + slow + (double)expo * 0.69314718055994530941723212145818; }
 };
 
+// device scratch shared by the forward and the reverse tree: per level elements + flags, [B][n_level]
+struct TreeBuffers {
+  double *e0, *e1, *e2;
+  unsigned *f0, *f1, *f2;
+  int n0, n1, n2;
+  __device__ __forceinline__ TreeView chain(int64_t b, int doubles) const {
+    return TreeView{e0 + (size_t)b * n0 * doubles, e1 + (size_t)b * n1 * doubles, e2 + (size_t)b * n2 * doubles, f0 + (size_t)b * n0,
+                    f1 + (size_t)b * n1, f2 + (size_t)b * n2, n0};
+  }
+};
+
 #ifndef XO_GP_MINBLOCKS
-#define XO_GP_MINBLOCKS 4  // resident CTAs per SM the forward scan is compiled for (build-time knob)
+#define XO_GP_MINBLOCKS 16  // resident warp-tiles per SM the forward scan is compiled for (build-time knob): 128 registers
 #endif
 template <int REC /* 0: none, 1: (v/D, K0, K1) per cadence for the smoother, 2: state entering every run of kRunB cadences */>
-__global__ void __launch_bounds__(kThreadsGp, XO_GP_MINBLOCKS)
+__global__ void __launch_bounds__(32, XO_GP_MINBLOCKS)
     gp_forward_kernel(const double *__restrict__ t, const double *__restrict__ y, const double *__restrict__ diag, int64_t N,
                       const double *__restrict__ S0, const double *__restrict__ w0, const double *__restrict__ Qf,
                       const double *__restrict__ jitter /* [B] added to diag, or null */, double eps,
-                      int tiles, int groups, unsigned *__restrict__ counters /* [0] ticket, [1 + b] tiles done of chain b */,
-                      unsigned *__restrict__ flagA, unsigned *__restrict__ flagT, double *__restrict__ aggA,
-                      double *__restrict__ aggT, double *__restrict__ cta_ll, GpStatus *__restrict__ status,
-                      double *__restrict__ loglike, double *__restrict__ rec, int64_t Tb) {
-  extern __shared__ __align__(16) unsigned char gp_smem_raw[];
-  GpFwdSmem &sm = *reinterpret_cast<GpFwdSmem *>(gp_smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) sm.ticket = atomicAdd(&counters[0], 1u);
-  __syncthreads();
-  const unsigned ticket = sm.ticket;
+                      unsigned *__restrict__ counters /* [0] ticket, [1 + b] tiles done of chain b */, const TreeBuffers tb,
+                      double *__restrict__ cta_ll, GpStatus *__restrict__ status, double *__restrict__ loglike,
+                      double *__restrict__ rec, int64_t Tb) {
+  __shared__ double st[32 * kPitch], sd[32 * kPitch], sy[32 * kPitch];
+  const int lane = threadIdx.x;
+  unsigned ticket = 0u;
+  if (lane == 0) ticket = atomicAdd(&counters[0], 1u);
+  ticket = __shfl_sync(kFullGp, ticket, 0);
+  const int tiles = tb.n0;
   const int64_t bch = ticket / (unsigned)tiles;
   const int tile = (int)(ticket % (unsigned)tiles);
   const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
   const double jit = jitter ? jitter[bch] : 0.0;
   const int64_t base = (int64_t)tile * kTile;
-  const int64_t nvalid = min((int64_t)kTile, N - base);
+  const int nvalid = (int)min((int64_t)kTile, N - base);
   const double *yb = y + bch * N;
-  // 1. the tile, coalesced (consecutive threads read consecutive cadences), once
-  for (int idx = tid; idx < kTile; idx += kThreadsGp) {
-    const int r = idx / kRun, i = idx % kRun, at = r * kPitch + i;
+  // 1. the tile, coalesced (consecutive lanes read consecutive cadences), once
+#pragma unroll 4
+  for (int idx = lane; idx < kTile; idx += 32) {
+    const int at = (idx / kRun) * kPitch + idx % kRun;
     if (idx < nvalid) {
-      sm.t[at] = __ldg(t + base + idx);
-      sm.d[at] = __ldg(diag + base + idx) + jit;
-      sm.y[at] = __ldg(yb + base + idx);
+      st[at] = __ldg(t + base + idx);
+      sd[at] = __ldg(diag + base + idx) + jit;
+      sy[at] = __ldg(yb + base + idx);
     }
   }
-  if (tid == 0) sm.t_halo = __ldg(t + (base > 0 ? base - 1 : 0));
-  __syncthreads();
-  const int64_t s = base + (int64_t)tid * kRun;
+  const double t_halo = __ldg(t + (base > 0 ? base - 1 : 0));  // the time stamp before the tile's first cadence
+  __syncwarp();
+  const int64_t s = base + (int64_t)lane * kRun;
   const int len = (int)max((int64_t)0, min((int64_t)kRun, N - s));
-  const double *ts = sm.t + tid * kPitch, *ds = sm.d + tid * kPitch, *ys = sm.y + tid * kPitch;
-  const double t_before = tid > 0 ? sm.t[(tid - 1) * kPitch + kRun - 1] : sm.t_halo;
+  const double *ts = st + lane * kPitch, *ds = sd + lane * kPitch, *ys = sy + lane * kPitch;
+  const double t_before = lane > 0 ? st[(lane - 1) * kPitch + kRun - 1] : t_halo;
   // 2. the run's scan element, from a known start
   Agg v = agg_identity();
   if (len > 0) {
@@ -395,72 +467,20 @@ __global__ void __launch_bounds__(kThreadsGp, XO_GP_MINBLOCKS)
     }
     v = Agg{A00, A01, A10, A11, b0, b1, k.a - Z00, -Z01, k.a * k.w2 - Z11, e0, e1, J00, J01, J11};
   }
-  v = cta_inclusive_scan(v, sm.warp_tot);  // inclusive over the CTA's runs (contains a __syncthreads)
-  if (lane == 31) sm.warp_incl[warp] = v;
-  // 3. publish the tile total, build the state entering the tile
-  if (tid == kThreadsGp - 1) {
-    agg_store(aggA + ((size_t)bch * tiles + tile) * kAggDoubles, v);
-    __threadfence();
-    st_release_u32(flagA + (size_t)bch * tiles + tile, 1u);
-  }
-  __syncthreads();
-  if (warp == 0) {
-    const int g = tile / kGroup, in_group = tile % kGroup;
-    bool ok = true;
-    // earlier tiles of the own group first: the group total must not wait for anything outside the group, or the
-    // totals of successive groups would be published one after the other (a serial chain over the whole chain)
-    Agg mine = agg_identity();
-    if (lane < in_group) {
-      ok &= wait_flag(flagA + (size_t)bch * tiles + (size_t)g * kGroup + lane);
-      mine = agg_load_cg(aggA + ((size_t)bch * tiles + (size_t)g * kGroup + lane) * kAggDoubles);
-    }
-    const Agg local = agg_warp_reduce(mine, in_group);
-    if (in_group == kGroup - 1 && g + 1 < groups) {  // last tile of a full group that has successors: publish the group total
-      const Agg total = agg_combine(local, sm.warp_incl[kWarpsGp - 1]);
-      if (lane == 0) {
-        agg_store(aggT + ((size_t)bch * groups + g) * kAggDoubles, total);
-        __threadfence();
-        st_release_u32(flagT + (size_t)bch * groups + g, 1u);
-      }
-    }
-    // whole groups before this one, windows of 32 totals in group order
-    Agg carry = agg_identity();
-    for (int w0g = 0; w0g < g; w0g += 32) {
-      const int cnt = min(32, g - w0g);
-      Agg tot = agg_identity();
-      if (lane < cnt) {
-        ok &= wait_flag(flagT + (size_t)bch * groups + w0g + lane);
-        tot = agg_load_cg(aggT + ((size_t)bch * groups + w0g + lane) * kAggDoubles);
-      }
-      carry = agg_combine(carry, agg_warp_reduce(tot, cnt));
-    }
-    const Agg excl = agg_combine(carry, local);
-    if (!__all_sync(kFullGp, ok) && lane == 0) atomicAdd(&status->wait_failures, 1ull);
-    if (lane == 0) {
-      double m0 = 0.0, m1 = 0.0, P00 = k.a, P01 = 0.0, P11 = k.a * k.w2;
-      agg_apply(excl, m0, m1, P00, P01, P11);
-      sm.entry[0] = m0;
-      sm.entry[1] = m1;
-      sm.entry[2] = k.a - P00;  // Z = Sigma_inf - P
-      sm.entry[3] = -P01;
-      sm.entry[4] = k.a * k.w2 - P11;
-    }
-  }
-  // exclusive in-CTA prefix of this thread's run: the inclusive value of the previous thread
-  Agg pre = agg_shfl_up(v, 1);
-  __syncthreads();
-  if (lane == 0 && warp > 0) pre = sm.warp_incl[warp - 1];
+  v = warp_inclusive_scan<AggOps>(v);
+  // exclusive prefix of this lane's run inside the tile: the inclusive value of the previous lane
+  const Agg pre = elem_shfl_up<AggOps>(v, 1);
+  // 3. the state entering the tile
+  bool ok = true;
+  const Agg excl = tree_exclusive<AggOps>(tb.chain(bch, kAggDoubles), tile, elem_shfl<AggOps>(v, 31), ok);
+  if (!__all_sync(kFullGp, ok) && lane == 0) atomicAdd(&status->wait_failures, 1ull);
   // 4. re-walk with plain Kalman steps
   double acc = 0.0;
   if (len > 0) {
-    double m0 = sm.entry[0], m1 = sm.entry[1], Z00 = sm.entry[2], Z01 = sm.entry[3], Z11 = sm.entry[4];
-    if (tid > 0) {
-      double P00 = k.a - Z00, P01 = -Z01, P11 = k.a * k.w2 - Z11;
-      agg_apply(pre, m0, m1, P00, P01, P11);
-      Z00 = k.a - P00;
-      Z01 = -P01;
-      Z11 = k.a * k.w2 - P11;
-    }
+    double m0 = 0.0, m1 = 0.0, P00 = k.a, P01 = 0.0, P11 = k.a * k.w2;  // the stationary prior
+    agg_apply(excl, m0, m1, P00, P01, P11);               // ... entering the tile
+    if (lane > 0) agg_apply(pre, m0, m1, P00, P01, P11);  // ... entering this lane's run
+    double Z00 = k.a - P00, Z01 = -P01, Z11 = k.a * k.w2 - P11;  // Z = Sigma_inf - P
     double tprev = t_before;
     ShoCache cc;
     LogProd lp;
@@ -504,20 +524,16 @@ __global__ void __launch_bounds__(kThreadsGp, XO_GP_MINBLOCKS)
     acc += lp.value();
     if (!isfinite(acc)) atomicAdd(&status->bad_lanes, 1ull);
   }
-  // 5. CTA sum in a fixed order; the last CTA of the chain folds the per-tile sums in tile order
+  // 5. tile sum in a fixed order; the last tile of the chain folds the per-tile sums in tile order
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFullGp, acc, o);
-  if (lane == 0) sm.red[warp] = acc;
-  __syncthreads();
-  if (tid == 0) {
-    double s4 = 0.0;
-    for (int w = 0; w < kWarpsGp; ++w) s4 += sm.red[w];
-    cta_ll[(size_t)bch * tiles + tile] = s4;
+  int is_last = 0;
+  if (lane == 0) {
+    cta_ll[(size_t)bch * tiles + tile] = acc;
     __threadfence();
-    sm.is_last = atomicAdd(&counters[1 + bch], 1u) == (unsigned)(tiles - 1);
+    is_last = atomicAdd(&counters[1 + bch], 1u) == (unsigned)(tiles - 1);
   }
-  __syncthreads();
-  if (sm.is_last && warp == 0) {
+  if (__shfl_sync(kFullGp, is_last, 0)) {
     __threadfence();
     double tot = 0.0;
     for (int i = lane; i < tiles; i += 32) tot += __ldcg(cta_ll + (size_t)bch * tiles + i);
@@ -761,35 +777,6 @@ __device__ __forceinline__ void adj_apply(const Adj &a, double (&L)[5]) {
   L[3] = z[1];
   L[4] = z[2];
 }
-__device__ __forceinline__ Adj adj_shfl_up(const Adj &a, int d) {
-  Adj o;
-  const double *src = a.A;
-  double *dst = o.A;
-#pragma unroll
-  for (int k = 0; k < kAdjDoubles; ++k) dst[k] = __shfl_up_sync(kFullGp, src[k], d);
-  return o;
-}
-__device__ __forceinline__ void adj_store(double *p, const Adj &a) {
-  const double *src = a.A;
-#pragma unroll
-  for (int k = 0; k < kAdjDoubles; ++k) p[k] = src[k];
-}
-__device__ Adj adj_cta_inclusive_scan(Adj v, Adj *warp_tot) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll 1
-  for (int d = 1; d < 32; d <<= 1) {
-    Adj o = adj_shfl_up(v, d);
-    if (lane >= d) v = adj_after(o, v);
-  }
-  if (lane == 31) warp_tot[warp] = v;
-  __syncthreads();
-  if (warp > 0) {
-    Adj pre = warp_tot[0];
-    for (int w = 1; w < warp; ++w) pre = adj_after(pre, warp_tot[w]);
-    v = adj_after(pre, v);
-  }
-  return v;
-}
 
 // forward quantities of step i, recomputed from the recorded state entering it
 struct StepFwd {
@@ -858,95 +845,68 @@ __device__ __forceinline__ void gp_step_adj(const StepFwd &s, double (&L)[5], do
   }
 }
 
-__device__ __forceinline__ Adj adj_load_cg(const double *p) {
-  Adj a;
-  double *dst = a.A;
-#pragma unroll
-  for (int k = 0; k < kAdjDoubles; ++k) dst[k] = __ldcg(p + k);
-  return a;
-}
-// fixed-order composition of the maps held by lanes [0, count) (lane 0 applied first); every lane gets the result
-__device__ __forceinline__ Adj adj_warp_reduce(Adj v, int count) {
-  const int lane = threadIdx.x & 31;
-#pragma unroll 1
-  for (int d = 1; d < 32; d <<= 1) {
-    Adj o = adj_shfl_up(v, d);
-    if (lane >= d && lane < count) v = adj_after(o, v);
-  }
-  const int last = count > 0 ? count - 1 : 0;
-  Adj r;
-  const double *src = v.A;
-  double *dst = r.A;
-#pragma unroll
-  for (int k = 0; k < kAdjDoubles; ++k) dst[k] = __shfl_sync(kFullGp, src[k], last);
-  return count > 0 ? r : adj_identity();
-}
-
-// ---- one-pass reverse (adjoint) scan -------------------------------------------
-// Same structure as the forward scan, run right-to-left: ticket -> (chain, reverse tile), thread `tid` owns
-// time-run 127 - tid of a tile of kTileB = 128 x 8 cadences, so thread order = scan order.  The forward pass
-// left only the state entering every run of 8 cadences (5 doubles per run, 5 B per cadence instead of 40);
-// each thread re-derives the states inside its run into shared memory (thread-contiguous, conflict-free) and
-// walks the run backwards twice: once pushing the origin and the five basis vectors (the run's affine map),
-// once -- after the in-CTA scan and the fixed-tree look-back over earlier tiles -- with the known incoming
-// lambda, accumulating the hyper-parameter cotangents and emitting d/dy, d/d diag through shared memory
-// (coalesced stores).  The last tile of a chain to finish folds the per-tile sums in tile order and chains
-// (a, c, h, w2) -> (S0, w0, Q).
-constexpr int kTileB = kThreadsGp * kRunB;
-constexpr int kPitchB = kRunB + 1;
-
-struct GpBwdSmem {
-  double t[kThreadsGp * kPitchB];
-  double d[kThreadsGp * kPitchB];  // diag in, d loglike / d diag out
-  double y[kThreadsGp * kPitchB];  // y in, d loglike / d y out
-  double st[5][kRunB][kThreadsGp]; // state entering every step of every run
-  Adj warp_tot[kWarpsGp];
-  Adj warp_incl[kWarpsGp];
-  double entry[5];
-  double t_halo;
-  double red[6][kWarpsGp];
-  unsigned ticket;
-  int is_last;
+struct AdjOps {
+  using E = Adj;
+  static constexpr int kDoubles = kAdjDoubles;
+  static __device__ __forceinline__ E identity() { return adj_identity(); }
+  static __device__ __forceinline__ E combine(const E &earlier, const E &later) { return adj_after(earlier, later); }
+  static __device__ __forceinline__ double *data(E &e) { return e.A; }
+  static __device__ __forceinline__ const double *data(const E &e) { return e.A; }
 };
 
-__global__ void __launch_bounds__(kThreadsGp, 3)
+// ---- one-pass reverse (adjoint) scan -------------------------------------------
+// Same structure as the forward scan, run right-to-left: ticket -> (chain, reverse tile), lane l owns time-run
+// 31 - l of a tile of kTileB = 32 x 8 cadences, so lane order = scan order.  The forward pass left only the state
+// entering every run of 8 cadences (5 doubles per run, 5 B per cadence instead of 40); each lane re-derives the
+// states inside its run into shared memory (lane-contiguous, conflict-free) and walks the run backwards twice:
+// once pushing the origin and the five basis vectors (the run's affine map), once -- after the warp scan and the
+// tree look-back over earlier tiles -- with the known incoming lambda, accumulating the hyper-parameter cotangents
+// and emitting d/dy, d/d diag through shared memory (coalesced stores).  The last tile of a chain to finish folds
+// the per-tile sums in tile order and chains (a, c, h, w2) -> (S0, w0, Q).
+constexpr int kTileB = 32 * kRunB;
+constexpr int kPitchB = kRunB + 1;
+
+__global__ void __launch_bounds__(32, 12)
     gp_backward_kernel(const double *__restrict__ t, const double *__restrict__ y, const double *__restrict__ diag, int64_t N,
                        const double *__restrict__ S0, const double *__restrict__ w0, const double *__restrict__ Qf,
-                       const double *__restrict__ jitter, double eps,
-                       int tiles, int groups, int64_t Tb, const double *__restrict__ rs /* [B][5][Tb] run-start states */,
-                       unsigned *__restrict__ counters, unsigned *__restrict__ flagA, unsigned *__restrict__ flagT,
-                       double *__restrict__ adjA, double *__restrict__ adjT, double *__restrict__ gpart /* [B][tiles][6] */,
-                       GpStatus *__restrict__ status, double *__restrict__ gy, double *__restrict__ gdiag,
-                       double *__restrict__ ghyper /* [B][3] */, double *__restrict__ gsum /* [B][2] or null */) {
-  extern __shared__ __align__(16) unsigned char gp_smem_raw[];
-  GpBwdSmem &sm = *reinterpret_cast<GpBwdSmem *>(gp_smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) sm.ticket = atomicAdd(&counters[0], 1u);
-  __syncthreads();
-  const unsigned ticket = sm.ticket;
+                       const double *__restrict__ jitter, double eps, int64_t Tb,
+                       const double *__restrict__ rs /* [B][5][Tb] run-start states */, unsigned *__restrict__ counters,
+                       const TreeBuffers tb, double *__restrict__ gpart /* [B][tiles][6] */, GpStatus *__restrict__ status,
+                       double *__restrict__ gy, double *__restrict__ gdiag, double *__restrict__ ghyper /* [B][3] */,
+                       double *__restrict__ gsum /* [B][2] or null */) {
+  __shared__ double st[32 * kPitchB];
+  __shared__ double sd[32 * kPitchB];        // diag in, d loglike / d diag out
+  __shared__ double sy[32 * kPitchB];        // y in, d loglike / d y out
+  __shared__ double sst[5][kRunB][32];       // state entering every step of every run
+  const int lane = threadIdx.x;
+  unsigned ticket = 0u;
+  if (lane == 0) ticket = atomicAdd(&counters[0], 1u);
+  ticket = __shfl_sync(kFullGp, ticket, 0);
+  const int tiles = tb.n0;
   const int64_t bch = ticket / (unsigned)tiles;
   const int rtile = (int)(ticket % (unsigned)tiles);  // 0 = the LAST tile in time
   const int ttile = tiles - 1 - rtile;
   const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
   const double jit = jitter ? jitter[bch] : 0.0;
   const int64_t base = (int64_t)ttile * kTileB;
-  const int64_t nvalid = min((int64_t)kTileB, N - base);
+  const int nvalid = (int)min((int64_t)kTileB, N - base);
   const double *yb = y + bch * N;
-  for (int idx = tid; idx < kTileB; idx += kThreadsGp) {
-    const int r = idx / kRunB, i = idx % kRunB, at = r * kPitchB + i;
+#pragma unroll 4
+  for (int idx = lane; idx < kTileB; idx += 32) {
+    const int at = (idx / kRunB) * kPitchB + idx % kRunB;
     if (idx < nvalid) {
-      sm.t[at] = __ldg(t + base + idx);
-      sm.d[at] = __ldg(diag + base + idx) + jit;
-      sm.y[at] = __ldg(yb + base + idx);
+      st[at] = __ldg(t + base + idx);
+      sd[at] = __ldg(diag + base + idx) + jit;
+      sy[at] = __ldg(yb + base + idx);
     }
   }
-  if (tid == 0) sm.t_halo = __ldg(t + (base > 0 ? base - 1 : 0));
-  __syncthreads();
-  const int r = kThreadsGp - 1 - tid;  // time-run inside the tile
+  const double t_halo = __ldg(t + (base > 0 ? base - 1 : 0));
+  __syncwarp();
+  const int r = 31 - lane;  // time-run inside the tile
   const int64_t s = base + (int64_t)r * kRunB;
   const int len = (int)max((int64_t)0, min((int64_t)kRunB, N - s));
-  double *ts = sm.t + r * kPitchB, *ds = sm.d + r * kPitchB, *ys = sm.y + r * kPitchB;
-  const double t_before = r > 0 ? sm.t[(r - 1) * kPitchB + kRunB - 1] : sm.t_halo;
+  double *ts = st + r * kPitchB, *ds = sd + r * kPitchB, *ys = sy + r * kPitchB;
+  const double t_before = r > 0 ? st[(r - 1) * kPitchB + kRunB - 1] : t_halo;
   // states entering every step of the run, re-derived from the run-start state the forward pass left
   if (len > 0) {
     const int64_t run = s / kRunB;
@@ -956,15 +916,15 @@ __global__ void __launch_bounds__(kThreadsGp, 3)
     ShoCache cc;
 #pragma unroll 1
     for (int i = 0; i < len; ++i) {
-      sm.st[0][i][tid] = m0;
-      sm.st[1][i][tid] = m1;
-      sm.st[2][i][tid] = Z00;
-      sm.st[3][i][tid] = Z01;
-      sm.st[4][i][tid] = Z11;
+      sst[0][i][lane] = m0;
+      sst[1][i][lane] = m1;
+      sst[2][i][lane] = Z00;
+      sst[3][i][lane] = Z01;
+      sst[4][i][lane] = Z11;
       if (i + 1 == len) break;
       const double ti = ts[i];
       double f00, f01, f10, f11;
-      sho_phi(k, (s + i) > 0 ? ti - tprev : 0.0, cc, f00, f01, f10, f11);
+      sho_phi(k, ti - tprev, cc, f00, f01, f10, f11);
       tprev = ti;
       double c0 = f00 * m0 + f01 * m1, c1 = f10 * m0 + f11 * m1;
       double z00 = f00 * Z00 + f01 * Z01, z01 = f00 * Z01 + f01 * Z11;
@@ -984,9 +944,8 @@ __global__ void __launch_bounds__(kThreadsGp, 3)
   }
   auto step_fwd = [&](int i, ShoCache &cc) {
     const double tp = i > 0 ? ts[i - 1] : t_before;
-    const double dt = (s + i) > 0 ? ts[i] - tp : 0.0;
-    return gp_step_fwd(k, dt, ys[i], ds[i], sm.st[0][i][tid], sm.st[1][i][tid], sm.st[2][i][tid], sm.st[3][i][tid],
-                       sm.st[4][i][tid], cc);
+    return gp_step_fwd(k, ts[i] - tp, ys[i], ds[i], sst[0][i][lane], sst[1][i][lane], sst[2][i][lane], sst[3][i][lane],
+                       sst[4][i][lane], cc);
   };
   // the run's map lambda_{e-1} -> lambda_{s-1}: push the origin (with the forcing) and the five basis vectors through it
   Adj v = adj_identity();
@@ -1017,60 +976,17 @@ __global__ void __launch_bounds__(kThreadsGp, 3)
     v.om[0] = O[0];
     v.om[1] = O[1];
   }
-  v = adj_cta_inclusive_scan(v, sm.warp_tot);
-  if (lane == 31) sm.warp_incl[warp] = v;
-  if (tid == kThreadsGp - 1) {
-    adj_store(adjA + ((size_t)bch * tiles + rtile) * kAdjDoubles, v);
-    __threadfence();
-    st_release_u32(flagA + (size_t)bch * tiles + rtile, 1u);
-  }
-  __syncthreads();
-  if (warp == 0) {
-    const int g = rtile / kGroup, in_group = rtile % kGroup;
-    bool ok = true;
-    // own group first, group total published before anything outside the group is waited for (see the forward scan)
-    Adj mine = adj_identity();
-    if (lane < in_group) {
-      ok &= wait_flag(flagA + (size_t)bch * tiles + (size_t)g * kGroup + lane);
-      mine = adj_load_cg(adjA + ((size_t)bch * tiles + (size_t)g * kGroup + lane) * kAdjDoubles);
-    }
-    const Adj local = adj_warp_reduce(mine, in_group);
-    if (in_group == kGroup - 1 && g + 1 < groups) {
-      const Adj total = adj_after(local, sm.warp_incl[kWarpsGp - 1]);
-      if (lane == 0) {
-        adj_store(adjT + ((size_t)bch * groups + g) * kAdjDoubles, total);
-        __threadfence();
-        st_release_u32(flagT + (size_t)bch * groups + g, 1u);
-      }
-    }
-    Adj carry = adj_identity();
-    for (int w0g = 0; w0g < g; w0g += 32) {
-      const int cnt = min(32, g - w0g);
-      Adj tot = adj_identity();
-      if (lane < cnt) {
-        ok &= wait_flag(flagT + (size_t)bch * groups + w0g + lane);
-        tot = adj_load_cg(adjT + ((size_t)bch * groups + w0g + lane) * kAdjDoubles);
-      }
-      carry = adj_after(carry, adj_warp_reduce(tot, cnt));
-    }
-    const Adj excl = adj_after(carry, local);
-    if (!__all_sync(kFullGp, ok) && lane == 0) atomicAdd(&status->wait_failures, 1ull);
-    if (lane == 0) {  // the map applied to lambda = 0 beyond the last cadence
-      sm.entry[0] = excl.om[0];
-      sm.entry[1] = excl.om[1];
-      sm.entry[2] = excl.oz[0];
-      sm.entry[3] = excl.oz[1];
-      sm.entry[4] = excl.oz[2];
-    }
-  }
-  Adj pre = adj_shfl_up(v, 1);
-  __syncthreads();
-  if (lane == 0 && warp > 0) pre = sm.warp_incl[warp - 1];
+  v = warp_inclusive_scan<AdjOps>(v);
+  const Adj pre = elem_shfl_up<AdjOps>(v, 1);
+  bool ok = true;
+  const Adj excl = tree_exclusive<AdjOps>(tb.chain(bch, kAdjDoubles), rtile, elem_shfl<AdjOps>(v, 31), ok);
+  if (!__all_sync(kFullGp, ok) && lane == 0) atomicAdd(&status->wait_failures, 1ull);
   double ga = 0.0, gc = 0.0, gh = 0.0, gw2 = 0.0;  // cotangents of a, c, h and w2 = c^2 +- h^2
-  double sy = 0.0, sd = 0.0;                        // sums of d/dy and d/d diag over the run
+  double sy_ = 0.0, sd_ = 0.0;                      // sums of d/dy and d/d diag over the run
   if (len > 0) {
-    double L[5] = {sm.entry[0], sm.entry[1], sm.entry[2], sm.entry[3], sm.entry[4]};
-    if (tid > 0) adj_apply(pre, L);
+    // the tree's map applied to lambda = 0 beyond the last cadence, then the in-warp prefix
+    double L[5] = {excl.om[0], excl.om[1], excl.oz[0], excl.oz[1], excl.oz[2]};
+    if (lane > 0) adj_apply(pre, L);
     ShoCache cc;
 #pragma unroll 1
     for (int i = len - 1; i >= 0; --i) {
@@ -1079,8 +995,8 @@ __global__ void __launch_bounds__(kThreadsGp, 3)
       gp_step_adj<true, true>(f, L, acc);
       ys[i] = acc[0];  // d / d y_i     (y_i, diag_i are dead from here on: every step reads its own only)
       ds[i] = acc[1];  // d / d diag_i
-      sy += acc[0];
-      sd += acc[1];
+      sy_ += acc[0];
+      sd_ += acc[1];
       ga += acc[2];
       // Phi = [[Cf + c Sf, Sf], [-w2 Sf, Cf - c Sf]]
       const double d0011 = acc[3] - acc[6];
@@ -1093,37 +1009,32 @@ __global__ void __launch_bounds__(kThreadsGp, 3)
     }
     if (!isfinite(ga + gc + gh + gw2)) atomicAdd(&status->bad_lanes, 1ull);
   }
-  double vals[6] = {ga, gc, gh, gw2, sy, sd};
+  double vals[6] = {ga, gc, gh, gw2, sy_, sd_};
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
-    double x = vals[j];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFullGp, x, o);
-    if (lane == 0) sm.red[j][warp] = x;
+    for (int o = 16; o > 0; o >>= 1) vals[j] += __shfl_xor_sync(kFullGp, vals[j], o);
   }
-  __syncthreads();
+  __syncwarp();
   // per-cadence gradients out, coalesced
   if (gy || gdiag) {
-    for (int idx = tid; idx < kTileB; idx += kThreadsGp) {
+#pragma unroll 4
+    for (int idx = lane; idx < kTileB; idx += 32) {
       if (idx < nvalid) {
         const int at = (idx / kRunB) * kPitchB + idx % kRunB;
-        if (gy) gy[bch * N + base + idx] = sm.y[at];
-        if (gdiag) gdiag[bch * N + base + idx] = sm.d[at];
+        if (gy) gy[bch * N + base + idx] = sy[at];
+        if (gdiag) gdiag[bch * N + base + idx] = sd[at];
       }
     }
   }
-  if (tid < 6) {
-    double s4 = 0.0;
-    for (int w = 0; w < kWarpsGp; ++w) s4 += sm.red[tid][w];
-    gpart[((size_t)bch * tiles + rtile) * 6 + tid] = s4;
-  }
-  __syncthreads();
-  if (tid == 0) {
+  int is_last = 0;
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) gpart[((size_t)bch * tiles + rtile) * 6 + j] = vals[j];
     __threadfence();
-    sm.is_last = atomicAdd(&counters[1 + bch], 1u) == (unsigned)(tiles - 1);
+    is_last = atomicAdd(&counters[1 + bch], 1u) == (unsigned)(tiles - 1);
   }
-  __syncthreads();
-  if (sm.is_last && warp == 0) {
+  if (__shfl_sync(kFullGp, is_last, 0)) {
     // fold the per-tile cotangents of (a, c, h, w2) in tile order and chain them to (S0, w0, Q):
     //   a = S0 w0 Q,  c = w0 / (2Q),  h = c f,  f = sqrt(max(+-(4Q^2 - 1), eps)),  w2 = c^2 +- h^2
     __threadfence();
@@ -1166,22 +1077,20 @@ __global__ void __launch_bounds__(kThreadsGp, 3)
   }
 }
 
+struct TreeOffsets {  // byte offsets of one tree's scratch inside the workspace
+  int n0, n1, n2;
+  size_t off_counters, off_f0, off_f1, off_f2, off_e0, off_e1, off_e2;
+};
 struct GpLayout {
-  int tiles, groups;    // forward pass: tiles of kTile cadences per chain, groups of kGroup tiles
-  int tiles_b, groups_b;  // reverse (adjoint) pass: tiles of kTileB cadences
-  int64_t Tb;           // runs of kRunB cadences per chain
-  int nctas_b;          // smoother pass (three-kernel form): CTAs per chain
-  size_t zero_bytes;    // status word + counters + flags at the head of the workspace: cleared before every call
-  size_t off_counters, off_flagA, off_flagT, off_aggA, off_aggT, off_ll;
-  size_t off_counters_b, off_flagA_b, off_flagT_b, off_adjA, off_adjT, off_rs, off_gpart;
+  TreeOffsets fwd, bwd;  // forward: tiles of kTile cadences; reverse (adjoint): tiles of kTileB cadences
+  int64_t Tb;            // runs of kRunB cadences per chain
+  int nctas_b;           // smoother pass (three-kernel form): CTAs per chain
+  size_t zero_bytes;     // status word + counters + flags at the head of the workspace: cleared before every call
+  size_t off_ll, off_rs, off_gpart;
   size_t off_rec, off_bpref, off_bcta, off_bstate, bytes;
 };
 inline GpLayout gp_layout(int64_t N, int64_t B, bool solve = false, bool grad = false) {
   GpLayout L;
-  L.tiles = (int)((N + kTile - 1) / kTile);
-  L.groups = (L.tiles + kGroup - 1) / kGroup;
-  L.tiles_b = (int)((N + kTileB - 1) / kTileB);
-  L.groups_b = (L.tiles_b + kGroup - 1) / kGroup;
   L.Tb = (N + kRunB - 1) / kRunB;
   L.nctas_b = (int)((L.Tb + kThreadsGp - 1) / kThreadsGp);
   size_t o = 256;  // GpStatus
@@ -1191,19 +1100,29 @@ inline GpLayout gp_layout(int64_t N, int64_t B, bool solve = false, bool grad = 
     return at;
   };
   auto take = [&](size_t n) { return take_bytes(n * sizeof(double)); };
-  L.off_counters = take_bytes((size_t)(1 + B) * sizeof(unsigned));
-  L.off_flagA = take_bytes((size_t)B * L.tiles * sizeof(unsigned));
-  L.off_flagT = take_bytes((size_t)B * L.groups * sizeof(unsigned));
-  L.off_counters_b = L.off_flagA_b = L.off_flagT_b = 0;
-  if (grad) {
-    L.off_counters_b = take_bytes((size_t)(1 + B) * sizeof(unsigned));
-    L.off_flagA_b = take_bytes((size_t)B * L.tiles_b * sizeof(unsigned));
-    L.off_flagT_b = take_bytes((size_t)B * L.groups_b * sizeof(unsigned));
-  }
+  auto tree_counts = [&](TreeOffsets &T, int64_t tile) {
+    T.n0 = (int)((N + tile - 1) / tile);
+    T.n1 = (T.n0 + 31) / 32;
+    T.n2 = (T.n1 + 31) / 32;
+  };
+  auto tree_flags = [&](TreeOffsets &T) {
+    T.off_counters = take_bytes((size_t)(1 + B) * sizeof(unsigned));
+    T.off_f0 = take_bytes((size_t)B * T.n0 * sizeof(unsigned));
+    T.off_f1 = take_bytes((size_t)B * T.n1 * sizeof(unsigned));
+    T.off_f2 = take_bytes((size_t)B * T.n2 * sizeof(unsigned));
+  };
+  auto tree_elems = [&](TreeOffsets &T, int doubles) {
+    T.off_e0 = take((size_t)B * T.n0 * doubles);
+    T.off_e1 = take((size_t)B * T.n1 * doubles);
+    T.off_e2 = take((size_t)B * T.n2 * doubles);
+  };
+  tree_counts(L.fwd, kTile);
+  tree_counts(L.bwd, kTileB);
+  tree_flags(L.fwd);
+  if (grad) tree_flags(L.bwd);
   L.zero_bytes = o;
-  L.off_aggA = take((size_t)B * L.tiles * kAggDoubles);
-  L.off_aggT = take((size_t)B * L.groups * kAggDoubles);
-  L.off_ll = take((size_t)B * L.tiles);
+  tree_elems(L.fwd, kAggDoubles);
+  L.off_ll = take((size_t)B * L.fwd.n0);
   L.off_rec = L.off_bpref = L.off_bcta = L.off_bstate = 0;
   if (solve) {
     L.off_rec = take((size_t)B * 3 * N);
@@ -1211,37 +1130,30 @@ inline GpLayout gp_layout(int64_t N, int64_t B, bool solve = false, bool grad = 
     L.off_bcta = take((size_t)B * L.nctas_b * 6);
     L.off_bstate = take((size_t)B * L.nctas_b * 2);
   }
-  L.off_adjA = L.off_adjT = L.off_rs = L.off_gpart = 0;
+  L.off_rs = L.off_gpart = 0;
   if (grad) {
     L.off_rs = take((size_t)B * 5 * L.Tb);
-    L.off_adjA = take((size_t)B * L.tiles_b * kAdjDoubles);
-    L.off_adjT = take((size_t)B * L.groups_b * kAdjDoubles);
-    L.off_gpart = take((size_t)B * L.tiles_b * 6);
+    tree_elems(L.bwd, kAdjDoubles);
+    L.off_gpart = take((size_t)B * L.bwd.n0 * 6);
   }
   L.bytes = o;
   return L;
+}
+inline TreeBuffers tree_buffers(char *ws, const TreeOffsets &T) {
+  auto d = [&](size_t off) { return reinterpret_cast<double *>(ws + off); };
+  auto u = [&](size_t off) { return reinterpret_cast<unsigned *>(ws + off); };
+  return TreeBuffers{d(T.off_e0), d(T.off_e1), d(T.off_e2), u(T.off_f0), u(T.off_f1), u(T.off_f2), T.n0, T.n1, T.n2};
 }
 
 // the one-pass forward scan: clear status/counters/flags (one stream-ordered memset), one kernel
 template <int REC>
 int gp_forward(const double *t, const double *y, const double *diag, int64_t N, const double *S0, const double *w0, const double *Q,
                const double *jitter, int64_t B, double eps, double *loglike, double *rec, char *ws, const GpLayout &L, cudaStream_t st) {
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gp_forward_kernel<REC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GpFwdSmem));
-    if (e != cudaSuccess) return -(int)e;
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
-  }
   cudaError_t e = cudaMemsetAsync(ws, 0, L.zero_bytes, st);
   if (e != cudaSuccess) return -(int)e;
-  const size_t total = (size_t)B * L.tiles;
-  xo::launch(gp_forward_kernel<REC>, dim3((unsigned)total), dim3(kThreadsGp), sizeof(GpFwdSmem), st, t, y, diag, N, S0, w0, Q, jitter, eps, L.tiles,
-             L.groups, reinterpret_cast<unsigned *>(ws + L.off_counters), reinterpret_cast<unsigned *>(ws + L.off_flagA),
-             reinterpret_cast<unsigned *>(ws + L.off_flagT), reinterpret_cast<double *>(ws + L.off_aggA),
-             reinterpret_cast<double *>(ws + L.off_aggT), reinterpret_cast<double *>(ws + L.off_ll), reinterpret_cast<GpStatus *>(ws),
-             loglike, rec, L.Tb);
+  xo::launch(gp_forward_kernel<REC>, dim3((unsigned)((size_t)B * L.fwd.n0)), dim3(32), 0, st, t, y, diag, N, S0, w0, Q, jitter, eps,
+             reinterpret_cast<unsigned *>(ws + L.fwd.off_counters), tree_buffers(ws, L.fwd), reinterpret_cast<double *>(ws + L.off_ll),
+             reinterpret_cast<GpStatus *>(ws), loglike, rec, L.Tb);
   return 0;
 }
 
@@ -1268,18 +1180,9 @@ int celerite_sho_grad_impl(const double *t, const double *y, const double *diag,
   XO_NVTX_SCOPE("xo_celerite_sho_grad");
   int rc = gp_forward<2>(t, y, diag, N, S0, w0, Q, jitter, B, eps, loglike, at(L.off_rs), ws, L, st);
   if (rc) return rc;
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GpBwdSmem));
-    if (e != cudaSuccess) return -(int)e;
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
-  }
-  xo::launch(gp_backward_kernel, dim3((unsigned)((size_t)B * L.tiles_b)), dim3(kThreadsGp), sizeof(GpBwdSmem), st, t, y, diag, N, S0, w0, Q,
-             jitter, eps, L.tiles_b, L.groups_b, L.Tb, at(L.off_rs), reinterpret_cast<unsigned *>(ws + L.off_counters_b),
-             reinterpret_cast<unsigned *>(ws + L.off_flagA_b), reinterpret_cast<unsigned *>(ws + L.off_flagT_b), at(L.off_adjA),
-             at(L.off_adjT), at(L.off_gpart), reinterpret_cast<GpStatus *>(ws), gy, gdiag, ghyper, gsum);
+  xo::launch(gp_backward_kernel, dim3((unsigned)((size_t)B * L.bwd.n0)), dim3(32), 0, st, t, y, diag, N, S0, w0, Q, jitter, eps, L.Tb,
+             (const double *)at(L.off_rs), reinterpret_cast<unsigned *>(ws + L.bwd.off_counters), tree_buffers(ws, L.bwd), at(L.off_gpart),
+             reinterpret_cast<GpStatus *>(ws), gy, gdiag, ghyper, gsum);
   return xo::launch_status();
 }
 
@@ -1298,7 +1201,7 @@ int xo_celerite_sho_loglike(const double *t, const double *y, const double *diag
   if (N < 0 || B < 0) return XO_EINVAL;
   if (B == 0) return 0;
   if (N == 0) return XO_EINVAL;
-  if ((double)B * (double)((N + kTile - 1) / kTile) > 2.0e9) return XO_ERANGE;
+  if ((double)B * (double)((N + kTileB - 1) / kTileB) > 2.0e9) return XO_ERANGE;
   if (!t || !y || !diag || !S0 || !w0 || !Q || !loglike || !workspace) return XO_EINVAL;
   XO_NVTX_SCOPE("xo_celerite_sho_loglike");
   GpLayout L = gp_layout(N, B);

@@ -52,6 +52,14 @@ transit)
   for V in $TRANSIT_VARIANTS; do XO_B200_LIB=exoplanet_b200/libxo_b200_$V.so bench_line $V --steps 20 --warmup 5 --no-cpu --no-kepler --no-extra; done
   capture transit transit_logp_grad_kernel 3 --steps 2 --warmup 3 --no-cpu --no-kepler --no-extra
   ;;
+both)
+  run_pytest all tests/test_gpu_fused.py tests/test_reference_glue.py tests/test_gpu_configs.py tests/test_gpu_sampling.py tests/test_gpu_gp.py
+  bench_line ours --steps 20 --warmup 5 --no-cpu --no-kepler
+  for V in $GP_VARIANTS; do XO_B200_LIB=exoplanet_b200/libxo_b200_$V.so bench_line $V --steps 20 --warmup 5 --no-cpu --no-kepler --extra gp; done
+  capture transit transit_logp_grad_kernel 3 --steps 2 --warmup 3 --no-cpu --no-kepler --no-extra
+  capture gpfwd "gp_forward_kernel" 27 --steps 1 --warmup 3 --no-cpu --no-kepler --extra gp
+  capture gpbwd "gp_backward_kernel" 14 --steps 1 --warmup 3 --no-cpu --no-kepler --extra gp
+  ;;
 final)
   run_pytest all tests
   for ML in 1 2; do XO_MODEL_LAUNCHES=$ML run_pytest launches$ML tests/test_gpu_fused.py; done
