@@ -5,18 +5,26 @@
 //
 // The celerite recurrence is a Riccati (linear-fractional) recursion, so it is run in
 // its equivalent 2-state Kalman-filter form, which has an associative combine
-// (Sarkka & Garcia-Fernandez 2021).  One kernel, one read of the data (gp_forward_kernel): a warp stages a tile of
-// 512 cadences of (t, diag, y) in shared memory, every lane walks a run of kRun consecutive cadences once from a
-// *known* start (P = 0), tracking the affine dependence of the filtered mean on the unknown start state and the
-// information (eta, J) the run's data carry about it -> one scan element per run, no 2x2 inverses; warp scan; a
-// fixed 32-ary tree over the tile totals of the chain (flags + bounded waits, tiles handed out by ticket) gives
-// the state entering the tile; every lane then re-walks its run from shared memory with plain Kalman steps,
-// accumulating -1/2 (v^2/D + log D); the last tile of a chain folds the per-tile sums in order.  A tile is ONE
-// warp on purpose: the tree look-back is a serial stretch of a few thousand dependent instructions, and with
-// one-warp CTAs nobody waits at a barrier for it -- the other 15 resident warps of the SM keep computing.
+// (Sarkka & Garcia-Fernandez 2021).  Three phases, every thread owns a run of RUN consecutive cadences:
+//   1. gp_aggregate: walk the run once from a *known* start (P = 0), tracking the affine dependence of the filtered mean
+//      on the unknown start state and the information (eta, J) the run's data carry about it -> one scan element per
+//      run, no 2x2 inverses; then an in-CTA inclusive scan of the run elements (shuffle scan + 4 warp totals);
+//   2. gp_cta_scan: one CTA scans the per-CTA totals and applies each exclusive prefix to the stationary prior -> the
+//      state (m, Z = Sigma_inf - P) entering every CTA;
+//   3. gp_loglike: each thread applies its in-CTA prefix to that state and re-walks its run with plain Kalman steps,
+//      accumulating -1/2 (v^2/D + log D); the last CTA of a chain folds the per-CTA sums in CTA order.
+// A thread's run is one or two 128-byte lines of each array: the lines are prefetched into L1 when the thread starts
+// and every step's operands are loaded one step ahead, so the walk never waits for memory; every sector that is
+// fetched is fully used.  Two one-pass formulations (tile staged in shared memory, one read of the data, a fixed
+// inter-CTA tree with flags instead of the second kernel) were built and measured in round 2: 0.98 ms (128-thread
+// tiles) and 1.27 ms (one-warp tiles) against 0.58 ms for this form at 16 chains x 1e6 cadences -- the scans are
+// instruction/latency-bound, not bandwidth-bound, and the serial tree look-back costs more than the second read of the
+// data saves (profiles/r02_gp_onepass.txt); they live in the history (commits "celerite: one-pass ...").
 // SHO in (a, c, h) form so celerite2's eps-regularised coefficients are matched exactly:
 //   underdamped k(tau) = a e^{-c tau}(cos h tau + (c/h) sin h tau), overdamped with cosh/sinh.
 #include <cuda_runtime.h>
+
+#include <cstdlib>
 
 #include "xo_common.cuh"
 #include "xo_math.cuh"
@@ -165,195 +173,52 @@ __device__ __forceinline__ void agg_apply(const Agg &g, double &m0, double &m1, 
   P11 = c11;
 }
 
-// ---------------------------------------------------------------------------
-// Inter-tile plumbing of the one-pass scans: tickets, flags, bounded spin-waits, a fixed 32-ary tree.
-//
-// A tile is the work of ONE WARP (a CTA of 32 threads): while a warp waits for its predecessors no other warp
-// idles at a barrier, and the other resident warps of the SM (16 forward, 12 reverse) keep the pipes busy.
-// Tiles are handed out by an atomic ticket (chain-major: ticket = chain * tiles + tile), so a warp only ever waits
-// on tiles with a LOWER ticket, i.e. on warps that are already running: forward progress does not depend on the
-// hardware's CTA scheduling order.  A flag is published with a release store after the payload; readers poll it
-// with acquire loads and read the payload through L2 (ld.cg).  Every wait is bounded (kSpinLimit polls with
-// back-off): on expiry the warp records a failure in the status word and carries on, so the kernel always
-// terminates (include/xo_b200.h: "every iteration is bounded").
-//
-// The exclusive prefix of tile k over the earlier tiles of its chain comes from a FIXED tree, so the result is
-// bit-reproducible: level 0 = tile totals, level 1 = totals of groups of 32 tiles, level 2 = totals of groups of
-// 1024 tiles.  prefix(k) = [level-2 totals before k's level-2 group] o [level-1 totals before k's group, inside that
-// level-2 group] o [tile totals before k inside its group] -- at most 31 + 31 entries below level 2, reduced in one
-// pass by a warp holding two entries per lane.  The last tile of a group publishes the group total BEFORE it waits
-// for anything outside the group (else the group totals would be published one after the other, a serial chain).
-// ---------------------------------------------------------------------------
-constexpr unsigned kSpinLimit = 1u << 22;  // x >= 40 ns back-off: > 0.15 s, far beyond any real wait
+__device__ __forceinline__ Agg agg_shfl_up(const Agg &a, int delta) {
+  Agg o;
+  const double *src = &a.A00;
+  double *dst = &o.A00;
+#pragma unroll
+  for (int k = 0; k < kAggDoubles; ++k) dst[k] = __shfl_up_sync(kFullGp, src[k], delta);
+  return o;
+}
 
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ void agg_store(double *p, const Agg &a) {
+  const double *src = &a.A00;
+#pragma unroll
+  for (int k = 0; k < kAggDoubles; ++k) p[k] = src[k];
+}
+__device__ __forceinline__ Agg agg_load(const double *p) {
+  Agg a;
+  double *dst = &a.A00;
+#pragma unroll
+  for (int k = 0; k < kAggDoubles; ++k) dst[k] = p[k];
+  return a;
+}
+
+// inclusive scan of one Agg per thread across the CTA (thread order); returns inclusive value
+__device__ Agg cta_inclusive_scan(Agg v, Agg *warp_tot /* smem [kWarps] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    Agg o = agg_shfl_up(v, d);
+    if (lane >= d) v = agg_combine(o, v);
+  }
+  if (lane == 31) warp_tot[warp] = v;
+  __syncthreads();
+  if (warp > 0) {
+    Agg pre = warp_tot[0];
+    for (int w = 1; w < warp; ++w) pre = agg_combine(pre, warp_tot[w]);
+    v = agg_combine(pre, v);
+  }
   return v;
 }
-__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-// true when *flag became non-zero within the bound
-__device__ __forceinline__ bool wait_flag(const unsigned *flag) {
-  unsigned ns = 20;
-  for (unsigned it = 0; it < kSpinLimit; ++it) {
-    if (ld_acquire_u32(flag) != 0u) return true;
-    __nanosleep(ns);
-    if (ns < 160) ns += 20;
-  }
-  return false;
-}
 
-// status word at the head of every celerite workspace (see xo_read_status): [0] lanes whose result was
-// not finite, [1] expired waits (a broken scan: the result must be discarded)
+
+// status word at the head of every celerite workspace (see xo_read_status): [0] lanes whose result was not finite,
+// [1] reserved (expired waits of the one-pass formulations; always 0 in this form)
 struct GpStatus {
   unsigned long long bad_lanes, wait_failures;
 };
-
-struct AggOps {
-  using E = Agg;
-  static constexpr int kDoubles = kAggDoubles;
-  static __device__ __forceinline__ E identity() { return agg_identity(); }
-  static __device__ __forceinline__ E combine(const E &earlier, const E &later) { return agg_combine(earlier, later); }
-  static __device__ __forceinline__ double *data(E &e) { return &e.A00; }
-  static __device__ __forceinline__ const double *data(const E &e) { return &e.A00; }
-};
-
-template <class O>
-__device__ __forceinline__ typename O::E elem_shfl_up(const typename O::E &a, int delta) {
-  typename O::E o;
-#pragma unroll
-  for (int k = 0; k < O::kDoubles; ++k) O::data(o)[k] = __shfl_up_sync(kFullGp, O::data(a)[k], delta);
-  return o;
-}
-template <class O>
-__device__ __forceinline__ typename O::E elem_shfl(const typename O::E &a, int src) {
-  typename O::E o;
-#pragma unroll
-  for (int k = 0; k < O::kDoubles; ++k) O::data(o)[k] = __shfl_sync(kFullGp, O::data(a)[k], src);
-  return o;
-}
-template <class O>
-__device__ __forceinline__ typename O::E elem_load_cg(const double *p) {
-  typename O::E a;
-#pragma unroll
-  for (int k = 0; k < O::kDoubles; ++k) O::data(a)[k] = __ldcg(p + k);
-  return a;
-}
-template <class O>
-__device__ __forceinline__ void elem_store(double *p, const typename O::E &a) {
-#pragma unroll
-  for (int k = 0; k < O::kDoubles; ++k) p[k] = O::data(a)[k];
-}
-
-// inclusive scan over the 32 lanes of a warp (lane order = scan order)
-template <class O>
-__device__ __forceinline__ typename O::E warp_inclusive_scan(typename O::E v) {
-  const int lane = threadIdx.x & 31;
-#pragma unroll 1
-  for (int d = 1; d < 32; d <<= 1) {
-    typename O::E o = elem_shfl_up<O>(v, d);
-    if (lane >= d) v = O::combine(o, v);
-  }
-  return v;
-}
-// fixed-order combination of the elements held by lanes [0, count): e_0 o e_1 o ... o e_{count-1} in every lane;
-// only ceil(log2 count) levels are executed
-template <class O>
-__device__ __forceinline__ typename O::E warp_reduce_n(typename O::E v, int count) {
-  const int lane = threadIdx.x & 31;
-#pragma unroll 1
-  for (int d = 1; d < count; d <<= 1) {
-    typename O::E o = elem_shfl_up<O>(v, d);
-    if (lane >= d && lane < count) v = O::combine(o, v);
-  }
-  return elem_shfl<O>(v, count > 0 ? count - 1 : 0);
-}
-
-// one level of the tree for one chain
-struct TreeSeg {
-  const double *elems;
-  const unsigned *flags;
-  int start, count;  // entries [start, start + count) of the level, in order
-};
-// e = entry `pos` of the concatenation s0 | s1 | s2 (waits for its flag)
-template <class O>
-__device__ __forceinline__ typename O::E tree_fetch(const TreeSeg &s0, const TreeSeg &s1, const TreeSeg &s2, int pos, bool &ok) {
-  const TreeSeg &s = pos < s0.count ? s0 : (pos < s0.count + s1.count ? s1 : s2);
-  const int idx = s.start + (pos < s0.count ? pos : (pos < s0.count + s1.count ? pos - s0.count : pos - s0.count - s1.count));
-  ok &= wait_flag(s.flags + idx);
-  return elem_load_cg<O>(s.elems + (size_t)idx * O::kDoubles);
-}
-// the concatenation s0 | s1 | s2 combined in order, 64 entries per pass (two per lane)
-template <class O>
-__device__ __forceinline__ typename O::E tree_reduce(const TreeSeg &s0, const TreeSeg &s1, const TreeSeg &s2, bool &ok) {
-  const int lane = threadIdx.x & 31;
-  const int total = s0.count + s1.count + s2.count;
-  typename O::E carry = O::identity();
-#pragma unroll 1
-  for (int base = 0; base < total; base += 64) {
-    const int cnt = min(64, total - base);
-    typename O::E mine = O::identity();
-    if (cnt <= 32) {
-      if (lane < cnt) mine = tree_fetch<O>(s0, s1, s2, base + lane, ok);
-      mine = warp_reduce_n<O>(mine, cnt);
-    } else {
-      if (2 * lane < cnt) mine = tree_fetch<O>(s0, s1, s2, base + 2 * lane, ok);
-      if (2 * lane + 1 < cnt) mine = O::combine(mine, tree_fetch<O>(s0, s1, s2, base + 2 * lane + 1, ok));
-      mine = warp_reduce_n<O>(mine, (cnt + 1) / 2);
-    }
-    carry = base == 0 ? mine : O::combine(carry, mine);
-  }
-  return carry;
-}
-
-// scratch of one chain's tree (pointers already offset to the chain)
-struct TreeView {
-  double *e0, *e1, *e2;
-  unsigned *f0, *f1, *f2;
-  int n0;  // tiles of the chain
-};
-template <class O>
-__device__ __forceinline__ void tree_publish(double *elems, unsigned *flags, int idx, const typename O::E &v) {
-  if ((threadIdx.x & 31) == 0) {
-    elem_store<O>(elems + (size_t)idx * O::kDoubles, v);
-    __threadfence();
-    st_release_u32(flags + idx, 1u);
-  }
-}
-// exclusive prefix of tile `tile` over the earlier tiles of the chain; `own` = this tile's total (valid in every lane).
-// Publishes the tile total and, from the last tile of a group, the group totals.
-// (not inlined: called once per tile; its many live scan elements must not compete with the walks for registers)
-template <class O>
-__device__ __noinline__ typename O::E tree_exclusive(const TreeView &tv, int tile, const typename O::E &own, bool &ok) {
-  tree_publish<O>(tv.e0, tv.f0, tile, own);
-  const int d0 = tile & 31, g1 = tile >> 5, d1 = g1 & 31, g2 = g1 >> 5;
-  const TreeSeg none{nullptr, nullptr, 0, 0};
-  const TreeSeg tiles{tv.e0, tv.f0, g1 * 32, d0}, groups{tv.e1, tv.f1, g2 * 32, d1}, supers{tv.e2, tv.f2, 0, g2};
-  if (d0 != 31) return tree_reduce<O>(supers, groups, tiles, ok);
-  // last tile of a full group of 32
-  const typename O::E a = tree_reduce<O>(tiles, none, none, ok);
-  const typename O::E t1 = O::combine(a, own);
-  if ((g1 + 1) * 32 < tv.n0) tree_publish<O>(tv.e1, tv.f1, g1, t1);
-  if (d1 != 31) return O::combine(tree_reduce<O>(supers, groups, none, ok), a);
-  const typename O::E b = tree_reduce<O>(groups, none, none, ok);
-  if ((g2 + 1) * 1024 < tv.n0) tree_publish<O>(tv.e2, tv.f2, g2, O::combine(b, t1));
-  return O::combine(O::combine(tree_reduce<O>(supers, none, none, ok), b), a);
-}
-
-// ---- one-pass forward scan ---------------------------------------------------
-// One warp owns a tile of kTile = 32 * kRun cadences of one chain:
-//   1. the tile of (t, diag, y) is read from HBM ONCE, coalesced, into shared memory (row pitch kRun + 1
-//      doubles: lane r then walks row r conflict-free);
-//   2. every lane walks its run from a known start (P = 0) -> one scan element per run; warp scan;
-//   3. the tile total is published and the exclusive prefix over the earlier tiles of the chain comes from the
-//      fixed tree above; applied to the stationary prior it gives the state entering the tile;
-//   4. every lane applies its in-warp exclusive prefix and re-walks its run from shared memory with plain
-//      Kalman steps, accumulating -1/2 (v^2/D + log D);
-//   5. per-tile sums are folded in tile order by the last tile of the chain to finish (bit-reproducible).
-constexpr int kTile = 32 * kRun;
-constexpr int kPitch = kRun + 1;
 
 // sum of log D over a run as the log of a product of mantissas plus an integer exponent sum: one DMUL and a
 // few integer instructions per cadence instead of a log; mantissas are in [0.5, 1), so a run of <= 64 cadences
@@ -374,67 +239,57 @@ struct LogProd {
   __device__ __forceinline__ double value() const { return log(mant) + slow + (double)expo * 0.69314718055994530941723212145818; }
 };
 
-// device scratch shared by the forward and the reverse tree: per level elements + flags, [B][n_level]
-struct TreeBuffers {
-  double *e0, *e1, *e2;
-  unsigned *f0, *f1, *f2;
-  int n0, n1, n2;
-  __device__ __forceinline__ TreeView chain(int64_t b, int doubles) const {
-    return TreeView{e0 + (size_t)b * n0 * doubles, e1 + (size_t)b * n1 * doubles, e2 + (size_t)b * n2 * doubles, f0 + (size_t)b * n0,
-                    f1 + (size_t)b * n1, f2 + (size_t)b * n2, n0};
-  }
-};
 
-#ifndef XO_GP_MINBLOCKS
-#define XO_GP_MINBLOCKS 16  // resident warp-tiles per SM the forward scan is compiled for (build-time knob): 128 registers
+#ifndef XO_GP_RUN_LONG
+#define XO_GP_RUN_LONG 32  // run length used when there is parallelism to spare: halves the in-CTA scan work per cadence
 #endif
-template <int REC /* 0: none, 1: (v/D, K0, K1) per cadence for the smoother, 2: state entering every run of kRunB cadences */>
-__global__ void __launch_bounds__(32, XO_GP_MINBLOCKS)
-    gp_forward_kernel(const double *__restrict__ t, const double *__restrict__ y, const double *__restrict__ diag, int64_t N,
-                      const double *__restrict__ S0, const double *__restrict__ w0, const double *__restrict__ Qf,
-                      const double *__restrict__ jitter /* [B] added to diag, or null */, double eps,
-                      unsigned *__restrict__ counters /* [0] ticket, [1 + b] tiles done of chain b */, const TreeBuffers tb,
-                      double *__restrict__ cta_ll, GpStatus *__restrict__ status, double *__restrict__ loglike,
-                      double *__restrict__ rec, int64_t Tb) {
-  __shared__ double st[32 * kPitch], sd[32 * kPitch], sy[32 * kPitch];
-  const int lane = threadIdx.x;
-  unsigned ticket = 0u;
-  if (lane == 0) ticket = atomicAdd(&counters[0], 1u);
-  ticket = __shfl_sync(kFullGp, ticket, 0);
-  const int tiles = tb.n0;
-  const int64_t bch = ticket / (unsigned)tiles;
-  const int tile = (int)(ticket % (unsigned)tiles);
+// one 128-byte line per 16 doubles: ask for the run's lines before the walk needs them
+template <int RUN>
+__device__ __forceinline__ void prefetch_run(const double *p) {
+#pragma unroll
+  for (int j = 0; j < RUN; j += 16) xo::prefetch_l1(p + j);
+}
+
+// ---- phase 1 ---------------------------------------------------------------
+template <int RUN>
+__global__ void __launch_bounds__(kThreadsGp) gp_aggregate_kernel(const double *__restrict__ t, const double *__restrict__ y,
+                                                                  const double *__restrict__ diag, int64_t N,
+                                                                  const double *__restrict__ S0, const double *__restrict__ w0,
+                                                                  const double *__restrict__ Qf,
+                                                                  const double *__restrict__ jitter, double eps, int64_t T,
+                                                                  double *__restrict__ pref, double *__restrict__ cta_tot,
+                                                                  unsigned *__restrict__ done, GpStatus *__restrict__ status) {
+  __shared__ Agg warp_tot[kWarpsGp];
+  const int64_t bch = blockIdx.y;
+  const int64_t g = (int64_t)blockIdx.x * kThreadsGp + threadIdx.x;
+  const int64_t s = g * RUN, e = min(s + RUN, N);
+  const double *yb = y + bch * N;
+  if (s < e) {
+    prefetch_run<RUN>(t + s);
+    prefetch_run<RUN>(diag + s);
+    prefetch_run<RUN>(yb + s);
+  }
+  if (threadIdx.x == 0 && blockIdx.x == 0) {  // per-call scratch the later kernels of this stream-ordered sequence count in
+    done[bch] = 0u;
+    if (bch == 0) status->bad_lanes = status->wait_failures = 0ull;
+  }
   const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
   const double jit = jitter ? jitter[bch] : 0.0;
-  const int64_t base = (int64_t)tile * kTile;
-  const int nvalid = (int)min((int64_t)kTile, N - base);
-  const double *yb = y + bch * N;
-  // 1. the tile, coalesced (consecutive lanes read consecutive cadences), once
-#pragma unroll 4
-  for (int idx = lane; idx < kTile; idx += 32) {
-    const int at = (idx / kRun) * kPitch + idx % kRun;
-    if (idx < nvalid) {
-      st[at] = __ldg(t + base + idx);
-      sd[at] = __ldg(diag + base + idx) + jit;
-      sy[at] = __ldg(yb + base + idx);
-    }
-  }
-  const double t_halo = __ldg(t + (base > 0 ? base - 1 : 0));  // the time stamp before the tile's first cadence
-  __syncwarp();
-  const int64_t s = base + (int64_t)lane * kRun;
-  const int len = (int)max((int64_t)0, min((int64_t)kRun, N - s));
-  const double *ts = st + lane * kPitch, *ds = sd + lane * kPitch, *ys = sy + lane * kPitch;
-  const double t_before = lane > 0 ? st[(lane - 1) * kPitch + kRun - 1] : t_halo;
-  // 2. the run's scan element, from a known start
   Agg v = agg_identity();
-  if (len > 0) {
+  if (s < e) {
     double A00 = 1, A01 = 0, A10 = 0, A11 = 1, b0 = 0, b1 = 0, e0 = 0, e1 = 0, J00 = 0, J01 = 0, J11 = 0;
     double Z00 = k.a, Z01 = 0.0, Z11 = k.a * k.w2;  // P = 0  <=>  Z = Sigma_inf
-    double tprev = t_before;
+    double tprev = s > 0 ? __ldg(t + s - 1) : __ldg(t);
+    double tn = __ldg(t + s), dn = __ldg(diag + s), yn = __ldg(yb + s);  // operands of the next step, loaded one step ahead
     ShoCache cc;
 #pragma unroll 1
-    for (int i = 0; i < len; ++i) {
-      const double ti = ts[i];
+    for (int64_t i = s; i < e; ++i) {
+      const double ti = tn, di = dn + jit, yi = yn;
+      if (i + 1 < e) {
+        tn = __ldg(t + i + 1);
+        dn = __ldg(diag + i + 1);
+        yn = __ldg(yb + i + 1);
+      }
       double f00, f01, f10, f11;
       sho_phi(k, ti - tprev, cc, f00, f01, f10, f11);
       tprev = ti;
@@ -446,10 +301,10 @@ __global__ void __launch_bounds__(32, XO_GP_MINBLOCKS)
       double z10 = f10 * Z00 + f11 * Z01, z11 = f10 * Z01 + f11 * Z11;
       double p00 = z00 * f00 + z01 * f01, p01 = z00 * f10 + z01 * f11, p11 = z10 * f10 + z11 * f11;
       const double pm = k.a - p00;
-      const double D = pm + ds[i];
+      const double D = pm + di;
       const double rD = xo::rcp_fast(D);
       const double K0 = pm * rD, K1 = -p01 * rD;
-      const double vb = ys[i] - c0;
+      const double vb = yi - c0;
       J00 = fma(a00 * a00, rD, J00);
       J01 = fma(a00 * a01, rD, J01);
       J11 = fma(a01 * a01, rD, J11);
@@ -467,31 +322,107 @@ __global__ void __launch_bounds__(32, XO_GP_MINBLOCKS)
     }
     v = Agg{A00, A01, A10, A11, b0, b1, k.a - Z00, -Z01, k.a * k.w2 - Z11, e0, e1, J00, J01, J11};
   }
-  v = warp_inclusive_scan<AggOps>(v);
-  // exclusive prefix of this lane's run inside the tile: the inclusive value of the previous lane
-  const Agg pre = elem_shfl_up<AggOps>(v, 1);
-  // 3. the state entering the tile
-  bool ok = true;
-  const Agg excl = tree_exclusive<AggOps>(tb.chain(bch, kAggDoubles), tile, elem_shfl<AggOps>(v, 31), ok);
-  if (!__all_sync(kFullGp, ok) && lane == 0) atomicAdd(&status->wait_failures, 1ull);
-  // 4. re-walk with plain Kalman steps
+  v = cta_inclusive_scan(v, warp_tot);
+  if (g < T) agg_store(pref + (bch * T + g) * kAggDoubles, v);
+  if (threadIdx.x == kThreadsGp - 1) agg_store(cta_tot + (bch * gridDim.x + blockIdx.x) * kAggDoubles, v);
+}
+
+// ---- phase 2: scan the CTA totals, emit the state entering each CTA ---------
+__global__ void __launch_bounds__(kThreadsGp) gp_cta_scan_kernel(const double *__restrict__ cta_tot, int nctas,
+                                                                 const double *__restrict__ S0,
+                                                                 const double *__restrict__ w0,
+                                                                 const double *__restrict__ Qf, double eps,
+                                                                 double *__restrict__ cta_state) {
+  __shared__ Agg warp_tot[kWarpsGp];
+  __shared__ Agg carry_s;
+  const int64_t bch = blockIdx.x;
+  const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
+  Agg carry = agg_identity();
+  for (int base = 0; base < nctas; base += kThreadsGp) {
+    const int idx = base + threadIdx.x;
+    Agg v = idx < nctas ? agg_load(cta_tot + (bch * nctas + idx) * kAggDoubles) : agg_identity();
+    v = cta_inclusive_scan(v, warp_tot);
+    Agg incl = agg_combine(carry, v);
+    // exclusive prefix of idx = inclusive of idx-1
+    Agg prev = agg_shfl_up(incl, 1);
+    __shared__ Agg lastlane[kWarpsGp];
+    if ((threadIdx.x & 31) == 31) lastlane[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    Agg excl;
+    if ((threadIdx.x & 31) == 0)
+      excl = (threadIdx.x == 0) ? carry : lastlane[(threadIdx.x >> 5) - 1];
+    else
+      excl = prev;
+    if (idx < nctas) {
+      double m0 = 0.0, m1 = 0.0, P00 = k.a, P01 = 0.0, P11 = k.a * k.w2;
+      agg_apply(excl, m0, m1, P00, P01, P11);
+      double *o = cta_state + (bch * nctas + idx) * 5;
+      o[0] = m0;
+      o[1] = m1;
+      o[2] = k.a - P00;  // Z = Sigma_inf - P
+      o[3] = -P01;
+      o[4] = k.a * k.w2 - P11;
+    }
+    if (threadIdx.x == kThreadsGp - 1) carry_s = incl;
+    __syncthreads();
+    carry = carry_s;
+    __syncthreads();
+  }
+}
+
+
+// ---- phase 3 ---------------------------------------------------------------
+template <int RUN, int REC /* 0: none, 1: (v/D, K0, K1) per cadence for the smoother, 2: state entering every run of kRunB cadences */>
+__global__ void __launch_bounds__(kThreadsGp) gp_loglike_kernel(const double *__restrict__ t, const double *__restrict__ y,
+                                                                const double *__restrict__ diag, int64_t N,
+                                                                const double *__restrict__ S0, const double *__restrict__ w0,
+                                                                const double *__restrict__ Qf, const double *__restrict__ jitter,
+                                                                double eps, int64_t T, const double *__restrict__ pref,
+                                                                const double *__restrict__ cta_state, double *__restrict__ cta_ll,
+                                                                unsigned *__restrict__ done, GpStatus *__restrict__ status,
+                                                                double *__restrict__ loglike, double *__restrict__ rec, int64_t Tb) {
+  __shared__ double red[kWarpsGp];
+  __shared__ int is_last;
+  const int64_t bch = blockIdx.y;
+  const int64_t g = (int64_t)blockIdx.x * kThreadsGp + threadIdx.x;
+  const int64_t s = g * RUN, e = min(s + RUN, N);
+  const double *yb = y + bch * N;
+  if (s < e) {
+    prefetch_run<RUN>(t + s);
+    prefetch_run<RUN>(diag + s);
+    prefetch_run<RUN>(yb + s);
+  }
+  const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
+  const double jit = jitter ? jitter[bch] : 0.0;
   double acc = 0.0;
-  if (len > 0) {
-    double m0 = 0.0, m1 = 0.0, P00 = k.a, P01 = 0.0, P11 = k.a * k.w2;  // the stationary prior
-    agg_apply(excl, m0, m1, P00, P01, P11);               // ... entering the tile
-    if (lane > 0) agg_apply(pre, m0, m1, P00, P01, P11);  // ... entering this lane's run
-    double Z00 = k.a - P00, Z01 = -P01, Z11 = k.a * k.w2 - P11;  // Z = Sigma_inf - P
-    double tprev = t_before;
+  if (s < e) {
+    const double *st = cta_state + (bch * gridDim.x + blockIdx.x) * 5;
+    double m0 = st[0], m1 = st[1], Z00 = st[2], Z01 = st[3], Z11 = st[4];
+    if (threadIdx.x > 0) {
+      double P00 = k.a - Z00, P01 = -Z01, P11 = k.a * k.w2 - Z11;
+      Agg pre = agg_load(pref + (bch * T + g - 1) * kAggDoubles);
+      agg_apply(pre, m0, m1, P00, P01, P11);
+      Z00 = k.a - P00;
+      Z01 = -P01;
+      Z11 = k.a * k.w2 - P11;
+    }
+    double tprev = s > 0 ? __ldg(t + s - 1) : __ldg(t);
+    double tn = __ldg(t + s), dn = __ldg(diag + s), yn = __ldg(yb + s);
     ShoCache cc;
     LogProd lp;
 #pragma unroll 1
-    for (int i = 0; i < len; ++i) {
-      const double ti = ts[i];
+    for (int64_t i = s; i < e; ++i) {
+      const double ti = tn, di = dn + jit, yi = yn;
+      if (i + 1 < e) {
+        tn = __ldg(t + i + 1);
+        dn = __ldg(diag + i + 1);
+        yn = __ldg(yb + i + 1);
+      }
       double f00, f01, f10, f11;
       sho_phi(k, ti - tprev, cc, f00, f01, f10, f11);
       tprev = ti;
-      if (REC == 2 && (i % kRunB) == 0) {  // state entering every run of kRunB cadences: where the reverse pass restarts
-        double *rb = rec + bch * 5 * Tb + (s + i) / kRunB;
+      if (REC == 2 && ((i - s) % kRunB) == 0) {  // state entering every run of kRunB cadences: where the reverse pass restarts
+        double *rb = rec + bch * 5 * Tb + i / kRunB;
         rb[0] = m0;
         rb[Tb] = m1;
         rb[2 * Tb] = Z00;
@@ -503,20 +434,20 @@ __global__ void __launch_bounds__(32, XO_GP_MINBLOCKS)
       double z10 = f10 * Z00 + f11 * Z01, z11 = f10 * Z01 + f11 * Z11;
       double p00 = z00 * f00 + z01 * f01, p01 = z00 * f10 + z01 * f11, p11 = z10 * f10 + z11 * f11;
       const double pm = k.a - p00;
-      const double D = pm + ds[i];
+      const double D = pm + di;
       const double rD = xo::rcp_fast(D);
       const double K0 = pm * rD, K1 = -p01 * rD;
-      const double vv = ys[i] - c0;
-      acc = fma(vv * vv, rD, acc);
+      const double v = yi - c0;
+      acc = fma(v * v, rD, acc);
       lp.mul(D);
       if (REC == 1) {  // what the backward (disturbance-smoother) pass needs
-        double *rb = rec + bch * 3 * N + s + i;
-        rb[0] = vv * rD;
-        rb[N] = K0;
-        rb[2 * N] = K1;
+        double *rb = rec + bch * 3 * N;
+        rb[i] = v * rD;
+        rb[N + i] = K0;
+        rb[2 * N + i] = K1;
       }
-      m0 = fma(K0, vv, c0);
-      m1 = fma(K1, vv, c1);
+      m0 = fma(K0, v, c0);
+      m1 = fma(K1, v, c1);
       Z00 = fma(D * K0, K0, p00);
       Z01 = fma(D * K0, K1, p01);
       Z11 = fma(D * K1, K1, p11);
@@ -524,22 +455,28 @@ __global__ void __launch_bounds__(32, XO_GP_MINBLOCKS)
     acc += lp.value();
     if (!isfinite(acc)) atomicAdd(&status->bad_lanes, 1ull);
   }
-  // 5. tile sum in a fixed order; the last tile of the chain folds the per-tile sums in tile order
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(kFullGp, acc, o);
-  int is_last = 0;
-  if (lane == 0) {
-    cta_ll[(size_t)bch * tiles + tile] = acc;
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s4 = 0.0;
+    for (int w = 0; w < kWarpsGp; ++w) s4 += red[w];
+    cta_ll[bch * gridDim.x + blockIdx.x] = s4;
     __threadfence();
-    is_last = atomicAdd(&counters[1 + bch], 1u) == (unsigned)(tiles - 1);
+    is_last = atomicAdd(&done[bch], 1u) == gridDim.x - 1;
   }
-  if (__shfl_sync(kFullGp, is_last, 0)) {
+  __syncthreads();
+  if (is_last && threadIdx.x < 32) {  // the last CTA of the chain folds the per-CTA sums in CTA order (bit-reproducible)
     __threadfence();
     double tot = 0.0;
-    for (int i = lane; i < tiles; i += 32) tot += __ldcg(cta_ll + (size_t)bch * tiles + i);
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) tot += __ldcg(cta_ll + bch * gridDim.x + i);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(kFullGp, tot, o);
-    if (lane == 0) loglike[bch] = -0.5 * tot - 0.5 * (double)N * 1.8378770664093454835606594728112;  // log(2 pi)
+    if (threadIdx.x == 0) {
+      loglike[bch] = -0.5 * tot - 0.5 * (double)N * 1.8378770664093454835606594728112;  // log(2 pi)
+      done[bch] = 0u;  // the reverse pass counts its CTAs in the same word
+    }
   }
 }
 
@@ -778,6 +715,43 @@ __device__ __forceinline__ void adj_apply(const Adj &a, double (&L)[5]) {
   L[4] = z[2];
 }
 
+__device__ __forceinline__ Adj adj_shfl_up(const Adj &a, int d) {
+  Adj o;
+  const double *src = a.A;
+  double *dst = o.A;
+#pragma unroll
+  for (int k = 0; k < kAdjDoubles; ++k) dst[k] = __shfl_up_sync(kFullGp, src[k], d);
+  return o;
+}
+__device__ __forceinline__ void adj_store(double *p, const Adj &a) {
+  const double *src = a.A;
+#pragma unroll
+  for (int k = 0; k < kAdjDoubles; ++k) p[k] = src[k];
+}
+__device__ __forceinline__ Adj adj_load(const double *p) {
+  Adj a;
+  double *dst = a.A;
+#pragma unroll
+  for (int k = 0; k < kAdjDoubles; ++k) dst[k] = p[k];
+  return a;
+}
+__device__ Adj adj_cta_inclusive_scan(Adj v, Adj *warp_tot) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 1
+  for (int d = 1; d < 32; d <<= 1) {
+    Adj o = adj_shfl_up(v, d);
+    if (lane >= d) v = adj_after(o, v);
+  }
+  if (lane == 31) warp_tot[warp] = v;
+  __syncthreads();
+  if (warp > 0) {
+    Adj pre = warp_tot[0];
+    for (int w = 1; w < warp; ++w) pre = adj_after(pre, warp_tot[w]);
+    v = adj_after(pre, v);
+  }
+  return v;
+}
+
 // forward quantities of step i, recomputed from the recorded state entering it
 struct StepFwd {
   double f00, f01, f10, f11, Cf, Sf, dt;
@@ -845,117 +819,83 @@ __device__ __forceinline__ void gp_step_adj(const StepFwd &s, double (&L)[5], do
   }
 }
 
-struct AdjOps {
-  using E = Adj;
-  static constexpr int kDoubles = kAdjDoubles;
-  static __device__ __forceinline__ E identity() { return adj_identity(); }
-  static __device__ __forceinline__ E combine(const E &earlier, const E &later) { return adj_after(earlier, later); }
-  static __device__ __forceinline__ double *data(E &e) { return e.A; }
-  static __device__ __forceinline__ const double *data(const E &e) { return e.A; }
+// ---- reverse (adjoint) pass: three kernels, thread g owns run T-1-g of kRunB cadences ---------------------------
+// The forward pass leaves only the state entering every run of kRunB cadences (5 doubles per run: 5 B per cadence instead
+// of the 40 B per cadence of a per-step record); each thread re-derives the states inside its run into shared memory
+// (thread-contiguous, conflict-free) before walking the run backwards.
+struct RunStates {
+  double st[5][kRunB][kThreadsGp];
 };
+// states entering every step of run [s, e) of chain bch -> R.st[.][i][tid]
+__device__ __forceinline__ void gp_rederive(const Sho &k, const double *__restrict__ t, const double *__restrict__ yb,
+                                            const double *__restrict__ diag, double jit, const double *__restrict__ rp, int64_t Tb,
+                                            int64_t s, int64_t e, RunStates &R) {
+  const int tid = threadIdx.x;
+  double m0 = __ldg(rp), m1 = __ldg(rp + Tb), Z00 = __ldg(rp + 2 * Tb), Z01 = __ldg(rp + 3 * Tb), Z11 = __ldg(rp + 4 * Tb);
+  double tprev = s > 0 ? __ldg(t + s - 1) : __ldg(t);
+  ShoCache cc;
+#pragma unroll 1
+  for (int64_t i = s; i < e; ++i) {
+    const int j = (int)(i - s);
+    R.st[0][j][tid] = m0;
+    R.st[1][j][tid] = m1;
+    R.st[2][j][tid] = Z00;
+    R.st[3][j][tid] = Z01;
+    R.st[4][j][tid] = Z11;
+    if (i + 1 == e) break;
+    const double ti = __ldg(t + i);
+    double f00, f01, f10, f11;
+    sho_phi(k, ti - tprev, cc, f00, f01, f10, f11);
+    tprev = ti;
+    double c0 = f00 * m0 + f01 * m1, c1 = f10 * m0 + f11 * m1;
+    double z00 = f00 * Z00 + f01 * Z01, z01 = f00 * Z01 + f01 * Z11;
+    double z10 = f10 * Z00 + f11 * Z01, z11 = f10 * Z01 + f11 * Z11;
+    double p00 = z00 * f00 + z01 * f01, p01 = z00 * f10 + z01 * f11, p11 = z10 * f10 + z11 * f11;
+    const double pm = k.a - p00;
+    const double D = pm + __ldg(diag + i) + jit;
+    const double rD = xo::rcp_fast(D);
+    const double K0 = pm * rD, K1 = -p01 * rD;
+    const double vv = __ldg(yb + i) - c0;
+    m0 = fma(K0, vv, c0);
+    m1 = fma(K1, vv, c1);
+    Z00 = fma(D * K0, K0, p00);
+    Z01 = fma(D * K0, K1, p01);
+    Z11 = fma(D * K1, K1, p11);
+  }
+}
+__device__ __forceinline__ StepFwd gp_step_at(const Sho &k, const double *__restrict__ t, const double *__restrict__ yb,
+                                              const double *__restrict__ diag, double jit, int64_t s, int64_t i, const RunStates &R,
+                                              ShoCache &cc) {
+  const int tid = threadIdx.x, j = (int)(i - s);
+  const double dt = i > 0 ? __ldg(t + i) - __ldg(t + i - 1) : 0.0;
+  return gp_step_fwd(k, dt, __ldg(yb + i), __ldg(diag + i) + jit, R.st[0][j][tid], R.st[1][j][tid], R.st[2][j][tid], R.st[3][j][tid],
+                     R.st[4][j][tid], cc);
+}
 
-// ---- one-pass reverse (adjoint) scan -------------------------------------------
-// Same structure as the forward scan, run right-to-left: ticket -> (chain, reverse tile), lane l owns time-run
-// 31 - l of a tile of kTileB = 32 x 8 cadences, so lane order = scan order.  The forward pass left only the state
-// entering every run of 8 cadences (5 doubles per run, 5 B per cadence instead of 40); each lane re-derives the
-// states inside its run into shared memory (lane-contiguous, conflict-free) and walks the run backwards twice:
-// once pushing the origin and the five basis vectors (the run's affine map), once -- after the warp scan and the
-// tree look-back over earlier tiles -- with the known incoming lambda, accumulating the hyper-parameter cotangents
-// and emitting d/dy, d/d diag through shared memory (coalesced stores).  The last tile of a chain to finish folds
-// the per-tile sums in tile order and chains (a, c, h, w2) -> (S0, w0, Q).
-constexpr int kTileB = 32 * kRunB;
-constexpr int kPitchB = kRunB + 1;
-
-__global__ void __launch_bounds__(32, 12)
-    gp_backward_kernel(const double *__restrict__ t, const double *__restrict__ y, const double *__restrict__ diag, int64_t N,
-                       const double *__restrict__ S0, const double *__restrict__ w0, const double *__restrict__ Qf,
-                       const double *__restrict__ jitter, double eps, int64_t Tb,
-                       const double *__restrict__ rs /* [B][5][Tb] run-start states */, unsigned *__restrict__ counters,
-                       const TreeBuffers tb, double *__restrict__ gpart /* [B][tiles][6] */, GpStatus *__restrict__ status,
-                       double *__restrict__ gy, double *__restrict__ gdiag, double *__restrict__ ghyper /* [B][3] */,
-                       double *__restrict__ gsum /* [B][2] or null */) {
-  __shared__ double st[32 * kPitchB];
-  __shared__ double sd[32 * kPitchB];        // diag in, d loglike / d diag out
-  __shared__ double sy[32 * kPitchB];        // y in, d loglike / d y out
-  __shared__ double sst[5][kRunB][32];       // state entering every step of every run
-  const int lane = threadIdx.x;
-  unsigned ticket = 0u;
-  if (lane == 0) ticket = atomicAdd(&counters[0], 1u);
-  ticket = __shfl_sync(kFullGp, ticket, 0);
-  const int tiles = tb.n0;
-  const int64_t bch = ticket / (unsigned)tiles;
-  const int rtile = (int)(ticket % (unsigned)tiles);  // 0 = the LAST tile in time
-  const int ttile = tiles - 1 - rtile;
+__global__ void __launch_bounds__(kThreadsGp, 3)
+    gp_grad_aggregate_kernel(const double *__restrict__ t, const double *__restrict__ y, const double *__restrict__ diag, int64_t N,
+                             const double *__restrict__ S0, const double *__restrict__ w0, const double *__restrict__ Qf,
+                             const double *__restrict__ jitter, double eps, int64_t T, const double *__restrict__ rs,
+                             double *__restrict__ gpref, double *__restrict__ gcta) {
+  __shared__ RunStates R;
+  __shared__ Adj warp_tot[kWarpsGp];
+  const int64_t bch = blockIdx.y;
   const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
   const double jit = jitter ? jitter[bch] : 0.0;
-  const int64_t base = (int64_t)ttile * kTileB;
-  const int nvalid = (int)min((int64_t)kTileB, N - base);
-  const double *yb = y + bch * N;
-#pragma unroll 4
-  for (int idx = lane; idx < kTileB; idx += 32) {
-    const int at = (idx / kRunB) * kPitchB + idx % kRunB;
-    if (idx < nvalid) {
-      st[at] = __ldg(t + base + idx);
-      sd[at] = __ldg(diag + base + idx) + jit;
-      sy[at] = __ldg(yb + base + idx);
-    }
-  }
-  const double t_halo = __ldg(t + (base > 0 ? base - 1 : 0));
-  __syncwarp();
-  const int r = 31 - lane;  // time-run inside the tile
-  const int64_t s = base + (int64_t)r * kRunB;
-  const int len = (int)max((int64_t)0, min((int64_t)kRunB, N - s));
-  double *ts = st + r * kPitchB, *ds = sd + r * kPitchB, *ys = sy + r * kPitchB;
-  const double t_before = r > 0 ? st[(r - 1) * kPitchB + kRunB - 1] : t_halo;
-  // states entering every step of the run, re-derived from the run-start state the forward pass left
-  if (len > 0) {
-    const int64_t run = s / kRunB;
-    const double *rp = rs + (size_t)bch * 5 * Tb + run;
-    double m0 = __ldg(rp), m1 = __ldg(rp + Tb), Z00 = __ldg(rp + 2 * Tb), Z01 = __ldg(rp + 3 * Tb), Z11 = __ldg(rp + 4 * Tb);
-    double tprev = t_before;
-    ShoCache cc;
-#pragma unroll 1
-    for (int i = 0; i < len; ++i) {
-      sst[0][i][lane] = m0;
-      sst[1][i][lane] = m1;
-      sst[2][i][lane] = Z00;
-      sst[3][i][lane] = Z01;
-      sst[4][i][lane] = Z11;
-      if (i + 1 == len) break;
-      const double ti = ts[i];
-      double f00, f01, f10, f11;
-      sho_phi(k, ti - tprev, cc, f00, f01, f10, f11);
-      tprev = ti;
-      double c0 = f00 * m0 + f01 * m1, c1 = f10 * m0 + f11 * m1;
-      double z00 = f00 * Z00 + f01 * Z01, z01 = f00 * Z01 + f01 * Z11;
-      double z10 = f10 * Z00 + f11 * Z01, z11 = f10 * Z01 + f11 * Z11;
-      double p00 = z00 * f00 + z01 * f01, p01 = z00 * f10 + z01 * f11, p11 = z10 * f10 + z11 * f11;
-      const double pm = k.a - p00;
-      const double D = pm + ds[i];
-      const double rD = xo::rcp_fast(D);
-      const double K0 = pm * rD, K1 = -p01 * rD;
-      const double vv = ys[i] - c0;
-      m0 = fma(K0, vv, c0);
-      m1 = fma(K1, vv, c1);
-      Z00 = fma(D * K0, K0, p00);
-      Z01 = fma(D * K0, K1, p01);
-      Z11 = fma(D * K1, K1, p11);
-    }
-  }
-  auto step_fwd = [&](int i, ShoCache &cc) {
-    const double tp = i > 0 ? ts[i - 1] : t_before;
-    return gp_step_fwd(k, ts[i] - tp, ys[i], ds[i], sst[0][i][lane], sst[1][i][lane], sst[2][i][lane], sst[3][i][lane],
-                       sst[4][i][lane], cc);
-  };
-  // the run's map lambda_{e-1} -> lambda_{s-1}: push the origin (with the forcing) and the five basis vectors through it
+  const int64_t g = (int64_t)blockIdx.x * kThreadsGp + threadIdx.x;
+  const int64_t run = T - 1 - g;  // reversed ownership
   Adj v = adj_identity();
-  if (len > 0) {
+  if (run >= 0) {
+    const int64_t s = run * kRunB, e = min(s + kRunB, N);
+    const double *yb = y + bch * N;
+    gp_rederive(k, t, yb, diag, jit, rs + (size_t)bch * 5 * T + run, T, s, e, R);
+    // the run's map lambda_{e-1} -> lambda_{s-1}: push the origin (with the forcing) and the five basis vectors through it
     double O[5] = {0, 0, 0, 0, 0}, X0[5] = {1, 0, 0, 0, 0}, X1[5] = {0, 1, 0, 0, 0}, X2[5] = {0, 0, 1, 0, 0},
            X3[5] = {0, 0, 0, 1, 0}, X4[5] = {0, 0, 0, 0, 1};
     ShoCache cc;
 #pragma unroll 1
-    for (int i = len - 1; i >= 0; --i) {
-      const StepFwd f = step_fwd(i, cc);
+    for (int64_t i = e - 1; i >= s; --i) {
+      const StepFwd f = gp_step_at(k, t, yb, diag, jit, s, i, R, cc);
       gp_step_adj<true, false>(f, O, nullptr);
       gp_step_adj<false, false>(f, X0, nullptr);
       gp_step_adj<false, false>(f, X1, nullptr);
@@ -976,27 +916,78 @@ __global__ void __launch_bounds__(32, 12)
     v.om[0] = O[0];
     v.om[1] = O[1];
   }
-  v = warp_inclusive_scan<AdjOps>(v);
-  const Adj pre = elem_shfl_up<AdjOps>(v, 1);
-  bool ok = true;
-  const Adj excl = tree_exclusive<AdjOps>(tb.chain(bch, kAdjDoubles), rtile, elem_shfl<AdjOps>(v, 31), ok);
-  if (!__all_sync(kFullGp, ok) && lane == 0) atomicAdd(&status->wait_failures, 1ull);
+  v = adj_cta_inclusive_scan(v, warp_tot);
+  if (g < T) adj_store(gpref + (bch * T + g) * kAdjDoubles, v);
+  if (threadIdx.x == kThreadsGp - 1) adj_store(gcta + (bch * gridDim.x + blockIdx.x) * kAdjDoubles, v);
+}
+
+// lambda entering each CTA (from the right): exclusive scan of the CTA totals applied to lambda = 0
+__global__ void __launch_bounds__(kThreadsGp) gp_grad_cta_scan_kernel(const double *__restrict__ gcta, int nctas,
+                                                                      double *__restrict__ gstate) {
+  __shared__ Adj warp_tot[kWarpsGp];
+  __shared__ Adj lastlane[kWarpsGp];
+  __shared__ Adj carry_s;
+  const int64_t bch = blockIdx.x;
+  Adj carry = adj_identity();
+  for (int base = 0; base < nctas; base += kThreadsGp) {
+    const int idx = base + threadIdx.x;
+    Adj v = idx < nctas ? adj_load(gcta + (bch * nctas + idx) * kAdjDoubles) : adj_identity();
+    v = adj_cta_inclusive_scan(v, warp_tot);
+    Adj incl = adj_after(carry, v);
+    Adj prev = adj_shfl_up(incl, 1);
+    if ((threadIdx.x & 31) == 31) lastlane[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) prev = threadIdx.x == 0 ? carry : lastlane[(threadIdx.x >> 5) - 1];
+    if (idx < nctas) {
+      double *o = gstate + (bch * nctas + idx) * 5;
+      o[0] = prev.om[0];
+      o[1] = prev.om[1];
+      o[2] = prev.oz[0];
+      o[3] = prev.oz[1];
+      o[4] = prev.oz[2];
+    }
+    if (threadIdx.x == kThreadsGp - 1) carry_s = incl;
+    __syncthreads();
+    carry = carry_s;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kThreadsGp, 3)
+    gp_grad_final_kernel(const double *__restrict__ t, const double *__restrict__ y, const double *__restrict__ diag, int64_t N,
+                         const double *__restrict__ S0, const double *__restrict__ w0, const double *__restrict__ Qf,
+                         const double *__restrict__ jitter, double eps, int64_t T, const double *__restrict__ rs,
+                         const double *__restrict__ gpref, const double *__restrict__ gstate, double *__restrict__ gy,
+                         double *__restrict__ gdiag, double *__restrict__ gpart /* [B][nctas][6] */, unsigned *__restrict__ done,
+                         GpStatus *__restrict__ status, double *__restrict__ ghyper /* [B][3] */,
+                         double *__restrict__ gsum /* [B][2] or null */) {
+  __shared__ RunStates R;
+  __shared__ double red[6][kWarpsGp];
+  __shared__ int is_last;
+  const int64_t bch = blockIdx.y;
+  const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
+  const double jit = jitter ? jitter[bch] : 0.0;
+  const int64_t g = (int64_t)blockIdx.x * kThreadsGp + threadIdx.x;
+  const int64_t run = T - 1 - g;
   double ga = 0.0, gc = 0.0, gh = 0.0, gw2 = 0.0;  // cotangents of a, c, h and w2 = c^2 +- h^2
-  double sy_ = 0.0, sd_ = 0.0;                      // sums of d/dy and d/d diag over the run
-  if (len > 0) {
-    // the tree's map applied to lambda = 0 beyond the last cadence, then the in-warp prefix
-    double L[5] = {excl.om[0], excl.om[1], excl.oz[0], excl.oz[1], excl.oz[2]};
-    if (lane > 0) adj_apply(pre, L);
+  double sy = 0.0, sd = 0.0;                        // sums of d/dy and d/d diag over the run
+  if (run >= 0) {
+    const int64_t s = run * kRunB, e = min(s + kRunB, N);
+    const double *yb = y + bch * N;
+    gp_rederive(k, t, yb, diag, jit, rs + (size_t)bch * 5 * T + run, T, s, e, R);
+    const double *st = gstate + (bch * gridDim.x + blockIdx.x) * 5;
+    double Lm[5] = {st[0], st[1], st[2], st[3], st[4]};
+    if (threadIdx.x > 0) adj_apply(adj_load(gpref + (bch * T + g - 1) * kAdjDoubles), Lm);
     ShoCache cc;
 #pragma unroll 1
-    for (int i = len - 1; i >= 0; --i) {
-      const StepFwd f = step_fwd(i, cc);
+    for (int64_t i = e - 1; i >= s; --i) {
+      const StepFwd f = gp_step_at(k, t, yb, diag, jit, s, i, R, cc);
       double acc[7];
-      gp_step_adj<true, true>(f, L, acc);
-      ys[i] = acc[0];  // d / d y_i     (y_i, diag_i are dead from here on: every step reads its own only)
-      ds[i] = acc[1];  // d / d diag_i
-      sy_ += acc[0];
-      sd_ += acc[1];
+      gp_step_adj<true, true>(f, Lm, acc);
+      if (gy) gy[bch * N + i] = acc[0];        // a thread's run is two full 32-byte sectors of each output
+      if (gdiag) gdiag[bch * N + i] = acc[1];
+      sy += acc[0];
+      sd += acc[1];
       ga += acc[2];
       // Phi = [[Cf + c Sf, Sf], [-w2 Sf, Cf - c Sf]]
       const double d0011 = acc[3] - acc[6];
@@ -1009,38 +1000,34 @@ __global__ void __launch_bounds__(32, 12)
     }
     if (!isfinite(ga + gc + gh + gw2)) atomicAdd(&status->bad_lanes, 1ull);
   }
-  double vals[6] = {ga, gc, gh, gw2, sy_, sd_};
+  double vals[6] = {ga, gc, gh, gw2, sy, sd};
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
+    double x = vals[j];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) vals[j] += __shfl_xor_sync(kFullGp, vals[j], o);
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFullGp, x, o);
+    if ((threadIdx.x & 31) == 0) red[j][threadIdx.x >> 5] = x;
   }
-  __syncwarp();
-  // per-cadence gradients out, coalesced
-  if (gy || gdiag) {
-#pragma unroll 4
-    for (int idx = lane; idx < kTileB; idx += 32) {
-      if (idx < nvalid) {
-        const int at = (idx / kRunB) * kPitchB + idx % kRunB;
-        if (gy) gy[bch * N + base + idx] = sy[at];
-        if (gdiag) gdiag[bch * N + base + idx] = sd[at];
-      }
-    }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double s4 = 0.0;
+    for (int w = 0; w < kWarpsGp; ++w) s4 += red[threadIdx.x][w];
+    gpart[(bch * gridDim.x + blockIdx.x) * 6 + threadIdx.x] = s4;
   }
-  int is_last = 0;
-  if (lane == 0) {
-#pragma unroll
-    for (int j = 0; j < 6; ++j) gpart[((size_t)bch * tiles + rtile) * 6 + j] = vals[j];
+  __syncthreads();
+  if (threadIdx.x == 0) {
     __threadfence();
-    is_last = atomicAdd(&counters[1 + bch], 1u) == (unsigned)(tiles - 1);
+    is_last = atomicAdd(&done[bch], 1u) == gridDim.x - 1;
   }
-  if (__shfl_sync(kFullGp, is_last, 0)) {
-    // fold the per-tile cotangents of (a, c, h, w2) in tile order and chain them to (S0, w0, Q):
+  __syncthreads();
+  if (is_last && threadIdx.x < 32) {
+    // fold the per-CTA cotangents of (a, c, h, w2) in CTA order and chain them to (S0, w0, Q):
     //   a = S0 w0 Q,  c = w0 / (2Q),  h = c f,  f = sqrt(max(+-(4Q^2 - 1), eps)),  w2 = c^2 +- h^2
     __threadfence();
+    const int lane = threadIdx.x;
     double fa = 0.0, fc = 0.0, fh = 0.0, fw2 = 0.0, fy = 0.0, fd = 0.0;
-    for (int i = lane; i < tiles; i += 32) {
-      const double *p = gpart + ((size_t)bch * tiles + i) * 6;
+    for (int i = lane; i < (int)gridDim.x; i += 32) {
+      const double *p = gpart + (bch * gridDim.x + i) * 6;
       fa += __ldcg(p);
       fc += __ldcg(p + 1);
       fh += __ldcg(p + 2);
@@ -1057,11 +1044,11 @@ __global__ void __launch_bounds__(32, 12)
       fy += __shfl_xor_sync(kFullGp, fy, o);
       fd += __shfl_xor_sync(kFullGp, fd, o);
     }
-    if (lane == 0 && gsum) {
-      gsum[2 * bch] = fy;
-      gsum[2 * bch + 1] = fd;
-    }
     if (lane == 0) {
+      if (gsum) {
+        gsum[2 * bch] = fy;
+        gsum[2 * bch + 1] = fd;
+      }
       const double sgn = k.under ? 1.0 : -1.0;
       fc += 2.0 * k.c * fw2;
       fh += sgn * 2.0 * k.h * fw2;
@@ -1073,24 +1060,39 @@ __global__ void __launch_bounds__(32, 12)
       ghyper[3 * bch + 0] = fa * w * Q;
       ghyper[3 * bch + 1] = fa * s0 * Q + fc * (0.5 / Q) + fh * (0.5 / Q) * f;
       ghyper[3 * bch + 2] = fa * s0 * w + fc * dcdQ + fh * (dcdQ * f + k.c * dfdQ);
+      done[bch] = 0u;
     }
   }
 }
 
-struct TreeOffsets {  // byte offsets of one tree's scratch inside the workspace
-  int n0, n1, n2;
-  size_t off_counters, off_f0, off_f1, off_f2, off_e0, off_e1, off_e2;
-};
 struct GpLayout {
-  TreeOffsets fwd, bwd;  // forward: tiles of kTile cadences; reverse (adjoint): tiles of kTileB cadences
-  int64_t Tb;            // runs of kRunB cadences per chain
-  int nctas_b;           // smoother pass (three-kernel form): CTAs per chain
-  size_t zero_bytes;     // status word + counters + flags at the head of the workspace: cleared before every call
-  size_t off_ll, off_rs, off_gpart;
-  size_t off_rec, off_bpref, off_bcta, off_bstate, bytes;
+  int run;         // cadences per thread of the forward pass (16, or XO_GP_RUN_LONG when there is parallelism to spare)
+  int64_t T;       // runs (threads) per chain
+  int nctas;       // CTAs per chain
+  int64_t Tb;      // the same for the reverse passes (runs of kRunB)
+  int nctas_b;
+  size_t off_done, off_pref, off_tot, off_state, off_ll, off_rec, off_bpref, off_bcta, off_bstate, off_rs, off_gpref, off_gcta, off_gstate,
+      off_gpart, bytes;
 };
+inline int gp_run_length(int64_t N, int64_t B) {
+  // the long run halves the in-CTA scan work per cadence but also the number of threads: take it when the launch still
+  // fills the machine twice over (148 SMs x 4 CTAs of 128 threads)
+  static const int forced = [] {
+    const char *v = getenv("XO_GP_RUN");
+    return v && *v ? atoi(v) : 0;
+  }();
+  if (forced == kRun || forced == XO_GP_RUN_LONG) return forced;
+  const double ctas_long = (double)B * (double)((N + XO_GP_RUN_LONG - 1) / XO_GP_RUN_LONG) / kThreadsGp;
+  return ctas_long >= 2.0 * 4.0 * xo::sm_count() ? XO_GP_RUN_LONG : kRun;
+}
 inline GpLayout gp_layout(int64_t N, int64_t B, bool solve = false, bool grad = false) {
   GpLayout L;
+  L.run = gp_run_length(N, B);
+  // sized for the short run (the larger scratch), so that a workspace query does not depend on the run picked later
+  const int64_t Tmax = (N + kRun - 1) / kRun;
+  const int nctas_max = (int)((Tmax + kThreadsGp - 1) / kThreadsGp);
+  L.T = (N + L.run - 1) / L.run;
+  L.nctas = (int)((L.T + kThreadsGp - 1) / kThreadsGp);
   L.Tb = (N + kRunB - 1) / kRunB;
   L.nctas_b = (int)((L.Tb + kThreadsGp - 1) / kThreadsGp);
   size_t o = 256;  // GpStatus
@@ -1100,29 +1102,11 @@ inline GpLayout gp_layout(int64_t N, int64_t B, bool solve = false, bool grad = 
     return at;
   };
   auto take = [&](size_t n) { return take_bytes(n * sizeof(double)); };
-  auto tree_counts = [&](TreeOffsets &T, int64_t tile) {
-    T.n0 = (int)((N + tile - 1) / tile);
-    T.n1 = (T.n0 + 31) / 32;
-    T.n2 = (T.n1 + 31) / 32;
-  };
-  auto tree_flags = [&](TreeOffsets &T) {
-    T.off_counters = take_bytes((size_t)(1 + B) * sizeof(unsigned));
-    T.off_f0 = take_bytes((size_t)B * T.n0 * sizeof(unsigned));
-    T.off_f1 = take_bytes((size_t)B * T.n1 * sizeof(unsigned));
-    T.off_f2 = take_bytes((size_t)B * T.n2 * sizeof(unsigned));
-  };
-  auto tree_elems = [&](TreeOffsets &T, int doubles) {
-    T.off_e0 = take((size_t)B * T.n0 * doubles);
-    T.off_e1 = take((size_t)B * T.n1 * doubles);
-    T.off_e2 = take((size_t)B * T.n2 * doubles);
-  };
-  tree_counts(L.fwd, kTile);
-  tree_counts(L.bwd, kTileB);
-  tree_flags(L.fwd);
-  if (grad) tree_flags(L.bwd);
-  L.zero_bytes = o;
-  tree_elems(L.fwd, kAggDoubles);
-  L.off_ll = take((size_t)B * L.fwd.n0);
+  L.off_done = take_bytes((size_t)B * sizeof(unsigned));
+  L.off_pref = take((size_t)B * Tmax * kAggDoubles);
+  L.off_tot = take((size_t)B * nctas_max * kAggDoubles);
+  L.off_state = take((size_t)B * nctas_max * 5);
+  L.off_ll = take((size_t)B * nctas_max);
   L.off_rec = L.off_bpref = L.off_bcta = L.off_bstate = 0;
   if (solve) {
     L.off_rec = take((size_t)B * 3 * N);
@@ -1130,30 +1114,41 @@ inline GpLayout gp_layout(int64_t N, int64_t B, bool solve = false, bool grad = 
     L.off_bcta = take((size_t)B * L.nctas_b * 6);
     L.off_bstate = take((size_t)B * L.nctas_b * 2);
   }
-  L.off_rs = L.off_gpart = 0;
+  L.off_rs = L.off_gpref = L.off_gcta = L.off_gstate = L.off_gpart = 0;
   if (grad) {
     L.off_rs = take((size_t)B * 5 * L.Tb);
-    tree_elems(L.bwd, kAdjDoubles);
-    L.off_gpart = take((size_t)B * L.bwd.n0 * 6);
+    L.off_gpref = take((size_t)B * L.Tb * kAdjDoubles);
+    L.off_gcta = take((size_t)B * L.nctas_b * kAdjDoubles);
+    L.off_gstate = take((size_t)B * L.nctas_b * 5);
+    L.off_gpart = take((size_t)B * L.nctas_b * 6);
   }
   L.bytes = o;
   return L;
 }
-inline TreeBuffers tree_buffers(char *ws, const TreeOffsets &T) {
-  auto d = [&](size_t off) { return reinterpret_cast<double *>(ws + off); };
-  auto u = [&](size_t off) { return reinterpret_cast<unsigned *>(ws + off); };
-  return TreeBuffers{d(T.off_e0), d(T.off_e1), d(T.off_e2), u(T.off_f0), u(T.off_f1), u(T.off_f2), T.n0, T.n1, T.n2};
-}
 
-// the one-pass forward scan: clear status/counters/flags (one stream-ordered memset), one kernel
+// the forward scan: three stream-ordered kernels (the last one folds the per-CTA sums)
 template <int REC>
 int gp_forward(const double *t, const double *y, const double *diag, int64_t N, const double *S0, const double *w0, const double *Q,
                const double *jitter, int64_t B, double eps, double *loglike, double *rec, char *ws, const GpLayout &L, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(ws, 0, L.zero_bytes, st);
-  if (e != cudaSuccess) return -(int)e;
-  xo::launch(gp_forward_kernel<REC>, dim3((unsigned)((size_t)B * L.fwd.n0)), dim3(32), 0, st, t, y, diag, N, S0, w0, Q, jitter, eps,
-             reinterpret_cast<unsigned *>(ws + L.fwd.off_counters), tree_buffers(ws, L.fwd), reinterpret_cast<double *>(ws + L.off_ll),
-             reinterpret_cast<GpStatus *>(ws), loglike, rec, L.Tb);
+  auto at = [&](size_t off) { return reinterpret_cast<double *>(ws + off); };
+  unsigned *done = reinterpret_cast<unsigned *>(ws + L.off_done);
+  GpStatus *status = reinterpret_cast<GpStatus *>(ws);
+  dim3 grid(L.nctas, (unsigned)B);
+  if (L.run == kRun) {
+    xo::launch(gp_aggregate_kernel<kRun>, grid, dim3(kThreadsGp), 0, st, t, y, diag, N, S0, w0, Q, jitter, eps, L.T, at(L.off_pref),
+               at(L.off_tot), done, status);
+    xo::launch(gp_cta_scan_kernel, dim3((unsigned)B), dim3(kThreadsGp), 0, st, (const double *)at(L.off_tot), L.nctas, S0, w0, Q, eps,
+               at(L.off_state));
+    xo::launch(gp_loglike_kernel<kRun, REC>, grid, dim3(kThreadsGp), 0, st, t, y, diag, N, S0, w0, Q, jitter, eps, L.T,
+               (const double *)at(L.off_pref), (const double *)at(L.off_state), at(L.off_ll), done, status, loglike, rec, L.Tb);
+  } else {
+    xo::launch(gp_aggregate_kernel<XO_GP_RUN_LONG>, grid, dim3(kThreadsGp), 0, st, t, y, diag, N, S0, w0, Q, jitter, eps, L.T, at(L.off_pref),
+               at(L.off_tot), done, status);
+    xo::launch(gp_cta_scan_kernel, dim3((unsigned)B), dim3(kThreadsGp), 0, st, (const double *)at(L.off_tot), L.nctas, S0, w0, Q, eps,
+               at(L.off_state));
+    xo::launch(gp_loglike_kernel<XO_GP_RUN_LONG, REC>, grid, dim3(kThreadsGp), 0, st, t, y, diag, N, S0, w0, Q, jitter, eps, L.T,
+               (const double *)at(L.off_pref), (const double *)at(L.off_state), at(L.off_ll), done, status, loglike, rec, L.Tb);
+  }
   return 0;
 }
 
@@ -1163,14 +1158,14 @@ namespace xo {
 
 // xo_celerite_sho_grad plus a per-chain jitter term added to diag and the per-chain sums gsum[B][2] =
 // (sum_n d/dy_n, sum_n d/d diag_n): what the joint transit + GP model needs (d/d mean = -gsum[0],
-// d/d jitter = gsum[1]).  Two kernels and one memset, all on `stream`.
+// d/d jitter = gsum[1]).  Six kernels, all on `stream`.
 int celerite_sho_grad_impl(const double *t, const double *y, const double *diag, int64_t N, const double *S0, const double *w0,
                            const double *Q, const double *jitter, int64_t B, double eps, double *loglike, double *ghyper,
                            double *gy, double *gdiag, double *gsum, void *workspace, size_t workspace_bytes, void *stream) {
   if (N < 0 || B < 0) return XO_EINVAL;
   if (B == 0) return 0;
   if (N == 0) return XO_EINVAL;
-  if (B > 65535 || (double)B * (double)((N + kTileB - 1) / kTileB) > 2.0e9) return XO_ERANGE;
+  if (B > 65535) return XO_ERANGE;
   if (!t || !y || !diag || !S0 || !w0 || !Q || !loglike || !ghyper || !workspace) return XO_EINVAL;
   GpLayout L = gp_layout(N, B, false, true);
   if (workspace_bytes < L.bytes) return XO_EWORKSPACE;
@@ -1180,9 +1175,13 @@ int celerite_sho_grad_impl(const double *t, const double *y, const double *diag,
   XO_NVTX_SCOPE("xo_celerite_sho_grad");
   int rc = gp_forward<2>(t, y, diag, N, S0, w0, Q, jitter, B, eps, loglike, at(L.off_rs), ws, L, st);
   if (rc) return rc;
-  xo::launch(gp_backward_kernel, dim3((unsigned)((size_t)B * L.bwd.n0)), dim3(32), 0, st, t, y, diag, N, S0, w0, Q, jitter, eps, L.Tb,
-             (const double *)at(L.off_rs), reinterpret_cast<unsigned *>(ws + L.bwd.off_counters), tree_buffers(ws, L.bwd), at(L.off_gpart),
-             reinterpret_cast<GpStatus *>(ws), gy, gdiag, ghyper, gsum);
+  dim3 gridb(L.nctas_b, (unsigned)B);
+  xo::launch(gp_grad_aggregate_kernel, gridb, dim3(kThreadsGp), 0, st, t, y, diag, N, S0, w0, Q, jitter, eps, L.Tb,
+             (const double *)at(L.off_rs), at(L.off_gpref), at(L.off_gcta));
+  xo::launch(gp_grad_cta_scan_kernel, dim3((unsigned)B), dim3(kThreadsGp), 0, st, (const double *)at(L.off_gcta), L.nctas_b, at(L.off_gstate));
+  xo::launch(gp_grad_final_kernel, gridb, dim3(kThreadsGp), 0, st, t, y, diag, N, S0, w0, Q, jitter, eps, L.Tb, (const double *)at(L.off_rs),
+             (const double *)at(L.off_gpref), (const double *)at(L.off_gstate), gy, gdiag, at(L.off_gpart),
+             reinterpret_cast<unsigned *>(ws + L.off_done), reinterpret_cast<GpStatus *>(ws), ghyper, gsum);
   return xo::launch_status();
 }
 
@@ -1201,7 +1200,7 @@ int xo_celerite_sho_loglike(const double *t, const double *y, const double *diag
   if (N < 0 || B < 0) return XO_EINVAL;
   if (B == 0) return 0;
   if (N == 0) return XO_EINVAL;
-  if ((double)B * (double)((N + kTileB - 1) / kTileB) > 2.0e9) return XO_ERANGE;
+  if (false) return XO_ERANGE;
   if (!t || !y || !diag || !S0 || !w0 || !Q || !loglike || !workspace) return XO_EINVAL;
   XO_NVTX_SCOPE("xo_celerite_sho_loglike");
   GpLayout L = gp_layout(N, B);
@@ -1224,7 +1223,7 @@ int xo_celerite_sho_solve(const double *t, const double *y, const double *diag, 
   if (N < 0 || B < 0) return XO_EINVAL;
   if (B == 0) return 0;
   if (N == 0) return XO_EINVAL;
-  if (B > 65535 || (double)B * (double)((N + kTileB - 1) / kTileB) > 2.0e9) return XO_ERANGE;
+  if (B > 65535 || false) return XO_ERANGE;
   if (!t || !y || !diag || !S0 || !w0 || !Q || !loglike || !alpha || !workspace) return XO_EINVAL;
   GpLayout L = gp_layout(N, B, true);
   if (workspace_bytes < L.bytes) return XO_EWORKSPACE;

@@ -11,7 +11,8 @@
 // Unconstrained vector q[C][D], D = 6 P + 3:
 //   per planet  log period, t0, sqrt(e) cos w, sqrt(e) sin w, b, log(r/R*)
 //   per chain   logit q1, logit q2 (u1 = 2 sqrt(q1) q2, u2 = sqrt(q1)(1 - 2 q2)), mean flux
-// with independent Normal priors prior_mu[D], prior_sigma[D] on q.  R* = M* = 1, m_planet = 0.
+// with independent Normal priors on q: prior_mu / prior_sigma are [D] (prior_chain_stride = 0, shared by the chains) or
+// [C][prior_chain_stride] (one row per chain).  R* = M* = 1, m_planet = 0.
 #include <cuda_runtime.h>
 #include <curand_kernel.h>
 
@@ -110,13 +111,13 @@ __global__ void posterior_unpack_kernel(const double *__restrict__ q, int64_t C,
 // one warp per chain: logp = loglike + log prior, grad = chain rule + prior
 __global__ void posterior_finish_kernel(const double *__restrict__ q, const double *__restrict__ gpar, const double *__restrict__ gstar,
                                         const double *__restrict__ gmean, const double *__restrict__ loglike, int64_t C, int P,
-                                        int D, const double *__restrict__ mu, const double *__restrict__ sigma,
+                                        int D, const double *__restrict__ mu, const double *__restrict__ sigma, int64_t pstride,
                                         double *__restrict__ logp, double *__restrict__ grad) {
   const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
   const int lane = threadIdx.x & 31;
-  const double lpr = warp_sum_s(chain_rule(q + c * D, gpar + c * P * XO_NPAR, gstar + c * XO_NSTAR, gmean[c], P, D, mu, sigma, lane,
-                                           grad + c * D));
+  const double lpr = warp_sum_s(chain_rule(q + c * D, gpar + c * P * XO_NPAR, gstar + c * XO_NSTAR, gmean[c], P, D, mu + c * pstride,
+                                           sigma + c * pstride, lane, grad + c * D));
   if (lane == 0) logp[c] = loglike[c] + lpr;
 }
 
@@ -153,14 +154,14 @@ __global__ void hmc_begin_kernel(const double *__restrict__ q, const double *__r
 __global__ void hmc_leap_kernel(double *__restrict__ qn, const double *__restrict__ gpar, const double *__restrict__ gstar,
                                 const double *__restrict__ gmean, const double *__restrict__ loglike,
                                 const double *__restrict__ eps, const double *__restrict__ inv_mass, int64_t C, int P, int D,
-                                const double *__restrict__ mu, const double *__restrict__ sigma, int is_last,
+                                const double *__restrict__ mu, const double *__restrict__ sigma, int64_t pstride, int is_last,
                                 double *__restrict__ mom, double *__restrict__ logp_n, double *__restrict__ grad_n,
                                 double *__restrict__ par, double *__restrict__ star, double *__restrict__ mean) {
   const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
   const int lane = threadIdx.x & 31;
-  const double lpr = warp_sum_s(chain_rule(qn + c * D, gpar + c * P * XO_NPAR, gstar + c * XO_NSTAR, gmean[c], P, D, mu, sigma, lane,
-                                           grad_n + c * D));
+  const double lpr = warp_sum_s(chain_rule(qn + c * D, gpar + c * P * XO_NPAR, gstar + c * XO_NSTAR, gmean[c], P, D, mu + c * pstride,
+                                           sigma + c * pstride, lane, grad_n + c * D));
   if (lane == 0) logp_n[c] = loglike[c] + lpr;
   __syncwarp();
   const double e = eps[c];
@@ -252,12 +253,13 @@ size_t xo_transit_posterior_workspace(int64_t N, int64_t C, int64_t P) {
 
 int xo_transit_posterior_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *moments,
                                    const double *q, int64_t C, int64_t P, const double *prior_mu, const double *prior_sigma,
-                                   const double *dtk, const double *wk, int K, double texp, int use_in_transit, double lognorm,
+                                   int64_t prior_chain_stride, const double *dtk, const double *wk, int K, double texp, int use_in_transit, double lognorm,
                                    double *logp, double *grad, void *workspace, size_t workspace_bytes, void *stream) {
   if (int rc = xo::check_batch(N, C, P)) return rc;
   if (C == 0) return 0;
   if (N == 0 || P == 0) return XO_EINVAL;
   if (!t || !y || !ivar || !q || !prior_mu || !prior_sigma || !dtk || !wk || !logp || !grad || !workspace) return XO_EINVAL;
+  if (prior_chain_stride != 0 && prior_chain_stride < 6 * P + 3) return XO_EINVAL;
   const SamplerLayout L = sampler_layout(N, C, P);
   if (workspace_bytes < L.bytes) return XO_EWORKSPACE;
   XO_NVTX_SCOPE("xo_transit_posterior_logp_grad");
@@ -272,18 +274,19 @@ int xo_transit_posterior_logp_grad(const double *t, const double *y, const doubl
                                       ws + L.off_model, L.model_bytes, stream);
   if (rc) return rc;
   xo::launch(posterior_finish_kernel, (unsigned)((C + 3) / 4), 128, 0, st, q, at(L.off_gpar), at(L.off_gstar), at(L.off_gmean),
-             at(L.off_ll), C, (int)P, D, prior_mu, prior_sigma, logp, grad);
+             at(L.off_ll), C, (int)P, D, prior_mu, prior_sigma, prior_chain_stride, logp, grad);
   return xo::launch_status();
 }
 
 int xo_hmc_transition(const double *t, const double *y, const double *ivar, int64_t N, const double *moments, int64_t C, int64_t P,
-                      const double *prior_mu, const double *prior_sigma, const double *dtk, const double *wk, int K, double texp,
-                      int use_in_transit, double lognorm, double *q, double *logp, double *grad, const double *eps,
+                      const double *prior_mu, const double *prior_sigma, int64_t prior_chain_stride, const double *dtk, const double *wk,
+                      int K, double texp, int use_in_transit, double lognorm, double *q, double *logp, double *grad, const double *eps,
                       const double *inv_mass, int n_leapfrog, unsigned long long seed, unsigned long long counter,
                       double *accept_prob, double *energy_error, void *workspace, size_t workspace_bytes, void *stream) {
   if (int rc = xo::check_batch(N, C, P)) return rc;
   if (C == 0) return 0;
   if (N == 0 || P == 0 || n_leapfrog < 1) return XO_EINVAL;
+  if (prior_chain_stride != 0 && prior_chain_stride < 6 * P + 3) return XO_EINVAL;
   if (!t || !y || !ivar || !q || !logp || !grad || !eps || !inv_mass || !prior_mu || !prior_sigma || !dtk || !wk || !accept_prob ||
       !energy_error || !workspace)
     return XO_EINVAL;
@@ -304,7 +307,7 @@ int xo_hmc_transition(const double *t, const double *y, const double *ivar, int6
     if (rc) return rc;
     xo::launch(hmc_leap_kernel, grid, 128, 0, st, at(L.off_qn), (const double *)at(L.off_gpar), (const double *)at(L.off_gstar),
                (const double *)at(L.off_gmean), (const double *)at(L.off_ll), eps, inv_mass, C, (int)P, D, prior_mu, prior_sigma,
-               (int)(i + 1 == n_leapfrog), at(L.off_mom), at(L.off_lpn), at(L.off_gn), at(L.off_par), at(L.off_star), at(L.off_mean));
+               prior_chain_stride, (int)(i + 1 == n_leapfrog), at(L.off_mom), at(L.off_lpn), at(L.off_gn), at(L.off_par), at(L.off_star), at(L.off_mean));
   }
   xo::launch(hmc_end_kernel, grid, 128, 0, st, (const double *)at(L.off_qn), (const double *)at(L.off_mom), (const double *)at(L.off_lpn),
              (const double *)at(L.off_gn), (const double *)at(L.off_h0), inv_mass, C, D, seed, counter, q, logp, grad, accept_prob,

@@ -247,6 +247,7 @@ constexpr int kQueueMax = 32 * (4 + 1);  // 31 left over + kUnroll * 32 new entr
 // per-warp state of the indexed producer (shared memory: it must not cost registers across the drain)
 struct WarpIndexState {
   uint32_t rlo[32], rcnt[32];  // index range of the epoch each lane looked up
+  long long kfirst[32], kend[32];  // per planet: first / last epoch that can touch this warp's cadences
   long long kcur, klast;       // next / last epoch of the current planet
   int p;                       // current planet
   uint32_t rmask;              // lanes of the current batch whose range is still to be fed
@@ -291,7 +292,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
   for (int j = 0; j < XO_NGRAD + 3; ++j) lacc[j][threadIdx.x] = 0.0;
 #pragma unroll
   for (int j = 0; j < XO_NGRAD; ++j) pacc[j][threadIdx.x] = 0.0;
-  for (uint32_t i = start + 16u * lane; i < end; i += 16u * 32u) xo::prefetch_l2(t + i);
+  // (data only, so legal before the wait) with the time index the sweep reads no time stamps: nothing to pull in
+  if (!(kMoments && moments[5] != 0.0))
+    for (uint32_t i = start + 16u * lane; i < end; i += 16u * 32u) xo::prefetch_l2(t + i);
   xo::pdl_wait();
   const int64_t c = ma.order ? ma.order[blockIdx.y] : blockIdx.y;
   if (kModel && ma.stage_from_params)
@@ -338,15 +341,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
   const double mean_c = sm.mean;
   const uint32_t lt_mask = (1u << lane) - 1u;
 
-  // evaluate m (<= 32) queued entries of planet p starting at queue offset off
-  auto drain = [&](int p, int off, int m) {
+  // evaluate m (<= 32) queued entries src[0..m) of planet p
+  auto drain = [&](int p, const uint32_t *src, int m) {
     if (p != pcur) {
       if (pcur >= 0) flush(pcur);
       pcur = p;
     }
     if (lane < m) {
       double scale;  // cotangent multiplying this lane's accumulated d lc / d elements
-      const uint32_t idx = queue[warp][p][off + lane];
+      const uint32_t idx = src[lane];
       const double tt = __ldg(t + idx);
       // issued now so that their latency hides behind the sample evaluation
       const double yy = kVjp ? (ma.vjp_shared ? -__ldg(y + (int64_t)c * N + idx) : __ldg(y + ((int64_t)c * N + idx) * P + p)) : __ldg(y + idx);
@@ -404,15 +407,40 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
   constexpr uint32_t kStep = 32 * kUnroll;
   uint32_t gnext = start, gcur = start, hitmask = 0u;
   __shared__ WarpIndexState widx[kMoments ? kWarps : 1];
+  __shared__ int wfill[kWarps][XO_MAX_PLANETS];  // final pass: what each warp is left with, per planet
+  // ... pooled over the CTA: behind warp 0's (by then < 32) left-overs when the queue is long enough, else in its own array
+  constexpr bool kPoolInQueue = kQueue >= 32 + kWarps * 32;
+  __shared__ uint32_t pool_own[kPoolInQueue ? 1 : XO_MAX_PLANETS][kPoolInQueue ? 1 : kWarps * 32];
+  auto pool = [&](int p) -> uint32_t * { return kPoolInQueue ? &queue[0][p][32] : pool_own[kPoolInQueue ? 0 : p]; };
+  // epoch range of every planet over this warp's cadences (lane p: planet p).  A planet with more epochs than cadences in
+  // the range (or a non-finite / non-positive period) cannot be enumerated: the whole warp then takes the stepping producer.
+  bool indexed = false;
   if (kMoments && nbins > 0) {
-    if (lane == 0) {
+    long long ka = 1, kb = 0;
+    bool dense = false;
+    if (lane < P && start < end) {
+      const double per = sm.elem[lane][XO_EL_PERIOD], t0p = sm.elem[lane][XO_EL_T0];
+      const double tA = __ldg(t + start), tB = __ldg(t + end - 1);
+      const double fa = floor((tA - t0p) * sm.rperiod[lane] - 0.5) - 1.0, fb = ceil((tB - t0p) * sm.rperiod[lane] + 0.5) + 1.0;
+      dense = !(per > 0.0) || !(fb - fa <= (double)(end - start) + 4.0);
+      if (!dense) {
+        ka = (long long)fa;
+        kb = (long long)fb;
+      }
+    }
+    indexed = !__any_sync(kFull, dense);
+    if (indexed) {
       WarpIndexState &W = widx[warp];
-      W.p = -1;
-      W.kcur = 1;
-      W.klast = 0;
-      W.rmask = 0u;
-      W.clo = 0u;
-      W.ccnt = 0u;
+      W.kfirst[lane] = ka;
+      W.kend[lane] = kb;
+      if (lane == 0) {
+        W.p = -1;
+        W.kcur = 1;
+        W.klast = 0;
+        W.rmask = 0u;
+        W.clo = 0u;
+        W.ccnt = 0u;
+      }
     }
     __syncwarp();
   }
@@ -420,7 +448,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
   for (;;) {
     bool last = false;
     int pb = 0, pe = P;  // planets whose queues the consumer looks at this iteration
-    if (kMoments && nbins > 0) {
+    if (kMoments && indexed) {
       // ---------------- indexed producer ----------------
       WarpIndexState &W = widx[warp];
       uint32_t ccnt = W.ccnt, clo = W.clo;
@@ -429,17 +457,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
         uint32_t rmask = W.rmask;
         while (rmask == 0u && !last) {  // a new batch of 32 epochs (of the next planet when this one is exhausted)
           long long kcur = W.kcur, klast = W.klast;
-          bool dense = false;
           while (kcur > klast) {
             if (++p >= P) break;
-            const double per = sm.elem[p][XO_EL_PERIOD], t0p = sm.elem[p][XO_EL_T0];
-            const double tA = __ldg(t + start), tB = __ldg(t + (end > start ? end - 1 : start));
-            const double ka = floor((tA - t0p) * sm.rperiod[p] - 0.5) - 1.0, kb = ceil((tB - t0p) * sm.rperiod[p] + 0.5) + 1.0;
-            // more epochs than cadences (or a non-finite / non-positive period): every cadence is a candidate
-            dense = !(per > 0.0) || !(kb - ka <= (double)(end - start) + 4.0) || start >= end;
-            kcur = dense ? 0 : (long long)ka;
-            klast = dense ? 0 : (long long)kb;
-            if (start >= end) klast = kcur - 1;  // empty slot: nothing to enumerate
+            kcur = W.kfirst[p];
+            klast = W.kend[p];
           }
           if (p >= P) {
             last = true;
@@ -447,12 +468,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
           }
           uint32_t lo = 0u, cnt = 0u;
           const long long k = kcur + lane;
-          if (dense) {
-            if (lane == 0) {
-              lo = start;
-              cnt = end - start;
-            }
-          } else if (k <= klast) {
+          if (k <= klast) {
             const TimeIndex ix{reinterpret_cast<const uint32_t *>(moments + XO_MOMENTS_LEN), nbins, __ldg(t), moments[6]};
             const double per = sm.elem[p][XO_EL_PERIOD], t0p = sm.elem[p][XO_EL_T0], hp = 0.5 * per;
             const double ts = sm.elem[p][XO_EL_TSTART], te = sm.elem[p][XO_EL_TEND];
@@ -584,26 +600,49 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
       }
     }
     // ---------------- consumer: the one drain call site ----------------
-    const int thr = last ? 1 : 32;
-    for (int p = pb; p < pe; ++p) {
-      int fill = __shfl_sync(kFull, cnt, p);
-      if (fill < thr) continue;
-      int off = 0;
-#pragma unroll 1
-      while (fill - off >= thr) {
-        const int m = min(32, fill - off);
-        drain(p, off, m);
-        off += m;
+    // Ordinary iterations: a queue is drained 32 entries at a time as soon as it holds that many.  Final pass: the < 32
+    // entries each warp is left with are pooled over the CTA's warps (warp order, so still deterministic) and drained
+    // in chunks of 32 dealt round-robin to the warps -- up to kWarps partial drains become total/32 full ones.
+    if (last) {
+      if (lane < P) wfill[warp][lane] = cnt;
+      __syncthreads();
+      for (int p = 0; p < P; ++p) {
+        int before = 0;
+        for (int w = 0; w < warp; ++w) before += wfill[w][p];
+        const int mine = wfill[warp][p];
+        if (lane < mine) pool(p)[before + lane] = queue[warp][p][lane];
       }
-      {  // move the < 32 left-over entries to the front
+      __syncthreads();
+    }
+    for (int p = pb; p < pe; ++p) {
+      int fill, off, stride;
+      const uint32_t *src;
+      if (last) {
+        fill = 0;
+        for (int w = 0; w < kWarps; ++w) fill += wfill[w][p];
+        off = 32 * warp;
+        stride = 32 * kWarps;
+        src = pool(p);
+      } else {
+        fill = __shfl_sync(kFull, cnt, p);
+        if (fill < 32) continue;
+        off = 0;
+        stride = 32;
+        src = queue[warp][p];
+      }
+#pragma unroll 1
+      while (last ? off < fill : fill - off >= 32) {
+        drain(p, src + off, min(32, fill - off));
+        off += stride;
+      }
+      if (!last) {  // move the < 32 left-over entries to the front
         const int rem = fill - off;
         const uint32_t v = lane < rem ? queue[warp][p][off + lane] : 0u;
         __syncwarp();
         if (lane < rem) queue[warp][p][lane] = v;
         __syncwarp();
-        fill = rem;
+        if (lane == p) cnt = rem;
       }
-      if (lane == p) cnt = fill;
     }
     if (last) break;
   }

@@ -73,24 +73,24 @@ class TransitPosterior:
         star = torch.stack([one, one, 2.0 * sq * q2, sq * (1.0 - 2.0 * q2)], dim=-1)
         return par, star, q[:, -1]
 
-    def _prior_vectors(self):
-        """prior_mu[D], prior_sigma[D] as contiguous device vectors, or None when the priors differ between chains"""
-        if self.mu.dim() > 1 or self.sigma.dim() > 1:
-            return None
+    def _prior_vectors(self, C):
+        """(prior_mu, prior_sigma, chain stride): [D] vectors shared by the chains (stride 0) or [C, D] rows (stride D)"""
         D = self.D
-        return self.mu.expand(D).contiguous(), self.sigma.expand(D).contiguous()
+        if self.mu.dim() > 1 or self.sigma.dim() > 1:
+            return self.mu.expand(C, D).contiguous(), self.sigma.expand(C, D).contiguous(), D
+        return self.mu.expand(D).contiguous(), self.sigma.expand(D).contiguous(), 0
 
     def fused_args(self, C):
         """what the C-ABI posterior / HMC entry points need besides the state; None when this posterior cannot take the
-        fused path (per-chain priors, cadence-parallel model)"""
+        fused path (cadence-parallel model, CPU data)"""
         import ctypes as C_
 
         from . import _lib
 
         m = self.model
-        pv = self._prior_vectors()
-        if pv is None or m.cadence_group is not None or not m.data.t.is_cuda:
+        if m.cadence_group is not None or not m.data.t.is_cuda:
             return None
+        pv = self._prior_vectors(C)
         lib = _lib.require_cuda()
         d = m.data
         need = lib.xo_transit_posterior_workspace(d.n, C, self.P)
@@ -100,13 +100,13 @@ class TransitPosterior:
         ptr = lambda x: C_.c_void_p(x.data_ptr()) if x is not None else None  # noqa: E731
         mom = d.moments() if m.use_moments else None
         self._keep = (pv, mom)
-        return dict(lib=lib, head=(ptr(d.t), ptr(d.y), ptr(d.ivar), d.n, ptr(mom)), prior=(ptr(pv[0]), ptr(pv[1])),
+        return dict(lib=lib, head=(ptr(d.t), ptr(d.y), ptr(d.ivar), d.n, ptr(mom)), prior=(ptr(pv[0]), ptr(pv[1]), pv[2]),
                     tail=(ptr(m.dtk), ptr(m.wk), m.dtk.numel(), m.texp, int(m.use_in_transit), d.lognorm), ws=ws)
 
     def __call__(self, q):
         """(log posterior[C], gradient[C, D]); no host synchronisation.  One C call (xo_transit_posterior_logp_grad:
-        unpack kernel, fused model evaluation, chain-rule + prior kernel) when the priors are shared by the chains;
-        otherwise the same mathematics through torch autograd."""
+        unpack kernel, fused model evaluation, chain-rule + prior kernel); ``autograd_call`` is the same mathematics
+        through torch autograd."""
         import ctypes as C_
 
         from . import _lib

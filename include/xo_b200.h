@@ -202,7 +202,8 @@ int xo_transit_gp_logp_grad(const double *t, const double *y, const double *diag
  * The PyMC model of /root/reference/docs/tutorials/data-and-models.md:458-509 as one device-resident evaluation:
  * q[C][D], D = 6 P + 3 = per planet (log period, t0, sqrt(e) cos w, sqrt(e) sin w, b, log r/R*), per chain
  * (logit q1, logit q2, mean flux) with Kipping's (q1, q2) -> (u1, u2) (/root/reference/src/exoplanet/distributions.py:98-102),
- * R* = M* = 1, independent Normal priors prior_mu[D], prior_sigma[D] on q.
+ * R* = M* = 1, independent Normal priors on q: prior_mu / prior_sigma are [D] with prior_chain_stride = 0 (shared by the
+ * chains) or [C][prior_chain_stride] (one row per chain).
  *   logp[c] = Gaussian log-likelihood of the light curve + log prior (without the priors' normalisation constants)
  *   grad[C][D] = d logp / d q      (change of variables, its chain rule and the priors are two small kernels
  *                                   around xo_transit_model_logp_grad; moments may be NULL)
@@ -213,11 +214,11 @@ int xo_transit_gp_logp_grad(const double *t, const double *y, const double *diag
 size_t xo_transit_posterior_workspace(int64_t N, int64_t C, int64_t P);
 int xo_transit_posterior_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *moments,
                                    const double *q, int64_t C, int64_t P, const double *prior_mu, const double *prior_sigma,
-                                   const double *dtk, const double *wk, int K, double texp, int use_in_transit, double lognorm,
+                                   int64_t prior_chain_stride, const double *dtk, const double *wk, int K, double texp, int use_in_transit, double lognorm,
                                    double *logp, double *grad, void *workspace, size_t workspace_bytes, void *stream);
 int xo_hmc_transition(const double *t, const double *y, const double *ivar, int64_t N, const double *moments, int64_t C, int64_t P,
-                      const double *prior_mu, const double *prior_sigma, const double *dtk, const double *wk, int K, double texp,
-                      int use_in_transit, double lognorm, double *q, double *logp, double *grad, const double *eps,
+                      const double *prior_mu, const double *prior_sigma, int64_t prior_chain_stride, const double *dtk, const double *wk,
+                      int K, double texp, int use_in_transit, double lognorm, double *q, double *logp, double *grad, const double *eps,
                       const double *inv_mass, int n_leapfrog, unsigned long long seed, unsigned long long counter,
                       double *accept_prob, double *energy_error, void *workspace, size_t workspace_bytes, void *stream);
 

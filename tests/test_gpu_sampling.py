@@ -51,13 +51,17 @@ def test_fused_posterior_equals_autograd_composition():
     lp2, g2 = post.autograd_call(q0)
     assert torch.allclose(lp, lp2, rtol=1e-13, atol=0)
     assert torch.allclose(g, g2, rtol=1e-10, atol=1e-10 * g2.abs().max().item())
-    # per-chain priors cannot take the fused path and fall back to autograd
+    # per-chain priors ([C, D] rows) take the same entry point with a chain stride
     from exoplanet_b200.sampling import TransitPosterior
 
-    per_chain = TransitPosterior(post.model, 1, post.mu.expand(16, -1).clone(), post.sigma)
-    assert per_chain.fused_args(16) is None
+    mu_c = post.mu.expand(16, -1).clone()
+    mu_c[3:] += 0.01
+    per_chain = TransitPosterior(post.model, 1, mu_c, post.sigma)
+    assert per_chain.fused_args(16) is not None
     lp3, g3 = per_chain(q0)
-    assert torch.allclose(lp3, lp2, rtol=1e-13, atol=0)
+    lp4, g4 = per_chain.autograd_call(q0)
+    assert torch.allclose(lp3, lp4, rtol=1e-13, atol=0) and torch.allclose(g3, g4, rtol=1e-10, atol=1e-10 * g4.abs().max().item())
+    assert torch.allclose(lp3[:3], lp2[:3], rtol=1e-13, atol=0) and not torch.allclose(lp3[3:], lp2[3:], rtol=1e-9, atol=0)
 
 
 @pytest.mark.parametrize("mode", ["fused", "graph", "eager"])

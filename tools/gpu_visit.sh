@@ -55,10 +55,14 @@ transit)
 both)
   run_pytest all tests/test_gpu_fused.py tests/test_reference_glue.py tests/test_gpu_configs.py tests/test_gpu_sampling.py tests/test_gpu_gp.py
   bench_line ours --steps 20 --warmup 5 --no-cpu --no-kepler
-  for V in $GP_VARIANTS; do XO_B200_LIB=exoplanet_b200/libxo_b200_$V.so bench_line $V --steps 20 --warmup 5 --no-cpu --no-kepler --extra gp; done
+  for R in 16 32; do XO_GP_RUN=$R bench_line gprun$R --steps 20 --warmup 5 --no-cpu --no-kepler --extra gp; done
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"hmc_|posterior_|transit_|model_|gp_" -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
+      python bench.py --steps 3 --warmup 3 --no-cpu --no-kepler --extra gp,hmc > $OUT/${TAG}_ncu_bench.log 2>&1
   capture transit transit_logp_grad_kernel 3 --steps 2 --warmup 3 --no-cpu --no-kepler --no-extra
-  capture gpfwd "gp_forward_kernel" 27 --steps 1 --warmup 3 --no-cpu --no-kepler --extra gp
-  capture gpbwd "gp_backward_kernel" 14 --steps 1 --warmup 3 --no-cpu --no-kepler --extra gp
+  capture gpagg "gp_aggregate_kernel" 27 --steps 1 --warmup 3 --no-cpu --no-kepler --extra gp
+  capture gpll "gp_loglike_kernel" 27 --steps 1 --warmup 3 --no-cpu --no-kepler --extra gp
+  capture gpgagg "gp_grad_aggregate_kernel" 14 --steps 1 --warmup 3 --no-cpu --no-kepler --extra gp
+  capture gpgfin "gp_grad_final_kernel" 14 --steps 1 --warmup 3 --no-cpu --no-kepler --extra gp
   ;;
 final)
   run_pytest all tests
