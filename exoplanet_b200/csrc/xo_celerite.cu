@@ -13,9 +13,10 @@
 //      state (m, Z = Sigma_inf - P) entering every CTA;
 //   3. gp_loglike: each thread applies its in-CTA prefix to that state and re-walks its run with plain Kalman steps,
 //      accumulating -1/2 (v^2/D + log D); the last CTA of a chain folds the per-CTA sums in CTA order.
-// A thread's run is one or two 128-byte lines of each array: the lines are prefetched into L1 when the thread starts
-// and every step's operands are loaded one step ahead, so the walk never waits for memory; every sector that is
-// fetched is fully used.  Two one-pass formulations (tile staged in shared memory, one read of the data, a fixed
+// A CTA's 128 runs are one contiguous tile of the series: it is read with coalesced loads into shared memory (row
+// pitch RUN + 1: conflict-free walks), so the dependent chains of the walks never wait for global memory (L1 prefetch
+// of each run's lines + operands loaded one step ahead was measured first: the resident CTAs' lines do not fit in L1,
+// long_scoreboard stayed at 7-13 stalls per issue).  Two one-pass formulations (tile staged in shared memory, one read of the data, a fixed
 // inter-CTA tree with flags instead of the second kernel) were built and measured in round 2: 0.98 ms (128-thread
 // tiles) and 1.27 ms (one-warp tiles) against 0.58 ms for this form at 16 chains x 1e6 cadences -- the scans are
 // instruction/latency-bound, not bandwidth-bound, and the serial tree look-back costs more than the second read of the
@@ -243,11 +244,31 @@ struct LogProd {
 #ifndef XO_GP_RUN_LONG
 #define XO_GP_RUN_LONG 32  // run length used when there is parallelism to spare: halves the in-CTA scan work per cadence
 #endif
-// one 128-byte line per 16 doubles: ask for the run's lines before the walk needs them
+// A CTA's 128 runs are one contiguous tile of the series: it is read from HBM with coalesced loads into shared memory
+// (row pitch RUN + 1 doubles: thread r then walks row r conflict-free), the walks never wait for global memory.
 template <int RUN>
-__device__ __forceinline__ void prefetch_run(const double *p) {
-#pragma unroll
-  for (int j = 0; j < RUN; j += 16) xo::prefetch_l1(p + j);
+struct TileSmem {
+  static constexpr int kPitchT = RUN + 1;
+  double t[kThreadsGp * (RUN + 1)];
+  double d[kThreadsGp * (RUN + 1)];  // diag + jitter
+  double y[kThreadsGp * (RUN + 1)];
+  double t_halo;                      // the time stamp before the tile's first cadence (t[0] itself for the first tile)
+};
+template <int RUN>
+__device__ __forceinline__ void stage_tile(TileSmem<RUN> &sm, const double *__restrict__ t, const double *__restrict__ diag,
+                                           const double *__restrict__ yb, double jit, int64_t base, int64_t N) {
+  const int nvalid = (int)max((int64_t)0, min((int64_t)kThreadsGp * RUN, N - base));
+#pragma unroll 4
+  for (int idx = threadIdx.x; idx < kThreadsGp * RUN; idx += kThreadsGp) {
+    const int at = (idx / RUN) * (RUN + 1) + idx % RUN;
+    if (idx < nvalid) {
+      sm.t[at] = __ldg(t + base + idx);
+      sm.d[at] = __ldg(diag + base + idx) + jit;
+      sm.y[at] = __ldg(yb + base + idx);
+    }
+  }
+  if (threadIdx.x == 0) sm.t_halo = __ldg(t + (base > 0 ? base - 1 : 0));
+  __syncthreads();
 }
 
 // ---- phase 1 ---------------------------------------------------------------
@@ -259,37 +280,32 @@ __global__ void __launch_bounds__(kThreadsGp) gp_aggregate_kernel(const double *
                                                                   const double *__restrict__ jitter, double eps, int64_t T,
                                                                   double *__restrict__ pref, double *__restrict__ cta_tot,
                                                                   unsigned *__restrict__ done, GpStatus *__restrict__ status) {
+  extern __shared__ __align__(16) unsigned char gp_smem_raw[];
+  TileSmem<RUN> &sm = *reinterpret_cast<TileSmem<RUN> *>(gp_smem_raw);
   __shared__ Agg warp_tot[kWarpsGp];
   const int64_t bch = blockIdx.y;
   const int64_t g = (int64_t)blockIdx.x * kThreadsGp + threadIdx.x;
   const int64_t s = g * RUN, e = min(s + RUN, N);
   const double *yb = y + bch * N;
-  if (s < e) {
-    prefetch_run<RUN>(t + s);
-    prefetch_run<RUN>(diag + s);
-    prefetch_run<RUN>(yb + s);
-  }
   if (threadIdx.x == 0 && blockIdx.x == 0) {  // per-call scratch the later kernels of this stream-ordered sequence count in
     done[bch] = 0u;
     if (bch == 0) status->bad_lanes = status->wait_failures = 0ull;
   }
   const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
   const double jit = jitter ? jitter[bch] : 0.0;
+  stage_tile<RUN>(sm, t, diag, yb, jit, (int64_t)blockIdx.x * kThreadsGp * RUN, N);
+  const double *ts = sm.t + threadIdx.x * (RUN + 1), *ds = sm.d + threadIdx.x * (RUN + 1), *ys = sm.y + threadIdx.x * (RUN + 1);
+  const double t_before = threadIdx.x > 0 ? sm.t[(threadIdx.x - 1) * (RUN + 1) + RUN - 1] : sm.t_halo;
   Agg v = agg_identity();
   if (s < e) {
     double A00 = 1, A01 = 0, A10 = 0, A11 = 1, b0 = 0, b1 = 0, e0 = 0, e1 = 0, J00 = 0, J01 = 0, J11 = 0;
     double Z00 = k.a, Z01 = 0.0, Z11 = k.a * k.w2;  // P = 0  <=>  Z = Sigma_inf
-    double tprev = s > 0 ? __ldg(t + s - 1) : __ldg(t);
-    double tn = __ldg(t + s), dn = __ldg(diag + s), yn = __ldg(yb + s);  // operands of the next step, loaded one step ahead
+    double tprev = t_before;
     ShoCache cc;
+    const int len = (int)(e - s);
 #pragma unroll 1
-    for (int64_t i = s; i < e; ++i) {
-      const double ti = tn, di = dn + jit, yi = yn;
-      if (i + 1 < e) {
-        tn = __ldg(t + i + 1);
-        dn = __ldg(diag + i + 1);
-        yn = __ldg(yb + i + 1);
-      }
+    for (int j = 0; j < len; ++j) {
+      const double ti = ts[j], di = ds[j], yi = ys[j];
       double f00, f01, f10, f11;
       sho_phi(k, ti - tprev, cc, f00, f01, f10, f11);
       tprev = ti;
@@ -381,19 +397,19 @@ __global__ void __launch_bounds__(kThreadsGp) gp_loglike_kernel(const double *__
                                                                 const double *__restrict__ cta_state, double *__restrict__ cta_ll,
                                                                 unsigned *__restrict__ done, GpStatus *__restrict__ status,
                                                                 double *__restrict__ loglike, double *__restrict__ rec, int64_t Tb) {
+  extern __shared__ __align__(16) unsigned char gp_smem_raw[];
+  TileSmem<RUN> &sm = *reinterpret_cast<TileSmem<RUN> *>(gp_smem_raw);
   __shared__ double red[kWarpsGp];
   __shared__ int is_last;
   const int64_t bch = blockIdx.y;
   const int64_t g = (int64_t)blockIdx.x * kThreadsGp + threadIdx.x;
   const int64_t s = g * RUN, e = min(s + RUN, N);
   const double *yb = y + bch * N;
-  if (s < e) {
-    prefetch_run<RUN>(t + s);
-    prefetch_run<RUN>(diag + s);
-    prefetch_run<RUN>(yb + s);
-  }
   const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
   const double jit = jitter ? jitter[bch] : 0.0;
+  stage_tile<RUN>(sm, t, diag, yb, jit, (int64_t)blockIdx.x * kThreadsGp * RUN, N);
+  const double *ts = sm.t + threadIdx.x * (RUN + 1), *ds = sm.d + threadIdx.x * (RUN + 1), *ys = sm.y + threadIdx.x * (RUN + 1);
+  const double t_before = threadIdx.x > 0 ? sm.t[(threadIdx.x - 1) * (RUN + 1) + RUN - 1] : sm.t_halo;
   double acc = 0.0;
   if (s < e) {
     const double *st = cta_state + (bch * gridDim.x + blockIdx.x) * 5;
@@ -406,18 +422,14 @@ __global__ void __launch_bounds__(kThreadsGp) gp_loglike_kernel(const double *__
       Z01 = -P01;
       Z11 = k.a * k.w2 - P11;
     }
-    double tprev = s > 0 ? __ldg(t + s - 1) : __ldg(t);
-    double tn = __ldg(t + s), dn = __ldg(diag + s), yn = __ldg(yb + s);
+    double tprev = t_before;
     ShoCache cc;
     LogProd lp;
+    const int len = (int)(e - s);
 #pragma unroll 1
-    for (int64_t i = s; i < e; ++i) {
-      const double ti = tn, di = dn + jit, yi = yn;
-      if (i + 1 < e) {
-        tn = __ldg(t + i + 1);
-        dn = __ldg(diag + i + 1);
-        yn = __ldg(yb + i + 1);
-      }
+    for (int j = 0; j < len; ++j) {
+      const int64_t i = s + j;
+      const double ti = ts[j], di = ds[j], yi = ys[j];
       double f00, f01, f10, f11;
       sho_phi(k, ti - tprev, cc, f00, f01, f10, f11);
       tprev = ti;
@@ -826,24 +838,41 @@ __device__ __forceinline__ void gp_step_adj(const StepFwd &s, double (&L)[5], do
 struct RunStates {
   double st[5][kRunB][kThreadsGp];
 };
-// states entering every step of run [s, e) of chain bch -> R.st[.][i][tid]
-__device__ __forceinline__ void gp_rederive(const Sho &k, const double *__restrict__ t, const double *__restrict__ yb,
-                                            const double *__restrict__ diag, double jit, const double *__restrict__ rp, int64_t Tb,
-                                            int64_t s, int64_t e, RunStates &R) {
+struct GradSmem {
+  TileSmem<kRunB> tile;  // the CTA's 128 runs: t, diag + jitter, y (the final kernel overwrites y / diag rows with d/dy, d/d diag)
+  RunStates R;
+};
+// The CTA with index bx owns runs T-1-(128 bx + tid), tid = 0..127: the contiguous block of time-runs
+// [r_lo, r_lo + 128) with r_lo = T - 128 (bx + 1) (negative for the last CTA: clipped, its first rows are then unused).
+struct GradTile {
+  int64_t r_lo, base;  // first time-run of the tile (may be negative), first cadence staged
+  int row0;            // smem row of time-run max(r_lo, 0)
+};
+__device__ __forceinline__ GradTile grad_tile(int64_t T) {
+  GradTile g;
+  g.r_lo = T - (int64_t)kThreadsGp * (blockIdx.x + 1);
+  const int64_t first = g.r_lo > 0 ? g.r_lo : 0;
+  g.base = first * kRunB;
+  g.row0 = 0;
+  return g;
+}
+// states entering every step of the run in smem row `row` (cadences [s, e)) -> R.st[.][j][tid]
+__device__ __forceinline__ void gp_rederive(const Sho &k, const TileSmem<kRunB> &tile, int row, const double *__restrict__ rp, int64_t Tb,
+                                            int len, RunStates &R) {
   const int tid = threadIdx.x;
+  const double *ts = tile.t + row * (kRunB + 1), *ds = tile.d + row * (kRunB + 1), *ys = tile.y + row * (kRunB + 1);
   double m0 = __ldg(rp), m1 = __ldg(rp + Tb), Z00 = __ldg(rp + 2 * Tb), Z01 = __ldg(rp + 3 * Tb), Z11 = __ldg(rp + 4 * Tb);
-  double tprev = s > 0 ? __ldg(t + s - 1) : __ldg(t);
+  double tprev = row > 0 ? tile.t[(row - 1) * (kRunB + 1) + kRunB - 1] : tile.t_halo;
   ShoCache cc;
 #pragma unroll 1
-  for (int64_t i = s; i < e; ++i) {
-    const int j = (int)(i - s);
+  for (int j = 0; j < len; ++j) {
     R.st[0][j][tid] = m0;
     R.st[1][j][tid] = m1;
     R.st[2][j][tid] = Z00;
     R.st[3][j][tid] = Z01;
     R.st[4][j][tid] = Z11;
-    if (i + 1 == e) break;
-    const double ti = __ldg(t + i);
+    if (j + 1 == len) break;
+    const double ti = ts[j];
     double f00, f01, f10, f11;
     sho_phi(k, ti - tprev, cc, f00, f01, f10, f11);
     tprev = ti;
@@ -852,10 +881,10 @@ __device__ __forceinline__ void gp_rederive(const Sho &k, const double *__restri
     double z10 = f10 * Z00 + f11 * Z01, z11 = f10 * Z01 + f11 * Z11;
     double p00 = z00 * f00 + z01 * f01, p01 = z00 * f10 + z01 * f11, p11 = z10 * f10 + z11 * f11;
     const double pm = k.a - p00;
-    const double D = pm + __ldg(diag + i) + jit;
+    const double D = pm + ds[j];
     const double rD = xo::rcp_fast(D);
     const double K0 = pm * rD, K1 = -p01 * rD;
-    const double vv = __ldg(yb + i) - c0;
+    const double vv = ys[j] - c0;
     m0 = fma(K0, vv, c0);
     m1 = fma(K1, vv, c1);
     Z00 = fma(D * K0, K0, p00);
@@ -863,13 +892,29 @@ __device__ __forceinline__ void gp_rederive(const Sho &k, const double *__restri
     Z11 = fma(D * K1, K1, p11);
   }
 }
-__device__ __forceinline__ StepFwd gp_step_at(const Sho &k, const double *__restrict__ t, const double *__restrict__ yb,
-                                              const double *__restrict__ diag, double jit, int64_t s, int64_t i, const RunStates &R,
-                                              ShoCache &cc) {
-  const int tid = threadIdx.x, j = (int)(i - s);
-  const double dt = i > 0 ? __ldg(t + i) - __ldg(t + i - 1) : 0.0;
-  return gp_step_fwd(k, dt, __ldg(yb + i), __ldg(diag + i) + jit, R.st[0][j][tid], R.st[1][j][tid], R.st[2][j][tid], R.st[3][j][tid],
-                     R.st[4][j][tid], cc);
+// forward quantities of step j of the run in smem row `row`
+__device__ __forceinline__ StepFwd gp_step_at(const Sho &k, const TileSmem<kRunB> &tile, int row, int j, const RunStates &R, ShoCache &cc) {
+  const int tid = threadIdx.x;
+  const double *ts = tile.t + row * (kRunB + 1);
+  const double tp = j > 0 ? ts[j - 1] : (row > 0 ? tile.t[(row - 1) * (kRunB + 1) + kRunB - 1] : tile.t_halo);
+  return gp_step_fwd(k, ts[j] - tp, tile.y[row * (kRunB + 1) + j], tile.d[row * (kRunB + 1) + j], R.st[0][j][tid], R.st[1][j][tid],
+                     R.st[2][j][tid], R.st[3][j][tid], R.st[4][j][tid], cc);
+}
+
+// the same step for a lambda whose mean part is zero and stays zero (the three Zbar basis vectors of a run's map: mbar
+// never depends on Zbar): only L[2..4] are read and written
+__device__ __forceinline__ void gp_step_adj_z(const StepFwd &s, double (&L)[5]) {
+  const double zb00 = L[2], zb01 = L[3], zb11 = L[4];
+  const double q = zb00 * s.k0 * s.k0 + zb01 * s.k0 * s.k1 + zb11 * s.k1 * s.k1;
+  const double Dbar = -q * s.rD * s.rD;
+  const double kb0 = (2.0 * zb00 * s.k0 + zb01 * s.k1) * s.rD;
+  const double kb1 = (zb01 * s.k0 + 2.0 * zb11 * s.k1) * s.rD;
+  const double pb00 = zb00 - kb0 - Dbar, hb = 0.5 * (zb01 - kb1), pb11 = zb11;
+  const double u00 = pb00 * s.f00 + hb * s.f10, u01 = pb00 * s.f01 + hb * s.f11;
+  const double u10 = hb * s.f00 + pb11 * s.f10, u11 = hb * s.f01 + pb11 * s.f11;
+  L[2] = s.f00 * u00 + s.f10 * u10;
+  L[3] = 2.0 * (s.f00 * u01 + s.f10 * u11);
+  L[4] = s.f01 * u01 + s.f11 * u11;
 }
 
 __global__ void __launch_bounds__(kThreadsGp, 3)
@@ -877,31 +922,35 @@ __global__ void __launch_bounds__(kThreadsGp, 3)
                              const double *__restrict__ S0, const double *__restrict__ w0, const double *__restrict__ Qf,
                              const double *__restrict__ jitter, double eps, int64_t T, const double *__restrict__ rs,
                              double *__restrict__ gpref, double *__restrict__ gcta) {
-  __shared__ RunStates R;
+  extern __shared__ __align__(16) unsigned char gp_smem_raw[];
+  GradSmem &sm = *reinterpret_cast<GradSmem *>(gp_smem_raw);
+  RunStates &R = sm.R;
   __shared__ Adj warp_tot[kWarpsGp];
   const int64_t bch = blockIdx.y;
   const Sho k = make_sho(S0[bch], w0[bch], Qf[bch], eps);
   const double jit = jitter ? jitter[bch] : 0.0;
   const int64_t g = (int64_t)blockIdx.x * kThreadsGp + threadIdx.x;
   const int64_t run = T - 1 - g;  // reversed ownership
+  const GradTile gt = grad_tile(T);
+  stage_tile<kRunB>(sm.tile, t, diag, y + bch * N, jit, gt.base, N);
   Adj v = adj_identity();
   if (run >= 0) {
     const int64_t s = run * kRunB, e = min(s + kRunB, N);
-    const double *yb = y + bch * N;
-    gp_rederive(k, t, yb, diag, jit, rs + (size_t)bch * 5 * T + run, T, s, e, R);
+    const int row = (int)(run - (gt.r_lo > 0 ? gt.r_lo : 0)), len = (int)(e - s);
+    gp_rederive(k, sm.tile, row, rs + (size_t)bch * 5 * T + run, T, len, R);
     // the run's map lambda_{e-1} -> lambda_{s-1}: push the origin (with the forcing) and the five basis vectors through it
     double O[5] = {0, 0, 0, 0, 0}, X0[5] = {1, 0, 0, 0, 0}, X1[5] = {0, 1, 0, 0, 0}, X2[5] = {0, 0, 1, 0, 0},
            X3[5] = {0, 0, 0, 1, 0}, X4[5] = {0, 0, 0, 0, 1};
     ShoCache cc;
 #pragma unroll 1
-    for (int64_t i = e - 1; i >= s; --i) {
-      const StepFwd f = gp_step_at(k, t, yb, diag, jit, s, i, R, cc);
+    for (int j = len - 1; j >= 0; --j) {
+      const StepFwd f = gp_step_at(k, sm.tile, row, j, R, cc);
       gp_step_adj<true, false>(f, O, nullptr);
       gp_step_adj<false, false>(f, X0, nullptr);
       gp_step_adj<false, false>(f, X1, nullptr);
-      gp_step_adj<false, false>(f, X2, nullptr);
-      gp_step_adj<false, false>(f, X3, nullptr);
-      gp_step_adj<false, false>(f, X4, nullptr);
+      gp_step_adj_z(f, X2);
+      gp_step_adj_z(f, X3);
+      gp_step_adj_z(f, X4);
     }
     v.A[0] = X0[0]; v.A[1] = X1[0]; v.A[2] = X0[1]; v.A[3] = X1[1];
 #pragma unroll
@@ -961,7 +1010,9 @@ __global__ void __launch_bounds__(kThreadsGp, 3)
                          double *__restrict__ gdiag, double *__restrict__ gpart /* [B][nctas][6] */, unsigned *__restrict__ done,
                          GpStatus *__restrict__ status, double *__restrict__ ghyper /* [B][3] */,
                          double *__restrict__ gsum /* [B][2] or null */) {
-  __shared__ RunStates R;
+  extern __shared__ __align__(16) unsigned char gp_smem_raw[];
+  GradSmem &sm = *reinterpret_cast<GradSmem *>(gp_smem_raw);
+  RunStates &R = sm.R;
   __shared__ double red[6][kWarpsGp];
   __shared__ int is_last;
   const int64_t bch = blockIdx.y;
@@ -969,23 +1020,25 @@ __global__ void __launch_bounds__(kThreadsGp, 3)
   const double jit = jitter ? jitter[bch] : 0.0;
   const int64_t g = (int64_t)blockIdx.x * kThreadsGp + threadIdx.x;
   const int64_t run = T - 1 - g;
+  const GradTile gt = grad_tile(T);
+  stage_tile<kRunB>(sm.tile, t, diag, y + bch * N, jit, gt.base, N);
   double ga = 0.0, gc = 0.0, gh = 0.0, gw2 = 0.0;  // cotangents of a, c, h and w2 = c^2 +- h^2
   double sy = 0.0, sd = 0.0;                        // sums of d/dy and d/d diag over the run
   if (run >= 0) {
     const int64_t s = run * kRunB, e = min(s + kRunB, N);
-    const double *yb = y + bch * N;
-    gp_rederive(k, t, yb, diag, jit, rs + (size_t)bch * 5 * T + run, T, s, e, R);
+    const int row = (int)(run - (gt.r_lo > 0 ? gt.r_lo : 0)), len = (int)(e - s);
+    gp_rederive(k, sm.tile, row, rs + (size_t)bch * 5 * T + run, T, len, R);
     const double *st = gstate + (bch * gridDim.x + blockIdx.x) * 5;
     double Lm[5] = {st[0], st[1], st[2], st[3], st[4]};
     if (threadIdx.x > 0) adj_apply(adj_load(gpref + (bch * T + g - 1) * kAdjDoubles), Lm);
     ShoCache cc;
 #pragma unroll 1
-    for (int64_t i = e - 1; i >= s; --i) {
-      const StepFwd f = gp_step_at(k, t, yb, diag, jit, s, i, R, cc);
+    for (int j = len - 1; j >= 0; --j) {
+      const StepFwd f = gp_step_at(k, sm.tile, row, j, R, cc);
       double acc[7];
       gp_step_adj<true, true>(f, Lm, acc);
-      if (gy) gy[bch * N + i] = acc[0];        // a thread's run is two full 32-byte sectors of each output
-      if (gdiag) gdiag[bch * N + i] = acc[1];
+      sm.tile.y[row * (kRunB + 1) + j] = acc[0];  // d / d y_i     (y_i, diag_i are dead from here on: every step reads its own only)
+      sm.tile.d[row * (kRunB + 1) + j] = acc[1];  // d / d diag_i
       sy += acc[0];
       sd += acc[1];
       ga += acc[2];
@@ -1009,6 +1062,20 @@ __global__ void __launch_bounds__(kThreadsGp, 3)
     if ((threadIdx.x & 31) == 0) red[j][threadIdx.x >> 5] = x;
   }
   __syncthreads();
+  // per-cadence gradients out of the tile, coalesced
+  if (gy || gdiag) {
+    // only the rows this CTA owns: the CTA holding the start of the series (r_lo < 0) staged rows of its neighbour too
+    const int nrows = gt.r_lo < 0 ? kThreadsGp + (int)gt.r_lo : kThreadsGp;
+    const int nvalid = (int)max((int64_t)0, min((int64_t)nrows * kRunB, N - gt.base));
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < kThreadsGp * kRunB; idx += kThreadsGp) {
+      if (idx < nvalid) {
+        const int at = (idx / kRunB) * (kRunB + 1) + idx % kRunB;
+        if (gy) gy[bch * N + gt.base + idx] = sm.tile.y[at];
+        if (gdiag) gdiag[bch * N + gt.base + idx] = sm.tile.d[at];
+      }
+    }
+  }
   if (threadIdx.x < 6) {
     double s4 = 0.0;
     for (int w = 0; w < kWarpsGp; ++w) s4 += red[threadIdx.x][w];
@@ -1066,7 +1133,7 @@ __global__ void __launch_bounds__(kThreadsGp, 3)
 }
 
 struct GpLayout {
-  int run;         // cadences per thread of the forward pass (16, or XO_GP_RUN_LONG when there is parallelism to spare)
+  int run;         // cadences per thread of the forward pass (16; XO_GP_RUN=32 selects XO_GP_RUN_LONG)
   int64_t T;       // runs (threads) per chain
   int nctas;       // CTAs per chain
   int64_t Tb;      // the same for the reverse passes (runs of kRunB)
@@ -1075,15 +1142,15 @@ struct GpLayout {
       off_gpart, bytes;
 };
 inline int gp_run_length(int64_t N, int64_t B) {
-  // the long run halves the in-CTA scan work per cadence but also the number of threads: take it when the launch still
-  // fills the machine twice over (148 SMs x 4 CTAs of 128 threads)
+  // the long run halves the in-CTA scan work per cadence but also the number of threads
   static const int forced = [] {
     const char *v = getenv("XO_GP_RUN");
     return v && *v ? atoi(v) : 0;
   }();
-  if (forced == kRun || forced == XO_GP_RUN_LONG) return forced;
-  const double ctas_long = (double)B * (double)((N + XO_GP_RUN_LONG - 1) / XO_GP_RUN_LONG) / kThreadsGp;
-  return ctas_long >= 2.0 * 4.0 * xo::sm_count() ? XO_GP_RUN_LONG : kRun;
+  (void)N;
+  (void)B;
+  // with the tiles staged in shared memory the long run costs occupancy (104 KB per CTA): kept as a build / run-time knob
+  return forced == XO_GP_RUN_LONG ? XO_GP_RUN_LONG : kRun;
 }
 inline GpLayout gp_layout(int64_t N, int64_t B, bool solve = false, bool grad = false) {
   GpLayout L;
@@ -1134,19 +1201,35 @@ int gp_forward(const double *t, const double *y, const double *diag, int64_t N, 
   unsigned *done = reinterpret_cast<unsigned *>(ws + L.off_done);
   GpStatus *status = reinterpret_cast<GpStatus *>(ws);
   dim3 grid(L.nctas, (unsigned)B);
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {  // tiles above 48 KB of shared memory need the opt-in, once per device
+    cudaError_t e = cudaFuncSetAttribute(gp_aggregate_kernel<kRun>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<kRun>));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gp_loglike_kernel<kRun, REC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem<kRun>));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gp_aggregate_kernel<XO_GP_RUN_LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)sizeof(TileSmem<XO_GP_RUN_LONG>));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gp_loglike_kernel<XO_GP_RUN_LONG, REC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)sizeof(TileSmem<XO_GP_RUN_LONG>));
+    if (e != cudaSuccess) return -(int)e;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
   if (L.run == kRun) {
-    xo::launch(gp_aggregate_kernel<kRun>, grid, dim3(kThreadsGp), 0, st, t, y, diag, N, S0, w0, Q, jitter, eps, L.T, at(L.off_pref),
+    xo::launch(gp_aggregate_kernel<kRun>, grid, dim3(kThreadsGp), sizeof(TileSmem<kRun>), st, t, y, diag, N, S0, w0, Q, jitter, eps, L.T, at(L.off_pref),
                at(L.off_tot), done, status);
     xo::launch(gp_cta_scan_kernel, dim3((unsigned)B), dim3(kThreadsGp), 0, st, (const double *)at(L.off_tot), L.nctas, S0, w0, Q, eps,
                at(L.off_state));
-    xo::launch(gp_loglike_kernel<kRun, REC>, grid, dim3(kThreadsGp), 0, st, t, y, diag, N, S0, w0, Q, jitter, eps, L.T,
+    xo::launch(gp_loglike_kernel<kRun, REC>, grid, dim3(kThreadsGp), sizeof(TileSmem<kRun>), st, t, y, diag, N, S0, w0, Q, jitter, eps, L.T,
                (const double *)at(L.off_pref), (const double *)at(L.off_state), at(L.off_ll), done, status, loglike, rec, L.Tb);
   } else {
-    xo::launch(gp_aggregate_kernel<XO_GP_RUN_LONG>, grid, dim3(kThreadsGp), 0, st, t, y, diag, N, S0, w0, Q, jitter, eps, L.T, at(L.off_pref),
+    xo::launch(gp_aggregate_kernel<XO_GP_RUN_LONG>, grid, dim3(kThreadsGp), sizeof(TileSmem<XO_GP_RUN_LONG>), st, t, y, diag, N, S0, w0, Q, jitter, eps, L.T, at(L.off_pref),
                at(L.off_tot), done, status);
     xo::launch(gp_cta_scan_kernel, dim3((unsigned)B), dim3(kThreadsGp), 0, st, (const double *)at(L.off_tot), L.nctas, S0, w0, Q, eps,
                at(L.off_state));
-    xo::launch(gp_loglike_kernel<XO_GP_RUN_LONG, REC>, grid, dim3(kThreadsGp), 0, st, t, y, diag, N, S0, w0, Q, jitter, eps, L.T,
+    xo::launch(gp_loglike_kernel<XO_GP_RUN_LONG, REC>, grid, dim3(kThreadsGp), sizeof(TileSmem<XO_GP_RUN_LONG>), st, t, y, diag, N, S0, w0, Q, jitter, eps, L.T,
                (const double *)at(L.off_pref), (const double *)at(L.off_state), at(L.off_ll), done, status, loglike, rec, L.Tb);
   }
   return 0;
@@ -1176,10 +1259,19 @@ int celerite_sho_grad_impl(const double *t, const double *y, const double *diag,
   int rc = gp_forward<2>(t, y, diag, N, S0, w0, Q, jitter, B, eps, loglike, at(L.off_rs), ws, L, st);
   if (rc) return rc;
   dim3 gridb(L.nctas_b, (unsigned)B);
-  xo::launch(gp_grad_aggregate_kernel, gridb, dim3(kThreadsGp), 0, st, t, y, diag, N, S0, w0, Q, jitter, eps, L.Tb,
+  static bool gattr[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !gattr[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gp_grad_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GradSmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gp_grad_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GradSmem));
+    if (e != cudaSuccess) return -(int)e;
+    if (dev >= 0 && dev < 64) gattr[dev] = true;
+  }
+  xo::launch(gp_grad_aggregate_kernel, gridb, dim3(kThreadsGp), sizeof(GradSmem), st, t, y, diag, N, S0, w0, Q, jitter, eps, L.Tb,
              (const double *)at(L.off_rs), at(L.off_gpref), at(L.off_gcta));
   xo::launch(gp_grad_cta_scan_kernel, dim3((unsigned)B), dim3(kThreadsGp), 0, st, (const double *)at(L.off_gcta), L.nctas_b, at(L.off_gstate));
-  xo::launch(gp_grad_final_kernel, gridb, dim3(kThreadsGp), 0, st, t, y, diag, N, S0, w0, Q, jitter, eps, L.Tb, (const double *)at(L.off_rs),
+  xo::launch(gp_grad_final_kernel, gridb, dim3(kThreadsGp), sizeof(GradSmem), st, t, y, diag, N, S0, w0, Q, jitter, eps, L.Tb, (const double *)at(L.off_rs),
              (const double *)at(L.off_gpref), (const double *)at(L.off_gstate), gy, gdiag, at(L.off_gpart),
              reinterpret_cast<unsigned *>(ws + L.off_done), reinterpret_cast<GpStatus *>(ws), ghyper, gsum);
   return xo::launch_status();
