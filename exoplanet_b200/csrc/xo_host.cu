@@ -250,7 +250,7 @@ int xo_transit_logp_grad_host(const double *t, const double *y, const double *iv
   XO_TRY(ds.err);
   const size_t ws = xo_transit_logp_grad_workspace(N, C, P);
   Arena ar(3 * pad(N) + pad(C * P * XO_NEL) + pad(3 * C) + pad(C) + 2 * pad(K) + pad(C) + pad(C * P * XO_NGRAD) +
-               pad(3 * C) + pad(C) + pad(xo_transit_moments_len(N)) + pad(ws, 1),
+               pad(3 * C) + pad(C) + pad(XO_MOMENTS_LEN) + pad(ws, 1),
            ds.st);
   XO_TRY(ar.err);
   double *dt = ar.take<double>(N), *dy = ar.take<double>(N), *dv = ar.take<double>(N);
@@ -258,8 +258,7 @@ int xo_transit_logp_grad_host(const double *t, const double *y, const double *iv
   double *dd = ar.take<double>(K), *dw = ar.take<double>(K);
   double *dlp = ar.take<double>(C), *dge = ar.take<double>(C * P * XO_NGRAD), *dgc = ar.take<double>(3 * C),
          *dgm = ar.take<double>(C);
-  const size_t mom_len = xo_transit_moments_len(N);
-  double *dmom = ar.take<double>(mom_len);
+  double *dmom = ar.take<double>(XO_MOMENTS_LEN);
   void *dws = ar.take<char>(ws);
   XO_TRY(h2d(dt, t, (size_t)N * 8, ds.st));
   XO_TRY(h2d(dy, y, (size_t)N * 8, ds.st));
@@ -269,9 +268,8 @@ int xo_transit_logp_grad_host(const double *t, const double *y, const double *iv
   XO_TRY(h2d(dm, mean, (size_t)C * 8, ds.st));
   XO_TRY(h2d(dd, dtk, (size_t)K * 8, ds.st));
   XO_TRY(h2d(dw, wk, (size_t)K * 8, ds.st));
-  // data moments + time index (two small data-only kernels): the sweep then reads no time stamp, y / ivar only in transit
+  // data moments (one pass, a few microseconds): the sweep then reads t only and skips quiet steps
   XO_RC(xo_transit_data_moments(dt, dy, dv, N, dmom, ds.st));
-  XO_RC(xo_transit_data_index(dt, N, dmom, mom_len, ds.st));
   XO_RC(xo_transit_logp_grad(dt, dy, dv, N, del, dcl, dm, C, P, dd, dw, K, lognorm, dmom, dlp, dge, dgc, dgm, dws, ws, ds.st));
   XO_TRY(d2h(logp, dlp, (size_t)C * 8, ds.st));
   XO_TRY(d2h(gel, dge, (size_t)C * P * XO_NGRAD * 8, ds.st));
@@ -293,12 +291,11 @@ int xo_transit_model_logp_grad_host(const double *t, const double *y, const doub
   const size_t ws = xo_transit_model_workspace(N, C, P);
   const size_t nin = (size_t)C * P * XO_NPAR + (size_t)C * XO_NSTAR + (size_t)C + 2 * (size_t)K;
   const size_t nout = (size_t)C + (size_t)C * P * XO_NPAR + (size_t)C * XO_NSTAR + (size_t)C;
-  Arena ar(3 * pad(N) + pad(nin) + pad(nout) + pad(xo_transit_moments_len(N)) + pad(ws, 1), ds.st);
+  Arena ar(pad(3 * N) + pad(nin) + pad(nout) + pad(XO_MOMENTS_LEN) + pad(ws, 1), ds.st);
   XO_TRY(ar.err);
-  double *dt = ar.take<double>(N), *dy = ar.take<double>(N), *dv = ar.take<double>(N);
+  double *dt = ar.take<double>(3 * N), *dy = dt + N, *dv = dy + N;  // one block: one DMA when the caller's arrays are one block too
   double *din = ar.take<double>(nin), *dout = ar.take<double>(nout);
-  const size_t mom_len = xo_transit_moments_len(N);
-  double *dmom = ar.take<double>(mom_len);
+  double *dmom = ar.take<double>(XO_MOMENTS_LEN);
   void *dws = ar.take<char>(ws);
   double *dp = din, *dst = dp + C * P * XO_NPAR, *dm = dst + C * XO_NSTAR, *dd = dm + C, *dw = dd + K;
   double *dlp = dout, *dgp = dlp + C, *dgs = dgp + C * P * XO_NPAR, *dgm = dgs + C * XO_NSTAR;
@@ -310,10 +307,15 @@ int xo_transit_model_logp_grad_host(const double *t, const double *y, const doub
     ar.also_ev = ds.ev_join;
     XO_TRY(cudaEventRecord(ds.ev_fork, ds.st));  // the arena exists from here on in stream order
   }
-  // the light curve: three DMAs straight from the caller's (ideally pinned) memory, enqueued first
-  XO_TRY(h2d(dt, t, (size_t)N * 8, ds.st));
-  XO_TRY(h2d(dy, y, (size_t)N * 8, ds.st));
-  XO_TRY(h2d(dv, ivar, (size_t)N * 8, ds.st));
+  // the light curve straight from the caller's (ideally pinned) memory, enqueued first: ONE DMA when t, y, ivar are
+  // consecutive slices of one host block (y == t + N, ivar == y + N), else three
+  if (y == t + N && ivar == y + N) {
+    XO_TRY(h2d(dt, t, (size_t)3 * N * 8, ds.st));
+  } else {
+    XO_TRY(h2d(dt, t, (size_t)N * 8, ds.st));
+    XO_TRY(h2d(dy, y, (size_t)N * 8, ds.st));
+    XO_TRY(h2d(dv, ivar, (size_t)N * 8, ds.st));
+  }
   cudaStream_t ps = split ? ds.side : ds.st;  // the parameters and the prologue overlap that upload
   if (split) XO_TRY(cudaStreamWaitEvent(ps, ds.ev_fork, 0));
   {  // the parameters: packed through pinned staging -> one DMA
@@ -335,9 +337,9 @@ int xo_transit_model_logp_grad_host(const double *t, const double *y, const doub
                                      dgs, dgm, dws, ws, ps, 1));
     XO_TRY(cudaEventRecord(ds.ev_join, ps));
   }
-  // data moments + time index (two small data-only kernels): the sweep then reads no time stamp, y / ivar only in transit
+  // data moments (one pass, a few microseconds): the sweep then reads t only and skips quiet steps.  No time index here:
+  // building it costs more than it saves when the light curve is uploaded for a single evaluation (the resident handle has it)
   XO_RC(xo_transit_data_moments(dt, dy, dv, N, dmom, ds.st));
-  XO_RC(xo_transit_data_index(dt, N, dmom, mom_len, ds.st));
   if (split) {
     XO_TRY(cudaStreamWaitEvent(ds.st, ds.ev_join, 0));
     ar.also = nullptr;  // joined: the main stream is ordered after everything the side stream did

@@ -64,6 +64,18 @@ both)
   capture gpgagg "gp_grad_aggregate_kernel" 14 --steps 1 --warmup 3 --no-cpu --no-kepler --extra gp
   capture gpgfin "gp_grad_final_kernel" 14 --steps 1 --warmup 3 --no-cpu --no-kepler --extra gp
   ;;
+sweep)
+  run_pytest host tests/test_gpu_fused.py tests/test_gpu_ops.py
+  bench_line ours --steps 20 --warmup 5 --no-cpu --no-kepler --extra gp
+  : > $OUT/${TAG}_sweep.txt
+  one() { echo -n "$1: " >> $OUT/${TAG}_sweep.txt; env $1 timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu --no-kepler --no-extra 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value']), round(d['ms_per_step'],5), round(d['e2e']['value']), round(d['e2e_resident_data']['value']))" >> $OUT/${TAG}_sweep.txt; }
+  one XO_NOOP=1; one XO_NOOP=2
+  for ML in 1 2; do one XO_MODEL_LAUNCHES=$ML; done
+  one XO_MODEL_HEAVY_FIRST=1; one XO_MODEL_PDL=0
+  for W in 12 16 20 28 32 40 48; do one XO_TRANSIT_WARPS_PER_SM=$W; done
+  for MB in 2 4; do one XO_TRANSIT_MINBLOCKS=$MB; done
+  cat $OUT/${TAG}_sweep.txt
+  ;;
 final)
   run_pytest all tests
   for ML in 1 2; do XO_MODEL_LAUNCHES=$ML run_pytest launches$ML tests/test_gpu_fused.py; done
