@@ -50,12 +50,54 @@ constexpr unsigned kFull = 0xffffffffu;
 struct ChainSmem {
   double elem[XO_MAX_PLANETS][XO_NEL];
   double rperiod[XO_MAX_PLANETS];
-  double wlo[XO_MAX_PLANETS], whi[XO_MAX_PLANETS];  // window in units of the period (phase)
+  double wlo[XO_MAX_PLANETS], whi[XO_MAX_PLANETS];  // window in units of the period (phase); widened by ttv_dmax for the sweep
+  double ttv_dmax[XO_MAX_PLANETS];                  // TTV: largest departure of a transit time from t0 + j P (0 without a table)
   double cl[3];
   double mean;
   double dtk[XO_MAX_STENCIL];
   double wk[XO_MAX_STENCIL];
 };
+
+// ---- transit-time tables (TTVOrbit, /root/reference/src/exoplanet/orbits/ttv.py:149-187) -------------------------------
+// index of the transit nearest to t: the number of mid-points between consecutive transit times that lie below t
+// (ttv.py:159-178: searchsorted over the bin edges; the two outermost edges select the same values as their neighbours)
+__device__ __forceinline__ int ttv_index(const double *__restrict__ tt, int n, double t) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (0.5 * (__ldg(tt + mid) + __ldg(tt + mid + 1)) < t)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+// centre of "epoch" k of a table: the table entry inside it, the first / last transit continued with period P outside
+__device__ __forceinline__ double ttv_centre(const double *__restrict__ tt, int n, double per, long long k) {
+  if (k < 0) return fma((double)k, per, __ldg(tt));
+  if (k >= n) return fma((double)(k - n + 1), per, __ldg(tt + n - 1));
+  return __ldg(tt + k);
+}
+struct TtvView {  // the table of (chain c, planet p), or n = 0
+  const double *tt;
+  int n;
+};
+__device__ __forceinline__ TtvView ttv_view(const double *times, const int *count, int nt, int64_t c, int P, int p) {
+  return times ? TtvView{times + ((size_t)c * P + p) * nt, count[p]} : TtvView{nullptr, 0};
+}
+// time shift that maps a cadence at t onto the element block's own ephemeris: t - (tt[j] - t0)
+__device__ __forceinline__ double ttv_shift(const TtvView &v, double t0, double t, int *j_out = nullptr) {
+  if (v.n <= 0) return 0.0;
+  const int j = ttv_index(v.tt, v.n, t);
+  if (j_out) *j_out = j;
+  return __ldg(v.tt + j) - t0;
+}
+// largest |tt[j] - (t0 + j P)| of a table: how far the sweep's periodic window test must be widened
+__device__ __forceinline__ double ttv_departure(const TtvView &v, double t0, double per) {
+  double d = 0.0;
+  for (int j = 0; j < v.n; ++j) d = fmax(d, fabs(__ldg(v.tt + j) - fma((double)j, per, t0)));
+  return d;
+}
 
 __device__ __forceinline__ void stage_derived(ChainSmem &sm, int P) {
   if (threadIdx.x < P) {
@@ -63,6 +105,20 @@ __device__ __forceinline__ void stage_derived(ChainSmem &sm, int P) {
     sm.rperiod[threadIdx.x] = rp;
     sm.wlo[threadIdx.x] = sm.elem[threadIdx.x][XO_EL_TSTART] * rp;
     sm.whi[threadIdx.x] = sm.elem[threadIdx.x][XO_EL_TEND] * rp;
+    sm.ttv_dmax[threadIdx.x] = 0.0;
+  }
+  __syncthreads();
+}
+// with a transit-time table the sweep's periodic test runs on the linear ephemeris (t0, P) with the window widened by the
+// largest departure of the table from it: a superset of the in-transit cadences (the extra ones evaluate to exactly 0)
+__device__ __forceinline__ void stage_ttv(ChainSmem &sm, const double *times, const int *count, int nt, int64_t c, int P) {
+  if (!times) return;
+  if (threadIdx.x < P) {
+    const int p = threadIdx.x;
+    const double d = ttv_departure(ttv_view(times, count, nt, c, P, p), sm.elem[p][XO_EL_T0], sm.elem[p][XO_EL_PERIOD]);
+    sm.ttv_dmax[p] = d;
+    sm.wlo[p] -= d * sm.rperiod[p];
+    sm.whi[p] += d * sm.rperiod[p];
   }
   __syncthreads();
 }
@@ -124,14 +180,17 @@ __global__ void __launch_bounds__(256) transit_lc_fwd_kernel(const double *__res
                                                              const double *__restrict__ cl, int P,
                                                              const double *__restrict__ dtk,
                                                              const double *__restrict__ wk, int K,
+                                                             const double *__restrict__ ttv_times,
+                                                             const int *__restrict__ ttv_count, int ttv_nt,
                                                              double *__restrict__ lc) {
   __shared__ ChainSmem sm;
   const int64_t c = blockIdx.y;
   stage_chain(sm, elem, cl, nullptr, dtk, wk, c, P, K);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
-    const double tt = __ldg(t + i);
+    const double t_i = __ldg(t + i);
     for (int p = 0; p < P; ++p) {
+      const double tt = t_i - ttv_shift(ttv_view(ttv_times, ttv_count, ttv_nt, c, P, p), sm.elem[p][XO_EL_T0], t_i);
       double acc = 0.0;
       if (xo::in_window(sm.elem[p], sm.rperiod[p], tt)) {
         for (int k = 0; k < K; ++k)
@@ -148,15 +207,18 @@ __global__ void __launch_bounds__(256) transit_resid_kernel(const double *__rest
                                                             const double *__restrict__ elem, const double *__restrict__ cl,
                                                             const double *__restrict__ mean, int P,
                                                             const double *__restrict__ dtk, const double *__restrict__ wk, int K,
+                                                            const double *__restrict__ ttv_times,
+                                                            const int *__restrict__ ttv_count, int ttv_nt,
                                                             double *__restrict__ resid) {
   __shared__ ChainSmem sm;
   const int64_t c = blockIdx.y;
   stage_chain(sm, elem, cl, mean, dtk, wk, c, P, K);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
-    const double tt = __ldg(t + i);
+    const double t_i = __ldg(t + i);
     double model = sm.mean;
     for (int p = 0; p < P; ++p) {
+      const double tt = t_i - ttv_shift(ttv_view(ttv_times, ttv_count, ttv_nt, c, P, p), sm.elem[p][XO_EL_T0], t_i);
       if (xo::in_window(sm.elem[p], sm.rperiod[p], tt)) {
         for (int k = 0; k < K; ++k)
           model = fma(sm.wk[k], xo::lc_point<false>(sm.elem[p], sm.cl, tt + sm.dtk[k], 0.0, nullptr, nullptr), model);
@@ -301,6 +363,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
     stage_chain_from_params(sm, ma, mean, dtk, wk, c, P, K);
   else
     stage_chain(sm, elem, cl, mean, dtk, wk, c, P, K);
+  stage_ttv(sm, ma.ttv_times, ma.ttv_count, ma.ttv_nt, c, P);
   double *const gl = &lacc[0][threadIdx.x];          // g[j]  at gl[j * kThreads]
   double *const gsl = &lacc[XO_NGRAD][threadIdx.x];  // gs[j] at gsl[j * kThreads]
   double *const pa = &pacc[0][threadIdx.x];          // sum over this lane's samples of scale * g[j]
@@ -347,6 +410,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
       if (pcur >= 0) flush(pcur);
       pcur = p;
     }
+    double g0s = 0.0;  // TTV: this lane's cotangent-scaled d lc / d (transit time)
+    int jself = -1;    // ... and the transit it belongs to
     if (lane < m) {
       double scale;  // cotangent multiplying this lane's accumulated d lc / d elements
       const uint32_t idx = src[lane];
@@ -362,9 +427,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
         const bool self = (q == p);
         if (!self && (kVjp || !in_window_phase(sm, q, tt))) continue;
         if (q < p) owner = false;
+        // with a transit-time table the cadence is measured from its nearest transit (ttv.py:175-187)
+        int jq = -1;
+        const double ttq = tt - ttv_shift(ttv_view(ma.ttv_times, ma.ttv_count, ma.ttv_nt, c, P, q), sm.elem[q][XO_EL_T0], tt, &jq);
+        if (self) jself = jq;
         for (int k = 0; k < K; ++k) {
           const double w = sm.wk[k];
-          ltot = fma(w, xo::lc_point<true, kThreads>(sm.elem[q], sm.cl, tt + sm.dtk[k], self ? w : 0.0, gl, gsl), ltot);
+          ltot = fma(w, xo::lc_point<true, kThreads>(sm.elem[q], sm.cl, ttq + sm.dtk[k], self ? w : 0.0, gl, gsl), ltot);
         }
       }
       if (kVjp) {
@@ -377,6 +446,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
           gm = fma(-iv, ltot, gm);
         }
       }
+      g0s = scale * gl[0];
       gc0 = fma(scale, gsl[0], gc0);
       gc1 = fma(scale, gsl[kThreads], gc1);
       gc2 = fma(scale, gsl[2 * kThreads], gc2);
@@ -388,6 +458,20 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
         gl[j * kThreads] = 0.0;
       }
       gl[kThreads] = 0.0;
+    }
+    if (ma.ttv_grad) {
+      // d / d (transit time): the entries of a drain are in cadence order, so the lanes of one transit are adjacent --
+      // segmented sum in lane order, one atomic per transit and drain
+      double v = g0s;
+      const int key = jself;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double o = __shfl_up_sync(kFull, v, d);
+        const int ko = __shfl_up_sync(kFull, key, d);
+        if (lane >= d && ko == key) v += o;
+      }
+      const int kn = __shfl_down_sync(kFull, key, 1);
+      if (key >= 0 && (lane == 31 || kn != key)) atomicAdd(ma.ttv_grad + ((size_t)c * P + p) * ma.ttv_nt + key, v);
     }
   };
 
@@ -421,7 +505,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
     if (lane < P && start < end) {
       const double per = sm.elem[lane][XO_EL_PERIOD], t0p = sm.elem[lane][XO_EL_T0];
       const double tA = __ldg(t + start), tB = __ldg(t + end - 1);
-      const double fa = floor((tA - t0p) * sm.rperiod[lane] - 0.5) - 1.0, fb = ceil((tB - t0p) * sm.rperiod[lane] + 0.5) + 1.0;
+      const double dm = sm.ttv_dmax[lane];  // 0 without a transit-time table
+      const double fa = floor((tA - t0p - dm) * sm.rperiod[lane] - 0.5) - 1.0, fb = ceil((tB - t0p + dm) * sm.rperiod[lane] + 0.5) + 1.0;
       dense = !(per > 0.0) || !(fb - fa <= (double)(end - start) + 4.0);
       if (!dense) {
         ka = (long long)fa;
@@ -472,13 +557,24 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
             const TimeIndex ix{reinterpret_cast<const uint32_t *>(moments + XO_MOMENTS_LEN), nbins, __ldg(t), moments[6]};
             const double per = sm.elem[p][XO_EL_PERIOD], t0p = sm.elem[p][XO_EL_T0], hp = 0.5 * per;
             const double ts = sm.elem[p][XO_EL_TSTART], te = sm.elem[p][XO_EL_TEND];
-            const double tc = fma((double)k, per, t0p);
-            // the window clipped to the epoch's own period; the clip boundary B_k = t0 + (k + 1/2) P is computed by the
-            // same expression on both sides, so consecutive epochs neither overlap nor leave a gap
-            const uint32_t i0 = (ts > -hp) ? index_bound<false>(t, (uint32_t)N, ix, tc + ts)
-                                           : index_bound<false>(t, (uint32_t)N, ix, fma((double)k - 0.5, per, t0p));
-            const uint32_t i1 = (te < hp) ? index_bound<true>(t, (uint32_t)N, ix, tc + te)
-                                          : index_bound<false>(t, (uint32_t)N, ix, fma((double)k + 0.5, per, t0p));
+            const TtvView tv = ttv_view(ma.ttv_times, ma.ttv_count, ma.ttv_nt, c, P, p);
+            uint32_t i0, i1;
+            if (tv.n > 0) {
+              // epoch k of a transit-time table: the cadences nearest to transit k (between the mid-points to its
+              // neighbours: (m_{k-1}, m_k], ttv.py:159-178) that fall inside the window around it
+              const double ck = ttv_centre(tv.tt, tv.n, per, k);
+              const double mlo = 0.5 * (ttv_centre(tv.tt, tv.n, per, k - 1) + ck), mhi = 0.5 * (ck + ttv_centre(tv.tt, tv.n, per, k + 1));
+              i0 = (ck + ts > mlo) ? index_bound<false>(t, (uint32_t)N, ix, ck + ts) : index_bound<true>(t, (uint32_t)N, ix, mlo);
+              i1 = (ck + te < mhi) ? index_bound<true>(t, (uint32_t)N, ix, ck + te) : index_bound<true>(t, (uint32_t)N, ix, mhi);
+            } else {
+              const double tc = fma((double)k, per, t0p);
+              // the window clipped to the epoch's own period; the clip boundary B_k = t0 + (k + 1/2) P is computed by the
+              // same expression on both sides, so consecutive epochs neither overlap nor leave a gap
+              i0 = (ts > -hp) ? index_bound<false>(t, (uint32_t)N, ix, tc + ts)
+                              : index_bound<false>(t, (uint32_t)N, ix, fma((double)k - 0.5, per, t0p));
+              i1 = (te < hp) ? index_bound<true>(t, (uint32_t)N, ix, tc + te)
+                             : index_bound<false>(t, (uint32_t)N, ix, fma((double)k + 0.5, per, t0p));
+            }
             lo = max(i0, start);
             const uint32_t hi = min(i1, end);
             cnt = hi > lo ? hi - lo : 0u;
@@ -1007,14 +1103,27 @@ void launch_transit_logp_grad(const double *t, const double *y, const double *iv
 #undef XO_LAUNCH
 }
 
-void launch_transit_resid(const double *t, const double *y, int64_t N, const double *elem, const double *cl, const double *mean,
-                          int64_t C, int P, const double *dtk, const double *wk, int K, double *resid, cudaStream_t st) {
+void launch_transit_lc_fwd(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int P, const double *dtk,
+                           const double *wk, int K, const double *ttv_times, const int *ttv_count, int ttv_nt, double *lc,
+                           cudaStream_t st) {
   const int sms = sm_count();
   int64_t per_chain = (N + 255) / 256;
   int64_t want = ((int64_t)sms * 8 + C - 1) / C;
   int gx = (int)(per_chain < want ? per_chain : want);
   if (gx < 1) gx = 1;
-  xo::launch(transit_resid_kernel, dim3(gx, (unsigned)C), dim3(256), 0, st, t, y, N, elem, cl, mean, P, dtk, wk, K, resid);
+  xo::launch(transit_lc_fwd_kernel, dim3(gx, (unsigned)C), dim3(256), 0, st, t, N, elem, cl, P, dtk, wk, K, ttv_times, ttv_count, ttv_nt, lc);
+}
+
+void launch_transit_resid(const double *t, const double *y, int64_t N, const double *elem, const double *cl, const double *mean,
+                          int64_t C, int P, const double *dtk, const double *wk, int K, double *resid, cudaStream_t st,
+                          const double *ttv_times, const int *ttv_count, int ttv_nt) {
+  const int sms = sm_count();
+  int64_t per_chain = (N + 255) / 256;
+  int64_t want = ((int64_t)sms * 8 + C - 1) / C;
+  int gx = (int)(per_chain < want ? per_chain : want);
+  if (gx < 1) gx = 1;
+  xo::launch(transit_resid_kernel, dim3(gx, (unsigned)C), dim3(256), 0, st, t, y, N, elem, cl, mean, P, dtk, wk, K, ttv_times, ttv_count,
+             ttv_nt, resid);
 }
 
 void launch_chain_order(const double *elem, int64_t C, int P, int *order, cudaStream_t st) {
@@ -1034,13 +1143,19 @@ int xo_transit_lc_fwd(const double *t, int64_t N, const double *elem, const doub
   if (K < 1 || K > XO_MAX_STENCIL) return XO_ERANGE;
   if (N == 0 || C == 0 || P == 0) return 0;
   if (!t || !elem || !cl || !dtk || !wk || !lc) return XO_EINVAL;
-  const int sms = xo::sm_count();
-  int64_t per_chain = (N + 255) / 256;
-  int64_t want = ((int64_t)sms * 8 + C - 1) / C;
-  int gx = (int)(per_chain < want ? per_chain : want);
-  if (gx < 1) gx = 1;
-  dim3 grid(gx, (unsigned)C);
-  xo::launch(transit_lc_fwd_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), t, N, elem, cl, (int)P, dtk, wk, K, lc);
+  xo::launch_transit_lc_fwd(t, N, elem, cl, C, (int)P, dtk, wk, K, nullptr, nullptr, 0, lc, static_cast<cudaStream_t>(stream));
+  return xo::launch_status();
+}
+
+// ---- the same three entry points for a TTVOrbit (/root/reference/src/exoplanet/orbits/ttv.py:35-187) ----
+int xo_transit_lc_fwd_ttv(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
+                          const double *dtk, const double *wk, int K, const double *ttv_times, const int *ttv_count, int ttv_nt,
+                          double *lc, void *stream) {
+  if (int rc = check_batch(N, C, P)) return rc;
+  if (K < 1 || K > XO_MAX_STENCIL) return XO_ERANGE;
+  if (N == 0 || C == 0 || P == 0) return 0;
+  if (!t || !elem || !cl || !dtk || !wk || !lc || !ttv_times || !ttv_count || ttv_nt < 1) return XO_EINVAL;
+  xo::launch_transit_lc_fwd(t, N, elem, cl, C, (int)P, dtk, wk, K, ttv_times, ttv_count, ttv_nt, lc, static_cast<cudaStream_t>(stream));
   return xo::launch_status();
 }
 
@@ -1116,6 +1231,69 @@ int xo_transit_lc_vjp(const double *t, int64_t N, const double *elem, const doub
   const int64_t tot = C * nacc;
   xo::launch(fold_partials_kernel, (unsigned)((tot + 127) / 128), 128, 0, st, partial, sp.slots, nacc, C, (int)P, 0.0, scratch, gel,
                                                                       gcl, scratch + C);
+  return xo::launch_status();
+}
+
+int xo_transit_logp_grad_ttv(const double *t, const double *y, const double *ivar, int64_t N, const double *elem,
+                             const double *cl, const double *mean, int64_t C, int64_t P, const double *dtk, const double *wk,
+                             int K, double lognorm, const double *moments, const double *ttv_times, const int *ttv_count,
+                             int ttv_nt, double *logp, double *gel, double *gcl, double *gmean, double *gttv, void *workspace,
+                             size_t workspace_bytes, void *stream) {
+  if (int rc = check_batch(N, C, P)) return rc;
+  if (K < 1 || K > XO_MAX_STENCIL) return XO_ERANGE;
+  if (C == 0) return 0;
+  if (N == 0 || P == 0) return XO_EINVAL;
+  if (!t || !y || !ivar || !elem || !cl || !mean || !dtk || !wk || !logp || !gel || !gcl || !gmean || !gttv || !workspace ||
+      !ttv_times || !ttv_count || ttv_nt < 1)
+    return XO_EINVAL;
+  if (workspace_bytes < xo_transit_logp_grad_workspace(N, C, P)) return XO_EWORKSPACE;
+  Split sp = split_transit(N, C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(gttv, 0, sizeof(double) * (size_t)C * P * ttv_nt, st);
+  if (e != cudaSuccess) return -(int)e;
+  double *partial = static_cast<double *>(workspace);
+  xo::ModelArgs ma;
+  ma.elements_only = 1;
+  ma.ttv_times = ttv_times;
+  ma.ttv_count = ttv_count;
+  ma.ttv_nt = ttv_nt;
+  ma.ttv_grad = gttv;
+  xo::launch_transit_logp_grad(t, y, ivar, N, elem, cl, mean, C, (int)P, dtk, wk, K, sp, moments, partial, st, &ma);
+  const int nacc = kNBase + (int)P * XO_NGRAD;
+  const int64_t tot = C * nacc;
+  xo::launch(fold_partials_kernel, (unsigned)((tot + 127) / 128), 128, 0, st, partial, sp.slots, nacc, C, (int)P, lognorm, logp, gel, gcl,
+             gmean);
+  return xo::launch_status();
+}
+
+int xo_transit_lc_vjp_ttv(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
+                          const double *dtk, const double *wk, int K, const double *ttv_times, const int *ttv_count, int ttv_nt,
+                          const double *bar_lc, double *gel, double *gcl, double *gttv, void *workspace, size_t workspace_bytes,
+                          void *stream) {
+  if (int rc = check_batch(N, C, P)) return rc;
+  if (K < 1 || K > XO_MAX_STENCIL) return XO_ERANGE;
+  if (C == 0) return 0;
+  if (N == 0 || P == 0) return XO_EINVAL;
+  if (!t || !elem || !cl || !dtk || !wk || !bar_lc || !gel || !gcl || !gttv || !workspace || !ttv_times || !ttv_count || ttv_nt < 1)
+    return XO_EINVAL;
+  if (workspace_bytes < xo_transit_logp_grad_workspace(N, C, P) + sizeof(double) * 2 * (size_t)C) return XO_EWORKSPACE;
+  Split sp = split_transit(N, C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(gttv, 0, sizeof(double) * (size_t)C * P * ttv_nt, st);
+  if (e != cudaSuccess) return -(int)e;
+  double *partial = static_cast<double *>(workspace);
+  double *scratch = partial + (size_t)C * sp.slots * (kNBase + P * XO_NGRAD);
+  xo::ModelArgs ma;
+  ma.elements_only = 1;
+  ma.ttv_times = ttv_times;
+  ma.ttv_count = ttv_count;
+  ma.ttv_nt = ttv_nt;
+  ma.ttv_grad = gttv;
+  xo::launch_transit_logp_grad(t, bar_lc, nullptr, N, elem, cl, nullptr, C, (int)P, dtk, wk, K, sp, nullptr, partial, st, &ma);
+  const int nacc = kNBase + (int)P * XO_NGRAD;
+  const int64_t tot = C * nacc;
+  xo::launch(fold_partials_kernel, (unsigned)((tot + 127) / 128), 128, 0, st, partial, sp.slots, nacc, C, (int)P, 0.0, scratch, gel, gcl,
+             scratch + C);
   return xo::launch_status();
 }
 

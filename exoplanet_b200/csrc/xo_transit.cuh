@@ -34,7 +34,20 @@ struct ModelArgs {
   // (d/d lc of a likelihood of the residual y - mean - sum_p lc), and gmean is taken from -vjp_gsum[2 c]
   int vjp_shared = 0;
   const double *vjp_gsum = nullptr;
+  // TTVOrbit (/root/reference/src/exoplanet/orbits/ttv.py:175-187): per (chain, planet) the sorted table of transit times
+  // ttv_times[C][P][ttv_nt] (all_transit_times; ttv_count[p] valid entries).  A cadence is measured from the NEAREST transit
+  // (bin edges half-way between consecutive transits) instead of from elem[XO_EL_T0]; ttv_grad[C][P][ttv_nt] receives
+  // d / d transit time (zero-initialised by the caller; accumulated with atomics).
+  const double *ttv_times = nullptr;
+  const int *ttv_count = nullptr;
+  int ttv_nt = 0;
+  double *ttv_grad = nullptr;
 };
+
+// light curve forward with an optional transit-time table (lc[C][N][P])
+void launch_transit_lc_fwd(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int P, const double *dtk,
+                           const double *wk, int K, const double *ttv_times, const int *ttv_count, int ttv_nt, double *lc,
+                           cudaStream_t st);
 
 // enqueue transit_logp_grad_kernel; partial[C][slots][kNBase + P*XO_NGRAD]; model != nullptr
 // selects the single-launch model mode (elem / cl are then ignored)
@@ -54,7 +67,8 @@ int model_logp_grad_phases(const double *t, const double *y, const double *ivar,
 
 // resid[C][N] = y[n] - mean[c] - sum_p lc[c][n][p]   (what a noise model of the residuals consumes)
 void launch_transit_resid(const double *t, const double *y, int64_t N, const double *elem, const double *cl, const double *mean,
-                          int64_t C, int P, const double *dtk, const double *wk, int K, double *resid, cudaStream_t st);
+                          int64_t C, int P, const double *dtk, const double *wk, int K, double *resid, cudaStream_t st,
+                          const double *ttv_times = nullptr, const int *ttv_count = nullptr, int ttv_nt = 0);
 // fold of the per-warp partials + reverse pass of the prologue (xo_model.cu)
 int launch_model_epilogue(const double *par, const double *star, const double *partial, int slots, int64_t C, int P, double lognorm,
                           double *logp, double *gpar, double *gstar, double *gmean, cudaStream_t st, bool pdl);

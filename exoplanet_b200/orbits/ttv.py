@@ -2,7 +2,9 @@
 so transit-timing variations move the transits without changing their shape.  Host-side mirror
 of /root/reference/src/exoplanet/orbits/ttv.py:35-187 over torch; only ``_warp_times`` differs
 from ``KeplerianOrbit`` (one ``searchsorted`` per cadence before the same Kepler solve), so light
-curves go through ``LimbDarkLightCurve``'s generic op-by-op path."""
+curves of a TTVOrbit go through the same fused kernels with the transit-time table as an extra argument
+(``ttv_table()`` -> ``xo_transit_lc_fwd_ttv`` / ``xo_transit_lc_vjp_ttv``); every other method uses the inherited
+op-by-op code."""
 import numpy as np
 import torch
 
@@ -81,5 +83,19 @@ class TTVOrbit(KeplerianOrbit):
         t = _tensor(t, self.device)
         return (t.unsqueeze(-1) if _pad else t) - self._nearest_transit(t)
 
-    def elements(self, *args, **kwargs):
-        raise NotImplementedError("TTVOrbit has no single element table; light curves use the generic path")
+    def ttv_table(self):
+        """(times[P, NT], count[P] int32): the transit-time tables the fused kernels take (``xo_transit_*_ttv``) -- row p is
+        ``all_transit_times[p]`` (differentiable), padded past ``count[p]`` by continuing the last transit with the period."""
+        nt = max(int(tt.shape[0]) for tt in self.all_transit_times)
+        rows = []
+        for i, tt in enumerate(self.all_transit_times):
+            n = int(tt.shape[0])
+            if n < nt:
+                extra = tt[-1] + self.period.reshape(-1)[i] * torch.arange(1, nt - n + 1, device=self.device, dtype=torch.float64)
+                tt = torch.cat([tt, extra])
+            rows.append(tt)
+        count = torch.tensor([int(tt.shape[0]) for tt in self.all_transit_times], dtype=torch.int32, device=self.device)
+        return torch.stack(rows), count
+
+    # ``elements()`` is inherited: the element block's (t0, period) is the linear ephemeris transit j departs from
+    # (transit j near t0 + j period), which is what the fused kernels' sweep tests against.

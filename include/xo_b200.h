@@ -149,6 +149,25 @@ int xo_transit_model_logp_grad(const double *t, const double *y, const double *i
 int xo_elements_from_params(const double *par, const double *star, int64_t C, int64_t P, double texp, int use_in_transit,
                             double *elem, double *cl, void *stream);
 
+/* ---- the same three entry points for a TTVOrbit (/root/reference/src/exoplanet/orbits/ttv.py:35-187) ----
+ * ttv_times[C][P][ttv_nt]: per (chain, planet) the sorted transit times (TTVOrbit.all_transit_times), ttv_count[P] (device
+ * int array) valid entries each.  A cadence is measured from its NEAREST transit (bin edges half-way between consecutive
+ * transits, ttv.py:159-187) instead of from elem[XO_EL_T0]; elem[XO_EL_T0] / XO_EL_PERIOD must be the linear ephemeris the
+ * table departs from (transit j near t0 + j P).  gttv[C][P][ttv_nt] = d / d transit time (zeroed by the call, accumulated
+ * with one atomic per transit and warp: sums of more than two partials may differ in the last bit between runs). */
+int xo_transit_lc_fwd_ttv(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
+                          const double *dtk, const double *wk, int K, const double *ttv_times, const int *ttv_count, int ttv_nt,
+                          double *lc, void *stream);
+int xo_transit_lc_vjp_ttv(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
+                          const double *dtk, const double *wk, int K, const double *ttv_times, const int *ttv_count, int ttv_nt,
+                          const double *bar_lc, double *gel, double *gcl, double *gttv, void *workspace, size_t workspace_bytes,
+                          void *stream);
+int xo_transit_logp_grad_ttv(const double *t, const double *y, const double *ivar, int64_t N, const double *elem,
+                             const double *cl, const double *mean, int64_t C, int64_t P, const double *dtk, const double *wk,
+                             int K, double lognorm, const double *moments, const double *ttv_times, const int *ttv_count,
+                             int ttv_nt, double *logp, double *gel, double *gcl, double *gmean, double *gttv, void *workspace,
+                             size_t workspace_bytes, void *stream);
+
 /* relative position / R_star and RV shape for every (chain, cadence, planet):
  * X,Y,Z,rv each [C][N][P], any may be NULL (keplerian.py:380-409, 658-670) */
 int xo_orbit_eval(const double *t, int64_t N, const double *elem, int64_t C, int64_t P, double *X, double *Y, double *Z,

@@ -201,6 +201,81 @@ def test_ttv_orbit_matches_reference_fixture(golden):
     assert np.max(np.abs(got - np.array(f["lc"]))) < 1e-12
 
 
+def test_ttv_fused_kernels_match_generic_path_values_and_gradients(golden):
+    """the fused TTV kernels (transit-time table as a kernel argument: light curve forward, its reverse pass with one
+    gradient per transit time, and the logp+grad kernel with both sweeps) against the op-by-op torch path, which itself
+    reproduces the reference fixture above"""
+    import ctypes as C
+
+    from exoplanet_b200 import _lib
+    from exoplanet_b200.light_curves import LimbDarkLightCurve
+    from exoplanet_b200.orbits import TTVOrbit
+
+    s = golden("reference_glue")["ttv"]
+    sh = s["shape"]
+    t = dev(s["t"])
+    r = dev(s["r"])
+    leaves = dict(period=dev(s["periods"]).requires_grad_(True), t0=dev(s["t0"]).requires_grad_(True),
+                  ecc=dev(sh["ecc"]).requires_grad_(True), omega=dev(sh["omega"]).requires_grad_(True), b=dev(sh["b"]).requires_grad_(True))
+    ttvs = [dev(v).requires_grad_(True) for v in s["ttvs"]]
+
+    def orbit():
+        return TTVOrbit(period=leaves["period"], t0=leaves["t0"], ttvs=ttvs, transit_inds=[np.array(i) for i in s["transit_inds"]],
+                        ecc=leaves["ecc"], omega=leaves["omega"], b=leaves["b"], r_star=sh["r_star"], m_star=sh["m_star"], device=DEV)
+
+    lc = LimbDarkLightCurve(s["u"][0], s["u"][1], device=DEV)
+    w = torch.linspace(0.5, 1.5, t.numel(), dtype=torch.float64, device=DEV)[:, None] * dev([1.0, -0.7])[None, :]
+    params = list(leaves.values()) + ttvs
+    for kw in ({}, dict(texp=0.05, oversample=5)):
+        fused_lc = lc.get_light_curve(orbit=orbit(), r=r, t=t, **kw)
+        o = orbit()
+        generic = lc._generic_light_curve(o, r, t, kw.get("texp"), kw.get("oversample", 7), 0, True, False)
+        assert torch.max(torch.abs(fused_lc - generic)).item() < 1e-13
+        assert torch.equal(fused_lc == 0.0, generic == 0.0)
+        ref = np.array(s["lc_texp" if kw else "lc"])
+        assert np.max(np.abs(fused_lc.detach().cpu().numpy() - ref)) < 1e-13
+        ga = torch.autograd.grad((fused_lc * w).sum(), params, allow_unused=True)
+        gb = torch.autograd.grad((generic * w).sum(), params, allow_unused=True)
+        for a, b_, name in zip(ga, gb, list(leaves) + ["ttv0", "ttv1"]):
+            assert a is not None and b_ is not None, name
+            assert torch.max(torch.abs(a - b_)).item() < 1e-8 * (b_.abs().max().item() + 1e-12), (name, a, b_)
+    # logp + grad with the table: indexed sweep (moments + time index) == stepping sweep == light-curve composition
+    o = orbit()
+    elem = o.elements(r=r).detach()[None].contiguous()
+    times, count = o.ttv_table()
+    times = times.detach()[None].contiguous()
+    cl = lc.c.detach()[None].contiguous()
+    N = t.numel()
+    truth = lc.get_light_curve(orbit=o, r=r, t=t).detach().sum(-1)
+    y = truth + dev(synthetic.noise(N, SIGMA))
+    data = fused.TransitData(np.array(s["t"]), y.cpu().numpy(), np.full(N, SIGMA), device=DEV)
+    lib = _lib.require_cuda()
+    ptr = lambda x: C.c_void_p(x.data_ptr()) if x is not None else None  # noqa: E731
+    mean = dev([1e-4])
+    dtk, wk = fused._stencil_dev(fused.exposure_stencil(None), torch.device(DEV))
+    res = {}
+    for mode in ("indexed", "stepping"):
+        ws = torch.empty(lib.xo_transit_logp_grad_workspace(N, 1, 2) // 8 + 1, dtype=torch.float64, device=DEV)
+        out = [torch.empty(1, dtype=torch.float64, device=DEV), torch.empty((1, 2, 10), dtype=torch.float64, device=DEV),
+               torch.empty((1, 3), dtype=torch.float64, device=DEV), torch.empty(1, dtype=torch.float64, device=DEV),
+               torch.empty_like(times)]
+        mom = data.moments() if mode == "indexed" else None
+        _lib.check(lib.xo_transit_logp_grad_ttv(ptr(data.t), ptr(data.y), ptr(data.ivar), N, ptr(elem), ptr(cl), ptr(mean), 1, 2, ptr(dtk), ptr(wk),
+                                                1, data.lognorm, ptr(mom), ptr(times), ptr(count), times.shape[-1], *[ptr(x) for x in out],
+                                                ptr(ws), ws.numel() * 8, _lib.stream_ptr()), "logp_grad_ttv")
+        res[mode] = [x.clone() for x in out]
+    for a, b_ in zip(res["indexed"], res["stepping"]):
+        assert torch.allclose(a, b_, rtol=1e-10, atol=1e-10 * b_.abs().max().item())
+    # against autograd through the fused light curve: logp = lognorm - 1/2 sum ivar (y - mean - sum_p lc)^2
+    lcv = lc.get_light_curve(orbit=orbit(), r=r, t=t)
+    logp = data.lognorm - 0.5 * (data.ivar * (data.y - mean - lcv.sum(-1)) ** 2).sum()
+    assert abs(res["indexed"][0].item() - logp.item()) < 1e-11 * abs(logp.item())
+    gt = torch.autograd.grad(logp, ttvs)
+    for p_, (g_, inds) in enumerate(zip(gt, s["transit_inds"])):
+        got = res["indexed"][4][0, p_, torch.as_tensor(inds, device=DEV)]
+        assert torch.max(torch.abs(got - g_)).item() < 1e-8 * g_.abs().max().item(), (p_, got, g_)
+
+
 # ------------------------------------------------------------------------------------------ f4: NUTS on the device
 def test_batched_nuts_on_device_gaussian_target():
     """lock-step NUTS on cuda: correlated-scale Gaussian, 256 chains; means and variances recovered"""

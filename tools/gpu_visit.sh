@@ -65,7 +65,7 @@ both)
   capture gpgfin "gp_grad_final_kernel" 14 --steps 1 --warmup 3 --no-cpu --no-kepler --extra gp
   ;;
 sweep)
-  run_pytest host tests/test_gpu_fused.py tests/test_gpu_ops.py
+  run_pytest host tests/test_gpu_fused.py tests/test_gpu_ops.py tests/test_gpu_configs.py tests/test_reference_glue.py tests/test_pytensor_ops.py
   bench_line ours --steps 20 --warmup 5 --no-cpu --no-kepler --extra gp
   : > $OUT/${TAG}_sweep.txt
   one() { echo -n "$1: " >> $OUT/${TAG}_sweep.txt; env $1 timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu --no-kepler --no-extra 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value']), round(d['ms_per_step'],5), round(d['e2e']['value']), round(d['e2e_resident_data']['value']))" >> $OUT/${TAG}_sweep.txt; }
