@@ -21,7 +21,7 @@ MAX_STENCIL = 33
 MAX_PLANETS = 8
 
 # element-block indices (include/xo_b200.h)
-EL_T0, EL_TREF, EL_N, EL_ECC, EL_COSW, EL_SINW, EL_COSI, EL_SINI, EL_AOR, EL_ROR, EL_PERIOD, EL_TSTART, EL_TEND, EL_KRV = range(14)
+EL_T0, EL_TREF, EL_N, EL_ECC, EL_COSW, EL_SINW, EL_COSI, EL_SINI, EL_AOR, EL_ROR, EL_PERIOD, EL_TSTART, EL_TEND, EL_KRV, EL_RSTAR = range(15)
 
 
 class XoError(RuntimeError):
@@ -45,8 +45,8 @@ _SIGNATURES = {
     "xo_contact_points": (_i32, [_vp] * 10 + [_i64, _vp]),
     "xo_transit_lc_fwd": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _vp]),
     "xo_transit_lc_vjp": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "xo_transit_lc_fwd_ttv": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp]),
-    "xo_transit_lc_vjp_ttv": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "xo_transit_lc_fwd_ex": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "xo_transit_lc_vjp_ex": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "xo_transit_logp_grad_ttv": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _dbl, _vp, _vp, _vp, _i32, _vp, _vp,
                                         _vp, _vp, _vp, _vp, _sz, _vp]),
     "xo_transit_logp_grad_workspace": (_sz, [_i64, _i64, _i64]),

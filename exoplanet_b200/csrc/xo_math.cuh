@@ -544,8 +544,72 @@ XO_HD void true_anomaly(const double *el, double tt, double &sf, double &cf, dou
 // sini,aor,ror) into g[10] and w * s into gs[3] (= w * d lc / d cl).
 // kStride: element stride of g / gs (1 for plain arrays; blockDim for per-thread columns of a
 // shared-memory matrix, which keeps the 13 accumulators out of registers during the heavy math).
-template <bool kGrad, int kStride = 1>
+// Light-travel delay (keplerian.py:411-470, _get_retarded_position with a -> -a, z0 = 0): the body is seen where it was
+// at the retarded time t - D, with D from its position, line-of-sight velocity and acceleration at t:
+//   z = R rr si swf,  vz = -n R aor si (e cw + cwf) / sqrt(1 - e^2),  az = -n^2 ((1 + e cf) / (1 - e^2))^3 z   [R_sun, days]
+//   D = (c/az) (u - sqrt(u^2 + 2 az z / c^2)), u = 1 + vz/c       (|az| < 1e-10:  D = -z / (c + vz))
+// R = r_star is element XO_EL_RSTAR (slot 14; 0 = no light delay).  kGrad: also d D / d (t0, tref, n, e, cw, sw, si, aor)
+// into dD[0..7] (si at index 6, aor at 7) -- the chain rule of the second solve needs them.
+constexpr double kCLight = 37231.66360672704;  // R_sun / day (orbits/constants.py:36)
+template <bool kGrad>
+XO_HD double light_delay(const double *el, double tt, double R, double *dD) {
+  double sf, cf, tm;
+  true_anomaly(el, tt, sf, cf, tm);
+  const double n = el[2], e = el[3], cw = el[4], sw = el[5], si = el[7], aor = el[8];
+  const double ome2 = (1.0 - e) * (1.0 + e), opc = fma(e, cf, 1.0);
+  const double rso = 1.0 / sqrt(ome2);
+  const double rr = aor * ome2 / opc;
+  const double cwf = cw * cf - sw * sf, swf = sw * cf + cw * sf;
+  const double z = R * rr * si * swf;
+  const double kv = -n * R * aor * si * rso;  // d vz / d (e cw + cwf)
+  const double vz = kv * fma(e, cw, cwf);
+  const double q = opc / ome2;
+  const double az = -n * n * q * q * q * z;
+  const double rc = 1.0 / kCLight, u = fma(vz, rc, 1.0);
+  double D, Dz, Dvz, Daz;
+  if (fabs(az) < 1.0e-10) {
+    const double rden = 1.0 / (kCLight + vz);
+    D = -z * rden;
+    Dz = -rden;
+    Dvz = z * rden * rden;
+    Daz = 0.0;
+  } else {
+    const double s = sqrt(fma(u, u, 2.0 * az * z * rc * rc));
+    D = (kCLight / az) * (u - s);
+    Dz = -rc / s;
+    Dvz = (1.0 - u / s) / az;
+    Daz = -D / az - z * rc / (az * s);
+  }
+  if (kGrad) {
+    const double bz = Dz - Daz * n * n * q * q * q, bvz = Dvz, bq = Daz * 3.0 * az / q;
+    const double brr = bz * R * si * swf, bswf = bz * R * si * rr, bcwf = bvz * kv;
+    const double bcf = -brr * rr * e / opc + bswf * sw + bcwf * cw + bq * e / ome2;
+    const double bsf = bswf * cw - bcwf * sw;
+    double be = brr * aor * (-2.0 * e * opc - ome2 * cf) / (opc * opc) + bvz * (kv * cw + vz * e / ome2) +
+                bq * (cf * ome2 + 2.0 * e * opc) / (ome2 * ome2);
+    const double dfdM = opc * opc * rso * rso * rso, dfde = (2.0 + e * cf) * sf / ome2;
+    const double bf = bsf * cf - bcf * sf;
+    const double bM = bf * dfdM;
+    be += bf * dfde;
+    dD[0] = dD[1] = -bM * n;
+    dD[2] = bM * tm + bvz * vz / n + Daz * 2.0 * az / n;
+    dD[3] = be;
+    dD[4] = bswf * sf + bcwf * cf + bvz * kv * e;
+    dD[5] = bswf * cf - bcwf * sf;
+    dD[6] = bz * R * rr * swf + bvz * vz / si;
+    dD[7] = brr * rr / aor + bvz * vz / aor;
+  }
+  return D;
+}
+
+template <bool kGrad, int kStride = 1, bool kDelay = false>
 XO_HD double lc_point(const double *el, const double *cl, double tt, double w, double *g, double *gs) {
+  double dD[8];
+  bool delayed = false;
+  if (kDelay && el[14] > 0.0) {  // XO_EL_RSTAR: light-travel delay on
+    tt -= light_delay<kGrad>(el, tt, el[14], dD);
+    delayed = true;
+  }
   double sf, cf, tm;
   true_anomaly(el, tt, sf, cf, tm);
   const double e = el[3], cw = el[4], sw = el[5], ci = el[6], si = el[7], aor = el[8], ror = el[9];
@@ -598,6 +662,16 @@ XO_HD double lc_point(const double *el, const double *cl, double tt, double w, d
   g[6 * kStride] = fma(dldb, db_dci, g[6 * kStride]);
   g[8 * kStride] = fma(dldb, db_drr * rr * rcp_fast(aor), g[8 * kStride]);
   g[9 * kStride] += dldr;
+  if (kDelay && delayed) {  // t' = t - D(theta): d lc / d theta += (d lc / d t') (-d D / d theta), d lc / d t' = -gt
+    g[0] = fma(gt, dD[0], g[0]);
+    g[kStride] = fma(gt, dD[1], g[kStride]);
+    g[2 * kStride] = fma(gt, dD[2], g[2 * kStride]);
+    g[3 * kStride] = fma(gt, dD[3], g[3 * kStride]);
+    g[4 * kStride] = fma(gt, dD[4], g[4 * kStride]);
+    g[5 * kStride] = fma(gt, dD[5], g[5 * kStride]);
+    g[7 * kStride] = fma(gt, dD[6], g[7 * kStride]);
+    g[8 * kStride] = fma(gt, dD[7], g[8 * kStride]);
+  }
   return lc;
 }
 

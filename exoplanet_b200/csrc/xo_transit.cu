@@ -175,6 +175,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ---------------------------------------------------------------------------
 // light curve forward: lc[C][N][P]
 // ---------------------------------------------------------------------------
+template <bool kDelay>
 __global__ void __launch_bounds__(256) transit_lc_fwd_kernel(const double *__restrict__ t, int64_t N,
                                                              const double *__restrict__ elem,
                                                              const double *__restrict__ cl, int P,
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(256) transit_lc_fwd_kernel(const double *__res
       double acc = 0.0;
       if (xo::in_window(sm.elem[p], sm.rperiod[p], tt)) {
         for (int k = 0; k < K; ++k)
-          acc = fma(sm.wk[k], xo::lc_point<false>(sm.elem[p], sm.cl, tt + sm.dtk[k], 0.0, nullptr, nullptr), acc);
+          acc = fma(sm.wk[k], xo::lc_point<false, 1, kDelay>(sm.elem[p], sm.cl, tt + sm.dtk[k], 0.0, nullptr, nullptr), acc);
       }
       __stcs(lc + (c * N + i) * P + p, acc);
     }
@@ -324,7 +325,9 @@ struct WarpIndexState {
 //              computed once per data set by transit_moments_kernel); the sweep then reads t only.
 // kModel     : single-launch model evaluation: elements from parameters at CTA start (ma.par/star),
 //              and the last CTA of each chain folds the partials and runs the reverse prologue.
-template <int kMinBlocks, bool kVjp, bool kMoments, bool kModel>
+// kDelay     : light-travel delay in the sample evaluation (element XO_EL_RSTAR > 0); sin i then carries a gradient
+// kTtv       : transit-time tables (ma.ttv_*): compiled out of the ordinary kernels
+template <int kMinBlocks, bool kVjp, bool kMoments, bool kModel, bool kDelay = false, bool kTtv = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel(
     const double *__restrict__ t, const double *__restrict__ y, const double *__restrict__ ivar, int64_t N,
     const double *__restrict__ elem, const double *__restrict__ cl, const double *__restrict__ mean, int P,
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
     stage_chain_from_params(sm, ma, mean, dtk, wk, c, P, K);
   else
     stage_chain(sm, elem, cl, mean, dtk, wk, c, P, K);
-  stage_ttv(sm, ma.ttv_times, ma.ttv_count, ma.ttv_nt, c, P);
+  if (kTtv) stage_ttv(sm, ma.ttv_times, ma.ttv_count, ma.ttv_nt, c, P);
   double *const gl = &lacc[0][threadIdx.x];          // g[j]  at gl[j * kThreads]
   double *const gsl = &lacc[XO_NGRAD][threadIdx.x];  // gs[j] at gsl[j * kThreads]
   double *const pa = &pacc[0][threadIdx.x];          // sum over this lane's samples of scale * g[j]
@@ -388,7 +391,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
   // once per drain
   auto flush = [&](int p) {
     __syncwarp();
-    if (lane < XO_NGRAD && lane != 1 && lane != 7) {  // d/dtref == d/dt0; sin i carries no gradient
+    if (lane < XO_NGRAD && lane != 1 && (kDelay || lane != 7)) {  // d/dtref == d/dt0; sin i carries a gradient only through the light delay
       const double v = row_sum(&pacc[0][warp * 32]);
       gacc[warp][p][lane] += v;
       if (lane == 0) gacc[warp][p][1] += v;
@@ -429,11 +432,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
         if (q < p) owner = false;
         // with a transit-time table the cadence is measured from its nearest transit (ttv.py:175-187)
         int jq = -1;
-        const double ttq = tt - ttv_shift(ttv_view(ma.ttv_times, ma.ttv_count, ma.ttv_nt, c, P, q), sm.elem[q][XO_EL_T0], tt, &jq);
+        const double ttq = kTtv ? tt - ttv_shift(ttv_view(ma.ttv_times, ma.ttv_count, ma.ttv_nt, c, P, q), sm.elem[q][XO_EL_T0], tt, &jq) : tt;
         if (self) jself = jq;
         for (int k = 0; k < K; ++k) {
           const double w = sm.wk[k];
-          ltot = fma(w, xo::lc_point<true, kThreads>(sm.elem[q], sm.cl, ttq + sm.dtk[k], self ? w : 0.0, gl, gsl), ltot);
+          ltot = fma(w, xo::lc_point<true, kThreads, kDelay>(sm.elem[q], sm.cl, ttq + sm.dtk[k], self ? w : 0.0, gl, gsl), ltot);
         }
       }
       if (kVjp) {
@@ -453,13 +456,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
       gsl[0] = gsl[kThreads] = gsl[2 * kThreads] = 0.0;
 #pragma unroll
       for (int j = 0; j < XO_NGRAD; ++j) {
-        if (j == 1 || j == 7) continue;
+        if (j == 1 || (j == 7 && !kDelay)) continue;
         pa[j * kThreads] = fma(scale, gl[j * kThreads], pa[j * kThreads]);
         gl[j * kThreads] = 0.0;
       }
       gl[kThreads] = 0.0;
     }
-    if (ma.ttv_grad) {
+    if (kTtv && ma.ttv_grad) {
       // d / d (transit time): the entries of a drain are in cadence order, so the lanes of one transit are adjacent --
       // segmented sum in lane order, one atomic per transit and drain
       double v = g0s;
@@ -505,7 +508,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
     if (lane < P && start < end) {
       const double per = sm.elem[lane][XO_EL_PERIOD], t0p = sm.elem[lane][XO_EL_T0];
       const double tA = __ldg(t + start), tB = __ldg(t + end - 1);
-      const double dm = sm.ttv_dmax[lane];  // 0 without a transit-time table
+      const double dm = kTtv ? sm.ttv_dmax[lane] : 0.0;  // 0 without a transit-time table
       const double fa = floor((tA - t0p - dm) * sm.rperiod[lane] - 0.5) - 1.0, fb = ceil((tB - t0p + dm) * sm.rperiod[lane] + 0.5) + 1.0;
       dense = !(per > 0.0) || !(fb - fa <= (double)(end - start) + 4.0);
       if (!dense) {
@@ -557,9 +560,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
             const TimeIndex ix{reinterpret_cast<const uint32_t *>(moments + XO_MOMENTS_LEN), nbins, __ldg(t), moments[6]};
             const double per = sm.elem[p][XO_EL_PERIOD], t0p = sm.elem[p][XO_EL_T0], hp = 0.5 * per;
             const double ts = sm.elem[p][XO_EL_TSTART], te = sm.elem[p][XO_EL_TEND];
-            const TtvView tv = ttv_view(ma.ttv_times, ma.ttv_count, ma.ttv_nt, c, P, p);
+            const TtvView tv = kTtv ? ttv_view(ma.ttv_times, ma.ttv_count, ma.ttv_nt, c, P, p) : TtvView{nullptr, 0};
             uint32_t i0, i1;
-            if (tv.n > 0) {
+            if (kTtv && tv.n > 0) {
               // epoch k of a transit-time table: the cadences nearest to transit k (between the mid-points to its
               // neighbours: (m_{k-1}, m_k], ttv.py:159-178) that fall inside the window around it
               const double ck = ttv_centre(tv.tt, tv.n, per, k);
@@ -1080,8 +1083,22 @@ void launch_transit_logp_grad(const double *t, const double *y, const double *iv
 #define XO_LAUNCH(MB, VJP, MOM, MODEL)                                                                                    \
   xo::launch_pdl(transit_logp_grad_kernel<MB, VJP, MOM, MODEL>, grid, dim3(kThreads), st, pdl, t, y, ivar, N, elem, cl, mean, P, \
                  dtk, wk, K, sp.L, sp.slots, moments, partial, ma)
+#define XO_LAUNCH_TTV(VJP, MOM)                                                                                                    \
+  xo::launch_pdl(transit_logp_grad_kernel<3, VJP, MOM, false, false, true>, grid, dim3(kThreads), st, pdl, t, y, ivar, N, elem, cl, mean, \
+                 P, dtk, wk, K, sp.L, sp.slots, moments, partial, ma)
+  if (ma.ttv_times) {  // TTVOrbit: element-level launches only
+    if (ivar == nullptr) XO_LAUNCH_TTV(true, false);
+    else if (moments) XO_LAUNCH_TTV(false, true);
+    else XO_LAUNCH_TTV(false, false);
+    return;
+  }
+#undef XO_LAUNCH_TTV
   if (ivar == nullptr) {  // light-curve VJP mode: y = bar_lc[C][N][P] (or -ybar[C][N] with model->vjp_shared)
-    XO_LAUNCH(3, true, false, false);
+    if (ma.light_delay)
+      xo::launch_pdl(transit_logp_grad_kernel<3, true, false, false, true>, grid, dim3(kThreads), st, pdl, t, y, ivar, N, elem, cl, mean, P,
+                     dtk, wk, K, sp.L, sp.slots, moments, partial, ma);
+    else
+      XO_LAUNCH(3, true, false, false);
     return;
   }
   const int mb = transit_min_blocks();
@@ -1105,13 +1122,18 @@ void launch_transit_logp_grad(const double *t, const double *y, const double *iv
 
 void launch_transit_lc_fwd(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int P, const double *dtk,
                            const double *wk, int K, const double *ttv_times, const int *ttv_count, int ttv_nt, double *lc,
-                           cudaStream_t st) {
+                           cudaStream_t st, bool light_delay) {
   const int sms = sm_count();
   int64_t per_chain = (N + 255) / 256;
   int64_t want = ((int64_t)sms * 8 + C - 1) / C;
   int gx = (int)(per_chain < want ? per_chain : want);
   if (gx < 1) gx = 1;
-  xo::launch(transit_lc_fwd_kernel, dim3(gx, (unsigned)C), dim3(256), 0, st, t, N, elem, cl, P, dtk, wk, K, ttv_times, ttv_count, ttv_nt, lc);
+  if (light_delay)
+    xo::launch(transit_lc_fwd_kernel<true>, dim3(gx, (unsigned)C), dim3(256), 0, st, t, N, elem, cl, P, dtk, wk, K, ttv_times, ttv_count,
+               ttv_nt, lc);
+  else
+    xo::launch(transit_lc_fwd_kernel<false>, dim3(gx, (unsigned)C), dim3(256), 0, st, t, N, elem, cl, P, dtk, wk, K, ttv_times, ttv_count,
+               ttv_nt, lc);
 }
 
 void launch_transit_resid(const double *t, const double *y, int64_t N, const double *elem, const double *cl, const double *mean,
@@ -1148,14 +1170,17 @@ int xo_transit_lc_fwd(const double *t, int64_t N, const double *elem, const doub
 }
 
 // ---- the same three entry points for a TTVOrbit (/root/reference/src/exoplanet/orbits/ttv.py:35-187) ----
-int xo_transit_lc_fwd_ttv(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
-                          const double *dtk, const double *wk, int K, const double *ttv_times, const int *ttv_count, int ttv_nt,
-                          double *lc, void *stream) {
+int xo_transit_lc_fwd_ex(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
+                         const double *dtk, const double *wk, int K, const double *ttv_times, const int *ttv_count, int ttv_nt,
+                         int light_delay, double *lc, void *stream) {
   if (int rc = check_batch(N, C, P)) return rc;
   if (K < 1 || K > XO_MAX_STENCIL) return XO_ERANGE;
   if (N == 0 || C == 0 || P == 0) return 0;
-  if (!t || !elem || !cl || !dtk || !wk || !lc || !ttv_times || !ttv_count || ttv_nt < 1) return XO_EINVAL;
-  xo::launch_transit_lc_fwd(t, N, elem, cl, C, (int)P, dtk, wk, K, ttv_times, ttv_count, ttv_nt, lc, static_cast<cudaStream_t>(stream));
+  if (!t || !elem || !cl || !dtk || !wk || !lc) return XO_EINVAL;
+  if (ttv_times && (!ttv_count || ttv_nt < 1)) return XO_EINVAL;
+  if (ttv_times && light_delay) return XO_EINVAL;  // the reference has no such combination either (ttv.py has no delayed path)
+  xo::launch_transit_lc_fwd(t, N, elem, cl, C, (int)P, dtk, wk, K, ttv_times, ttv_count, ttv_nt, lc, static_cast<cudaStream_t>(stream),
+                            light_delay != 0);
   return xo::launch_status();
 }
 
@@ -1266,21 +1291,23 @@ int xo_transit_logp_grad_ttv(const double *t, const double *y, const double *iva
   return xo::launch_status();
 }
 
-int xo_transit_lc_vjp_ttv(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
-                          const double *dtk, const double *wk, int K, const double *ttv_times, const int *ttv_count, int ttv_nt,
-                          const double *bar_lc, double *gel, double *gcl, double *gttv, void *workspace, size_t workspace_bytes,
-                          void *stream) {
+int xo_transit_lc_vjp_ex(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
+                         const double *dtk, const double *wk, int K, const double *ttv_times, const int *ttv_count, int ttv_nt,
+                         int light_delay, const double *bar_lc, double *gel, double *gcl, double *gttv, void *workspace,
+                         size_t workspace_bytes, void *stream) {
   if (int rc = check_batch(N, C, P)) return rc;
   if (K < 1 || K > XO_MAX_STENCIL) return XO_ERANGE;
   if (C == 0) return 0;
   if (N == 0 || P == 0) return XO_EINVAL;
-  if (!t || !elem || !cl || !dtk || !wk || !bar_lc || !gel || !gcl || !gttv || !workspace || !ttv_times || !ttv_count || ttv_nt < 1)
-    return XO_EINVAL;
+  if (!t || !elem || !cl || !dtk || !wk || !bar_lc || !gel || !gcl || !workspace) return XO_EINVAL;
+  if (ttv_times && (!ttv_count || ttv_nt < 1 || !gttv || light_delay)) return XO_EINVAL;
   if (workspace_bytes < xo_transit_logp_grad_workspace(N, C, P) + sizeof(double) * 2 * (size_t)C) return XO_EWORKSPACE;
   Split sp = split_transit(N, C);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(gttv, 0, sizeof(double) * (size_t)C * P * ttv_nt, st);
-  if (e != cudaSuccess) return -(int)e;
+  if (ttv_times) {
+    cudaError_t e = cudaMemsetAsync(gttv, 0, sizeof(double) * (size_t)C * P * ttv_nt, st);
+    if (e != cudaSuccess) return -(int)e;
+  }
   double *partial = static_cast<double *>(workspace);
   double *scratch = partial + (size_t)C * sp.slots * (kNBase + P * XO_NGRAD);
   xo::ModelArgs ma;
@@ -1288,7 +1315,8 @@ int xo_transit_lc_vjp_ttv(const double *t, int64_t N, const double *elem, const 
   ma.ttv_times = ttv_times;
   ma.ttv_count = ttv_count;
   ma.ttv_nt = ttv_nt;
-  ma.ttv_grad = gttv;
+  ma.ttv_grad = ttv_times ? gttv : nullptr;
+  ma.light_delay = light_delay != 0;
   xo::launch_transit_logp_grad(t, bar_lc, nullptr, N, elem, cl, nullptr, C, (int)P, dtk, wk, K, sp, nullptr, partial, st, &ma);
   const int nacc = kNBase + (int)P * XO_NGRAD;
   const int64_t tot = C * nacc;

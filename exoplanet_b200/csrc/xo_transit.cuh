@@ -42,12 +42,14 @@ struct ModelArgs {
   const int *ttv_count = nullptr;
   int ttv_nt = 0;
   double *ttv_grad = nullptr;
+  // light-curve VJP mode only: light-travel delay (keplerian.py:411-470); the element blocks carry R_star in XO_EL_RSTAR
+  int light_delay = 0;
 };
 
 // light curve forward with an optional transit-time table (lc[C][N][P])
 void launch_transit_lc_fwd(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int P, const double *dtk,
                            const double *wk, int K, const double *ttv_times, const int *ttv_count, int ttv_nt, double *lc,
-                           cudaStream_t st);
+                           cudaStream_t st, bool light_delay = false);
 
 // enqueue transit_logp_grad_kernel; partial[C][slots][kNBase + P*XO_NGRAD]; model != nullptr
 // selects the single-launch model mode (elem / cl are then ignored)

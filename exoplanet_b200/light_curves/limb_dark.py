@@ -58,6 +58,42 @@ class _FusedLightCurve(torch.autograd.Function):
         return full, gcl[0], None, None, None
 
 
+class _FusedLightCurveDelay(torch.autograd.Function):
+    """lc[N, P] with light-travel delay (keplerian.py:411-470): every sample at its retarded time (a second Kepler solve in
+    the kernel); gradients w.r.t. the element table (sin i included) and cl.  elem[:, 14] = R_star."""
+
+    @staticmethod
+    def forward(ctx, elem, cl, t, dtk, wk):
+        lib = _lib.require_cuda()
+        e3 = elem.detach().contiguous().unsqueeze(0)
+        c2 = cl.detach().contiguous().unsqueeze(0)
+        P = e3.shape[1]
+        lc = torch.empty((1, t.numel(), P), dtype=torch.float64, device=t.device)
+        with torch.cuda.device(t.device):
+            _lib.check(lib.xo_transit_lc_fwd_ex(_ptr(t), t.numel(), _ptr(e3), _ptr(c2), 1, P, _ptr(dtk), _ptr(wk), dtk.numel(), None, None, 0,
+                                                1, _ptr(lc), _lib.stream_ptr()), "transit_lc_fwd_ex")
+        ctx.save_for_backward(e3, c2, t, dtk, wk)
+        return lc[0]
+
+    @staticmethod
+    def backward(ctx, bar):
+        lib = _lib.require_cuda()
+        e3, c2, t, dtk, wk = ctx.saved_tensors
+        P = e3.shape[1]
+        bar = bar.contiguous().unsqueeze(0)
+        need = lib.xo_transit_logp_grad_workspace(t.numel(), 1, P) + 16
+        ws = torch.empty(need // 8 + 2, dtype=torch.float64, device=t.device)
+        gel = torch.empty((1, P, _lib.NGRAD), dtype=torch.float64, device=t.device)
+        gcl = torch.empty((1, 3), dtype=torch.float64, device=t.device)
+        with torch.cuda.device(t.device):
+            _lib.check(lib.xo_transit_lc_vjp_ex(_ptr(t), t.numel(), _ptr(e3), _ptr(c2), 1, P, _ptr(dtk), _ptr(wk), dtk.numel(), None, None, 0,
+                                                1, _ptr(bar), _ptr(gel), _ptr(gcl), None, _ptr(ws), ws.numel() * 8, _lib.stream_ptr()),
+                       "transit_lc_vjp_ex")
+        full = torch.zeros_like(e3[0])
+        full[:, :_lib.NGRAD] = gel[0]
+        return full, gcl[0], None, None, None
+
+
 class _FusedLightCurveTTV(torch.autograd.Function):
     """lc[N, P] = f(elem[P, 16], cl[3], transit times[P, NT]) for a TTVOrbit (ttv.py:175-187: every cadence is measured
     from its nearest transit); gradients w.r.t. the element table, cl and every transit time."""
@@ -71,8 +107,8 @@ class _FusedLightCurveTTV(torch.autograd.Function):
         P, nt = tt.shape
         lc = torch.empty((1, t.numel(), P), dtype=torch.float64, device=t.device)
         with torch.cuda.device(t.device):
-            _lib.check(lib.xo_transit_lc_fwd_ttv(_ptr(t), t.numel(), _ptr(e3), _ptr(c2), 1, P, _ptr(dtk), _ptr(wk), dtk.numel(), _ptr(tt),
-                                                 _ptr(count), nt, _ptr(lc), _lib.stream_ptr()), "transit_lc_fwd_ttv")
+            _lib.check(lib.xo_transit_lc_fwd_ex(_ptr(t), t.numel(), _ptr(e3), _ptr(c2), 1, P, _ptr(dtk), _ptr(wk), dtk.numel(), _ptr(tt),
+                                                _ptr(count), nt, 0, _ptr(lc), _lib.stream_ptr()), "transit_lc_fwd_ex")
         ctx.save_for_backward(e3, c2, tt, t, dtk, wk, count)
         return lc[0]
 
@@ -88,9 +124,9 @@ class _FusedLightCurveTTV(torch.autograd.Function):
         gcl = torch.empty((1, 3), dtype=torch.float64, device=t.device)
         gtt = torch.empty((1, P, nt), dtype=torch.float64, device=t.device)
         with torch.cuda.device(t.device):
-            _lib.check(lib.xo_transit_lc_vjp_ttv(_ptr(t), t.numel(), _ptr(e3), _ptr(c2), 1, P, _ptr(dtk), _ptr(wk), dtk.numel(), _ptr(tt),
-                                                 _ptr(count), nt, _ptr(bar), _ptr(gel), _ptr(gcl), _ptr(gtt), _ptr(ws), ws.numel() * 8,
-                                                 _lib.stream_ptr()), "transit_lc_vjp_ttv")
+            _lib.check(lib.xo_transit_lc_vjp_ex(_ptr(t), t.numel(), _ptr(e3), _ptr(c2), 1, P, _ptr(dtk), _ptr(wk), dtk.numel(), _ptr(tt),
+                                                _ptr(count), nt, 0, _ptr(bar), _ptr(gel), _ptr(gcl), _ptr(gtt), _ptr(ws), ws.numel() * 8,
+                                                _lib.stream_ptr()), "transit_lc_vjp_ex")
         full = torch.zeros_like(e3[0])
         full[:, :_lib.NGRAD] = gel[0]
         full[:, 0] = 0.0  # the time axis is anchored on the transit times, not on elem's t0 (its derivative is in gtt)
@@ -145,6 +181,13 @@ class LimbDarkLightCurve:
             elem = orbit.elements(r=r, texp=tex, use_in_transit=use_in_transit)
             dtk, wk = fused._stencil_dev(fused.exposure_stencil(tex, oversample, order), dev)
             return _FusedLightCurve.apply(elem, self.c, t.contiguous(), dtk, wk)
+        if type(orbit) is KeplerianOrbit and light_delay and scalar_texp and t.dim() == 1 and t.is_cuda and not (
+                isinstance(orbit.r_star, torch.Tensor) and orbit.r_star.requires_grad):
+            # the fused delay kernels do not return d / d R_star: an R_star that is being differentiated takes the op-by-op path
+            tex = None if texp is None else float(texp)
+            elem = orbit.elements(r=r, texp=tex, use_in_transit=bool(use_in_transit), light_delay=True)
+            dtk, wk = fused._stencil_dev(fused.exposure_stencil(tex, oversample, order), dev)
+            return _FusedLightCurveDelay.apply(elem, self.c, t.contiguous(), dtk, wk)
         from ..orbits.ttv import TTVOrbit
 
         if type(orbit) is TTVOrbit and not light_delay and scalar_texp and t.dim() == 1 and t.is_cuda:

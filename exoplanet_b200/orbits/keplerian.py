@@ -197,9 +197,12 @@ class KeplerianOrbit:
         self.tref = self.t_periastron - self.t0
 
     # ------------------------------------------------------------------ element table
-    def elements(self, r=None, texp=None, use_in_transit=True, K=None):
+    def elements(self, r=None, texp=None, use_in_transit=True, K=None, light_delay=False):
         """[P, 16] element blocks for the fused kernels (include/xo_b200.h).  ``r`` is the planet
-        radius in R_sun (same convention as ``get_light_curve``)."""
+        radius in R_sun (same convention as ``get_light_curve``).  ``light_delay``: slot XO_EL_RSTAR carries R_star (the
+        delay is dimensional) and the window is the ordinary one widened by the largest possible delay -- the reference
+        evaluates every cadence in this mode (keplerian.py:720-723), which gives the same light curve because the flux is
+        exactly 0 outside the contact points."""
         ror_in = None if r is None else _tensor(r, self.device).reshape(-1) / self.r_star
         z = torch.zeros_like(self.a + self.period + self.t0).reshape(-1)
         if ror_in is not None:
@@ -218,7 +221,12 @@ class KeplerianOrbit:
         else:
             ts, te = torch.full_like(z, -float("inf")), torch.full_like(z, float("inf"))
         Kc = z if K is None else _tensor(K, self.device) + z
-        cols = [self.t0 + z, self.tref + z, n, ecc, cw, sw, cosi, sini, a / self.r_star, ror, period, ts, te, Kc, z, z]
+        rs = z
+        if light_delay:
+            rs = (self.r_star + z).detach()
+            margin = (2.0 * a * (1.0 + ecc) / _el.C_LIGHT).detach()
+            ts, te = ts - margin, te + margin
+        cols = [self.t0 + z, self.tref + z, n, ecc, cw, sw, cosi, sini, a / self.r_star, ror, period, ts, te, Kc, rs, z]
         return torch.stack(cols, dim=-1).reshape(-1, 16)
 
     # ------------------------------------------------------------------ anomalies

@@ -149,19 +149,26 @@ int xo_transit_model_logp_grad(const double *t, const double *y, const double *i
 int xo_elements_from_params(const double *par, const double *star, int64_t C, int64_t P, double texp, int use_in_transit,
                             double *elem, double *cl, void *stream);
 
-/* ---- the same three entry points for a TTVOrbit (/root/reference/src/exoplanet/orbits/ttv.py:35-187) ----
- * ttv_times[C][P][ttv_nt]: per (chain, planet) the sorted transit times (TTVOrbit.all_transit_times), ttv_count[P] (device
- * int array) valid entries each.  A cadence is measured from its NEAREST transit (bin edges half-way between consecutive
- * transits, ttv.py:159-187) instead of from elem[XO_EL_T0]; elem[XO_EL_T0] / XO_EL_PERIOD must be the linear ephemeris the
- * table departs from (transit j near t0 + j P).  gttv[C][P][ttv_nt] = d / d transit time (zeroed by the call, accumulated
- * with one atomic per transit and warp: sums of more than two partials may differ in the last bit between runs). */
-int xo_transit_lc_fwd_ttv(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
-                          const double *dtk, const double *wk, int K, const double *ttv_times, const int *ttv_count, int ttv_nt,
-                          double *lc, void *stream);
-int xo_transit_lc_vjp_ttv(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
-                          const double *dtk, const double *wk, int K, const double *ttv_times, const int *ttv_count, int ttv_nt,
-                          const double *bar_lc, double *gel, double *gcl, double *gttv, void *workspace, size_t workspace_bytes,
-                          void *stream);
+/* ---- the re-entrant callers of the same kernel: TTVOrbit and light-travel delay ----
+ * TTVOrbit (/root/reference/src/exoplanet/orbits/ttv.py:35-187): ttv_times[C][P][ttv_nt] holds, per (chain, planet), the sorted
+ * transit times (TTVOrbit.all_transit_times), ttv_count[P] (DEVICE int array) valid entries each; NULL = ordinary orbit.
+ * A cadence is measured from its NEAREST transit (bin edges half-way between consecutive transits, ttv.py:159-187) instead
+ * of from elem[XO_EL_T0]; elem[XO_EL_T0] / XO_EL_PERIOD must be the linear ephemeris the table departs from (transit j near
+ * t0 + j P).  gttv[C][P][ttv_nt] = d / d transit time (zeroed by the call, accumulated with one atomic per transit and warp:
+ * sums of more than two partials may differ in the last bit between runs).
+ * Light-travel delay (orbits/keplerian.py:411-470, get_relative_position(light_delay=True) -> limb_dark.py:215): light_delay
+ * != 0 and elem[XO_EL_RSTAR] = R_star in R_sun; every sample is evaluated at the retarded time t - D(position, line-of-sight
+ * velocity and acceleration at t) -- a second Kepler solve -- and the reverse pass carries d D / d elements (sin i included;
+ * d / d R_star is not provided).  The reference evaluates every cadence in this mode (in_transit raises for light_delay,
+ * keplerian.py:720-723): pass the window of an ordinary orbit widened by 2 a (1 + e) / c, or (-inf, +inf). */
+#define XO_EL_RSTAR 14
+int xo_transit_lc_fwd_ex(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
+                         const double *dtk, const double *wk, int K, const double *ttv_times, const int *ttv_count, int ttv_nt,
+                         int light_delay, double *lc, void *stream);
+int xo_transit_lc_vjp_ex(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
+                         const double *dtk, const double *wk, int K, const double *ttv_times, const int *ttv_count, int ttv_nt,
+                         int light_delay, const double *bar_lc, double *gel, double *gcl, double *gttv, void *workspace,
+                         size_t workspace_bytes, void *stream);
 int xo_transit_logp_grad_ttv(const double *t, const double *y, const double *ivar, int64_t N, const double *elem,
                              const double *cl, const double *mean, int64_t C, int64_t P, const double *dtk, const double *wk,
                              int K, double lognorm, const double *moments, const double *ttv_times, const int *ttv_count,

@@ -235,6 +235,9 @@ def main():
     for order in (0, 1, 2):
         s1["lc_texp_order%d" % order] = arr(lc.get_light_curve(orbit=orbit, r=r_pl, t=tt, texp=0.1, oversample=7, order=order))
     s1["lc_texp_os4"] = arr(lc.get_light_curve(orbit=orbit, r=r_pl, t=tt, texp=0.05, oversample=4))
+    # light-travel delay (keplerian.py:411-470): every cadence evaluated at its retarded position (limb_dark.py:156,215)
+    s1["lc_light_delay"] = arr(lc.get_light_curve(orbit=orbit, r=r_pl, t=tt, light_delay=True))
+    s1["lc_light_delay_texp"] = arr(lc.get_light_curve(orbit=orbit, r=r_pl, t=tt, texp=0.1, oversample=7, light_delay=True))
     out["two_planets"] = s1
 
     # ---- scenario 2: circular, single planet, impact parameter (data-and-models tutorial shape)
