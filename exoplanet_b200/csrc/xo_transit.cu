@@ -407,6 +407,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
   const double mean_c = sm.mean;
   const uint32_t lt_mask = (1u << lane) - 1u;
 
+  bool indexed = false;  // this warp enumerates transit epochs through the time index (set below, before the first drain)
   // evaluate m (<= 32) queued entries src[0..m) of planet p
   auto drain = [&](int p, const uint32_t *src, int m) {
     if (p != pcur) {
@@ -428,11 +429,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
       // planet that is also in transit at this cadence with weight 0 (value only)
       for (int q = 0; q < P; ++q) {
         const bool self = (q == p);
-        if (!self && (kVjp || !in_window_phase(sm, q, tt))) continue;
-        if (q < p) owner = false;
+        if (!self && kVjp) continue;
         // with a transit-time table the cadence is measured from its nearest transit (ttv.py:175-187)
         int jq = -1;
         const double ttq = kTtv ? tt - ttv_shift(ttv_view(ma.ttv_times, ma.ttv_count, ma.ttv_nt, c, P, q), sm.elem[q][XO_EL_T0], tt, &jq) : tt;
+        // "is this cadence also in planet q's queue?" must be the producer's own predicate, or the per-cadence terms are
+        // owned twice / by nobody: the stepping producer tests the (TTV: widened) phase window, the indexed one the exact
+        // window around the nearest transit
+        if (!self && !((kTtv && indexed) ? xo::in_window(sm.elem[q], sm.rperiod[q], ttq) : in_window_phase(sm, q, tt))) continue;
+        if (q < p) owner = false;
         if (self) jself = jq;
         for (int k = 0; k < K; ++k) {
           const double w = sm.wk[k];
@@ -501,7 +506,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
   auto pool = [&](int p) -> uint32_t * { return kPoolInQueue ? &queue[0][p][32] : pool_own[kPoolInQueue ? 0 : p]; };
   // epoch range of every planet over this warp's cadences (lane p: planet p).  A planet with more epochs than cadences in
   // the range (or a non-finite / non-positive period) cannot be enumerated: the whole warp then takes the stepping producer.
-  bool indexed = false;
   if (kMoments && nbins > 0) {
     long long ka = 1, kb = 0;
     bool dense = false;
@@ -516,7 +520,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
         kb = (long long)fb;
       }
     }
-    indexed = !__any_sync(kFull, dense);
+    // CTA-uniform: in the final pass a warp also drains entries the other warps of the CTA queued, and the drain's
+    // "is this cadence in planet q's queue too" predicate depends on the producer
+    indexed = __syncthreads_and(!__any_sync(kFull, dense)) != 0;
     if (indexed) {
       WarpIndexState &W = widx[warp];
       W.kfirst[lane] = ka;
@@ -1049,13 +1055,13 @@ int transit_min_blocks() {
   return v;
 }
 static int transit_warps_per_sm() {
-  static int v = env_int("XO_TRANSIT_WARPS_PER_SM", 24);
+  static int v = env_int("XO_TRANSIT_WARPS_PER_SM", 20);  // re-measured in round 2 (profiles/r02_tuning_sweep.txt): 20 beats 24 by 2 %
   return v;
 }
 
 Split split_transit(int64_t N, int64_t C) {
   const int sms = sm_count();
-  // aim at ~24 warps per SM over the whole launch, at least 256 cadences per warp
+  // aim at ~20 warps per SM over the whole launch, at least 256 cadences per warp
   int64_t target = ((int64_t)sms * transit_warps_per_sm() + C - 1) / C;
   int64_t maxw = (N + 255) / 256;
   int64_t w = target < 1 ? 1 : (target > maxw ? maxw : target);
