@@ -64,6 +64,16 @@ both)
   capture gpgagg "gp_grad_aggregate_kernel" 14 --steps 1 --warmup 3 --no-cpu --no-kepler --extra gp
   capture gpgfin "gp_grad_final_kernel" 14 --steps 1 --warmup 3 --no-cpu --no-kepler --extra gp
   ;;
+scale)
+  # usage: gpurun --gpus N -- 'NG=N bash tools/gpu_visit.sh TAG scale'
+  TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29517"
+  timeout 900 $TR bench.py --gpus $NG --steps 20 --warmup 5 > $OUT/${TAG}_bench_${NG}gpu.json 2> $OUT/${TAG}_bench_${NG}gpu.err; echo "bench($NG gpu) exit $?" >> $OUT/${TAG}_bench_${NG}gpu.err
+  timeout 900 $TR bench.py --gpus $NG --steps 20 --warmup 5 --same-seed --no-kepler > $OUT/${TAG}_bench_${NG}gpu_sameseed.json 2> $OUT/${TAG}_bench_${NG}gpu_sameseed.err; echo "bench($NG gpu, same seed) exit $?" >> $OUT/${TAG}_bench_${NG}gpu_sameseed.err
+  [ "$NG" = "2" ] && timeout 600 $TR bench.py --impl reference --gpus $NG --steps 20 --warmup 5 > $OUT/${TAG}_bench_${NG}gpu_ref.json 2> $OUT/${TAG}_bench_${NG}gpu_ref.err; echo "bench($NG gpu, reference arm) exit $?" >> $OUT/${TAG}_bench_${NG}gpu_ref.err
+  for f in $OUT/${TAG}_bench_${NG}gpu*.json; do echo "== $f"; head -c 1500 $f; echo; done
+  tail -3 $OUT/${TAG}_bench_${NG}gpu*.err
+  exit 0
+  ;;
 sweep)
   run_pytest host tests/test_gpu_fused.py tests/test_gpu_ops.py tests/test_gpu_configs.py tests/test_reference_glue.py tests/test_pytensor_ops.py
   bench_line ours --steps 20 --warmup 5 --no-cpu --no-kepler --extra gp
