@@ -645,16 +645,22 @@ def arm_ours(args):
         step_host()
         nw += 1
     barrier()
-    e2e_steps = []
-    e0 = time.perf_counter()
-    for _ in range(args.steps):
-        s0 = time.perf_counter()
-        step_host()  # synchronous: returns when logp and the gradients are in host memory
-        e2e_steps.append(time.perf_counter() - s0)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - e0
-    if os.environ.get("XO_BENCH_VERBOSE"):
-        sys.stderr.write("e2e per-step us: " + " ".join("%.0f" % (x * 1e6) for x in e2e_steps) + "\n")
+    # K synchronous calls, timed as a block; the block is repeated 5 times and the MEDIAN block is reported (the host<->device
+    # path of a fresh box is bimodal -- the same 2.4 MB upload takes 65 or 185 us depending on the PCIe link state,
+    # profiles/r01_e2e_breakdown.txt -- one block of 20 calls lands on either mode)
+    e2e_blocks = []
+    for _rep in range(5):
+        e2e_steps = []
+        e0 = time.perf_counter()
+        for _ in range(args.steps):
+            s0 = time.perf_counter()
+            step_host()  # synchronous: returns when logp and the gradients are in host memory
+            e2e_steps.append(time.perf_counter() - s0)
+        torch.cuda.synchronize()
+        e2e_blocks.append(time.perf_counter() - e0)
+        if os.environ.get("XO_BENCH_VERBOSE"):
+            sys.stderr.write("e2e per-step us: " + " ".join("%.0f" % (x * 1e6) for x in e2e_steps) + "\n")
+    e2e_s = float(np.median(e2e_blocks))
     # ---- e2e with the light curve resident (uploaded once, as a compiled model holds its
     # constants): per step only the parameters go in and logp + gradients come back ----------
     handle = C.c_void_p()
@@ -674,15 +680,18 @@ def arm_ours(args):
         step_resident()
         nw += 1
     barrier()
-    res_steps = []
-    r0 = time.perf_counter()
-    for _ in range(args.steps):
-        s0 = time.perf_counter()
-        step_resident()
-        res_steps.append(time.perf_counter() - s0)
-    res_s = time.perf_counter() - r0
-    if os.environ.get("XO_BENCH_VERBOSE"):
-        sys.stderr.write("resident per-step us: " + " ".join("%.0f" % (x * 1e6) for x in res_steps) + "\n")
+    res_blocks = []
+    for _rep in range(5):
+        res_steps = []
+        r0 = time.perf_counter()
+        for _ in range(args.steps):
+            s0 = time.perf_counter()
+            step_resident()
+            res_steps.append(time.perf_counter() - s0)
+        res_blocks.append(time.perf_counter() - r0)
+        if os.environ.get("XO_BENCH_VERBOSE"):
+            sys.stderr.write("resident per-step us: " + " ".join("%.0f" % (x * 1e6) for x in res_steps) + "\n")
+    res_s = float(np.median(res_blocks))
     lib.xo_transit_data_destroy(handle)
     clocks = sampler.stop() if rank == 0 else None
     h2d = sum(h[k].numel() * 8 for k in h)
@@ -817,7 +826,10 @@ def arm_ours(args):
         "value_full_sweep": {"value": total_evals / (ms_full * 1e-3), "unit": "evals/s", "ms_per_step": ms_full / args.steps,
                              "note": "same step with moments = NULL: y and ivar of every cadence are read and summed in the sweep, as the CPU arm does"},
         "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "xo_transit_model_logp_grad_host: t,y,ivar,params from pinned host memory every call; logp+grads back to host"},
+                "api": "xo_transit_model_logp_grad_host: t,y,ivar (one pinned block, one DMA), params from pinned host memory every call; "
+                       "logp+grads back to host",
+                "timing": "median of 5 blocks of `steps` synchronous calls",
+                "blocks_evals_per_s": [float(C_loc * args.steps / b) for b in e2e_blocks]},
         "e2e_resident_data": {"value": total_evals / (res_ms * 1e-3), "unit": "evals/s",
                               "h2d_bytes_per_step": sum(h[k].numel() * 8 for k in ("par", "star", "mean", "dtk", "wk")), "d2h_bytes_per_step": d2h,
                               "api": "xo_transit_model_logp_grad_resident: light curve uploaded once (xo_transit_data_create); params in, logp+grads out per call"},
@@ -870,6 +882,10 @@ def main():
     if args.impl == "reference":
         # pin the OpenMP team before libgomp is loaded (the oracle is dlopen'ed later): unpinned threads were the
         # main source of the 2x run-to-run spread of this arm in round 1
+        # torchrun exports OMP_NUM_THREADS=1 to every rank unless the user set it; this arm is "the reference's CPU path with all
+        # the host threads it can use", run by rank 0 alone: drop that default so the OpenMP team spans the machine
+        if ("TORCHELASTIC_RUN_ID" in os.environ or "LOCAL_RANK" in os.environ) and os.environ.get("OMP_NUM_THREADS") == "1":
+            del os.environ["OMP_NUM_THREADS"]
         os.environ.setdefault("OMP_PROC_BIND", "close")
         os.environ.setdefault("OMP_PLACES", "cores")
         os.environ.setdefault("OMP_WAIT_POLICY", "active")
