@@ -108,6 +108,20 @@ struct Arena {
 };
 inline size_t pad(size_t n, size_t sz = 8) { return (n * sz + 255) & ~(size_t)255; }
 
+// Once a host entry point has enqueued asynchronous copies that touch the CALLER's buffers it must not return before they
+// have completed, also on an error path (the caller is free to release the buffers as soon as the call returns).
+struct StreamGuard {
+  cudaStream_t a, b;
+  bool armed = true;
+  explicit StreamGuard(cudaStream_t s, cudaStream_t side = nullptr) : a(s), b(side) {}
+  void disarm() { armed = false; }
+  ~StreamGuard() {
+    if (!armed) return;
+    if (b) cudaStreamSynchronize(b);
+    cudaStreamSynchronize(a);
+  }
+};
+
 #define XO_TRY(expr)                         \
   do {                                       \
     cudaError_t _e = (expr);                 \
@@ -154,6 +168,7 @@ int xo_kepler_host(const double *M, const double *e, double *sinf, double *cosf,
   if (!M || !e || !sinf || !cosf) return XO_EINVAL;
   DeviceScope ds(device);
   XO_TRY(ds.err);
+  StreamGuard guard(ds.st, ds.side);  // declared before the arena: the stream-ordered free is enqueued first, then the guard waits
   const size_t b = (size_t)n * 8;
   Arena ar(4 * pad(n), ds.st);
   XO_TRY(ar.err);
@@ -164,6 +179,7 @@ int xo_kepler_host(const double *M, const double *e, double *sinf, double *cosf,
   XO_TRY(d2h(sinf, ds_, b, ds.st));
   XO_TRY(d2h(cosf, dc, b, ds.st));
   XO_TRY(cudaStreamSynchronize(ds.st));
+  guard.disarm();
   return 0;
 }
 
@@ -173,6 +189,7 @@ int xo_qsv_host(const double *b, const double *r, double *s, double *dsdb, doubl
   if (!b || !r || !s || ((dsdb == nullptr) != (dsdr == nullptr))) return XO_EINVAL;
   DeviceScope ds(device);
   XO_TRY(ds.err);
+  StreamGuard guard(ds.st, ds.side);  // declared before the arena: the stream-ordered free is enqueued first, then the guard waits
   const size_t nb = (size_t)n * 8;
   Arena ar(2 * pad(n) + 3 * pad(3 * n), ds.st);
   XO_TRY(ar.err);
@@ -187,6 +204,7 @@ int xo_qsv_host(const double *b, const double *r, double *s, double *dsdb, doubl
     XO_TRY(d2h(dsdr, dR, 3 * nb, ds.st));
   }
   XO_TRY(cudaStreamSynchronize(ds.st));
+  guard.disarm();
   return 0;
 }
 
@@ -198,6 +216,7 @@ int xo_contact_points_host(const double *a, const double *e, const double *cosw,
   if (!a || !e || !cosw || !sinw || !cosi || !sini || !L || !M_left || !M_right || !flag) return XO_EINVAL;
   DeviceScope ds(device);
   XO_TRY(ds.err);
+  StreamGuard guard(ds.st, ds.side);  // declared before the arena: the stream-ordered free is enqueued first, then the guard waits
   const size_t nb = (size_t)n * 8;
   Arena ar(9 * pad(n) + pad(n, 4), ds.st);
   XO_TRY(ar.err);
@@ -214,6 +233,7 @@ int xo_contact_points_host(const double *a, const double *e, const double *cosw,
   XO_TRY(d2h(M_right, dr, nb, ds.st));
   XO_TRY(d2h(flag, df, (size_t)n * 4, ds.st));
   XO_TRY(cudaStreamSynchronize(ds.st));
+  guard.disarm();
   return 0;
 }
 
@@ -224,6 +244,7 @@ int xo_transit_lc_host(const double *t, int64_t N, const double *elem, const dou
   if (!t || !elem || !cl || !dtk || !wk || !lc) return XO_EINVAL;
   DeviceScope ds(device);
   XO_TRY(ds.err);
+  StreamGuard guard(ds.st, ds.side);  // declared before the arena: the stream-ordered free is enqueued first, then the guard waits
   Arena ar(pad(N) + pad(C * P * XO_NEL) + pad(3 * C) + 2 * pad(K) + pad(C * N * P), ds.st);
   XO_TRY(ar.err);
   double *dt = ar.take<double>(N), *del = ar.take<double>(C * P * XO_NEL), *dcl = ar.take<double>(3 * C);
@@ -236,6 +257,7 @@ int xo_transit_lc_host(const double *t, int64_t N, const double *elem, const dou
   XO_RC(xo_transit_lc_fwd(dt, N, del, dcl, C, P, dd, dw, K, dlc, ds.st));
   XO_TRY(d2h(lc, dlc, (size_t)C * N * P * 8, ds.st));
   XO_TRY(cudaStreamSynchronize(ds.st));
+  guard.disarm();
   return 0;
 }
 
@@ -248,6 +270,7 @@ int xo_transit_logp_grad_host(const double *t, const double *y, const double *iv
   if (!t || !y || !ivar || !elem || !cl || !mean || !dtk || !wk || !logp || !gel || !gcl || !gmean) return XO_EINVAL;
   DeviceScope ds(device);
   XO_TRY(ds.err);
+  StreamGuard guard(ds.st, ds.side);  // declared before the arena: the stream-ordered free is enqueued first, then the guard waits
   const size_t ws = xo_transit_logp_grad_workspace(N, C, P);
   Arena ar(3 * pad(N) + pad(C * P * XO_NEL) + pad(3 * C) + pad(C) + 2 * pad(K) + pad(C) + pad(C * P * XO_NGRAD) +
                pad(3 * C) + pad(C) + pad(XO_MOMENTS_LEN) + pad(ws, 1),
@@ -276,6 +299,7 @@ int xo_transit_logp_grad_host(const double *t, const double *y, const double *iv
   XO_TRY(d2h(gcl, dgc, (size_t)C * 3 * 8, ds.st));
   XO_TRY(d2h(gmean, dgm, (size_t)C * 8, ds.st));
   XO_TRY(cudaStreamSynchronize(ds.st));
+  guard.disarm();
   return 0;
 }
 
@@ -288,6 +312,7 @@ int xo_transit_model_logp_grad_host(const double *t, const double *y, const doub
   if (!t || !y || !ivar || !par || !star || !mean || !dtk || !wk || !logp || !gpar || !gstar || !gmean) return XO_EINVAL;
   DeviceScope ds(device);
   XO_TRY(ds.err);
+  StreamGuard guard(ds.st, ds.side);  // declared before the arena: the stream-ordered free is enqueued first, then the guard waits
   const size_t ws = xo_transit_model_workspace(N, C, P);
   const size_t nin = (size_t)C * P * XO_NPAR + (size_t)C * XO_NSTAR + (size_t)C + 2 * (size_t)K;
   const size_t nout = (size_t)C + (size_t)C * P * XO_NPAR + (size_t)C * XO_NSTAR + (size_t)C;

@@ -6,9 +6,10 @@
     Ml, Mr, fl = ops.contact_points(a, e, cosw, sinw, cosi, sini, L)   # keplerian.py:744-753
 
 CUDA fp64 tensors in -> CUDA fp64 tensors out with reverse-mode gradients
-(torch.autograd.Function whose backward launches the VJP kernels).  numpy arrays
-/ CPU tensors in -> numpy arrays out through the host-buffer C entry points (the
-shape PyTensor's ``Op.perform`` needs); still computed on the GPU, no CPU path.
+(torch.autograd.Function whose backward launches the VJP kernels).  CPU torch tensors are moved to the
+current CUDA device, go through the same autograd Functions (so gradients are kept) and the results come
+back on the CPU.  numpy arrays in -> numpy arrays out through the host-buffer C entry points (the shape
+PyTensor's ``Op.perform`` needs); still computed on the GPU, no CPU path.
 """
 import ctypes as C
 
@@ -29,7 +30,17 @@ def _nptr(a):
 
 
 def _is_cuda(*xs):
-    return any(isinstance(x, torch.Tensor) and x.is_cuda for x in xs)
+    """torch path: any torch tensor among the inputs (numpy-only calls take the host-buffer entry points)"""
+    return any(isinstance(x, torch.Tensor) for x in xs)
+
+
+def _torch_device(*xs):
+    """(device the kernels run on, device the results are returned on)"""
+    for x in xs:
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            return x.device, x.device
+    _lib.require_cuda()
+    return torch.device("cuda", torch.cuda.current_device()), torch.device("cpu")
 
 
 def _as_cuda(x, device):
@@ -78,14 +89,15 @@ def kepler(M, e):
     ``e`` is broadcast against ``M`` (the reference materialises ``ecc + zeros_like(M)``,
     keplerian.py:333)."""
     if _is_cuda(M, e):
-        dev = M.device if isinstance(M, torch.Tensor) and M.is_cuda else e.device
+        dev, out = _torch_device(M, e)
         M = _as_cuda(M, dev)
         e = _as_cuda(e, dev)
         M, e = torch.broadcast_tensors(M, e)
-        return _Kepler.apply(M, e)
+        sf, cf = _Kepler.apply(M, e)
+        return sf.to(out), cf.to(out)
     lib = _lib.require_cuda()
-    M = np.asarray(M.detach().cpu().numpy() if isinstance(M, torch.Tensor) else M, dtype=np.float64)
-    e = np.asarray(e.detach().cpu().numpy() if isinstance(e, torch.Tensor) else e, dtype=np.float64)
+    M = np.asarray(M, dtype=np.float64)
+    e = np.asarray(e, dtype=np.float64)
     M, e = [np.ascontiguousarray(x) for x in np.broadcast_arrays(M, e)]
     sinf = np.empty_like(M)
     cosf = np.empty_like(M)
@@ -128,11 +140,11 @@ def quad_solution_vector(b, r):
     """Agol-Luger-Foreman-Mackey solution vector for quadratic limb darkening:
     shape ``b.shape + (3,)``; ``lc = s @ c - 1`` (limb_dark.py:21-24)."""
     if _is_cuda(b, r):
-        dev = b.device if isinstance(b, torch.Tensor) and b.is_cuda else r.device
+        dev, out = _torch_device(b, r)
         b = _as_cuda(b, dev)
         r = _as_cuda(r, dev)
         b, r = torch.broadcast_tensors(b, r)
-        return _QuadSolutionVector.apply(b, r)
+        return _QuadSolutionVector.apply(b, r).to(out)
     return quad_solution_vector_with_jac(b, r, jac=False)
 
 
@@ -156,7 +168,7 @@ def contact_points(a, e, cosw, sinw, cosi, sini, L):
     args = (a, e, cosw, sinw, cosi, sini, L)
     if _is_cuda(*args):
         lib = _lib.require_cuda()
-        dev = next(x.device for x in args if isinstance(x, torch.Tensor) and x.is_cuda)
+        dev, out = _torch_device(*args)
         ts = torch.broadcast_tensors(*[_as_cuda(x, dev).detach() for x in args])
         ts = [x.contiguous() for x in ts]
         Ml = torch.empty_like(ts[0])
@@ -165,7 +177,7 @@ def contact_points(a, e, cosw, sinw, cosi, sini, L):
         with torch.cuda.device(dev):
             _lib.check(lib.xo_contact_points(*[_ptr(x) for x in ts], _ptr(Ml), _ptr(Mr), _ptr(flag), ts[0].numel(),
                                              _lib.stream_ptr()), "contact_points")
-        return Ml, Mr, flag
+        return Ml.to(out), Mr.to(out), flag.to(out)
     lib = _lib.require_cuda()
     arrs = [np.ascontiguousarray(x) for x in np.broadcast_arrays(*[np.asarray(x, dtype=np.float64) for x in args])]
     Ml = np.empty_like(arrs[0])

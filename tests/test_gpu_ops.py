@@ -191,3 +191,22 @@ def test_error_codes_on_device():
     assert lib.xo_transit_lc_fwd(p, 8, p, p, 1, 1, p, p, 99, p, None) == 2  # stencil above XO_MAX_STENCIL
     with pytest.raises(_lib.XoError):
         _lib.check(3, "demo")
+
+
+def test_cpu_torch_tensors_keep_their_gradients():
+    """a CPU tensor that requires grad must not be detached into the numpy path: it is moved to the device,
+    goes through the autograd Function and the result comes back on the CPU with its graph"""
+    M = torch.linspace(-3.0, 3.0, 50, dtype=torch.float64, requires_grad=True)
+    e = torch.full((50,), 0.3, dtype=torch.float64, requires_grad=True)
+    sf, cf = ops.kepler(M, e)
+    assert sf.device.type == "cpu" and sf.requires_grad
+    gM, ge = torch.autograd.grad((sf * 0.7 + cf * 0.2).sum(), [M, e])
+    so, co = O.kepler(M.detach().numpy(), e.detach().numpy())
+    bM, be = O.kepler_vjp(so, co, e.detach().numpy(), np.full(50, 0.7), np.full(50, 0.2))
+    assert np.allclose(gM.numpy(), bM, rtol=1e-10, atol=1e-12) and np.allclose(ge.numpy(), be, rtol=1e-10, atol=1e-12)
+    b = torch.linspace(0.0, 1.2, 40, dtype=torch.float64, requires_grad=True)
+    s = ops.quad_solution_vector(b, torch.tensor(0.1, dtype=torch.float64))
+    assert s.device.type == "cpu" and s.shape == (40, 3) and s.requires_grad
+    # numpy in -> numpy out is unchanged
+    sn, cn = ops.kepler(M.detach().numpy(), 0.3)
+    assert isinstance(sn, np.ndarray) and np.allclose(sn, so, atol=1e-13)
