@@ -300,6 +300,8 @@ def extra_configs(lib, dev, args):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import xo_oracle as O
 
+    O._skip_cpu = bool(args.no_cpu)  # no CPU timing legs inside the extras either
+
     def d(x):
         return torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float64, device=dev)
 
@@ -310,6 +312,8 @@ def extra_configs(lib, dev, args):
     N = N_CADENCES
     t = synthetic.cadence_times(N)
     y = synthetic.noise(N, SIGMA)
+    if want("c0"):
+        _extra_config0(lib, dev, d, flush, out, O)
     if want("c2"):
         _extra_config2(lib, dev, d, flush, out, O, t, y)
     if want("gp"):
@@ -319,6 +323,62 @@ def extra_configs(lib, dev, args):
     if want("hmc"):
         _extra_hmc(lib, dev, d, flush, out, O, t, y)
     return out
+
+
+def _extra_config0(lib, dev, d, flush, out, O):
+    """configs[0] (BASELINE: PyMC logp+dlogp on the reference's PyTensor ops, N=1e3, circular) cannot be executed in
+    this image (no PyTensor / exoplanet-core; probe_reference_tier() says so in `run.reference_tier`).  SURVEY.md 8(d)
+    "Config 1 caveat": the same problem through the CPU restatement stands in for it -- circular orbits bypass the Kepler
+    solver (keplerian.py:331-332); quad_solution_vector and the closed-form in_transit branch (:733-741) are exercised."""
+    import time
+
+    import torch
+
+    from exoplanet_b200 import fused, synthetic
+
+    N = 1000
+    t = np.arange(N, dtype=np.float64) * 0.02
+    res = {}
+    entry = {"unit": "model+grad evals/s", "cadences": N, "note": "SUBSTITUTE for configs[0]: the reference's PyMC/PyTensor path is not runnable "
+             "here; CPU figure = the oracle port on the same N=1e3 circular problem, one thread per evaluation as the reference's ops are"}
+    for Cn in (1, 128, 4096):
+        p = synthetic.transit_params(Cn, 1, seed=synthetic.SEED + 3, ecc=0.0)
+        p["period"] = np.clip(p["period"], 3.0, 15.0)  # at least one transit inside the 20-day series
+        truth = {k: (v[:1] if hasattr(v, "shape") else v) for k, v in p.items()}
+        el_t = O.elements_from_params(truth["period"], truth["t0"], truth["ecc"], truth["omega"], truth["b"], truth["ror"])
+        dtk, wk = O.stencil(None)
+        y = O.transit_lc(t, el_t, O.get_cl(truth["u1"], truth["u2"]), dtk, wk)[0, :, 0] + synthetic.noise(N, SIGMA)
+        data = fused.TransitData(t, y, np.full(N, SIGMA), device=dev)
+        model = fused.TransitModel(data)
+        par = fused.pack_params(d(p["period"]), d(p["t0"]), d(p["ecc"]), d(p["omega"]), d(p["b"]), d(p["ror"]), d(p["m_planet"]), d(p["K"]))
+        one = torch.ones(Cn, dtype=torch.float64, device=dev)
+        star = fused.pack_star(one, one, d(p["u1"]), d(p["u2"]))
+        mean = d(p["mean"])
+
+        def step():
+            res["o"] = model.logp_grad(par, star, mean)
+
+        ms = _time_steps(step, 20, flush)
+        sel = np.unique(np.linspace(0, Cn - 1, 8).astype(int))
+        el_o = O.elements_from_params(p["period"][sel], p["t0"][sel], p["ecc"][sel], p["omega"][sel], p["b"][sel], p["ror"][sel])
+        args_o = (t, y, np.full(N, 1 / SIGMA ** 2), el_o, O.get_cl(p["u1"][sel], p["u2"][sel]), p["mean"][sel], np.zeros(1), np.ones(1))
+        lo, geo, _, gmo = O.transit_logp_grad(*args_o, lognorm=data.lognorm)
+        entry["%d chains" % Cn] = {
+            "value": Cn / (ms * 1e-3), "ms_per_step": ms,
+            "parity_logp_rel_err": float(np.max(np.abs(res["o"][0].cpu().numpy()[sel] - lo) / np.abs(lo))),
+            "parity_gmean_rel_err": float(np.max(np.abs(res["o"][3].cpu().numpy()[sel] - gmo) / np.abs(gmo).max()))}
+        if Cn == 128 and not getattr(O, "_skip_cpu", False):
+            O.set_threads(1)
+            reps, t0 = 0, time.perf_counter()
+            while time.perf_counter() - t0 < 2.0:
+                O.transit_logp_grad(*args_o, lognorm=data.lognorm)
+                reps += 1
+            dt = time.perf_counter() - t0
+            O.set_threads(os.cpu_count() or 1)
+            entry["cpu_port"] = {"cores": 1, "value": reps * len(sel) / dt, "unit": "model+grad evals/s", "kind": "port",
+                                 "sample": "%d passes over %d chains, %.1f s" % (reps, len(sel), dt)}
+    entry["value"] = entry["128 chains"]["value"]
+    out["configs[0] substitute: circular orbit, N=1e3 (Kepler solver bypassed)"] = entry
 
 
 def _extra_config2(lib, dev, d, flush, out, O, t, y):
@@ -874,7 +934,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-kepler", action="store_true", help="skip the Kepler micro-benchmark")
     ap.add_argument("--no-extra", action="store_true", help="skip the brief configs[2] / configs[3] measurements")
-    ap.add_argument("--extra", default="", help="comma list restricting the other-config measurements: c2,gp,c4,hmc (default: all)")
+    ap.add_argument("--extra", default="", help="comma list restricting the other-config measurements: c0,c2,gp,c4,hmc (default: all)")
     ap.add_argument("--same-seed", action="store_true", help="multi-GPU: every rank evaluates the same chains (identical per-rank work)")
     ap.add_argument("--full-sweep", action="store_true",
                     help="sum the Gaussian terms of every cadence in the sweep instead of using the data moments")

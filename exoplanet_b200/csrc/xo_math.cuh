@@ -368,6 +368,67 @@ XO_HD void cel3(double kc, double kc2, double p, double a, double b, double &G, 
 }
 
 // ---------------------------------------------------------------------------
+// The measure-zero configurations of quad_solution_vector (b = 0, b = r, b = 1 - r) in their own NON-inlined functions.
+// Inlined, their r-only subexpressions (divisions, acos, sqrt) are loop-invariant in the sweep of the logp kernel -- r is the
+// chain's radius ratio -- and the compiler hoists them in front of every drain: ~360 instructions each time, 11% of that
+// kernel's instruction count (profiles/r02_transit.txt, "line 440").  Results are returned by value (registers).
+// ---------------------------------------------------------------------------
+#if defined(__CUDACC__)
+#define XO_RARE static __host__ __device__ __noinline__
+#else
+#define XO_RARE static
+#endif
+enum QsvKind { kB0, kHalf, kEqSmall, kEqLarge, kTangent, kLimb, kInside };
+struct QsvEq {
+  int kind;
+  double kc2, aux;
+};
+XO_RARE QsvEq qsv_eq_kind(double r, double r2) {  // b == r: which closed form, and the modulus of its elliptic integrals
+  QsvEq o{kHalf, 1.0, 0.0};
+  if (r == 0.5) return o;
+  if (r < 0.5) {
+    o.kind = kEqSmall;
+    o.kc2 = 1.0 - 4.0 * r2;  // m = 4 r^2; G = K(m)
+  } else {
+    o.kind = kEqLarge;
+    o.aux = 0.25 / r2;  // m = 1/(4 r^2)
+    o.kc2 = 1.0 - o.aux;
+  }
+  return o;
+}
+struct QsvLam {
+  double Lam, d1b, d1r;
+};
+XO_RARE QsvLam qsv_rare(int kind, double r, double r2, double aux, double onembmr2, double G, double E, double Em) {
+  QsvLam o;
+  if (kind == kB0) {
+    const double x = sqrt(fmax(0.0, 1.0 - r2));
+    o.Lam = -2.0 / 3.0 * x * x * x;
+    o.d1b = 0.0;
+    o.d1r = -2.0 * kPi * r * x;
+  } else if (kind == kTangent) {
+    const double sqA = sqrt(onembmr2);
+    o.Lam = 2.0 / (3.0 * kPi) * acos(1.0 - 2.0 * r) - 4.0 / (9.0 * kPi) * (3.0 + 2.0 * r - 8.0 * r2) * sqrt(r * (1.0 - r)) -
+            (r > 0.5 ? 2.0 / 3.0 : 0.0);
+    o.d1r = -4.0 * r * sqA;
+    o.d1b = 4.0 * r * sqA / 3.0;
+  } else if (kind == kHalf) {
+    o.Lam = 1.0 / 3.0 - 4.0 / (9.0 * kPi);
+    o.d1r = -4.0 * r;
+    o.d1b = 4.0 * r / 3.0;
+  } else if (kind == kEqSmall) {
+    o.Lam = 1.0 / 3.0 + 2.0 / (9.0 * kPi) * (4.0 * (2.0 * r2 - 1.0) * E + (1.0 - 4.0 * r2) * G);
+    o.d1r = -4.0 * r * E;
+    o.d1b = 4.0 * r / 3.0 * (2.0 * Em - E);
+  } else {  // kEqLarge
+    o.Lam = 1.0 / 3.0 + 16.0 * r / (9.0 * kPi) * (2.0 * r2 - 1.0) * E - (1.0 - 4.0 * r2) * (3.0 - 8.0 * r2) / (9.0 * kPi * r) * G;
+    o.d1r = -8.0 * r2 * aux * Em;
+    o.d1b = 8.0 * r2 / 3.0 * aux * (2.0 * E - Em);
+  }
+  return o;
+}
+
+// ---------------------------------------------------------------------------
 // quad_solution_vector(b, r): s[3] and (optionally) ds/db, ds/dr.
 // b may be negative: |b| is used and d/db carries sign(b).
 // ---------------------------------------------------------------------------
@@ -430,23 +491,16 @@ XO_HD void qsv(double b_in, double r, double *s, double *dsdb, double *dsdr) {
   // linear term  s1 = 2pi/3 (1 - Theta(r - b)) - pi Lambda.  Every regime that needs elliptic
   // integrals first reduces to ONE cel3 call (so a warp whose lanes sit in different regimes
   // walks the AGM ladder once, together), then finishes with its own closed form.
-  enum { kB0, kHalf, kEqSmall, kEqLarge, kTangent, kLimb, kInside };
   int kind;
   double kc2 = 1.0, cp = 1.0, ca = 1.0, cb = 1.0;  // cel(kc, p, a, b) arguments
   double aux = 0.0, qq = 0.0;
   if (b == 0.0) {
     kind = kB0;
   } else if (b == r) {
-    if (r == 0.5) {
-      kind = kHalf;
-    } else if (r < 0.5) {
-      kind = kEqSmall;
-      kc2 = 1.0 - 4.0 * r2;  // m = 4 r^2; G = K(m)
-    } else {
-      kind = kEqLarge;
-      aux = 0.25 / r2;  // m = 1/(4 r^2)
-      kc2 = 1.0 - aux;
-    }
+    const QsvEq eq = qsv_eq_kind(r, r2);
+    kind = eq.kind;
+    kc2 = eq.kc2;
+    aux = eq.aux;
   } else if (t4 == 0.0) {
     kind = kTangent;  // b = 1 - r
   } else if (t4 > 0.0) {
@@ -478,29 +532,11 @@ XO_HD void qsv(double b_in, double r, double *s, double *dsdb, double *dsdr) {
     Lam = 2.0 * sqA * fma(onembpr2, G, -(4.0 - 7.0 * r2 - b2) * E) * XO_K(30);
     d1r = -4.0 * r * sqA * E;
     d1b = 4.0 * r * sqA * XO_K(31) * (2.0 * Em - E);
-  } else if (kind == kB0) {
-    const double x = sqrt(fmax(0.0, 1.0 - r2));
-    Lam = -2.0 / 3.0 * x * x * x;
-    d1b = 0.0;
-    d1r = -2.0 * kPi * r * x;
-  } else if (kind == kTangent) {
-    const double sqA = sqrt(onembmr2);
-    Lam = 2.0 / (3.0 * kPi) * acos(1.0 - 2.0 * r) - 4.0 / (9.0 * kPi) * (3.0 + 2.0 * r - 8.0 * r2) * sqrt(r * (1.0 - r)) -
-          (r > 0.5 ? 2.0 / 3.0 : 0.0);
-    d1r = -4.0 * r * sqA;
-    d1b = 4.0 * r * sqA / 3.0;
-  } else if (kind == kHalf) {
-    Lam = 1.0 / 3.0 - 4.0 / (9.0 * kPi);
-    d1r = -4.0 * r;
-    d1b = 4.0 * r / 3.0;
-  } else if (kind == kEqSmall) {
-    Lam = 1.0 / 3.0 + 2.0 / (9.0 * kPi) * (4.0 * (2.0 * r2 - 1.0) * E + (1.0 - 4.0 * r2) * G);
-    d1r = -4.0 * r * E;
-    d1b = 4.0 * r / 3.0 * (2.0 * Em - E);
-  } else {  // kEqLarge
-    Lam = 1.0 / 3.0 + 16.0 * r / (9.0 * kPi) * (2.0 * r2 - 1.0) * E - (1.0 - 4.0 * r2) * (3.0 - 8.0 * r2) / (9.0 * kPi * r) * G;
-    d1r = -8.0 * r2 * aux * Em;
-    d1b = 8.0 * r2 / 3.0 * aux * (2.0 * E - Em);
+  } else {  // b = 0, b = r, b = 1 - r
+    const QsvLam o = qsv_rare(kind, r, r2, aux, onembmr2, G, E, Em);
+    Lam = o.Lam;
+    d1b = o.d1b;
+    d1r = o.d1r;
   }
   s[1] = fma(-XO_K(25), Lam, r > b ? 0.0 : XO_K(26));
   if (kJac) {

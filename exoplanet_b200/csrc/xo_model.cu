@@ -18,7 +18,7 @@ namespace {
 
 __global__ void model_prologue_kernel(const double *__restrict__ par, const double *__restrict__ star, int64_t C, int P,
                                       double texp, int use_in_transit, double *__restrict__ elem,
-                                      double *__restrict__ cl) {
+                                      double *__restrict__ cl, int64_t N, uint32_t *__restrict__ weights) {
   xo::pdl_launch_dependents();  // the logp kernel may start its data-only preamble now
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t idx = tid >> 1;
@@ -27,13 +27,20 @@ __global__ void model_prologue_kernel(const double *__restrict__ par, const doub
   const int64_t c = ii / P;
   xo::prologue_pair(par + ii * XO_NPAR, star + c * XO_NSTAR, texp, use_in_transit, (int)(tid & 1), active, elem + ii * XO_NEL);
   if (active && (tid & 1) == 0 && idx % P == 0) xo::limb_coeffs(star[c * XO_NSTAR + 2], star[c * XO_NSTAR + 3], cl + 3 * c);
+  if (weights) {  // expected in-transit work of this (chain, planet): the logp kernel deals its CTAs out by these
+    __syncwarp();  // the pair's element block is complete
+    if (active && (tid & 1) == 0) {
+      const double *el = elem + ii * XO_NEL;
+      weights[ii] = xo::transit_weight(el[XO_EL_PERIOD], el[XO_EL_TSTART], el[XO_EL_TEND], N);
+    }
+  }
 }
 
 // one warp per chain
 __global__ void model_epilogue_kernel(const double *__restrict__ par, const double *__restrict__ star,
                                       const double *__restrict__ partial, int slots, int64_t C, int P, double lognorm,
                                       double *__restrict__ logp, double *__restrict__ gpar, double *__restrict__ gstar,
-                                      double *__restrict__ gmean) {
+                                      double *__restrict__ gmean, const int2 *__restrict__ rows) {
   const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
   const int nacc = xo::kNBase + P * XO_NGRAD;
@@ -41,12 +48,15 @@ __global__ void model_epilogue_kernel(const double *__restrict__ par, const doub
   // parameter-only half first: as a programmatic dependent of the logp kernel this overlaps its tail
   const xo::EpiPre pre = xo::epilogue_pre(par + (c * P + (lane < P ? lane : 0)) * XO_NPAR, star + c * XO_NSTAR);
   xo::pdl_wait();
-  xo::epilogue_chain<true>(pre, star + c * XO_NSTAR, partial + c * slots * nacc, slots, P, lognorm, logp + c,
+  // the chain's rows of `partial`: slots of them, or what the weighted partition of the logp kernel dealt it
+  const int64_t first = rows ? rows[c].x : c * slots;
+  const int count = rows ? rows[c].y : slots;
+  xo::epilogue_chain<true>(pre, star + c * XO_NSTAR, partial + first * nacc, count, P, lognorm, logp + c,
                            gpar + c * P * XO_NPAR, gstar + c * XO_NSTAR, gmean + c);
 }
 
 struct ModelLayout {
-  size_t off_elem, off_cl, off_partial, off_counter, bytes;
+  size_t off_elem, off_cl, off_partial, off_counter, off_weights, off_rows, bytes;
   xo::Split sp;
 };
 inline ModelLayout model_layout(int64_t N, int64_t C, int64_t P) {
@@ -60,8 +70,11 @@ inline ModelLayout model_layout(int64_t N, int64_t C, int64_t P) {
   };
   L.off_elem = take((size_t)C * P * XO_NEL);
   L.off_cl = take((size_t)C * 3);
-  L.off_partial = take((size_t)C * L.sp.slots * (xo::kNBase + P * XO_NGRAD));
+  const size_t rows_uniform = (size_t)C * L.sp.slots, rows_weighted = (size_t)xo::transit_weighted_rows(N, C);
+  L.off_partial = take((rows_uniform > rows_weighted ? rows_uniform : rows_weighted) * (xo::kNBase + P * XO_NGRAD));
   L.off_counter = take((size_t)C);  // per-chain arrival counters of the single-launch mode
+  L.off_weights = take(((size_t)C * P + 1) / 2);  // uint32 [C][P]
+  L.off_rows = take((size_t)C);                   // int2 [C]
   L.bytes = o;
   return L;
 }
@@ -84,9 +97,9 @@ static int model_launches() {
 bool model_split_supported() { return model_launches() == 3; }
 
 int launch_model_epilogue(const double *par, const double *star, const double *partial, int slots, int64_t C, int P, double lognorm,
-                          double *logp, double *gpar, double *gstar, double *gmean, cudaStream_t st, bool pdl) {
+                          double *logp, double *gpar, double *gstar, double *gmean, cudaStream_t st, bool pdl, const int2 *rows) {
   cudaError_t le = xo::launch_pdl(model_epilogue_kernel, dim3((unsigned)((C + 3) / 4)), dim3(128), st, pdl, par, star, partial, slots, C, P,
-                                  lognorm, logp, gpar, gstar, gmean);
+                                  lognorm, logp, gpar, gstar, gmean, rows);
   return le == cudaSuccess ? 0 : -(int)le;
 }
 
@@ -130,7 +143,8 @@ int model_logp_grad_phases(const double *t, const double *y, const double *ivar,
     ma.gstar = gstar;
     ma.gmean = gmean;
     if (launches == 2)
-      xo::launch(model_prologue_kernel, (unsigned)((2 * cp + 63) / 64), 64, 0, st, par, star, C, (int)P, texp, use_in_transit, elem, cl);
+      xo::launch(model_prologue_kernel, (unsigned)((2 * cp + 63) / 64), 64, 0, st, par, star, C, (int)P, texp, use_in_transit, elem, cl, N,
+                 (uint32_t *)nullptr);
     xo::launch_transit_logp_grad(t, y, ivar, N, elem, cl, mean, C, (int)P, dtk, wk, K, L.sp, moments, partial, st, &ma);
     return xo::launch_status();
   }
@@ -138,8 +152,13 @@ int model_logp_grad_phases(const double *t, const double *y, const double *ivar,
     const char *v = getenv("XO_MODEL_PDL");
     return !(v && *v == '0');
   }();
+  // CTAs of the logp kernel dealt to the chains by their expected in-transit work (weights from the prologue)
+  const bool weighted = xo::transit_weighted(C, P);
+  uint32_t *weights = weighted ? reinterpret_cast<uint32_t *>(ws + L.off_weights) : nullptr;
+  int2 *rows = weighted ? reinterpret_cast<int2 *>(ws + L.off_rows) : nullptr;
   if (phases & 1)
-    xo::launch(model_prologue_kernel, (unsigned)((2 * cp + 63) / 64), 64, 0, st, par, star, C, (int)P, texp, use_in_transit, elem, cl);
+    xo::launch(model_prologue_kernel, (unsigned)((2 * cp + 63) / 64), 64, 0, st, par, star, C, (int)P, texp, use_in_transit, elem, cl, N,
+               weights);
   if (!(phases & 2)) return xo::launch_status();
   static const int lpt = [] {
     const char *v = getenv("XO_MODEL_HEAVY_FIRST");
@@ -147,19 +166,27 @@ int model_logp_grad_phases(const double *t, const double *y, const double *ivar,
   }();
   xo::ModelArgs ord;
   const xo::ModelArgs *pord = nullptr;
-  if (lpt && C > 1) {
+  if (lpt && C > 1 && !weighted) {
     int *order = reinterpret_cast<int *>(ws + L.off_counter);  // the counter slot is free in this mode
     xo::launch_chain_order(elem, C, (int)P, order, st);
     ord.order = order;
     ord.elements_only = 1;
     pord = &ord;
   }
+  if (weighted) {
+    ord.weights = weights;
+    ord.rows = rows;
+    ord.nchains = (int)C;
+    ord.grid_ctas = (int)xo::transit_weighted_grid(N, C);
+    ord.elements_only = 1;
+    pord = &ord;
+  }
   // heavy-first inserts the ordering kernel between prologue and logp kernel: no early start then
   // (nor when the prologue ran on another stream: the kernel preceding this one is then unrelated)
   xo::launch_transit_logp_grad(t, y, ivar, N, elem, cl, mean, C, (int)P, dtk, wk, K, L.sp, moments, partial, st, pord,
-                               pdl && !pord && phases == 3);
+                               pdl && !ord.order && phases == 3);
   cudaError_t le = xo::launch_pdl(model_epilogue_kernel, dim3((unsigned)((C + 3) / 4)), dim3(128), st, pdl, par, star,
-                                  (const double *)partial, L.sp.slots, C, (int)P, lognorm, logp, gpar, gstar, gmean);
+                                  (const double *)partial, L.sp.slots, C, (int)P, lognorm, logp, gpar, gstar, gmean, (const int2 *)rows);
   if (le != cudaSuccess) return -(int)le;
   return xo::launch_status();
 }
@@ -190,8 +217,8 @@ int xo_elements_from_params(const double *par, const double *star, int64_t C, in
   if (C == 0 || P == 0) return 0;
   if (!par || !star || !elem || !cl) return XO_EINVAL;
   const int64_t cp = C * P;
-  xo::launch(model_prologue_kernel, (unsigned)((2 * cp + 63) / 64), 64, 0, static_cast<cudaStream_t>(stream), 
-      par, star, C, (int)P, texp, use_in_transit, elem, cl);
+  xo::launch(model_prologue_kernel, (unsigned)((2 * cp + 63) / 64), 64, 0, static_cast<cudaStream_t>(stream), par, star, C, (int)P, texp,
+             use_in_transit, elem, cl, (int64_t)0, (uint32_t *)nullptr);
   return xo::launch_status();
 }
 

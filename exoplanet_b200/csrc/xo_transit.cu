@@ -307,15 +307,79 @@ inline int index_bins(int64_t N) {
 constexpr int sweep_unroll(bool moments) { return (moments || kWarps > 4) ? 1 : 4; }
 constexpr int kQueueMax = 32 * (4 + 1);  // 31 left over + kUnroll * 32 new entries
 
-// per-warp state of the indexed producer (shared memory: it must not cost registers across the drain)
-struct WarpIndexState {
-  uint32_t rlo[32], rcnt[32];  // index range of the epoch each lane looked up
-  long long kfirst[32], kend[32];  // per planet: first / last epoch that can touch this warp's cadences
-  long long kcur, klast;       // next / last epoch of the current planet
-  int p;                       // current planet
-  uint32_t rmask;              // lanes of the current batch whose range is still to be fed
-  uint32_t clo, ccnt;          // what is left of the range being fed
+// CTA-level state of the indexed producer: one batch of kThreads transit epochs of one planet (thread i: epoch kcur + i),
+// the cadence range of each (rlo, count) and the exclusive prefix of the counts -- entry e of the batch is cadence
+// rlo[r] + e - roff[r] with r the last range whose offset is <= e (drains look it up; nothing is queued).
+struct CtaIndexState {
+  uint32_t rlo[kThreads], roff[kThreads + 1];
+  uint32_t wtot[kWarps];
+  long long kfirst[XO_MAX_PLANETS], kend[XO_MAX_PLANETS];  // per planet: first / last epoch that can touch this CTA's cadences
 };
+
+// Work partition of the launch (ma.weights != nullptr): the G CTAs of the grid are dealt to the chains in proportion to their
+// expected number of in-transit cadences (weights[c][p], written by whoever derived the element blocks), every chain getting
+// at least one: n_c = 1 + floor(w_c (G - C) / sum w).  Every CTA derives the same table from the same integers (block
+// reduction + block scan over the chains, a few hundred cycles) and picks its own (chain, part) from it.  Without weights:
+// chain = blockIdx.y, part = blockIdx.x of gridDim.x.
+struct Partition {
+  int64_t c;       // chain
+  uint32_t part, nparts;
+  int64_t row0;    // first row of this CTA in `partial` (one row per warp)
+  bool idle;
+};
+
+__device__ __forceinline__ Partition weighted_partition(const uint32_t *__restrict__ w, int C, int P, int2 *__restrict__ rows,
+                                                        Partition *sh, unsigned long long *red) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t G = gridDim.x * gridDim.y, b = blockIdx.y * gridDim.x + blockIdx.x;
+  const int k = (C + kThreads - 1) / kThreads;  // chains per thread, blocked: thread i owns chains [i k, i k + k)
+  const int c0 = min(C, tid * k), c1 = min(C, c0 + k);
+  auto chain_weight = [&](int c) {
+    uint32_t wc = 0u;
+    for (int p = 0; p < P; ++p) wc += __ldg(w + (size_t)c * P + p);
+    return wc;
+  };
+  // total weight (integers: the same in every CTA whatever the order of the additions)
+  unsigned long long mine = 0ull;
+  for (int c = c0; c < c1; ++c) mine += chain_weight(c);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(kFull, mine, o);
+  if (lane == 0) red[warp] = mine;
+  if (tid == 0) sh->idle = true;
+  __syncthreads();
+  unsigned long long total = 0ull;
+  for (int x = 0; x < kWarps; ++x) total += red[x];
+  // just below (G - C) / total, so that the floors cannot add up to more than G - C
+  const double scale = total ? (double)(G - (uint32_t)C) / (double)total * (1.0 - 0x1p-40) : 0.0;
+  auto ctas_of = [&](int c) { return 1u + (uint32_t)((double)chain_weight(c) * scale); };
+  uint32_t n_mine = 0u;
+  for (int c = c0; c < c1; ++c) n_mine += ctas_of(c);
+  uint32_t inc = n_mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t v = __shfl_up_sync(kFull, inc, d);
+    if (lane >= d) inc += v;
+  }
+  __syncthreads();  // red[] has been read
+  if (lane == 31) red[warp] = inc;
+  __syncthreads();
+  uint32_t cum = inc - n_mine;
+  for (int x = 0; x < warp; ++x) cum += (uint32_t)red[x];
+  for (int c = c0; c < c1; ++c) {
+    const uint32_t n = ctas_of(c);
+    if (b >= cum && b < cum + n) {
+      sh->c = c;
+      sh->part = b - cum;
+      sh->nparts = n;
+      sh->row0 = (int64_t)b * kWarps;  // the chain's rows are those of its CTAs cum .. cum + n - 1
+      sh->idle = false;
+      if (rows && b == cum) rows[c] = make_int2((int)(cum * kWarps), (int)(n * kWarps));
+    }
+    cum += n;
+  }
+  __syncthreads();
+  return *sh;
+}
 
 // kVjp = false: Gaussian log-likelihood (y, ivar, mean) and its gradient.
 // kVjp = true : reverse pass of the light curve alone: `y` is the cotangent bar_lc[C][N][P]
@@ -342,12 +406,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
   __shared__ double gacc[kWarps][XO_MAX_PLANETS][XO_NGRAD];
   __shared__ double lacc[XO_NGRAD + 3][kThreads];  // per-thread gradient accumulators of one drain
   __shared__ double pacc[XO_NGRAD][kThreads];      // per-thread cotangent-scaled sums of the current planet
-  // heaviest chains first (ma.order, optional): CTAs are dispatched in blockIdx order, so the long
-  // ones start early and the short ones fill the tail of the launch
+  __shared__ CtaIndexState cix;
+  __shared__ Partition part_sh;
+  __shared__ unsigned long long part_red[kWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int slot = blockIdx.x * kWarps + warp;
-  const uint32_t start = (uint32_t)min((int64_t)slot * L, N);
-  const uint32_t end = (uint32_t)min((int64_t)slot * L + L, N);
+  const bool weighted = !kModel && ma.weights != nullptr;
   // Everything up to pdl_wait() is independent of the kernel that precedes this one in the stream
   // (the model prologue writing elem / cl): when launched as its programmatic dependent this part
   // overlaps the prologue's tail -- accumulators zeroed, this warp's time stamps pulled into L2.
@@ -358,10 +421,34 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
 #pragma unroll
   for (int j = 0; j < XO_NGRAD; ++j) pacc[j][threadIdx.x] = 0.0;
   // (data only, so legal before the wait) with the time index the sweep reads no time stamps: nothing to pull in
-  if (!(kMoments && moments[5] != 0.0))
-    for (uint32_t i = start + 16u * lane; i < end; i += 16u * 32u) xo::prefetch_l2(t + i);
+  if (!weighted && !(kMoments && moments[5] != 0.0)) {
+    const int64_t s0 = ((int64_t)blockIdx.x * kWarps + warp) * L;
+    const uint32_t pa0 = (uint32_t)min(s0, N), pa1 = (uint32_t)min(s0 + L, N);
+    for (uint32_t i = pa0 + 16u * lane; i < pa1; i += 16u * 32u) xo::prefetch_l2(t + i);
+  }
   xo::pdl_wait();
-  const int64_t c = ma.order ? ma.order[blockIdx.y] : blockIdx.y;
+  // which chain, and which part of its cadences, this CTA works on
+  Partition pt;
+  if (weighted) {
+    pt = weighted_partition(ma.weights, ma.nchains, P, ma.rows, &part_sh, part_red);
+    if (pt.idle) return;  // more CTAs in the grid than the table deals out
+  } else {
+    // heaviest chains first (ma.order, optional): CTAs are dispatched in blockIdx order, so the long
+    // ones start early and the short ones fill the tail of the launch
+    pt.c = ma.order ? ma.order[blockIdx.y] : blockIdx.y;
+    pt.part = blockIdx.x;
+    pt.nparts = gridDim.x;
+    pt.row0 = pt.c * slots + (int64_t)blockIdx.x * kWarps;
+    pt.idle = false;
+  }
+  const int64_t c = pt.c;
+  // cadences per warp: the launch's L, or this chain's own split over its nparts CTAs
+  const int64_t Lw = weighted ? ((N + (int64_t)pt.nparts * kWarps - 1) / ((int64_t)pt.nparts * kWarps) + 31) / 32 * 32 : L;
+  const int slot = (int)pt.part * kWarps + warp;
+  const uint32_t start = (uint32_t)min((int64_t)slot * Lw, N);
+  const uint32_t end = (uint32_t)min((int64_t)slot * Lw + Lw, N);
+  const uint32_t cstart = (uint32_t)min((int64_t)pt.part * kWarps * Lw, N);  // ... and of the whole CTA
+  const uint32_t cend = (uint32_t)min(((int64_t)pt.part + 1) * kWarps * Lw, N);
   if (kModel && ma.stage_from_params)
     stage_chain_from_params(sm, ma, mean, dtk, wk, c, P, K);
   else
@@ -407,9 +494,18 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
   const double mean_c = sm.mean;
   const uint32_t lt_mask = (1u << lane) - 1u;
 
-  bool indexed = false;  // this warp enumerates transit epochs through the time index (set below, before the first drain)
-  // evaluate m (<= 32) queued entries src[0..m) of planet p
-  auto drain = [&](int p, const uint32_t *src, int m) {
+  bool indexed = false;  // this CTA enumerates transit epochs through the time index (set below, before the first drain)
+  // entry e of the current batch of the indexed producer -> cadence (see CtaIndexState)
+  auto batch_entry = [&](uint32_t e) {
+    int lo = 0;
+#pragma unroll
+    for (int h = kThreads >> 1; h > 0; h >>= 1)
+      if (cix.roff[lo + h] <= e) lo += h;
+    return cix.rlo[lo] + (e - cix.roff[lo]);
+  };
+  // evaluate m (<= 32) entries of planet p: src[off .. off + m) of a queue, or (src == nullptr) entries off .. off + m of
+  // the indexed producer's batch
+  auto drain = [&](int p, const uint32_t *src, int off, int m) {
     if (p != pcur) {
       if (pcur >= 0) flush(pcur);
       pcur = p;
@@ -418,7 +514,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
     int jself = -1;    // ... and the transit it belongs to
     if (lane < m) {
       double scale;  // cotangent multiplying this lane's accumulated d lc / d elements
-      const uint32_t idx = src[lane];
+      const uint32_t idx = src ? src[off + lane] : batch_entry((uint32_t)(off + lane));
       const double tt = __ldg(t + idx);
       // issued now so that their latency hides behind the sample evaluation
       const double yy = kVjp ? (ma.vjp_shared ? -__ldg(y + (int64_t)c * N + idx) : __ldg(y + ((int64_t)c * N + idx) * P + p)) : __ldg(y + idx);
@@ -484,139 +580,125 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
   };
 
   // The sweep is a producer / consumer loop written as ONE loop, so that the expensive drain body exists once in
-  // the binary.  Each iteration the producer appends at most 32 candidate cadences per planet to the queues, the
-  // consumer drains every queue that holds >= 32 entries; a final pass (last = true) drains what is left.
-  // Two producers:
-  //  * indexed (data moments + time index, sorted t): no time stamp is read.  Per planet the transit epochs that
-  //    can touch this warp's cadence range are enumerated 32 at a time (one per lane: window bounds -> index range
-  //    by table look-up), and the ranges are fed to the queue in order.  State lives in shared memory (widx).
-  //  * stepping: steps of 32*kUnroll cadences; for sorted t with moments, steps are taken 32 at a time (lane l:
+  // the binary.  Two producers:
+  //  * indexed (data moments + time index, sorted t): no time stamp is read and nothing is queued.  The CTA works as one:
+  //    per planet, the transit epochs that can touch the CTA's cadence range are taken kThreads at a time (one per thread:
+  //    window bounds -> cadence range by table look-up), a block scan turns the range lengths into offsets, and the
+  //    warps drain the batch's entries 32 at a time, round robin -- every drain but the batch's last is full.
+  //  * stepping (per warp): steps of 32*kUnroll cadences; for sorted t with moments, steps are taken 32 at a time (lane l:
   //    can step l contain an in-transit cadence of any planet?  one ballot gives the group's hit mask, only set
-  //    bits are visited); otherwise every cadence is read and the out-of-transit Gaussian terms accumulated.
+  //    bits are visited); otherwise every cadence is read and the out-of-transit Gaussian terms accumulated.  In-window
+  //    cadences go to per-warp, per-planet queues that are drained whenever they hold >= 32 entries; a final pass
+  //    (last = true) pools what the CTA's warps are left with.
   const bool sorted = kMoments && moments[4] != 0.0;  // t non-decreasing: steps can be skipped wholesale
   const int nbins = kMoments ? (int)moments[5] : 0;   // > 0: the block carries the time index
   const double *tp = t + lane;
   constexpr uint32_t kStep = 32 * kUnroll;
   uint32_t gnext = start, gcur = start, hitmask = 0u;
-  __shared__ WarpIndexState widx[kMoments ? kWarps : 1];
   __shared__ int wfill[kWarps][XO_MAX_PLANETS];  // final pass: what each warp is left with, per planet
   // ... pooled over the CTA: behind warp 0's (by then < 32) left-overs when the queue is long enough, else in its own array
   constexpr bool kPoolInQueue = kQueue >= 32 + kWarps * 32;
   __shared__ uint32_t pool_own[kPoolInQueue ? 1 : XO_MAX_PLANETS][kPoolInQueue ? 1 : kWarps * 32];
   auto pool = [&](int p) -> uint32_t * { return kPoolInQueue ? &queue[0][p][32] : pool_own[kPoolInQueue ? 0 : p]; };
-  // epoch range of every planet over this warp's cadences (lane p: planet p).  A planet with more epochs than cadences in
-  // the range (or a non-finite / non-positive period) cannot be enumerated: the whole warp then takes the stepping producer.
+  // epoch range of every planet over this CTA's cadences (thread p: planet p).  A planet with more epochs than cadences in
+  // the range (or a non-finite / non-positive period) cannot be enumerated: the CTA then takes the stepping producer.
+  __shared__ int ix_p;                  // indexed producer: current planet, next / last epoch of it
+  __shared__ long long ix_kcur, ix_klast;
   if (kMoments && nbins > 0) {
-    long long ka = 1, kb = 0;
     bool dense = false;
-    if (lane < P && start < end) {
-      const double per = sm.elem[lane][XO_EL_PERIOD], t0p = sm.elem[lane][XO_EL_T0];
-      const double tA = __ldg(t + start), tB = __ldg(t + end - 1);
-      const double dm = kTtv ? sm.ttv_dmax[lane] : 0.0;  // 0 without a transit-time table
-      const double fa = floor((tA - t0p - dm) * sm.rperiod[lane] - 0.5) - 1.0, fb = ceil((tB - t0p + dm) * sm.rperiod[lane] + 0.5) + 1.0;
-      dense = !(per > 0.0) || !(fb - fa <= (double)(end - start) + 4.0);
-      if (!dense) {
-        ka = (long long)fa;
-        kb = (long long)fb;
+    if (threadIdx.x < P) {
+      long long ka = 1, kb = 0;
+      if (cstart < cend) {
+        const int q = threadIdx.x;
+        const double per = sm.elem[q][XO_EL_PERIOD], t0p = sm.elem[q][XO_EL_T0];
+        const double tA = __ldg(t + cstart), tB = __ldg(t + cend - 1);
+        const double dm = kTtv ? sm.ttv_dmax[q] : 0.0;  // 0 without a transit-time table
+        const double fa = floor((tA - t0p - dm) * sm.rperiod[q] - 0.5) - 1.0, fb = ceil((tB - t0p + dm) * sm.rperiod[q] + 0.5) + 1.0;
+        dense = !(per > 0.0) || !(fb - fa <= (double)(cend - cstart) + 4.0);
+        if (!dense) {
+          ka = (long long)fa;
+          kb = (long long)fb;
+        }
       }
+      cix.kfirst[threadIdx.x] = ka;
+      cix.kend[threadIdx.x] = kb;
     }
-    // CTA-uniform: in the final pass a warp also drains entries the other warps of the CTA queued, and the drain's
-    // "is this cadence in planet q's queue too" predicate depends on the producer
-    indexed = __syncthreads_and(!__any_sync(kFull, dense)) != 0;
-    if (indexed) {
-      WarpIndexState &W = widx[warp];
-      W.kfirst[lane] = ka;
-      W.kend[lane] = kb;
-      if (lane == 0) {
-        W.p = -1;
-        W.kcur = 1;
-        W.klast = 0;
-        W.rmask = 0u;
-        W.clo = 0u;
-        W.ccnt = 0u;
-      }
+    if (threadIdx.x == 0) {
+      ix_p = -1;
+      ix_kcur = 1;
+      ix_klast = 0;
     }
-    __syncwarp();
+    // CTA-uniform: the drain's "is this cadence in planet q's queue too" predicate depends on the producer
+    indexed = __syncthreads_and(!dense) != 0;
   }
 #pragma unroll 1
   for (;;) {
     bool last = false;
-    int pb = 0, pe = P;  // planets whose queues the consumer looks at this iteration
+    int pb = 0, pe = P;  // planets the consumer looks at this iteration
+    uint32_t btot = 0u;  // indexed producer: entries in the current batch
     if (kMoments && indexed) {
-      // ---------------- indexed producer ----------------
-      WarpIndexState &W = widx[warp];
-      uint32_t ccnt = W.ccnt, clo = W.clo;
-      int p = W.p;
-      if (ccnt == 0u) {
-        uint32_t rmask = W.rmask;
-        while (rmask == 0u && !last) {  // a new batch of 32 epochs (of the next planet when this one is exhausted)
-          long long kcur = W.kcur, klast = W.klast;
-          while (kcur > klast) {
-            if (++p >= P) break;
-            kcur = W.kfirst[p];
-            klast = W.kend[p];
-          }
-          if (p >= P) {
-            last = true;
-            break;
-          }
-          uint32_t lo = 0u, cnt = 0u;
-          const long long k = kcur + lane;
-          if (k <= klast) {
-            const TimeIndex ix{reinterpret_cast<const uint32_t *>(moments + XO_MOMENTS_LEN), nbins, __ldg(t), moments[6]};
-            const double per = sm.elem[p][XO_EL_PERIOD], t0p = sm.elem[p][XO_EL_T0], hp = 0.5 * per;
-            const double ts = sm.elem[p][XO_EL_TSTART], te = sm.elem[p][XO_EL_TEND];
-            const TtvView tv = kTtv ? ttv_view(ma.ttv_times, ma.ttv_count, ma.ttv_nt, c, P, p) : TtvView{nullptr, 0};
-            uint32_t i0, i1;
-            if (kTtv && tv.n > 0) {
-              // epoch k of a transit-time table: the cadences nearest to transit k (between the mid-points to its
-              // neighbours: (m_{k-1}, m_k], ttv.py:159-178) that fall inside the window around it
-              const double ck = ttv_centre(tv.tt, tv.n, per, k);
-              const double mlo = 0.5 * (ttv_centre(tv.tt, tv.n, per, k - 1) + ck), mhi = 0.5 * (ck + ttv_centre(tv.tt, tv.n, per, k + 1));
-              i0 = (ck + ts > mlo) ? index_bound<false>(t, (uint32_t)N, ix, ck + ts) : index_bound<true>(t, (uint32_t)N, ix, mlo);
-              i1 = (ck + te < mhi) ? index_bound<true>(t, (uint32_t)N, ix, ck + te) : index_bound<true>(t, (uint32_t)N, ix, mhi);
-            } else {
-              const double tc = fma((double)k, per, t0p);
-              // the window clipped to the epoch's own period; the clip boundary B_k = t0 + (k + 1/2) P is computed by the
-              // same expression on both sides, so consecutive epochs neither overlap nor leave a gap
-              i0 = (ts > -hp) ? index_bound<false>(t, (uint32_t)N, ix, tc + ts)
-                              : index_bound<false>(t, (uint32_t)N, ix, fma((double)k - 0.5, per, t0p));
-              i1 = (te < hp) ? index_bound<true>(t, (uint32_t)N, ix, tc + te)
-                             : index_bound<false>(t, (uint32_t)N, ix, fma((double)k + 0.5, per, t0p));
-            }
-            lo = max(i0, start);
-            const uint32_t hi = min(i1, end);
-            cnt = hi > lo ? hi - lo : 0u;
-          }
-          __syncwarp();
-          W.rlo[lane] = lo;
-          W.rcnt[lane] = cnt;
-          rmask = __ballot_sync(kFull, cnt != 0u);
-          if (lane == 0) {
-            W.p = p;
-            W.kcur = kcur + 32;
-            W.klast = klast;
-          }
-          __syncwarp();
-        }
-        if (!last) {
-          const int src = __ffs(rmask) - 1;
-          rmask &= rmask - 1u;
-          clo = W.rlo[src];
-          ccnt = W.rcnt[src];
-          if (lane == 0) W.rmask = rmask;
-        }
+      // ---------------- indexed producer (the whole CTA in step) ----------------
+      int p = ix_p;
+      long long kcur = ix_kcur, klast = ix_klast;
+      while (kcur > klast) {  // this planet is exhausted: on to the next one
+        if (++p >= P) break;
+        kcur = cix.kfirst[p];
+        klast = cix.kend[p];
       }
-      if (!last) {
-        const uint32_t m = min(ccnt, 32u);
-        const int fill = __shfl_sync(kFull, cnt, p);
-        if (lane < m) queue[warp][p][fill + lane] = clo + lane;
-        if (lane == p) cnt = fill + (int)m;
-        if (lane == 0) {
-          W.clo = clo + m;
-          W.ccnt = ccnt - m;
+      if (p >= P) {
+        last = true;
+      } else {
+        uint32_t lo = 0u, rc = 0u;
+        const long long k = kcur + threadIdx.x;
+        if (k <= klast) {
+          const TimeIndex ix{reinterpret_cast<const uint32_t *>(moments + XO_MOMENTS_LEN), nbins, __ldg(t), moments[6]};
+          const double per = sm.elem[p][XO_EL_PERIOD], t0p = sm.elem[p][XO_EL_T0], hp = 0.5 * per;
+          const double ts = sm.elem[p][XO_EL_TSTART], te = sm.elem[p][XO_EL_TEND];
+          const TtvView tv = kTtv ? ttv_view(ma.ttv_times, ma.ttv_count, ma.ttv_nt, c, P, p) : TtvView{nullptr, 0};
+          uint32_t i0, i1;
+          if (kTtv && tv.n > 0) {
+            // epoch k of a transit-time table: the cadences nearest to transit k (between the mid-points to its
+            // neighbours: (m_{k-1}, m_k], ttv.py:159-178) that fall inside the window around it
+            const double ck = ttv_centre(tv.tt, tv.n, per, k);
+            const double mlo = 0.5 * (ttv_centre(tv.tt, tv.n, per, k - 1) + ck), mhi = 0.5 * (ck + ttv_centre(tv.tt, tv.n, per, k + 1));
+            i0 = (ck + ts > mlo) ? index_bound<false>(t, (uint32_t)N, ix, ck + ts) : index_bound<true>(t, (uint32_t)N, ix, mlo);
+            i1 = (ck + te < mhi) ? index_bound<true>(t, (uint32_t)N, ix, ck + te) : index_bound<true>(t, (uint32_t)N, ix, mhi);
+          } else {
+            const double tc = fma((double)k, per, t0p);
+            // the window clipped to the epoch's own period; the clip boundary B_k = t0 + (k + 1/2) P is computed by the
+            // same expression on both sides, so consecutive epochs neither overlap nor leave a gap
+            i0 = (ts > -hp) ? index_bound<false>(t, (uint32_t)N, ix, tc + ts)
+                            : index_bound<false>(t, (uint32_t)N, ix, fma((double)k - 0.5, per, t0p));
+            i1 = (te < hp) ? index_bound<true>(t, (uint32_t)N, ix, tc + te)
+                           : index_bound<false>(t, (uint32_t)N, ix, fma((double)k + 0.5, per, t0p));
+          }
+          lo = max(i0, cstart);
+          const uint32_t hi = min(i1, cend);
+          rc = hi > lo ? hi - lo : 0u;
         }
-        __syncwarp();
+        uint32_t inc = rc;  // inclusive scan of the range lengths over the warp ...
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t v = __shfl_up_sync(kFull, inc, d);
+          if (lane >= d) inc += v;
+        }
+        __syncthreads();  // every warp is done with the previous batch (and has read ix_*)
+        if (lane == 31) cix.wtot[warp] = inc;
+        if (threadIdx.x == 0) {
+          ix_p = p;
+          ix_kcur = kcur + kThreads;
+          ix_klast = klast;
+        }
+        __syncthreads();
+        uint32_t base = 0u;  // ... and over the CTA
+        for (int w = 0; w < kWarps; ++w) {
+          if (w < warp) base += cix.wtot[w];
+          btot += cix.wtot[w];
+        }
+        cix.rlo[threadIdx.x] = lo;
+        cix.roff[threadIdx.x] = base + inc - rc;
+        if (threadIdx.x == 0) cix.roff[kThreads] = btot;
+        __syncthreads();
         pb = p;
         pe = p + 1;
       }
@@ -705,9 +787,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
       }
     }
     // ---------------- consumer: the one drain call site ----------------
-    // Ordinary iterations: a queue is drained 32 entries at a time as soon as it holds that many.  Final pass: the < 32
+    // Indexed batches: entries 32 w, 32 (w + kWarps), ... of the batch go to warp w.  Stepping producer, ordinary
+    // iterations: a queue is drained 32 entries at a time as soon as it holds that many; its final pass: the < 32
     // entries each warp is left with are pooled over the CTA's warps (warp order, so still deterministic) and drained
     // in chunks of 32 dealt round-robin to the warps -- up to kWarps partial drains become total/32 full ones.
+    const bool coop = kMoments && indexed;
+    if (coop && last) break;  // batches leave nothing behind
     if (last) {
       if (lane < P) wfill[warp][lane] = cnt;
       __syncthreads();
@@ -722,7 +807,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
     for (int p = pb; p < pe; ++p) {
       int fill, off, stride;
       const uint32_t *src;
-      if (last) {
+      if (coop) {
+        fill = (int)btot;
+        off = 32 * warp;
+        stride = 32 * kWarps;
+        src = nullptr;
+      } else if (last) {
         fill = 0;
         for (int w = 0; w < kWarps; ++w) fill += wfill[w][p];
         off = 32 * warp;
@@ -736,11 +826,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
         src = queue[warp][p];
       }
 #pragma unroll 1
-      while (last ? off < fill : fill - off >= 32) {
-        drain(p, src + off, min(32, fill - off));
+      while ((coop || last) ? off < fill : fill - off >= 32) {
+        drain(p, src, off, min(32, fill - off));
         off += stride;
       }
-      if (!last) {  // move the < 32 left-over entries to the front
+      if (!last && !coop) {  // move the < 32 left-over entries to the front
         const int rem = fill - off;
         const uint32_t v = lane < rem ? queue[warp][p][off + lane] : 0u;
         __syncwarp();
@@ -765,7 +855,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
   gl[3 * kThreads] = gc1;
   gl[4 * kThreads] = gc2;
   __syncwarp();
-  double *out = partial + ((int64_t)c * slots + slot) * nacc;
+  double *out = partial + (pt.row0 + warp) * nacc;
   if (lane < kNBase) out[lane] = row_sum(&lacc[0][warp * 32]);
   for (int i = lane; i < P * XO_NGRAD; i += 32) out[kNBase + i] = gacc[warp][i / XO_NGRAD][i % XO_NGRAD];
   if (kModel) {
@@ -773,7 +863,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
     __shared__ int is_last;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(ma.counter + c, 1u) == gridDim.x - 1) ? 1 : 0;
+    if (threadIdx.x == 0) is_last = (atomicAdd(ma.counter + c, 1u) == pt.nparts - 1) ? 1 : 0;
     __syncthreads();
     if (is_last && warp == 0) {
       __threadfence();
@@ -1063,6 +1153,13 @@ Split split_transit(int64_t N, int64_t C) {
   const int sms = sm_count();
   // aim at ~20 warps per SM over the whole launch, at least 256 cadences per warp
   int64_t target = ((int64_t)sms * transit_warps_per_sm() + C - 1) / C;
+  // at least two CTAs per chain while the weighted partition can still deal them out unevenly: with one CTA per chain the
+  // heaviest chain alone sets the length of the launch's tail (1024 chains: 3.2e6 -> 4.2e6 evals/s, profiles/r02_tuning_sweep.txt)
+  static const int min_ctas = [] {
+    const char *v = getenv("XO_TRANSIT_MIN_CTAS");
+    return v && *v ? atoi(v) : 2;
+  }();
+  if (C > 1 && C <= kMaxWeighted && target < (int64_t)min_ctas * kWarps) target = (int64_t)min_ctas * kWarps;
   int64_t maxw = (N + 255) / 256;
   int64_t w = target < 1 ? 1 : (target > maxw ? maxw : target);
   if (w < 1) w = 1;
@@ -1071,6 +1168,27 @@ Split split_transit(int64_t N, int64_t C) {
   L = ((L + 31) / 32) * 32;
   return Split{(int)w, L};
 }
+
+bool transit_weighted(int64_t C, int64_t P) {
+  static const bool on = [] {  // XO_TRANSIT_WEIGHTED=0: every chain gets the same number of CTAs
+    const char *v = getenv("XO_TRANSIT_WEIGHTED");
+    return !(v && *v == '0');
+  }();
+  return on && C > 1 && C * P <= kMaxWeighted;
+}
+
+int64_t transit_weighted_grid(int64_t N, int64_t C) {
+  const Split sp = split_transit(N, C);
+  const int64_t g0 = (int64_t)(sp.slots / kWarps) * C;   // what the uniform split would launch
+  const int64_t wave = (int64_t)sm_count() * transit_min_blocks();  // resident CTAs (3 per SM for the 168-register kernel)
+  if (g0 <= wave) return g0;
+  static const int waves_env = env_int("XO_TRANSIT_WAVES", 0);
+  int64_t waves = waves_env > 0 ? waves_env : (g0 + wave / 2) / wave;
+  if (waves * wave < C) waves = (C + wave - 1) / wave;
+  return waves * wave;
+}
+
+int64_t transit_weighted_rows(int64_t N, int64_t C) { return transit_weighted_grid(N, C) * kWarps; }
 
 int check_batch(int64_t N, int64_t C, int64_t P) {
   if (N < 0 || C < 0 || P < 0) return XO_EINVAL;
@@ -1084,8 +1202,8 @@ void launch_transit_logp_grad(const double *t, const double *y, const double *iv
                               const double *cl, const double *mean, int64_t C, int P, const double *dtk,
                               const double *wk, int K, Split sp, const double *moments, double *partial,
                               cudaStream_t st, const ModelArgs *model, bool pdl) {
-  dim3 grid(sp.slots / kWarps, (unsigned)C);
   const ModelArgs ma = model ? *model : ModelArgs{};
+  const dim3 grid = ma.weights ? dim3((unsigned)ma.grid_ctas) : dim3(sp.slots / kWarps, (unsigned)C);
 #define XO_LAUNCH(MB, VJP, MOM, MODEL)                                                                                    \
   xo::launch_pdl(transit_logp_grad_kernel<MB, VJP, MOM, MODEL>, grid, dim3(kThreads), st, pdl, t, y, ivar, N, elem, cl, mean, P, \
                  dtk, wk, K, sp.L, sp.slots, moments, partial, ma)

@@ -44,7 +44,26 @@ struct ModelArgs {
   double *ttv_grad = nullptr;
   // light-curve VJP mode only: light-travel delay (keplerian.py:411-470); the element blocks carry R_star in XO_EL_RSTAR
   int light_delay = 0;
+  // work partition by expected in-transit cadences (element-level launches): weights[C][P] (>= 1 each, see
+  // transit_weight()), written by the kernel that derived the element blocks; rows[C] receives (first row, rows) of each
+  // chain in `partial` for the fold.  null: every chain gets gridDim.x CTAs.
+  const uint32_t *weights = nullptr;
+  int2 *rows = nullptr;
+  int nchains = 0;    // with weights: number of chains (the grid is then one-dimensional, grid_ctas CTAs)
+  int grid_ctas = 0;  // with weights: transit_weighted_grid()
 };
+
+// Expected drains (32 in-transit cadences each) of one planet over N cadences, + 1: the unit of the work partition
+__host__ __device__ inline uint32_t transit_weight(double period, double tstart, double tend, int64_t N) {
+  const double d = (tend - tstart) / period;
+  const double duty = !(d < 1.0) ? 1.0 : (d > 0.0 ? d : 0.0);  // NaN, infinite window, window >= period: every cadence
+  return 1u + (uint32_t)(duty * (double)N * (1.0 / 32.0));
+}
+constexpr int64_t kMaxWeighted = 4096;  // chains * planets up to which the logp kernel builds the partition table in every CTA
+bool transit_weighted(int64_t C, int64_t P);
+// CTAs of a weighted launch: whole waves of the device (every CTA slot busy until the end) once the launch exceeds one wave
+int64_t transit_weighted_grid(int64_t N, int64_t C);
+int64_t transit_weighted_rows(int64_t N, int64_t C);  // rows of `partial` such a launch writes (one per warp)
 
 // light curve forward with an optional transit-time table (lc[C][N][P])
 void launch_transit_lc_fwd(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int P, const double *dtk,
@@ -73,7 +92,7 @@ void launch_transit_resid(const double *t, const double *y, int64_t N, const dou
                           const double *ttv_times = nullptr, const int *ttv_count = nullptr, int ttv_nt = 0);
 // fold of the per-warp partials + reverse pass of the prologue (xo_model.cu)
 int launch_model_epilogue(const double *par, const double *star, const double *partial, int slots, int64_t C, int P, double lognorm,
-                          double *logp, double *gpar, double *gstar, double *gmean, cudaStream_t st, bool pdl);
+                          double *logp, double *gpar, double *gstar, double *gmean, cudaStream_t st, bool pdl, const int2 *rows = nullptr);
 
 // celerite gradient with per-chain jitter and per-chain sums of d/dy, d/d diag (xo_celerite.cu)
 int celerite_sho_grad_impl(const double *t, const double *y, const double *diag, int64_t N, const double *S0, const double *w0,

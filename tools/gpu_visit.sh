@@ -86,6 +86,17 @@ sweep)
   for MB in 2 4; do one XO_TRANSIT_MINBLOCKS=$MB; done
   cat $OUT/${TAG}_sweep.txt
   ;;
+ab)
+  # usage: AB_ENVS="XO_A=1 XO_B=2,XO_C=3" (space separated variants; commas join several assignments of one variant)
+  run_pytest fused tests/test_gpu_fused.py tests/test_reference_glue.py tests/test_gpu_configs.py tests/test_gpu_sampling.py
+  bench_line ours --steps 20 --warmup 5 --no-cpu --no-kepler --extra c4,hmc
+  : > $OUT/${TAG}_sweep.txt
+  one() { echo -n "$1: " >> $OUT/${TAG}_sweep.txt; env ${1//,/ } timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu --no-kepler --extra c4 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value']), round(d['ms_per_step'],5), round(d['e2e']['value']), round(d['e2e_resident_data']['value']), [(k, v.get('value')) for k, v in d.get('other_configs', {}).items() if isinstance(v, dict)])" >> $OUT/${TAG}_sweep.txt 2>&1; }
+  one XO_NOOP=1
+  for E in $AB_ENVS; do one $E; done
+  cat $OUT/${TAG}_sweep.txt
+  [ -n "$AB_CAPTURE" ] && capture transit transit_logp_grad_kernel 3 --steps 2 --warmup 3 --no-cpu --no-kepler --no-extra
+  ;;
 final)
   run_pytest all tests
   for ML in 1 2; do XO_MODEL_LAUNCHES=$ML run_pytest launches$ML tests/test_gpu_fused.py; done
