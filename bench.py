@@ -549,6 +549,26 @@ def _extra_hmc(lib, dev, d, flush, out, O, t, y):
         out["HMC driver, configs[1] x 128 chains, 8 leapfrog steps per transition, %s" % mode] = {
             "value": 128 * 8 / (msj * 1e-3), "unit": "leapfrog model+grad evals/s (incl. parameter transforms, their chain rule and the priors)",
             "ms_per_transition": msj, "chain_transitions_per_s": 128 / (msj * 1e-3), "accept_mean": float(hmc.accept_prob.mean().item())}
+    # ---- the NUTS driver on the same posterior: doublings as CUDA graphs against one launch per tensor op
+    from exoplanet_b200.sampling import BatchedNUTS
+
+    for mode, use_graph in (("one CUDA graph per doubling", True), ("eager launches", False)):
+        nuts = BatchedNUTS(post, q_init, step_size=1e-6, max_depth=4, seed=2, use_graph=use_graph)
+        for _ in range(2):
+            nuts.transition()
+        torch.cuda.synchronize()
+        n0 = nuts.n_leapfrog
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            nuts.transition()
+        b.record()
+        torch.cuda.synchronize()
+        leaves = nuts.n_leapfrog - n0
+        msl = a.elapsed_time(b) / max(leaves, 1)
+        out["NUTS driver, configs[1] x 128 chains, max_depth 4, %s" % mode] = {
+            "value": 128 / (msl * 1e-3), "unit": "leapfrog model+grad evals/s (tree building, U-turn checks and multinomial sampling included)",
+            "ms_per_leapfrog": msl, "leapfrogs_per_transition": leaves / 5, "depth_mean": float(nuts.depth.to(torch.float64).mean().item())}
 
 
 def arm_ours(args):

@@ -45,8 +45,9 @@ _SIGNATURES = {
     "xo_contact_points": (_i32, [_vp] * 10 + [_i64, _vp]),
     "xo_transit_lc_fwd": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _vp]),
     "xo_transit_lc_vjp": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "xo_transit_lc_fwd_ex": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp]),
-    "xo_transit_lc_vjp_ex": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "xo_transit_lc_fwd_ex": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "xo_transit_lc_vjp_ex": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
+                                    _vp]),
     "xo_transit_logp_grad_ttv": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _dbl, _vp, _vp, _vp, _i32, _vp, _vp,
                                         _vp, _vp, _vp, _vp, _sz, _vp]),
     "xo_transit_logp_grad_workspace": (_sz, [_i64, _i64, _i64]),

@@ -248,7 +248,6 @@ struct LogProd {
 // (row pitch RUN + 1 doubles: thread r then walks row r conflict-free), the walks never wait for global memory.
 template <int RUN>
 struct TileSmem {
-  static constexpr int kPitchT = RUN + 1;
   double t[kThreadsGp * (RUN + 1)];
   double d[kThreadsGp * (RUN + 1)];  // diag + jitter
   double y[kThreadsGp * (RUN + 1)];

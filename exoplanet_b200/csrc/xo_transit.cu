@@ -183,19 +183,21 @@ __global__ void __launch_bounds__(256) transit_lc_fwd_kernel(const double *__res
                                                              const double *__restrict__ wk, int K,
                                                              const double *__restrict__ ttv_times,
                                                              const int *__restrict__ ttv_count, int ttv_nt,
-                                                             double *__restrict__ lc) {
+                                                             const double *__restrict__ texp_vec, double *__restrict__ lc) {
   __shared__ ChainSmem sm;
   const int64_t c = blockIdx.y;
   stage_chain(sm, elem, cl, nullptr, dtk, wk, c, P, K);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride) {
     const double t_i = __ldg(t + i);
+    // per-cadence exposure times (limb_dark.py:199-205): dtk then holds the unit stencil, scaled here
+    const double tx = texp_vec ? __ldg(texp_vec + i) : 1.0;
     for (int p = 0; p < P; ++p) {
       const double tt = t_i - ttv_shift(ttv_view(ttv_times, ttv_count, ttv_nt, c, P, p), sm.elem[p][XO_EL_T0], t_i);
       double acc = 0.0;
       if (xo::in_window(sm.elem[p], sm.rperiod[p], tt)) {
         for (int k = 0; k < K; ++k)
-          acc = fma(sm.wk[k], xo::lc_point<false, 1, kDelay>(sm.elem[p], sm.cl, tt + sm.dtk[k], 0.0, nullptr, nullptr), acc);
+          acc = fma(sm.wk[k], xo::lc_point<false, 1, kDelay>(sm.elem[p], sm.cl, tt + __dmul_rn(tx, sm.dtk[k]), 0.0, nullptr, nullptr), acc);
       }
       __stcs(lc + (c * N + i) * P + p, acc);
     }
@@ -318,8 +320,8 @@ struct CtaIndexState {
 
 // Work partition of the launch (ma.weights != nullptr): the G CTAs of the grid are dealt to the chains in proportion to their
 // expected number of in-transit cadences (weights[c][p], written by whoever derived the element blocks), every chain getting
-// at least one: n_c = 1 + floor(w_c (G - C) / sum w).  Every CTA derives the same table from the same integers (block
-// reduction + block scan over the chains, a few hundred cycles) and picks its own (chain, part) from it.  Without weights:
+// at least one, such that the heaviest CTA is as light as possible (weighted_partition).  Every CTA derives the same table
+// from the same integers (block reductions + one block scan over the chains) and picks its own (chain, part) from it.  Without weights:
 // chain = blockIdx.y, part = blockIdx.x of gridDim.x.
 struct Partition {
   int64_t c;       // chain
@@ -328,20 +330,24 @@ struct Partition {
   bool idle;
 };
 
+constexpr int kPartK = 4;  // chains per thread the table is built for: C <= kPartK * kThreads (transit_weighted())
 __device__ __forceinline__ Partition weighted_partition(const uint32_t *__restrict__ w, int C, int P, int2 *__restrict__ rows,
                                                         Partition *sh, unsigned long long *red) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t G = gridDim.x * gridDim.y, b = blockIdx.y * gridDim.x + blockIdx.x;
-  const int k = (C + kThreads - 1) / kThreads;  // chains per thread, blocked: thread i owns chains [i k, i k + k)
-  const int c0 = min(C, tid * k), c1 = min(C, c0 + k);
-  auto chain_weight = [&](int c) {
-    uint32_t wc = 0u;
-    for (int p = 0; p < P; ++p) wc += __ldg(w + (size_t)c * P + p);
-    return wc;
-  };
-  // total weight (integers: the same in every CTA whatever the order of the additions)
+  // thread i owns chains i, i + kThreads, ... (their weights stay in registers for the whole table computation)
+  uint32_t wv[kPartK];
   unsigned long long mine = 0ull;
-  for (int c = c0; c < c1; ++c) mine += chain_weight(c);
+#pragma unroll
+  for (int j = 0; j < kPartK; ++j) {
+    const int c = tid + j * kThreads;
+    uint32_t wc = 0u;
+    if (c < C)
+      for (int p = 0; p < P; ++p) wc += __ldg(w + (size_t)c * P + p);
+    wv[j] = wc;  // 0: no such chain
+    mine += wc;
+  }
+  // total weight (integers: the same in every CTA whatever the order of the additions)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(kFull, mine, o);
   if (lane == 0) red[warp] = mine;
@@ -349,33 +355,65 @@ __device__ __forceinline__ Partition weighted_partition(const uint32_t *__restri
   __syncthreads();
   unsigned long long total = 0ull;
   for (int x = 0; x < kWarps; ++x) total += red[x];
-  // just below (G - C) / total, so that the floors cannot add up to more than G - C
-  const double scale = total ? (double)(G - (uint32_t)C) / (double)total * (1.0 - 0x1p-40) : 0.0;
-  auto ctas_of = [&](int c) { return 1u + (uint32_t)((double)chain_weight(c) * scale); };
-  uint32_t n_mine = 0u;
-  for (int c = c0; c < c1; ++c) n_mine += ctas_of(c);
-  uint32_t inc = n_mine;
+  // CTAs per chain: n_c = ceil(w_c r) with the largest r for which they add up to at most G, i.e. the apportionment with
+  // the smallest heaviest CTA (max w_c / n_c).  r = (G - C) / total is always feasible (sum of ceilings <= G - C + C),
+  // r = G / total in general is not: five bisection steps in between, each one block-wide integer sum -- every CTA of the
+  // launch walks the same steps on the same integers and ends up with the same table.
+  double r_lo = total ? (double)(G - (uint32_t)C) / (double)total * (1.0 - 0x1p-40) : 0.0;
+  double r_hi = total ? (double)G / (double)total : 0.0;
+  auto ctas_of = [&](uint32_t wc, double r) {  // ceil(wc r), at least 1; 0 for an empty slot
+    const double x = (double)wc * r;
+    const uint32_t f = (uint32_t)x;
+    return wc ? max(1u, f + ((double)f < x ? 1u : 0u)) : 0u;
+  };
+  uint32_t *red32 = reinterpret_cast<uint32_t *>(red);  // [2][kWarps], alternating: one barrier per step
+  __syncthreads();                                      // red[] (64-bit view) has been read
+#pragma unroll 1
+  for (int it = 0; it < 5; ++it) {
+    const double r = 0.5 * (r_lo + r_hi);
+    uint32_t cnt = 0u;
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t v = __shfl_up_sync(kFull, inc, d);
-    if (lane >= d) inc += v;
+    for (int j = 0; j < kPartK; ++j) cnt += ctas_of(wv[j], r);
+    cnt = __reduce_add_sync(kFull, cnt);
+    uint32_t *buf = red32 + (it & 1) * kWarps;
+    if (lane == 0) buf[warp] = cnt;
+    __syncthreads();
+    uint32_t all = 0u;
+    for (int x = 0; x < kWarps; ++x) all += buf[x];
+    if (all <= G) r_lo = r; else r_hi = r;
   }
-  __syncthreads();  // red[] has been read
-  if (lane == 31) red[warp] = inc;
-  __syncthreads();
-  uint32_t cum = inc - n_mine;
-  for (int x = 0; x < warp; ++x) cum += (uint32_t)red[x];
-  for (int c = c0; c < c1; ++c) {
-    const uint32_t n = ctas_of(c);
-    if (b >= cum && b < cum + n) {
+  // chain order of the table: c = i + j kThreads sorted by (j, i), i.e. ascending c
+  uint32_t nj[kPartK];
+#pragma unroll
+  for (int j = 0; j < kPartK; ++j) nj[j] = ctas_of(wv[j], r_lo);
+  uint32_t cum_prev = 0u;  // CTAs of all chains of the slices before j
+#pragma unroll
+  for (int j = 0; j < kPartK; ++j) {
+    if (j * kThreads >= C) break;
+    uint32_t inc = nj[j];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(kFull, inc, d);
+      if (lane >= d) inc += v;
+    }
+    __syncthreads();  // the previous use of the buffers is over
+    if (lane == 31) red32[warp] = inc;
+    __syncthreads();
+    uint32_t cum = cum_prev + inc - nj[j], slice = 0u;
+    for (int x = 0; x < kWarps; ++x) {
+      if (x < warp) cum += red32[x];
+      slice += red32[x];
+    }
+    const int c = tid + j * kThreads;
+    if (c < C && b >= cum && b < cum + nj[j]) {
       sh->c = c;
       sh->part = b - cum;
-      sh->nparts = n;
+      sh->nparts = nj[j];
       sh->row0 = (int64_t)b * kWarps;  // the chain's rows are those of its CTAs cum .. cum + n - 1
       sh->idle = false;
-      if (rows && b == cum) rows[c] = make_int2((int)(cum * kWarps), (int)(n * kWarps));
+      if (rows && b == cum) rows[c] = make_int2((int)(cum * kWarps), (int)(nj[j] * kWarps));
     }
-    cum += n;
+    cum_prev += slice;
   }
   __syncthreads();
   return *sh;
@@ -519,6 +557,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
       // issued now so that their latency hides behind the sample evaluation
       const double yy = kVjp ? (ma.vjp_shared ? -__ldg(y + (int64_t)c * N + idx) : __ldg(y + ((int64_t)c * N + idx) * P + p)) : __ldg(y + idx);
       const double iv = kVjp ? 0.0 : __ldg(ivar + idx);
+      const double tx = (kTtv && ma.texp_vec) ? __ldg(ma.texp_vec + idx) : 1.0;  // per-cadence exposure time (unit stencil in dtk)
       double ltot = 0.0;
       bool owner = true;  // the lowest in-window planet owns the per-cadence terms
       // one call site for the sample evaluation: planet p with its gradient weights, any other
@@ -537,7 +576,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
         if (self) jself = jq;
         for (int k = 0; k < K; ++k) {
           const double w = sm.wk[k];
-          ltot = fma(w, xo::lc_point<true, kThreads, kDelay>(sm.elem[q], sm.cl, ttq + sm.dtk[k], self ? w : 0.0, gl, gsl), ltot);
+          ltot = fma(w, xo::lc_point<true, kThreads, kDelay>(sm.elem[q], sm.cl, kTtv ? ttq + __dmul_rn(tx, sm.dtk[k]) : ttq + sm.dtk[k],
+                                                             self ? w : 0.0, gl, gsl), ltot);
         }
       }
       if (kVjp) {
@@ -1169,21 +1209,27 @@ Split split_transit(int64_t N, int64_t C) {
   return Split{(int)w, L};
 }
 
+// Weighted partition only while there are fewer chains than resident CTA slots: then every chain needs several CTAs to fill
+// the device and how many each gets decides the balance (128 chains: 61.8 -> 56.7 us per step).  With more chains than slots
+// the hardware's dynamic CTA dispatch evens the load out by itself and the table only costs (1024 chains: 4.2e6 evals/s with
+// two CTAs per chain, 3.7e6 weighted; profiles/r02_tuning_sweep.txt).
+static int64_t transit_wave() { return (int64_t)sm_count() * transit_min_blocks(); }  // resident CTAs (3 per SM at 168 registers)
+
 bool transit_weighted(int64_t C, int64_t P) {
-  static const bool on = [] {  // XO_TRANSIT_WEIGHTED=0: every chain gets the same number of CTAs
-    const char *v = getenv("XO_TRANSIT_WEIGHTED");
-    return !(v && *v == '0');
-  }();
-  return on && C > 1 && C * P <= kMaxWeighted;
+  static const int mode = env_int("XO_TRANSIT_WEIGHTED", -1);  // 0: never, 1: whenever the table fits, default: see above
+  if (mode == 0 || C <= 1 || C * P > kMaxWeighted || C > kPartK * kThreads) return false;
+  return mode == 1 || C <= transit_wave();
 }
 
+// CTAs of a weighted launch: whole waves of the device -- every CTA slot busy from the start, and (equal work per CTA)
+// until the end; one wave while that leaves at least two CTAs per chain on average
 int64_t transit_weighted_grid(int64_t N, int64_t C) {
   const Split sp = split_transit(N, C);
-  const int64_t g0 = (int64_t)(sp.slots / kWarps) * C;   // what the uniform split would launch
-  const int64_t wave = (int64_t)sm_count() * transit_min_blocks();  // resident CTAs (3 per SM for the 168-register kernel)
-  if (g0 <= wave) return g0;
+  const int64_t g0 = (int64_t)(sp.slots / kWarps) * C;  // what the uniform split would launch
+  const int64_t wave = transit_wave();
+  if (g0 <= wave) return g0;  // short series: the launch does not fill the device anyway
   static const int waves_env = env_int("XO_TRANSIT_WAVES", 0);
-  int64_t waves = waves_env > 0 ? waves_env : (g0 + wave / 2) / wave;
+  int64_t waves = waves_env > 0 ? waves_env : (2 * C + wave - 1) / wave;
   if (waves * wave < C) waves = (C + wave - 1) / wave;
   return waves * wave;
 }
@@ -1210,7 +1256,7 @@ void launch_transit_logp_grad(const double *t, const double *y, const double *iv
 #define XO_LAUNCH_TTV(VJP, MOM)                                                                                                    \
   xo::launch_pdl(transit_logp_grad_kernel<3, VJP, MOM, false, false, true>, grid, dim3(kThreads), st, pdl, t, y, ivar, N, elem, cl, mean, \
                  P, dtk, wk, K, sp.L, sp.slots, moments, partial, ma)
-  if (ma.ttv_times) {  // TTVOrbit: element-level launches only
+  if (ma.ttv_times || ma.texp_vec) {  // TTVOrbit, per-cadence exposure times: element-level launches only
     if (ivar == nullptr) XO_LAUNCH_TTV(true, false);
     else if (moments) XO_LAUNCH_TTV(false, true);
     else XO_LAUNCH_TTV(false, false);
@@ -1246,7 +1292,7 @@ void launch_transit_logp_grad(const double *t, const double *y, const double *iv
 
 void launch_transit_lc_fwd(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int P, const double *dtk,
                            const double *wk, int K, const double *ttv_times, const int *ttv_count, int ttv_nt, double *lc,
-                           cudaStream_t st, bool light_delay) {
+                           cudaStream_t st, bool light_delay, const double *texp_vec) {
   const int sms = sm_count();
   int64_t per_chain = (N + 255) / 256;
   int64_t want = ((int64_t)sms * 8 + C - 1) / C;
@@ -1254,10 +1300,10 @@ void launch_transit_lc_fwd(const double *t, int64_t N, const double *elem, const
   if (gx < 1) gx = 1;
   if (light_delay)
     xo::launch(transit_lc_fwd_kernel<true>, dim3(gx, (unsigned)C), dim3(256), 0, st, t, N, elem, cl, P, dtk, wk, K, ttv_times, ttv_count,
-               ttv_nt, lc);
+               ttv_nt, texp_vec, lc);
   else
     xo::launch(transit_lc_fwd_kernel<false>, dim3(gx, (unsigned)C), dim3(256), 0, st, t, N, elem, cl, P, dtk, wk, K, ttv_times, ttv_count,
-               ttv_nt, lc);
+               ttv_nt, texp_vec, lc);
 }
 
 void launch_transit_resid(const double *t, const double *y, int64_t N, const double *elem, const double *cl, const double *mean,
@@ -1296,7 +1342,7 @@ int xo_transit_lc_fwd(const double *t, int64_t N, const double *elem, const doub
 // ---- the same three entry points for a TTVOrbit (/root/reference/src/exoplanet/orbits/ttv.py:35-187) ----
 int xo_transit_lc_fwd_ex(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
                          const double *dtk, const double *wk, int K, const double *ttv_times, const int *ttv_count, int ttv_nt,
-                         int light_delay, double *lc, void *stream) {
+                         int light_delay, const double *texp_vec, double *lc, void *stream) {
   if (int rc = check_batch(N, C, P)) return rc;
   if (K < 1 || K > XO_MAX_STENCIL) return XO_ERANGE;
   if (N == 0 || C == 0 || P == 0) return 0;
@@ -1304,7 +1350,7 @@ int xo_transit_lc_fwd_ex(const double *t, int64_t N, const double *elem, const d
   if (ttv_times && (!ttv_count || ttv_nt < 1)) return XO_EINVAL;
   if (ttv_times && light_delay) return XO_EINVAL;  // the reference has no such combination either (ttv.py has no delayed path)
   xo::launch_transit_lc_fwd(t, N, elem, cl, C, (int)P, dtk, wk, K, ttv_times, ttv_count, ttv_nt, lc, static_cast<cudaStream_t>(stream),
-                            light_delay != 0);
+                            light_delay != 0, texp_vec);
   return xo::launch_status();
 }
 
@@ -1417,14 +1463,15 @@ int xo_transit_logp_grad_ttv(const double *t, const double *y, const double *iva
 
 int xo_transit_lc_vjp_ex(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
                          const double *dtk, const double *wk, int K, const double *ttv_times, const int *ttv_count, int ttv_nt,
-                         int light_delay, const double *bar_lc, double *gel, double *gcl, double *gttv, void *workspace,
-                         size_t workspace_bytes, void *stream) {
+                         int light_delay, const double *texp_vec, const double *bar_lc, double *gel, double *gcl, double *gttv,
+                         void *workspace, size_t workspace_bytes, void *stream) {
   if (int rc = check_batch(N, C, P)) return rc;
   if (K < 1 || K > XO_MAX_STENCIL) return XO_ERANGE;
   if (C == 0) return 0;
   if (N == 0 || P == 0) return XO_EINVAL;
   if (!t || !elem || !cl || !dtk || !wk || !bar_lc || !gel || !gcl || !workspace) return XO_EINVAL;
   if (ttv_times && (!ttv_count || ttv_nt < 1 || !gttv || light_delay)) return XO_EINVAL;
+  if (texp_vec && light_delay) return XO_EINVAL;  // the delayed reverse pass has no per-cadence stencil (use the scalar form)
   if (workspace_bytes < xo_transit_logp_grad_workspace(N, C, P) + sizeof(double) * 2 * (size_t)C) return XO_EWORKSPACE;
   Split sp = split_transit(N, C);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1441,6 +1488,7 @@ int xo_transit_lc_vjp_ex(const double *t, int64_t N, const double *elem, const d
   ma.ttv_nt = ttv_nt;
   ma.ttv_grad = ttv_times ? gttv : nullptr;
   ma.light_delay = light_delay != 0;
+  ma.texp_vec = texp_vec;
   xo::launch_transit_logp_grad(t, bar_lc, nullptr, N, elem, cl, nullptr, C, (int)P, dtk, wk, K, sp, nullptr, partial, st, &ma);
   const int nacc = kNBase + (int)P * XO_NGRAD;
   const int64_t tot = C * nacc;

@@ -44,6 +44,8 @@ struct ModelArgs {
   double *ttv_grad = nullptr;
   // light-curve VJP mode only: light-travel delay (keplerian.py:411-470); the element blocks carry R_star in XO_EL_RSTAR
   int light_delay = 0;
+  // per-cadence exposure times texp_vec[N] (limb_dark.py:199-205; element-level launches): dtk then holds the UNIT stencil
+  const double *texp_vec = nullptr;
   // work partition by expected in-transit cadences (element-level launches): weights[C][P] (>= 1 each, see
   // transit_weight()), written by the kernel that derived the element blocks; rows[C] receives (first row, rows) of each
   // chain in `partial` for the fold.  null: every chain gets gridDim.x CTAs.
@@ -68,7 +70,7 @@ int64_t transit_weighted_rows(int64_t N, int64_t C);  // rows of `partial` such 
 // light curve forward with an optional transit-time table (lc[C][N][P])
 void launch_transit_lc_fwd(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int P, const double *dtk,
                            const double *wk, int K, const double *ttv_times, const int *ttv_count, int ttv_nt, double *lc,
-                           cudaStream_t st, bool light_delay = false);
+                           cudaStream_t st, bool light_delay = false, const double *texp_vec = nullptr);
 
 // enqueue transit_logp_grad_kernel; partial[C][slots][kNBase + P*XO_NGRAD]; model != nullptr
 // selects the single-launch model mode (elem / cl are then ignored)

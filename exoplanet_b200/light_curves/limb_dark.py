@@ -71,7 +71,7 @@ class _FusedLightCurveDelay(torch.autograd.Function):
         lc = torch.empty((1, t.numel(), P), dtype=torch.float64, device=t.device)
         with torch.cuda.device(t.device):
             _lib.check(lib.xo_transit_lc_fwd_ex(_ptr(t), t.numel(), _ptr(e3), _ptr(c2), 1, P, _ptr(dtk), _ptr(wk), dtk.numel(), None, None, 0,
-                                                1, _ptr(lc), _lib.stream_ptr()), "transit_lc_fwd_ex")
+                                                1, None, _ptr(lc), _lib.stream_ptr()), "transit_lc_fwd_ex")
         ctx.save_for_backward(e3, c2, t, dtk, wk)
         return lc[0]
 
@@ -87,7 +87,7 @@ class _FusedLightCurveDelay(torch.autograd.Function):
         gcl = torch.empty((1, 3), dtype=torch.float64, device=t.device)
         with torch.cuda.device(t.device):
             _lib.check(lib.xo_transit_lc_vjp_ex(_ptr(t), t.numel(), _ptr(e3), _ptr(c2), 1, P, _ptr(dtk), _ptr(wk), dtk.numel(), None, None, 0,
-                                                1, _ptr(bar), _ptr(gel), _ptr(gcl), None, _ptr(ws), ws.numel() * 8, _lib.stream_ptr()),
+                                                1, None, _ptr(bar), _ptr(gel), _ptr(gcl), None, _ptr(ws), ws.numel() * 8, _lib.stream_ptr()),
                        "transit_lc_vjp_ex")
         full = torch.zeros_like(e3[0])
         full[:, :_lib.NGRAD] = gel[0]
@@ -108,7 +108,7 @@ class _FusedLightCurveTTV(torch.autograd.Function):
         lc = torch.empty((1, t.numel(), P), dtype=torch.float64, device=t.device)
         with torch.cuda.device(t.device):
             _lib.check(lib.xo_transit_lc_fwd_ex(_ptr(t), t.numel(), _ptr(e3), _ptr(c2), 1, P, _ptr(dtk), _ptr(wk), dtk.numel(), _ptr(tt),
-                                                _ptr(count), nt, 0, _ptr(lc), _lib.stream_ptr()), "transit_lc_fwd_ex")
+                                                _ptr(count), nt, 0, None, _ptr(lc), _lib.stream_ptr()), "transit_lc_fwd_ex")
         ctx.save_for_backward(e3, c2, tt, t, dtk, wk, count)
         return lc[0]
 
@@ -125,13 +125,49 @@ class _FusedLightCurveTTV(torch.autograd.Function):
         gtt = torch.empty((1, P, nt), dtype=torch.float64, device=t.device)
         with torch.cuda.device(t.device):
             _lib.check(lib.xo_transit_lc_vjp_ex(_ptr(t), t.numel(), _ptr(e3), _ptr(c2), 1, P, _ptr(dtk), _ptr(wk), dtk.numel(), _ptr(tt),
-                                                _ptr(count), nt, 0, _ptr(bar), _ptr(gel), _ptr(gcl), _ptr(gtt), _ptr(ws), ws.numel() * 8,
+                                                _ptr(count), nt, 0, None, _ptr(bar), _ptr(gel), _ptr(gcl), _ptr(gtt), _ptr(ws), ws.numel() * 8,
                                                 _lib.stream_ptr()), "transit_lc_vjp_ex")
         full = torch.zeros_like(e3[0])
         full[:, :_lib.NGRAD] = gel[0]
         full[:, 0] = 0.0  # the time axis is anchored on the transit times, not on elem's t0 (its derivative is in gtt)
         valid = torch.arange(nt, device=t.device)[None, :] < count[:, None]
         return full, gcl[0], torch.where(valid, gtt[0], torch.zeros_like(gtt[0])), None, None, None, None
+
+
+class _FusedLightCurveTexp(torch.autograd.Function):
+    """lc[N, P] with one exposure time per cadence (limb_dark.py:199-205): sample k of cadence i sits at t_i + texp[i] dt_k;
+    ``dtk`` is the unit stencil.  Gradients w.r.t. the element table and cl (exposure times are data)."""
+
+    @staticmethod
+    def forward(ctx, elem, cl, t, dtk, wk, texp_vec):
+        lib = _lib.require_cuda()
+        e3 = elem.detach().contiguous().unsqueeze(0)
+        c2 = cl.detach().contiguous().unsqueeze(0)
+        P = e3.shape[1]
+        lc = torch.empty((1, t.numel(), P), dtype=torch.float64, device=t.device)
+        with torch.cuda.device(t.device):
+            _lib.check(lib.xo_transit_lc_fwd_ex(_ptr(t), t.numel(), _ptr(e3), _ptr(c2), 1, P, _ptr(dtk), _ptr(wk), dtk.numel(), None, None, 0,
+                                                0, _ptr(texp_vec), _ptr(lc), _lib.stream_ptr()), "transit_lc_fwd_ex")
+        ctx.save_for_backward(e3, c2, t, dtk, wk, texp_vec)
+        return lc[0]
+
+    @staticmethod
+    def backward(ctx, bar):
+        lib = _lib.require_cuda()
+        e3, c2, t, dtk, wk, texp_vec = ctx.saved_tensors
+        P = e3.shape[1]
+        bar = bar.contiguous().unsqueeze(0)
+        need = lib.xo_transit_logp_grad_workspace(t.numel(), 1, P) + 16
+        ws = torch.empty(need // 8 + 2, dtype=torch.float64, device=t.device)
+        gel = torch.empty((1, P, _lib.NGRAD), dtype=torch.float64, device=t.device)
+        gcl = torch.empty((1, 3), dtype=torch.float64, device=t.device)
+        with torch.cuda.device(t.device):
+            _lib.check(lib.xo_transit_lc_vjp_ex(_ptr(t), t.numel(), _ptr(e3), _ptr(c2), 1, P, _ptr(dtk), _ptr(wk), dtk.numel(), None, None, 0,
+                                                0, _ptr(texp_vec), _ptr(bar), _ptr(gel), _ptr(gcl), None, _ptr(ws), ws.numel() * 8,
+                                                _lib.stream_ptr()), "transit_lc_vjp_ex")
+        full = torch.zeros_like(e3[0])
+        full[:, :_lib.NGRAD] = gel[0]
+        return full, gcl[0], None, None, None, None
 
 
 class LimbDarkLightCurve:
@@ -188,6 +224,14 @@ class LimbDarkLightCurve:
             elem = orbit.elements(r=r, texp=tex, use_in_transit=bool(use_in_transit), light_delay=True)
             dtk, wk = fused._stencil_dev(fused.exposure_stencil(tex, oversample, order), dev)
             return _FusedLightCurveDelay.apply(elem, self.c, t.contiguous(), dtk, wk)
+        if type(orbit) is KeplerianOrbit and not light_delay and not scalar_texp and t.dim() == 1 and t.is_cuda:
+            # one exposure time per cadence (limb_dark.py:199-205): unit stencil, scaled per cadence in the kernel; the window
+            # carries the longest exposure (what the reference's broadcast of t_start - texp/2 amounts to, keplerian.py:766-770)
+            tv = _tensor(texp, dev).to(torch.float64).reshape(-1).contiguous()
+            if tv.numel() == t.numel():
+                elem = orbit.elements(r=r, texp=float(tv.max()), use_in_transit=use_in_transit)
+                dtk, wk = fused._stencil_dev(fused.exposure_stencil(1.0, oversample, order), dev)
+                return _FusedLightCurveTexp.apply(elem, self.c, t.contiguous(), dtk, wk, tv)
         from ..orbits.ttv import TTVOrbit
 
         if type(orbit) is TTVOrbit and not light_delay and scalar_texp and t.dim() == 1 and t.is_cuda:

@@ -324,113 +324,162 @@ class BatchedNUTS(BatchedHMC):
 
     Extra state after a transition: ``depth[C]`` (doublings used), ``diverging[C]``, ``n_leapfrog``."""
 
-    def __init__(self, logp_grad, q0, step_size=1e-2, max_depth=8, seed=0, target_accept=0.8):
+    def __init__(self, logp_grad, q0, step_size=1e-2, max_depth=8, seed=0, target_accept=0.8, use_graph=True):
         super().__init__(logp_grad, q0, step_size=step_size, n_leapfrog=1, seed=seed, target_accept=target_accept, use_graph=False)
         self.max_depth = int(max_depth)
-        C = self.q.shape[0]
-        dev = self.q.device
+        C, D = self.q.shape
+        dev, dt = self.q.device, self.q.dtype
         self.depth = torch.zeros(C, dtype=torch.int64, device=dev)
         self.diverging = torch.zeros(C, dtype=torch.bool, device=dev)
         self.n_leapfrog = 0
+        # The tree lives in persistent buffers that the pieces of a transition (begin, doubling j, end) update in place, so
+        # that each piece is ONE CUDA graph (captured the first time it runs, replayed afterwards): a doubling of depth j is
+        # 2^j model evaluations and ~50 small tensor kernels per leaf, launch-bound when issued one by one.  The host looks at
+        # the device once per doubling ("is any chain still growing?"), exactly as without graphs.
+        self._nuts_graph = bool(use_graph) and dev.type == "cuda"
+        self._pieces = {}
+        z = lambda *shape, dtype=dt: torch.zeros(shape, dtype=dtype, device=dev)  # noqa: E731
+        self._t = dict(h0=z(C), ql=z(C, D), pl=z(C, D), gl=z(C, D), qr=z(C, D), pr=z(C, D), gr=z(C, D), q_prop=z(C, D), lp_prop=z(C),
+                       g_prop=z(C, D), p_sum=z(C, D), log_w=z(C), active=z(C, dtype=torch.bool), depth=z(C, dtype=torch.int64),
+                       diverged=z(C, dtype=torch.bool), acc_sum=z(C), n_leaves=z(C), dh_max=z(C),
+                       ck_p=z(self.max_depth + 1, C, D), ck_s=z(self.max_depth + 1, C, D))
 
     @staticmethod
     def _turning(im, p_left, p_right, p_sum):
         adj = p_sum - 0.5 * (p_left + p_right)
         return ((im * p_left * adj).sum(-1) <= 0.0) | ((im * p_right * adj).sum(-1) <= 0.0)
 
-    def _transition(self):
-        q0, im = self.q, self.inv_mass
-        C, D = q0.shape
-        dev, dt = q0.device, q0.dtype
-        eps = self.eps[:, None]
-        p0 = torch.randn((C, D), dtype=dt, device=dev, generator=self.gen) / torch.sqrt(im)
-        h0 = -self.logp + 0.5 * (p0 * p0 * im).sum(-1)
+    # ---- the three pieces of a transition; all state in self._t, updated in place ----
+    def _begin(self):
+        T, im = self._t, self.inv_mass
+        p0 = torch.randn(self.q.shape, dtype=self.q.dtype, device=self.q.device, generator=self.gen) / torch.sqrt(im)
+        T["h0"].copy_(-self.logp + 0.5 * (p0 * p0 * im).sum(-1))
         # the tree: both edges, the current proposal, sum of momenta, log of the summed weights exp(-H)
-        ql, pl, gl = q0.clone(), p0.clone(), self.grad.clone()
-        qr, pr, gr = q0.clone(), p0.clone(), self.grad.clone()
-        q_prop, lp_prop, g_prop = q0.clone(), self.logp.clone(), self.grad.clone()
-        p_sum = p0.clone()
-        log_w = -h0  # weight of the initial point
-        active = torch.ones(C, dtype=torch.bool, device=dev)
-        depth = torch.zeros(C, dtype=torch.int64, device=dev)
-        diverged = torch.zeros(C, dtype=torch.bool, device=dev)
-        acc_sum = torch.zeros(C, dtype=dt, device=dev)
-        n_leaves = torch.zeros(C, dtype=dt, device=dev)
-        ck_p = torch.zeros((self.max_depth + 1, C, D), dtype=dt, device=dev)
-        ck_s = torch.zeros((self.max_depth + 1, C, D), dtype=dt, device=dev)
+        for k in ("ql", "qr", "q_prop"):
+            T[k].copy_(self.q)
+        for k in ("pl", "pr", "p_sum"):
+            T[k].copy_(p0)
+        for k in ("gl", "gr", "g_prop"):
+            T[k].copy_(self.grad)
+        T["lp_prop"].copy_(self.logp)
+        T["log_w"].copy_(-T["h0"])  # weight of the initial point
+        T["active"].fill_(True)
+        T["diverged"].fill_(False)
+        for k in ("depth", "acc_sum", "n_leaves", "dh_max"):
+            T[k].zero_()
+
+    def _doubling(self, j):
+        T, im = self._t, self.inv_mass
+        C, D = self.q.shape
+        dev, dt = self.q.device, self.q.dtype
+        eps = self.eps[:, None]
+        h0, active = T["h0"], T["active"].clone()
+        ck_p, ck_s = T["ck_p"], T["ck_s"]
         neg_inf = torch.full((C,), -float("inf"), dtype=dt, device=dev)
-        dh_max = torch.zeros(C, dtype=dt, device=dev)
+        dh_max, diverged = T["dh_max"].clone(), T["diverged"].clone()
+        acc_sum, n_leaves = T["acc_sum"].clone(), T["n_leaves"].clone()
+        go_right = torch.rand(C, dtype=dt, device=dev, generator=self.gen) < 0.5
+        sgn = torch.where(go_right, 1.0, -1.0).to(dt)[:, None]
+        # start from the edge the new half grows out of
+        q = torch.where(go_right[:, None], T["qr"], T["ql"])
+        p = torch.where(go_right[:, None], T["pr"], T["pl"])
+        g = torch.where(go_right[:, None], T["gr"], T["gl"])
+        sub_ok = active.clone()  # still building a valid (non-turning, non-diverging) half
+        s_psum = torch.zeros_like(p)
+        s_logw = neg_inf.clone()
+        s_q, s_lp, s_g = q.clone(), self.logp.clone(), g.clone()
+        for n in range(2 ** j):
+            p = p + 0.5 * sgn * eps * g
+            q = q + sgn * eps * im * p
+            lp, g = self.f(q)
+            p = p + 0.5 * sgn * eps * g
+            h = -lp + 0.5 * (p * p * im).sum(-1)
+            dh = h - h0
+            dh = torch.where(torch.isfinite(dh), dh, torch.full_like(dh, float("inf")))
+            dh_max = torch.where(active & (dh.abs() > dh_max.abs()) & torch.isfinite(dh), dh, dh_max)
+            div_now = sub_ok & (dh > 1000.0)
+            diverged = diverged | div_now
+            sub_ok = sub_ok & ~div_now
+            # acceptance statistic over every leaf that was actually visited
+            acc_sum = acc_sum + torch.where(active, torch.exp(torch.clamp(-dh, max=0.0)), torch.zeros_like(dh))
+            n_leaves = n_leaves + active.to(dt)
+            # progressive (uniform-by-weight) sampling of the proposal inside this half
+            w_new = torch.where(sub_ok, -h, neg_inf)
+            s_logw_new = torch.logaddexp(s_logw, w_new)
+            take = sub_ok & (torch.log(torch.rand(C, dtype=dt, device=dev, generator=self.gen)) < w_new - s_logw_new)
+            s_q = torch.where(take[:, None], q, s_q)
+            s_lp = torch.where(take, lp, s_lp)
+            s_g = torch.where(take[:, None], g, s_g)
+            s_logw = torch.where(sub_ok, s_logw_new, s_logw)
+            s_psum = torch.where(sub_ok[:, None], s_psum + p, s_psum)
+            # U-turn checks inside the half: checkpoints at even leaves, checks at odd ones
+            idx_max = _popcount(n >> 1)
+            if n % 2 == 0:
+                ck_p[idx_max].copy_(p)
+                ck_s[idx_max].copy_(s_psum)
+            else:
+                idx_min = idx_max - _trailing_ones(n) + 1
+                for i in range(idx_max, idx_min - 1, -1):
+                    sub_sum = s_psum - ck_s[i] + ck_p[i]
+                    sub_ok = sub_ok & ~self._turning(im, ck_p[i], p, sub_sum)
+        # merge the half into the tree (only where it is valid)
+        merged = active & sub_ok
+        take = merged & (torch.log(torch.rand(C, dtype=dt, device=dev, generator=self.gen)) < s_logw - T["log_w"])
+        T["q_prop"].copy_(torch.where(take[:, None], s_q, T["q_prop"]))
+        T["lp_prop"].copy_(torch.where(take, s_lp, T["lp_prop"]))
+        T["g_prop"].copy_(torch.where(take[:, None], s_g, T["g_prop"]))
+        T["log_w"].copy_(torch.where(merged, torch.logaddexp(T["log_w"], s_logw), T["log_w"]))
+        T["p_sum"].copy_(torch.where(merged[:, None], T["p_sum"] + s_psum, T["p_sum"]))
+        mr, ml = (merged & go_right)[:, None], (merged & ~go_right)[:, None]
+        for k, v in (("q", q), ("p", p), ("g", g)):
+            T[k + "r"].copy_(torch.where(mr, v, T[k + "r"]))
+            T[k + "l"].copy_(torch.where(ml, v, T[k + "l"]))
+        T["depth"].add_(active.to(torch.int64))
+        T["dh_max"].copy_(dh_max)
+        T["diverged"].copy_(diverged)
+        T["acc_sum"].copy_(acc_sum)
+        T["n_leaves"].copy_(n_leaves)
+        # the whole tree must not have turned either
+        turned = self._turning(im, T["pl"], T["pr"], T["p_sum"])
+        T["active"].copy_(merged & ~turned)
+
+    def _end(self):
+        T = self._t
+        self.q.copy_(T["q_prop"])
+        self.logp.copy_(T["lp_prop"])
+        self.grad.copy_(T["g_prop"])
+        self.accept_prob.copy_(T["acc_sum"] / torch.clamp(T["n_leaves"], min=1.0))
+        self.energy_error.copy_(T["dh_max"])  # largest energy error met along the trajectory
+        self.depth.copy_(T["depth"])
+        self.diverging.copy_(T["diverged"])
+
+    def _run(self, key, fn, *args):
+        """run one piece: eagerly, or as its CUDA graph (first call: a real run on a side stream, then the capture)"""
+        if not self._nuts_graph:
+            fn(*args)
+            return
+        g = self._pieces.get(key)
+        if g is not None:
+            g.replay()
+            return
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):  # this run IS the piece's execution for this call; the graph serves the later ones
+            fn(*args)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        g.register_generator_state(self.gen)
+        with torch.cuda.graph(g):
+            fn(*args)
+        self._pieces[key] = g
+
+    def _transition(self):
+        self._run("begin", self._begin)
         for j in range(self.max_depth):
-            go_right = torch.rand(C, dtype=dt, device=dev, generator=self.gen) < 0.5
-            sgn = torch.where(go_right, 1.0, -1.0).to(dt)[:, None]
-            # start from the edge the new half grows out of
-            q = torch.where(go_right[:, None], qr, ql)
-            p = torch.where(go_right[:, None], pr, pl)
-            g = torch.where(go_right[:, None], gr, gl)
-            sub_ok = active.clone()  # still building a valid (non-turning, non-diverging) half
-            s_psum = torch.zeros_like(p)
-            s_logw = neg_inf.clone()
-            s_q, s_lp, s_g = q.clone(), self.logp.clone(), g.clone()
-            first_p = None
-            for n in range(2 ** j):
-                p = p + 0.5 * sgn * eps * g
-                q = q + sgn * eps * im * p
-                lp, g = self.f(q)
-                p = p + 0.5 * sgn * eps * g
-                self.n_leapfrog += 1
-                h = -lp + 0.5 * (p * p * im).sum(-1)
-                dh = h - h0
-                dh = torch.where(torch.isfinite(dh), dh, torch.full_like(dh, float("inf")))
-                dh_max = torch.where(active & (dh.abs() > dh_max.abs()) & torch.isfinite(dh), dh, dh_max)
-                div_now = sub_ok & (dh > 1000.0)
-                diverged |= div_now
-                sub_ok = sub_ok & ~div_now
-                # acceptance statistic over every leaf that was actually visited
-                acc_sum += torch.where(active, torch.exp(torch.clamp(-dh, max=0.0)), torch.zeros_like(dh))
-                n_leaves += active.to(dt)
-                # progressive (uniform-by-weight) sampling of the proposal inside this half
-                w_new = torch.where(sub_ok, -h, neg_inf)
-                s_logw_new = torch.logaddexp(s_logw, w_new)
-                take = sub_ok & (torch.log(torch.rand(C, dtype=dt, device=dev, generator=self.gen)) < w_new - s_logw_new)
-                s_q = torch.where(take[:, None], q, s_q)
-                s_lp = torch.where(take, lp, s_lp)
-                s_g = torch.where(take[:, None], g, s_g)
-                s_logw = torch.where(sub_ok, s_logw_new, s_logw)
-                s_psum = torch.where(sub_ok[:, None], s_psum + p, s_psum)
-                if n == 0:
-                    first_p = p.clone()
-                # U-turn checks inside the half: checkpoints at even leaves, checks at odd ones
-                idx_max = _popcount(n >> 1)
-                if n % 2 == 0:
-                    ck_p[idx_max] = p
-                    ck_s[idx_max] = s_psum
-                else:
-                    idx_min = idx_max - _trailing_ones(n) + 1
-                    for i in range(idx_max, idx_min - 1, -1):
-                        sub_sum = s_psum - ck_s[i] + ck_p[i]
-                        sub_ok = sub_ok & ~self._turning(im, ck_p[i], p, sub_sum)
-            # merge the half into the tree (only where it is valid)
-            merged = active & sub_ok
-            take = merged & (torch.log(torch.rand(C, dtype=dt, device=dev, generator=self.gen)) < s_logw - log_w)
-            q_prop = torch.where(take[:, None], s_q, q_prop)
-            lp_prop = torch.where(take, s_lp, lp_prop)
-            g_prop = torch.where(take[:, None], s_g, g_prop)
-            log_w = torch.where(merged, torch.logaddexp(log_w, s_logw), log_w)
-            p_sum = torch.where(merged[:, None], p_sum + s_psum, p_sum)
-            mr, ml = (merged & go_right)[:, None], (merged & ~go_right)[:, None]
-            qr, pr, gr = torch.where(mr, q, qr), torch.where(mr, p, pr), torch.where(mr, g, gr)
-            ql, pl, gl = torch.where(ml, q, ql), torch.where(ml, p, pl), torch.where(ml, g, gl)
-            depth = depth + active.to(depth.dtype)
-            # the whole tree must not have turned either
-            turned = self._turning(im, pl, pr, p_sum)
-            active = merged & ~turned
-            if j + 1 < self.max_depth and not bool(active.any()):  # the one look at the device per doubling
+            self._run(("doubling", j), self._doubling, j)
+            self.n_leapfrog += 2 ** j
+            if j + 1 < self.max_depth and not bool(self._t["active"].any()):  # the one look at the device per doubling
                 break
-        self.q.copy_(q_prop)
-        self.logp.copy_(lp_prop)
-        self.grad.copy_(g_prop)
+        self._run("end", self._end)
         self.n_evals = self.n_leapfrog - self.L  # transition() adds L (= 1): n_evals counts model evaluations
-        self.accept_prob.copy_(acc_sum / torch.clamp(n_leaves, min=1.0))
-        self.energy_error.copy_(dh_max)  # largest energy error met along the trajectory
-        self.depth.copy_(depth)
-        self.diverging.copy_(diverged)
+

@@ -160,15 +160,19 @@ int xo_elements_from_params(const double *par, const double *star, int64_t C, in
  * != 0 and elem[XO_EL_RSTAR] = R_star in R_sun; every sample is evaluated at the retarded time t - D(position, line-of-sight
  * velocity and acceleration at t) -- a second Kepler solve -- and the reverse pass carries d D / d elements (sin i included;
  * d / d R_star is not provided).  The reference evaluates every cadence in this mode (in_transit raises for light_delay,
- * keplerian.py:720-723): pass the window of an ordinary orbit widened by 2 a (1 + e) / c, or (-inf, +inf). */
+ * keplerian.py:720-723): pass the window of an ordinary orbit widened by 2 a (1 + e) / c, or (-inf, +inf).
+ * Per-cadence exposure times (/root/reference/src/exoplanet/light_curves/limb_dark.py:199-205, tests/light_curves_test.py:105):
+ * texp_vec[N] != NULL scales the stencil of every cadence, t_i + texp_vec[i] * dtk[k]; dtk then holds the UNIT stencil
+ * (offsets in exposure times) and the element windows must be wide enough for the longest exposure (or infinite, the
+ * reference's use_in_transit=False).  Not combined with light_delay in the reverse pass. */
 #define XO_EL_RSTAR 14
 int xo_transit_lc_fwd_ex(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
                          const double *dtk, const double *wk, int K, const double *ttv_times, const int *ttv_count, int ttv_nt,
-                         int light_delay, double *lc, void *stream);
+                         int light_delay, const double *texp_vec, double *lc, void *stream);
 int xo_transit_lc_vjp_ex(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
                          const double *dtk, const double *wk, int K, const double *ttv_times, const int *ttv_count, int ttv_nt,
-                         int light_delay, const double *bar_lc, double *gel, double *gcl, double *gttv, void *workspace,
-                         size_t workspace_bytes, void *stream);
+                         int light_delay, const double *texp_vec, const double *bar_lc, double *gel, double *gcl, double *gttv,
+                         void *workspace, size_t workspace_bytes, void *stream);
 int xo_transit_logp_grad_ttv(const double *t, const double *y, const double *ivar, int64_t N, const double *elem,
                              const double *cl, const double *mean, int64_t C, int64_t P, const double *dtk, const double *wk,
                              int K, double lognorm, const double *moments, const double *ttv_times, const int *ttv_count,

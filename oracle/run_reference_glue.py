@@ -236,6 +236,10 @@ def main():
         s1["lc_texp_order%d" % order] = arr(lc.get_light_curve(orbit=orbit, r=r_pl, t=tt, texp=0.1, oversample=7, order=order))
     s1["lc_texp_os4"] = arr(lc.get_light_curve(orbit=orbit, r=r_pl, t=tt, texp=0.05, oversample=4))
     # light-travel delay (keplerian.py:411-470): every cadence evaluated at its retarded position (limb_dark.py:156,215)
+    # one exposure time per cadence (limb_dark.py:199-205; the reference's own test uses use_in_transit=False)
+    texp_vec = 0.02 + 0.08 * (0.5 + 0.5 * np.sin(0.37 * np.arange(len(np.asarray(tt)))))
+    s1["texp_vec"] = arr(texp_vec)
+    s1["lc_texp_vec"] = arr(lc.get_light_curve(orbit=orbit, r=r_pl, t=tt, texp=texp_vec, oversample=7, order=1, use_in_transit=False))
     s1["lc_light_delay"] = arr(lc.get_light_curve(orbit=orbit, r=r_pl, t=tt, light_delay=True))
     s1["lc_light_delay_texp"] = arr(lc.get_light_curve(orbit=orbit, r=r_pl, t=tt, texp=0.1, oversample=7, light_delay=True))
     out["two_planets"] = s1

@@ -362,3 +362,49 @@ def test_batched_nuts_on_transit_posterior_agrees_with_hmc():
     for j in (0, 1, 5, 8):  # log period, t0, log r/R*, mean flux: the well-constrained coordinates
         assert abs(a[:, j].mean() - b[:, j].mean()).item() < 0.5 * max(sa[j].item(), sb[j].item()), (j, a[:, j].mean(), b[:, j].mean(), sa[j], sb[j])
         assert 0.65 < (sb[j] / sa[j]).item() < 1.55, (j, sa[j], sb[j])
+
+
+def test_per_cadence_exposure_times_fused_kernels(golden):
+    """one exposure time per cadence (limb_dark.py:199-205) inside the fused kernels: against the reference's own
+    get_light_curve(texp=vector, use_in_transit=False) (fixture from oracle/run_reference_glue.py), the reference's
+    test_variable_texp property (constant vector == scalar, tests/light_curves_test.py:105-146), and the reverse pass
+    against autograd through the op-by-op path"""
+    from exoplanet_b200.light_curves import LimbDarkLightCurve
+    from exoplanet_b200.light_curves.limb_dark import _FusedLightCurveTexp
+    from exoplanet_b200.orbits import KeplerianOrbit
+
+    s = golden("reference_glue")["two_planets"]
+    p = s["params"]
+    keys = ("period", "t0", "ecc", "omega", "b", "m_planet")
+    leaves = {k: dev(p[k]).requires_grad_(True) for k in keys}
+
+    def orbit():
+        return KeplerianOrbit(m_star=p["m_star"], r_star=p["r_star"], Omega=dev(p["Omega"]), device=DEV, **leaves)
+
+    lc = LimbDarkLightCurve(s["u"][0], s["u"][1], device=DEV)
+    t, r = dev(s["t_lc"]), dev(s["r_pl"])
+    tv = dev(s["texp_vec"])
+    got = lc.get_light_curve(orbit=orbit(), r=r, t=t, texp=tv, oversample=7, order=1, use_in_transit=False)
+    assert isinstance(got.grad_fn, _FusedLightCurveTexp._backward_cls)
+    ref = np.array(s["lc_texp_vec"])
+    assert np.max(np.abs(got.detach().cpu().numpy() - ref)) < 2e-13
+    # with the in-transit window (widened by the longest exposure) the same values, exact zeros elsewhere
+    win = lc.get_light_curve(orbit=orbit(), r=r, t=t, texp=tv, oversample=7, order=1)
+    assert torch.max(torch.abs(win - got)).item() < 1e-15
+    # constant vector == scalar, both ways round (the reference's test_variable_texp)
+    const = torch.full_like(t, 0.1)
+    for uit in (False, None):
+        a = lc.get_light_curve(orbit=orbit(), r=r, t=t, texp=0.1, use_in_transit=uit)
+        b_ = lc.get_light_curve(orbit=orbit(), r=r, t=t, texp=const, use_in_transit=False)
+        assert torch.max(torch.abs(a - b_)).item() < 1e-14
+    # reverse pass
+    w = torch.linspace(0.5, 1.5, t.numel(), dtype=torch.float64, device=DEV)[:, None] * dev([1.0, -0.7])[None, :]
+    generic = lc._generic_light_curve(orbit(), r, t, tv, 7, 1, False, False)
+    assert torch.max(torch.abs(generic - got)).item() < 1e-13
+    ga = torch.autograd.grad((got * w).sum(), list(leaves.values()), allow_unused=True)
+    gb = torch.autograd.grad((generic * w).sum(), list(leaves.values()), allow_unused=True)
+    for a, b_, name in zip(ga, gb, keys):
+        if b_ is None:
+            continue
+        assert a is not None, name
+        assert torch.max(torch.abs(a - b_)).item() < 1e-8 * (b_.abs().max().item() + 1e-12), (name, a, b_)

@@ -1,9 +1,9 @@
 #!/bin/bash
 # usage: tools/gpurun_retry.sh LOGFILE [--gpus N] --timeout S -- 'command'
-# retries while gpurun answers "transient" (no box / slot free: nothing charged)
+# retries while gpurun answers that nothing was charged (no box / slot free, pod draining): up to ~40 min
 LOG=$1; shift
-for i in 1 2 3 4 5 6; do
+for i in $(seq 1 40); do
   /usr/local/graft/bin/gpurun "$@" > $LOG 2>&1
-  if grep -q "status=transient" $LOG || grep -q "exit code 3" $LOG; then sleep 60; continue; fi
+  if grep -q "nothing was charged" $LOG || grep -q "status=transient" $LOG || grep -q "exit code 3" $LOG; then sleep 60; continue; fi
   break
 done
