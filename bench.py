@@ -189,6 +189,21 @@ def cpu_port_setup(t, p, truth):
     return O, y, dtk, wk
 
 
+def _host_state(load_before=None):
+    """what else competes for the host's cores while the CPU arm is timed (the GPU boxes are shared): load averages, the
+    cgroup's CPU quota and the CPUs this process may run on"""
+    out = {"loadavg_after": [round(x, 1) for x in os.getloadavg()]}
+    if load_before is not None:
+        out["loadavg_before"] = [round(x, 1) for x in load_before]
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            out["cgroup_cpu_quota"] = open(path).read().strip()
+            break
+        except OSError:
+            pass
+    return out
+
+
 def arm_reference(args):
     """The reference's own CPU implementation of the path is exoplanet-core (not in this image) -> the
     CPU restatement (oracle port) on all host cores.  One step = `inner` passes over the same 128-chain batch the
@@ -200,6 +215,8 @@ def arm_reference(args):
     if rank != 0:
         return
     tier = probe_reference_tier()
+    load0 = os.getloadavg()
+    cpus_allowed = len(os.sched_getaffinity(0))  # before libgomp pins this thread to one core
     nc = args.chains
     t, p, truth = build_problem(nc)
     O, y, dtk, wk = cpu_port_setup(t, p, truth)
@@ -256,7 +273,7 @@ def arm_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": bench_config(nc, args.gpus),
         "cpu_baseline": {"value": val, "unit": "evals/s", "cores": threads, "kind": "port",
-                         "sample": "%d passes over %d chains x N=1e5 per step (OpenMP over chains, pinned), %d steps, %.2f s timed; "
+                         "sample": "%d passes over %d chains x N=1e5 per step (OpenMP over chains x 8 cadence blocks, pinned), %d steps, %.2f s timed; "
                                    "value from the median step" % (inner, nc, args.steps, float(per.sum())),
                          "value_mean": nc * inner / mean, "value_best": nc * inner / best,
                          "step_time_spread": float((per.max() - per.min()) / med),
@@ -264,7 +281,7 @@ def arm_reference(args):
                          "use_in_transit_false": {"value": ka / min(ba), "unit": "evals/s", "cores": threads,
                                                   "sample": "%d chains, every cadence solved, best of 2" % ka},
                          "omp": {k: os.environ.get(k) for k in ("OMP_PROC_BIND", "OMP_PLACES", "OMP_NUM_THREADS")},
-                         "host_cpus": os.cpu_count()},
+                         "host_cpus": os.cpu_count(), "host": dict(_host_state(load0), cpus_allowed=cpus_allowed)},
         "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "reference_tier": tier,
         "note": "CPU restatement of the reference mathematics (oracle/xo_oracle.c); exoplanet-core/PyTensor are not installable here",
@@ -360,7 +377,8 @@ def _extra_config0(lib, dev, d, flush, out, O):
 
         ms = _time_steps(step, 20, flush)
         sel = np.unique(np.linspace(0, Cn - 1, 8).astype(int))
-        el_o = O.elements_from_params(p["period"][sel], p["t0"][sel], p["ecc"][sel], p["omega"][sel], p["b"][sel], p["ror"][sel])
+        el_o = O.elements_from_params(p["period"][sel], p["t0"][sel], p["ecc"][sel], p["omega"][sel], p["b"][sel], p["ror"][sel],
+                                      m_planet=p["m_planet"][sel])
         args_o = (t, y, np.full(N, 1 / SIGMA ** 2), el_o, O.get_cl(p["u1"][sel], p["u2"][sel]), p["mean"][sel], np.zeros(1), np.ones(1))
         lo, geo, _, gmo = O.transit_logp_grad(*args_o, lognorm=data.lognorm)
         entry["%d chains" % Cn] = {
@@ -720,10 +738,29 @@ def arm_ours(args):
     # warm-up: >= W calls AND >= 0.15 s of sustained host<->device traffic -- the PCIe link / copy
     # engines reach full speed only after tens of ms of activity (tools/numa_probe.py: the same
     # 3 x 0.8 MB copy takes 185 us cold, 65 us warm), and an MCMC run is sustained traffic
-    w0, nw = time.perf_counter(), 0
-    while nw < max(3, args.warmup) or time.perf_counter() - w0 < 0.15:
+    def pcie_link():
+        try:
+            q = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pcie.link.gen.current,pcie.link.width.current",
+                                "--format=csv,noheader"], capture_output=True, text=True, timeout=10).stdout.strip()
+            return q
+        except Exception:
+            return None
+
+    link_before = pcie_link()
+    # ... and until the per-call time has settled (the median of the last 20 calls within 5 % of the 20 before), at most 2 s
+    w0, nw, hist = time.perf_counter(), 0, []
+    while True:
+        s0 = time.perf_counter()
         step_host()
+        hist.append(time.perf_counter() - s0)
         nw += 1
+        el = time.perf_counter() - w0
+        if nw >= max(3, args.warmup) and el >= 0.15:
+            settled = len(hist) >= 40 and abs(np.median(hist[-20:]) / np.median(hist[-40:-20]) - 1.0) < 0.05
+            if settled or el > 2.0:
+                break
+    e2e_warm = {"calls": nw, "seconds": time.perf_counter() - w0, "first_calls_us": [round(x * 1e6) for x in hist[:3]],
+                "last_calls_us_median": round(float(np.median(hist[-20:])) * 1e6), "pcie_link_before": link_before}
     barrier()
     # K synchronous calls, timed as a block; the block is repeated 5 times and the MEDIAN block is reported (the host<->device
     # path of a fresh box is bimodal -- the same 2.4 MB upload takes 65 or 185 us depending on the PCIe link state,
@@ -908,7 +945,7 @@ def arm_ours(args):
         "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "xo_transit_model_logp_grad_host: t,y,ivar (one pinned block, one DMA), params from pinned host memory every call; "
                        "logp+grads back to host",
-                "timing": "median of 5 blocks of `steps` synchronous calls",
+                "timing": "median of 5 blocks of `steps` synchronous calls", "warmup": e2e_warm, "pcie_link_after": pcie_link(),
                 "blocks_evals_per_s": [float(C_loc * args.steps / b) for b in e2e_blocks]},
         "e2e_resident_data": {"value": total_evals / (res_ms * 1e-3), "unit": "evals/s",
                               "h2d_bytes_per_step": sum(h[k].numel() * 8 for k in ("par", "star", "mean", "dtk", "wk")), "d2h_bytes_per_step": d2h,

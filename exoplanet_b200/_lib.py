@@ -54,6 +54,7 @@ _SIGNATURES = {
     "xo_transit_data_moments": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "xo_transit_moments_len": (_sz, [_i64]),
     "xo_transit_data_index": (_i32, [_vp, _i64, _vp, _sz, _vp]),
+    "xo_transit_data_moments_index": (_i32, [_vp, _vp, _vp, _i64, _vp, _sz, _vp]),
     "xo_transit_logp_grad": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _dbl, _vp, _vp, _vp, _vp, _vp,
                                     _vp, _sz, _vp]),
     "xo_transit_model_workspace": (_sz, [_i64, _i64, _i64]),

@@ -163,6 +163,7 @@ const char *xo_strerror(int status) {
 }
 
 int xo_kepler_host(const double *M, const double *e, double *sinf, double *cosf, int64_t n, int device) {
+  XO_NVTX_SCOPE("xo_kepler_host");
   if (n < 0) return XO_EINVAL;
   if (n == 0) return 0;
   if (!M || !e || !sinf || !cosf) return XO_EINVAL;
@@ -184,6 +185,7 @@ int xo_kepler_host(const double *M, const double *e, double *sinf, double *cosf,
 }
 
 int xo_qsv_host(const double *b, const double *r, double *s, double *dsdb, double *dsdr, int64_t n, int device) {
+  XO_NVTX_SCOPE("xo_qsv_host");
   if (n < 0) return XO_EINVAL;
   if (n == 0) return 0;
   if (!b || !r || !s || ((dsdb == nullptr) != (dsdr == nullptr))) return XO_EINVAL;
@@ -211,6 +213,7 @@ int xo_qsv_host(const double *b, const double *r, double *s, double *dsdb, doubl
 int xo_contact_points_host(const double *a, const double *e, const double *cosw, const double *sinw, const double *cosi,
                            const double *sini, const double *L, double *M_left, double *M_right, int32_t *flag,
                            int64_t n, int device) {
+  XO_NVTX_SCOPE("xo_contact_points_host");
   if (n < 0) return XO_EINVAL;
   if (n == 0) return 0;
   if (!a || !e || !cosw || !sinw || !cosi || !sini || !L || !M_left || !M_right || !flag) return XO_EINVAL;
@@ -239,6 +242,7 @@ int xo_contact_points_host(const double *a, const double *e, const double *cosw,
 
 int xo_transit_lc_host(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
                        const double *dtk, const double *wk, int K, double *lc, int device) {
+  XO_NVTX_SCOPE("xo_transit_lc_host");
   if (N < 0 || C < 0 || P < 0 || K < 1) return XO_EINVAL;
   if (N == 0 || C == 0 || P == 0) return 0;
   if (!t || !elem || !cl || !dtk || !wk || !lc) return XO_EINVAL;
@@ -265,6 +269,7 @@ int xo_transit_logp_grad_host(const double *t, const double *y, const double *iv
                               const double *cl, const double *mean, int64_t C, int64_t P, const double *dtk,
                               const double *wk, int K, double lognorm, double *logp, double *gel, double *gcl,
                               double *gmean, int device) {
+  XO_NVTX_SCOPE("xo_transit_logp_grad_host");
   if (N <= 0 || C < 0 || P <= 0 || K < 1) return XO_EINVAL;
   if (C == 0) return 0;
   if (!t || !y || !ivar || !elem || !cl || !mean || !dtk || !wk || !logp || !gel || !gcl || !gmean) return XO_EINVAL;
@@ -272,8 +277,9 @@ int xo_transit_logp_grad_host(const double *t, const double *y, const double *iv
   XO_TRY(ds.err);
   StreamGuard guard(ds.st, ds.side);  // declared before the arena: the stream-ordered free is enqueued first, then the guard waits
   const size_t ws = xo_transit_logp_grad_workspace(N, C, P);
+  const size_t mom_len = xo_transit_moments_len(N);  // moments + time index
   Arena ar(3 * pad(N) + pad(C * P * XO_NEL) + pad(3 * C) + pad(C) + 2 * pad(K) + pad(C) + pad(C * P * XO_NGRAD) +
-               pad(3 * C) + pad(C) + pad(XO_MOMENTS_LEN) + pad(ws, 1),
+               pad(3 * C) + pad(C) + pad(mom_len) + pad(ws, 1),
            ds.st);
   XO_TRY(ar.err);
   double *dt = ar.take<double>(N), *dy = ar.take<double>(N), *dv = ar.take<double>(N);
@@ -281,7 +287,7 @@ int xo_transit_logp_grad_host(const double *t, const double *y, const double *iv
   double *dd = ar.take<double>(K), *dw = ar.take<double>(K);
   double *dlp = ar.take<double>(C), *dge = ar.take<double>(C * P * XO_NGRAD), *dgc = ar.take<double>(3 * C),
          *dgm = ar.take<double>(C);
-  double *dmom = ar.take<double>(XO_MOMENTS_LEN);
+  double *dmom = ar.take<double>(mom_len);
   void *dws = ar.take<char>(ws);
   XO_TRY(h2d(dt, t, (size_t)N * 8, ds.st));
   XO_TRY(h2d(dy, y, (size_t)N * 8, ds.st));
@@ -291,8 +297,8 @@ int xo_transit_logp_grad_host(const double *t, const double *y, const double *iv
   XO_TRY(h2d(dm, mean, (size_t)C * 8, ds.st));
   XO_TRY(h2d(dd, dtk, (size_t)K * 8, ds.st));
   XO_TRY(h2d(dw, wk, (size_t)K * 8, ds.st));
-  // data moments (one pass, a few microseconds): the sweep then reads t only and skips quiet steps
-  XO_RC(xo_transit_data_moments(dt, dy, dv, N, dmom, ds.st));
+  // data moments + time index (one pass, a few microseconds): the sweep then reads no time stamps
+  XO_RC(xo_transit_data_moments_index(dt, dy, dv, N, dmom, mom_len, ds.st));
   XO_RC(xo_transit_logp_grad(dt, dy, dv, N, del, dcl, dm, C, P, dd, dw, K, lognorm, dmom, dlp, dge, dgc, dgm, dws, ws, ds.st));
   XO_TRY(d2h(logp, dlp, (size_t)C * 8, ds.st));
   XO_TRY(d2h(gel, dge, (size_t)C * P * XO_NGRAD * 8, ds.st));
@@ -307,6 +313,7 @@ int xo_transit_model_logp_grad_host(const double *t, const double *y, const doub
                                     const double *star, const double *mean, int64_t C, int64_t P, const double *dtk,
                                     const double *wk, int K, double texp, int use_in_transit, double lognorm,
                                     double *logp, double *gpar, double *gstar, double *gmean, int device) {
+  XO_NVTX_SCOPE("xo_transit_model_logp_grad_host");
   if (N <= 0 || C < 0 || P <= 0 || K < 1) return XO_EINVAL;
   if (C == 0) return 0;
   if (!t || !y || !ivar || !par || !star || !mean || !dtk || !wk || !logp || !gpar || !gstar || !gmean) return XO_EINVAL;
@@ -316,11 +323,12 @@ int xo_transit_model_logp_grad_host(const double *t, const double *y, const doub
   const size_t ws = xo_transit_model_workspace(N, C, P);
   const size_t nin = (size_t)C * P * XO_NPAR + (size_t)C * XO_NSTAR + (size_t)C + 2 * (size_t)K;
   const size_t nout = (size_t)C + (size_t)C * P * XO_NPAR + (size_t)C * XO_NSTAR + (size_t)C;
-  Arena ar(pad(3 * N) + pad(nin) + pad(nout) + pad(XO_MOMENTS_LEN) + pad(ws, 1), ds.st);
+  const size_t mom_len = xo_transit_moments_len(N);  // moments + time index
+  Arena ar(pad(3 * N) + pad(nin) + pad(nout) + pad(mom_len) + pad(ws, 1), ds.st);
   XO_TRY(ar.err);
   double *dt = ar.take<double>(3 * N), *dy = dt + N, *dv = dy + N;  // one block: one DMA when the caller's arrays are one block too
   double *din = ar.take<double>(nin), *dout = ar.take<double>(nout);
-  double *dmom = ar.take<double>(XO_MOMENTS_LEN);
+  double *dmom = ar.take<double>(mom_len);
   void *dws = ar.take<char>(ws);
   double *dp = din, *dst = dp + C * P * XO_NPAR, *dm = dst + C * XO_NSTAR, *dd = dm + C, *dw = dd + K;
   double *dlp = dout, *dgp = dlp + C, *dgs = dgp + C * P * XO_NPAR, *dgm = dgs + C * XO_NSTAR;
@@ -362,9 +370,9 @@ int xo_transit_model_logp_grad_host(const double *t, const double *y, const doub
                                      dgs, dgm, dws, ws, ps, 1));
     XO_TRY(cudaEventRecord(ds.ev_join, ps));
   }
-  // data moments (one pass, a few microseconds): the sweep then reads t only and skips quiet steps.  No time index here:
-  // building it costs more than it saves when the light curve is uploaded for a single evaluation (the resident handle has it)
-  XO_RC(xo_transit_data_moments(dt, dy, dv, N, dmom, ds.st));
+  // data moments and the time index in one pass (a few microseconds): the sweep then reads no time stamp at all and the out-of-
+  // transit Gaussian terms are closed-form
+  XO_RC(xo_transit_data_moments_index(dt, dy, dv, N, dmom, mom_len, ds.st));
   if (split) {
     XO_TRY(cudaStreamWaitEvent(ds.st, ds.ev_join, 0));
     ar.also = nullptr;  // joined: the main stream is ordered after everything the side stream did
@@ -398,6 +406,7 @@ struct xo_transit_data {
 
 int xo_transit_data_create(const double *t, const double *y, const double *ivar, int64_t N, int device,
                            xo_transit_data **out) {
+  XO_NVTX_SCOPE("xo_transit_data_create");
   if (!t || !y || !ivar || N <= 0 || !out) return XO_EINVAL;
   int prev = 0;
   XO_TRY(cudaGetDevice(&prev));
@@ -418,8 +427,7 @@ int xo_transit_data_create(const double *t, const double *y, const double *ivar,
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(d->y, y, nb, cudaMemcpyHostToDevice, d->st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d->ivar, ivar, nb, cudaMemcpyHostToDevice, d->st);
-  int rc = e == cudaSuccess ? xo_transit_data_moments(d->t, d->y, d->ivar, N, d->moments, d->st) : -(int)e;
-  if (rc == 0) rc = xo_transit_data_index(d->t, N, d->moments, mom_len, d->st);
+  int rc = e == cudaSuccess ? xo_transit_data_moments_index(d->t, d->y, d->ivar, N, d->moments, mom_len, d->st) : -(int)e;
   if (rc == 0) rc = xo::cuda_status(cudaStreamSynchronize(d->st));
   cudaSetDevice(prev);
   if (rc != 0) {
@@ -431,6 +439,7 @@ int xo_transit_data_create(const double *t, const double *y, const double *ivar,
 }
 
 int xo_transit_data_destroy(xo_transit_data *d) {
+  XO_NVTX_SCOPE("xo_transit_data_destroy");
   if (!d) return 0;
   int prev = 0;
   cudaGetDevice(&prev);
@@ -448,6 +457,7 @@ int xo_transit_model_logp_grad_resident(xo_transit_data *d, const double *par, c
                                         int64_t C, int64_t P, const double *dtk, const double *wk, int K, double texp,
                                         int use_in_transit, double lognorm, int use_moments, double *logp, double *gpar,
                                         double *gstar, double *gmean) {
+  XO_NVTX_SCOPE("xo_transit_model_logp_grad_resident");
   if (!d || C < 0 || P <= 0 || K < 1) return XO_EINVAL;
   if (C == 0) return 0;
   if (!par || !star || !mean || !dtk || !wk || !logp || !gpar || !gstar || !gmean) return XO_EINVAL;

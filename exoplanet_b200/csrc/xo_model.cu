@@ -205,6 +205,7 @@ int xo_transit_model_logp_grad(const double *t, const double *y, const double *i
                                const double *wk, int K, double texp, int use_in_transit, double lognorm,
                                const double *moments, double *logp, double *gpar, double *gstar, double *gmean,
                                void *workspace, size_t workspace_bytes, void *stream) {
+  XO_NVTX_SCOPE("xo_transit_model_logp_grad");
   return xo::model_logp_grad_phases(t, y, ivar, N, par, star, mean, C, P, dtk, wk, K, texp, use_in_transit, lognorm, moments, logp,
                                     gpar, gstar, gmean, workspace, workspace_bytes, stream, 3);
 }
@@ -212,6 +213,7 @@ int xo_transit_model_logp_grad(const double *t, const double *y, const double *i
 // element blocks only (prologue), for callers that want to inspect / reuse them
 int xo_elements_from_params(const double *par, const double *star, int64_t C, int64_t P, double texp, int use_in_transit,
                             double *elem, double *cl, void *stream) {
+  XO_NVTX_SCOPE("xo_elements_from_params");
   if (C < 0 || P < 0) return XO_EINVAL;
   if (P > XO_MAX_PLANETS) return XO_ERANGE;
   if (C == 0 || P == 0) return 0;

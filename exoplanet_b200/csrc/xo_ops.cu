@@ -180,6 +180,7 @@ extern "C" {
 
 int xo_kepler_fwd_bcast(const double *M, const double *e, int64_t e_inner, double *sinf, double *cosf, int64_t n,
                         void *stream) {
+  XO_NVTX_SCOPE("xo_kepler_fwd_bcast");
   if (n < 0 || e_inner < 1) return XO_EINVAL;
   if (n == 0) return 0;
   if (!M || !e || !sinf || !cosf) return XO_EINVAL;
@@ -208,11 +209,13 @@ int xo_kepler_fwd_bcast(const double *M, const double *e, int64_t e_inner, doubl
 }
 
 int xo_kepler_fwd(const double *M, const double *e, double *sinf, double *cosf, int64_t n, void *stream) {
+  XO_NVTX_SCOPE("xo_kepler_fwd");
   return xo_kepler_fwd_bcast(M, e, 1, sinf, cosf, n, stream);
 }
 
 int xo_kepler_vjp(const double *sinf, const double *cosf, const double *e, const double *bsinf, const double *bcosf,
                   double *bM, double *be, int64_t n, void *stream) {
+  XO_NVTX_SCOPE("xo_kepler_vjp");
   if (n < 0) return XO_EINVAL;
   if (n == 0) return 0;
   if (!sinf || !cosf || !e || !bsinf || !bcosf || !bM || !be) return XO_EINVAL;
@@ -230,6 +233,7 @@ int xo_kepler_vjp(const double *sinf, const double *cosf, const double *e, const
 }
 
 int xo_qsv_fwd(const double *b, const double *r, double *s, double *dsdb, double *dsdr, int64_t n, void *stream) {
+  XO_NVTX_SCOPE("xo_qsv_fwd");
   if (n < 0) return XO_EINVAL;
   if (n == 0) return 0;
   if (!b || !r || !s || ((dsdb == nullptr) != (dsdr == nullptr))) return XO_EINVAL;
@@ -243,6 +247,7 @@ int xo_qsv_fwd(const double *b, const double *r, double *s, double *dsdb, double
 }
 
 int xo_qsv_vjp(const double *bs, const double *dsdb, const double *dsdr, double *bb, double *br, int64_t n, void *stream) {
+  XO_NVTX_SCOPE("xo_qsv_vjp");
   if (n < 0) return XO_EINVAL;
   if (n == 0) return 0;
   if (!bs || !dsdb || !dsdr || !bb || !br) return XO_EINVAL;
@@ -254,6 +259,7 @@ int xo_qsv_vjp(const double *bs, const double *dsdb, const double *dsdr, double 
 int xo_contact_points(const double *a, const double *e, const double *cosw, const double *sinw, const double *cosi,
                       const double *sini, const double *L, double *M_left, double *M_right, int32_t *flag, int64_t n,
                       void *stream) {
+  XO_NVTX_SCOPE("xo_contact_points");
   if (n < 0) return XO_EINVAL;
   if (n == 0) return 0;
   if (!a || !e || !cosw || !sinw || !cosi || !sini || !L || !M_left || !M_right || !flag) return XO_EINVAL;

@@ -11,22 +11,22 @@
 // cl [C][3], mean [C]; outputs are O(#params) per chain.
 //
 // Design of the logp+grad kernel (the dominant kernel):
-//  * one CTA = 4 independent warps of one chain, each owning a contiguous cadence range; the
-//    chain's element block, limb-darkening vector and exposure stencil are staged once in
-//    shared memory;
-//  * with the data moments and sorted t the sweep is sparse: steps of 32 cadences are tested 32
-//    at a time (lane l: can step l contain an in-transit cadence of any planet?), one ballot
-//    gives the hit mask and only hit steps are loaded; otherwise every cadence is read, 128 per
-//    step, and the out-of-transit part of the likelihood is accumulated on the way;
-//  * in-window (cadence, planet) pairs are appended (ballot + prefix popcount, i.e. in a fixed
-//    order) to a per-warp, per-planet queue in shared memory; whenever a queue holds >= 32
-//    entries the warp drains 32 of them with all lanes busy on the expensive part (Kepler
-//    solve -> projection -> limb-darkening integral -> analytic VJP);
-//  * per-lane gradient sums live in shared memory and are added up over the warp in a fixed
-//    order once per warp (or when the drained planet changes), so results are bit-reproducible
-//    run to run; a second tiny kernel (or the model epilogue) folds the per-warp partials;
-//  * launched as a programmatic dependent of the model prologue: everything before pdl_wait()
-//    (accumulator zeroing, L2 prefetch of the time stamps) overlaps the prologue's tail.
+//  * one CTA = 4 warps working on one chain and a contiguous part of its cadences; which chain and part comes from
+//    a table every CTA derives from per-chain work estimates (weighted_partition), so that a launch of whole waves
+//    keeps every CTA slot busy with the same amount of work; the chain's element block, limb-darkening vector and
+//    exposure stencil are staged once in shared memory;
+//  * in-transit (cadence, planet) samples are evaluated 32 at a time with all lanes busy on the expensive part
+//    (Kepler solve -> projection -> limb-darkening integral -> analytic VJP).  With the data moments, sorted t and the
+//    time index the CTA enumerates the transit epochs that touch its cadences (one per thread: window -> cadence
+//    range by table look-up), a block scan numbers the samples, and the warps take them 32 at a time; no time stamp
+//    is read, nothing is queued.  Otherwise each warp steps through its cadences (with moments: 32 steps tested per
+//    ballot, only hit steps loaded; without: every cadence read and the out-of-transit Gaussian terms summed on the
+//    way), appends in-window cadences to per-warp, per-planet queues and drains a queue whenever it holds >= 32;
+//  * per-lane gradient sums live in shared memory and are added up over the warp in a fixed order once per warp
+//    (or when the drained planet changes), so results are bit-reproducible run to run; a second tiny kernel (or the
+//    model epilogue) folds the per-warp partials;
+//  * launched as a programmatic dependent of the model prologue: everything before pdl_wait() (accumulator
+//    zeroing) overlaps the prologue's tail.
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -46,6 +46,15 @@ constexpr int kThreads = kWarps * 32;
 using xo::kNBase;
 using xo::Split;
 constexpr unsigned kFull = 0xffffffffu;
+// How the drain of the logp kernel reads its chain's elements (see lc_point): as volatile shared memory, i.e. re-loaded at
+// every use (a broadcast LDS) instead of held in registers across the whole sample evaluation.  That is what lets the kernel
+// fit 128 registers with 36 B of spills (plain pointer: 196 B) and run 4 CTAs per SM: 54.5 -> 52.9 us per 128-chain step,
+// 4.21e6 -> 4.46e6 evals/s at 1024 chains (profiles/r02_tuning_sweep.txt).  -DXO_ELEM_PLAIN restores the plain pointer.
+#ifdef XO_ELEM_PLAIN
+using DrainElemPtr = const double *;
+#else
+using DrainElemPtr = const volatile double *;
+#endif
 
 struct ChainSmem {
   double elem[XO_MAX_PLANETS][XO_NEL];
@@ -576,7 +585,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
         if (self) jself = jq;
         for (int k = 0; k < K; ++k) {
           const double w = sm.wk[k];
-          ltot = fma(w, xo::lc_point<true, kThreads, kDelay>(sm.elem[q], sm.cl, kTtv ? ttq + __dmul_rn(tx, sm.dtk[k]) : ttq + sm.dtk[k],
+          ltot = fma(w, xo::lc_point<true, kThreads, kDelay, DrainElemPtr>(sm.elem[q], sm.cl, kTtv ? ttq + __dmul_rn(tx, sm.dtk[k]) : ttq + sm.dtk[k],
                                                              self ? w : 0.0, gl, gsl), ltot);
         }
       }
@@ -925,7 +934,7 @@ constexpr int kMomThreads = 256;
 constexpr int kMomMaxCtas = (XO_MOMENTS_LEN - 8) / 4;
 __global__ void __launch_bounds__(kMomThreads) transit_moments_kernel(const double *__restrict__ t, const double *__restrict__ y,
                                                                       const double *__restrict__ ivar, int64_t N,
-                                                                      double *__restrict__ out) {
+                                                                      double *__restrict__ out, int nb) {
   __shared__ double red[4][kMomThreads / 32];
   __shared__ double yref_s;
   __shared__ int is_last;
@@ -937,13 +946,39 @@ __global__ void __launch_bounds__(kMomThreads) transit_moments_kernel(const doub
   __syncthreads();
   const double yref = yref_s;
   double s1 = 0.0, sy = 0.0, syy = 0.0, bad = 0.0;
+  // nb > 0: the time index (see TimeIndex below) is built in the same pass -- table[j] = first cadence with t >= edge_j =
+  // tmin + j w: the thread holding (t_i, t_{i+1}) owns the edges in (t_i, t_{i+1}] (-> i + 1), thread 0 also those <= t_0
+  // (-> 0), the last one those > t_{N-1} (-> N).  Meaningless when t is not sorted; the fold below then marks it unusable.
+  const double tmin = __ldg(t), bw = nb > 0 ? (__ldg(t + N - 1) - tmin) / (double)nb : 0.0;
+  const bool build = nb > 0 && bw > 0.0 && isfinite(bw);
+  const double inv_bw = build ? 1.0 / bw : 0.0;
+  uint32_t *table = reinterpret_cast<uint32_t *>(out + XO_MOMENTS_LEN);
+  auto edges_le = [&](double x) {  // number of edges j in [0, nb] with edge_j <= x (edge_j as index_bound computes it)
+    const double u = (x - tmin) * inv_bw;
+    int e = !(u >= 0.0) ? 0 : (u >= (double)nb ? nb + 1 : (int)u + 1);
+    while (e <= nb && fma((double)e, bw, tmin) <= x) ++e;
+    while (e > 0 && fma((double)(e - 1), bw, tmin) > x) --e;
+    return e;
+  };
   const int64_t stride = (int64_t)gridDim.x * kMomThreads;
   for (int64_t i = (int64_t)blockIdx.x * kMomThreads + threadIdx.x; i < N; i += stride) {
     const double w = __ldg(ivar + i), d = __ldg(y + i) - yref;
     s1 += w;
     sy = fma(w, d, sy);
     syy = fma(w * d, d, syy);
-    if (i + 1 < N && !(__ldg(t + i + 1) >= __ldg(t + i))) bad += 1.0;
+    const double ti = __ldg(t + i), tn = i + 1 < N ? __ldg(t + i + 1) : ti;
+    if (!(tn >= ti)) bad += 1.0;
+    if (build && tn >= ti) {
+      const int e0 = min(edges_le(ti), nb);  // the last edge (= t_{N-1} up to rounding) always maps to N, as in transit_index_kernel
+      if (i == 0)
+        for (int j = 0; j < e0; ++j) table[j] = 0u;
+      if (i + 1 < N) {
+        const int e1 = min(edges_le(tn), nb);
+        for (int j = e0; j < e1; ++j) table[j] = (uint32_t)(i + 1);
+      } else {
+        for (int j = e0; j <= nb; ++j) table[j] = (uint32_t)N;
+      }
+    }
   }
   double v4[4] = {s1, sy, syy, bad};
 #pragma unroll
@@ -977,7 +1012,8 @@ __global__ void __launch_bounds__(kMomThreads) transit_moments_kernel(const doub
     out[2] = f4[1];
     out[3] = f4[2];
     out[4] = f4[3] == 0.0 ? 1.0 : 0.0;
-    out[5] = out[6] = 0.0;
+    out[5] = (build && f4[3] == 0.0) ? (double)nb : 0.0;  // the sweep only trusts the table of a sorted series
+    out[6] = (build && f4[3] == 0.0) ? inv_bw : 0.0;
     *ticket = 0u;
     reinterpret_cast<unsigned *>(out + 7)[1] = 0u;
   }
@@ -1181,7 +1217,7 @@ static int env_int(const char *name, int dflt) {
   return v && *v ? atoi(v) : dflt;
 }
 int transit_min_blocks() {
-  static int v = env_int("XO_TRANSIT_MINBLOCKS", 3);
+  static int v = env_int("XO_TRANSIT_MINBLOCKS", 4);  // 128 registers, 4 CTAs per SM (see DrainElemPtr); 3 = 168 registers
   return v;
 }
 static int transit_warps_per_sm() {
@@ -1213,7 +1249,7 @@ Split split_transit(int64_t N, int64_t C) {
 // the device and how many each gets decides the balance (128 chains: 61.8 -> 56.7 us per step).  With more chains than slots
 // the hardware's dynamic CTA dispatch evens the load out by itself and the table only costs (1024 chains: 4.2e6 evals/s with
 // two CTAs per chain, 3.7e6 weighted; profiles/r02_tuning_sweep.txt).
-static int64_t transit_wave() { return (int64_t)sm_count() * transit_min_blocks(); }  // resident CTAs (3 per SM at 168 registers)
+static int64_t transit_wave() { return (int64_t)sm_count() * transit_min_blocks(); }  // resident CTAs (4 per SM at 128 registers)
 
 bool transit_weighted(int64_t C, int64_t P) {
   static const int mode = env_int("XO_TRANSIT_WEIGHTED", -1);  // 0: never, 1: whenever the table fits, default: see above
@@ -1331,6 +1367,7 @@ extern "C" {
 
 int xo_transit_lc_fwd(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
                       const double *dtk, const double *wk, int K, double *lc, void *stream) {
+  XO_NVTX_SCOPE("xo_transit_lc_fwd");
   if (int rc = check_batch(N, C, P)) return rc;
   if (K < 1 || K > XO_MAX_STENCIL) return XO_ERANGE;
   if (N == 0 || C == 0 || P == 0) return 0;
@@ -1343,6 +1380,7 @@ int xo_transit_lc_fwd(const double *t, int64_t N, const double *elem, const doub
 int xo_transit_lc_fwd_ex(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
                          const double *dtk, const double *wk, int K, const double *ttv_times, const int *ttv_count, int ttv_nt,
                          int light_delay, const double *texp_vec, double *lc, void *stream) {
+  XO_NVTX_SCOPE("xo_transit_lc_fwd_ex");
   if (int rc = check_batch(N, C, P)) return rc;
   if (K < 1 || K > XO_MAX_STENCIL) return XO_ERANGE;
   if (N == 0 || C == 0 || P == 0) return 0;
@@ -1362,13 +1400,30 @@ size_t xo_transit_logp_grad_workspace(int64_t N, int64_t C, int64_t P) {
 
 int xo_transit_data_moments(const double *t, const double *y, const double *ivar, int64_t N, double *moments,
                             void *stream) {
+  XO_NVTX_SCOPE("xo_transit_data_moments");
   if (N <= 0 || !t || !y || !ivar || !moments) return XO_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaMemsetAsync(moments + 7, 0, sizeof(double), st);  // the arrival ticket
   if (e != cudaSuccess) return -(int)e;
   const int64_t want = (N + 4 * kMomThreads - 1) / (4 * kMomThreads);
   const int ctas = (int)(want < 1 ? 1 : want > kMomMaxCtas ? kMomMaxCtas : want);
-  xo::launch(transit_moments_kernel, ctas, kMomThreads, 0, st, t, y, ivar, N, moments);
+  xo::launch(transit_moments_kernel, ctas, kMomThreads, 0, st, t, y, ivar, N, moments, 0);
+  return xo::launch_status();
+}
+
+// moments and time index in ONE pass over the data (what xo_transit_data_moments + xo_transit_data_index give in two)
+int xo_transit_data_moments_index(const double *t, const double *y, const double *ivar, int64_t N, double *moments, size_t moments_len,
+                                  void *stream) {
+  XO_NVTX_SCOPE("xo_transit_data_moments_index");
+  if (N <= 0 || !t || !y || !ivar || !moments) return XO_EINVAL;
+  if (N >= ((int64_t)1 << 32)) return XO_ERANGE;
+  if (moments_len < xo_transit_moments_len(N)) return XO_EWORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(moments + 7, 0, sizeof(double), st);  // the arrival ticket
+  if (e != cudaSuccess) return -(int)e;
+  const int64_t want = (N + 4 * kMomThreads - 1) / (4 * kMomThreads);
+  const int ctas = (int)(want < 1 ? 1 : want > kMomMaxCtas ? kMomMaxCtas : want);
+  xo::launch(transit_moments_kernel, ctas, kMomThreads, 0, st, t, y, ivar, N, moments, index_bins(N));
   return xo::launch_status();
 }
 
@@ -1378,6 +1433,7 @@ size_t xo_transit_moments_len(int64_t N) {
 }
 
 int xo_transit_data_index(const double *t, int64_t N, double *moments, size_t moments_len, void *stream) {
+  XO_NVTX_SCOPE("xo_transit_data_index");
   if (N <= 0 || !t || !moments) return XO_EINVAL;
   if (N >= ((int64_t)1 << 32)) return XO_ERANGE;
   if (moments_len < xo_transit_moments_len(N)) return XO_EWORKSPACE;
@@ -1390,6 +1446,7 @@ int xo_transit_logp_grad(const double *t, const double *y, const double *ivar, i
                          const double *cl, const double *mean, int64_t C, int64_t P, const double *dtk, const double *wk,
                          int K, double lognorm, const double *moments, double *logp, double *gel, double *gcl,
                          double *gmean, void *workspace, size_t workspace_bytes, void *stream) {
+  XO_NVTX_SCOPE("xo_transit_logp_grad");
   if (int rc = check_batch(N, C, P)) return rc;
   if (K < 1 || K > XO_MAX_STENCIL) return XO_ERANGE;
   if (C == 0) return 0;
@@ -1411,6 +1468,7 @@ int xo_transit_logp_grad(const double *t, const double *y, const double *ivar, i
 int xo_transit_lc_vjp(const double *t, int64_t N, const double *elem, const double *cl, int64_t C, int64_t P,
                       const double *dtk, const double *wk, int K, const double *bar_lc, double *gel, double *gcl,
                       void *workspace, size_t workspace_bytes, void *stream) {
+  XO_NVTX_SCOPE("xo_transit_lc_vjp");
   if (int rc = check_batch(N, C, P)) return rc;
   if (K < 1 || K > XO_MAX_STENCIL) return XO_ERANGE;
   if (C == 0) return 0;
@@ -1434,6 +1492,7 @@ int xo_transit_logp_grad_ttv(const double *t, const double *y, const double *iva
                              int K, double lognorm, const double *moments, const double *ttv_times, const int *ttv_count,
                              int ttv_nt, double *logp, double *gel, double *gcl, double *gmean, double *gttv, void *workspace,
                              size_t workspace_bytes, void *stream) {
+  XO_NVTX_SCOPE("xo_transit_logp_grad_ttv");
   if (int rc = check_batch(N, C, P)) return rc;
   if (K < 1 || K > XO_MAX_STENCIL) return XO_ERANGE;
   if (C == 0) return 0;
@@ -1465,6 +1524,7 @@ int xo_transit_lc_vjp_ex(const double *t, int64_t N, const double *elem, const d
                          const double *dtk, const double *wk, int K, const double *ttv_times, const int *ttv_count, int ttv_nt,
                          int light_delay, const double *texp_vec, const double *bar_lc, double *gel, double *gcl, double *gttv,
                          void *workspace, size_t workspace_bytes, void *stream) {
+  XO_NVTX_SCOPE("xo_transit_lc_vjp_ex");
   if (int rc = check_batch(N, C, P)) return rc;
   if (K < 1 || K > XO_MAX_STENCIL) return XO_ERANGE;
   if (C == 0) return 0;
@@ -1499,6 +1559,7 @@ int xo_transit_lc_vjp_ex(const double *t, int64_t N, const double *elem, const d
 
 int xo_orbit_eval(const double *t, int64_t N, const double *elem, int64_t C, int64_t P, double *X, double *Y, double *Z,
                   double *rv, void *stream) {
+  XO_NVTX_SCOPE("xo_orbit_eval");
   if (int rc = check_batch(N, C, P)) return rc;
   if (N == 0 || C == 0 || P == 0) return 0;
   if (!t || !elem) return XO_EINVAL;
@@ -1521,6 +1582,7 @@ size_t xo_rv_logp_grad_workspace(int64_t N, int64_t C, int64_t P) {
 int xo_rv_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *elem,
                     const double *gamma, int64_t C, int64_t P, double lognorm, double *logp, double *grv, double *ggamma,
                     void *workspace, size_t workspace_bytes, void *stream) {
+  XO_NVTX_SCOPE("xo_rv_logp_grad");
   if (int rc = check_batch(N, C, P)) return rc;
   if (C == 0) return 0;
   if (N == 0 || P == 0) return XO_EINVAL;

@@ -105,16 +105,18 @@ class TransitData:
     def moments(self, index=True):
         """Device tensor (y_ref, sum ivar, sum ivar (y - y_ref), sum ivar (y - y_ref)^2, t_is_sorted, n_bins, 1/w, ...):
         the data-only part of the Gaussian sums (xo_transit_data_moments) followed, for sorted t, by the
-        time -> cadence index the sweep uses instead of reading time stamps (xo_transit_data_index); computed once."""
+        time -> cadence index the sweep uses instead of reading time stamps (xo_transit_data_moments_index); computed once."""
         if self._moments is None and self.y is not None and self.ivar is not None:
             lib = _lib.require_cuda()
             n = lib.xo_transit_moments_len(self.n) if index else MOMENTS_LEN
             m = torch.zeros(n, dtype=torch.float64, device=self.device)
             with torch.cuda.device(self.device):
-                _lib.check(lib.xo_transit_data_moments(_ptr(self.t), _ptr(self.y), _ptr(self.ivar), self.n, _ptr(m), _lib.stream_ptr()),
-                           "moments")
-                if index:
-                    _lib.check(lib.xo_transit_data_index(_ptr(self.t), self.n, _ptr(m), n, _lib.stream_ptr()), "index")
+                if index:  # moments and time index in one pass over the data
+                    _lib.check(lib.xo_transit_data_moments_index(_ptr(self.t), _ptr(self.y), _ptr(self.ivar), self.n, _ptr(m), n,
+                                                                 _lib.stream_ptr()), "moments+index")
+                else:
+                    _lib.check(lib.xo_transit_data_moments(_ptr(self.t), _ptr(self.y), _ptr(self.ivar), self.n, _ptr(m), _lib.stream_ptr()),
+                               "moments")
             self._moments = m
         return self._moments
 

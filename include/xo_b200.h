@@ -129,6 +129,10 @@ int xo_transit_data_moments(const double *t, const double *y, const double *ivar
  * testing time stamps (same result, same evaluated set).  A block without the index (moments[5] = 0) keeps working. */
 size_t xo_transit_moments_len(int64_t N); /* in doubles */
 int xo_transit_data_index(const double *t, int64_t N, double *moments, size_t moments_len, void *stream);
+/* both in ONE pass over the data (the index costs a few integer operations per cadence on top of the moments' loads): what
+ * the per-call host entry points and the resident data handle use */
+int xo_transit_data_moments_index(const double *t, const double *y, const double *ivar, int64_t N, double *moments,
+                                  size_t moments_len, void *stream);
 int xo_transit_logp_grad(const double *t, const double *y, const double *ivar, int64_t N, const double *elem,
                          const double *cl, const double *mean, int64_t C, int64_t P, const double *dtk, const double *wk,
                          int K, double lognorm, const double *moments, double *logp, double *gel, double *gcl,

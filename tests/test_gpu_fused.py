@@ -411,6 +411,43 @@ def test_host_entry_point_from_two_threads():
             assert np.array_equal(a, b)
 
 
+def test_one_pass_index_equals_the_standalone_index_kernel():
+    """the time index built inside the moments pass (xo_transit_data_moments_index) == the one the standalone kernel builds
+    by one binary search per bin (xo_transit_data_index), entry for entry: long gaps (one thread owns thousands of edges),
+    repeated time stamps, two cadences"""
+    import ctypes as C
+
+    from exoplanet_b200 import _lib
+
+    lib = _lib.require_cuda()
+    rng = np.random.default_rng(5)
+    for N in (2, 3, 4097, 60000):
+        t = np.cumsum(rng.uniform(0.01, 0.03, N))
+        if N > 1000:
+            t[N // 3:] += 400.0   # a long gap
+            t[N // 2:] += 0.5
+            t[100:110] = t[100]   # repeated stamps
+        y = 1.0 + 5e-4 * rng.normal(size=N)
+        ivar = np.full(N, 4e6)
+        tt, yy, vv = dev(t), dev(y), dev(ivar)
+        n = lib.xo_transit_moments_len(N)
+        a = torch.zeros(n, dtype=torch.float64, device=DEV)
+        b_ = torch.zeros(n, dtype=torch.float64, device=DEV)
+        ptr = lambda x: C.c_void_p(x.data_ptr())  # noqa: E731
+        assert lib.xo_transit_data_moments_index(ptr(tt), ptr(yy), ptr(vv), N, ptr(a), n, _lib.stream_ptr()) == 0
+        assert lib.xo_transit_data_moments(ptr(tt), ptr(yy), ptr(vv), N, ptr(b_), _lib.stream_ptr()) == 0
+        assert lib.xo_transit_data_index(ptr(tt), N, ptr(b_), n, _lib.stream_ptr()) == 0
+        a, b_ = a.cpu().numpy(), b_.cpu().numpy()
+        nb = int(a[5])
+        assert nb == int(b_[5]) == max(N // 2, 1) and a[6] == b_[6]
+        assert np.array_equal(a[:7], b_[:7])
+        ta, tb = a[1024:].view(np.uint32)[: nb + 1], b_[1024:].view(np.uint32)[: nb + 1]
+        assert np.array_equal(ta, tb), (N, np.flatnonzero(ta != tb)[:10])
+        # a block too short for the table is refused (XO_EWORKSPACE = 3), nothing is written
+        assert lib.xo_transit_data_moments_index(ptr(tt), ptr(yy), ptr(vv), N, ptr(torch.zeros(1024, dtype=torch.float64, device=DEV)), 1024,
+                                                 _lib.stream_ptr()) == 3
+
+
 @pytest.mark.parametrize("case", ["gaps", "short_period", "flag_window", "wide_window", "three_planets", "tiny", "unsorted", "texp"])
 def test_indexed_sweep_edge_cases(case):
     """the epoch-enumerating sweep (time index) against the oracle where its bookkeeping could go wrong: irregular

@@ -11,6 +11,7 @@ mkdir -p $OUT
 NCU_FULL="ncu --set full --metrics smsp__inst_executed_pipe_fp64.sum --clock-control none --import-source on"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_gpu.txt 2>&1
 lscpu | grep -E "Model name|^CPU\(s\)|Thread|Core|Socket" >> $OUT/${TAG}_gpu.txt; nproc >> $OUT/${TAG}_gpu.txt
+(echo -n "cgroup cpu.max: "; cat /sys/fs/cgroup/cpu.max 2>/dev/null || cat /sys/fs/cgroup/cpu/cpu.cfs_quota_us 2>/dev/null; grep Cpus_allowed_list /proc/self/status; uptime) >> $OUT/${TAG}_gpu.txt 2>&1
 
 run_pytest() { # name, args...
   local name=$1; shift
