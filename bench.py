@@ -189,10 +189,25 @@ def cpu_port_setup(t, p, truth):
     return O, y, dtk, wk
 
 
+def _cpu_quota():
+    """CPUs the cgroup lets this container use (CFS quota / period), or None when unlimited / unknown"""
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        return None if q == "max" else float(q) / float(per)
+    except (OSError, ValueError):
+        pass
+    try:
+        q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        return None if q <= 0 else q / per
+    except (OSError, ValueError):
+        return None
+
+
 def _host_state(load_before=None):
     """what else competes for the host's cores while the CPU arm is timed (the GPU boxes are shared): load averages, the
     cgroup's CPU quota and the CPUs this process may run on"""
-    out = {"loadavg_after": [round(x, 1) for x in os.getloadavg()]}
+    out = {"loadavg_after": [round(x, 1) for x in os.getloadavg()], "cpu_quota": _cpu_quota()}
     if load_before is not None:
         out["loadavg_before"] = [round(x, 1) for x in load_before]
     for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
@@ -273,7 +288,7 @@ def arm_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": bench_config(nc, args.gpus),
         "cpu_baseline": {"value": val, "unit": "evals/s", "cores": threads, "kind": "port",
-                         "sample": "%d passes over %d chains x N=1e5 per step (OpenMP over chains x 8 cadence blocks, pinned), %d steps, %.2f s timed; "
+                         "sample": "%d passes over %d chains x N=1e5 per step (OpenMP over chains x 8 cadence blocks), %d steps, %.2f s timed; "
                                    "value from the median step" % (inner, nc, args.steps, float(per.sum())),
                          "value_mean": nc * inner / mean, "value_best": nc * inner / best,
                          "step_time_spread": float((per.max() - per.min()) / med),
@@ -1003,8 +1018,17 @@ def main():
         # the host threads it can use", run by rank 0 alone: drop that default so the OpenMP team spans the machine
         if ("TORCHELASTIC_RUN_ID" in os.environ or "LOCAL_RANK" in os.environ) and os.environ.get("OMP_NUM_THREADS") == "1":
             del os.environ["OMP_NUM_THREADS"]
-        os.environ.setdefault("OMP_PROC_BIND", "close")
-        os.environ.setdefault("OMP_PLACES", "cores")
+        quota = _cpu_quota()
+        if quota is not None and quota < (os.cpu_count() or 1) / 2 and "OMP_NUM_THREADS" not in os.environ:
+            # a container with a CFS quota below the core count (the GPU boxes of this pool: 16 CPUs of 128): a team larger than
+            # the quota is throttled by the scheduler in the middle of its parallel regions (and spinning idle threads burn the
+            # quota) -- the 2x spread and the 9x-over-one-thread "scaling" of the 64-thread runs.  One thread per quota CPU,
+            # placed by the kernel (the first 16 cores are not ours alone).
+            os.environ["OMP_NUM_THREADS"] = str(max(1, int(quota)))
+            os.environ.setdefault("OMP_PROC_BIND", "false")
+        else:
+            os.environ.setdefault("OMP_PROC_BIND", "close")
+            os.environ.setdefault("OMP_PLACES", "cores")
         os.environ.setdefault("OMP_WAIT_POLICY", "active")
         arm_reference(args)
     else:
