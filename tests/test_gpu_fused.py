@@ -510,3 +510,46 @@ def test_indexed_sweep_edge_cases(case):
     assert np.max(np.abs(gel.cpu().numpy() - geo) / scale) < 1e-10
     assert np.max(np.abs(gcl.cpu().numpy() - gco) / (np.abs(gco).max() + 1e-300)) < 1e-10
     assert np.max(np.abs(gmean.cpu().numpy() - gmo) / np.abs(gmo).max()) < 1e-10
+
+
+@pytest.mark.parametrize("C,P,N", [(2, 1, 40000), (300, 1, 20000), (512, 8, 3000), (513, 1, 6000), (40, 3, 100000)])
+def test_work_partition_shapes(C, P, N):
+    """the weighted partition of the logp launch (CTAs dealt to the chains by expected in-transit work, xo_transit.cu
+    weighted_partition) in its different regimes -- two chains sharing the whole device very unevenly, more than one wave,
+    four chains per thread of the table with eight planets each, one chain too many for the table (uniform split), many CTAs
+    per chain on the full-size series -- against the element-level launch (uniform split) of the same elements, and the
+    oracle on a few chains"""
+    import ctypes as Ct
+
+    from exoplanet_b200 import _lib
+
+    p = synthetic.transit_params(C, P, seed=300 + C)
+    if C == 2:  # one chain in transit almost always, the other almost never
+        p["period"][0, 0], p["b"][0, 0], p["ror"][0, 0], p["ecc"][0, 0] = 3.0, 0.0, 0.12, 0.0
+        p["period"][1, 0], p["b"][1, 0], p["ror"][1, 0] = 29.0, 0.85, 0.03
+    t = synthetic.cadence_times(N)
+    y = synthetic.noise(N)
+    data = fused.TransitData(t, y, np.full(N, 5e-4), device=DEV)
+    par = fused.pack_params(dev(p["period"]), dev(p["t0"]), dev(p["ecc"]), dev(p["omega"]), dev(p["b"]), dev(p["ror"]),
+                            dev(p["m_planet"]), dev(p["K"]))
+    star = fused.pack_star(torch.ones(C, dtype=torch.float64, device=DEV), torch.ones(C, dtype=torch.float64, device=DEV), dev(p["u1"]),
+                           dev(p["u2"]))
+    mean = dev(p["mean"])
+    logp, gpar, gstar, gmean = fused.TransitModel(data).logp_grad(par, star, mean)
+    elem = torch.empty((C, P, 16), dtype=torch.float64, device=DEV)
+    clk = torch.empty((C, 3), dtype=torch.float64, device=DEV)
+    assert _lib.load().xo_elements_from_params(Ct.c_void_p(par.data_ptr()), Ct.c_void_p(star.data_ptr()), C, P, 0.0, 1,
+                                               Ct.c_void_p(elem.data_ptr()), Ct.c_void_p(clk.data_ptr()), None) == 0
+    lp2, gel2, gcl2, gm2 = fused.transit_logp_grad(data, elem, clk, mean, fused.exposure_stencil(None))
+    assert torch.allclose(logp, lp2, rtol=1e-12, atol=0), ((logp - lp2).abs() / lp2.abs()).max()
+    assert torch.allclose(gmean, gm2, rtol=1e-9, atol=1e-9 * gm2.abs().max().item())
+    again = fused.TransitModel(data).logp_grad(par, star, mean)
+    for a, b in zip((logp, gpar, gstar, gmean), again):
+        assert torch.equal(a, b)  # the partition is a deterministic function of the parameters
+    sel = np.unique(np.linspace(0, C - 1, 3).astype(int))
+    el_o = O.elements_from_params(p["period"][sel], p["t0"][sel], p["ecc"][sel], p["omega"][sel], p["b"][sel], p["ror"][sel],
+                                  m_planet=p["m_planet"][sel])
+    lo, _, _, gmo = O.transit_logp_grad(t, y, np.full(N, 1 / 5e-4 ** 2), el_o, O.get_cl(p["u1"][sel], p["u2"][sel]), p["mean"][sel],
+                                        *O.stencil(None), lognorm=data.lognorm)
+    assert np.max(np.abs(logp.cpu().numpy()[sel] - lo) / np.abs(lo)) < 1e-10
+    assert np.max(np.abs(gmean.cpu().numpy()[sel] - gmo) / np.abs(gmo).max()) < 1e-9

@@ -106,12 +106,15 @@ final)
   bench_line ours --steps 20 --warmup 5
   bench_line ref1 --impl reference --steps 20 --warmup 5
   bench_line ref2 --impl reference --steps 20 --warmup 5
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"transit_|model_|kepler_fwd|fold_|gp_|rv_" -c 200 --csv --log-file $OUT/${TAG}_launches.csv \
-      python bench.py --steps 5 --warmup 3 --no-cpu > $OUT/${TAG}_ncu_bench.log 2>&1
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"transit_|model_|kepler_fwd|fold_|gp_|rv_|hmc_|posterior_" -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
+      python bench.py --steps 5 --warmup 3 --no-cpu --extra c2,gp,hmc > $OUT/${TAG}_ncu_bench.log 2>&1
   capture transit transit_logp_grad_kernel 3 --steps 2 --warmup 3 --no-cpu --no-kepler --no-extra
   capture kepler kepler_fwd_kernel 4 --steps 1 --warmup 3 --no-cpu --no-extra
-  capture rv rv_logp_grad_kernel 4 --steps 1 --warmup 3 --no-cpu --no-kepler
-  capture gp "gp_" 0 --steps 1 --warmup 3 --no-cpu --no-kepler
+  capture rv rv_logp_grad_kernel 4 --steps 1 --warmup 3 --no-cpu --no-kepler --extra c2
+  capture gpagg "gp_aggregate_kernel" 27 --steps 1 --warmup 3 --no-cpu --no-kepler --extra gp
+  capture gpll "gp_loglike_kernel" 27 --steps 1 --warmup 3 --no-cpu --no-kepler --extra gp
+  capture gpgagg "gp_grad_aggregate_kernel" 14 --steps 1 --warmup 3 --no-cpu --no-kepler --extra gp
+  capture gpgfin "gp_grad_final_kernel" 14 --steps 1 --warmup 3 --no-cpu --no-kepler --extra gp
   timeout 600 compute-sanitizer --tool memcheck --report-api-errors no --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_memcheck.log 2>&1; echo "memcheck exit $?" >> $OUT/${TAG}_memcheck.log
   timeout 600 compute-sanitizer --tool racecheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_racecheck.log 2>&1; echo "racecheck exit $?" >> $OUT/${TAG}_racecheck.log
   ;;
