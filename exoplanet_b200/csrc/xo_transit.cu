@@ -467,11 +467,23 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
   for (int j = 0; j < XO_NGRAD + 3; ++j) lacc[j][threadIdx.x] = 0.0;
 #pragma unroll
   for (int j = 0; j < XO_NGRAD; ++j) pacc[j][threadIdx.x] = 0.0;
-  // (data only, so legal before the wait) with the time index the sweep reads no time stamps: nothing to pull in
-  if (!weighted && !(kMoments && moments[5] != 0.0)) {
-    const int64_t s0 = ((int64_t)blockIdx.x * kWarps + warp) * L;
-    const uint32_t pa0 = (uint32_t)min(s0, N), pa1 = (uint32_t)min(s0 + L, N);
-    for (uint32_t i = pa0 + 16u * lane; i < pa1; i += 16u * 32u) xo::prefetch_l2(t + i);
+  // (data only, so legal before the wait) Pull the light curve and the time index into L2 while the preceding kernel is
+  // still deriving the elements: every line of them is touched by some chain of the launch (ncu: 2.7 MB of DRAM reads per
+  // launch = t, y, ivar and the table once), and what would be a chain of dependent cold misses at the start of each CTA
+  // (window -> table entry -> time stamp -> sample) becomes L2 hits.  The launch's threads share the lines evenly.
+  {
+    const int64_t gthreads = (int64_t)gridDim.x * gridDim.y * kThreads;
+    const int64_t gtid = ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * kThreads + threadIdx.x;
+    const int64_t nl = (N * 8 + 127) / 128;  // 128-byte lines per array
+    auto pull = [&](const double *base, int64_t lines) {
+      for (int64_t i = gtid; i < lines; i += gthreads) xo::prefetch_l2(reinterpret_cast<const char *>(base) + i * 128);
+    };
+    pull(t, nl);
+    if (!kVjp) {
+      pull(y, nl);
+      pull(ivar, nl);
+    }
+    if (kMoments) pull(moments, (XO_MOMENTS_LEN * 8 + ((int64_t)moments[5] + 1) * 4 + 127) / 128);
   }
   xo::pdl_wait();
   // which chain, and which part of its cadences, this CTA works on
