@@ -322,8 +322,8 @@ constexpr int kQueueMax = 32 * (4 + 1);  // 31 left over + kUnroll * 32 new entr
 // the cadence range of each (rlo, count) and the exclusive prefix of the counts -- entry e of the batch is cadence
 // rlo[r] + e - roff[r] with r the last range whose offset is <= e (drains look it up; nothing is queued).
 struct CtaIndexState {
-  uint32_t rlo[kThreads], roff[kThreads + 1];
-  uint32_t wtot[kWarps];
+  uint32_t rlo[kThreads], roff[kThreads];
+  alignas(16) uint32_t wtot[kWarps];  // own 16 bytes: the compiler reads the four totals with one vector load
   long long kfirst[XO_MAX_PLANETS], kend[XO_MAX_PLANETS];  // per planet: first / last epoch that can touch this CTA's cadences
 };
 
@@ -758,7 +758,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) transit_logp_grad_kernel
         }
         cix.rlo[threadIdx.x] = lo;
         cix.roff[threadIdx.x] = base + inc - rc;
-        if (threadIdx.x == 0) cix.roff[kThreads] = btot;
         __syncthreads();
         pb = p;
         pe = p + 1;
