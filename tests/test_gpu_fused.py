@@ -553,3 +553,25 @@ def test_work_partition_shapes(C, P, N):
                                         *O.stencil(None), lognorm=data.lognorm)
     assert np.max(np.abs(logp.cpu().numpy()[sel] - lo) / np.abs(lo)) < 1e-10
     assert np.max(np.abs(gmean.cpu().numpy()[sel] - gmo) / np.abs(gmo).max()) < 1e-9
+
+
+@pytest.mark.parametrize("use_moments,use_in_transit", [(False, True), (True, False), (False, False)])
+def test_parameter_level_model_options_agree(use_moments, use_in_transit):
+    """the parameter-level model with the data moments switched off (every cadence read and summed in the sweep: the
+    stepping producer under the weighted partition, whose weights then include the sweep itself) and / or with the
+    in-transit window switched off (every cadence evaluated, keplerian.py:155-157) == the default evaluation"""
+    N, C, P = 20000, 12, 2
+    p = synthetic.transit_params(C, P, seed=91)
+    t = synthetic.cadence_times(N)
+    y = synthetic.noise(N)
+    data = fused.TransitData(t, y, np.full(N, 5e-4), device=DEV)
+    par = fused.pack_params(dev(p["period"]), dev(p["t0"]), dev(p["ecc"]), dev(p["omega"]), dev(p["b"]), dev(p["ror"]),
+                            dev(p["m_planet"]), dev(p["K"]))
+    one = torch.ones(C, dtype=torch.float64, device=DEV)
+    star = fused.pack_star(one, one, dev(p["u1"]), dev(p["u2"]))
+    mean = dev(p["mean"])
+    ref = fused.TransitModel(data).logp_grad(par, star, mean)
+    got = fused.TransitModel(data, use_moments=use_moments, use_in_transit=use_in_transit).logp_grad(par, star, mean)
+    assert torch.allclose(got[0], ref[0], rtol=1e-11, atol=0)
+    for a, b in zip(got[1:], ref[1:]):
+        assert torch.allclose(a, b, rtol=1e-8, atol=1e-9 * b.abs().max().item())
