@@ -585,8 +585,10 @@ def _extra_hmc(lib, dev, d, flush, out, O, t, y):
     # ---- the NUTS driver on the same posterior: doublings as CUDA graphs against one launch per tensor op
     from exoplanet_b200.sampling import BatchedNUTS
 
-    for mode, use_graph in (("one CUDA graph per doubling", True), ("eager launches", False)):
-        nuts = BatchedNUTS(post, q_init, step_size=1e-6, max_depth=4, seed=2, use_graph=use_graph)
+    for mode, use_graph, fused_tree in (("tree kernels (xo_nuts_*), one CUDA graph per doubling", True, True),
+                                        ("tensor operations, one CUDA graph per doubling", True, False),
+                                        ("tensor operations, eager launches", False, False)):
+        nuts = BatchedNUTS(post, q_init, step_size=1e-6, max_depth=4, seed=2, use_graph=use_graph, fused_tree=fused_tree)
         for _ in range(2):
             nuts.transition()
         torch.cuda.synchronize()

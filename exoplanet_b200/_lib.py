@@ -75,6 +75,11 @@ _SIGNATURES = {
     "xo_transit_posterior_workspace": (_sz, [_i64, _i64, _i64]),
     "xo_transit_posterior_logp_grad": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _i32, _dbl, _i32, _dbl, _vp,
                                               _vp, _vp, _sz, _vp]),
+    "xo_nuts_state_layout": (_sz, [_i64, _i32, _i32, _vp]),
+    "xo_nuts_start": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "xo_nuts_leaf_pre": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "xo_nuts_leaf_post": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "xo_nuts_merge": (_i32, [_vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "xo_hmc_transition": (_i32, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _i32, _dbl, _i32, _dbl, _vp, _vp, _vp, _vp, _vp,
                                  _i32, C.c_ulonglong, C.c_ulonglong, _vp, _vp, _vp, _sz, _vp]),
     "xo_kepler_host": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32]),

@@ -324,7 +324,11 @@ class BatchedNUTS(BatchedHMC):
 
     Extra state after a transition: ``depth[C]`` (doublings used), ``diverging[C]``, ``n_leapfrog``."""
 
-    def __init__(self, logp_grad, q0, step_size=1e-2, max_depth=8, seed=0, target_accept=0.8, use_graph=True):
+    _SCALARS = ("h0", "log_w", "lp_prop", "active", "depth", "diverged", "acc_sum", "n_leaves", "dh_max", "sgn", "sub_ok", "s_logw", "s_lp",
+                "go_right")
+    _VECTORS = ("ql", "pl", "gl", "qr", "pr", "gr", "q_prop", "g_prop", "p_sum", "q", "p", "g", "s_q", "s_g", "s_psum")
+
+    def __init__(self, logp_grad, q0, step_size=1e-2, max_depth=8, seed=0, target_accept=0.8, use_graph=True, fused_tree=None):
         super().__init__(logp_grad, q0, step_size=step_size, n_leapfrog=1, seed=seed, target_accept=target_accept, use_graph=False)
         self.max_depth = int(max_depth)
         C, D = self.q.shape
@@ -338,11 +342,31 @@ class BatchedNUTS(BatchedHMC):
         # the device once per doubling ("is any chain still growing?"), exactly as without graphs.
         self._nuts_graph = bool(use_graph) and dev.type == "cuda"
         self._pieces = {}
+        # fused_tree (default on CUDA, float64): the tree bookkeeping of a doubling runs in the library's NUTS kernels
+        # (csrc/xo_nuts.cu: two launches per leaf instead of ~50 tensor operations); the tensor code below stays as the
+        # CPU path and as the implementation the kernels are checked against (same uniforms -> same states).
+        self._fused_tree = (dev.type == "cuda" and dt == torch.float64) if fused_tree is None else bool(fused_tree)
         z = lambda *shape, dtype=dt: torch.zeros(shape, dtype=dtype, device=dev)  # noqa: E731
-        self._t = dict(h0=z(C), ql=z(C, D), pl=z(C, D), gl=z(C, D), qr=z(C, D), pr=z(C, D), gr=z(C, D), q_prop=z(C, D), lp_prop=z(C),
-                       g_prop=z(C, D), p_sum=z(C, D), log_w=z(C), active=z(C, dtype=torch.bool), depth=z(C, dtype=torch.int64),
-                       diverged=z(C, dtype=torch.bool), acc_sum=z(C), n_leaves=z(C), dh_max=z(C),
-                       ck_p=z(self.max_depth + 1, C, D), ck_s=z(self.max_depth + 1, C, D))
+        if self._fused_tree:
+            import ctypes as C_
+
+            from . import _lib
+
+            lib = _lib.require_cuda()
+            offs = (C_.c_int64 * 31)()
+            n = lib.xo_nuts_state_layout(C, D, self.max_depth, offs)
+            self._state = z(n)
+            self._lib = lib
+            view = lambda o, *shape: self._state[o:o + math.prod(shape)].view(*shape)  # noqa: E731
+            self._t = {k: view(offs[i], C) for i, k in enumerate(self._SCALARS)}
+            self._t.update({k: view(offs[len(self._SCALARS) + i], C, D) for i, k in enumerate(self._VECTORS)})
+            self._t["ck_p"] = view(offs[29], self.max_depth + 1, C, D)
+            self._t["ck_s"] = view(offs[30], self.max_depth + 1, C, D)
+        else:
+            self._t = dict(h0=z(C), ql=z(C, D), pl=z(C, D), gl=z(C, D), qr=z(C, D), pr=z(C, D), gr=z(C, D), q_prop=z(C, D), lp_prop=z(C),
+                           g_prop=z(C, D), p_sum=z(C, D), log_w=z(C), active=z(C, dtype=torch.bool), depth=z(C, dtype=torch.int64),
+                           diverged=z(C, dtype=torch.bool), acc_sum=z(C), n_leaves=z(C), dh_max=z(C),
+                           ck_p=z(self.max_depth + 1, C, D), ck_s=z(self.max_depth + 1, C, D))
 
     @staticmethod
     def _turning(im, p_left, p_right, p_sum):
@@ -368,7 +392,33 @@ class BatchedNUTS(BatchedHMC):
         for k in ("depth", "acc_sum", "n_leaves", "dh_max"):
             T[k].zero_()
 
+    def _doubling_fused(self, j):
+        """one doubling through the library's NUTS kernels; the uniforms are drawn here, in the order the tensor code draws them"""
+        import ctypes as C_
+
+        from . import _lib
+
+        T, lib = self._t, self._lib
+        C, D = self.q.shape
+        dev, dt = self.q.device, self.q.dtype
+        ptr = lambda x: C_.c_void_p(x.data_ptr())  # noqa: E731
+        st, md, stream = ptr(self._state), self.max_depth, _lib.stream_ptr()
+        eps, im = self.eps.contiguous(), self.inv_mass.contiguous()
+        rand = lambda: torch.rand(C, dtype=dt, device=dev, generator=self.gen)  # noqa: E731
+        with torch.cuda.device(dev):
+            u = rand()
+            _lib.check(lib.xo_nuts_start(st, C, D, md, ptr(u), ptr(self.logp), stream), "nuts_start")
+            for n in range(2 ** j):
+                _lib.check(lib.xo_nuts_leaf_pre(st, C, D, md, ptr(eps), ptr(im), stream), "nuts_leaf_pre")
+                lp, g = self.f(T["q"])
+                lp, g, u = lp.contiguous(), g.contiguous(), rand()
+                _lib.check(lib.xo_nuts_leaf_post(st, C, D, md, ptr(eps), ptr(im), ptr(lp), ptr(g), ptr(u), n, stream), "nuts_leaf_post")
+            u = rand()
+            _lib.check(lib.xo_nuts_merge(st, C, D, md, ptr(im), ptr(u), stream), "nuts_merge")
+
     def _doubling(self, j):
+        if self._fused_tree:
+            return self._doubling_fused(j)
         T, im = self._t, self.inv_mass
         C, D = self.q.shape
         dev, dt = self.q.device, self.q.dtype
@@ -450,8 +500,8 @@ class BatchedNUTS(BatchedHMC):
         self.grad.copy_(T["g_prop"])
         self.accept_prob.copy_(T["acc_sum"] / torch.clamp(T["n_leaves"], min=1.0))
         self.energy_error.copy_(T["dh_max"])  # largest energy error met along the trajectory
-        self.depth.copy_(T["depth"])
-        self.diverging.copy_(T["diverged"])
+        self.depth.copy_(T["depth"])          # (the fused state keeps counts and flags as doubles: copy_ converts)
+        self.diverging.copy_(T["diverged"] != 0)
 
     def _run(self, key, fn, *args):
         """run one piece: eagerly, or as its CUDA graph (first call: a real run on a side stream, then the capture)"""

@@ -302,6 +302,25 @@ int xo_read_status(const void *workspace, unsigned long long *bad_lanes, unsigne
 int xo_diag_dfma_peak(int reps, double *dfma_per_s, double *best_ms, void *stream);
 long long xo_diag_launch_count(void);
 
+/* ---- the tree bookkeeping of a lock-step No-U-Turn sampler (csrc/xo_nuts.cu; SURVEY.md 8f #4: what PyMC's NUTS,
+ * /root/reference/docs/tutorials/data-and-models.md:505-509, does per chain and process) -------------------------------
+ * Multinomial NUTS with the generalised U-turn criterion over C chains in step; D coordinates per chain; any logp+gradient
+ * callback in between (the fused transit posterior above is one).  `state` is one block of xo_nuts_state_layout() doubles
+ * (flags 0.0 / 1.0): offsets[0..13] the per-chain scalars h0, log_w, lp_prop, active, depth, diverged, acc_sum, n_leaves,
+ * dh_max, sgn, sub_ok, s_logw, s_lp, go_right ([C] each); offsets[14..28] the per-coordinate arrays ql, pl, gl, qr, pr,
+ * gr, q_prop, g_prop, p_sum, q, p, g, s_q, s_g, s_psum ([C][D] each); offsets[29], [30] the U-turn checkpoints ck_p, ck_s
+ * ([max_depth + 1][C][D] each).  One doubling j: xo_nuts_start (u_dir[C] uniform: direction; the new half starts from that
+ * edge), then for leaf = 0 .. 2^j - 1: xo_nuts_leaf_pre (half kick, drift: state.q is where logp is wanted),
+ * <caller evaluates logp[C], grad[C][D] at state.q>, xo_nuts_leaf_post (u_take[C] uniform); then xo_nuts_merge
+ * (u_merge[C] uniform) -- state.active then says which chains keep growing.  The uniforms come from the caller, so the
+ * kernels are deterministic and can be checked state for state against the tensor implementation. */
+size_t xo_nuts_state_layout(int64_t C, int D, int max_depth, int64_t *offsets /*[31] or NULL*/);
+int xo_nuts_start(double *state, int64_t C, int D, int max_depth, const double *u_dir, const double *logp_cur, void *stream);
+int xo_nuts_leaf_pre(double *state, int64_t C, int D, int max_depth, const double *eps, const double *inv_mass, void *stream);
+int xo_nuts_leaf_post(double *state, int64_t C, int D, int max_depth, const double *eps, const double *inv_mass, const double *logp,
+                      const double *grad, const double *u_take, int leaf, void *stream);
+int xo_nuts_merge(double *state, int64_t C, int D, int max_depth, const double *inv_mass, const double *u_merge, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -340,6 +340,54 @@ def test_batched_nuts_on_device_gaussian_target():
     assert int(nuts.depth.max()) >= 1 and nuts.n_leapfrog > 0
 
 
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_nuts_tree_kernels_equal_the_tensor_implementation(use_graph):
+    """the library's NUTS kernels (xo_nuts_start / leaf_pre / leaf_post / merge) are deterministic functions of the same
+    inputs as the tensor code of BatchedNUTS._doubling, uniforms included: from the same seed the two samplers visit the
+    same states -- positions, log-densities, tree depths, divergence flags, acceptance statistics -- transition after
+    transition, eagerly and as CUDA graphs (a banana-shaped target so that U-turns happen at every depth)"""
+    from exoplanet_b200.sampling import BatchedNUTS
+
+    D, C = 5, 96
+    sd = torch.tensor([0.3, 1.0, 2.0, 0.05, 4.0], dtype=torch.float64, device=DEV)
+
+    def target(q):
+        x = q.clone()
+        x[:, 1] = q[:, 1] - 0.3 * q[:, 0] ** 2  # curved: the step size that suits one region turns early in another
+        z = x / sd
+        g = -z / sd
+        g0 = g[:, 0] + g[:, 1] * (-0.6 * q[:, 0])
+        gq = g.clone()
+        gq[:, 0] = g0
+        lp = -0.5 * (z * z).sum(-1)
+        # a wall far out: divergences (energy error > 1000) must be handled identically too
+        far = q[:, 2].abs() > 9.0
+        return torch.where(far, torch.full_like(lp, -1e6), lp), gq
+
+    gen = torch.Generator(device=DEV).manual_seed(11)
+    q0 = sd * torch.randn((C, D), dtype=torch.float64, device=DEV, generator=gen)
+    depths, diverged = set(), 0
+    for step, n_it in ((0.07, 10), (0.12, 6)):  # well-tuned: depths 1..6; too large: divergences on the narrow coordinate
+        a = BatchedNUTS(target, q0, step_size=step, max_depth=6, seed=21, use_graph=use_graph, fused_tree=True)
+        b_ = BatchedNUTS(target, q0, step_size=step, max_depth=6, seed=21, use_graph=use_graph, fused_tree=False)
+        for it in range(n_it):
+            a.transition()
+            b_.transition()
+            if it == 4:  # the adaptation path too
+                a._adapt_step()
+                b_._adapt_step()
+            assert torch.equal(a.depth, b_.depth), (step, it, a.depth, b_.depth)
+            assert torch.equal(a.diverging, b_.diverging)
+            assert torch.allclose(a.q, b_.q, rtol=1e-10, atol=1e-12), (step, it, (a.q - b_.q).abs().max())
+            assert torch.allclose(a.logp, b_.logp, rtol=1e-10, atol=1e-10)
+            assert torch.allclose(a.accept_prob, b_.accept_prob, rtol=1e-9, atol=1e-12)
+            assert torch.allclose(a.energy_error, b_.energy_error, rtol=1e-8, atol=1e-10)
+            assert a.n_leapfrog == b_.n_leapfrog
+            depths |= set(a.depth.tolist())
+            diverged += int(a.diverging.sum())
+    assert len(depths) >= 5 and diverged > 0, (depths, diverged)  # trees of every depth were built, and some diverged
+
+
 def test_batched_nuts_on_transit_posterior_agrees_with_hmc():
     """NUTS and fixed-length HMC target the same fused transit posterior: their pooled posterior means agree
     within the Monte-Carlo error and their widths within 35 %"""

@@ -7,7 +7,7 @@ NAME=$1; SRC=$2; shift 2
 cd "$(dirname "$0")/../exoplanet_b200/csrc"
 python build.py > /dev/null
 OBJS=""
-for f in xo_ops xo_transit xo_model xo_celerite xo_host xo_diag xo_joint xo_sampler; do
+for f in xo_ops xo_transit xo_model xo_celerite xo_host xo_diag xo_joint xo_sampler xo_nuts; do
   if [ "$f.cu" = "$SRC" ]; then
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr -ccbin /usr/bin/g++ "$@" -c $f.cu -o /tmp/${f}_$NAME.o
     OBJS="$OBJS /tmp/${f}_$NAME.o"
