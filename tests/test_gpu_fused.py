@@ -575,3 +575,42 @@ def test_parameter_level_model_options_agree(use_moments, use_in_transit):
     assert torch.allclose(got[0], ref[0], rtol=1e-11, atol=0)
     for a, b in zip(got[1:], ref[1:]):
         assert torch.allclose(a, b, rtol=1e-8, atol=1e-9 * b.abs().max().item())
+
+
+def test_parameter_level_model_random_shapes():
+    """the whole parameter-level evaluation (prologue -> partition -> indexed / stepping sweep -> epilogue) on two dozen random
+    problem shapes -- chains, planets, cadences, exposure time, gaps in the sampling, a short-period planet among long ones --
+    against the oracle: logp, d/d mean and the element gradients pushed through the oracle's own elements"""
+    rng = np.random.default_rng(2024)
+    for trial in range(24):
+        C = int(rng.integers(1, 48))
+        P = int(rng.integers(1, 5))
+        N = int(rng.integers(300, 24000))
+        texp = None if trial % 3 else float(rng.uniform(0.005, 0.05))
+        t = synthetic.cadence_times(N)
+        if trial % 4 == 1:  # gaps
+            keep = np.ones(N, bool)
+            for a in rng.integers(0, max(N - 400, 1), 3):
+                keep[a:a + int(rng.integers(20, 400))] = False
+            t = t[keep]
+            N = t.size
+        p = synthetic.transit_params(C, P, seed=1000 + trial)
+        if trial % 5 == 2:
+            p["period"][0, 0] = 0.7  # many epochs of one planet
+        y = synthetic.noise(N, seed=trial)
+        data = fused.TransitData(t, y, np.full(N, 5e-4), device=DEV)
+        par = fused.pack_params(dev(p["period"]), dev(p["t0"]), dev(p["ecc"]), dev(p["omega"]), dev(p["b"]), dev(p["ror"]),
+                                dev(p["m_planet"]), dev(p["K"]))
+        one = torch.ones(C, dtype=torch.float64, device=DEV)
+        logp, gpar, gstar, gmean = fused.TransitModel(data, texp=texp).logp_grad(par, fused.pack_star(one, one, dev(p["u1"]), dev(p["u2"])),
+                                                                               dev(p["mean"]))
+        el_o = O.elements_from_params(p["period"], p["t0"], p["ecc"], p["omega"], p["b"], p["ror"], m_planet=p["m_planet"], texp=texp)
+        lo, geo, gco, gmo = O.transit_logp_grad(t, y, np.full(N, 1 / 5e-4 ** 2), el_o, O.get_cl(p["u1"], p["u2"]), p["mean"], *O.stencil(texp),
+                                                lognorm=data.lognorm)
+        tag = (trial, C, P, N, texp)
+        assert np.max(np.abs(logp.cpu().numpy() - lo) / np.abs(lo)) < 1e-10, tag
+        assert np.max(np.abs(gmean.cpu().numpy() - gmo) / (np.abs(gmo).max() + 1e-300)) < 1e-9, tag
+        # d logp / d (r/R*) = the element gradient's ror slot (nothing else depends on it but the window): index 5 of par
+        g_ror = geo[..., 9]
+        assert np.max(np.abs(gpar.cpu().numpy()[..., 5] - g_ror) / (np.abs(g_ror).max() + 1e-300)) < 1e-7, tag
+        assert bool(torch.isfinite(gpar).all()) and bool(torch.isfinite(gstar).all()), tag
