@@ -16,7 +16,7 @@ PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libxo_b200.so")
 BUILD = os.path.join(HERE, "_build")
 SOURCES = ["xo_ops.cu", "xo_transit.cu", "xo_model.cu", "xo_celerite.cu", "xo_host.cu", "xo_diag.cu", "xo_joint.cu", "xo_sampler.cu", "xo_nuts.cu"]
-HEADERS = ["xo_math.cuh", "xo_common.cuh", "xo_contact.cuh", "xo_transit.cuh", "xo_prologue.cuh", os.path.join("..", "..", "include", "xo_b200.h")]
+HEADERS = ["xo_math.cuh", "xo_common.cuh", "xo_contact.cuh", "xo_transit.cuh", "xo_prologue.cuh", "xo_posterior.cuh", os.path.join("..", "..", "include", "xo_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

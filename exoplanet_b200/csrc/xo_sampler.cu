@@ -17,77 +17,16 @@
 #include <curand_kernel.h>
 
 #include "xo_common.cuh"
+#include "xo_posterior.cuh"
 #include "xo_transit.cuh"
 
 namespace {
 
-constexpr int kNpl = 6;
+using xo::chain_rule;
+using xo::kNpl;
+using xo::unpack_planet;
+using xo::unpack_star;
 constexpr unsigned kFullS = 0xffffffffu;
-
-// q[c] -> par[c][P][8], star[c][4], mean[c]; one thread per (chain, planet) plus one per chain
-__device__ __forceinline__ void unpack_planet(const double *q, double *par) {
-  const double h = q[2], k = q[3];
-  par[0] = exp(q[0]);
-  par[1] = q[1];
-  par[2] = h * h + k * k;
-  par[3] = atan2(k, h);
-  par[4] = q[4];
-  par[5] = exp(q[5]);
-  par[6] = 0.0;
-  par[7] = 0.0;
-}
-__device__ __forceinline__ void unpack_star(const double *qs, double *star, double *mean) {
-  const double q1 = 1.0 / (1.0 + exp(-qs[0])), q2 = 1.0 / (1.0 + exp(-qs[1]));
-  const double sq = sqrt(q1);
-  star[0] = 1.0;
-  star[1] = 1.0;
-  star[2] = 2.0 * sq * q2;
-  star[3] = sq * (1.0 - 2.0 * q2);
-  *mean = qs[2];
-}
-
-// chain rule of the change of variables + the Normal priors; lane-parallel over the D coordinates of one chain.
-// Returns this lane's share of the log prior (to be summed over the warp).
-__device__ __forceinline__ double chain_rule(const double *q, const double *gpar, const double *gstar, double gmean, int P, int D,
-                                             const double *mu, const double *sigma, int lane, double *grad) {
-  double lprior = 0.0;
-  for (int j = lane; j < D; j += 32) {
-    double g;
-    if (j < kNpl * P) {
-      const int p = j / kNpl, i = j % kNpl;
-      const double *qp = q + p * kNpl, *gp = gpar + p * XO_NPAR;
-      const double h = qp[2], k = qp[3], e = h * h + k * k;
-      switch (i) {
-        case 0: g = gp[0] * exp(qp[0]); break;
-        case 1: g = gp[1]; break;
-        case 2: g = gp[2] * 2.0 * h + (e > 0.0 ? gp[3] * (-k / e) : 0.0); break;
-        case 3: g = gp[2] * 2.0 * k + (e > 0.0 ? gp[3] * (h / e) : 0.0); break;
-        case 4: g = gp[4]; break;
-        default: g = gp[5] * exp(qp[5]); break;
-      }
-    } else {
-      const double *qs = q + kNpl * P;
-      const int i = j - kNpl * P;
-      if (i == 2) {
-        g = gmean;
-      } else {
-        const double q1 = 1.0 / (1.0 + exp(-qs[0])), q2 = 1.0 / (1.0 + exp(-qs[1]));
-        const double sq = sqrt(q1);
-        if (i == 0) {
-          const double gq1 = gstar[2] * q2 / sq + gstar[3] * (1.0 - 2.0 * q2) / (2.0 * sq);
-          g = gq1 * q1 * (1.0 - q1);
-        } else {
-          const double gq2 = 2.0 * sq * (gstar[2] - gstar[3]);
-          g = gq2 * q2 * (1.0 - q2);
-        }
-      }
-    }
-    const double z = (q[j] - mu[j]) / sigma[j];
-    lprior -= 0.5 * z * z;
-    grad[j] = g - z / sigma[j];
-  }
-  return lprior;
-}
 
 __device__ __forceinline__ double warp_sum_s(double v) {
 #pragma unroll
@@ -267,6 +206,24 @@ int xo_transit_posterior_logp_grad(const double *t, const double *y, const doubl
   auto at = [&](size_t off) { return reinterpret_cast<double *>(ws + off); };
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int D = kNpl * (int)P + 3;
+  if (xo::model_split_supported()) {
+    // the model's own prologue and epilogue kernels apply the change of variables, its chain rule and the priors in place:
+    // 3 launches per posterior evaluation instead of 5
+    xo::PosteriorIO io;
+    io.q = q;
+    io.D = D;
+    io.mu = prior_mu;
+    io.sigma = prior_sigma;
+    io.pstride = prior_chain_stride;
+    io.par = at(L.off_par);
+    io.star = at(L.off_star);
+    io.mean = at(L.off_mean);
+    io.logp = logp;
+    io.grad = grad;
+    return xo::model_logp_grad_phases(t, y, ivar, N, at(L.off_par), at(L.off_star), at(L.off_mean), C, P, dtk, wk, K, texp, use_in_transit,
+                                      lognorm, moments, at(L.off_ll), at(L.off_gpar), at(L.off_gstar), at(L.off_gmean), ws + L.off_model,
+                                      L.model_bytes, stream, 3, &io);
+  }
   xo::launch(posterior_unpack_kernel, (unsigned)((C * P + C + 127) / 128), 128, 0, st, q, C, (int)P, D, at(L.off_par), at(L.off_star),
              at(L.off_mean));
   int rc = xo_transit_model_logp_grad(t, y, ivar, N, at(L.off_par), at(L.off_star), at(L.off_mean), C, P, dtk, wk, K, texp,

@@ -86,7 +86,7 @@ int model_logp_grad_phases(const double *t, const double *y, const double *ivar,
                            const double *star, const double *mean, int64_t C, int64_t P, const double *dtk, const double *wk,
                            int K, double texp, int use_in_transit, double lognorm, const double *moments, double *logp,
                            double *gpar, double *gstar, double *gmean, void *workspace, size_t workspace_bytes, void *stream,
-                           int phases);
+                           int phases, const struct PosteriorIO *posterior = nullptr);
 
 // resid[C][N] = y[n] - mean[c] - sum_p lc[c][n][p]   (what a noise model of the residuals consumes)
 void launch_transit_resid(const double *t, const double *y, int64_t N, const double *elem, const double *cl, const double *mean,
