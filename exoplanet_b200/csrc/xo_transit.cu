@@ -1409,6 +1409,16 @@ size_t xo_transit_logp_grad_workspace(int64_t N, int64_t C, int64_t P) {
   return sizeof(double) * (size_t)C * (size_t)sp.slots * (size_t)(kNBase + P * XO_NGRAD);
 }
 
+// cadences per thread of the moments pass (XO_MOMENTS_PER_THREAD): fewer = more CTAs in flight for a 2.4 MB problem
+static int64_t moments_per_thread() {
+  static const int v = [] {
+    const char *e = getenv("XO_MOMENTS_PER_THREAD");
+    const int x = e && *e ? atoi(e) : 4;
+    return x < 1 ? 1 : x;
+  }();
+  return v;
+}
+
 int xo_transit_data_moments(const double *t, const double *y, const double *ivar, int64_t N, double *moments,
                             void *stream) {
   XO_NVTX_SCOPE("xo_transit_data_moments");
@@ -1416,7 +1426,7 @@ int xo_transit_data_moments(const double *t, const double *y, const double *ivar
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaMemsetAsync(moments + 7, 0, sizeof(double), st);  // the arrival ticket
   if (e != cudaSuccess) return -(int)e;
-  const int64_t want = (N + 4 * kMomThreads - 1) / (4 * kMomThreads);
+  const int64_t want = (N + moments_per_thread() * kMomThreads - 1) / (moments_per_thread() * kMomThreads);
   const int ctas = (int)(want < 1 ? 1 : want > kMomMaxCtas ? kMomMaxCtas : want);
   xo::launch(transit_moments_kernel, ctas, kMomThreads, 0, st, t, y, ivar, N, moments, 0);
   return xo::launch_status();
@@ -1432,7 +1442,7 @@ int xo_transit_data_moments_index(const double *t, const double *y, const double
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaMemsetAsync(moments + 7, 0, sizeof(double), st);  // the arrival ticket
   if (e != cudaSuccess) return -(int)e;
-  const int64_t want = (N + 4 * kMomThreads - 1) / (4 * kMomThreads);
+  const int64_t want = (N + moments_per_thread() * kMomThreads - 1) / (moments_per_thread() * kMomThreads);
   const int ctas = (int)(want < 1 ? 1 : want > kMomMaxCtas ? kMomMaxCtas : want);
   xo::launch(transit_moments_kernel, ctas, kMomThreads, 0, st, t, y, ivar, N, moments, index_bins(N));
   return xo::launch_status();
