@@ -166,3 +166,38 @@ def test_batched_nuts_gaussian_targets_cpu():
     one = BatchedNUTS(corr_target, torch.zeros(1, 2, dtype=torch.float64), step_size=0.3, max_depth=1, seed=1)
     one.warmup(10, adapt_mass=False)
     assert one.sample(5)["q"].shape == (5, 1, 2) and int(one.depth.max()) <= 1
+
+
+def test_bench_reads_the_container_cpu_quota(monkeypatch):
+    """bench.py sizes the CPU arm's OpenMP team to the cgroup's CFS quota (the GPU boxes give a container 16 of 128 CPUs;
+    a 64-thread team inside that quota is what made round 1's CPU numbers irreproducible): both cgroup layouts, no limit"""
+    import builtins
+    import importlib.util
+    import io
+    import os
+
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    real_open = builtins.open
+
+    def fake(files):
+        def _open(path, *a, **k):
+            if str(path).startswith("/sys/fs/cgroup"):
+                if path in files:
+                    return io.StringIO(files[path])
+                raise OSError(path)
+            return real_open(path, *a, **k)
+        return _open
+
+    monkeypatch.setattr(builtins, "open", fake({"/sys/fs/cgroup/cpu.max": "1600000 100000\n"}))
+    assert bench._cpu_quota() == 16.0
+    monkeypatch.setattr(builtins, "open", fake({"/sys/fs/cgroup/cpu.max": "max 100000\n"}))
+    assert bench._cpu_quota() is None
+    monkeypatch.setattr(builtins, "open", fake({"/sys/fs/cgroup/cpu/cpu.cfs_quota_us": "-1\n", "/sys/fs/cgroup/cpu/cpu.cfs_period_us": "100000\n"}))
+    assert bench._cpu_quota() is None
+    monkeypatch.setattr(builtins, "open", fake({"/sys/fs/cgroup/cpu/cpu.cfs_quota_us": "350000\n", "/sys/fs/cgroup/cpu/cpu.cfs_period_us": "100000\n"}))
+    assert bench._cpu_quota() == 3.5
+    monkeypatch.setattr(builtins, "open", fake({}))
+    assert bench._cpu_quota() is None
+    assert "cpu_quota" in bench._host_state()

@@ -207,3 +207,33 @@ def test_rv_grad_matches_finite_differences():
             em[p, j] -= h
             fd = (O.rv_logp_grad(t, y, ivar, ep[None], gamma)[0][0] - O.rv_logp_grad(t, y, ivar, em[None], gamma)[0][0]) / (2 * h)
             assert abs(fd - grv[0, p, k]) <= 1e-5 * abs(fd) + 1e-4, (p, j, fd, grv[0, p, k])
+
+
+def _series(N, C=3, P=2, seed=5):
+    from exoplanet_b200 import synthetic
+
+    p = synthetic.transit_params(C, P, seed=seed)
+    t = synthetic.cadence_times(N)
+    el = O.elements_from_params(p["period"], p["t0"], p["ecc"], p["omega"], p["b"], p["ror"])
+    cl = O.get_cl(p["u1"], p["u2"])
+    y = synthetic.noise(N)
+    return t, y, np.full(N, 4.0e6), el, cl, p["mean"]
+
+
+def test_logp_grad_thread_count_and_block_additivity():
+    t, y, iv, el, cl, mean = _series(20000)
+    dtk, wk = O.stencil(None)
+    threads = O.max_threads()
+    O.set_threads(1)
+    a = O.transit_logp_grad(t, y, iv, el, cl, mean, dtk, wk)
+    O.set_threads(threads)
+    b = O.transit_logp_grad(t, y, iv, el, cl, mean, dtk, wk)
+    for x, z in zip(a, b):
+        assert np.array_equal(x, z)
+    # additive over cadences: the two halves (each below the blocking threshold: plain cadence-order sums) add up to the whole
+    h = 8000
+    lo = O.transit_logp_grad(t[:h], y[:h], iv[:h], el, cl, mean, dtk, wk)
+    hi = O.transit_logp_grad(t[h:16000], y[h:16000], iv[h:16000], el, cl, mean, dtk, wk)
+    whole = O.transit_logp_grad(t[:16000], y[:16000], iv[:16000], el, cl, mean, dtk, wk)
+    for x, u, v in zip(whole, lo, hi):
+        assert np.allclose(x, u + v, rtol=1e-12, atol=1e-9 * np.abs(x).max())
