@@ -201,3 +201,46 @@ def test_bench_reads_the_container_cpu_quota(monkeypatch):
     monkeypatch.setattr(builtins, "open", fake({}))
     assert bench._cpu_quota() is None
     assert "cpu_quota" in bench._host_state()
+
+
+def test_partition_apportionment_algorithm():
+    """the rule the logp kernel uses to deal its CTAs out to the chains (xo_transit.cu weighted_partition: n_c = ceil(w_c r)
+    with the largest r from five bisection steps between the always-feasible (G - C) / W and G / W), restated in numpy:
+    never more CTAs than the grid has, at least one per chain, and a heaviest CTA within 25 % of the best possible
+    apportionment (greedy minimax) -- on the bench's own weight distribution and on adversarial ones"""
+    rng = np.random.default_rng(8)
+
+    def deal(w, G):
+        W, C = int(w.sum()), w.size
+        lo, hi = (G - C) / W * (1.0 - 2.0 ** -40), G / W
+        for _ in range(5):
+            r = 0.5 * (lo + hi)
+            if np.maximum(1, np.ceil(w * r)).sum() <= G:
+                lo = r
+            else:
+                hi = r
+        return np.maximum(1, np.ceil(w * lo)).astype(int)
+
+    def best(w, G):
+        n = np.ones(w.size)
+        for _ in range(G - w.size):
+            n[np.argmax(w / n)] += 1
+        return n
+
+    cases = []
+    p = synthetic.transit_params(128, 1, seed=synthetic.SEED, ecc=0.5)
+    el = O.elements_from_params(p["period"], p["t0"], p["ecc"], p["omega"], p["b"], p["ror"])[:, 0]
+    duty = np.clip((el[:, 12] - el[:, 11]) / el[:, 10], 0.0, 1.0)
+    cases.append((1 + np.floor(duty * 100000 / 32), 592))
+    cases.append((rng.integers(1, 4000, 300).astype(float), 1184))
+    cases.append((np.full(64, 7.0), 592))                                   # all equal
+    cases.append((np.r_[1e6, np.ones(99)], 592))                            # one chain has all the work
+    cases.append((rng.integers(1, 50, 512).astype(float), 1184))            # about two CTAs per chain
+    for w, G in cases:
+        n = deal(w, G)
+        assert n.min() >= 1 and n.sum() <= G, (n.sum(), G)
+        heavy, opt = (w / n).max(), (w / best(w, G)).max()
+        assert heavy <= 1.25 * opt + 1e-9, (heavy, opt, G, w.size)
+    # the bench's distribution: the heaviest CTA within 15 % of the average load (the round's 6-CTAs-per-chain split: 3x)
+    w, G = cases[0]
+    assert (w / deal(w, G)).max() <= 1.15 * w.sum() / G
