@@ -780,7 +780,7 @@ def arm_ours(args):
         hist.append(time.perf_counter() - s0)
         nw += 1
         el = time.perf_counter() - w0
-        if nw >= max(3, args.warmup) and el >= 0.15:
+        if nw >= max(3, args.warmup) and el >= 0.4:
             settled = len(hist) >= 40 and abs(np.median(hist[-20:]) / np.median(hist[-40:-20]) - 1.0) < 0.05
             if settled or el > 2.0:
                 break
@@ -799,12 +799,12 @@ def arm_ours(args):
                 "last_calls_us_median": round(float(np.median(hist[-20:])) * 1e6), "pcie_link_before": link_before,
                 "pcie_link_after_warmup": link_mid, "calls_waiting_for_the_link": extra}
     barrier()
-    # K synchronous calls, timed as a block; blocks are repeated for at least 0.5 s (and at least 5 of them) and the MEDIAN
+    # K synchronous calls, timed as a block; blocks are repeated for at least 1 s (and at least 5 of them) and the MEDIAN
     # block is reported: the host<->device path of a fresh process has slow plateaus of a few hundred milliseconds (the same
     # call takes 105 or 250 us; tools/e2e_repeat.sh, profiles/r02_e2e_repeat.txt), longer than 5 blocks of 20 calls
     e2e_blocks = []
     e2e_t0 = time.perf_counter()
-    while len(e2e_blocks) < 5 or (time.perf_counter() - e2e_t0 < 0.5 and len(e2e_blocks) < 1000):
+    while len(e2e_blocks) < 5 or (time.perf_counter() - e2e_t0 < 1.0 and len(e2e_blocks) < 2000):
         e2e_steps = []
         e0 = time.perf_counter()
         for _ in range(args.steps):
@@ -983,7 +983,7 @@ def arm_ours(args):
         "e2e": {"value": e2e, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "xo_transit_model_logp_grad_host: t,y,ivar (one pinned block, one DMA), params from pinned host memory every call; "
                        "logp+grads back to host",
-                "timing": "median of %d blocks of `steps` synchronous calls (>= 0.5 s of them)" % len(e2e_blocks),
+                "timing": "median of %d blocks of `steps` synchronous calls (>= 1 s of them)" % len(e2e_blocks),
                 "blocks_quartiles_evals_per_s": [float(C_loc * args.steps / np.percentile(e2e_blocks, q)) for q in (75, 50, 25)], "warmup": e2e_warm, "pcie_link_after": pcie_link(),
                 "blocks_evals_per_s": [float(C_loc * args.steps / b) for b in e2e_blocks[:5]]},
         "e2e_resident_data": {"value": total_evals / (res_ms * 1e-3), "unit": "evals/s",
